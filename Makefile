@@ -1,0 +1,38 @@
+# Build everything in-tree (artefacts are git-ignored but travel to the GPU box with gpurun).
+#   make            -> libvkv.so (CUDA, sm_100a) + libvkv_host.so (host generators) + oracle/liboracle.so
+#   make ref        -> oracle/_ref/*.so from the reference's own sources (only where /root/reference exists)
+NVCC      ?= /usr/local/cuda/bin/nvcc
+CXX       ?= g++
+PKG       := vk_gltf_viewer_b200
+CSRC      := $(PKG)/csrc
+HOSTSRC   := $(PKG)/host
+
+# -fmad=false: the parity contract is "every fp32 op individually rounded" (SURVEY §8c); -prec-div/-prec-sqrt are defaults.
+NVCCFLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -fmad=false \
+             -Xcompiler -fPIC,-Wall,-Wno-unused-function -Xptxas -v
+CXXFLAGS  := -O2 -std=c++17 -fPIC -Wall -Wextra -ffp-contract=off -fno-fast-math -pthread
+
+CU_SRCS   := $(wildcard $(CSRC)/*.cu)
+CU_HDRS   := $(wildcard $(CSRC)/*.cuh) $(wildcard include/*.h)
+HOST_SRCS := $(wildcard $(HOSTSRC)/*.cpp)
+HOST_HDRS := $(wildcard $(HOSTSRC)/*.hpp) $(wildcard include/*.h)
+
+all: $(PKG)/libvkv.so $(PKG)/libvkv_host.so oracle/liboracle.so
+
+$(PKG)/libvkv.so: $(CU_SRCS) $(CU_HDRS)
+	$(NVCC) $(NVCCFLAGS) -shared -o $@ $(CU_SRCS) -Iinclude 2> $(PKG)/ptxas.log || (cat $(PKG)/ptxas.log; exit 1)
+	@grep -E "registers|spill" $(PKG)/ptxas.log | sort | uniq -c | sort -rn | head -5 || true
+
+$(PKG)/libvkv_host.so: $(HOST_SRCS) $(HOST_HDRS)
+	$(CXX) $(CXXFLAGS) -shared -o $@ $(HOST_SRCS) -Iinclude
+
+oracle/liboracle.so: oracle/oracle.cpp oracle/oracle.h include/vkv_abi.h
+	$(CXX) $(CXXFLAGS) -O3 -mavx2 -shared -o $@ oracle/oracle.cpp
+
+ref:
+	@if [ -d /root/reference ]; then sh oracle/build_ref.sh; else echo "no /root/reference here: using prebuilt oracle/_ref if present"; fi
+
+clean:
+	rm -f $(PKG)/libvkv.so $(PKG)/libvkv_host.so oracle/liboracle.so $(PKG)/ptxas.log
+
+.PHONY: all ref clean

@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""bench.py — frames/s (and Gtris/s) of the geometry hot path: two-pass meshlet cull + visbuffer raster + HiZ build.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 3]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one frame of a camera sweep over the synthetic scene of BASELINE.json config 3 (the configuration the
+north-star target is quoted on: 10x10x10 lattice of a 100,352-triangle patch = 100.35M triangles, 3840x2160, two-pass HiZ).
+Multi-GPU = independent views sharded per GPU: the scene is replicated, every rank renders its own K
+views, no data-path collective; value = (N*K frames) / max-over-ranks device time  ("scaling": "weak").
+
+--impl reference times the CPU implementation of the same path on the host cores (the oracle port; the reference's own
+shaders cannot run here: no Vulkan ICD / glslang — DESIGN.md §Oracle), rank 0 only.
+
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+CONFIGS = {
+    # id: (label, builder kwargs, resolution)
+    1: ("cfg1: icosphere 64,980 tris, 640x480", dict(kind="icosphere", frequency=57), (640, 480)),
+    2: ("cfg2: atrium 262,144 tris int16-quantised, 1920x1080", dict(kind="atrium", detail=128), (1920, 1080)),
+    3: ("cfg3: 10x10x10 lattice of a 224x224-quad patch (100.35M tris), 3840x2160, two-pass HiZ", dict(kind="lattice", n=(10, 10, 10), quads=224), (3840, 2160)),
+    4: ("cfg4: city 50x40 unique buildings x ~10k tris (~20M tris), 1920x1080, 64-view sweep", dict(kind="city", n=(50, 40), tris=10000), (1920, 1080)),
+    5: ("cfg5: 22x22x21 lattice (1.02B tris), 7680x4320", dict(kind="lattice", n=(22, 22, 21), quads=224), (7680, 4320)),
+}
+NVIEWS = 64
+
+
+def build_scene(spec):
+    from vk_gltf_viewer_b200.scene import Scene
+    k = spec["kind"]
+    if k == "icosphere":
+        return Scene.icosphere(spec["frequency"])
+    if k == "atrium":
+        return Scene.atrium(spec["detail"])
+    if k == "lattice":
+        return Scene.lattice(*spec["n"], spec["quads"], 0x5EED0003)
+    if k == "city":
+        return Scene.city(*spec["n"], spec["tris"], 0x5EED0004)
+    raise ValueError(k)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.idx)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_frames(scene, W, H, views, nframes, threads=0):
+    """the oracle (CPU port of the reference path) timed on the host cores: two-pass frames of the same sweep"""
+    from tests import oracle_lib as O
+    from vk_gltf_viewer_b200.scene import Camera
+    cam = Camera(W, H)
+    cam.look_at(*views[0])
+    pc = scene.host_push_constants(cam)
+    tg = O.Targets(W, H)
+    O.frame(pc, tg, two_pass=True, threads=threads)  # warm-up: fills the pyramid the first timed frame culls against
+    times = []
+    for k in range(nframes):
+        cam.look_at(*views[(k + 1) % len(views)])
+        t0 = time.perf_counter()
+        O.frame(pc, tg, two_pass=True, threads=threads)
+        times.append(time.perf_counter() - t0)
+    return times
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--one-pass", action="store_true", help="reference one-pass mode instead of the two-pass extension")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    label, spec, (W, H) = CONFIGS[args.config]
+    ncores = os.cpu_count() or 1
+
+    # ------------------------------------------------------------------ reference arm (CPU, rank 0 only)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        scene = build_scene(spec)
+        cnt = scene.counts()
+        views = [scene.default_view(i, NVIEWS) for i in range(NVIEWS)]
+        steps = max(1, args.steps)
+        for _ in range(max(0, args.warmup - 1)):
+            pass  # cpu_frames always runs one warm-up frame (it also seeds the pyramid); extra warm-ups add nothing on a CPU
+        times = cpu_frames(scene, W, H, views, steps)
+        total = sum(times)
+        fps = steps / total
+        line = {
+            "impl": "reference", "metric": "frames/s (two-pass cull + HiZ + visbuffer)", "value": fps, "unit": "frames/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": max(1, args.warmup), "ms_per_step": 1e3 * total / steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32+u64", "data": "synthetic",
+            "gtris_per_s": cnt.triangles_instanced * fps / 1e9,
+            "config": {"workload": label, "resolution": [W, H], "meshlet_draws": cnt.draws, "triangles": cnt.triangles_instanced, "passes": 2},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": ncores, "kind": "port",
+                             "sample": f"{steps} full two-pass frames of the same camera sweep (CPU oracle, all host threads)"},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ our arm (CUDA)
+    from vk_gltf_viewer_b200 import api
+    from vk_gltf_viewer_b200.scene import Camera
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    scene = build_scene(spec)
+    cnt = scene.counts()
+    views = [scene.default_view(i, NVIEWS) for i in range(NVIEWS)]
+    # view sharding: rank r renders views r, r+world, ...
+    my_views = [views[(rank + i * world) % NVIEWS] for i in range(args.warmup + args.steps + 1)]
+
+    r = api.Renderer(W, H, device=local_rank)
+    cam = Camera(W, H)
+    cam.look_at(*my_views[0])
+    pc = r.upload_scene(scene, cam)
+    flags = api.FRAME_ONE_PASS if args.one_pass else api.FRAME_TWO_PASS
+    # all cameras of the sweep resident in HBM: the device-timed loop switches the camera ADDRESS per frame
+    cam_addrs = []
+    for v in my_views[1:]:
+        cam.look_at(*v)
+        cam_addrs.append(r.upload(np.frombuffer(cam.raw(), np.uint8)))
+
+    def barrier():
+        r.sync()
+        if dist is not None:
+            dist.barrier()
+            import torch
+            torch.cuda.synchronize()
+
+    # warm-up (>= 3): also seeds the pyramid
+    r.frame(pc, flags)
+    for k in range(max(3, args.warmup)):
+        pc.cameraBuffer = cam_addrs[k % len(cam_addrs)]
+        r.frame(pc, flags)
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+
+    # ---- device-timed: K frames, each bracketed by CUDA events on the launching stream; L2 flushed between frames
+    barrier()
+    per = []
+    stage = {k: 0.0 for k in ("clear_ms", "cull_a_ms", "raster_a_ms", "hiz_a_ms", "cull_b_ms", "raster_b_ms", "hiz_b_ms")}
+    vis_a = vis_b = occ_a = 0
+    launches = 0
+    for k in range(args.steps):
+        pc.cameraBuffer = cam_addrs[(args.warmup + k) % len(cam_addrs)]
+        r.flush_l2(256 << 20)
+        st = r.frame(pc, flags | api.FRAME_TIMED)
+        per.append(st.total_ms)
+        for s in stage:
+            stage[s] += getattr(st, s)
+        vis_a += st.visible_a; vis_b += st.visible_b; occ_a += st.occluded_a
+        launches += st.kernel_launches
+    barrier()
+    dev_ms = sum(per)
+
+    # ---- end to end through the C ABI with HOST buffers: per step H2D camera + transforms (the reference re-uploads
+    # both every frame: camera.cpp:180-193, world.cpp:321-344) and D2H of the frame's counters (vkv_stats)
+    transforms = np.ascontiguousarray(scene.transforms())
+    pc.cameraBuffer = cam_addrs[0]
+    own_cam = r.upload(np.frombuffer(cam.raw(), np.uint8))
+    pc.cameraBuffer = own_cam
+    h2d = 352 + transforms.nbytes
+    d2h = 256
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        cam.look_at(*my_views[1 + (args.warmup + k) % (len(my_views) - 1)])
+        r._ck(r.L.vkv_update(r.h, own_cam, cam.raw(), 352))
+        r._ck(r.L.vkv_update(r.h, pc.transformBuffer, transforms.ctypes.data, transforms.nbytes))
+        r.frame(pc, flags)  # returns vkv_stats: blocking D2H of the counters
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    clocks = sampler.stop() if rank == 0 else None
+
+    if dist is not None:
+        import torch
+        t = torch.tensor([dev_ms, e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_s = t.tolist()
+        ln = torch.tensor([launches], device="cuda", dtype=torch.int64)
+        dist.all_reduce(ln)
+        launches = int(ln.item())
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm = peaks.get("hbm_gbs", 6650.0)
+        peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+        K = args.steps
+        fps = world * K / (dev_ms / 1e3)
+        # algorithmic bytes per launch (SURVEY §8d definitions)
+        N = cnt.draws
+        U = cnt.meshlets_unique * 36 + cnt.transforms * 64 + cnt.primitives * 64 + 352
+        pyr_bytes = 4 * r.pyramid_floats
+        avg = lambda x: x / K
+        bytes_cull_a = 12 * N + U + 4 * (avg(vis_a) + avg(occ_a))
+        bytes_cull_b = 4 * avg(occ_a) + 12 * avg(occ_a) + U + 4 * avg(vis_b)
+        bytes_hiz = 8 * W * H + pyr_bytes  # depth is read fused from the 64-bit visbuffer: 8 B/pixel, not 4
+        bytes_clear = 8 * W * H
+        per_meshlet = 48 + 28 * 64 + 3 * 95
+        bytes_raster_a = avg(vis_a) * per_meshlet
+        stages = {}
+        for name, b, ms in (("clear", bytes_clear, stage["clear_ms"]), ("cull_a", bytes_cull_a, stage["cull_a_ms"]), ("raster_a", bytes_raster_a, stage["raster_a_ms"]),
+                            ("hiz_a", bytes_hiz, stage["hiz_a_ms"]), ("cull_b", bytes_cull_b, stage["cull_b_ms"]), ("raster_b", avg(vis_b) * per_meshlet, stage["raster_b_ms"]),
+                            ("hiz_b", bytes_hiz, stage["hiz_b_ms"])):
+            m = ms / K
+            gbs = (b / 1e9) / (m / 1e3) if m > 0 else 0.0
+            stages[name] = {"ms": round(m, 5), "bytes": int(b), "GB/s": round(gbs, 1), "frac_hbm": round(gbs / hbm, 4)}
+        dom = max(stages, key=lambda s: stages[s]["ms"])
+        line = {
+            "metric": "frames/s (two-pass cull + HiZ + visbuffer)" if not args.one_pass else "frames/s (one-pass cull + visbuffer + HiZ)",
+            "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": max(3, args.warmup),
+            "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32+u64", "data": "synthetic",
+            "gtris_per_s": cnt.triangles_instanced * fps / 1e9,
+            "config": {"workload": label, "resolution": [W, H], "meshlet_draws": N, "triangles": cnt.triangles_instanced,
+                       "passes": 1 if args.one_pass else 2, "parallelism": f"views sharded over {world} GPU(s), scene replicated",
+                       "l2": "256 MB scratch written between timed frames (L2 flush); each frame timed by its own CUDA event pair",
+                       "visible_a_avg": avg(vis_a), "occluded_a_avg": avg(occ_a), "visible_b_avg": avg(vis_b)},
+            "e2e": {"value": world * K / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "note": "camera + all node transforms uploaded from host every frame, frame counters read back every frame (wall clock, no L2 flush)"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["GB/s"], "peak": hbm, "unit": "GB/s", "frac": stages[dom]["frac_hbm"],
+                         "traffic": None, "peak_source": peak_src,
+                         "note": "raster is L2-atomic / issue bound, its GB/s is input-side bytes only (SURVEY §8d); see stages for cull/HiZ/clear fractions"},
+            "stages": stages,
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline:
+            nfr = 2 if args.config in (3, 5) else 5
+            ct = cpu_frames(scene, W, H, views, nfr)
+            cfps = nfr / sum(ct)
+            line["cpu_baseline"] = {"value": cfps, "unit": "frames/s", "cores": ncores, "kind": "port",
+                                    "sample": f"{nfr} full two-pass frames of the same sweep after 1 warm-up frame (CPU oracle, all host threads)"}
+        print(json.dumps(line))
+    r.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

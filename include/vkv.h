@@ -1,0 +1,113 @@
+/* vkv.h — C ABI of the B200 geometry hot path (libvkv.so): meshlet cull -> visibility-buffer raster -> HiZ pyramid.
+ *
+ * The reference has no plugin/FFI interface; the seam this library replaces is the code region in
+ * Application::run() that records the mesh-shader draw and the hiz_reduce dispatch loop, plus the target creation
+ * behind it (paths relative to the upstream tree):
+ *
+ *   vkv_create / vkv_resize   initVisbufferPass (application.cpp:181-270) + initHiZReductionPass (:472-529),
+ *                             updateRenderResolution (:578-602)
+ *   vkv_upload / vkv_update   createMeshBuffers + staging copies (assets.cpp:233-286,385-424), World::addAsset
+ *                             (world.cpp:89-178), rebuildDrawBuffer / updateTransformBuffer (world.cpp:267-290,321-344),
+ *                             Camera mapped write (camera.cpp:109,180-193)
+ *   vkv_frame                 "Visbuffer pass" (application.cpp:763-867: clears :782,:807, push constants :849-859,
+ *                             vkCmdDrawMeshTasksEXT :861) + "HiZ reduction" (:951-1003)
+ *   vkv_cull                  shaders/visbuffer/visbuffer.task.glsl:25-76 (+ culling.h.glsl:8-56)
+ *   vkv_raster                shaders/visbuffer/visbuffer.mesh.glsl:30-104 + fixed-function raster/depth state
+ *                             (application.cpp:326-340) + visbuffer.frag.glsl:36
+ *   vkv_hiz                   shaders/hiz_reduce.comp.glsl:21-31 + dispatch loop application.cpp:964-1000
+ *   vkv_read_*                what the resolve pass / next frame's task shader read (application.cpp:917-949)
+ *
+ * Errors: the reference throws vulkan_error from vk::checkResult (include/vulkan/vk.hpp:27-61); here every call returns
+ * 0 or a negative vkv_status and never throws; vkv_last_error() gives the message.
+ * Threading: one context per GPU; frame/stage calls are single-threaded per context (the reference records frames on
+ * one thread); vkv_upload/vkv_free are internally locked (the reference uploads from worker threads).
+ * All `host` pointers are borrowed for the duration of the call. No torch / CUDA types appear in any signature.
+ */
+#ifndef VKV_H
+#define VKV_H
+
+#include "vkv_abi.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vkv_ctx vkv_ctx;
+
+enum vkv_status {
+	VKV_OK = 0,
+	VKV_ERR_CUDA = -1,        /* a CUDA runtime call failed (message has the cudaError string) */
+	VKV_ERR_INVALID = -2,     /* bad argument */
+	VKV_ERR_NO_DEVICE = -3,   /* no CUDA device / driver: there is NO CPU fallback */
+	VKV_ERR_OOM = -4,
+	VKV_ERR_LIMIT = -5        /* meshletDrawCount > 2^25 (visbuffer.h.glsl:15-17) */
+};
+
+/* vkv_frame flags */
+enum {
+	VKV_FRAME_ONE_PASS = 0,        /* reference behaviour: cull against the PREVIOUS pyramid with prevOcclusionViewProjection */
+	VKV_FRAME_TWO_PASS = 1 << 0,   /* extension: + re-test pass-A occlusion rejects against the fresh pyramid */
+	VKV_FRAME_NO_HIZ = 1 << 1,     /* camera->freezeCullingMatrix: skip the pyramid rebuild (application.cpp:951) */
+	VKV_FRAME_STATUS = 1 << 2,     /* also write the per-draw status bytes (parity / debugging) */
+	VKV_FRAME_TIMED = 1 << 3,      /* fill the *_ms fields of vkv_stats (CUDA events; syncs the stream at frame end) */
+	VKV_FRAME_NO_CULL = 1 << 4     /* rasterise every MeshletDraw (debug; what the task shader does with culling disabled) */
+};
+
+/* per-draw status byte (VKV_FRAME_STATUS) — same values as the oracle's */
+enum { VKV_ST_FRUSTUM_CULLED = 0, VKV_ST_OCCLUDED = 1, VKV_ST_VISIBLE = 2, VKV_ST_NOT_TESTED = 3 };
+
+typedef struct vkv_stats {
+	uint32_t draws;              /* meshletDrawCount */
+	uint32_t visible_a, occluded_a, visible_b, tested_b;
+	float clear_ms, cull_a_ms, raster_a_ms, hiz_a_ms, cull_b_ms, raster_b_ms, hiz_b_ms, total_ms; /* VKV_FRAME_TIMED */
+	uint32_t kernel_launches;    /* kernels of this library launched by the call */
+} vkv_stats;
+
+/* ---- lifetime ------------------------------------------------------------------------------------------- */
+int vkv_create(vkv_ctx** out, int cuda_device, uint32_t width, uint32_t height);
+int vkv_resize(vkv_ctx*, uint32_t width, uint32_t height);
+void vkv_destroy(vkv_ctx*);
+const char* vkv_last_error(vkv_ctx*);  /* ctx may be NULL: message of the last failed vkv_create on this thread */
+/* run on an existing CUDA stream (cudaStream_t passed as void*); NULL restores the context's own stream */
+int vkv_set_stream(vkv_ctx*, void* cuda_stream);
+int vkv_sync(vkv_ctx*);
+
+/* ---- device memory ---------------------------------------------------------------------------------------- */
+int vkv_upload(vkv_ctx*, const void* host, size_t bytes, uint64_t* dev_addr);       /* alloc + copy; address is 256-byte aligned */
+int vkv_update(vkv_ctx*, uint64_t dev_addr, const void* host, size_t bytes);        /* rewrite (camera, transforms) — async on the ctx stream */
+int vkv_free(vkv_ctx*, uint64_t dev_addr);
+
+/* ---- per frame -------------------------------------------------------------------------------------------- */
+int vkv_frame(vkv_ctx*, const vkv_VisbufferPushConstants* pc, uint32_t flags, vkv_stats* out);
+/* individually callable stages (per-stage timing / parity).  pass: 0 = A (reference), 1 = B (two-pass extension) */
+int vkv_clear(vkv_ctx*);
+int vkv_cull(vkv_ctx*, const vkv_VisbufferPushConstants* pc, int pass, uint32_t flags, uint32_t* n_visible);
+int vkv_raster(vkv_ctx*, const vkv_VisbufferPushConstants* pc, int pass);
+int vkv_hiz(vkv_ctx*);
+/* rasterise an explicit MeshletDraw index list (host pointer) — test hook */
+int vkv_raster_list(vkv_ctx*, const vkv_VisbufferPushConstants* pc, const uint32_t* draw_ids, uint32_t n);
+
+/* ---- results (blocking device->host copies on the ctx stream) ------------------------------------------- */
+int vkv_read_visbuffer64(vkv_ctx*, uint64_t* host);                /* W*H keys: (~floatBits(depth) << 32) | packVisBuffer */
+int vkv_read_ids(vkv_ctx*, uint32_t* host);                        /* W*H, == the reference's R32_UINT attachment */
+int vkv_read_depth(vkv_ctx*, float* host);                         /* W*H, == the reference's D32_SFLOAT attachment */
+int vkv_read_hiz_mip(vkv_ctx*, uint32_t mip, float* host, uint32_t* w, uint32_t* h);
+int vkv_read_pyramid(vkv_ctx*, float* host, uint32_t floats);      /* all mips, contiguous (layout: vkv_abi.h) */
+int vkv_write_pyramid(vkv_ctx*, const float* host, uint32_t floats);/* test hook: preset "previous frame" pyramid */
+int vkv_read_visible(vkv_ctx*, int pass, uint32_t* draw_ids, uint32_t cap, uint32_t* n);   /* survivors, unordered */
+int vkv_read_status(vkv_ctx*, int pass, uint8_t* status, uint32_t n);                      /* needs VKV_FRAME_STATUS */
+uint32_t vkv_pyramid_floats(vkv_ctx*);
+
+/* ---- measurement helpers -------------------------------------------------------------------------------------- */
+/* CUDA events on the ctx stream: record slot i (0..15); elapsed ms between two recorded slots (syncs on the later one) */
+int vkv_event_record(vkv_ctx*, int slot);
+int vkv_event_elapsed(vkv_ctx*, int from, int to, float* ms);
+/* write `bytes` of a scratch buffer (> L2) to evict the working set between timed iterations */
+int vkv_flush_l2(vkv_ctx*, size_t bytes);
+/* device pointer of the 64-bit visbuffer (for the multi-GPU min-merge; see vkv_merge_*) */
+uint64_t vkv_visbuffer64_ptr(vkv_ctx*);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

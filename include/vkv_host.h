@@ -1,0 +1,102 @@
+/* vkv_host.h — C ABI of the host-side input generators (libvkv_host.so).
+ *
+ * This is the C++ host mirror of what the reference does BEFORE the hot path: it produces, byte for byte in the
+ * reference's layouts (include/vkv_abi.h), the buffers the renderer uploads.  None of it runs on the GPU and none
+ * of it is timed in the frame metric.
+ *
+ *   reference                                                     here
+ *   assets.cpp:288-373  processPrimitive (meshlets + AABBs)       vkvh_scene_add_primitive
+ *   world.cpp:187-228   iterateNode  (M = scale(rotate(translate)))vkvh_scene_add_node_trs
+ *   world.cpp:230-293   rebuildDrawBuffer (MeshletDraw per node x meshlet) vkvh_scene_finalize
+ *   world.cpp:295-345   updateTransformBuffer                     vkvh_scene_finalize
+ *   world.cpp:89-178    addAsset primitive/material upload        vkvh_scene_upload
+ *   camera.cpp:38-48,70-84,170-193  updateCamera                  vkvh_camera_update
+ *   assets.cpp:486-492  default material at index 0               vkvh_scene_new
+ */
+#ifndef VKV_HOST_H
+#define VKV_HOST_H
+
+#include "vkv_abi.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vkvh_scene vkvh_scene;
+
+/* Optional replacement meshlet builder with meshoptimizer's signatures (meshoptimizer.h: meshopt_buildMeshletsBound,
+ * meshopt_buildMeshlets, meshopt_optimizeMeshlet).  Tests point these at the reference's own meshoptimizer build
+ * (oracle/_ref) to obtain byte-identical inputs; the product default is the built-in builder. */
+typedef struct vkvh_meshopt_Meshlet { unsigned vertex_offset, triangle_offset, vertex_count, triangle_count; } vkvh_meshopt_Meshlet;
+typedef size_t (*vkvh_build_bound_fn)(size_t index_count, size_t max_vertices, size_t max_triangles);
+typedef size_t (*vkvh_build_fn)(vkvh_meshopt_Meshlet* meshlets, unsigned* meshlet_vertices, unsigned char* meshlet_triangles,
+                                const unsigned* indices, size_t index_count, const float* vertex_positions, size_t vertex_count,
+                                size_t vertex_positions_stride, size_t max_vertices, size_t max_triangles, float cone_weight);
+typedef void (*vkvh_optimize_fn)(unsigned* meshlet_vertices, unsigned char* meshlet_triangles, size_t triangle_count, size_t vertex_count);
+void vkvh_set_meshlet_builder(vkvh_build_bound_fn bound, vkvh_build_fn build, vkvh_optimize_fn optimize);
+
+/* --- scene construction ------------------------------------------------------------------------------------ */
+vkvh_scene* vkvh_scene_new(void);                       /* material 0 = default (assets.cpp:486-492) */
+void vkvh_scene_free(vkvh_scene*);
+/* returns material index to pass to add_primitive (already +1-shifted like assets.cpp:292-294) */
+uint32_t vkvh_scene_add_material(vkvh_scene*, const float albedo[4], int double_sided);
+/* positions: float xyz, tightly packed.  Builds meshlets (64 v / 124 t / cone 0) and per-meshlet AABBs. Returns primitive index. */
+int32_t vkvh_scene_add_primitive(vkvh_scene*, const float* positions, uint32_t vertex_count,
+                                 const uint32_t* indices, uint32_t index_count, uint32_t material_index);
+/* KHR_mesh_quantization: int16 non-normalised positions expanded to f32 on the host exactly as
+ * fastgltf::iterateAccessor<vec3> does (tools.hpp:266-289; assets.cpp:310-314). normalized!=0 -> max(x/32767,-1). */
+int32_t vkvh_scene_add_primitive_i16(vkvh_scene*, const int16_t* positions, uint32_t vertex_count, int normalized,
+                                     const uint32_t* indices, uint32_t index_count, uint32_t material_index);
+/* adds a mesh node with TRS (translation xyz, rotation quaternion xyzw, scale xyz); parent = -1 for a root. Returns node index.
+ * primitive < 0 -> transform-only node. */
+int32_t vkvh_scene_add_node_trs(vkvh_scene*, int32_t parent, int32_t primitive, const float t[3], const float r[4], const float s[3]);
+/* walks the node tree depth-first and emits MeshletDraw[] + transforms[] (world.cpp:230-345) */
+int vkvh_scene_finalize(vkvh_scene*);
+
+/* --- procedural scenes for the BASELINE.json configs ---------------------------------------- */
+vkvh_scene* vkvh_scene_icosphere(uint32_t frequency);                                     /* cfg 1: 57 -> 64,980 tris */
+vkvh_scene* vkvh_scene_atrium(uint32_t detail);                                           /* cfg 2: 128 -> 262,144 tris, int16 positions */
+vkvh_scene* vkvh_scene_lattice(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t patch_quads, uint64_t seed); /* cfg 3/5 */
+vkvh_scene* vkvh_scene_city(uint32_t nbx, uint32_t nby, uint32_t target_tris_per_building, uint64_t seed);  /* cfg 4 */
+/* a sensible camera for view `view` of `nviews` (eye, centre) for the scene kind */
+void vkvh_scene_default_view(const vkvh_scene*, uint32_t view, uint32_t nviews, float eye[3], float center[3]);
+
+/* --- accessors ---------------------------------------------------------------------------------------------- */
+typedef struct vkvh_counts {
+	uint32_t primitives, materials, transforms, draws, nodes;
+	uint64_t triangles_unique, triangles_instanced, meshlets_unique, vertices_unique;
+} vkvh_counts;
+void vkvh_scene_counts(const vkvh_scene*, vkvh_counts*);
+const vkv_MeshletDraw* vkvh_scene_draws(const vkvh_scene*);
+const float* vkvh_scene_transforms(const vkvh_scene*);
+const vkv_Material* vkvh_scene_materials(const vkvh_scene*);
+/* per primitive arrays */
+typedef struct vkvh_primitive_view {
+	const uint32_t* vertex_indices; uint64_t vertex_indices_count;
+	const uint8_t* triangles; uint64_t triangles_bytes;
+	const vkv_Vertex* vertices; uint64_t vertex_count;
+	const vkv_Meshlet* meshlets; uint64_t meshlet_count;
+	vkv_Primitive header;     /* buffer addresses = HOST addresses of the arrays above */
+} vkvh_primitive_view;
+int vkvh_scene_primitive(const vkvh_scene*, uint32_t index, vkvh_primitive_view* out);
+
+/* Push constants over HOST memory (for the CPU oracle).  `camera` must outlive the use. */
+int vkvh_scene_host_pc(vkvh_scene*, const vkv_Camera* camera, vkv_VisbufferPushConstants* out);
+
+/* Upload everything through a callback with vkv_upload's shape and build the DEVICE push constants
+ * (mirrors createMeshBuffers/addAsset/rebuildDrawBuffer/updateTransformBuffer uploads).  The camera slot is
+ * uploaded once here; use vkv_update (include/vkv.h) to rewrite it per frame. */
+typedef int (*vkvh_upload_fn)(void* user, const void* host, size_t bytes, uint64_t* dev_addr);
+int vkvh_scene_upload(vkvh_scene*, vkvh_upload_fn upload, void* user, const vkv_Camera* camera, vkv_VisbufferPushConstants* out);
+
+/* --- camera (camera.cpp:170-193) ----------------------------------------------------------------------------- */
+/* first!=0: all four matrices are set to the new viewProjection (headless start).
+ * otherwise prev* <- current, then viewProjection/occlusionViewProjection/frustum are rewritten. */
+void vkvh_camera_update(vkv_Camera* cam, const float eye[3], const float center[3], const float up[3],
+                        uint32_t width, uint32_t height, int first);
+void vkvh_frustum_from_vp(const float vp[16], float frustum[6][4]);  /* camera.cpp:70-84 */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,33 @@
+#!/bin/sh
+# build_ref.sh — compile the parts of the REFERENCE that are plain C++ into oracle/_ref/ (git-ignored, travels with gpurun).
+# TEST INFRASTRUCTURE ONLY.  Sources are compiled where they lie under /root/reference; nothing is copied into the repo.
+# Outputs:
+#   oracle/_ref/libmeshopt_ref.so  meshoptimizer @ the reference's pinned submodule (meshopt_buildMeshlets & co)
+#   oracle/_ref/libref_shim.so     culling.h.glsl:1-30 (isAabbInFrustum, getWorldSpaceAabbExtent) + the shared layout headers
+#                                  compiled as C++ against the reference's glm; camera.cpp:38-48,70-84 (reverseDepth,
+#                                  generateCameraFrustum); glm perspective/lookAt; fastgltf::math translate/rotate/scale.
+# The GLSL task/mesh/fragment/compute shaders themselves cannot be built or run here (no glslang, no Vulkan ICD) — see DESIGN.md.
+set -e
+REF=${REF:-/root/reference}
+HERE=$(cd "$(dirname "$0")" && pwd)
+OUT="$HERE/_ref"
+TMP=$(mktemp -d /tmp/vkv_ref_build.XXXXXX)
+trap 'rm -rf "$TMP"' EXIT
+mkdir -p "$OUT" "$TMP/vulkan"
+CXX=${CXX:-g++}
+
+# 1. meshoptimizer, straight from the submodule
+$CXX -O2 -fPIC -shared -o "$OUT/libmeshopt_ref.so" "$REF"/submodules/meshoptimizer/src/*.cpp
+
+# 2. shim.  common.h.glsl pulls <vulkan/vk.hpp> (volk, fmt, tracy) only for VkDeviceAddress: give it a one-line stand-in.
+printf '#pragma once\n#include <cstdint>\ntypedef std::uint64_t VkDeviceAddress;\n' > "$TMP/vulkan/vk.hpp"
+# culling.h.glsl is dual GLSL/C++ up to line 30; the rest (array constructors) is GLSL-only. Compile the C++-valid head in place.
+# The only edit is mechanical: GLSL swizzle `plane.xyz` -> `vec3(plane)` (glm has no .xyz member without MS extensions).
+{ sed -n '1,30p' "$REF/shaders/culling.h.glsl" | sed 's/plane\.xyz/vec3(plane)/g'; printf 'GLSL_NAMESPACE_END\n#endif\n'; } > "$TMP/culling_head.h.glsl"
+# camera.cpp free functions reverseDepth (38-48) and generateCameraFrustum (70-84)
+{ printf '#define ZoneScoped\n#include <array>\n#include <glm/glm.hpp>\n'; sed -n '38,48p;70,84p' "$REF/src/vk_gltf_viewer/camera.cpp"; } > "$TMP/camera_fns.inc"
+
+$CXX -std=c++20 -O2 -fPIC -shared -ffp-contract=off \
+    -I"$TMP" -I"$REF/shaders" -I"$REF/submodules/glm" -I"$REF/submodules/fastgltf/include" \
+    -o "$OUT/libref_shim.so" "$HERE/ref_shim.cpp"
+echo "built: $(ls "$OUT")"

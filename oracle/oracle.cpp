@@ -1,0 +1,563 @@
+// oracle.cpp — CPU restatement of the reference's cull / visbuffer raster / HiZ path.
+// TEST INFRASTRUCTURE ONLY (see oracle.h).  PARITY UNPINNED except where oracle.h says otherwise.
+// Build: g++ -O2 -std=c++17 -ffp-contract=off -fno-fast-math -fPIC -shared (oracle/Makefile).
+//
+// Every function cites the reference file:line it restates (paths relative to the upstream tree).
+#include "oracle.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <functional>
+#include <thread>
+#include <vector>
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// Arithmetic policy.  Every operation is a single correctly-rounded fp32 op.
+// ---------------------------------------------------------------------------------------------
+struct V3 { float x, y, z; };
+struct V4 { float x, y, z, w; };
+
+inline float gmin(float x, float y) { return y < x ? y : x; } // GLSL min(x,y)
+inline float gmax(float x, float y) { return x < y ? y : x; } // GLSL max(x,y)
+inline float gclamp(float x, float lo, float hi) { return gmin(gmax(x, lo), hi); }
+
+// mat4 (column-major m[c*4+r]) * vec4 : ((c0*x + c1*y) + c2*z) + c3*w
+inline V4 mul44(const float* m, V4 v) {
+	V4 r;
+	r.x = ((m[0] * v.x + m[4] * v.y) + m[8] * v.z) + m[12] * v.w;
+	r.y = ((m[1] * v.x + m[5] * v.y) + m[9] * v.z) + m[13] * v.w;
+	r.z = ((m[2] * v.x + m[6] * v.y) + m[10] * v.z) + m[14] * v.w;
+	r.w = ((m[3] * v.x + m[7] * v.y) + m[11] * v.z) + m[15] * v.w;
+	return r;
+}
+inline void mul44m(const float* a, const float* b, float* out) { // out = a*b, column by column
+	for (int c = 0; c < 4; ++c) {
+		V4 col = mul44(a, V4{b[c * 4 + 0], b[c * 4 + 1], b[c * 4 + 2], b[c * 4 + 3]});
+		out[c * 4 + 0] = col.x; out[c * 4 + 1] = col.y; out[c * 4 + 2] = col.z; out[c * 4 + 3] = col.w;
+	}
+}
+inline float dot3(V3 a, V3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+
+// determinant(mat3(c0,c1,c2)) = dot(c0, c1.yzx*c2.zxy - c1.zxy*c2.yzx)
+inline float det3(V3 c0, V3 c1, V3 c2) {
+	V3 d;
+	d.x = c1.y * c2.z - c1.z * c2.y;
+	d.y = c1.z * c2.x - c1.x * c2.z;
+	d.z = c1.x * c2.y - c1.y * c2.x;
+	return dot3(c0, d);
+}
+// determinant(mat4): cofactor expansion along the first column; only the sign is consumed (mesh.glsl:71,94)
+inline float det4(const float* m) {
+	auto col3 = [&](int c, int skipRow) {
+		float v[3]; int k = 0;
+		for (int r = 0; r < 4; ++r) if (r != skipRow) v[k++] = m[c * 4 + r];
+		return V3{v[0], v[1], v[2]};
+	};
+	float d0 = det3(col3(1, 0), col3(2, 0), col3(3, 0));
+	float d1 = det3(col3(1, 1), col3(2, 1), col3(3, 1));
+	float d2 = det3(col3(1, 2), col3(2, 2), col3(3, 2));
+	float d3 = det3(col3(1, 3), col3(2, 3), col3(3, 3));
+	return ((m[0] * d0 - m[1] * d1) + m[2] * d2) - m[3] * d3;
+}
+
+inline uint32_t fbits(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
+
+inline bool near_rel(float a, float b, float ulps) {
+	float m = std::fmax(std::fabs(a), std::fabs(b));
+	return std::fabs(a - b) <= ulps * 1.1920929e-7f * m;
+}
+
+template <class F>
+void parallel_for(size_t n, int threads, F fn) {
+	if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
+	if (threads < 1) threads = 1;
+	if ((size_t)threads > n) threads = n ? (int)n : 1;
+	if (threads == 1) { fn(0, n, 0); return; }
+	std::vector<std::thread> pool;
+	for (int t = 0; t < threads; ++t) {
+		size_t b = n * t / threads, e = n * (t + 1) / threads;
+		pool.emplace_back([=] { fn(b, e, t); });
+	}
+	for (auto& th : pool) th.join();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Min-reduction LINEAR sampler with CLAMP_TO_EDGE (application.cpp:438-453):
+// texels {i0, i0+1} per axis with i0 = floor(u*size - 0.5); a texel whose bilinear weight is 0
+// (frac == 0 -> i0+1) takes no part in the reduction.
+// ---------------------------------------------------------------------------------------------
+inline void footprint(float coord, uint32_t size, int& lo, int& hi, int* ambig) {
+	float u = coord * (float)size - 0.5f;
+	if (!(u >= -1.0f)) { lo = hi = 0; return; }                      // NaN or far left: clamps to texel 0
+	if (u >= (float)size) { lo = hi = (int)size - 1; return; }
+	float fl = std::floor(u);
+	float frac = u - fl;
+	int i0 = (int)fl;
+	int i1 = (frac == 0.0f) ? i0 : i0 + 1;
+	if (ambig && (frac < 1e-4f || frac > 1.0f - 1e-4f)) *ambig |= 1;
+	int mx = (int)size - 1;
+	lo = i0 < 0 ? 0 : (i0 > mx ? mx : i0);
+	hi = i1 < 0 ? 0 : (i1 > mx ? mx : i1);
+}
+
+inline float sample_min(const float* img, uint32_t w, uint32_t h, float u, float v, int* ambig) {
+	int x0, x1, y0, y1;
+	footprint(u, w, x0, x1, ambig);
+	footprint(v, h, y0, y1, ambig);
+	float m = img[(size_t)y0 * w + x0];
+	m = gmin(m, img[(size_t)y0 * w + x1]);
+	m = gmin(m, img[(size_t)y1 * w + x0]);
+	m = gmin(m, img[(size_t)y1 * w + x1]);
+	return m;
+}
+
+// culling.h.glsl:32-41
+const float kAabbPositions[8][3] = {
+	{1, -1, -1}, {1, 1, -1}, {-1, 1, -1}, {-1, -1, -1}, {1, -1, 1}, {1, 1, 1}, {-1, -1, 1}, {-1, 1, 1}};
+
+struct Pyr {
+	uint32_t levels, off[17], w[16], h[16], total;
+};
+
+// visbuffer.task.glsl:44-65 for one MeshletDraw
+uint8_t cull_one(const vkv_VisbufferPushConstants* pc, uint32_t drawIdx, const vkv_Camera& cam, const float* occVP,
+                 const Pyr& pyr, const float* pyramid) {
+	const vkv_MeshletDraw* draws = (const vkv_MeshletDraw*)pc->drawBuffer;
+	const float* transforms = (const float*)pc->transformBuffer;
+	const vkv_Primitive* prims = (const vkv_Primitive*)pc->primitiveBuffer;
+	const vkv_MeshletDraw d = draws[drawIdx];                                   // task.glsl:44
+	const float* T = transforms + (size_t)d.transformIndex * 16;                // :45
+	const vkv_Primitive& prim = prims[d.primitiveIndex];                        // :46
+	const vkv_Meshlet& ml = ((const vkv_Meshlet*)prim.meshletBuffer)[d.meshletIndex]; // :47
+	uint8_t flags = 0;
+
+	// :50  worldAabbCenter = (T * vec4(center,1)).xyz
+	V4 wc4 = mul44(T, V4{ml.aabbCenter[0], ml.aabbCenter[1], ml.aabbCenter[2], 1.0f});
+	V3 wc{wc4.x, wc4.y, wc4.z};
+	// :51 -> culling.h.glsl:22-29  abs(mat3(T)) * extent
+	V3 e{ml.aabbExtents[0], ml.aabbExtents[1], ml.aabbExtents[2]};
+	V3 we;
+	we.x = (std::fabs(T[0]) * e.x + std::fabs(T[4]) * e.y) + std::fabs(T[8]) * e.z;
+	we.y = (std::fabs(T[1]) * e.x + std::fabs(T[5]) * e.y) + std::fabs(T[9]) * e.z;
+	we.z = (std::fabs(T[2]) * e.x + std::fabs(T[6]) * e.y) + std::fabs(T[10]) * e.z;
+
+	// :52 -> culling.h.glsl:8-19
+	for (int i = 0; i < 6; ++i) {
+		const float* p = cam.frustum[i];
+		float radius = dot3(we, V3{std::fabs(p[0]), std::fabs(p[1]), std::fabs(p[2])});
+		float distance = dot3(V3{p[0], p[1], p[2]}, wc) - p[3];
+		if (near_rel(-radius, distance, 4.0f)) flags |= ORC_AMBIG_FRUSTUM;
+		if (-radius > distance) return ORC_FRUSTUM_CULLED | flags;
+	}
+
+	// :56 -> culling.h.glsl:44-56
+	V3 ssMin{1.f, 1.f, 1.f}, ssMax{-1.f, -1.f, -1.f};
+	for (int i = 0; i < 8; ++i) {
+		V4 pos{kAabbPositions[i][0] * we.x + wc.x, kAabbPositions[i][1] * we.y + wc.y, kAabbPositions[i][2] * we.z + wc.z, 1.0f};
+		V4 clip = mul44(occVP, pos);
+		if (!(clip.w > 0.0f)) flags |= ORC_CROSSES_CAMERA;
+		float ndcx = gclamp(clip.x / clip.w, -1.f, 1.f);
+		float ndcy = gclamp(clip.y / clip.w, -1.f, 1.f);
+		float uvx = ndcx * 0.5f + 0.5f;
+		float uvy = ndcy * 0.5f + 0.5f;
+		float z = clip.z / clip.w;
+		ssMin.x = gmin(ssMin.x, uvx); ssMin.y = gmin(ssMin.y, uvy); ssMin.z = gmin(ssMin.z, z);
+		ssMax.x = gmax(ssMax.x, uvx); ssMax.y = gmax(ssMax.y, uvy); ssMax.z = gmax(ssMax.z, z);
+	}
+	// :57-59 ; pyramidSize = textureSize(pyramid, 0) (:33)
+	float width = (ssMax.x - ssMin.x) * (float)(int)pyr.w[0];
+	float height = (ssMax.y - ssMin.y) * (float)(int)pyr.h[0];
+	float m = gmax(width, height);
+	// floor(log2(m)) as the exact binary exponent; the sampler clamps lod to [minLod,maxLod]=[0,16] and to
+	// the existing mips (application.cpp:451-452).  NaN / <=0 -> level 0 ; +inf -> last mip.
+	int level;
+	if (!(m > 0.0f)) level = 0;
+	else if (std::isinf(m)) level = 16;
+	else {
+		level = std::ilogb(m);
+		float up = std::nextafter(std::nextafter(m, INFINITY), INFINITY);
+		if (std::ilogb(up) != level) flags |= ORC_AMBIG_LEVEL;
+		if (level < 0) level = 0;
+		if (level > 16) level = 16;
+	}
+	if (level > (int)pyr.levels - 1) level = (int)pyr.levels - 1;
+	// :61-62
+	float cx = (ssMin.x + ssMax.x) * 0.5f;
+	float cy = (ssMin.y + ssMax.y) * 0.5f;
+	int amb = 0;
+	float depth = sample_min(pyramid + pyr.off[level], pyr.w[level], pyr.h[level], cx, cy, &amb);
+	if (amb) flags |= ORC_AMBIG_FOOTPRINT;
+	if (near_rel(depth, ssMax.z, 4.0f)) flags |= ORC_AMBIG_HIZ;
+	// :64
+	bool visible = depth < ssMax.z;
+	return (visible ? ORC_VISIBLE : ORC_OCCLUDED) | flags;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Rasteriser.  Fixed-function rules restated:
+//   viewport (0,0,W,H), depth [0,1]; pixel centres at +0.5; 8 sub-pixel bits; top-left fill rule;
+//   cullMode NONE; depthClamp off => clip to 0<=z<=w; guard band |x|,|y| <= 8w (implementation choice);
+//   depth = screen-space linear interpolation of z/w; test GREATER_OR_EQUAL, clear 0.0.
+// ---------------------------------------------------------------------------------------------
+constexpr int kSubBits = 8;
+constexpr int kSub = 1 << kSubBits;
+constexpr float kGuard = 8.0f;
+
+struct SetupTri {
+	int32_t ax, ay, bx, by, cx, cy;
+	int32_t xmin, xmax, ymin, ymax;
+	int64_t area2;
+	float za, dzb, dzc, invA;
+	uint32_t id;
+};
+
+struct RasterStats {
+	uint64_t tris_in = 0, facing = 0, rejected = 0, clipped = 0, degenerate = 0, rasterised = 0;
+};
+
+inline bool has_nan(const V4& v) { return !(v.x == v.x && v.y == v.y && v.z == v.z && v.w == v.w); }
+
+// One already-inside (post-clip) triangle -> SetupTri
+inline void setup_projected(const V4& A, const V4& B, const V4& C, uint32_t id, uint32_t W, uint32_t H,
+                            std::vector<SetupTri>& out, RasterStats& st) {
+	if (!(A.w > 0.f) || !(B.w > 0.f) || !(C.w > 0.f)) { st.degenerate++; return; }
+	const float hw = (float)W * 0.5f, hh = (float)H * 0.5f;
+	auto proj = [&](const V4& v, int32_t& fx, int32_t& fy, float& z) {
+		float nx = v.x / v.w, ny = v.y / v.w;
+		z = v.z / v.w;
+		float sx = nx * hw + hw;
+		float sy = ny * hh + hh;
+		fx = (int32_t)std::lrintf(sx * (float)kSub);
+		fy = (int32_t)std::lrintf(sy * (float)kSub);
+	};
+	SetupTri t;
+	float za, zb, zc;
+	proj(A, t.ax, t.ay, za);
+	proj(B, t.bx, t.by, zb);
+	proj(C, t.cx, t.cy, zc);
+	int64_t area2 = (int64_t)(t.bx - t.ax) * (t.cy - t.ay) - (int64_t)(t.by - t.ay) * (t.cx - t.ax);
+	if (area2 == 0) { st.degenerate++; return; }
+	if (area2 < 0) { // cullMode NONE: both windings are drawn; normalise to positive area
+		std::swap(t.bx, t.cx); std::swap(t.by, t.cy); std::swap(zb, zc);
+		area2 = -area2;
+	}
+	t.area2 = area2;
+	t.za = za; t.dzb = zb - za; t.dzc = zc - za;
+	t.invA = 1.0f / (float)area2;
+	int32_t minx = std::min(t.ax, std::min(t.bx, t.cx)), maxx = std::max(t.ax, std::max(t.bx, t.cx));
+	int32_t miny = std::min(t.ay, std::min(t.by, t.cy)), maxy = std::max(t.ay, std::max(t.by, t.cy));
+	t.xmin = std::max<int32_t>(0, (minx + (kSub / 2 - 1)) >> kSubBits);
+	t.xmax = std::min<int32_t>((int32_t)W - 1, (maxx - kSub / 2) >> kSubBits);
+	t.ymin = std::max<int32_t>(0, (miny + (kSub / 2 - 1)) >> kSubBits);
+	t.ymax = std::min<int32_t>((int32_t)H - 1, (maxy - kSub / 2) >> kSubBits);
+	if (t.xmin > t.xmax || t.ymin > t.ymax) { st.rejected++; return; }
+	t.id = id;
+	out.push_back(t);
+	st.rasterised++;
+}
+
+// Sutherland–Hodgman against one plane; dist(v) >= 0 is inside.  The intersection is always evaluated
+// from the inside vertex towards the outside vertex so a shared edge yields the same point in both triangles.
+template <class D>
+inline int clip_plane(const V4* in, int n, V4* out, D dist) {
+	int m = 0;
+	for (int i = 0; i < n; ++i) {
+		const V4& cur = in[i];
+		const V4& nxt = in[(i + 1) % n];
+		float dc = dist(cur), dn = dist(nxt);
+		bool ic = dc >= 0.f, inx = dn >= 0.f;
+		if (ic) out[m++] = cur;
+		if (ic != inx) {
+			const V4& a = ic ? cur : nxt; // inside
+			const V4& b = ic ? nxt : cur; // outside
+			float da = ic ? dc : dn, db = ic ? dn : dc;
+			float t = da / (da - db);
+			V4 r;
+			r.x = a.x + t * (b.x - a.x);
+			r.y = a.y + t * (b.y - a.y);
+			r.z = a.z + t * (b.z - a.z);
+			r.w = a.w + t * (b.w - a.w);
+			out[m++] = r;
+		}
+	}
+	return m;
+}
+
+inline void raster_setup(const V4& A, const V4& B, const V4& C, uint32_t id, uint32_t W, uint32_t H,
+                         std::vector<SetupTri>& out, RasterStats& st) {
+	if (has_nan(A) || has_nan(B) || has_nan(C)) { st.rejected++; return; }
+	// trivial reject: all three vertices outside one view-volume plane
+	auto code = [](const V4& v) {
+		int c = 0;
+		if (v.x < -v.w) c |= 1;
+		if (v.x > v.w) c |= 2;
+		if (v.y < -v.w) c |= 4;
+		if (v.y > v.w) c |= 8;
+		if (v.z < 0.f) c |= 16;
+		if (v.z > v.w) c |= 32;
+		return c;
+	};
+	int ca = code(A), cb = code(B), cc = code(C);
+	if (ca & cb & cc) { st.rejected++; return; }
+	auto needs = [](const V4& v) {
+		float g = kGuard * v.w;
+		return v.z < 0.f || v.z > v.w || v.x > g || v.x < -g || v.y > g || v.y < -g || !(v.w > 0.f);
+	};
+	if (!(needs(A) || needs(B) || needs(C))) { setup_projected(A, B, C, id, W, H, out, st); return; }
+	st.clipped++;
+	V4 p0[12], p1[12];
+	p0[0] = A; p0[1] = B; p0[2] = C;
+	int n = 3;
+	n = clip_plane(p0, n, p1, [](const V4& v) { return v.w - v.z; }); if (n < 3) return;      // near (reverse-Z: z<=w)
+	n = clip_plane(p1, n, p0, [](const V4& v) { return v.z; }); if (n < 3) return;            // far  (z>=0)
+	n = clip_plane(p0, n, p1, [](const V4& v) { return kGuard * v.w - v.x; }); if (n < 3) return;
+	n = clip_plane(p1, n, p0, [](const V4& v) { return kGuard * v.w + v.x; }); if (n < 3) return;
+	n = clip_plane(p0, n, p1, [](const V4& v) { return kGuard * v.w - v.y; }); if (n < 3) return;
+	n = clip_plane(p1, n, p0, [](const V4& v) { return kGuard * v.w + v.y; }); if (n < 3) return;
+	for (int i = 1; i + 1 < n; ++i) setup_projected(p0[0], p0[i], p0[i + 1], id, W, H, out, st);
+}
+
+// visbuffer.mesh.glsl:30-104 for one surviving MeshletDraw -> setup triangles
+void meshlet_setup(const vkv_VisbufferPushConstants* pc, uint32_t drawId, const vkv_Camera& cam, uint32_t W, uint32_t H,
+                   std::vector<SetupTri>& out, RasterStats& st) {
+	const vkv_MeshletDraw d = ((const vkv_MeshletDraw*)pc->drawBuffer)[drawId];           // mesh.glsl:32
+	const vkv_Primitive& prim = ((const vkv_Primitive*)pc->primitiveBuffer)[d.primitiveIndex];
+	const vkv_Meshlet& ml = ((const vkv_Meshlet*)prim.meshletBuffer)[d.meshletIndex];
+	const vkv_Material& mat = ((const vkv_Material*)pc->materialBuffer)[prim.materialIndex];
+	const float* T = (const float*)pc->transformBuffer + (size_t)d.transformIndex * 16;  // :43
+	float mvp[16];
+	mul44m(cam.viewProjection, T, mvp);                                                  // :44
+	const uint32_t* vidx = (const uint32_t*)prim.vertexIndexBuffer;
+	const vkv_Vertex* verts = (const vkv_Vertex*)prim.vertexBuffer;
+	const uint8_t* tris = (const uint8_t*)prim.primitiveIndexBuffer;
+	V4 clip[VKV_MAX_VERTICES];
+	uint32_t vc = ml.vertexCount, tc = ml.triangleCount;
+	for (uint32_t v = 0; v < vc && v < VKV_MAX_VERTICES; ++v) {                          // :50-69
+		const float* p = verts[vidx[ml.vertexOffset + v]].position;
+		clip[v] = mul44(mvp, V4{p[0], p[1], p[2], 1.0f});                                // :61
+	}
+	float transformDet = det4(T);                                                        // :71
+	bool doubleSided = mat.doubleSided != 0;
+	for (uint32_t t = 0; t < tc; ++t) {                                                  // :73-103
+		uint32_t a = tris[ml.triangleOffset + t * 3 + 0], b = tris[ml.triangleOffset + t * 3 + 1],
+		         c = tris[ml.triangleOffset + t * 3 + 2];
+		st.tris_in++;
+		if (!doubleSided) {                                                              // :86-98
+			float det = det3(V3{clip[a].x, clip[a].y, clip[a].w}, V3{clip[b].x, clip[b].y, clip[b].w},
+			                 V3{clip[c].x, clip[c].y, clip[c].w});
+			bool cull = (transformDet < 0.0f) ? (det < 0.0f) : (det > 0.0f);
+			if (cull) { st.facing++; continue; }
+		}
+		raster_setup(clip[a], clip[b], clip[c], vkv_pack_visbuffer(drawId, t), W, H, out, st);   // frag.glsl:36
+	}
+}
+
+inline bool top_left(int32_t dx, int32_t dy) { return dy < 0 || (dy == 0 && dx > 0); }
+
+// rasterise rows [y0,y1) of one set-up triangle
+inline void raster_rows(const SetupTri& t, int y0, int y1, uint32_t W, float* depth, uint32_t* ids_ref, uint32_t* ids_min,
+                        uint8_t* tie, uint64_t& frags, uint64_t& passed) {
+	int ys = std::max(y0, t.ymin), ye = std::min(y1 - 1, t.ymax);
+	if (ys > ye) return;
+	// edge k opposite vertex k: w0 = E(b,c,p), w1 = E(c,a,p), w2 = E(a,b,p); E(u,v,p) = (vx-ux)(py-uy) - (vy-uy)(px-ux)
+	const int64_t e0dx = t.cx - t.bx, e0dy = t.cy - t.by;
+	const int64_t e1dx = t.ax - t.cx, e1dy = t.ay - t.cy;
+	const int64_t e2dx = t.bx - t.ax, e2dy = t.by - t.ay;
+	const int64_t b0 = top_left((int32_t)e0dx, (int32_t)e0dy) ? 0 : 1;
+	const int64_t b1 = top_left((int32_t)e1dx, (int32_t)e1dy) ? 0 : 1;
+	const int64_t b2 = top_left((int32_t)e2dx, (int32_t)e2dy) ? 0 : 1;
+	for (int y = ys; y <= ye; ++y) {
+		const int64_t py = (int64_t)y * kSub + kSub / 2;
+		const int64_t px0 = (int64_t)t.xmin * kSub + kSub / 2;
+		int64_t w0 = e0dx * (py - t.by) - e0dy * (px0 - t.bx);
+		int64_t w1 = e1dx * (py - t.cy) - e1dy * (px0 - t.cx);
+		int64_t w2 = e2dx * (py - t.ay) - e2dy * (px0 - t.ax);
+		size_t row = (size_t)y * W;
+		for (int x = t.xmin; x <= t.xmax; ++x) {
+			if (w0 >= b0 && w1 >= b1 && w2 >= b2) {
+				float l1 = (float)w1 * t.invA;
+				float l2 = (float)w2 * t.invA;
+				float z = (t.za + l1 * t.dzb) + l2 * t.dzc;
+				z = (z > 0.0f) ? z : 0.0f;
+				z = (z < 1.0f) ? z : 1.0f;
+				frags++;
+				size_t p = row + x;
+				float d = depth[p];
+				if (z > d) {                       // GREATER_OR_EQUAL, strict part
+					depth[p] = z; ids_ref[p] = t.id; ids_min[p] = t.id; tie[p] = 0; passed++;
+				} else if (z == d) {               // GREATER_OR_EQUAL, equal part: the later primitive wins
+					if (ids_ref[p] == VKV_VISBUFFER_CLEAR) { ids_ref[p] = t.id; ids_min[p] = t.id; tie[p] = 0; }
+					else {
+						if (t.id != ids_min[p]) { tie[p] = 1; if (t.id < ids_min[p]) ids_min[p] = t.id; }
+						ids_ref[p] = t.id;
+					}
+					passed++;
+				}
+			}
+			w0 -= e0dy * kSub; w1 -= e1dy * kSub; w2 -= e2dy * kSub;
+		}
+	}
+}
+
+} // namespace
+
+extern "C" {
+
+uint32_t orc_pyramid_layout(uint32_t W, uint32_t H, uint32_t offsets[17], uint32_t w[16], uint32_t h[16], uint32_t* total) {
+	uint32_t levels = vkv_mip_levels(W, H);
+	if (levels > 16) levels = 16;
+	uint32_t off = 0;
+	for (uint32_t k = 0; k < levels; ++k) {
+		w[k] = vkv_mip_extent(W, k);
+		h[k] = vkv_mip_extent(H, k);
+		offsets[k] = off;
+		off += w[k] * h[k];
+	}
+	offsets[levels] = off;
+	if (total) *total = off;
+	return levels;
+}
+
+float orc_sample_min(const float* img, uint32_t w, uint32_t h, float u, float v, int* ambig) {
+	return sample_min(img, w, h, u, v, ambig);
+}
+
+uint64_t orc_vis64_key(float depth, uint32_t id) { return ((uint64_t)(~fbits(depth)) << 32) | id; }
+
+int orc_cull(const vkv_VisbufferPushConstants* pc, uint32_t W, uint32_t H, const float* pyramid, int vp_select,
+             const uint8_t* only_status, uint8_t* status, orc_counters* ctr, int threads) {
+	Pyr pyr;
+	pyr.levels = orc_pyramid_layout(W, H, pyr.off, pyr.w, pyr.h, &pyr.total);
+	if (pyr.levels == 0) return -1;
+	const vkv_Camera cam = *(const vkv_Camera*)pc->cameraBuffer; // task.glsl:31
+	const float* occVP = vp_select == 0 ? cam.prevOcclusionViewProjection : cam.viewProjection;
+	const uint32_t N = pc->meshletDrawCount;
+	// chunks of maxMeshlets draws = one reference task workgroup (task.glsl:28-29)
+	const size_t chunks = (N + VKV_MAX_MESHLETS_PER_TASK - 1) / VKV_MAX_MESHLETS_PER_TASK;
+	parallel_for(chunks, threads, [&](size_t b, size_t e, int) {
+		for (size_t c = b; c < e; ++c) {
+			uint32_t lo = (uint32_t)c * VKV_MAX_MESHLETS_PER_TASK, hi = std::min<uint32_t>(N, lo + VKV_MAX_MESHLETS_PER_TASK);
+			for (uint32_t i = lo; i < hi; ++i) {
+				if (only_status && (only_status[i] & ORC_STATUS_MASK) != ORC_OCCLUDED) { status[i] = ORC_NOT_TESTED; continue; }
+				status[i] = cull_one(pc, i, cam, occVP, pyr, pyramid);
+			}
+		}
+	});
+	if (ctr) {
+		for (uint32_t i = 0; i < N; ++i) {
+			uint8_t s = status[i];
+			if ((s & ORC_STATUS_MASK) == ORC_NOT_TESTED) continue;
+			ctr->tested++;
+			switch (s & ORC_STATUS_MASK) {
+				case ORC_FRUSTUM_CULLED: ctr->frustum_culled++; break;
+				case ORC_OCCLUDED: ctr->occluded++; break;
+				case ORC_VISIBLE: ctr->visible++; break;
+			}
+			if (s & ORC_AMBIG_FRUSTUM) ctr->ambig_frustum++;
+			if (s & ORC_AMBIG_HIZ) ctr->ambig_hiz++;
+			if (s & ORC_AMBIG_LEVEL) ctr->ambig_level++;
+			if (s & ORC_AMBIG_FOOTPRINT) ctr->ambig_footprint++;
+			if (s & ORC_CROSSES_CAMERA) ctr->crosses_camera++;
+		}
+	}
+	return 0;
+}
+
+void orc_clear(uint32_t W, uint32_t H, float* depth, uint32_t* ids_ref, uint32_t* ids_min, uint8_t* tie) {
+	size_t n = (size_t)W * H;
+	for (size_t i = 0; i < n; ++i) {
+		depth[i] = 0.0f;                                   // application.cpp:807
+		if (ids_ref) ids_ref[i] = VKV_VISBUFFER_CLEAR;     // application.cpp:782
+		if (ids_min) ids_min[i] = VKV_VISBUFFER_CLEAR;
+		if (tie) tie[i] = 0;
+	}
+}
+
+int orc_raster(const vkv_VisbufferPushConstants* pc, uint32_t W, uint32_t H, const uint32_t* draw_ids, uint32_t n_draws,
+               float* depth, uint32_t* ids_ref, uint32_t* ids_min, uint8_t* tie, orc_counters* ctr, int threads) {
+	if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
+	if (threads < 1) threads = 1;
+	const vkv_Camera cam = *(const vkv_Camera*)pc->cameraBuffer;
+	// Phase 1: geometry + triangle setup, parallel over contiguous chunks of the draw list (order preserved)
+	const int nchunks = std::max(1, std::min<int>(threads * 4, (int)n_draws));
+	std::vector<std::vector<SetupTri>> lists(nchunks);
+	std::vector<RasterStats> stats(nchunks);
+	std::atomic<int> next{0};
+	auto work1 = [&] {
+		for (;;) {
+			int c = next.fetch_add(1);
+			if (c >= nchunks) break;
+			size_t b = (size_t)n_draws * c / nchunks, e = (size_t)n_draws * (c + 1) / nchunks;
+			for (size_t i = b; i < e; ++i) meshlet_setup(pc, draw_ids[i], cam, W, H, lists[c], stats[c]);
+		}
+	};
+	{
+		std::vector<std::thread> pool;
+		for (int t = 1; t < threads; ++t) pool.emplace_back(work1);
+		work1();
+		for (auto& th : pool) th.join();
+	}
+	// Phase 2: pixels, parallel over horizontal bands; each band walks all triangles in submission order,
+	// so the result equals a sequential rasteriser.
+	const int bands = std::max(1, std::min<int>(threads * 8, (int)H));
+	std::vector<uint64_t> frags(bands, 0), passed(bands, 0);
+	std::atomic<int> nextb{0};
+	auto work2 = [&] {
+		for (;;) {
+			int b = nextb.fetch_add(1);
+			if (b >= bands) break;
+			int y0 = (int)((size_t)H * b / bands), y1 = (int)((size_t)H * (b + 1) / bands);
+			for (int c = 0; c < nchunks; ++c)
+				for (const SetupTri& t : lists[c])
+					if (t.ymax >= y0 && t.ymin < y1) raster_rows(t, y0, y1, W, depth, ids_ref, ids_min, tie, frags[b], passed[b]);
+		}
+	};
+	{
+		std::vector<std::thread> pool;
+		for (int t = 1; t < threads; ++t) pool.emplace_back(work2);
+		work2();
+		for (auto& th : pool) th.join();
+	}
+	if (ctr) {
+		ctr->meshlets += n_draws;
+		for (auto& s : stats) {
+			ctr->triangles_in += s.tris_in; ctr->triangles_culled_facing += s.facing; ctr->triangles_rejected += s.rejected;
+			ctr->triangles_clipped += s.clipped; ctr->triangles_degenerate += s.degenerate; ctr->triangles_rasterised += s.rasterised;
+		}
+		for (int b = 0; b < bands; ++b) { ctr->fragments += frags[b]; ctr->fragments_passed += passed[b]; }
+		uint64_t ties = 0;
+		for (size_t i = 0, n = (size_t)W * H; i < n; ++i) ties += tie[i];
+		ctr->tie_pixels = ties;
+	}
+	return 0;
+}
+
+int orc_hiz(uint32_t W, uint32_t H, const float* depth, float* pyramid, int threads) {
+	Pyr pyr;
+	pyr.levels = orc_pyramid_layout(W, H, pyr.off, pyr.w, pyr.h, &pyr.total);
+	// application.cpp:964-979: view 0 = depth image, view i = pyramid mip i-1; dispatch i writes levelSize = res >> i
+	for (uint32_t i = 1; i <= pyr.levels; ++i) {
+		const uint32_t dw = W >> i, dh = H >> i;
+		if (dw == 0 || dh == 0) continue; // zero-sized dispatch: the mip keeps its previous contents
+		const float* src = (i == 1) ? depth : pyramid + pyr.off[i - 2];
+		const uint32_t sw = (i == 1) ? W : pyr.w[i - 2], sh = (i == 1) ? H : pyr.h[i - 2];
+		float* dst = pyramid + pyr.off[i - 1];
+		const uint32_t dstride = pyr.w[i - 1];
+		parallel_for(dh, (dw * dh > 4096) ? threads : 1, [&](size_t b, size_t e, int) {
+			for (size_t y = b; y < e; ++y)
+				for (uint32_t x = 0; x < dw; ++x) {
+					// hiz_reduce.comp.glsl:28 : texture(src, (vec2(pos) + 0.5) / imageSize)
+					float u = ((float)x + 0.5f) / (float)dw;
+					float v = ((float)y + 0.5f) / (float)dh;
+					dst[y * dstride + x] = sample_min(src, sw, sh, u, v, nullptr);
+				}
+		});
+	}
+	return 0;
+}
+
+} // extern "C"

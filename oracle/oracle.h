@@ -1,0 +1,99 @@
+/* oracle.h — CPU restatement of the reference's per-frame geometry path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product: only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it,
+ * and only as the checker (or as the timed CPU baseline), never on the product path.
+ *
+ * PARITY UNPINNED for cull / raster / HiZ: the reference ships no tests, golden images or
+ * known-answer vectors for these stages, and its shaders cannot be run in
+ * this image (no Vulkan loader / lavapipe / glslang).  What *is* pinned:
+ *   - culling.h.glsl:8-29 (isAabbInFrustum, getWorldSpaceAabbExtent) compile as C++ against the
+ *     reference's glm; oracle/build_ref.sh builds them into oracle/_ref/ and
+ *     tests/test_oracle_vs_ref.py checks this restatement against them bit-for-bit;
+ *   - the data layouts (include/vkv_abi.h static_asserts == the reference headers compiled as C++);
+ *   - meshoptimizer / glm used as input generators from the reference's pinned submodules.
+ *
+ * Arithmetic policy, compiled with -ffp-contract=off and no fast-math:
+ *   fp32 round-to-nearest, no FMA contraction;
+ *   dot(a,b)      = ((a.x*b.x + a.y*b.y) + a.z*b.z) [+ a.w*b.w]
+ *   mat4*vec4     = ((c0*x + c1*y) + c2*z) + c3*w per component; mat4*mat4 column by column
+ *   mat3*vec3     = (c0*x + c1*y) + c2*z
+ *   det(mat3)     = dot(c0, cross-like(c1,c2)) (expansion along the first column)
+ *   min(x,y) = y<x?y:x ; max(x,y) = x<y?y:x ; clamp = min(max(x,lo),hi)   (GLSL spec definitions)
+ *   floor(log2(x)) = exact binary exponent
+ *
+ * All pointers are HOST pointers; the u64 "device address" fields of vkv_Primitive and
+ * vkv_VisbufferPushConstants carry host addresses here.
+ */
+#ifndef VKV_ORACLE_H
+#define VKV_ORACLE_H
+
+#include "../include/vkv_abi.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* per-draw status written by orc_cull */
+enum {
+	ORC_FRUSTUM_CULLED = 0,
+	ORC_OCCLUDED = 1,
+	ORC_VISIBLE = 2,
+	ORC_NOT_TESTED = 3,
+	ORC_STATUS_MASK = 3,
+	/* diagnostic flags (ambiguous = a comparison within a few ulp of its threshold; excluded-and-counted class) */
+	ORC_AMBIG_FRUSTUM = 1 << 2,
+	ORC_AMBIG_HIZ = 1 << 3,
+	ORC_AMBIG_LEVEL = 1 << 4,   /* max(w,h) within 2 ulp below a power of two */
+	ORC_CROSSES_CAMERA = 1 << 5, /* some AABB corner has clip.w <= 0 */
+	ORC_AMBIG_FOOTPRINT = 1 << 6 /* sampler frac within 1e-4 of 0 */
+};
+
+typedef struct orc_counters {
+	uint64_t tested, frustum_culled, occluded, visible;
+	uint64_t ambig_frustum, ambig_hiz, ambig_level, ambig_footprint, crosses_camera;
+	/* raster */
+	uint64_t meshlets, triangles_in, triangles_culled_facing, triangles_rejected, triangles_clipped,
+	         triangles_degenerate, triangles_rasterised, fragments, fragments_passed, tie_pixels;
+} orc_counters;
+
+/* Pyramid storage: one contiguous float array, mip k at offsets[k], extent w[k] x h[k].
+ * Returns mipLevels (application.cpp:472-473); total floats in *total. */
+uint32_t orc_pyramid_layout(uint32_t W, uint32_t H, uint32_t offsets[17], uint32_t w[16], uint32_t h[16], uint32_t* total);
+
+/* visbuffer.task.glsl:25-76 + culling.h.glsl:8-56 + sampler state application.cpp:438-453.
+ * vp_select: 0 = camera.prevOcclusionViewProjection (reference behaviour; pass A)
+ *            1 = camera.viewProjection (two-pass extension: pass B re-test against the current pyramid)
+ * only_status: if non-NULL, only draws with (only_status[i]&3)==ORC_OCCLUDED are tested (pass B); others get ORC_NOT_TESTED.
+ * status[N] receives the per-draw result; threads<=0 -> hardware_concurrency. */
+int orc_cull(const vkv_VisbufferPushConstants* pc, uint32_t W, uint32_t H, const float* pyramid,
+             int vp_select, const uint8_t* only_status, uint8_t* status, orc_counters* ctr, int threads);
+
+/* visbuffer.mesh.glsl:30-104 + fixed-function state (application.cpp:326-340,772-841;
+ * pipeline_builder.cpp:225-277) + visbuffer.frag.glsl:36.
+ * Rasterises the given MeshletDraw indices IN ORDER onto (depth, ids_ref, ids_min, tie) which are in/out
+ * (clear first with orc_clear).  ids_ref follows the reference tie rule (>= : last writer wins),
+ * ids_min keeps the lowest id among exact-depth ties (what a 64-bit atomicMin produces), tie[p]=1 where
+ * the final depth is shared by >= 2 different ids. */
+int orc_raster(const vkv_VisbufferPushConstants* pc, uint32_t W, uint32_t H,
+               const uint32_t* draw_ids, uint32_t n_draws,
+               float* depth, uint32_t* ids_ref, uint32_t* ids_min, uint8_t* tie,
+               orc_counters* ctr, int threads);
+
+void orc_clear(uint32_t W, uint32_t H, float* depth, uint32_t* ids_ref, uint32_t* ids_min, uint8_t* tie);
+
+/* hiz_reduce.comp.glsl:21-31 + application.cpp:951-1003 + min-sampler footprint rule.
+ * Mips whose dispatch size is 0 in either axis are left untouched. */
+int orc_hiz(uint32_t W, uint32_t H, const float* depth, float* pyramid, int threads);
+
+/* The sampler itself, exposed for unit tests: min over the <=2x2 non-zero-weight texels around (u,v)
+ * of a w x h image with CLAMP_TO_EDGE.  *ambig is OR-ed with 1 if a frac is within 1e-4 of 0. */
+float orc_sample_min(const float* img, uint32_t w, uint32_t h, float u, float v, int* ambig);
+
+/* 64-bit visbuffer key: (~floatBits(depth) << 32) | id */
+uint64_t orc_vis64_key(float depth, uint32_t id);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,96 @@
+// ref_shim.cpp — extern "C" window onto the parts of the REFERENCE that compile as C++ (built by oracle/build_ref.sh
+// into oracle/_ref/libref_shim.so).  TEST INFRASTRUCTURE ONLY: used to pin the CPU oracle and the host input
+// generators against the reference's own code.  Everything included below is read in place from /root/reference.
+#include <array>
+#include <cstddef>
+#include <cstdint>
+#include <cstring>
+
+#include <glm/glm.hpp>
+#include <glm/gtc/matrix_transform.hpp>
+
+#include "mesh_common.h.glsl"          // reference: glsl::Camera, Meshlet, Vertex, MeshletDraw, Primitive, Material
+#include "visbuffer/visbuffer.h.glsl"  // reference: glsl::VisbufferPushConstants, packVisBuffer
+#include "culling_head.h.glsl"         // reference: culling.h.glsl:1-30 (generated slice, see build_ref.sh)
+#include "camera_fns.inc"              // reference: camera.cpp reverseDepth + generateCameraFrustum
+
+#include <fastgltf/math.hpp>
+
+extern "C" {
+
+// culling.h.glsl:8-19
+int ref_is_aabb_in_frustum(const float c[3], const float e[3], const float frustum[24]) {
+	glm::vec4 f[6];
+	for (int i = 0; i < 6; ++i) f[i] = glm::vec4(frustum[i * 4], frustum[i * 4 + 1], frustum[i * 4 + 2], frustum[i * 4 + 3]);
+	return glsl::isAabbInFrustum(glm::vec3(c[0], c[1], c[2]), glm::vec3(e[0], e[1], e[2]), f) ? 1 : 0;
+}
+
+// culling.h.glsl:22-29
+void ref_world_aabb_extent(const float e[3], const float m[16], float out[3]) {
+	glm::mat4 t;
+	std::memcpy(&t, m, 64);
+	glm::vec3 r = glsl::getWorldSpaceAabbExtent(glm::vec3(e[0], e[1], e[2]), t);
+	out[0] = r.x; out[1] = r.y; out[2] = r.z;
+}
+
+// task.glsl:50 as glm evaluates it on the C++ side (NOTE: glm's mat4*vec4 pairs the adds, the oracle's policy is
+// left-to-right; the test compares within 1 ulp and reports how many differ)
+void ref_transform_point(const float m[16], const float p[3], float out[3]) {
+	glm::mat4 t;
+	std::memcpy(&t, m, 64);
+	glm::vec4 r = t * glm::vec4(p[0], p[1], p[2], 1.0f);
+	out[0] = r.x; out[1] = r.y; out[2] = r.z;
+}
+
+uint32_t ref_pack_visbuffer(uint32_t drawIndex, uint32_t primitiveId) { return glsl::packVisBuffer(drawIndex, primitiveId); }
+
+// sizeof/offsetof table of the shared structs, in the order tests/test_abi.py expects
+int ref_layout(uint32_t* out, int cap) {
+	const uint32_t v[] = {
+		(uint32_t)sizeof(glsl::Camera), (uint32_t)offsetof(glsl::Camera, prevOcclusionViewProjection), (uint32_t)offsetof(glsl::Camera, viewProjection),
+		(uint32_t)offsetof(glsl::Camera, occlusionViewProjection), (uint32_t)offsetof(glsl::Camera, frustum),
+		(uint32_t)sizeof(glsl::Meshlet), (uint32_t)offsetof(glsl::Meshlet, triangleOffset), (uint32_t)offsetof(glsl::Meshlet, vertexCount),
+		(uint32_t)offsetof(glsl::Meshlet, triangleCount), (uint32_t)offsetof(glsl::Meshlet, aabbExtents), (uint32_t)offsetof(glsl::Meshlet, aabbCenter),
+		(uint32_t)sizeof(glsl::Vertex), (uint32_t)offsetof(glsl::Vertex, color), (uint32_t)offsetof(glsl::Vertex, normal), (uint32_t)offsetof(glsl::Vertex, uv),
+		(uint32_t)sizeof(glsl::MeshletDraw), (uint32_t)offsetof(glsl::MeshletDraw, meshletIndex), (uint32_t)offsetof(glsl::MeshletDraw, transformIndex),
+		(uint32_t)sizeof(glsl::Primitive), (uint32_t)offsetof(glsl::Primitive, meshletBuffer), (uint32_t)offsetof(glsl::Primitive, aabbExtents),
+		(uint32_t)offsetof(glsl::Primitive, aabbCenter), (uint32_t)offsetof(glsl::Primitive, meshletCount), (uint32_t)offsetof(glsl::Primitive, materialIndex),
+		(uint32_t)sizeof(glsl::Material), (uint32_t)offsetof(glsl::Material, albedoIndex), (uint32_t)offsetof(glsl::Material, uvOffset),
+		(uint32_t)offsetof(glsl::Material, alphaCutoff), (uint32_t)offsetof(glsl::Material, doubleSided),
+		(uint32_t)sizeof(glsl::VisbufferPushConstants), (uint32_t)offsetof(glsl::VisbufferPushConstants, meshletDrawCount),
+		(uint32_t)offsetof(glsl::VisbufferPushConstants, transformBuffer), (uint32_t)offsetof(glsl::VisbufferPushConstants, primitiveBuffer),
+		(uint32_t)offsetof(glsl::VisbufferPushConstants, cameraBuffer), (uint32_t)offsetof(glsl::VisbufferPushConstants, materialBuffer),
+		(uint32_t)offsetof(glsl::VisbufferPushConstants, depthPyramid),
+		glsl::maxVertices, glsl::maxPrimitives, glsl::maxMeshlets, glsl::triangleBits, glsl::drawIndexBits,
+	};
+	const int n = (int)(sizeof(v) / sizeof(v[0]));
+	for (int i = 0; i < n && i < cap; ++i) out[i] = v[i];
+	return n;
+}
+
+// Camera::updateCamera's matrix assembly (camera.cpp:170-193) with the reference's own glm + reverseDepth + generateCameraFrustum
+void ref_camera(const float eye[3], const float center[3], const float up[3], uint32_t W, uint32_t H, float vp_out[16], float frustum_out[24]) {
+	auto view = glm::lookAtRH(glm::vec3(eye[0], eye[1], eye[2]), glm::vec3(center[0], center[1], center[2]), glm::vec3(up[0], up[1], up[2]));
+	static constexpr auto zNear = 0.1f;
+	static constexpr auto zFar = 1000.0f;
+	static constexpr auto fov = glm::radians(75.0f);
+	const auto aspectRatio = static_cast<float>(W) / static_cast<float>(H);
+	auto projectionMatrix = glm::perspectiveRH_ZO(fov, aspectRatio, zNear, zFar);
+	projectionMatrix[1][1] *= -1;
+	glm::mat4 vp = reverseDepth(projectionMatrix) * view;
+	std::memcpy(vp_out, &vp, 64);
+	std::array<glm::vec4, 6> fr;
+	generateCameraFrustum(vp, fr);
+	std::memcpy(frustum_out, fr.data(), 96);
+}
+
+// world.cpp:221 : scale(rotate(translate(parent, T), R), S) with fastgltf::math
+void ref_node_matrix(const float parent[16], const float t[3], const float r[4], const float s[3], float out[16]) {
+	namespace fm = fastgltf::math;
+	fm::fmat4x4 p;
+	std::memcpy(p.data(), parent, 64);
+	auto m = fm::scale(fm::rotate(fm::translate(p, fm::fvec3(t[0], t[1], t[2])), fm::fquat(r[0], r[1], r[2], r[3])), fm::fvec3(s[0], s[1], s[2]));
+	std::memcpy(out, m.data(), 64);
+}
+
+} // extern "C"

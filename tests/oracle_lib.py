@@ -1,0 +1,123 @@
+"""ctypes binding of oracle/liboracle.so — TEST INFRASTRUCTURE (see oracle/oracle.h).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from vk_gltf_viewer_b200 import abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+FRUSTUM_CULLED, OCCLUDED, VISIBLE, NOT_TESTED, STATUS_MASK = 0, 1, 2, 3, 3
+AMBIG_FRUSTUM, AMBIG_HIZ, AMBIG_LEVEL, CROSSES_CAMERA, AMBIG_FOOTPRINT = 4, 8, 16, 32, 64
+
+
+class Counters(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in (
+        "tested", "frustum_culled", "occluded", "visible",
+        "ambig_frustum", "ambig_hiz", "ambig_level", "ambig_footprint", "crosses_camera",
+        "meshlets", "triangles_in", "triangles_culled_facing", "triangles_rejected", "triangles_clipped",
+        "triangles_degenerate", "triangles_rasterised", "fragments", "fragments_passed", "tie_pixels")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = os.path.join(ROOT, "oracle", "liboracle.so")
+        if not os.path.exists(path):
+            subprocess.check_call(["make", "-C", ROOT, "oracle/liboracle.so"])
+        L = C.CDLL(path)
+        L.orc_pyramid_layout.restype = C.c_uint32
+        L.orc_cull.argtypes = [C.POINTER(abi.PushConstants), C.c_uint32, C.c_uint32, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                               C.POINTER(Counters), C.c_int]
+        L.orc_raster.argtypes = [C.POINTER(abi.PushConstants), C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.POINTER(Counters), C.c_int]
+        L.orc_clear.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_hiz.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_sample_min.restype = C.c_float
+        L.orc_sample_min.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.POINTER(C.c_int)]
+        L.orc_vis64_key.restype = C.c_uint64
+        L.orc_vis64_key.argtypes = [C.c_float, C.c_uint32]
+        _lib = L
+    return _lib
+
+
+class Targets:
+    """depth / ids / tie images + pyramid for one view (what the reference's attachments hold)."""
+
+    def __init__(self, W, H):
+        self.W, self.H = W, H
+        self.depth = np.zeros((H, W), np.float32)
+        self.ids_ref = np.full((H, W), abi.VISBUFFER_CLEAR, np.uint32)
+        self.ids_min = np.full((H, W), abi.VISBUFFER_CLEAR, np.uint32)
+        self.tie = np.zeros((H, W), np.uint8)
+        self.levels, self.layout, total = abi.pyramid_layout(W, H)
+        self.pyramid = np.zeros(total, np.float32)  # context-create clear: 0.0 = far
+
+    def clear(self):
+        lib().orc_clear(self.W, self.H, self.depth.ctypes.data, self.ids_ref.ctypes.data, self.ids_min.ctypes.data, self.tie.ctypes.data)
+
+    def mip(self, k):
+        off, w, h = self.layout[k]
+        return self.pyramid[off:off + w * h].reshape(h, w)
+
+    def vis64(self):
+        """the 64-bit visbuffer an atomicMin rasteriser must produce: (~bits(depth) << 32) | ids_min"""
+        hi = (~self.depth.view(np.uint32)).astype(np.uint64)
+        return (hi << np.uint64(32)) | self.ids_min.astype(np.uint64)
+
+
+def cull(pc, W, H, pyramid, vp_select=0, only_status=None, threads=0):
+    n = pc.meshletDrawCount
+    status = np.zeros(n, np.uint8)
+    ctr = Counters()
+    rc = lib().orc_cull(C.byref(pc), W, H, pyramid.ctypes.data, vp_select,
+                        only_status.ctypes.data if only_status is not None else None, status.ctypes.data, C.byref(ctr), threads)
+    assert rc == 0
+    return status, ctr
+
+
+def raster(pc, tg: Targets, draw_ids, threads=0):
+    ids = np.ascontiguousarray(draw_ids, np.uint32)
+    ctr = Counters()
+    rc = lib().orc_raster(C.byref(pc), tg.W, tg.H, ids.ctypes.data, ids.shape[0], tg.depth.ctypes.data, tg.ids_ref.ctypes.data,
+                          tg.ids_min.ctypes.data, tg.tie.ctypes.data, C.byref(ctr), threads)
+    assert rc == 0
+    return ctr
+
+
+def hiz(tg: Targets, threads=0):
+    rc = lib().orc_hiz(tg.W, tg.H, tg.depth.ctypes.data, tg.pyramid.ctypes.data, threads)
+    assert rc == 0
+
+
+def visible_ids(status):
+    return np.nonzero((status & STATUS_MASK) == VISIBLE)[0].astype(np.uint32)
+
+
+def frame(pc, tg: Targets, two_pass=False, threads=0):
+    """One frame as the reference records it (cull with the previous pyramid -> raster -> HiZ rebuild), or the two-pass
+    extension: A = reference pass; HiZ; B = re-test A's occlusion rejects with the current VP/pyramid; raster; HiZ."""
+    tg.clear()
+    stA, cA = cull(pc, tg.W, tg.H, tg.pyramid, 0, None, threads)
+    visA = visible_ids(stA)
+    rA = raster(pc, tg, visA, threads)
+    hiz(tg, threads)
+    out = {"statusA": stA, "visibleA": visA, "cullA": cA, "rasterA": rA}
+    if two_pass:
+        stB, cB = cull(pc, tg.W, tg.H, tg.pyramid, 1, stA, threads)
+        visB = visible_ids(stB)
+        rB = raster(pc, tg, visB, threads)
+        hiz(tg, threads)
+        out.update({"statusB": stB, "visibleB": visB, "cullB": cB, "rasterB": rB})
+    return out

@@ -1,0 +1,103 @@
+"""Small deterministic scenes shared by the CPU and GPU tests (edge cases the reference's shaders have to get right)."""
+import numpy as np
+
+from vk_gltf_viewer_b200.scene import Camera, Scene
+
+
+def grid_mesh(nu, nv, fn, flip=False):
+    """lofted grid like host/procedural.cpp: (nu+1)*(nv+1) vertices, 2*nu*nv triangles"""
+    us, vs = np.meshgrid(np.linspace(0, 1, nu + 1, dtype=np.float32), np.linspace(0, 1, nv + 1, dtype=np.float32))
+    pos = np.stack(fn(us, vs), axis=-1).reshape(-1, 3).astype(np.float32)
+    idx = []
+    for j in range(nv):
+        for i in range(nu):
+            a = j * (nu + 1) + i
+            b, c, d = a + 1, a + nu + 1, a + nu + 2
+            idx += ([a, c, b, b, c, d] if flip else [a, b, c, b, d, c])
+    return pos, np.asarray(idx, np.uint32)
+
+
+def single_triangle(double_sided=True):
+    s = Scene.new()
+    m = s.add_material(double_sided=double_sided)
+    p = s.add_primitive([[-1, -1, 0], [1, -1, 0], [0, 1, 0]], [0, 1, 2], m)
+    s.add_node(p)
+    return s.finalize()
+
+
+def fullscreen_quad(z=-5.0, size=50.0):
+    """two huge triangles far beyond the viewport: exercises the guard-band clipper and the cooperative path"""
+    s = Scene.new()
+    m = s.add_material(double_sided=True)
+    p = s.add_primitive([[-size, -size, z], [size, -size, z], [size, size, z], [-size, size, z]], [0, 1, 2, 0, 2, 3], m)
+    s.add_node(p)
+    return s.finalize()
+
+
+def ground_plane(n=24, extent=40.0, y=-1.0):
+    """tessellated floor passing under (and behind) the camera: near-plane clipping + w<=0 vertices"""
+    pos, idx = grid_mesh(n, n, lambda u, v: ((u * 2 - 1) * extent, np.full_like(u, y), (v * 2 - 1) * extent), flip=True)
+    s = Scene.new()
+    m = s.add_material(double_sided=True)
+    p = s.add_primitive(pos, idx, m)
+    s.add_node(p)
+    return s.finalize()
+
+
+def coplanar_overlap():
+    """two identical quads in the same plane from two nodes: every covered pixel is an exact depth tie"""
+    s = Scene.new()
+    m = s.add_material(double_sided=True)
+    pos, idx = grid_mesh(6, 6, lambda u, v: (u * 2 - 1, v * 2 - 1, np.zeros_like(u)))
+    p = s.add_primitive(pos, idx, m)
+    s.add_node(p)
+    s.add_node(p)
+    return s.finalize()
+
+
+def occluder_and_hidden(n_hidden=6):
+    """a big wall in front of a few small tessellated cards: second-frame HiZ must reject the cards"""
+    s = Scene.new()
+    m = s.add_material(double_sided=True)
+    wall, widx = grid_mesh(16, 16, lambda u, v: ((u * 2 - 1) * 6, (v * 2 - 1) * 6, np.zeros_like(u)))
+    pw = s.add_primitive(wall, widx, m)
+    s.add_node(pw, translation=(0, 0, 0))
+    card, cidx = grid_mesh(4, 4, lambda u, v: ((u * 2 - 1) * 0.3, (v * 2 - 1) * 0.3, np.zeros_like(u)))
+    pc = s.add_primitive(card, cidx, m)
+    rng = np.random.default_rng(7)
+    for _ in range(n_hidden):
+        x, y = rng.uniform(-2, 2, 2)
+        s.add_node(pc, translation=(float(x), float(y), -3.0 - float(rng.uniform(0, 3))))
+    # and two cards poking out beside the wall (must stay visible)
+    s.add_node(pc, translation=(7.5, 0, -2.0))
+    s.add_node(pc, translation=(-7.5, 1, -2.0))
+    return s.finalize()
+
+
+def mirrored_instances():
+    """negative-determinant node transform: facing test flips (mesh.glsl:94-98); one single-sided material"""
+    s = Scene.new()
+    pos, idx = grid_mesh(8, 8, lambda u, v: (u * 2 - 1, v * 2 - 1, 0.2 * np.sin(u * 6) * np.cos(v * 5)))
+    p = s.add_primitive(pos, idx, 0)
+    s.add_node(p, translation=(-1.2, 0, 0))
+    s.add_node(p, translation=(1.2, 0, 0), scale=(-1, 1, 1))
+    s.add_node(p, translation=(0, 1.5, -1), rotation=(0, 0.38268343, 0, 0.92387953), scale=(0.5, -0.7, 1.3))
+    return s.finalize()
+
+
+def random_soup(n_tris=400, seed=3, spread=3.0, size=0.8):
+    """random intersecting triangles at random depths (some behind the camera), double sided"""
+    rng = np.random.default_rng(seed)
+    centers = rng.uniform(-spread, spread, (n_tris, 1, 3)).astype(np.float32)
+    centers[:, :, 2] = rng.uniform(-12, 4, (n_tris, 1))
+    pos = (centers + rng.uniform(-size, size, (n_tris, 3, 3))).astype(np.float32).reshape(-1, 3)
+    idx = np.arange(n_tris * 3, dtype=np.uint32)
+    s = Scene.new()
+    m = s.add_material(double_sided=True)
+    p = s.add_primitive(pos, idx, m)
+    s.add_node(p)
+    return s.finalize()
+
+
+def camera(W, H, eye=(0, 0, 3), center=(0, 0, 0)):
+    return Camera(W, H).look_at(eye, center)

@@ -1,0 +1,176 @@
+"""GPU parity: the CUDA path (through the C ABI, include/vkv.h) against the CPU oracle on identical inputs.
+
+Bar: bit-exact visible-meshlet sets, bit-exact 64-bit visbuffer (depth bits and IDs; exact-depth ties are
+resolved lowest-id-wins by atomicMin, the oracle reports them and also carries the reference's last-writer-wins image),
+bit-exact HiZ mips.
+"""
+import numpy as np
+import pytest
+
+from tests import oracle_lib as O
+from tests import scenes as S
+from vk_gltf_viewer_b200 import abi, api
+from vk_gltf_viewer_b200.scene import Camera, Scene
+
+pytestmark = pytest.mark.gpu
+
+
+def compare_frame(r: api.Renderer, tg: O.Targets, out, two_pass, label=""):
+    """compare everything observable after one frame"""
+    visA = np.sort(r.read_visible(0))
+    assert np.array_equal(visA, out["visibleA"]), f"{label}: pass-A visible set differs: gpu {visA.size} vs oracle {out['visibleA'].size}"
+    if two_pass:
+        visB = np.sort(r.read_visible(1))
+        assert np.array_equal(visB, out["visibleB"]), f"{label}: pass-B visible set differs: gpu {visB.size} vs oracle {out['visibleB'].size}"
+    vis = r.read_visbuffer64()
+    want = tg.vis64()
+    bad = vis != want
+    assert not bad.any(), f"{label}: {int(bad.sum())} of {bad.size} visbuffer keys differ (first at {np.argwhere(bad)[0]}: gpu {vis[bad][0]:#x} oracle {want[bad][0]:#x})"
+    # the reference's own images: depth identical everywhere, IDs identical away from exact-depth ties
+    assert np.array_equal(r.read_depth().view(np.uint32), tg.depth.view(np.uint32))
+    ids = r.read_ids()
+    notie = tg.tie == 0
+    assert np.array_equal(ids[notie], tg.ids_ref[notie])
+    pyr = r.read_pyramid()
+    assert np.array_equal(pyr.view(np.uint32), tg.pyramid.view(np.uint32)), f"{label}: pyramid differs in {(pyr.view(np.uint32) != tg.pyramid.view(np.uint32)).sum()} texels"
+
+
+def run_views(scene: Scene, W, H, views, two_pass=False):
+    """render a sequence of camera positions; frame k culls against frame k-1's pyramid, on both sides"""
+    cam = Camera(W, H)
+    cam.look_at(*views[0])
+    r = api.Renderer(W, H)
+    pc_dev = r.upload_scene(scene, cam)
+    pc_host = scene.host_push_constants(cam)
+    tg = O.Targets(W, H)
+    flags = api.FRAME_STATUS | (api.FRAME_TWO_PASS if two_pass else 0)
+    summary = []
+    for k, (eye, center) in enumerate(views):
+        if k:
+            cam.look_at(eye, center)
+            r.update_camera(pc_dev, cam)
+        out = O.frame(pc_host, tg, two_pass=two_pass)
+        st = r.frame(pc_dev, flags)
+        assert st.visible_a == out["visibleA"].size
+        compare_frame(r, tg, out, two_pass, label=f"view {k}")
+        # status bytes: same classification per draw
+        n = pc_host.meshletDrawCount
+        assert np.array_equal(r.read_status(n, 0), out["statusA"] & O.STATUS_MASK)
+        if two_pass:
+            assert np.array_equal(r.read_status(n, 1), out["statusB"] & O.STATUS_MASK)
+        summary.append((st.visible_a, st.occluded_a, st.visible_b, int(tg.tie.sum())))
+    r.close()
+    return summary
+
+
+def orbit(scene, n, W, H):
+    return [scene.default_view(i, 24) for i in range(n)]
+
+
+def test_icosphere_cfg1():
+    """BASELINE config 1: 64,980-triangle icosphere, 640x480"""
+    s = Scene.icosphere(57)
+    summ = run_views(s, 640, 480, [((0, 0, 3), (0, 0, 0)), ((0.05, 0.02, 3), (0, 0, 0)), ((0.4, 0.3, 2.9), (0, 0, 0))])
+    assert summ[1][1] > 0  # second frame occlusion-culls the back of the sphere
+
+
+def test_icosphere_two_pass():
+    s = Scene.icosphere(40)
+    summ = run_views(s, 640, 480, [((0, 0, 3), (0, 0, 0)), ((1.5, 0.5, 2.5), (0, 0, 0)), ((2.9, 0.2, 0.5), (0, 0, 0))], two_pass=True)
+    assert any(v[2] > 0 for v in summ[1:])  # camera moved: pass B recovers disoccluded meshlets
+
+
+@pytest.mark.parametrize("res", [(640, 480), (1920, 1080), (333, 217)])
+def test_single_triangle(res):
+    run_views(S.single_triangle(), res[0], res[1], [((0, 0, 3), (0, 0, 0)), ((0.3, 0.1, 2.0), (0, 0, 0))])
+
+
+def test_fullscreen_quad_guard_band():
+    run_views(S.fullscreen_quad(), 640, 480, [((0, 0, 3), (0, 0, 0)), ((0, 0, 3), (0.5, 0.2, 0))])
+
+
+def test_ground_plane_near_clip():
+    run_views(S.ground_plane(), 800, 450, [((0, 0, 3), (0, -0.2, 0)), ((1, 0.5, 2), (0, -0.5, -3)), ((0, 2, 0), (0.3, -1, 0.2))])
+
+
+def test_coplanar_ties():
+    summ = run_views(S.coplanar_overlap(), 320, 240, [((0, 0, 3), (0, 0, 0)), ((0.2, 0, 3), (0, 0, 0))])
+    assert summ[0][3] > 1000  # tie pixels exist and were compared through ids_min
+
+
+def test_occlusion_wall():
+    summ = run_views(S.occluder_and_hidden(), 640, 480, [((0, 0, 8), (0, 0, 0)), ((0, 0, 8), (0, 0, 0)), ((0.5, 0, 8), (0, 0, 0))], two_pass=True)
+    assert summ[1][1] >= 6  # the hidden cards are rejected by HiZ on the second frame
+
+
+def test_mirrored_single_sided():
+    run_views(S.mirrored_instances(), 640, 480, [((0, 0, 4), (0, 0, 0)), ((2, 1, 3), (0, 0, 0)), ((0, 0, -4), (0, 0, 0))])
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_random_soup(seed):
+    run_views(S.random_soup(seed=seed), 512, 384, [((0, 0, 3), (0, 0, 0)), ((0.5, 0.2, 2), (0, 0, -2)), ((-1, 0, -3), (0, 0, -6))], two_pass=True)
+
+
+def test_atrium_cfg2_small():
+    """BASELINE config 2 geometry (int16-quantised atrium) at reduced detail; full size in test_atrium_cfg2_full"""
+    s = Scene.atrium(32)
+    run_views(s, 960, 540, orbit(s, 3, 960, 540), two_pass=True)
+
+
+def test_lattice_small():
+    s = Scene.lattice(4, 3, 4, 48)
+    run_views(s, 1280, 720, orbit(s, 3, 1280, 720), two_pass=True)
+
+
+def test_city_small():
+    s = Scene.city(6, 5, 2000)
+    run_views(s, 1024, 576, [s.default_view(i, 8) for i in range(3)], two_pass=True)
+
+
+def test_atrium_cfg2_full():
+    """BASELINE config 2 at full size: 262,144 triangles, 1920x1080"""
+    s = Scene.atrium(128)
+    assert s.counts().triangles_instanced == 262144
+    run_views(s, 1920, 1080, orbit(s, 2, 1920, 1080), two_pass=True)
+
+
+@pytest.mark.parametrize("res", [(640, 480), (1920, 1080), (3840, 2160), (1000, 1000), (1366, 768), (255, 257)])
+def test_hiz_only(res):
+    """HiZ kernels alone on a random depth image written through the visbuffer (all mips bit-exact, incl. odd sizes)"""
+    W, H = res
+    s = S.random_soup(200, seed=11, spread=4.0, size=2.5)
+    run_views(s, W, H, [((0, 0, 3), (0, 0, 0))])
+
+
+def test_no_cull_flag_matches_oracle_raster_of_all_draws():
+    s = Scene.icosphere(12)
+    W, H = 320, 240
+    cam = S.camera(W, H)
+    r = api.Renderer(W, H)
+    pc_dev = r.upload_scene(s, cam)
+    pc_host = s.host_push_constants(cam)
+    tg = O.Targets(W, H)
+    O.raster(pc_host, tg, np.arange(pc_host.meshletDrawCount, dtype=np.uint32))
+    r.frame(pc_dev, api.FRAME_NO_CULL)
+    assert np.array_equal(r.read_visbuffer64(), tg.vis64())
+    # explicit list entry point, reversed submission order: atomicMin result is order independent
+    r.clear()
+    r.raster_list(pc_dev, np.arange(pc_host.meshletDrawCount, dtype=np.uint32)[::-1].copy())
+    assert np.array_equal(r.read_visbuffer64(), tg.vis64())
+    r.close()
+
+
+def test_errors():
+    r = api.Renderer(64, 64)
+    pc = abi.PushConstants()
+    pc.meshletDrawCount = 10  # NULL buffers
+    with pytest.raises(api.VkvError):
+        r.frame(pc)
+    pc.meshletDrawCount = (1 << 25) + 1
+    with pytest.raises(api.VkvError) as e:
+        r.frame(pc)
+    assert e.value.code == -5 or e.value.code == -2
+    with pytest.raises(api.VkvError):
+        r.read_status(4, 0)
+    r.close()

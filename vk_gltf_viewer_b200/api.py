@@ -1,0 +1,234 @@
+"""Python face of libvkv.so (include/vkv.h) — the drop-in for the reference's visbuffer + HiZ passes.
+
+Names follow the reference: a `Renderer` owns what `VisibilityBufferPass` + `HiZReductionPass` own in
+application.hpp:41-83 (visbuffer, depth, pyramid), `frame()` is the region of Application::run() the library replaces
+(application.cpp:763-867, 951-1003).  Every call goes through the C ABI; there is no Python/CPU fallback.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+from ._native import vkv_lib
+
+FRAME_ONE_PASS = 0
+FRAME_TWO_PASS = 1 << 0
+FRAME_NO_HIZ = 1 << 1
+FRAME_STATUS = 1 << 2
+FRAME_TIMED = 1 << 3
+FRAME_NO_CULL = 1 << 4
+
+ST_FRUSTUM_CULLED, ST_OCCLUDED, ST_VISIBLE, ST_NOT_TESTED = 0, 1, 2, 3
+
+
+class VkvError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"vkv error {code}: {msg}")
+        self.code = code
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("draws", C.c_uint32), ("visible_a", C.c_uint32), ("occluded_a", C.c_uint32), ("visible_b", C.c_uint32), ("tested_b", C.c_uint32),
+        ("clear_ms", C.c_float), ("cull_a_ms", C.c_float), ("raster_a_ms", C.c_float), ("hiz_a_ms", C.c_float),
+        ("cull_b_ms", C.c_float), ("raster_b_ms", C.c_float), ("hiz_b_ms", C.c_float), ("total_ms", C.c_float),
+        ("kernel_launches", C.c_uint32),
+    ]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+EXPORTS = [
+    "vkv_create", "vkv_resize", "vkv_destroy", "vkv_last_error", "vkv_set_stream", "vkv_sync",
+    "vkv_upload", "vkv_update", "vkv_free",
+    "vkv_frame", "vkv_clear", "vkv_cull", "vkv_raster", "vkv_hiz", "vkv_raster_list",
+    "vkv_read_visbuffer64", "vkv_read_ids", "vkv_read_depth", "vkv_read_hiz_mip", "vkv_read_pyramid", "vkv_write_pyramid",
+    "vkv_read_visible", "vkv_read_status", "vkv_pyramid_floats",
+    "vkv_event_record", "vkv_event_elapsed", "vkv_flush_l2", "vkv_visbuffer64_ptr",
+]
+
+_bound = False
+
+
+def _lib():
+    global _bound
+    L = vkv_lib()
+    if not _bound:
+        vp, u32, u64, i = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int
+        PC = C.POINTER(abi.PushConstants)
+        L.vkv_create.argtypes = [C.POINTER(vp), i, u32, u32]
+        L.vkv_resize.argtypes = [vp, u32, u32]
+        L.vkv_destroy.argtypes = [vp]
+        L.vkv_destroy.restype = None
+        L.vkv_last_error.argtypes = [vp]
+        L.vkv_last_error.restype = C.c_char_p
+        L.vkv_set_stream.argtypes = [vp, vp]
+        L.vkv_sync.argtypes = [vp]
+        L.vkv_upload.argtypes = [vp, vp, C.c_size_t, C.POINTER(u64)]
+        L.vkv_update.argtypes = [vp, u64, vp, C.c_size_t]
+        L.vkv_free.argtypes = [vp, u64]
+        L.vkv_frame.argtypes = [vp, PC, u32, C.POINTER(Stats)]
+        L.vkv_clear.argtypes = [vp]
+        L.vkv_cull.argtypes = [vp, PC, i, u32, C.POINTER(u32)]
+        L.vkv_raster.argtypes = [vp, PC, i]
+        L.vkv_hiz.argtypes = [vp]
+        L.vkv_raster_list.argtypes = [vp, PC, vp, u32]
+        L.vkv_read_visbuffer64.argtypes = [vp, vp]
+        L.vkv_read_ids.argtypes = [vp, vp]
+        L.vkv_read_depth.argtypes = [vp, vp]
+        L.vkv_read_hiz_mip.argtypes = [vp, u32, vp, C.POINTER(u32), C.POINTER(u32)]
+        L.vkv_read_pyramid.argtypes = [vp, vp, u32]
+        L.vkv_write_pyramid.argtypes = [vp, vp, u32]
+        L.vkv_read_visible.argtypes = [vp, i, vp, u32, C.POINTER(u32)]
+        L.vkv_read_status.argtypes = [vp, i, vp, u32]
+        L.vkv_pyramid_floats.argtypes = [vp]
+        L.vkv_pyramid_floats.restype = u32
+        L.vkv_event_record.argtypes = [vp, i]
+        L.vkv_event_elapsed.argtypes = [vp, i, i, C.POINTER(C.c_float)]
+        L.vkv_flush_l2.argtypes = [vp, C.c_size_t]
+        L.vkv_visbuffer64_ptr.argtypes = [vp]
+        L.vkv_visbuffer64_ptr.restype = u64
+        _bound = True
+    return L
+
+
+class Renderer:
+    """One context per GPU (include/vkv.h)."""
+
+    def __init__(self, width: int, height: int, device: int = 0):
+        self.L = _lib()
+        self.W, self.H = int(width), int(height)
+        h = C.c_void_p()
+        rc = self.L.vkv_create(C.byref(h), device, self.W, self.H)
+        if rc:
+            raise VkvError(rc, (self.L.vkv_last_error(None) or b"").decode())
+        self.h = h
+        self.levels, self.layout, self.pyramid_floats = abi.pyramid_layout(self.W, self.H)
+        self._camera_addr = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.vkv_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc:
+            raise VkvError(rc, (self.L.vkv_last_error(self.h) or b"").decode())
+
+    # ---- memory -------------------------------------------------------------------------------------------
+    def upload(self, array) -> int:
+        a = np.ascontiguousarray(array)
+        addr = C.c_uint64()
+        self._ck(self.L.vkv_upload(self.h, a.ctypes.data, a.nbytes, C.byref(addr)))
+        return addr.value
+
+    def upload_scene(self, scene, camera) -> abi.PushConstants:
+        """World::addAsset + rebuildDrawBuffer + updateTransformBuffer + camera buffer: returns DEVICE push constants."""
+        def cb(user, host, nbytes, out):
+            return self.L.vkv_upload(self.h, host, nbytes, out)
+        pc = scene.upload(cb, None, camera)
+        self._camera_addr = pc.cameraBuffer
+        return pc
+
+    def update_camera(self, pc: abi.PushConstants, camera):
+        """Camera::updateCamera's mapped write (camera.cpp:180-193)."""
+        self._keep = camera.raw()
+        self._ck(self.L.vkv_update(self.h, pc.cameraBuffer, self._keep, len(self._keep)))
+
+    def resize(self, width, height):
+        self._ck(self.L.vkv_resize(self.h, width, height))
+        self.W, self.H = int(width), int(height)
+        self.levels, self.layout, self.pyramid_floats = abi.pyramid_layout(self.W, self.H)
+
+    # ---- frame --------------------------------------------------------------------------------------------
+    def frame(self, pc, flags=FRAME_ONE_PASS, stats=True):
+        st = Stats() if stats else None
+        self._ck(self.L.vkv_frame(self.h, C.byref(pc), flags, C.byref(st) if st is not None else None))
+        return st
+
+    def clear(self):
+        self._ck(self.L.vkv_clear(self.h))
+
+    def cull(self, pc, pass_=0, flags=0, count=True):
+        n = C.c_uint32()
+        self._ck(self.L.vkv_cull(self.h, C.byref(pc), pass_, flags, C.byref(n) if count else None))
+        return n.value
+
+    def raster(self, pc, pass_=0):
+        self._ck(self.L.vkv_raster(self.h, C.byref(pc), pass_))
+
+    def raster_list(self, pc, draw_ids):
+        ids = np.ascontiguousarray(draw_ids, np.uint32)
+        self._ck(self.L.vkv_raster_list(self.h, C.byref(pc), ids.ctypes.data, ids.shape[0]))
+
+    def hiz(self):
+        self._ck(self.L.vkv_hiz(self.h))
+
+    def sync(self):
+        self._ck(self.L.vkv_sync(self.h))
+
+    # ---- results ------------------------------------------------------------------------------------------
+    def read_visbuffer64(self):
+        out = np.empty((self.H, self.W), np.uint64)
+        self._ck(self.L.vkv_read_visbuffer64(self.h, out.ctypes.data))
+        return out
+
+    def read_ids(self):
+        out = np.empty((self.H, self.W), np.uint32)
+        self._ck(self.L.vkv_read_ids(self.h, out.ctypes.data))
+        return out
+
+    def read_depth(self):
+        out = np.empty((self.H, self.W), np.float32)
+        self._ck(self.L.vkv_read_depth(self.h, out.ctypes.data))
+        return out
+
+    def read_pyramid(self):
+        out = np.empty(self.pyramid_floats, np.float32)
+        self._ck(self.L.vkv_read_pyramid(self.h, out.ctypes.data, out.shape[0]))
+        return out
+
+    def write_pyramid(self, floats):
+        a = np.ascontiguousarray(floats, np.float32)
+        self._ck(self.L.vkv_write_pyramid(self.h, a.ctypes.data, a.shape[0]))
+
+    def read_mip(self, k):
+        off, w, h = self.layout[k]
+        out = np.empty((h, w), np.float32)
+        self._ck(self.L.vkv_read_hiz_mip(self.h, k, out.ctypes.data, None, None))
+        return out
+
+    def read_visible(self, pass_=0):
+        n = C.c_uint32()
+        self._ck(self.L.vkv_read_visible(self.h, pass_, None, 0, C.byref(n)))
+        out = np.empty(n.value, np.uint32)
+        if n.value:
+            self._ck(self.L.vkv_read_visible(self.h, pass_, out.ctypes.data, out.shape[0], C.byref(n)))
+        return out
+
+    def read_status(self, n, pass_=0):
+        out = np.empty(n, np.uint8)
+        self._ck(self.L.vkv_read_status(self.h, pass_, out.ctypes.data, n))
+        return out
+
+    # ---- measurement --------------------------------------------------------------------------------------
+    def event_record(self, slot):
+        self._ck(self.L.vkv_event_record(self.h, slot))
+
+    def event_elapsed(self, a, b) -> float:
+        ms = C.c_float()
+        self._ck(self.L.vkv_event_elapsed(self.h, a, b, C.byref(ms)))
+        return ms.value
+
+    def flush_l2(self, nbytes=256 << 20):
+        self._ck(self.L.vkv_flush_l2(self.h, nbytes))
+
+    def visbuffer64_ptr(self) -> int:
+        return self.L.vkv_visbuffer64_ptr(self.h)

@@ -1,0 +1,522 @@
+// ctx.cu — the extern "C" boundary (include/vkv.h): context, device memory, frame orchestration, readback.
+// There is no CPU fallback anywhere in this file: without a CUDA device vkv_create fails with VKV_ERR_NO_DEVICE.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+
+#include "kernels.cuh"
+
+struct vkv_ctx {
+	int device = 0;
+	int num_sms = 148;
+	cudaStream_t own_stream = nullptr;
+	cudaStream_t stream = nullptr;
+	uint32_t W = 0, H = 0;
+	unsigned long long* vis = nullptr;
+	float* pyramid = nullptr;
+	PyramidDesc pyr{};
+	uint32_t exact_levels = 0;
+	// per-draw buffers (grow-only)
+	uint32_t cap_draws = 0;
+	uint32_t* list_visible[2] = {nullptr, nullptr};
+	uint32_t* list_occluded[2] = {nullptr, nullptr};
+	uint32_t* list_tmp = nullptr;
+	uint32_t* tmp_count = nullptr;
+	uint8_t* status[2] = {nullptr, nullptr};
+	bool status_valid[2] = {false, false};
+	FrameCounters* counters = nullptr;
+	FrameCounters* h_counters = nullptr; // pinned
+	// readback scratch
+	uint32_t* tmp_ids = nullptr;
+	float* tmp_depth = nullptr;
+	void* flush_buf = nullptr;
+	size_t flush_bytes = 0;
+	cudaEvent_t events[16] = {};
+	cudaEvent_t stage_ev[9] = {};
+	std::map<uint64_t, size_t> allocs;
+	std::mutex mtx;
+	std::string err;
+};
+
+namespace {
+
+thread_local std::string g_create_err;
+
+int fail(vkv_ctx* c, int code, const char* fmt, ...) {
+	char buf[512];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof(buf), fmt, ap);
+	va_end(ap);
+	if (c) c->err = buf; else g_create_err = buf;
+	return code;
+}
+
+#define CK(call)                                                                                                      \
+	do {                                                                                                              \
+		cudaError_t e_ = (call);                                                                                      \
+		if (e_ != cudaSuccess) return fail(c, e_ == cudaErrorMemoryAllocation ? VKV_ERR_OOM : VKV_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+	} while (0)
+
+void fill_pyramid_desc(uint32_t W, uint32_t H, PyramidDesc& d, uint32_t& exact) {
+	memset(&d, 0, sizeof(d));
+	d.levels = vkv_mip_levels(W, H);
+	if (d.levels > 16) d.levels = 16;
+	uint32_t off = 0;
+	for (uint32_t k = 0; k < d.levels; ++k) {
+		d.w[k] = vkv_mip_extent(W, k);
+		d.h[k] = vkv_mip_extent(H, k);
+		d.off[k] = off;
+		off += d.w[k] * d.h[k];
+	}
+	d.off[d.levels] = off;
+	d.total = off;
+	// leading mips whose source is exactly 2x their dispatch size (application.cpp:965: levelSize = res >> i)
+	exact = 0;
+	for (uint32_t k = 0; k < d.levels && k < 4; ++k) {
+		const uint32_t sw = k == 0 ? W : d.w[k - 1], sh = k == 0 ? H : d.h[k - 1];
+		const uint32_t dw = W >> (k + 1), dh = H >> (k + 1);
+		if (dw == 0 || dh == 0 || sw != 2 * dw || sh != 2 * dh || dw != d.w[k] || dh != d.h[k]) break;
+		exact = k + 1;
+	}
+}
+
+int free_targets(vkv_ctx* c) {
+	if (c->vis) cudaFree(c->vis);
+	if (c->pyramid) cudaFree(c->pyramid);
+	if (c->tmp_ids) cudaFree(c->tmp_ids);
+	if (c->tmp_depth) cudaFree(c->tmp_depth);
+	c->vis = nullptr; c->pyramid = nullptr; c->tmp_ids = nullptr; c->tmp_depth = nullptr;
+	return 0;
+}
+
+int alloc_targets(vkv_ctx* c, uint32_t W, uint32_t H) {
+	if (W < 2 || H < 2 || W > 32768 || H > 32768) return fail(c, VKV_ERR_INVALID, "resolution %ux%u out of range", W, H);
+	free_targets(c);
+	c->W = W; c->H = H;
+	fill_pyramid_desc(W, H, c->pyr, c->exact_levels);
+	CK(cudaMalloc(&c->vis, (size_t)W * H * 8));
+	CK(cudaMalloc(&c->pyramid, (size_t)(c->pyr.total ? c->pyr.total : 1) * 4));
+	// initial contents: visbuffer cleared; pyramid 0.0 everywhere = "far" (nothing occludes)
+	CK(launch_fill64(c->vis, (size_t)W * H, VKV_VIS64_CLEAR, c->num_sms, c->stream));
+	CK(cudaMemsetAsync(c->pyramid, 0, (size_t)(c->pyr.total ? c->pyr.total : 1) * 4, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	return VKV_OK;
+}
+
+int ensure_draws(vkv_ctx* c, uint32_t n) {
+	if (n > VKV_MAX_MESHLET_DRAWS) return fail(c, VKV_ERR_LIMIT, "meshletDrawCount %u exceeds 2^25 (visbuffer.h.glsl:15-17)", n);
+	if (n <= c->cap_draws) return VKV_OK;
+	CK(cudaStreamSynchronize(c->stream));
+	uint32_t cap = n + n / 8 + 1024;
+	for (int i = 0; i < 2; ++i) {
+		if (c->list_visible[i]) cudaFree(c->list_visible[i]);
+		if (c->list_occluded[i]) cudaFree(c->list_occluded[i]);
+		if (c->status[i]) cudaFree(c->status[i]);
+		CK(cudaMalloc(&c->list_visible[i], (size_t)cap * 4));
+		CK(cudaMalloc(&c->list_occluded[i], (size_t)cap * 4));
+		CK(cudaMalloc(&c->status[i], (size_t)cap));
+		c->status_valid[i] = false;
+	}
+	if (c->list_tmp) cudaFree(c->list_tmp);
+	CK(cudaMalloc(&c->list_tmp, (size_t)cap * 4));
+	c->cap_draws = cap;
+	return VKV_OK;
+}
+
+CullParams make_cull(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, int pass, uint32_t flags) {
+	CullParams p{};
+	p.draws = (const vkv_MeshletDraw*)pc->drawBuffer;
+	p.transforms = (const float*)pc->transformBuffer;
+	p.primitives = (const vkv_Primitive*)pc->primitiveBuffer;
+	p.camera = (const vkv_Camera*)pc->cameraBuffer;
+	p.pyramid = c->pyramid;
+	p.pyr = c->pyr;
+	p.n = pc->meshletDrawCount;
+	p.in_list = pass == 0 ? nullptr : c->list_occluded[0];
+	p.in_count = pass == 0 ? nullptr : &c->counters->occluded[0];
+	p.out_visible = c->list_visible[pass];
+	p.out_occluded = c->list_occluded[pass];
+	p.counters = c->counters;
+	p.status = (flags & VKV_FRAME_STATUS) ? c->status[pass] : nullptr;
+	p.pass = pass;
+	p.vp_select = pass;
+	p.skip_hiz = 0;
+	return p;
+}
+
+RasterParams make_raster(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, const uint32_t* list, const uint32_t* count, uint32_t* work) {
+	RasterParams r{};
+	r.draws = (const vkv_MeshletDraw*)pc->drawBuffer;
+	r.transforms = (const float*)pc->transformBuffer;
+	r.primitives = (const vkv_Primitive*)pc->primitiveBuffer;
+	r.materials = (const vkv_Material*)pc->materialBuffer;
+	r.camera = (const vkv_Camera*)pc->cameraBuffer;
+	r.list = list; r.count = count; r.work = work;
+	r.vis = c->vis; r.W = c->W; r.H = c->H;
+	return r;
+}
+
+HizParams make_hiz(vkv_ctx* c) {
+	HizParams h{};
+	h.vis = c->vis; h.pyramid = c->pyramid; h.pyr = c->pyr; h.W = c->W; h.H = c->H; h.exact_levels = c->exact_levels;
+	return h;
+}
+
+int check_pc(vkv_ctx* c, const vkv_VisbufferPushConstants* pc) {
+	if (!c) return VKV_ERR_INVALID;
+	if (!pc) return fail(c, VKV_ERR_INVALID, "push constants are NULL");
+	if (pc->meshletDrawCount && (!pc->drawBuffer || !pc->transformBuffer || !pc->primitiveBuffer || !pc->cameraBuffer || !pc->materialBuffer))
+		return fail(c, VKV_ERR_INVALID, "push constants hold a NULL buffer address");
+	return ensure_draws(c, pc->meshletDrawCount);
+}
+
+} // namespace
+
+extern "C" {
+
+const char* vkv_last_error(vkv_ctx* c) { return c ? c->err.c_str() : g_create_err.c_str(); }
+
+int vkv_create(vkv_ctx** out, int cuda_device, uint32_t width, uint32_t height) {
+	if (!out) return VKV_ERR_INVALID;
+	*out = nullptr;
+	vkv_ctx* c = nullptr;
+	int ndev = 0;
+	cudaError_t e = cudaGetDeviceCount(&ndev);
+	if (e != cudaSuccess || ndev == 0)
+		return fail(nullptr, VKV_ERR_NO_DEVICE, "no CUDA device (%s); libvkv has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "count=0");
+	if (cuda_device < 0 || cuda_device >= ndev) return fail(nullptr, VKV_ERR_INVALID, "cuda_device %d out of range [0,%d)", cuda_device, ndev);
+	c = new vkv_ctx();
+	c->device = cuda_device;
+	auto bail = [&](int rc) { g_create_err = c->err; vkv_destroy(c); return rc; };
+	if (cudaSetDevice(cuda_device) != cudaSuccess) { c->err = "cudaSetDevice failed"; return bail(VKV_ERR_CUDA); }
+	cudaDeviceProp prop;
+	if (cudaGetDeviceProperties(&prop, cuda_device) == cudaSuccess) c->num_sms = prop.multiProcessorCount;
+	if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { c->err = "cudaStreamCreate failed"; return bail(VKV_ERR_CUDA); }
+	c->stream = c->own_stream;
+	for (auto& ev : c->events) cudaEventCreate(&ev);
+	for (auto& ev : c->stage_ev) cudaEventCreate(&ev);
+	if (cudaMalloc(&c->counters, sizeof(FrameCounters)) != cudaSuccess || cudaMalloc(&c->tmp_count, 256) != cudaSuccess ||
+	    cudaMallocHost(&c->h_counters, sizeof(FrameCounters)) != cudaSuccess) {
+		c->err = "allocating counters failed";
+		return bail(VKV_ERR_OOM);
+	}
+	cudaMemset(c->counters, 0, sizeof(FrameCounters));
+	int rc = alloc_targets(c, width, height);
+	if (rc != VKV_OK) return bail(rc);
+	*out = c;
+	return VKV_OK;
+}
+
+int vkv_resize(vkv_ctx* c, uint32_t width, uint32_t height) {
+	if (!c) return VKV_ERR_INVALID;
+	CK(cudaSetDevice(c->device));
+	CK(cudaStreamSynchronize(c->stream));
+	return alloc_targets(c, width, height);
+}
+
+void vkv_destroy(vkv_ctx* c) {
+	if (!c) return;
+	cudaSetDevice(c->device);
+	if (c->stream) cudaStreamSynchronize(c->stream);
+	free_targets(c);
+	for (int i = 0; i < 2; ++i) {
+		if (c->list_visible[i]) cudaFree(c->list_visible[i]);
+		if (c->list_occluded[i]) cudaFree(c->list_occluded[i]);
+		if (c->status[i]) cudaFree(c->status[i]);
+	}
+	if (c->list_tmp) cudaFree(c->list_tmp);
+	if (c->tmp_count) cudaFree(c->tmp_count);
+	if (c->counters) cudaFree(c->counters);
+	if (c->h_counters) cudaFreeHost(c->h_counters);
+	if (c->flush_buf) cudaFree(c->flush_buf);
+	for (auto& kv : c->allocs) cudaFree((void*)(uintptr_t)kv.first);
+	for (auto& ev : c->events) if (ev) cudaEventDestroy(ev);
+	for (auto& ev : c->stage_ev) if (ev) cudaEventDestroy(ev);
+	if (c->own_stream) cudaStreamDestroy(c->own_stream);
+	delete c;
+}
+
+int vkv_set_stream(vkv_ctx* c, void* s) {
+	if (!c) return VKV_ERR_INVALID;
+	CK(cudaStreamSynchronize(c->stream));
+	c->stream = s ? (cudaStream_t)s : c->own_stream;
+	return VKV_OK;
+}
+
+int vkv_sync(vkv_ctx* c) {
+	if (!c) return VKV_ERR_INVALID;
+	CK(cudaSetDevice(c->device));
+	CK(cudaStreamSynchronize(c->stream));
+	return VKV_OK;
+}
+
+int vkv_upload(vkv_ctx* c, const void* host, size_t bytes, uint64_t* dev_addr) {
+	if (!c || !dev_addr || (!host && bytes)) return c ? fail(c, VKV_ERR_INVALID, "vkv_upload: NULL argument") : VKV_ERR_INVALID;
+	std::lock_guard<std::mutex> lock(c->mtx);
+	CK(cudaSetDevice(c->device));
+	void* d = nullptr;
+	// pad so that 16-byte vector loads over the tail of any array stay inside the allocation
+	const size_t padded = ((bytes ? bytes : 1) + 255) & ~(size_t)255;
+	CK(cudaMalloc(&d, padded));
+	if (bytes) CK(cudaMemcpy(d, host, bytes, cudaMemcpyHostToDevice));
+	c->allocs[(uint64_t)(uintptr_t)d] = bytes;
+	*dev_addr = (uint64_t)(uintptr_t)d;
+	return VKV_OK;
+}
+
+int vkv_update(vkv_ctx* c, uint64_t dev_addr, const void* host, size_t bytes) {
+	if (!c || !host) return VKV_ERR_INVALID;
+	{
+		std::lock_guard<std::mutex> lock(c->mtx);
+		auto it = c->allocs.upper_bound(dev_addr);
+		if (it == c->allocs.begin()) return fail(c, VKV_ERR_INVALID, "vkv_update: unknown address");
+		--it;
+		if (dev_addr + bytes > it->first + it->second) return fail(c, VKV_ERR_INVALID, "vkv_update: range exceeds the allocation");
+	}
+	CK(cudaSetDevice(c->device));
+	CK(cudaMemcpyAsync((void*)(uintptr_t)dev_addr, host, bytes, cudaMemcpyHostToDevice, c->stream));
+	return VKV_OK;
+}
+
+int vkv_free(vkv_ctx* c, uint64_t dev_addr) {
+	if (!c) return VKV_ERR_INVALID;
+	std::lock_guard<std::mutex> lock(c->mtx);
+	auto it = c->allocs.find(dev_addr);
+	if (it == c->allocs.end()) return fail(c, VKV_ERR_INVALID, "vkv_free: unknown address");
+	CK(cudaSetDevice(c->device));
+	CK(cudaStreamSynchronize(c->stream));
+	CK(cudaFree((void*)(uintptr_t)dev_addr));
+	c->allocs.erase(it);
+	return VKV_OK;
+}
+
+int vkv_clear(vkv_ctx* c) {
+	if (!c) return VKV_ERR_INVALID;
+	CK(cudaSetDevice(c->device));
+	CK(launch_fill64(c->vis, (size_t)c->W * c->H, VKV_VIS64_CLEAR, c->num_sms, c->stream)); // application.cpp:782,807
+	return VKV_OK;
+}
+
+int vkv_cull(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, int pass, uint32_t flags, uint32_t* n_visible) {
+	int rc = check_pc(c, pc);
+	if (rc) return rc;
+	if (pass < 0 || pass > 1) return fail(c, VKV_ERR_INVALID, "pass must be 0 or 1");
+	CK(cudaSetDevice(c->device));
+	CK(cudaMemsetAsync(&c->counters->visible[pass], 0, 4, c->stream));
+	CK(cudaMemsetAsync(&c->counters->occluded[pass], 0, 4, c->stream));
+	CullParams p = make_cull(c, pc, pass, flags);
+	if (p.status) CK(cudaMemsetAsync(p.status, VKV_ST_NOT_TESTED, pc->meshletDrawCount, c->stream));
+	c->status_valid[pass] = p.status != nullptr;
+	if (pc->meshletDrawCount) CK(launch_cull(p, c->num_sms, c->stream));
+	if (n_visible) {
+		CK(cudaMemcpyAsync(c->h_counters, c->counters, sizeof(FrameCounters), cudaMemcpyDeviceToHost, c->stream));
+		CK(cudaStreamSynchronize(c->stream));
+		*n_visible = c->h_counters->visible[pass];
+	}
+	return VKV_OK;
+}
+
+int vkv_raster(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, int pass) {
+	int rc = check_pc(c, pc);
+	if (rc) return rc;
+	if (pass < 0 || pass > 1) return fail(c, VKV_ERR_INVALID, "pass must be 0 or 1");
+	CK(cudaSetDevice(c->device));
+	CK(cudaMemsetAsync(&c->counters->work[pass], 0, 4, c->stream));
+	CK(launch_raster(make_raster(c, pc, c->list_visible[pass], &c->counters->visible[pass], &c->counters->work[pass]), c->num_sms, c->stream));
+	return VKV_OK;
+}
+
+int vkv_raster_list(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, const uint32_t* draw_ids, uint32_t n) {
+	int rc = check_pc(c, pc);
+	if (rc) return rc;
+	if (n > c->cap_draws) { rc = ensure_draws(c, n); if (rc) return rc; }
+	CK(cudaSetDevice(c->device));
+	uint32_t hdr[2] = {n, 0};
+	CK(cudaMemcpyAsync(c->tmp_count, hdr, 8, cudaMemcpyHostToDevice, c->stream));
+	if (n) CK(cudaMemcpyAsync(c->list_tmp, draw_ids, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+	CK(launch_raster(make_raster(c, pc, c->list_tmp, c->tmp_count, c->tmp_count + 1), c->num_sms, c->stream));
+	CK(cudaStreamSynchronize(c->stream)); // draw_ids / hdr are borrowed
+	return VKV_OK;
+}
+
+int vkv_hiz(vkv_ctx* c) {
+	if (!c) return VKV_ERR_INVALID;
+	CK(cudaSetDevice(c->device));
+	CK(launch_hiz(make_hiz(c), c->num_sms, c->stream, nullptr));
+	return VKV_OK;
+}
+
+int vkv_frame(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, uint32_t flags, vkv_stats* out) {
+	int rc = check_pc(c, pc);
+	if (rc) return rc;
+	CK(cudaSetDevice(c->device));
+	cudaStream_t s = c->stream;
+	const bool timed = (flags & VKV_FRAME_TIMED) && out;
+	const bool two = (flags & VKV_FRAME_TWO_PASS) != 0;
+	const uint32_t N = pc->meshletDrawCount;
+	int launches = 0, ev = 0;
+	auto mark = [&]() { if (timed) cudaEventRecord(c->stage_ev[ev], s); ++ev; };
+	CK(cudaMemsetAsync(c->counters, 0, sizeof(FrameCounters), s));
+	mark(); // 0
+	CK(launch_fill64(c->vis, (size_t)c->W * c->H, VKV_VIS64_CLEAR, c->num_sms, s)); ++launches;
+	mark(); // 1
+	if (flags & VKV_FRAME_NO_CULL) {
+		CK(launch_iota(c->list_visible[0], N, &c->counters->visible[0], c->num_sms, s)); ++launches;
+		c->status_valid[0] = false;
+	} else {
+		CullParams p = make_cull(c, pc, 0, flags);
+		if (p.status) CK(cudaMemsetAsync(p.status, VKV_ST_NOT_TESTED, N, s));
+		c->status_valid[0] = p.status != nullptr;
+		if (N) { CK(launch_cull(p, c->num_sms, s)); ++launches; }
+	}
+	mark(); // 2
+	CK(launch_raster(make_raster(c, pc, c->list_visible[0], &c->counters->visible[0], &c->counters->work[0]), c->num_sms, s)); ++launches;
+	mark(); // 3
+	if (!(flags & VKV_FRAME_NO_HIZ)) CK(launch_hiz(make_hiz(c), c->num_sms, s, &launches));
+	mark(); // 4
+	if (two && !(flags & VKV_FRAME_NO_CULL)) {
+		CullParams p = make_cull(c, pc, 1, flags);
+		if (p.status) CK(cudaMemsetAsync(p.status, VKV_ST_NOT_TESTED, N, s));
+		c->status_valid[1] = p.status != nullptr;
+		if (N) { CK(launch_cull(p, c->num_sms, s)); ++launches; }
+		mark(); // 5
+		CK(launch_raster(make_raster(c, pc, c->list_visible[1], &c->counters->visible[1], &c->counters->work[1]), c->num_sms, s)); ++launches;
+		mark(); // 6
+		if (!(flags & VKV_FRAME_NO_HIZ)) CK(launch_hiz(make_hiz(c), c->num_sms, s, &launches));
+		mark(); // 7
+	}
+	if (out) {
+		memset(out, 0, sizeof(*out));
+		CK(cudaMemcpyAsync(c->h_counters, c->counters, sizeof(FrameCounters), cudaMemcpyDeviceToHost, s));
+		CK(cudaStreamSynchronize(s));
+		out->draws = N;
+		out->visible_a = c->h_counters->visible[0];
+		out->occluded_a = c->h_counters->occluded[0];
+		out->visible_b = c->h_counters->visible[1];
+		out->tested_b = two ? c->h_counters->occluded[0] : 0;
+		out->kernel_launches = (uint32_t)launches;
+		if (timed) {
+			auto el = [&](int a, int b) { float ms = 0; cudaEventElapsedTime(&ms, c->stage_ev[a], c->stage_ev[b]); return ms; };
+			out->clear_ms = el(0, 1); out->cull_a_ms = el(1, 2); out->raster_a_ms = el(2, 3); out->hiz_a_ms = el(3, 4);
+			if (two && !(flags & VKV_FRAME_NO_CULL)) { out->cull_b_ms = el(4, 5); out->raster_b_ms = el(5, 6); out->hiz_b_ms = el(6, 7); out->total_ms = el(0, 7); }
+			else out->total_ms = el(0, 4);
+		}
+	}
+	return VKV_OK;
+}
+
+int vkv_read_visbuffer64(vkv_ctx* c, uint64_t* host) {
+	if (!c || !host) return VKV_ERR_INVALID;
+	CK(cudaSetDevice(c->device));
+	CK(cudaMemcpyAsync(host, c->vis, (size_t)c->W * c->H * 8, cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	return VKV_OK;
+}
+
+static int read_split(vkv_ctx* c, uint32_t* ids, float* depth) {
+	const size_t n = (size_t)c->W * c->H;
+	CK(cudaSetDevice(c->device));
+	if (!c->tmp_ids) CK(cudaMalloc(&c->tmp_ids, n * 4));
+	if (!c->tmp_depth) CK(cudaMalloc(&c->tmp_depth, n * 4));
+	CK(launch_split_vis(c->vis, n, ids ? c->tmp_ids : nullptr, depth ? c->tmp_depth : nullptr, c->num_sms, c->stream));
+	if (ids) CK(cudaMemcpyAsync(ids, c->tmp_ids, n * 4, cudaMemcpyDeviceToHost, c->stream));
+	if (depth) CK(cudaMemcpyAsync(depth, c->tmp_depth, n * 4, cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	return VKV_OK;
+}
+int vkv_read_ids(vkv_ctx* c, uint32_t* host) { return (c && host) ? read_split(c, host, nullptr) : VKV_ERR_INVALID; }
+int vkv_read_depth(vkv_ctx* c, float* host) { return (c && host) ? read_split(c, nullptr, host) : VKV_ERR_INVALID; }
+
+uint32_t vkv_pyramid_floats(vkv_ctx* c) { return c ? c->pyr.total : 0; }
+
+int vkv_read_hiz_mip(vkv_ctx* c, uint32_t mip, float* host, uint32_t* w, uint32_t* h) {
+	if (!c) return VKV_ERR_INVALID;
+	if (mip >= c->pyr.levels) return fail(c, VKV_ERR_INVALID, "mip %u >= %u levels", mip, c->pyr.levels);
+	if (w) *w = c->pyr.w[mip];
+	if (h) *h = c->pyr.h[mip];
+	if (host) {
+		CK(cudaSetDevice(c->device));
+		CK(cudaMemcpyAsync(host, c->pyramid + c->pyr.off[mip], (size_t)c->pyr.w[mip] * c->pyr.h[mip] * 4, cudaMemcpyDeviceToHost, c->stream));
+		CK(cudaStreamSynchronize(c->stream));
+	}
+	return VKV_OK;
+}
+
+int vkv_read_pyramid(vkv_ctx* c, float* host, uint32_t floats) {
+	if (!c || !host) return VKV_ERR_INVALID;
+	if (floats != c->pyr.total) return fail(c, VKV_ERR_INVALID, "pyramid holds %u floats, caller passed %u", c->pyr.total, floats);
+	CK(cudaSetDevice(c->device));
+	CK(cudaMemcpyAsync(host, c->pyramid, (size_t)floats * 4, cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	return VKV_OK;
+}
+
+int vkv_write_pyramid(vkv_ctx* c, const float* host, uint32_t floats) {
+	if (!c || !host) return VKV_ERR_INVALID;
+	if (floats != c->pyr.total) return fail(c, VKV_ERR_INVALID, "pyramid holds %u floats, caller passed %u", c->pyr.total, floats);
+	CK(cudaSetDevice(c->device));
+	CK(cudaMemcpyAsync(c->pyramid, host, (size_t)floats * 4, cudaMemcpyHostToDevice, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	return VKV_OK;
+}
+
+int vkv_read_visible(vkv_ctx* c, int pass, uint32_t* draw_ids, uint32_t cap, uint32_t* n) {
+	if (!c || pass < 0 || pass > 1 || !n) return VKV_ERR_INVALID;
+	CK(cudaSetDevice(c->device));
+	CK(cudaMemcpyAsync(c->h_counters, c->counters, sizeof(FrameCounters), cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	const uint32_t cnt = c->h_counters->visible[pass];
+	*n = cnt;
+	if (draw_ids && cnt) {
+		if (cap < cnt) return fail(c, VKV_ERR_INVALID, "vkv_read_visible: capacity %u < %u survivors", cap, cnt);
+		CK(cudaMemcpyAsync(draw_ids, c->list_visible[pass], (size_t)cnt * 4, cudaMemcpyDeviceToHost, c->stream));
+		CK(cudaStreamSynchronize(c->stream));
+	}
+	return VKV_OK;
+}
+
+int vkv_read_status(vkv_ctx* c, int pass, uint8_t* status, uint32_t n) {
+	if (!c || pass < 0 || pass > 1 || !status) return VKV_ERR_INVALID;
+	if (!c->status_valid[pass]) return fail(c, VKV_ERR_INVALID, "status of pass %d was not recorded (pass VKV_FRAME_STATUS)", pass);
+	if (n > c->cap_draws) return fail(c, VKV_ERR_INVALID, "n exceeds the draw capacity");
+	CK(cudaSetDevice(c->device));
+	CK(cudaMemcpyAsync(status, c->status[pass], n, cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	return VKV_OK;
+}
+
+int vkv_event_record(vkv_ctx* c, int slot) {
+	if (!c || slot < 0 || slot >= 16) return VKV_ERR_INVALID;
+	CK(cudaSetDevice(c->device));
+	CK(cudaEventRecord(c->events[slot], c->stream));
+	return VKV_OK;
+}
+
+int vkv_event_elapsed(vkv_ctx* c, int from, int to, float* ms) {
+	if (!c || !ms || from < 0 || from >= 16 || to < 0 || to >= 16) return VKV_ERR_INVALID;
+	CK(cudaSetDevice(c->device));
+	CK(cudaEventSynchronize(c->events[to]));
+	CK(cudaEventElapsedTime(ms, c->events[from], c->events[to]));
+	return VKV_OK;
+}
+
+int vkv_flush_l2(vkv_ctx* c, size_t bytes) {
+	if (!c) return VKV_ERR_INVALID;
+	CK(cudaSetDevice(c->device));
+	if (bytes > c->flush_bytes) {
+		if (c->flush_buf) cudaFree(c->flush_buf);
+		c->flush_buf = nullptr; c->flush_bytes = 0;
+		CK(cudaMalloc(&c->flush_buf, bytes));
+		c->flush_bytes = bytes;
+	}
+	CK(launch_fill32((uint32_t*)c->flush_buf, bytes / 4, 0u, c->num_sms, c->stream));
+	return VKV_OK;
+}
+
+uint64_t vkv_visbuffer64_ptr(vkv_ctx* c) { return c ? (uint64_t)(uintptr_t)c->vis : 0; }
+
+} // extern "C"

@@ -1,0 +1,51 @@
+// kernels.cuh — parameter blocks and launchers of the sm_100a kernels (one .cu per stage).
+#pragma once
+#include "common.cuh"
+
+struct CullParams {
+	const vkv_MeshletDraw* draws;
+	const float* transforms;
+	const vkv_Primitive* primitives;
+	const vkv_Camera* camera;
+	const float* pyramid;
+	PyramidDesc pyr;
+	uint32_t n;                  // meshletDrawCount (upper bound of the work size)
+	const uint32_t* in_list;     // pass B: the draws pass A rejected by occlusion; NULL = all draws [0,n)
+	const uint32_t* in_count;    // device count of in_list
+	uint32_t* out_visible;
+	uint32_t* out_occluded;      // may be NULL
+	FrameCounters* counters;
+	uint8_t* status;             // may be NULL
+	int pass;                    // 0 = A, 1 = B
+	int vp_select;               // 0 = prevOcclusionViewProjection (reference), 1 = viewProjection (pass B)
+	int skip_hiz;                // frustum only
+};
+
+struct RasterParams {
+	const vkv_MeshletDraw* draws;
+	const float* transforms;
+	const vkv_Primitive* primitives;
+	const vkv_Material* materials;
+	const vkv_Camera* camera;
+	const uint32_t* list;        // MeshletDraw indices to rasterise
+	const uint32_t* count;       // device count
+	uint32_t* work;              // work-stealing cursor (zeroed per launch)
+	unsigned long long* vis;     // W*H 64-bit keys
+	uint32_t W, H;
+};
+
+struct HizParams {
+	const unsigned long long* vis;
+	float* pyramid;
+	PyramidDesc pyr;
+	uint32_t W, H;
+	uint32_t exact_levels;       // leading mips whose source is exactly 2x (handled by the tiled kernel), <= 4
+};
+
+cudaError_t launch_cull(const CullParams& p, int num_sms, cudaStream_t stream);
+cudaError_t launch_iota(uint32_t* out, uint32_t n, uint32_t* count, int num_sms, cudaStream_t stream);
+cudaError_t launch_raster(const RasterParams& p, int num_sms, cudaStream_t stream);
+cudaError_t launch_hiz(const HizParams& p, int num_sms, cudaStream_t stream, int* launches);
+cudaError_t launch_fill64(unsigned long long* dst, size_t n, unsigned long long value, int num_sms, cudaStream_t stream);
+cudaError_t launch_fill32(uint32_t* dst, size_t n, uint32_t value, int num_sms, cudaStream_t stream);
+cudaError_t launch_split_vis(const unsigned long long* vis, size_t n, uint32_t* ids, float* depth, int num_sms, cudaStream_t stream);

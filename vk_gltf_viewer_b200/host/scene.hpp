@@ -1,0 +1,48 @@
+// scene.hpp — host-side scene container: what World + AssetLoadTask hold in the reference
+// (world.hpp / assets.hpp), reduced to the buffers the geometry path consumes.
+#pragma once
+#include "../../include/vkv_host.h"
+#include "hmath.hpp"
+
+#include <string>
+#include <vector>
+
+namespace vkvh {
+
+struct MeshletRec { uint32_t vertex_offset, triangle_offset, vertex_count, triangle_count; };
+
+struct PrimitiveData {
+	std::vector<vkv_Vertex> vertices;
+	std::vector<uint32_t> meshletVertices;   // Primitive.vertexIndexBuffer
+	std::vector<uint8_t> meshletTriangles;   // Primitive.primitiveIndexBuffer
+	std::vector<vkv_Meshlet> meshlets;       // Primitive.meshletBuffer
+	vkv_Primitive header{};                  // addresses filled per address space
+	uint64_t triangles = 0;
+};
+
+struct Node {
+	int32_t parent = -1;
+	int32_t primitive = -1;
+	float t[3] = {0, 0, 0}, r[4] = {0, 0, 0, 1}, s[3] = {1, 1, 1};
+	std::vector<int32_t> children;
+};
+
+void build_meshlets_builtin(const std::vector<vkv_Vertex>& vertices, const std::vector<uint32_t>& indices,
+                            std::vector<MeshletRec>& meshlets, std::vector<uint32_t>& meshletVertices,
+                            std::vector<uint8_t>& meshletTriangles);
+
+} // namespace vkvh
+
+struct vkvh_scene {
+	std::vector<vkvh::PrimitiveData> primitives;
+	std::vector<vkv_Material> materials;
+	std::vector<vkvh::Node> nodes;
+	std::vector<int32_t> roots;
+	std::vector<vkv_MeshletDraw> draws;
+	std::vector<float> transforms; // 16 per mesh node, traversal order
+	std::vector<vkv_Primitive> hostPrimitives;
+	bool finalized = false;
+	// default-view hints set by the procedural generators
+	int kind = 0; // 0 custom, 1 icosphere, 2 atrium, 3 lattice, 4 city
+	float boundsMin[3] = {0, 0, 0}, boundsMax[3] = {0, 0, 0};
+};
