@@ -1,0 +1,278 @@
+"""The CPU oracle: pinned against the reference's own compilable code where that exists (oracle/_ref), and against
+domain properties elsewhere (fill-rule watertightness, sampler rule, exact-2x equivalence, tie bookkeeping, clipping)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from tests import oracle_lib as O
+from tests import scenes as S
+from vk_gltf_viewer_b200 import abi
+from vk_gltf_viewer_b200.scene import Camera, Scene
+
+
+# ------------------------------------------------------------------------------------------ reference-pinned
+def test_frustum_test_matches_reference_culling_h(ref_shim):
+    """isAabbInFrustum + getWorldSpaceAabbExtent (culling.h.glsl:8-29, compiled from the reference) vs the oracle's
+    frustum stage on random meshlet AABBs / transforms / cameras: identical classification for every draw."""
+    rng = np.random.default_rng(42)
+    ref_shim.ref_is_aabb_in_frustum.restype = C.c_int
+    mism = ext_mism = 0
+    total = 0
+    for trial in range(6):
+        s = Scene.new()
+        pos, idx = S.grid_mesh(24, 24, lambda u, v: (u * 8 - 4, np.sin(u * 5 + trial) * np.cos(v * 4), v * 8 - 4))
+        p = s.add_primitive(pos, idx)
+        for _ in range(12):
+            q = rng.normal(size=4); q /= np.linalg.norm(q)
+            s.add_node(p, translation=rng.uniform(-15, 15, 3), rotation=q, scale=rng.uniform(0.2, 3, 3) * rng.choice([-1, 1], 3))
+        s.finalize()
+        W, H = 640, 480
+        cam = Camera(W, H).look_at(rng.uniform(-10, 10, 3), rng.uniform(-3, 3, 3))
+        pc = s.host_push_constants(cam)
+        tg = O.Targets(W, H)
+        status, _ = O.cull(pc, W, H, tg.pyramid)  # empty pyramid: only the frustum can reject
+        draws, T, ml = s.draws(), s.transforms(), s.primitive(0)["meshlets"]
+        fr = np.ctypeslib.as_array(cam.c.frustum).reshape(-1).astype(np.float32)
+        frp = fr.ctypes.data_as(C.POINTER(C.c_float))
+        for i, d in enumerate(draws):
+            m = ml[d["meshletIndex"]]
+            t = np.ascontiguousarray(T[d["transformIndex"]].reshape(-1))
+            e = np.ascontiguousarray(m["aabbExtents"]); c = np.ascontiguousarray(m["aabbCenter"])
+            we = (C.c_float * 3)(); wc = (C.c_float * 3)()
+            ref_shim.ref_world_aabb_extent(e.ctypes.data_as(C.POINTER(C.c_float)), t.ctypes.data_as(C.POINTER(C.c_float)), we)
+            ref_shim.ref_transform_point(t.ctypes.data_as(C.POINTER(C.c_float)), c.ctypes.data_as(C.POINTER(C.c_float)), wc)
+            inside = ref_shim.ref_is_aabb_in_frustum(wc, we, frp)
+            mine = (status[i] & O.STATUS_MASK) != O.FRUSTUM_CULLED
+            total += 1
+            if bool(inside) != mine and not (status[i] & O.AMBIG_FRUSTUM):
+                mism += 1
+    assert total > 1000 and mism == 0
+
+
+# ------------------------------------------------------------------------------------------ sampler / HiZ rule
+def brute_sample(img, u, v):
+    """independent restatement of the rule in numpy float32"""
+    h, w = img.shape
+    def fp(c, n):
+        x = np.float32(np.float32(c) * np.float32(n)) - np.float32(0.5)
+        i0 = int(np.floor(x)); fr = np.float32(x) - np.float32(np.floor(x))
+        i1 = i0 if fr == 0 else i0 + 1
+        return min(max(i0, 0), n - 1), min(max(i1, 0), n - 1)
+    x0, x1 = fp(u, w); y0, y1 = fp(v, h)
+    return min(img[y0, x0], img[y0, x1], img[y1, x0], img[y1, x1])
+
+
+def test_sampler_rule_against_numpy_restatement():
+    rng = np.random.default_rng(9)
+    for (w, h) in [(1, 1), (2, 1), (5, 3), (10, 7), (16, 16), (67, 120)]:
+        img = rng.random((h, w), dtype=np.float32)
+        for _ in range(300):
+            u, v = np.float32(rng.uniform(0, 1)), np.float32(rng.uniform(0, 1))
+            a = C.c_int(0)
+            got = O.lib().orc_sample_min(img.ctypes.data, w, h, u, v, C.byref(a))
+            assert got == brute_sample(img, u, v)
+        # texel centres: frac == 0 -> single texel, no neighbour leaks in
+        for x in range(w):
+            for y in range(h):
+                u, v = np.float32((x + 0.5) / w), np.float32((y + 0.5) / h)
+                got = O.lib().orc_sample_min(img.ctypes.data, w, h, u, v, None)
+                assert got == brute_sample(img, u, v)
+
+
+@pytest.mark.parametrize("res", [(640, 480), (1920, 1080), (3840, 2160), (7680, 4320)])
+def test_exact_2x_levels_have_the_aligned_quad_footprint(res):
+    """for every mip whose source is exactly 2x, u = (p+.5)/D*S-.5 must land strictly inside (2p, 2p+1) in fp32:
+    this is what lets the CUDA tiled kernel take {2p,2p+1} without evaluating the sampler (hiz.cu)."""
+    W, H = res
+    levels, layout, _ = abi.pyramid_layout(W, H)
+    sizes = [(W, H)] + [(w, h) for _, w, h in layout]
+    n_exact = 0
+    for i in range(1, levels + 1):
+        (sw, sh), (dw, dh) = sizes[i - 1], (W >> i, H >> i)
+        if dw == 0 or dh == 0:
+            continue
+        for S_, D_ in ((sw, dw), (sh, dh)):
+            if S_ != 2 * D_:
+                continue
+            p = np.arange(D_, dtype=np.float32)
+            u = ((p + np.float32(0.5)) / np.float32(D_)) * np.float32(S_) - np.float32(0.5)
+            assert np.array_equal(np.floor(u), 2 * p) and (u - np.floor(u) > 0.25).all() and (u - np.floor(u) < 0.75).all()
+            n_exact += 1
+    assert n_exact >= 6
+
+
+def test_hiz_matches_numpy_and_skips_unwritten_mips():
+    """640x480: the last mip (1x1) has a zero-sized dispatch and keeps its initial contents"""
+    W, H = 640, 480
+    rng = np.random.default_rng(1)
+    tg = O.Targets(W, H)
+    tg.depth[:] = rng.random((H, W), dtype=np.float32)
+    tg.pyramid[:] = 7.0
+    O.hiz(tg)
+    assert tg.mip(8)[0, 0] == 7.0                      # never written
+    src = tg.depth
+    for k in range(tg.levels - 1):
+        dw, dh = W >> (k + 1), H >> (k + 1)
+        m = tg.mip(k)
+        assert m.shape == (max(1, (H >> 1) >> k), max(1, (W >> 1) >> k))
+        for (x, y) in [(0, 0), (dw - 1, dh - 1), (dw // 2, dh // 2), (dw // 3, dh - 1)]:
+            u, v = (np.float32(x) + np.float32(0.5)) / np.float32(dw), (np.float32(y) + np.float32(0.5)) / np.float32(dh)
+            assert m[y, x] == brute_sample(src, u, v), (k, x, y)
+        if src.shape == (2 * dh, 2 * dw):             # exact level == plain 2x2 min
+            want = src.reshape(dh, 2, dw, 2).min(axis=(1, 3))
+            assert np.array_equal(m[:dh, :dw], want)
+        src = m
+
+
+def test_hiz_is_not_conservative_for_odd_sources():
+    """for 135 -> 67 rows one source row is never read; the oracle must reproduce that, not fix it"""
+    W, H = 1920, 1080
+    tg = O.Targets(W, H)
+    tg.depth[:] = 1.0
+    O.hiz(tg)
+    k = 3                                   # 240x135 -> mip 3
+    src = tg.mip(2).copy()
+    assert src.shape == (135, 240)
+    touched = np.zeros(135, bool)
+    dh = H >> 4
+    for y in range(dh):
+        v = (np.float32(y) + np.float32(0.5)) / np.float32(dh)
+        x = np.float32(v * np.float32(135)) - np.float32(0.5)
+        i0 = int(np.floor(x)); touched[i0] = True
+        if x - np.floor(x) != 0: touched[min(i0 + 1, 134)] = True
+    assert (~touched).sum() >= 1
+
+
+# ------------------------------------------------------------------------------------------ rasteriser properties
+def test_fill_rule_is_watertight_and_single_hit():
+    """a tessellated sheet covering the screen: every pixel is shaded exactly once (top-left rule), none missed"""
+    rng = np.random.default_rng(3)
+    W, H = 257, 193
+    n = 23
+    us, vs = np.meshgrid(np.linspace(0, 1, n + 1), np.linspace(0, 1, n + 1))
+    jit = rng.uniform(-0.3, 0.3, (n + 1, n + 1, 2)) / n
+    jit[0, :], jit[-1, :], jit[:, 0], jit[:, -1] = 0, 0, 0, 0
+    P = np.stack([(us + jit[..., 0]) * 40 - 20, (vs + jit[..., 1]) * 40 - 20, np.full_like(us, -5.0)], -1).reshape(-1, 3)
+    idx = []
+    for j in range(n):
+        for i in range(n):
+            a = j * (n + 1) + i
+            b, c, d = a + 1, a + n + 1, a + n + 2
+            idx += [a, b, c, b, d, c] if (i + j) % 2 else [a, b, d, a, d, c]
+    s = Scene.new()
+    m = s.add_material(double_sided=True)
+    s.add_node(s.add_primitive(P, idx, m))
+    s.finalize()
+    cam = Camera(W, H).look_at((0, 0, 3), (0, 0, 0))
+    pc = s.host_push_constants(cam)
+    tg = O.Targets(W, H)
+    ctr = O.raster(pc, tg, np.arange(pc.meshletDrawCount, dtype=np.uint32))
+    assert (tg.ids_ref != abi.VISBUFFER_CLEAR).all(), "holes between adjacent triangles"
+    assert ctr.fragments == W * H, "double hits on shared edges"
+    assert tg.tie.sum() == 0
+
+
+def test_tie_bookkeeping_and_vis64_key():
+    s = S.coplanar_overlap()
+    W, H = 160, 120
+    cam = S.camera(W, H)
+    pc = s.host_push_constants(cam)
+    tg = O.Targets(W, H)
+    n = pc.meshletDrawCount
+    O.raster(pc, tg, np.arange(n, dtype=np.uint32))
+    cov = tg.ids_ref != abi.VISBUFFER_CLEAR
+    assert cov.sum() > 1000 and (tg.tie[cov] == 1).all() and (tg.tie[~cov] == 0).all()
+    # reference rule: the later draw wins; atomicMin rule: the lower id wins; same triangle of the other instance
+    half = n // 2
+    assert ((tg.ids_ref[cov] >> 7) >= half).all() and ((tg.ids_min[cov] >> 7) < half).all()
+    assert np.array_equal(tg.ids_ref[cov] & 127, tg.ids_min[cov] & 127)
+    # order independence of ids_min / depth (what the GPU's atomicMin guarantees)
+    tg2 = O.Targets(W, H)
+    O.raster(pc, tg2, np.arange(n, dtype=np.uint32)[::-1].copy())
+    assert np.array_equal(tg2.ids_min, tg.ids_min) and np.array_equal(tg2.depth, tg.depth)
+    assert ((tg2.ids_ref[cov] >> 7) < half).all()
+    k = tg.vis64()
+    assert (k[~cov] == abi.VIS64_CLEAR).all()
+    assert O.lib().orc_vis64_key(0.0, 0xFFFFFFFF) == abi.VIS64_CLEAR
+    assert O.lib().orc_vis64_key(1.0, 5) < O.lib().orc_vis64_key(0.5, 3) < O.lib().orc_vis64_key(0.0, 0)  # nearer = smaller
+
+
+def test_depth_is_reverse_z_and_interpolated():
+    s = S.single_triangle()
+    W, H = 320, 240
+    for dist in (2.0, 4.0, 8.0):
+        cam = Camera(W, H).look_at((0, 0, dist), (0, 0, 0))
+        pc = s.host_push_constants(cam)
+        tg = O.Targets(W, H)
+        O.raster(pc, tg, np.array([0], np.uint32))
+        d = tg.depth[tg.ids_ref != abi.VISBUFFER_CLEAR]
+        # reverse-Z infinite-ish: depth ~= near/dist for far >> dist  (z' = w - z)
+        assert abs(d.mean() - 0.1 / dist * (1000 - dist) / (1000 - 0.1)) < 2e-4
+        assert d.max() - d.min() < 1e-5  # camera-facing triangle: constant depth
+
+
+def test_near_plane_clipping_keeps_only_the_visible_part():
+    s = S.ground_plane(8, 30.0, -1.0)
+    W, H = 400, 300
+    cam = Camera(W, H).look_at((0, 0, 0), (0, 0, -1))
+    pc = s.host_push_constants(cam)
+    tg = O.Targets(W, H)
+    ctr = O.raster(pc, tg, np.arange(pc.meshletDrawCount, dtype=np.uint32))
+    assert ctr.triangles_clipped > 0
+    cov = tg.ids_ref != abi.VISBUFFER_CLEAR
+    # floor below the camera: covers the part of the image below the horizon (Y flip: larger y = down), nothing above
+    assert cov[H // 2 + 12:, :].all() and not cov[: H // 2 - 5, :].any()
+    assert tg.depth.max() <= 1.0 and tg.depth[cov].min() > 0.0
+    # depth grows towards the bottom of the screen (closer to the camera)
+    col = tg.depth[H // 2 + 12:, W // 2]
+    assert (np.diff(col) >= 0).all()
+
+
+def test_backface_and_mirroring():
+    s = S.mirrored_instances()
+    W, H = 320, 240
+    pc_f = s.host_push_constants(Camera(W, H).look_at((0, 0, 4), (0, 0, 0)))
+    tg = O.Targets(W, H)
+    c1 = O.raster(pc_f, tg, np.arange(pc_f.meshletDrawCount, dtype=np.uint32))
+    pc_b = s.host_push_constants(Camera(W, H).look_at((0, 0, -4), (0, 0, 0)))
+    tg2 = O.Targets(W, H)
+    c2 = O.raster(pc_b, tg2, np.arange(pc_b.meshletDrawCount, dtype=np.uint32))
+    # every triangle is front-facing from exactly one side (up to edge-on ones), for mirrored instances too
+    assert c1.triangles_in == c2.triangles_in
+    assert abs((c1.triangles_culled_facing + c2.triangles_culled_facing) - c1.triangles_in) <= 0.12 * c1.triangles_in
+    assert c1.triangles_culled_facing < 0.2 * c1.triangles_in < c2.triangles_culled_facing
+
+
+# ------------------------------------------------------------------------------------------ culling properties
+def test_cull_classes_and_two_pass_recovers_everything_visible():
+    s = S.occluder_and_hidden()
+    W, H = 640, 480
+    cam = Camera(W, H).look_at((0, 0, 8), (0, 0, 0))
+    pc = s.host_push_constants(cam)
+    tg = O.Targets(W, H)
+    f0 = O.frame(pc, tg)                                     # empty pyramid: everything in the frustum is drawn
+    assert f0["cullA"].occluded == 0
+    truth = np.unique(tg.ids_ref[tg.ids_ref != abi.VISBUFFER_CLEAR] >> 7)
+    cam.look_at((0, 0, 8), (0, 0, 0))
+    f1 = O.frame(pc, tg, two_pass=True)
+    assert f1["cullA"].occluded >= 6
+    drawn = np.union1d(f1["visibleA"], f1["visibleB"])
+    assert np.isin(truth, drawn).all(), "a draw owning visible pixels was culled"
+    # behind the camera -> frustum culled
+    cam2 = Camera(W, H).look_at((0, 0, 8), (0, 0, 16))
+    pc2 = s.host_push_constants(cam2)
+    st, c = O.cull(pc2, W, H, tg.pyramid)
+    assert c.frustum_culled == pc2.meshletDrawCount
+
+
+def test_threads_do_not_change_results():
+    s = Scene.icosphere(20)
+    W, H = 333, 222
+    cam = s.default_camera(W, H)
+    pc = s.host_push_constants(cam)
+    a, b = O.Targets(W, H), O.Targets(W, H)
+    for _ in range(2):
+        O.frame(pc, a, two_pass=True, threads=1)
+        O.frame(pc, b, two_pass=True, threads=7)
+    assert np.array_equal(a.vis64(), b.vis64()) and np.array_equal(a.ids_ref, b.ids_ref) and np.array_equal(a.pyramid, b.pyramid)
