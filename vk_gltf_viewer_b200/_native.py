@@ -34,5 +34,6 @@ def host_lib() -> C.CDLL:
 def vkv_lib() -> C.CDLL:
     global _vkv
     if _vkv is None:
-        _vkv = _load("libvkv.so")
+        # VKV_LIBVKV: load another in-tree build of the SAME library (kernel tuning variants); still no fallback
+        _vkv = _load(os.environ.get("VKV_LIBVKV", "libvkv.so"))
     return _vkv

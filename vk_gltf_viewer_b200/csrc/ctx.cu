@@ -2,6 +2,7 @@
 // There is no CPU fallback anywhere in this file: without a CUDA device vkv_create fails with VKV_ERR_NO_DEVICE.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -29,6 +30,12 @@ struct vkv_ctx {
 	bool status_valid[2] = {false, false};
 	FrameCounters* counters = nullptr;
 	FrameCounters* h_counters = nullptr; // pinned
+	// per-transform mvp / determinant sign (mesh.glsl:44,71 hoisted; grow-only)
+	float* xf_mvp = nullptr;
+	uint32_t* xf_det = nullptr;
+	uint32_t xf_cap = 0;
+	uint32_t xf_count = 0;
+	int raster_pre_read = 0;
 	// readback scratch
 	uint32_t* tmp_ids = nullptr;
 	float* tmp_depth = nullptr;
@@ -127,6 +134,40 @@ int ensure_draws(vkv_ctx* c, uint32_t n) {
 	return VKV_OK;
 }
 
+// mesh.glsl:43-44,71 once per mesh-node: needs the transform count, which the push constants do not carry — it is the
+// extent of the vkv_upload allocation the transform buffer lives in.
+int prepare_transforms(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, int* launches) {
+	c->xf_count = 0;
+	if (!pc->meshletDrawCount) return VKV_OK;
+	size_t bytes = 0;
+	{
+		std::lock_guard<std::mutex> lock(c->mtx);
+		auto it = c->allocs.upper_bound(pc->transformBuffer);
+		if (it != c->allocs.begin()) {
+			--it;
+			if (pc->transformBuffer < it->first + it->second) bytes = it->first + it->second - pc->transformBuffer;
+		}
+	}
+	if (bytes < 64) return fail(c, VKV_ERR_INVALID, "transformBuffer does not point into a vkv_upload allocation");
+	const size_t n64 = bytes / 64;
+	if (n64 > 0xffffffffull) return fail(c, VKV_ERR_INVALID, "transform buffer too large");
+	const uint32_t n = (uint32_t)n64;
+	if (n > c->xf_cap) {
+		CK(cudaStreamSynchronize(c->stream));
+		if (c->xf_mvp) cudaFree(c->xf_mvp);
+		if (c->xf_det) cudaFree(c->xf_det);
+		c->xf_mvp = nullptr; c->xf_det = nullptr; c->xf_cap = 0;
+		const uint32_t cap = n + n / 8 + 64;
+		CK(cudaMalloc(&c->xf_mvp, (size_t)cap * 64));
+		CK(cudaMalloc(&c->xf_det, (size_t)cap * 4));
+		c->xf_cap = cap;
+	}
+	CK(launch_prepare_transforms((const float*)pc->transformBuffer, (const vkv_Camera*)pc->cameraBuffer, n, c->xf_mvp, c->xf_det, c->num_sms, c->stream));
+	if (launches) ++*launches;
+	c->xf_count = n;
+	return VKV_OK;
+}
+
 CullParams make_cull(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, int pass, uint32_t flags) {
 	CullParams p{};
 	p.draws = (const vkv_MeshletDraw*)pc->drawBuffer;
@@ -157,6 +198,7 @@ RasterParams make_raster(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, const
 	r.camera = (const vkv_Camera*)pc->cameraBuffer;
 	r.list = list; r.count = count; r.work = work;
 	r.vis = c->vis; r.W = c->W; r.H = c->H;
+	r.mvp = c->xf_mvp; r.detNeg = c->xf_det; r.pre_read = c->raster_pre_read;
 	return r;
 }
 
@@ -197,6 +239,7 @@ int vkv_create(vkv_ctx** out, int cuda_device, uint32_t width, uint32_t height) 
 	if (cudaGetDeviceProperties(&prop, cuda_device) == cudaSuccess) c->num_sms = prop.multiProcessorCount;
 	if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { c->err = "cudaStreamCreate failed"; return bail(VKV_ERR_CUDA); }
 	c->stream = c->own_stream;
+	if (const char* e = getenv("VKV_RASTER_PRE_READ")) c->raster_pre_read = atoi(e);
 	for (auto& ev : c->events) cudaEventCreate(&ev);
 	for (auto& ev : c->stage_ev) cudaEventCreate(&ev);
 	if (cudaMalloc(&c->counters, sizeof(FrameCounters)) != cudaSuccess || cudaMalloc(&c->tmp_count, 256) != cudaSuccess ||
@@ -229,6 +272,8 @@ void vkv_destroy(vkv_ctx* c) {
 		if (c->status[i]) cudaFree(c->status[i]);
 	}
 	if (c->list_tmp) cudaFree(c->list_tmp);
+	if (c->xf_mvp) cudaFree(c->xf_mvp);
+	if (c->xf_det) cudaFree(c->xf_det);
 	if (c->tmp_count) cudaFree(c->tmp_count);
 	if (c->counters) cudaFree(c->counters);
 	if (c->h_counters) cudaFreeHost(c->h_counters);
@@ -326,6 +371,8 @@ int vkv_raster(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, int pass) {
 	if (pass < 0 || pass > 1) return fail(c, VKV_ERR_INVALID, "pass must be 0 or 1");
 	CK(cudaSetDevice(c->device));
 	CK(cudaMemsetAsync(&c->counters->work[pass], 0, 4, c->stream));
+	rc = prepare_transforms(c, pc, nullptr);
+	if (rc) return rc;
 	CK(launch_raster(make_raster(c, pc, c->list_visible[pass], &c->counters->visible[pass], &c->counters->work[pass]), c->num_sms, c->stream));
 	return VKV_OK;
 }
@@ -338,6 +385,8 @@ int vkv_raster_list(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, const uint
 	uint32_t hdr[2] = {n, 0};
 	CK(cudaMemcpyAsync(c->tmp_count, hdr, 8, cudaMemcpyHostToDevice, c->stream));
 	if (n) CK(cudaMemcpyAsync(c->list_tmp, draw_ids, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+	rc = prepare_transforms(c, pc, nullptr);
+	if (rc) return rc;
 	CK(launch_raster(make_raster(c, pc, c->list_tmp, c->tmp_count, c->tmp_count + 1), c->num_sms, c->stream));
 	CK(cudaStreamSynchronize(c->stream)); // draw_ids / hdr are borrowed
 	return VKV_OK;
@@ -374,6 +423,8 @@ int vkv_frame(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, uint32_t flags, 
 		if (N) { CK(launch_cull(p, c->num_sms, s)); ++launches; }
 	}
 	mark(); // 2
+	rc = prepare_transforms(c, pc, &launches);
+	if (rc) return rc;
 	CK(launch_raster(make_raster(c, pc, c->list_visible[0], &c->counters->visible[0], &c->counters->work[0]), c->num_sms, s)); ++launches;
 	mark(); // 3
 	if (!(flags & VKV_FRAME_NO_HIZ)) CK(launch_hiz(make_hiz(c), c->num_sms, s, &launches));

@@ -32,6 +32,9 @@ struct RasterParams {
 	uint32_t* work;              // work-stealing cursor (zeroed per launch)
 	unsigned long long* vis;     // W*H 64-bit keys
 	uint32_t W, H;
+	const float* mvp;            // per transform: viewProjection * transform (launch_prepare_transforms)
+	const uint32_t* detNeg;      // per transform: determinant(transform) < 0
+	int pre_read;                // filter fragments with a plain read before the atomic (tuning switch; same result)
 };
 
 struct HizParams {
@@ -44,6 +47,8 @@ struct HizParams {
 
 cudaError_t launch_cull(const CullParams& p, int num_sms, cudaStream_t stream);
 cudaError_t launch_iota(uint32_t* out, uint32_t n, uint32_t* count, int num_sms, cudaStream_t stream);
+cudaError_t launch_prepare_transforms(const float* transforms, const vkv_Camera* camera, uint32_t n, float* mvp, uint32_t* detNeg,
+                                      int num_sms, cudaStream_t stream);
 cudaError_t launch_raster(const RasterParams& p, int num_sms, cudaStream_t stream);
 cudaError_t launch_hiz(const HizParams& p, int num_sms, cudaStream_t stream, int* launches);
 cudaError_t launch_fill64(unsigned long long* dst, size_t n, unsigned long long value, int num_sms, cudaStream_t stream);
