@@ -35,7 +35,6 @@ struct vkv_ctx {
 	uint32_t* xf_det = nullptr;
 	uint32_t xf_cap = 0;
 	uint32_t xf_count = 0;
-	int raster_pre_read = 0;
 	// readback scratch
 	uint32_t* tmp_ids = nullptr;
 	float* tmp_depth = nullptr;
@@ -198,7 +197,7 @@ RasterParams make_raster(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, const
 	r.camera = (const vkv_Camera*)pc->cameraBuffer;
 	r.list = list; r.count = count; r.work = work;
 	r.vis = c->vis; r.W = c->W; r.H = c->H;
-	r.mvp = c->xf_mvp; r.detNeg = c->xf_det; r.pre_read = c->raster_pre_read;
+	r.mvp = c->xf_mvp; r.detNeg = c->xf_det;
 	return r;
 }
 
@@ -239,7 +238,6 @@ int vkv_create(vkv_ctx** out, int cuda_device, uint32_t width, uint32_t height) 
 	if (cudaGetDeviceProperties(&prop, cuda_device) == cudaSuccess) c->num_sms = prop.multiProcessorCount;
 	if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { c->err = "cudaStreamCreate failed"; return bail(VKV_ERR_CUDA); }
 	c->stream = c->own_stream;
-	if (const char* e = getenv("VKV_RASTER_PRE_READ")) c->raster_pre_read = atoi(e);
 	for (auto& ev : c->events) cudaEventCreate(&ev);
 	for (auto& ev : c->stage_ev) cudaEventCreate(&ev);
 	if (cudaMalloc(&c->counters, sizeof(FrameCounters)) != cudaSuccess || cudaMalloc(&c->tmp_count, 256) != cudaSuccess ||

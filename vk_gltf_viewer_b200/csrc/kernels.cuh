@@ -34,7 +34,6 @@ struct RasterParams {
 	uint32_t W, H;
 	const float* mvp;            // per transform: viewProjection * transform (launch_prepare_transforms)
 	const uint32_t* detNeg;      // per transform: determinant(transform) < 0
-	int pre_read;                // filter fragments with a plain read before the atomic (tuning switch; same result)
 };
 
 struct HizParams {

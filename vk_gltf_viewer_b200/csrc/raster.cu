@@ -3,21 +3,36 @@
 // per-triangle facing cull), the fixed-function clip / viewport / raster / depth stages configured at
 // application.cpp:326-340,772-841 (+ src/vulkan/pipeline_builder.cpp:225-277) and visbuffer.frag.glsl:36.
 //
-// One warp per meshlet (work-stealing over the survivor list).  Vertices are transformed once into per-warp shared
-// memory (clip position + snapped screen position); each lane then owns triangles: facing cull, trivial reject,
-// integer edge setup.  Small triangles are scanned by their lane (int32 edge functions — exact, no overflow);
-// large or clipped ones are handed to the whole warp (8x4 pixel stamps, int64 edge functions, stamp-level reject).
-// Visibility is resolved with ONE 64-bit atomicMin per covered pixel on (~depthBits << 32 | drawId << 7 | tri),
-// preceded by a plain read that filters already-occluded fragments.
+// One warp per meshlet, work-stealing over the survivor list in batches of kBatch:
+//   * one lane per meshlet of the batch walks the dependent header chain (list -> draw -> primitive -> meshlet), so the
+//     chain's L2 latency is paid once per batch, not once per meshlet;
+//   * while meshlet j is processed, meshlet j+1's vertex indices are in flight in registers and its vertex positions,
+//     triangle index words and mvp are copied global -> shared with cp.async (no registers held across the phases);
+//   * mvp = viewProjection * transform and sign(det(transform)) come from a per-transform prologue kernel;
+//   * vertex phase: clip position, outcodes and the snapped 24.8 screen position go to per-warp shared memory;
+//   * triangle phase 1 (all triangles, one per lane): facing cull, trivial reject, pixel-centre bbox test; survivors are
+//     compacted with ballot/popc into a shared list;
+//   * triangle phase 2 (survivors only, full lanes): integer edge setup; small triangles are scanned by their lane with
+//     int32 edge functions, large or clipped ones by the whole warp in 8x4 stamps with int64 edge functions;
+//   * visibility: ONE fire-and-forget 64-bit RED.MIN per covered pixel on (~depthBits << 32 | drawId << 7 | triangle).
 #include "kernels.cuh"
 
 namespace {
 
-constexpr int kWarpsPerBlock = 8;
+#ifndef VKV_RASTER_WARPS
+#define VKV_RASTER_WARPS 8
+#endif
+constexpr int kWarpsPerBlock = VKV_RASTER_WARPS;
 constexpr int kThreads = kWarpsPerBlock * 32;
 constexpr int kSerialMaxDim = 8;   // lane-serial path: bbox <= 8x8 pixels
-constexpr int kBatch = 8;          // meshlets fetched per work-stealing grab (one lane walks each meshlet's header chain)
-constexpr int kMinBlocks = 3;      // register budget: 65536 / (256 * 3) = 85 -> 24 warps / SM
+#ifndef VKV_RASTER_BATCH
+#define VKV_RASTER_BATCH 4
+#endif
+#ifndef VKV_RASTER_MIN_BLOCKS
+#define VKV_RASTER_MIN_BLOCKS 2
+#endif
+constexpr int kBatch = VKV_RASTER_BATCH;           // meshlets fetched per work-stealing grab
+constexpr int kMinBlocks = VKV_RASTER_MIN_BLOCKS;  // 128 registers, no spills, 16 warps / SM (measured: 24 warps at 80 registers spill and are slower)
 
 struct Tri {
 	int ax, ay, bx, by, cx, cy;      // snapped vertices, 24.8 fixed point, area2 > 0
@@ -28,17 +43,37 @@ struct Tri {
 	uint32_t small;                  // vertex extent <= 2^14 sub-pixels in x and y: every edge value fits in int32
 };
 
+// what one lane fetches for one meshlet of a batch (mesh.glsl:31-36 resolved to addresses)
+struct alignas(16) MeshletHdr {
+	const uint32_t* vidx;      // primitive.vertexIndexBuffer + meshlet.vertexOffset
+	const uint8_t* tri;        // primitive.primitiveIndexBuffer + meshlet.triangleOffset
+	const vkv_Vertex* verts;   // primitive.vertexBuffer
+	uint32_t drawId;
+	uint32_t tIdx;
+	uint32_t counts;           // vertexCount | triangleCount << 8 | doubleSided << 16 | detNegative << 17
+	uint32_t pad[3];
+};
+
 struct WarpScratch {
-	float4 clip[VKV_MAX_VERTICES];
-	int2 fxy[VKV_MAX_VERTICES];
-	float zndc[VKV_MAX_VERTICES];
-	uint32_t flags[VKV_MAX_VERTICES];
-	uint32_t tri_words[96];          // up to 124*3 = 372 index bytes
+	float4 cxyw[VKV_MAX_VERTICES];   // clip x, y, w and the outcode bits (what phase 1 reads: one LDS.128 per vertex)
+	int4 scr[VKV_MAX_VERTICES];      // snapped x, y (24.8), z_ndc bits, unused
+	float cz[VKV_MAX_VERTICES];      // clip z (clipper only)
+	float pos[VKV_MAX_VERTICES * 3]; // cp.async landing zone: object-space positions of the next meshlet
+	uint32_t tri_words[2][96];       // cp.async landing zone (double buffered): up to 124*3 = 372 index bytes
+	uint32_t surv[128];              // phase-1 survivors: ia | ib << 8 | ic << 16 | triangle << 24 | needsClip << 31
+	float mvp[16];                   // cp.async landing zone
 	Tri sub[8];
+	MeshletHdr hdr[kBatch];
 	int nsub;
 };
 
-enum { F_NEEDS_CLIP = 64 };
+enum { F_NEEDS_CLIP = 64, F_NAN = 128 };
+
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 __device__ __forceinline__ bool top_left(int dx, int dy) { return dy < 0 || (dy == 0 && dx > 0); }
 
@@ -51,10 +86,33 @@ __device__ __forceinline__ void project(float4 c, float hw, float hh, int& fx, i
 	fy = __float2int_rn(sy * (float)VKV_SUB);
 }
 
+// pixel-centre bounding box of three snapped vertices, clipped to the viewport; false = no pixel centre inside
+__device__ __forceinline__ bool tri_bbox(int ax, int ay, int bx, int by, int cx, int cy, uint32_t W, uint32_t H, int& xmin, int& xmax,
+                                         int& ymin, int& ymax, uint32_t& small) {
+	const int minx = min(ax, min(bx, cx)), maxx = max(ax, max(bx, cx));
+	const int miny = min(ay, min(by, cy)), maxy = max(ay, max(by, cy));
+	xmin = max(0, (minx + (VKV_SUB / 2 - 1)) >> VKV_SUB_BITS);
+	xmax = min((int)W - 1, (maxx - VKV_SUB / 2) >> VKV_SUB_BITS);
+	ymin = max(0, (miny + (VKV_SUB / 2 - 1)) >> VKV_SUB_BITS);
+	ymax = min((int)H - 1, (maxy - VKV_SUB / 2) >> VKV_SUB_BITS);
+	small = (maxx - minx <= 16384 && maxy - miny <= 16384) ? 1u : 0u;
+	return xmin <= xmax && ymin <= ymax;
+}
+
 // integer setup shared by every path; false = nothing to draw
 __device__ __forceinline__ bool setup_tri(int ax, int ay, float za, int bx, int by, float zb, int cx, int cy, float zc, uint32_t id,
                                           uint32_t W, uint32_t H, Tri& t) {
-	long long area2 = (long long)(bx - ax) * (cy - ay) - (long long)(by - ay) * (cx - ax);
+	if (!tri_bbox(ax, ay, bx, by, cx, cy, W, H, t.xmin, t.xmax, t.ymin, t.ymax, t.small)) return false;
+	long long area2;
+	float fa;
+	if (t.small) { // every delta < 2^15: both products < 2^29, the difference fits in int32 (same value as the int64 form)
+		const int a32 = (bx - ax) * (cy - ay) - (by - ay) * (cx - ax);
+		area2 = a32;
+		fa = (float)abs(a32);
+	} else {
+		area2 = (long long)(bx - ax) * (cy - ay) - (long long)(by - ay) * (cx - ax);
+		fa = (float)(area2 < 0 ? -area2 : area2);
+	}
 	if (area2 == 0) return false;
 	if (area2 < 0) { // cullMode NONE: both windings are drawn
 		int tx = bx; bx = cx; cx = tx;
@@ -62,23 +120,14 @@ __device__ __forceinline__ bool setup_tri(int ax, int ay, float za, int bx, int 
 		float tz = zb; zb = zc; zc = tz;
 		area2 = -area2;
 	}
-	const int minx = min(ax, min(bx, cx)), maxx = max(ax, max(bx, cx));
-	const int miny = min(ay, min(by, cy)), maxy = max(ay, max(by, cy));
-	t.xmin = max(0, (minx + (VKV_SUB / 2 - 1)) >> VKV_SUB_BITS);
-	t.xmax = min((int)W - 1, (maxx - VKV_SUB / 2) >> VKV_SUB_BITS);
-	t.ymin = max(0, (miny + (VKV_SUB / 2 - 1)) >> VKV_SUB_BITS);
-	t.ymax = min((int)H - 1, (maxy - VKV_SUB / 2) >> VKV_SUB_BITS);
-	if (t.xmin > t.xmax || t.ymin > t.ymax) return false;
 	t.ax = ax; t.ay = ay; t.bx = bx; t.by = by; t.cx = cx; t.cy = cy;
 	t.area2 = area2;
 	t.za = za; t.dzb = zb - za; t.dzc = zc - za;
-	t.invA = 1.0f / (float)area2;
+	t.invA = 1.0f / fa;
 	t.id = id;
-	t.small = (maxx - minx <= 16384 && maxy - miny <= 16384) ? 1u : 0u;
 	return true;
 }
 
-template <bool PRE_READ>
 __device__ __forceinline__ void shade(unsigned long long* __restrict__ vis, uint32_t W, int x, int y, float w1, float w2, float invA,
                                       float za, float dzb, float dzc, uint32_t id) {
 	const float l1 = w1 * invA;
@@ -87,15 +136,12 @@ __device__ __forceinline__ void shade(unsigned long long* __restrict__ vis, uint
 	z = (z > 0.0f) ? z : 0.0f;
 	z = (z < 1.0f) ? z : 1.0f;
 	const unsigned long long key = ((unsigned long long)(~__float_as_uint(z)) << 32) | id;
-	unsigned long long* p = vis + (size_t)y * W + x;
-	// PRE_READ: a plain L2 read filters fragments that are already behind (saves atomic traffic, costs an L2 round trip
-	// per fragment); otherwise a fire-and-forget RED.MIN.U64 — the issuing lane never waits.
-	if (PRE_READ) { if (key < __ldcg(p)) atomicMin(p, key); }
-	else atomicMin(p, key);
+	// result unused -> RED.E.MIN.64: fire and forget, the lane never waits for L2 (a read-before-atomic filter was measured
+	// 30% slower on cfg 3: the L2 round trip per fragment costs more than the saved atomics)
+	atomicMin(vis + (size_t)y * W + x, key);
 }
 
 // Lane-serial scan of a small triangle; all edge values fit in int32 (deltas <= 2^14 sub-pixels).
-template <bool PRE_READ>
 __device__ __forceinline__ void raster_serial(const Tri& t, unsigned long long* __restrict__ vis, uint32_t W) {
 	const int e0dx = t.cx - t.bx, e0dy = t.cy - t.by;
 	const int e1dx = t.ax - t.cx, e1dy = t.ay - t.cy;
@@ -108,7 +154,7 @@ __device__ __forceinline__ void raster_serial(const Tri& t, unsigned long long* 
 	for (int y = t.ymin; y <= t.ymax; ++y) {
 		int w0 = r0, w1 = r1, w2 = r2;
 		for (int x = t.xmin; x <= t.xmax; ++x) {
-			if (w0 >= b0 && w1 >= b1 && w2 >= b2) shade<PRE_READ>(vis, W, x, y, (float)w1, (float)w2, t.invA, t.za, t.dzb, t.dzc, t.id);
+			if (w0 >= b0 && w1 >= b1 && w2 >= b2) shade(vis, W, x, y, (float)w1, (float)w2, t.invA, t.za, t.dzb, t.dzc, t.id);
 			w0 -= e0dy * VKV_SUB; w1 -= e1dy * VKV_SUB; w2 -= e2dy * VKV_SUB;
 		}
 		r0 += e0dx * VKV_SUB; r1 += e1dx * VKV_SUB; r2 += e2dx * VKV_SUB;
@@ -116,7 +162,6 @@ __device__ __forceinline__ void raster_serial(const Tri& t, unsigned long long* 
 }
 
 // Whole-warp scan in 8x4 stamps with stamp-level rejection; int64 edge functions (any triangle inside the guard band).
-template <bool PRE_READ>
 __device__ __noinline__ void raster_coop(const Tri& t, unsigned long long* __restrict__ vis, uint32_t W, uint32_t lane) {
 	const long long e0dx = t.cx - t.bx, e0dy = t.cy - t.by;
 	const long long e1dx = t.ax - t.cx, e1dy = t.ay - t.cy;
@@ -142,7 +187,7 @@ __device__ __noinline__ void raster_coop(const Tri& t, unsigned long long* __res
 				const long long w0 = s0 + o0, w1 = s1 + o1, w2 = s2 + o2;
 				const int x = tx + lx, y = ty + ly;
 				if (x <= t.xmax && y <= t.ymax && w0 >= b0 && w1 >= b1 && w2 >= b2)
-					shade<PRE_READ>(vis, W, x, y, (float)w1, (float)w2, t.invA, t.za, t.dzb, t.dzc, t.id);
+					shade(vis, W, x, y, (float)w1, (float)w2, t.invA, t.za, t.dzb, t.dzc, t.id);
 			}
 			s0 -= e0dy * 8 * VKV_SUB; s1 -= e1dy * 8 * VKV_SUB; s2 -= e2dy * 8 * VKV_SUB;
 		}
@@ -234,26 +279,13 @@ __global__ void prepare_transforms_kernel(const float* __restrict__ transforms, 
 	}
 }
 
-// what one lane fetches for one meshlet of a batch (mesh.glsl:31-36 resolved to addresses)
-struct alignas(16) MeshletHdr {
-	const uint32_t* vidx;      // primitive.vertexIndexBuffer + meshlet.vertexOffset
-	const uint8_t* tri;        // primitive.primitiveIndexBuffer + meshlet.triangleOffset
-	const vkv_Vertex* verts;   // primitive.vertexBuffer
-	uint32_t drawId;
-	uint32_t tIdx;
-	uint32_t counts;           // vertexCount | triangleCount << 8 | doubleSided << 16 | detNegative << 17
-	uint32_t pad[3];
-};
-
-template <bool PRE_READ>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) raster_kernel(const RasterParams p) {
 	__shared__ WarpScratch scratch[kWarpsPerBlock];
-	__shared__ MeshletHdr hdrs[kWarpsPerBlock][kBatch];
-	__shared__ __align__(16) float sMvp[kWarpsPerBlock][16];
 	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	WarpScratch& ws = scratch[warp];
 	const uint32_t count = __ldg(p.count);
 	const float hw = (float)p.W * 0.5f, hh = (float)p.H * 0.5f;
+	const uint32_t below = (1u << lane) - 1u;
 
 	for (;;) {
 		uint32_t base = 0;
@@ -282,138 +314,164 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) raster_kernel(const Rast
 			h.verts = (const vkv_Vertex*)b1.x;
 			h.drawId = drawId; h.tIdx = tIdx;
 			h.counts = vc | (tc << 8) | (ds << 16) | (dn << 17);
-			hdrs[warp][lane] = h;
+			ws.hdr[lane] = h;
 		}
 		__syncwarp();
 
-		// software pipeline over the batch: while meshlet j is processed, the vertex indices (then positions), the triangle
-		// bytes and the mvp of meshlet j+1 are already in flight
-		uint32_t vi0 = 0, vi1 = 0;                 // vertex indices of the NEXT meshlet (slots lane, lane+32)
-		float px0 = 0, py0 = 0, pz0 = 0, px1 = 0, py1 = 0, pz1 = 0; // positions of the CURRENT meshlet
-		uint32_t tw0 = 0, tw1 = 0, tw2 = 0;        // triangle index words of the CURRENT meshlet
-		float mv = 0.f;                            // lanes 0..15: mvp element of the CURRENT meshlet
-		{
-			const MeshletHdr& h = hdrs[warp][0];
+		uint32_t vi0 = 0, vi1 = 0; // vertex indices (slots lane, lane+32) of the meshlet whose copies are issued next
+		auto load_indices = [&](const MeshletHdr& h) {
 			const uint32_t vc = h.counts & 0xffu;
 			if (lane < vc) vi0 = __ldg(h.vidx + lane);
 			if (lane + 32 < vc) vi1 = __ldg(h.vidx + lane + 32);
-		}
-		auto issue_loads = [&](const MeshletHdr& h) { // positions + triangle words + mvp of meshlet h (vi0/vi1 hold its indices)
+		};
+		// positions (vi0/vi1 hold the meshlet's indices), triangle index words and mvp: global -> shared, asynchronously
+		auto issue_copies = [&](const MeshletHdr& h, uint32_t buf) {
 			const uint32_t vc = h.counts & 0xffu, tc = (h.counts >> 8) & 0xffu;
-			if (lane < vc) { const float* q = h.verts[vi0].position; px0 = __ldg(q); py0 = __ldg(q + 1); pz0 = __ldg(q + 2); }
-			if (lane + 32 < vc) { const float* q = h.verts[vi1].position; px1 = __ldg(q); py1 = __ldg(q + 1); pz1 = __ldg(q + 2); }
+			if (lane < vc) {
+				const float* q = h.verts[vi0].position;
+				cp_async4(&ws.pos[lane * 3], q); cp_async4(&ws.pos[lane * 3 + 1], q + 1); cp_async4(&ws.pos[lane * 3 + 2], q + 2);
+			}
+			if (lane + 32 < vc) {
+				const float* q = h.verts[vi1].position;
+				cp_async4(&ws.pos[lane * 3 + 96], q); cp_async4(&ws.pos[lane * 3 + 97], q + 1); cp_async4(&ws.pos[lane * 3 + 98], q + 2);
+			}
 			const uint32_t nWords = (tc * 3 + 3) >> 2;
 			if ((((uintptr_t)h.tri) & 3) == 0) {
 				const uint32_t* w = (const uint32_t*)h.tri;
-				if (lane < nWords) tw0 = __ldg(w + lane);
-				if (lane + 32 < nWords) tw1 = __ldg(w + lane + 32);
-				if (lane + 64 < nWords) tw2 = __ldg(w + lane + 64);
+#pragma unroll
+				for (uint32_t k = 0; k < 96; k += 32)
+					if (lane + k < nWords) cp_async4(&ws.tri_words[buf][lane + k], w + lane + k);
 			} else { // unaligned triangle slice (never produced by the reference's builder: assets.cpp:339 pads to 4)
 				const uint32_t nBytes = tc * 3;
-				auto gather = [&](uint32_t wi) {
+				for (uint32_t wi = lane; wi < nWords; wi += 32) {
 					uint32_t r = 0;
-					for (uint32_t b = 0; b < 4; ++b) if (wi * 4 + b < nBytes) r |= (uint32_t)__ldg(h.tri + wi * 4 + b) << (8 * b);
-					return r;
-				};
-				if (lane < nWords) tw0 = gather(lane);
-				if (lane + 32 < nWords) tw1 = gather(lane + 32);
-				if (lane + 64 < nWords) tw2 = gather(lane + 64);
+					for (uint32_t b = 0; b < 4; ++b)
+						if (wi * 4 + b < nBytes) r |= (uint32_t)__ldg(h.tri + wi * 4 + b) << (8 * b);
+					ws.tri_words[buf][wi] = r;
+				}
 			}
-			if (lane < 16) mv = __ldg(p.mvp + (size_t)h.tIdx * 16 + lane);
+			if (lane < 16) cp_async4(&ws.mvp[lane], p.mvp + (size_t)h.tIdx * 16 + lane);
+			cp_async_commit();
 		};
-		issue_loads(hdrs[warp][0]);
+		load_indices(ws.hdr[0]);
+		issue_copies(ws.hdr[0], 0);
 
 		for (uint32_t j = 0; j < nb; ++j) {
-			const MeshletHdr h = hdrs[warp][j];
+			const MeshletHdr h = ws.hdr[j];
 			const uint32_t drawId = h.drawId;
 			const uint32_t vc = h.counts & 0xffu, tc = (h.counts >> 8) & 0xffu;
 			const bool doubleSided = (h.counts >> 16) & 1u, detNeg = (h.counts >> 17) & 1u;
 			// vertex indices of meshlet j+1: in flight during this meshlet's vertex phase
-			if (j + 1 < nb) {
-				const MeshletHdr& hn = hdrs[warp][j + 1];
-				const uint32_t vcn = hn.counts & 0xffu;
-				if (lane < vcn) vi0 = __ldg(hn.vidx + lane);
-				if (lane + 32 < vcn) vi1 = __ldg(hn.vidx + lane + 32);
-			}
-			// stage this meshlet's triangle words and mvp
-			ws.tri_words[lane] = tw0; ws.tri_words[lane + 32] = tw1; ws.tri_words[lane + 64] = tw2;
-			if (lane < 16) sMvp[warp][lane] = mv;
+			if (j + 1 < nb) load_indices(ws.hdr[j + 1]);
+			cp_async_wait_all();
 			__syncwarp();
-			float mvp[16];
-#pragma unroll
-			for (int c = 0; c < 4; ++c) {
-				const float4 col = *(const float4*)&sMvp[warp][c * 4];
-				mvp[c * 4] = col.x; mvp[c * 4 + 1] = col.y; mvp[c * 4 + 2] = col.z; mvp[c * 4 + 3] = col.w;
-			}
+
 			// :50-69 vertices
+			{
+				float mvp[16];
 #pragma unroll
-			for (int half = 0; half < 2; ++half) {
-				const uint32_t v = lane + half * 32;
-				if (v < vc) {
-					const float4 c = half ? mul44(mvp, px1, py1, pz1, 1.0f) : mul44(mvp, px0, py0, pz0, 1.0f); // :61
-					uint32_t f = 0;
-					if (c.x < -c.w) f |= 1;
-					if (c.x > c.w) f |= 2;
-					if (c.y < -c.w) f |= 4;
-					if (c.y > c.w) f |= 8;
-					if (c.z < 0.f) f |= 16;
-					if (c.z > c.w) f |= 32;
-					const float g = VKV_GUARD * c.w;
-					if (c.z < 0.f || c.z > c.w || c.x > g || c.x < -g || c.y > g || c.y < -g) f |= F_NEEDS_CLIP;
-					if (!(c.x == c.x && c.y == c.y && c.z == c.z && c.w == c.w)) f |= 0x80; // NaN -> reject
-					int fx = 0, fy = 0;
-					float z = 0.f;
-					if (!(f & (F_NEEDS_CLIP | 0x80)) && c.w > 0.f) project(c, hw, hh, fx, fy, z);
-					else if (!(f & 0x80) && !(c.w > 0.f)) f |= F_NEEDS_CLIP; // degenerate w: let the clipper decide
-					ws.clip[v] = c;
-					ws.fxy[v] = make_int2(fx, fy);
-					ws.zndc[v] = z;
-					ws.flags[v] = f;
+				for (int c = 0; c < 4; ++c) {
+					const float4 col = *(const float4*)&ws.mvp[c * 4];
+					mvp[c * 4] = col.x; mvp[c * 4 + 1] = col.y; mvp[c * 4 + 2] = col.z; mvp[c * 4 + 3] = col.w;
+				}
+#pragma unroll
+				for (int half = 0; half < 2; ++half) {
+					const uint32_t v = lane + half * 32;
+					if (v < vc) {
+						const float4 c = mul44(mvp, ws.pos[v * 3], ws.pos[v * 3 + 1], ws.pos[v * 3 + 2], 1.0f); // :61
+						uint32_t f = 0;
+						if (c.x < -c.w) f |= 1;
+						if (c.x > c.w) f |= 2;
+						if (c.y < -c.w) f |= 4;
+						if (c.y > c.w) f |= 8;
+						if (c.z < 0.f) f |= 16;
+						if (c.z > c.w) f |= 32;
+						const float g = VKV_GUARD * c.w;
+						if (c.z < 0.f || c.z > c.w || c.x > g || c.x < -g || c.y > g || c.y < -g) f |= F_NEEDS_CLIP;
+						if (!(c.x == c.x && c.y == c.y && c.z == c.z && c.w == c.w)) f |= F_NAN; // NaN -> reject
+						int fx = 0, fy = 0;
+						float z = 0.f;
+						if (!(f & (F_NEEDS_CLIP | F_NAN)) && c.w > 0.f) project(c, hw, hh, fx, fy, z);
+						else if (!(f & F_NAN) && !(c.w > 0.f)) f |= F_NEEDS_CLIP; // degenerate w: let the clipper decide
+						ws.cxyw[v] = make_float4(c.x, c.y, c.w, __uint_as_float(f));
+						ws.scr[v] = make_int4(fx, fy, __float_as_int(z), 0);
+						ws.cz[v] = c.z;
+					}
 				}
 			}
 			__syncwarp();
-			// positions / triangle words / mvp of meshlet j+1: in flight during this meshlet's triangle phase
-			if (j + 1 < nb) issue_loads(hdrs[warp][j + 1]);
+			// positions / triangle words / mvp of meshlet j+1: in flight during this meshlet's triangle phases
+			if (j + 1 < nb) issue_copies(ws.hdr[j + 1], (j + 1) & 1);
 
-			// :73-103 triangles
-			const uint8_t* tb = (const uint8_t*)ws.tri_words;
+			// :73-103 triangles, phase 1: facing cull + trivial reject + bbox test, survivors compacted
+			const uint8_t* tb = (const uint8_t*)ws.tri_words[j & 1];
+			uint32_t nSurv = 0;
 			for (uint32_t tbase = 0; tbase < tc; tbase += 32) {
 				const uint32_t t = tbase + lane;
-				int kind = 0; // 0 nothing, 1 serial, 2 cooperative, 3 clip
-				Tri tri;
-				uint32_t ia = 0, ib = 0, ic = 0;
+				bool keep = false;
+				uint32_t entry = 0;
 				if (t < tc) {
-					ia = tb[t * 3]; ib = tb[t * 3 + 1]; ic = tb[t * 3 + 2];
+					uint32_t ia = tb[t * 3], ib = tb[t * 3 + 1], ic = tb[t * 3 + 2];
 					ia = min(ia, vc - 1); ib = min(ib, vc - 1); ic = min(ic, vc - 1); // robustness only
-					const float4 A = ws.clip[ia], B = ws.clip[ib], C = ws.clip[ic];
-					const uint32_t fa = ws.flags[ia], fb = ws.flags[ib], fc = ws.flags[ic];
+					const float4 A = ws.cxyw[ia], B = ws.cxyw[ib], C = ws.cxyw[ic];  // x, y, w, outcode
+					const uint32_t fa = __float_as_uint(A.w), fb = __float_as_uint(B.w), fc = __float_as_uint(C.w);
 					bool cull = false;
 					if (!doubleSided) { // :86-98
-						const float det = det3(make_float3(A.x, A.y, A.w), make_float3(B.x, B.y, B.w), make_float3(C.x, C.y, C.w));
+						const float det = det3(make_float3(A.x, A.y, A.z), make_float3(B.x, B.y, B.z), make_float3(C.x, C.y, C.z));
 						cull = detNeg ? (det < 0.0f) : (det > 0.0f);
 					}
-					const uint32_t id = (drawId << VKV_TRIANGLE_BITS) | t; // frag.glsl:36
-					if (!cull && !((fa | fb | fc) & 0x80) && !(fa & fb & fc & 63)) {
-						if ((fa | fb | fc) & F_NEEDS_CLIP) kind = 3;
+					if (!cull && !((fa | fb | fc) & F_NAN) && !(fa & fb & fc & 63)) {
+						entry = ia | (ib << 8) | (ic << 16) | (t << 24);
+						if ((fa | fb | fc) & F_NEEDS_CLIP) { keep = true; entry |= 0x80000000u; }
 						else {
-							const int2 a = ws.fxy[ia], b = ws.fxy[ib], c = ws.fxy[ic];
-							if (setup_tri(a.x, a.y, ws.zndc[ia], b.x, b.y, ws.zndc[ib], c.x, c.y, ws.zndc[ic], id, p.W, p.H, tri))
-								kind = (tri.small && tri.xmax - tri.xmin < kSerialMaxDim && tri.ymax - tri.ymin < kSerialMaxDim) ? 1 : 2;
+							const int4 a = ws.scr[ia], b = ws.scr[ib], c = ws.scr[ic];
+							int x0, x1, y0, y1;
+							uint32_t sm;
+							keep = tri_bbox(a.x, a.y, b.x, b.y, c.x, c.y, p.W, p.H, x0, x1, y0, y1, sm);
 						}
 					}
 				}
-				if (kind == 1) raster_serial<PRE_READ>(tri, p.vis, p.W);
+				const uint32_t m = __ballot_sync(0xffffffffu, keep);
+				if (keep) ws.surv[nSurv + __popc(m & below)] = entry;
+				nSurv += __popc(m);
+			}
+			__syncwarp();
+
+			// phase 2: survivors only — edge setup and rasterisation
+			for (uint32_t sbase = 0; sbase < nSurv; sbase += 32) {
+				const uint32_t s = sbase + lane;
+				int kind = 0; // 0 nothing, 1 serial, 2 cooperative, 3 clip
+				Tri tri;
+				uint32_t entry = 0;
+				if (s < nSurv) {
+					entry = ws.surv[s];
+					const uint32_t ia = entry & 0xffu, ib = (entry >> 8) & 0xffu, ic = (entry >> 16) & 0xffu;
+					const uint32_t id = (drawId << VKV_TRIANGLE_BITS) | ((entry >> 24) & 0x7fu); // frag.glsl:36
+					if (entry & 0x80000000u) kind = 3;
+					else {
+						const int4 a = ws.scr[ia], b = ws.scr[ib], c = ws.scr[ic];
+						if (setup_tri(a.x, a.y, __int_as_float(a.z), b.x, b.y, __int_as_float(b.z), c.x, c.y, __int_as_float(c.z), id, p.W, p.H, tri))
+							kind = (tri.small && tri.xmax - tri.xmin < kSerialMaxDim && tri.ymax - tri.ymin < kSerialMaxDim) ? 1 : 2;
+					}
+				}
+				if (kind == 1) raster_serial(tri, p.vis, p.W);
 				uint32_t coop = __ballot_sync(0xffffffffu, kind >= 2);
 				while (coop) {
 					const int src = __ffs(coop) - 1;
 					coop &= coop - 1;
 					if ((int)lane == src) {
 						if (kind == 2) { ws.sub[0] = tri; ws.nsub = 1; }
-						else ws.nsub = clip_and_setup(ws.clip[ia], ws.clip[ib], ws.clip[ic], (drawId << VKV_TRIANGLE_BITS) | t, p.W, p.H, ws.sub);
+						else {
+							const uint32_t ia = entry & 0xffu, ib = (entry >> 8) & 0xffu, ic = (entry >> 16) & 0xffu;
+							const float4 A = ws.cxyw[ia], B = ws.cxyw[ib], C = ws.cxyw[ic];
+							ws.nsub = clip_and_setup(make_float4(A.x, A.y, ws.cz[ia], A.z), make_float4(B.x, B.y, ws.cz[ib], B.z),
+							                         make_float4(C.x, C.y, ws.cz[ic], C.z),
+							                         (drawId << VKV_TRIANGLE_BITS) | ((entry >> 24) & 0x7fu), p.W, p.H, ws.sub);
+						}
 					}
 					__syncwarp();
 					const int n = ws.nsub;
-					for (int s = 0; s < n; ++s) raster_coop<PRE_READ>(ws.sub[s], p.vis, p.W, lane);
+					for (int k = 0; k < n; ++k) raster_coop(ws.sub[k], p.vis, p.W, lane);
 					__syncwarp();
 				}
 			}
@@ -450,16 +508,13 @@ cudaError_t launch_prepare_transforms(const float* transforms, const vkv_Camera*
 }
 
 cudaError_t launch_raster(const RasterParams& p, int num_sms, cudaStream_t stream) {
-	static int perSm[2] = {0, 0};
-	const int v = p.pre_read ? 1 : 0;
-	if (perSm[v] == 0) {
+	static int perSm = 0;
+	if (perSm == 0) {
 		int n = 0;
-		if (v) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, raster_kernel<true>, kThreads, 0);
-		else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, raster_kernel<false>, kThreads, 0);
-		perSm[v] = n < 1 ? 1 : n;
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, raster_kernel, kThreads, 0);
+		perSm = n < 1 ? 1 : n;
 	}
-	if (v) raster_kernel<true><<<num_sms * perSm[v], kThreads, 0, stream>>>(p);
-	else raster_kernel<false><<<num_sms * perSm[v], kThreads, 0, stream>>>(p);
+	raster_kernel<<<num_sms * perSm, kThreads, 0, stream>>>(p);
 	return cudaGetLastError();
 }
 
