@@ -50,7 +50,8 @@ enum {
 	VKV_FRAME_NO_HIZ = 1 << 1,     /* camera->freezeCullingMatrix: skip the pyramid rebuild (application.cpp:951) */
 	VKV_FRAME_STATUS = 1 << 2,     /* also write the per-draw status bytes (parity / debugging) */
 	VKV_FRAME_TIMED = 1 << 3,      /* fill the *_ms fields of vkv_stats (CUDA events; syncs the stream at frame end) */
-	VKV_FRAME_NO_CULL = 1 << 4     /* rasterise every MeshletDraw (debug; what the task shader does with culling disabled) */
+	VKV_FRAME_NO_CULL = 1 << 4,    /* rasterise every MeshletDraw (debug; what the task shader does with culling disabled) */
+	VKV_FRAME_MERGE = 1 << 5       /* multi-GPU: min-merge the visbuffer with the attached peers before each pyramid build */
 };
 
 /* per-draw status byte (VKV_FRAME_STATUS) — same values as the oracle's */
@@ -61,6 +62,7 @@ typedef struct vkv_stats {
 	uint32_t visible_a, occluded_a, visible_b, tested_b;
 	float clear_ms, cull_a_ms, raster_a_ms, hiz_a_ms, cull_b_ms, raster_b_ms, hiz_b_ms, total_ms; /* VKV_FRAME_TIMED */
 	uint32_t kernel_launches;    /* kernels of this library launched by the call */
+	float merge_a_ms, merge_b_ms; /* VKV_FRAME_TIMED + VKV_FRAME_MERGE */
 } vkv_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------------------------- */
@@ -86,6 +88,20 @@ int vkv_raster(vkv_ctx*, const vkv_VisbufferPushConstants* pc, int pass);
 int vkv_hiz(vkv_ctx*);
 /* rasterise an explicit MeshletDraw index list (host pointer) — test hook */
 int vkv_raster_list(vkv_ctx*, const vkv_VisbufferPushConstants* pc, const uint32_t* draw_ids, uint32_t n);
+
+/* ---- multi-GPU: one process (and one context) per GPU; a single huge view is sharded by MeshletDraw range and the
+ * per-GPU 64-bit visbuffers are min-merged over NVLink peer memory (BASELINE config 5).  The reference is
+ * single-GPU: there is no call site to cite, only the data contract — drawIndex stays the index into the GLOBAL list
+ * (visbuffer.h.glsl:15-16), so the merged image is bit-identical to a single-GPU frame. -------------------------------- */
+/* this GPU culls / rasterises MeshletDraws [first_draw, first_draw + draw_count) of pc->drawBuffer; enable = 0 restores the whole list */
+int vkv_set_shard(vkv_ctx*, uint32_t first_draw, uint32_t draw_count, int enable);
+/* 128-byte opaque handle (two cudaIpcMemHandle_t: visbuffer + barrier flags) to pass to the other ranks (any transport) */
+int vkv_ipc_export(vkv_ctx*, void* handle128);
+/* handles = nranks * 128 bytes, in rank order (the caller's own entry is ignored); opens the peers' buffers */
+int vkv_ipc_attach(vkv_ctx*, int rank, int nranks, const void* handles);
+int vkv_ipc_detach(vkv_ctx*);
+/* all ranks call it at the same point of their stream: barrier, fused reduce-scatter + all-gather u64 min, barrier */
+int vkv_merge(vkv_ctx*);
 
 /* ---- results (blocking device->host copies on the ctx stream) ------------------------------------------- */
 int vkv_read_visbuffer64(vkv_ctx*, uint64_t* host);                /* W*H keys: (~floatBits(depth) << 32) | packVisBuffer */

@@ -1,0 +1,67 @@
+"""torchrun worker for tests/test_multigpu.py: meshlet-range-sharded two-pass frames on WORLD_SIZE GPUs must be
+bit-identical to the single-list CPU oracle on every rank (visbuffer, pyramid) and the ranks' visible sets must
+partition the oracle's."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from tests import oracle_lib as O  # noqa: E402
+from vk_gltf_viewer_b200 import api, multigpu  # noqa: E402
+from vk_gltf_viewer_b200.scene import Camera, Scene  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    mode = sys.argv[1] if len(sys.argv) > 1 else "p2p"
+    W, H = 1280, 720
+    scene = Scene.lattice(4, 3, 4, 48)
+    views = [scene.default_view(i, 24) for i in range(3)]
+    cam = Camera(W, H).look_at(*views[0])
+    r = api.Renderer(W, H, device=local)
+    pc_dev = r.upload_scene(scene, cam)
+    pc_host = scene.host_push_constants(cam)
+    N = pc_host.meshletDrawCount
+    first, count = multigpu.shard_range(N, rank, world)
+    r.set_shard(first, count)
+    multigpu.attach_peers(r, dist)
+    tg = O.Targets(W, H)
+    for k, (eye, center) in enumerate(views):
+        if k:
+            cam.look_at(eye, center)
+            r.update_camera(pc_dev, cam)
+        out = O.frame(pc_host, tg, two_pass=True)
+        if mode == "p2p":
+            st = r.frame(pc_dev, api.FRAME_TWO_PASS | api.FRAME_MERGE | api.FRAME_STATUS)
+        else:  # library collective as the cross-check: stage by stage with ncclAllReduce(min) in place of vkv_merge
+            r.clear()
+            r.cull(pc_dev, 0, api.FRAME_STATUS); r.raster(pc_dev, 0); multigpu.nccl_min_merge(r, dist); r.hiz()
+            r.cull(pc_dev, 1, api.FRAME_STATUS); r.raster(pc_dev, 1); multigpu.nccl_min_merge(r, dist); r.hiz()
+            r.sync()
+        vis = r.read_visbuffer64()
+        assert np.array_equal(vis, tg.vis64()), f"rank {rank} view {k}: merged visbuffer differs from the single-list oracle ({int((vis != tg.vis64()).sum())} keys)"
+        assert np.array_equal(r.read_pyramid().view(np.uint32), tg.pyramid.view(np.uint32)), f"rank {rank} view {k}: pyramid differs"
+        mine = lambda ids: ids[(ids >= first) & (ids < first + count)]
+        assert np.array_equal(np.sort(r.read_visible(0)), mine(out["visibleA"])), f"rank {rank} view {k}: pass-A set"
+        assert np.array_equal(np.sort(r.read_visible(1)), mine(out["visibleB"])), f"rank {rank} view {k}: pass-B set"
+        nA = torch.tensor([r.read_visible(0).size, r.read_visible(1).size], device="cuda")
+        dist.all_reduce(nA)
+        assert nA.tolist() == [out["visibleA"].size, out["visibleB"].size]
+    r.ipc_detach()
+    r.close()
+    dist.barrier()
+    if rank == 0:
+        print(f"mgpu ok: {world} ranks, mode {mode}, {N} draws, {len(views)} views bit-exact")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

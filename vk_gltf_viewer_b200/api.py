@@ -17,6 +17,7 @@ FRAME_NO_HIZ = 1 << 1
 FRAME_STATUS = 1 << 2
 FRAME_TIMED = 1 << 3
 FRAME_NO_CULL = 1 << 4
+FRAME_MERGE = 1 << 5
 
 ST_FRUSTUM_CULLED, ST_OCCLUDED, ST_VISIBLE, ST_NOT_TESTED = 0, 1, 2, 3
 
@@ -32,7 +33,7 @@ class Stats(C.Structure):
         ("draws", C.c_uint32), ("visible_a", C.c_uint32), ("occluded_a", C.c_uint32), ("visible_b", C.c_uint32), ("tested_b", C.c_uint32),
         ("clear_ms", C.c_float), ("cull_a_ms", C.c_float), ("raster_a_ms", C.c_float), ("hiz_a_ms", C.c_float),
         ("cull_b_ms", C.c_float), ("raster_b_ms", C.c_float), ("hiz_b_ms", C.c_float), ("total_ms", C.c_float),
-        ("kernel_launches", C.c_uint32),
+        ("kernel_launches", C.c_uint32), ("merge_a_ms", C.c_float), ("merge_b_ms", C.c_float),
     ]
 
     def as_dict(self):
@@ -46,6 +47,7 @@ EXPORTS = [
     "vkv_read_visbuffer64", "vkv_read_ids", "vkv_read_depth", "vkv_read_hiz_mip", "vkv_read_pyramid", "vkv_write_pyramid",
     "vkv_read_visible", "vkv_read_status", "vkv_pyramid_floats",
     "vkv_event_record", "vkv_event_elapsed", "vkv_flush_l2", "vkv_visbuffer64_ptr",
+    "vkv_set_shard", "vkv_ipc_export", "vkv_ipc_attach", "vkv_ipc_detach", "vkv_merge",
 ]
 
 _bound = False
@@ -89,6 +91,11 @@ def _lib():
         L.vkv_flush_l2.argtypes = [vp, C.c_size_t]
         L.vkv_visbuffer64_ptr.argtypes = [vp]
         L.vkv_visbuffer64_ptr.restype = u64
+        L.vkv_set_shard.argtypes = [vp, u32, u32, i]
+        L.vkv_ipc_export.argtypes = [vp, vp]
+        L.vkv_ipc_attach.argtypes = [vp, i, i, vp]
+        L.vkv_ipc_detach.argtypes = [vp]
+        L.vkv_merge.argtypes = [vp]
         _bound = True
     return L
 
@@ -232,3 +239,23 @@ class Renderer:
 
     def visbuffer64_ptr(self) -> int:
         return self.L.vkv_visbuffer64_ptr(self.h)
+
+    # ---- multi-GPU (meshlet-range sharding) ---------------------------------------------------
+    def set_shard(self, first_draw=0, draw_count=0, enable=True):
+        self._ck(self.L.vkv_set_shard(self.h, first_draw, draw_count, 1 if enable else 0))
+
+    def ipc_export(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        self._ck(self.L.vkv_ipc_export(self.h, buf))
+        return buf.raw
+
+    def ipc_attach(self, rank: int, handles):
+        blob = b"".join(handles)
+        assert len(blob) == 128 * len(handles)
+        self._ck(self.L.vkv_ipc_attach(self.h, rank, len(handles), blob))
+
+    def ipc_detach(self):
+        self._ck(self.L.vkv_ipc_detach(self.h))
+
+    def merge(self):
+        self._ck(self.L.vkv_merge(self.h))

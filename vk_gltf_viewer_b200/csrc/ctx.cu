@@ -35,13 +35,20 @@ struct vkv_ctx {
 	uint32_t* xf_det = nullptr;
 	uint32_t xf_cap = 0;
 	uint32_t xf_count = 0;
+	// multi-GPU: this GPU's shard of the draw list and the peers' visbuffers mapped through CUDA IPC
+	uint32_t shard_first = 0, shard_count = 0;
+	bool sharded = false;
+	MergeParams mp{};
+	bool attached = false;
+	uint32_t* sync_flags = nullptr;   // kMaxRanks barrier slots + 1 error word, peer-mapped
+	uint32_t epoch = 0;
 	// readback scratch
 	uint32_t* tmp_ids = nullptr;
 	float* tmp_depth = nullptr;
 	void* flush_buf = nullptr;
 	size_t flush_bytes = 0;
 	cudaEvent_t events[16] = {};
-	cudaEvent_t stage_ev[9] = {};
+	cudaEvent_t stage_ev[12] = {};
 	std::map<uint64_t, size_t> allocs;
 	std::mutex mtx;
 	std::string err;
@@ -175,7 +182,8 @@ CullParams make_cull(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, int pass,
 	p.camera = (const vkv_Camera*)pc->cameraBuffer;
 	p.pyramid = c->pyramid;
 	p.pyr = c->pyr;
-	p.n = pc->meshletDrawCount;
+	p.n = c->sharded ? c->shard_count : pc->meshletDrawCount;
+	p.first = c->sharded ? c->shard_first : 0u;
 	p.in_list = pass == 0 ? nullptr : c->list_occluded[0];
 	p.in_count = pass == 0 ? nullptr : &c->counters->occluded[0];
 	p.out_visible = c->list_visible[pass];
@@ -212,7 +220,32 @@ int check_pc(vkv_ctx* c, const vkv_VisbufferPushConstants* pc) {
 	if (!pc) return fail(c, VKV_ERR_INVALID, "push constants are NULL");
 	if (pc->meshletDrawCount && (!pc->drawBuffer || !pc->transformBuffer || !pc->primitiveBuffer || !pc->cameraBuffer || !pc->materialBuffer))
 		return fail(c, VKV_ERR_INVALID, "push constants hold a NULL buffer address");
+	if (c->sharded && (uint64_t)c->shard_first + c->shard_count > pc->meshletDrawCount)
+		return fail(c, VKV_ERR_INVALID, "draw shard [%u, +%u) exceeds meshletDrawCount %u", c->shard_first, c->shard_count, pc->meshletDrawCount);
 	return ensure_draws(c, pc->meshletDrawCount);
+}
+
+void detach_peers(vkv_ctx* c) {
+	if (!c->attached) return;
+	for (int r = 0; r < c->mp.nranks; ++r) {
+		if (r == c->mp.rank) continue;
+		if (c->mp.vis[r]) cudaIpcCloseMemHandle(c->mp.vis[r]);
+		if (c->mp.flags[r]) cudaIpcCloseMemHandle(c->mp.flags[r]);
+	}
+	memset(&c->mp, 0, sizeof(c->mp));
+	c->attached = false;
+}
+
+// barrier -> fused reduce-scatter/all-gather min over peer memory -> barrier (merge.cu)
+int enqueue_merge(vkv_ctx* c, int* launches) {
+	if (!c->attached) return fail(c, VKV_ERR_INVALID, "merge requested but no peers are attached (vkv_ipc_attach)");
+	const unsigned long long timeout_ns = 5ull * 1000 * 1000 * 1000;
+	c->mp.n = (size_t)c->W * c->H;
+	CK(launch_xgpu_barrier(c->mp, ++c->epoch, timeout_ns, c->stream));
+	CK(launch_merge_min(c->mp, c->num_sms, c->stream));
+	CK(launch_xgpu_barrier(c->mp, ++c->epoch, timeout_ns, c->stream));
+	if (launches) *launches += 3;
+	return VKV_OK;
 }
 
 } // namespace
@@ -256,6 +289,7 @@ int vkv_resize(vkv_ctx* c, uint32_t width, uint32_t height) {
 	if (!c) return VKV_ERR_INVALID;
 	CK(cudaSetDevice(c->device));
 	CK(cudaStreamSynchronize(c->stream));
+	detach_peers(c); // the visbuffer is reallocated: peers must re-export / re-attach
 	return alloc_targets(c, width, height);
 }
 
@@ -263,6 +297,8 @@ void vkv_destroy(vkv_ctx* c) {
 	if (!c) return;
 	cudaSetDevice(c->device);
 	if (c->stream) cudaStreamSynchronize(c->stream);
+	detach_peers(c);
+	if (c->sync_flags) cudaFree(c->sync_flags);
 	free_targets(c);
 	for (int i = 0; i < 2; ++i) {
 		if (c->list_visible[i]) cudaFree(c->list_visible[i]);
@@ -403,45 +439,57 @@ int vkv_frame(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, uint32_t flags, 
 	CK(cudaSetDevice(c->device));
 	cudaStream_t s = c->stream;
 	const bool timed = (flags & VKV_FRAME_TIMED) && out;
-	const bool two = (flags & VKV_FRAME_TWO_PASS) != 0;
+	const bool two = (flags & VKV_FRAME_TWO_PASS) && !(flags & VKV_FRAME_NO_CULL);
+	const bool merge = (flags & VKV_FRAME_MERGE) != 0;
+	const bool hiz = !(flags & VKV_FRAME_NO_HIZ);
 	const uint32_t N = pc->meshletDrawCount;
-	int launches = 0, ev = 0;
-	auto mark = [&]() { if (timed) cudaEventRecord(c->stage_ev[ev], s); ++ev; };
+	const uint32_t first = c->sharded ? c->shard_first : 0u, cnt = c->sharded ? c->shard_count : N;
+	if (merge && !c->attached) return fail(c, VKV_ERR_INVALID, "VKV_FRAME_MERGE needs vkv_ipc_attach first");
+	int launches = 0;
+	enum { E_BEGIN, E_CLEAR, E_CULL_A, E_RASTER_A, E_MERGE_A, E_HIZ_A, E_CULL_B, E_RASTER_B, E_MERGE_B, E_HIZ_B, E_COUNT };
+	auto mark = [&](int e) { if (timed) cudaEventRecord(c->stage_ev[e], s); };
 	CK(cudaMemsetAsync(c->counters, 0, sizeof(FrameCounters), s));
-	mark(); // 0
-	CK(launch_fill64(c->vis, (size_t)c->W * c->H, VKV_VIS64_CLEAR, c->num_sms, s)); ++launches;
-	mark(); // 1
+	mark(E_BEGIN);
+	CK(launch_fill64(c->vis, (size_t)c->W * c->H, VKV_VIS64_CLEAR, c->num_sms, s)); ++launches; // application.cpp:782,807
+	mark(E_CLEAR);
 	if (flags & VKV_FRAME_NO_CULL) {
-		CK(launch_iota(c->list_visible[0], N, &c->counters->visible[0], c->num_sms, s)); ++launches;
+		CK(launch_iota(c->list_visible[0], first, cnt, &c->counters->visible[0], c->num_sms, s)); ++launches;
 		c->status_valid[0] = false;
 	} else {
 		CullParams p = make_cull(c, pc, 0, flags);
 		if (p.status) CK(cudaMemsetAsync(p.status, VKV_ST_NOT_TESTED, N, s));
 		c->status_valid[0] = p.status != nullptr;
-		if (N) { CK(launch_cull(p, c->num_sms, s)); ++launches; }
+		if (cnt) { CK(launch_cull(p, c->num_sms, s)); ++launches; }
 	}
-	mark(); // 2
+	mark(E_CULL_A);
 	rc = prepare_transforms(c, pc, &launches);
 	if (rc) return rc;
 	CK(launch_raster(make_raster(c, pc, c->list_visible[0], &c->counters->visible[0], &c->counters->work[0]), c->num_sms, s)); ++launches;
-	mark(); // 3
-	if (!(flags & VKV_FRAME_NO_HIZ)) CK(launch_hiz(make_hiz(c), c->num_sms, s, &launches));
-	mark(); // 4
-	if (two && !(flags & VKV_FRAME_NO_CULL)) {
+	mark(E_RASTER_A);
+	if (merge) { rc = enqueue_merge(c, &launches); if (rc) return rc; }
+	mark(E_MERGE_A);
+	if (hiz) CK(launch_hiz(make_hiz(c), c->num_sms, s, &launches));
+	mark(E_HIZ_A);
+	if (two) {
 		CullParams p = make_cull(c, pc, 1, flags);
 		if (p.status) CK(cudaMemsetAsync(p.status, VKV_ST_NOT_TESTED, N, s));
 		c->status_valid[1] = p.status != nullptr;
-		if (N) { CK(launch_cull(p, c->num_sms, s)); ++launches; }
-		mark(); // 5
+		if (cnt) { CK(launch_cull(p, c->num_sms, s)); ++launches; }
+		mark(E_CULL_B);
 		CK(launch_raster(make_raster(c, pc, c->list_visible[1], &c->counters->visible[1], &c->counters->work[1]), c->num_sms, s)); ++launches;
-		mark(); // 6
-		if (!(flags & VKV_FRAME_NO_HIZ)) CK(launch_hiz(make_hiz(c), c->num_sms, s, &launches));
-		mark(); // 7
+		mark(E_RASTER_B);
+		if (merge) { rc = enqueue_merge(c, &launches); if (rc) return rc; }
+		mark(E_MERGE_B);
+		if (hiz) CK(launch_hiz(make_hiz(c), c->num_sms, s, &launches));
+		mark(E_HIZ_B);
 	}
 	if (out) {
 		memset(out, 0, sizeof(*out));
 		CK(cudaMemcpyAsync(c->h_counters, c->counters, sizeof(FrameCounters), cudaMemcpyDeviceToHost, s));
+		uint32_t merge_err = 0;
+		if (merge) CK(cudaMemcpyAsync(&merge_err, c->sync_flags + kMaxRanks, 4, cudaMemcpyDeviceToHost, s));
 		CK(cudaStreamSynchronize(s));
+		if (merge_err) return fail(c, VKV_ERR_CUDA, "multi-GPU merge barrier timed out (a peer did not reach the merge)");
 		out->draws = N;
 		out->visible_a = c->h_counters->visible[0];
 		out->occluded_a = c->h_counters->occluded[0];
@@ -450,12 +498,81 @@ int vkv_frame(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, uint32_t flags, 
 		out->kernel_launches = (uint32_t)launches;
 		if (timed) {
 			auto el = [&](int a, int b) { float ms = 0; cudaEventElapsedTime(&ms, c->stage_ev[a], c->stage_ev[b]); return ms; };
-			out->clear_ms = el(0, 1); out->cull_a_ms = el(1, 2); out->raster_a_ms = el(2, 3); out->hiz_a_ms = el(3, 4);
-			if (two && !(flags & VKV_FRAME_NO_CULL)) { out->cull_b_ms = el(4, 5); out->raster_b_ms = el(5, 6); out->hiz_b_ms = el(6, 7); out->total_ms = el(0, 7); }
-			else out->total_ms = el(0, 4);
+			out->clear_ms = el(E_BEGIN, E_CLEAR); out->cull_a_ms = el(E_CLEAR, E_CULL_A); out->raster_a_ms = el(E_CULL_A, E_RASTER_A);
+			out->merge_a_ms = el(E_RASTER_A, E_MERGE_A); out->hiz_a_ms = el(E_MERGE_A, E_HIZ_A);
+			if (two) {
+				out->cull_b_ms = el(E_HIZ_A, E_CULL_B); out->raster_b_ms = el(E_CULL_B, E_RASTER_B);
+				out->merge_b_ms = el(E_RASTER_B, E_MERGE_B); out->hiz_b_ms = el(E_MERGE_B, E_HIZ_B);
+				out->total_ms = el(E_BEGIN, E_HIZ_B);
+			} else out->total_ms = el(E_BEGIN, E_HIZ_A);
 		}
 	}
 	return VKV_OK;
+}
+
+/* ---- multi-GPU ------------------------------------------------------------------------------------------------ */
+
+int vkv_set_shard(vkv_ctx* c, uint32_t first_draw, uint32_t draw_count, int enable) {
+	if (!c) return VKV_ERR_INVALID;
+	c->sharded = enable != 0;
+	c->shard_first = enable ? first_draw : 0;
+	c->shard_count = enable ? draw_count : 0;
+	return VKV_OK;
+}
+
+int vkv_ipc_export(vkv_ctx* c, void* handle128) {
+	if (!c || !handle128) return VKV_ERR_INVALID;
+	CK(cudaSetDevice(c->device));
+	if (!c->sync_flags) {
+		CK(cudaMalloc(&c->sync_flags, (kMaxRanks + 1) * 4));
+		CK(cudaMemset(c->sync_flags, 0, (kMaxRanks + 1) * 4));
+	}
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle layout");
+	cudaIpcMemHandle_t h[2];
+	CK(cudaIpcGetMemHandle(&h[0], c->vis));
+	CK(cudaIpcGetMemHandle(&h[1], c->sync_flags));
+	memcpy(handle128, h, 128);
+	return VKV_OK;
+}
+
+int vkv_ipc_attach(vkv_ctx* c, int rank, int nranks, const void* handles) {
+	if (!c || !handles) return VKV_ERR_INVALID;
+	if (nranks < 1 || nranks > kMaxRanks || rank < 0 || rank >= nranks) return fail(c, VKV_ERR_INVALID, "rank %d of %d out of range (max %d ranks)", rank, nranks, kMaxRanks);
+	if (!c->sync_flags) return fail(c, VKV_ERR_INVALID, "vkv_ipc_attach: call vkv_ipc_export first");
+	CK(cudaSetDevice(c->device));
+	CK(cudaStreamSynchronize(c->stream));
+	detach_peers(c);
+	c->mp.rank = rank; c->mp.nranks = nranks;
+	c->mp.error = c->sync_flags + kMaxRanks;
+	c->attached = true; // from here on detach_peers() closes whatever was opened
+	const cudaIpcMemHandle_t* h = (const cudaIpcMemHandle_t*)handles;
+	for (int r = 0; r < nranks; ++r) {
+		if (r == rank) { c->mp.vis[r] = c->vis; c->mp.flags[r] = c->sync_flags; continue; }
+		void *pv = nullptr, *pf = nullptr;
+		cudaError_t e = cudaIpcOpenMemHandle(&pv, h[2 * r], cudaIpcMemLazyEnablePeerAccess);
+		if (e == cudaSuccess) { c->mp.vis[r] = (unsigned long long*)pv; e = cudaIpcOpenMemHandle(&pf, h[2 * r + 1], cudaIpcMemLazyEnablePeerAccess); }
+		if (e != cudaSuccess) {
+			detach_peers(c);
+			return fail(c, VKV_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
+		}
+		c->mp.flags[r] = (uint32_t*)pf;
+	}
+	c->epoch = 0;
+	return VKV_OK;
+}
+
+int vkv_ipc_detach(vkv_ctx* c) {
+	if (!c) return VKV_ERR_INVALID;
+	CK(cudaSetDevice(c->device));
+	CK(cudaStreamSynchronize(c->stream));
+	detach_peers(c);
+	return VKV_OK;
+}
+
+int vkv_merge(vkv_ctx* c) {
+	if (!c) return VKV_ERR_INVALID;
+	CK(cudaSetDevice(c->device));
+	return enqueue_merge(c, nullptr);
 }
 
 int vkv_read_visbuffer64(vkv_ctx* c, uint64_t* host) {

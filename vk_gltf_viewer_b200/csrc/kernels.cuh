@@ -9,7 +9,8 @@ struct CullParams {
 	const vkv_Camera* camera;
 	const float* pyramid;
 	PyramidDesc pyr;
-	uint32_t n;                  // meshletDrawCount (upper bound of the work size)
+	uint32_t n;                  // number of draws this launch tests when in_list is NULL (upper bound of the work size otherwise)
+	uint32_t first;              // first MeshletDraw of this GPU's shard (in_list == NULL): draw ids stay global
 	const uint32_t* in_list;     // pass B: the draws pass A rejected by occlusion; NULL = all draws [0,n)
 	const uint32_t* in_count;    // device count of in_list
 	uint32_t* out_visible;
@@ -45,7 +46,7 @@ struct HizParams {
 };
 
 cudaError_t launch_cull(const CullParams& p, int num_sms, cudaStream_t stream);
-cudaError_t launch_iota(uint32_t* out, uint32_t n, uint32_t* count, int num_sms, cudaStream_t stream);
+cudaError_t launch_iota(uint32_t* out, uint32_t first, uint32_t n, uint32_t* count, int num_sms, cudaStream_t stream);
 cudaError_t launch_prepare_transforms(const float* transforms, const vkv_Camera* camera, uint32_t n, float* mvp, uint32_t* detNeg,
                                       int num_sms, cudaStream_t stream);
 cudaError_t launch_raster(const RasterParams& p, int num_sms, cudaStream_t stream);
@@ -53,3 +54,15 @@ cudaError_t launch_hiz(const HizParams& p, int num_sms, cudaStream_t stream, int
 cudaError_t launch_fill64(unsigned long long* dst, size_t n, unsigned long long value, int num_sms, cudaStream_t stream);
 cudaError_t launch_fill32(uint32_t* dst, size_t n, uint32_t value, int num_sms, cudaStream_t stream);
 cudaError_t launch_split_vis(const unsigned long long* vis, size_t n, uint32_t* ids, float* depth, int num_sms, cudaStream_t stream);
+
+// ---- multi-GPU visbuffer min-merge over NVLink peer memory (merge.cu) ------------------------------------------------
+constexpr int kMaxRanks = 16;
+struct MergeParams {
+	unsigned long long* vis[kMaxRanks];   // every rank's W*H visbuffer (index == rank; [rank] is the local one)
+	uint32_t* flags[kMaxRanks];           // every rank's barrier slots (kMaxRanks u32 each)
+	int rank, nranks;
+	size_t n;                             // W*H
+	uint32_t* error;                      // local: set to 1 when a barrier timed out
+};
+cudaError_t launch_xgpu_barrier(const MergeParams& p, uint32_t epoch, unsigned long long timeout_ns, cudaStream_t stream);
+cudaError_t launch_merge_min(const MergeParams& p, int num_sms, cudaStream_t stream);
