@@ -54,7 +54,8 @@ def build_scene(spec):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md): the sampler runs from
+    before the warm-up, every row is time-stamped on arrival and only rows inside [t0, t1] of the timed region count."""
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, gpu_index):
@@ -64,7 +65,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.idx)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.idx)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -73,27 +74,34 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0, t1):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1 + 0.03 and len(r) >= 9]
+        scope = "timed region"
+        if len(rows) < 3:  # very short runs: fall back to everything since the warm-up started
+            rows = [r for (t, r) in self.rows if len(r) >= 9]
+            scope = "warm-up + timed region"
+        num = lambda v: float(v) if v.replace(".", "", 1).isdigit() else None
+        sm = [x for x in (num(r[1]) for r in rows) if x is not None]
+        mx = [x for x in (num(r[2]) for r in rows) if x is not None]
+        pw = [x for x in (num(r[3]) for r in rows) if x is not None]
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            if len(r) >= 9:
-                for n, v in zip(names, r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+        for r in rows:
+            for n, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(pw) if pw else None, "scope": scope}
 
 
 def cpu_frames(scene, W, H, views, nframes, threads=0):
@@ -117,10 +125,12 @@ def cpu_frames(scene, W, H, views, nframes, threads=0):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default: 200 frames on the GPU arm, 20 on the CPU reference arm)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=3)
+    ap.add_argument("--shard", default="auto", choices=["auto", "views", "range"],
+                    help="multi-GPU: independent views per GPU (default, cfg 1-4) or one view sharded by MeshletDraw range (cfg 5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--one-pass", action="store_true", help="reference one-pass mode instead of the two-pass extension")
     args = ap.parse_args()
@@ -138,7 +148,7 @@ def main():
         scene = build_scene(spec)
         cnt = scene.counts()
         views = [scene.default_view(i, NVIEWS) for i in range(NVIEWS)]
-        steps = max(1, args.steps)
+        steps = max(1, args.steps if args.steps is not None else 20)
         for _ in range(max(0, args.warmup - 1)):
             pass  # cpu_frames always runs one warm-up frame (it also seeds the pyramid); extra warm-ups add nothing on a CPU
         times = cpu_frames(scene, W, H, views, steps)
@@ -159,7 +169,7 @@ def main():
         return
 
     # ------------------------------------------------------------------ our arm (CUDA)
-    from vk_gltf_viewer_b200 import api
+    from vk_gltf_viewer_b200 import api, multigpu
     from vk_gltf_viewer_b200.scene import Camera
 
     dist = None
@@ -169,17 +179,25 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    shard = args.shard if args.shard != "auto" else ("range" if args.config == 5 else "views")
     scene = build_scene(spec)
     cnt = scene.counts()
     views = [scene.default_view(i, NVIEWS) for i in range(NVIEWS)]
-    # view sharding: rank r renders views r, r+world, ...
-    my_views = [views[(rank + i * world) % NVIEWS] for i in range(args.warmup + args.steps + 1)]
+    steps, warm = max(1, args.steps if args.steps is not None else 200), max(3, args.warmup)
+    if shard == "views":   # rank r renders views r, r+world, ...: no data-path collective
+        my_views = [views[(rank + i * world) % NVIEWS] for i in range(warm + steps + 1)]
+    else:                  # every rank renders the SAME views, each its own range of the draw list
+        my_views = [views[i % NVIEWS] for i in range(warm + steps + 1)]
 
     r = api.Renderer(W, H, device=local_rank)
     cam = Camera(W, H)
     cam.look_at(*my_views[0])
     pc = r.upload_scene(scene, cam)
     flags = api.FRAME_ONE_PASS if args.one_pass else api.FRAME_TWO_PASS
+    if shard == "range" and world > 1:
+        r.set_shard_interleaved(rank, world, 11)  # 2048-draw blocks round-robin: balances the surviving work (a contiguous half does not)
+        multigpu.attach_peers(r, dist)
+        flags |= api.FRAME_MERGE
     # all cameras of the sweep resident in HBM: the device-timed loop switches the camera ADDRESS per frame
     cam_addrs = []
     for v in my_views[1:]:
@@ -193,62 +211,66 @@ def main():
             import torch
             torch.cuda.synchronize()
 
-    # warm-up (>= 3): also seeds the pyramid
-    r.frame(pc, flags)
-    for k in range(max(3, args.warmup)):
-        pc.cameraBuffer = cam_addrs[k % len(cam_addrs)]
-        r.frame(pc, flags)
-
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
 
+    # warm-up (>= 3): also seeds the pyramid
+    r.frame(pc, flags)
+    for k in range(warm):
+        pc.cameraBuffer = cam_addrs[k % len(cam_addrs)]
+        r.frame(pc, flags)
+
     # ---- device-timed: K frames, each bracketed by CUDA events on the launching stream; L2 flushed between frames
     barrier()
+    t_begin = time.time()
     per = []
-    stage = {k: 0.0 for k in ("clear_ms", "cull_a_ms", "raster_a_ms", "hiz_a_ms", "cull_b_ms", "raster_b_ms", "hiz_b_ms")}
+    stage_names = ("clear_ms", "cull_a_ms", "raster_a_ms", "merge_a_ms", "hiz_a_ms", "cull_b_ms", "raster_b_ms", "merge_b_ms", "hiz_b_ms")
+    stage = {k: 0.0 for k in stage_names}
     vis_a = vis_b = occ_a = 0
     launches = 0
-    for k in range(args.steps):
-        pc.cameraBuffer = cam_addrs[(args.warmup + k) % len(cam_addrs)]
+    for k in range(steps):
+        pc.cameraBuffer = cam_addrs[(warm + k) % len(cam_addrs)]
         r.flush_l2(256 << 20)
         st = r.frame(pc, flags | api.FRAME_TIMED)
         per.append(st.total_ms)
-        for s in stage:
-            stage[s] += getattr(st, s)
+        for sname in stage:
+            stage[sname] += getattr(st, sname)
         vis_a += st.visible_a; vis_b += st.visible_b; occ_a += st.occluded_a
-        launches += st.kernel_launches
+        launches += st.kernel_launches + 1  # + the L2-flush fill kernel
     barrier()
+    t_end = time.time()
     dev_ms = sum(per)
 
     # ---- end to end through the C ABI with HOST buffers: per step H2D camera + transforms (the reference re-uploads
     # both every frame: camera.cpp:180-193, world.cpp:321-344) and D2H of the frame's counters (vkv_stats)
     transforms = np.ascontiguousarray(scene.transforms())
-    pc.cameraBuffer = cam_addrs[0]
     own_cam = r.upload(np.frombuffer(cam.raw(), np.uint8))
     pc.cameraBuffer = own_cam
     h2d = 352 + transforms.nbytes
     d2h = 256
     barrier()
     t0 = time.perf_counter()
-    for k in range(args.steps):
-        cam.look_at(*my_views[1 + (args.warmup + k) % (len(my_views) - 1)])
+    for k in range(steps):
+        cam.look_at(*my_views[1 + (warm + k) % (len(my_views) - 1)])
         r._ck(r.L.vkv_update(r.h, own_cam, cam.raw(), 352))
         r._ck(r.L.vkv_update(r.h, pc.transformBuffer, transforms.ctypes.data, transforms.nbytes))
         r.frame(pc, flags)  # returns vkv_stats: blocking D2H of the counters
     barrier()
     e2e_s = time.perf_counter() - t0
 
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
 
     if dist is not None:
         import torch
         t = torch.tensor([dev_ms, e2e_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_ms, e2e_s = t.tolist()
-        ln = torch.tensor([launches], device="cuda", dtype=torch.int64)
+        ln = torch.tensor([launches, vis_a, vis_b, occ_a], device="cuda", dtype=torch.int64)
         dist.all_reduce(ln)
-        launches = int(ln.item())
+        launches = int(ln[0].item())
+        if shard == "range":
+            vis_a, vis_b, occ_a = int(ln[1].item()), int(ln[2].item()), int(ln[3].item())
 
     if rank == 0:
         peaks = {}
@@ -257,44 +279,61 @@ def main():
         except Exception:
             pass
         hbm = peaks.get("hbm_gbs", 6650.0)
-        peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
-        K = args.steps
-        fps = world * K / (dev_ms / 1e3)
-        # algorithmic bytes per launch (SURVEY §8d definitions)
-        N = cnt.draws
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+        K = steps
+        frames_total = world * K if shard == "views" else K
+        fps = frames_total / (dev_ms / 1e3)
+        # algorithmic bytes per launch (SURVEY §8d definitions), per GPU
+        per_gpu = 1.0 / world if shard == "range" else 1.0
+        N = cnt.draws * per_gpu
         U = cnt.meshlets_unique * 36 + cnt.transforms * 64 + cnt.primitives * 64 + 352
         pyr_bytes = 4 * r.pyramid_floats
-        avg = lambda x: x / K
+        avg = lambda x: x / K * per_gpu
         bytes_cull_a = 12 * N + U + 4 * (avg(vis_a) + avg(occ_a))
         bytes_cull_b = 4 * avg(occ_a) + 12 * avg(occ_a) + U + 4 * avg(vis_b)
         bytes_hiz = 8 * W * H + pyr_bytes  # depth is read fused from the 64-bit visbuffer: 8 B/pixel, not 4
         bytes_clear = 8 * W * H
         per_meshlet = 48 + 28 * 64 + 3 * 95
-        bytes_raster_a = avg(vis_a) * per_meshlet
+        bytes_merge = 8 * W * H * 2 if (flags & api.FRAME_MERGE) else 0  # per GPU: strip read from n ranks + written to n ranks = 2 * 8WH
         stages = {}
-        for name, b, ms in (("clear", bytes_clear, stage["clear_ms"]), ("cull_a", bytes_cull_a, stage["cull_a_ms"]), ("raster_a", bytes_raster_a, stage["raster_a_ms"]),
-                            ("hiz_a", bytes_hiz, stage["hiz_a_ms"]), ("cull_b", bytes_cull_b, stage["cull_b_ms"]), ("raster_b", avg(vis_b) * per_meshlet, stage["raster_b_ms"]),
+        for name, b, ms in (("clear", bytes_clear, stage["clear_ms"]), ("cull_a", bytes_cull_a, stage["cull_a_ms"]),
+                            ("raster_a", avg(vis_a) * per_meshlet, stage["raster_a_ms"]), ("merge_a", bytes_merge, stage["merge_a_ms"]),
+                            ("hiz_a", bytes_hiz, stage["hiz_a_ms"]), ("cull_b", bytes_cull_b, stage["cull_b_ms"]),
+                            ("raster_b", avg(vis_b) * per_meshlet, stage["raster_b_ms"]), ("merge_b", bytes_merge, stage["merge_b_ms"]),
                             ("hiz_b", bytes_hiz, stage["hiz_b_ms"])):
             m = ms / K
+            if m <= 0 and b == 0:
+                continue
             gbs = (b / 1e9) / (m / 1e3) if m > 0 else 0.0
             stages[name] = {"ms": round(m, 5), "bytes": int(b), "GB/s": round(gbs, 1), "frac_hbm": round(gbs / hbm, 4)}
-        dom = max(stages, key=lambda s: stages[s]["ms"])
+        dom = max(stages, key=lambda sname: stages[sname]["ms"])
+        traffic = None
+        try:  # dram bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this workload
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            ent = tr.get(f"cfg{args.config}", {}).get(dom)
+            if ent and world == 1:
+                traffic = ent["dram_read_bytes"] + ent["dram_write_bytes"]
+        except Exception:
+            pass
         line = {
             "metric": "frames/s (two-pass cull + HiZ + visbuffer)" if not args.one_pass else "frames/s (one-pass cull + visbuffer + HiZ)",
-            "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": max(3, args.warmup),
-            "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": warm,
+            "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak" if shard == "views" else "strong", "vs_baseline": None,
             "dtype": "f32+u64", "data": "synthetic",
             "gtris_per_s": cnt.triangles_instanced * fps / 1e9,
-            "config": {"workload": label, "resolution": [W, H], "meshlet_draws": N, "triangles": cnt.triangles_instanced,
-                       "passes": 1 if args.one_pass else 2, "parallelism": f"views sharded over {world} GPU(s), scene replicated",
+            "config": {"workload": label, "resolution": [W, H], "meshlet_draws": cnt.draws, "triangles": cnt.triangles_instanced,
+                       "passes": 1 if args.one_pass else 2,
+                       "parallelism": (f"views sharded over {world} GPU(s), scene replicated, no collective" if shard == "views" else
+                                       f"one view, MeshletDraw list sharded over {world} GPU(s) in interleaved 2048-draw ranges, u64 min-merge over NVLink peer memory before each HiZ build"),
                        "l2": "256 MB scratch written between timed frames (L2 flush); each frame timed by its own CUDA event pair",
-                       "visible_a_avg": avg(vis_a), "occluded_a_avg": avg(occ_a), "visible_b_avg": avg(vis_b)},
-            "e2e": {"value": world * K / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                       "visible_a_avg": vis_a / K, "occluded_a_avg": occ_a / K, "visible_b_avg": vis_b / K},
+            "e2e": {"value": frames_total / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "note": "camera + all node transforms uploaded from host every frame, frame counters read back every frame (wall clock, no L2 flush)"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["GB/s"], "peak": hbm, "unit": "GB/s", "frac": stages[dom]["frac_hbm"],
-                         "traffic": None, "peak_source": peak_src,
-                         "note": "raster is L2-atomic / issue bound, its GB/s is input-side bytes only (SURVEY §8d); see stages for cull/HiZ/clear fractions"},
+                         "traffic": traffic, "peak_source": peak_src,
+                         "note": "dominant kernel = software rasteriser: SM-issue / L2-atomic bound, working set L2 resident (dram traffic << algorithmic input bytes); "
+                                 "`achieved` = input-side algorithmic bytes (SURVEY §8d) / CUDA-event time; cull / HiZ / clear fractions are in `stages`"},
             "stages": stages,
             "clocks": clocks,
         }
@@ -307,6 +346,7 @@ def main():
         print(json.dumps(line))
     r.close()
     if dist is not None:
+        dist.barrier()
         dist.destroy_process_group()
 
 

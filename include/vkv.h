@@ -95,6 +95,9 @@ int vkv_raster_list(vkv_ctx*, const vkv_VisbufferPushConstants* pc, const uint32
  * (visbuffer.h.glsl:15-16), so the merged image is bit-identical to a single-GPU frame. -------------------------------- */
 /* this GPU culls / rasterises MeshletDraws [first_draw, first_draw + draw_count) of pc->drawBuffer; enable = 0 restores the whole list */
 int vkv_set_shard(vkv_ctx*, uint32_t first_draw, uint32_t draw_count, int enable);
+/* load-balanced variant: the list is cut into blocks of 2^block_log2 draws dealt round-robin, rank r owns blocks r, r+n, ...
+ * (occlusion makes contiguous halves of a list very unequal in surviving work); nranks = 1 switches sharding off */
+int vkv_set_shard_interleaved(vkv_ctx*, int rank, int nranks, uint32_t block_log2);
 /* 128-byte opaque handle (two cudaIpcMemHandle_t: visbuffer + barrier flags) to pass to the other ranks (any transport) */
 int vkv_ipc_export(vkv_ctx*, void* handle128);
 /* handles = nranks * 128 bytes, in rank order (the caller's own entry is ignored); opens the peers' buffers */

@@ -30,8 +30,13 @@ def main():
     pc_dev = r.upload_scene(scene, cam)
     pc_host = scene.host_push_constants(cam)
     N = pc_host.meshletDrawCount
-    first, count = multigpu.shard_range(N, rank, world)
-    r.set_shard(first, count)
+    if mode.endswith("interleaved"):   # blocks of 32 draws dealt round-robin (small scene: make the interleave real)
+        r.set_shard_interleaved(rank, world, 5)
+        mine = lambda ids: ids[multigpu.interleaved_owner(ids, world, 5) == rank]
+    else:
+        first, count = multigpu.shard_range(N, rank, world)
+        r.set_shard(first, count)
+        mine = lambda ids: ids[(ids >= first) & (ids < first + count)]
     multigpu.attach_peers(r, dist)
     tg = O.Targets(W, H)
     for k, (eye, center) in enumerate(views):
@@ -39,7 +44,7 @@ def main():
             cam.look_at(eye, center)
             r.update_camera(pc_dev, cam)
         out = O.frame(pc_host, tg, two_pass=True)
-        if mode == "p2p":
+        if mode.startswith("p2p"):
             st = r.frame(pc_dev, api.FRAME_TWO_PASS | api.FRAME_MERGE | api.FRAME_STATUS)
         else:  # library collective as the cross-check: stage by stage with ncclAllReduce(min) in place of vkv_merge
             r.clear()
@@ -49,7 +54,6 @@ def main():
         vis = r.read_visbuffer64()
         assert np.array_equal(vis, tg.vis64()), f"rank {rank} view {k}: merged visbuffer differs from the single-list oracle ({int((vis != tg.vis64()).sum())} keys)"
         assert np.array_equal(r.read_pyramid().view(np.uint32), tg.pyramid.view(np.uint32)), f"rank {rank} view {k}: pyramid differs"
-        mine = lambda ids: ids[(ids >= first) & (ids < first + count)]
         assert np.array_equal(np.sort(r.read_visible(0)), mine(out["visibleA"])), f"rank {rank} view {k}: pass-A set"
         assert np.array_equal(np.sort(r.read_visible(1)), mine(out["visibleB"])), f"rank {rank} view {k}: pass-B set"
         nA = torch.tensor([r.read_visible(0).size, r.read_visible(1).size], device="cuda")

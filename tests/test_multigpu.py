@@ -33,6 +33,16 @@ def test_shard_range_partitions_the_list():
         multigpu.shard_range(10, 2, 2)
 
 
+def test_interleaved_owner_covers_every_draw_once():
+    ids = np.arange(100000, dtype=np.uint32)
+    for world in (2, 3, 4, 8):
+        own = multigpu.interleaved_owner(ids, world, 11)
+        assert own.min() == 0 and own.max() == world - 1
+        assert (own[:2048] == 0).all() and (own[2048:4096] == 1).all()
+        counts = np.bincount(own.astype(np.int64), minlength=world)
+        assert counts.sum() == ids.size and counts.max() - counts.min() <= 2048
+
+
 def test_view_shard_round_robin():
     for world in (1, 2, 4, 8):
         seen = sorted(v for r in range(world) for v in multigpu.view_shard(64, r, world))
@@ -115,7 +125,7 @@ def _ngpus():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", ["p2p", "nccl"])
+@pytest.mark.parametrize("mode", ["p2p", "nccl", "p2p-interleaved"])
 def test_range_sharded_frames_match_single_list_oracle(mode):
     n = _ngpus()
     if n < 2:

@@ -47,7 +47,7 @@ EXPORTS = [
     "vkv_read_visbuffer64", "vkv_read_ids", "vkv_read_depth", "vkv_read_hiz_mip", "vkv_read_pyramid", "vkv_write_pyramid",
     "vkv_read_visible", "vkv_read_status", "vkv_pyramid_floats",
     "vkv_event_record", "vkv_event_elapsed", "vkv_flush_l2", "vkv_visbuffer64_ptr",
-    "vkv_set_shard", "vkv_ipc_export", "vkv_ipc_attach", "vkv_ipc_detach", "vkv_merge",
+    "vkv_set_shard", "vkv_set_shard_interleaved", "vkv_ipc_export", "vkv_ipc_attach", "vkv_ipc_detach", "vkv_merge",
 ]
 
 _bound = False
@@ -92,6 +92,7 @@ def _lib():
         L.vkv_visbuffer64_ptr.argtypes = [vp]
         L.vkv_visbuffer64_ptr.restype = u64
         L.vkv_set_shard.argtypes = [vp, u32, u32, i]
+        L.vkv_set_shard_interleaved.argtypes = [vp, i, i, u32]
         L.vkv_ipc_export.argtypes = [vp, vp]
         L.vkv_ipc_attach.argtypes = [vp, i, i, vp]
         L.vkv_ipc_detach.argtypes = [vp]
@@ -243,6 +244,9 @@ class Renderer:
     # ---- multi-GPU (meshlet-range sharding) ---------------------------------------------------
     def set_shard(self, first_draw=0, draw_count=0, enable=True):
         self._ck(self.L.vkv_set_shard(self.h, first_draw, draw_count, 1 if enable else 0))
+
+    def set_shard_interleaved(self, rank, nranks, block_log2=11):
+        self._ck(self.L.vkv_set_shard_interleaved(self.h, rank, nranks, block_log2))
 
     def ipc_export(self) -> bytes:
         buf = C.create_string_buffer(128)

@@ -36,7 +36,8 @@ struct vkv_ctx {
 	uint32_t xf_cap = 0;
 	uint32_t xf_count = 0;
 	// multi-GPU: this GPU's shard of the draw list and the peers' visbuffers mapped through CUDA IPC
-	uint32_t shard_first = 0, shard_count = 0;
+	uint32_t shard_first = 0, shard_count = 0;       // contiguous shard
+	uint32_t shard_block_log2 = 0, shard_rank = 0, shard_nranks = 1; // interleaved shard (blocks of 2^k draws, round-robin)
 	bool sharded = false;
 	MergeParams mp{};
 	bool attached = false;
@@ -182,8 +183,18 @@ CullParams make_cull(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, int pass,
 	p.camera = (const vkv_Camera*)pc->cameraBuffer;
 	p.pyramid = c->pyramid;
 	p.pyr = c->pyr;
-	p.n = c->sharded ? c->shard_count : pc->meshletDrawCount;
-	p.first = c->sharded ? c->shard_first : 0u;
+	p.total = pc->meshletDrawCount;
+	p.n = pc->meshletDrawCount;
+	if (c->sharded && c->shard_block_log2) { // local index space: my blocks, the last one possibly ragged (bounded by `total` in the kernel)
+		const uint32_t B = c->shard_block_log2;
+		const uint64_t blocks = ((uint64_t)pc->meshletDrawCount + (1u << B) - 1) >> B;
+		const uint64_t mine = blocks > c->shard_rank ? (blocks - c->shard_rank + c->shard_nranks - 1) / c->shard_nranks : 0;
+		p.n = (uint32_t)(mine << B);
+		p.shard_block_log2 = B; p.shard_rank = c->shard_rank; p.shard_nranks = c->shard_nranks;
+	} else if (c->sharded) {
+		p.n = c->shard_count;
+		p.first = c->shard_first;
+	}
 	p.in_list = pass == 0 ? nullptr : c->list_occluded[0];
 	p.in_count = pass == 0 ? nullptr : &c->counters->occluded[0];
 	p.out_visible = c->list_visible[pass];
@@ -220,7 +231,7 @@ int check_pc(vkv_ctx* c, const vkv_VisbufferPushConstants* pc) {
 	if (!pc) return fail(c, VKV_ERR_INVALID, "push constants are NULL");
 	if (pc->meshletDrawCount && (!pc->drawBuffer || !pc->transformBuffer || !pc->primitiveBuffer || !pc->cameraBuffer || !pc->materialBuffer))
 		return fail(c, VKV_ERR_INVALID, "push constants hold a NULL buffer address");
-	if (c->sharded && (uint64_t)c->shard_first + c->shard_count > pc->meshletDrawCount)
+	if (c->sharded && !c->shard_block_log2 && (uint64_t)c->shard_first + c->shard_count > pc->meshletDrawCount)
 		return fail(c, VKV_ERR_INVALID, "draw shard [%u, +%u) exceeds meshletDrawCount %u", c->shard_first, c->shard_count, pc->meshletDrawCount);
 	return ensure_draws(c, pc->meshletDrawCount);
 }
@@ -390,7 +401,7 @@ int vkv_cull(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, int pass, uint32_
 	CullParams p = make_cull(c, pc, pass, flags);
 	if (p.status) CK(cudaMemsetAsync(p.status, VKV_ST_NOT_TESTED, pc->meshletDrawCount, c->stream));
 	c->status_valid[pass] = p.status != nullptr;
-	if (pc->meshletDrawCount) CK(launch_cull(p, c->num_sms, c->stream));
+	if (p.n) CK(launch_cull(p, c->num_sms, c->stream));
 	if (n_visible) {
 		CK(cudaMemcpyAsync(c->h_counters, c->counters, sizeof(FrameCounters), cudaMemcpyDeviceToHost, c->stream));
 		CK(cudaStreamSynchronize(c->stream));
@@ -443,7 +454,6 @@ int vkv_frame(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, uint32_t flags, 
 	const bool merge = (flags & VKV_FRAME_MERGE) != 0;
 	const bool hiz = !(flags & VKV_FRAME_NO_HIZ);
 	const uint32_t N = pc->meshletDrawCount;
-	const uint32_t first = c->sharded ? c->shard_first : 0u, cnt = c->sharded ? c->shard_count : N;
 	if (merge && !c->attached) return fail(c, VKV_ERR_INVALID, "VKV_FRAME_MERGE needs vkv_ipc_attach first");
 	int launches = 0;
 	enum { E_BEGIN, E_CLEAR, E_CULL_A, E_RASTER_A, E_MERGE_A, E_HIZ_A, E_CULL_B, E_RASTER_B, E_MERGE_B, E_HIZ_B, E_COUNT };
@@ -453,13 +463,14 @@ int vkv_frame(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, uint32_t flags, 
 	CK(launch_fill64(c->vis, (size_t)c->W * c->H, VKV_VIS64_CLEAR, c->num_sms, s)); ++launches; // application.cpp:782,807
 	mark(E_CLEAR);
 	if (flags & VKV_FRAME_NO_CULL) {
-		CK(launch_iota(c->list_visible[0], first, cnt, &c->counters->visible[0], c->num_sms, s)); ++launches;
+		CullParams p = make_cull(c, pc, 0, 0);
+		CK(launch_iota(p, c->list_visible[0], &c->counters->visible[0], c->num_sms, s)); ++launches;
 		c->status_valid[0] = false;
 	} else {
 		CullParams p = make_cull(c, pc, 0, flags);
 		if (p.status) CK(cudaMemsetAsync(p.status, VKV_ST_NOT_TESTED, N, s));
 		c->status_valid[0] = p.status != nullptr;
-		if (cnt) { CK(launch_cull(p, c->num_sms, s)); ++launches; }
+		if (p.n) { CK(launch_cull(p, c->num_sms, s)); ++launches; }
 	}
 	mark(E_CULL_A);
 	rc = prepare_transforms(c, pc, &launches);
@@ -474,7 +485,7 @@ int vkv_frame(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, uint32_t flags, 
 		CullParams p = make_cull(c, pc, 1, flags);
 		if (p.status) CK(cudaMemsetAsync(p.status, VKV_ST_NOT_TESTED, N, s));
 		c->status_valid[1] = p.status != nullptr;
-		if (cnt) { CK(launch_cull(p, c->num_sms, s)); ++launches; }
+		if (p.n) { CK(launch_cull(p, c->num_sms, s)); ++launches; }
 		mark(E_CULL_B);
 		CK(launch_raster(make_raster(c, pc, c->list_visible[1], &c->counters->visible[1], &c->counters->work[1]), c->num_sms, s)); ++launches;
 		mark(E_RASTER_B);
@@ -517,6 +528,17 @@ int vkv_set_shard(vkv_ctx* c, uint32_t first_draw, uint32_t draw_count, int enab
 	c->sharded = enable != 0;
 	c->shard_first = enable ? first_draw : 0;
 	c->shard_count = enable ? draw_count : 0;
+	c->shard_block_log2 = 0; c->shard_rank = 0; c->shard_nranks = 1;
+	return VKV_OK;
+}
+
+int vkv_set_shard_interleaved(vkv_ctx* c, int rank, int nranks, uint32_t block_log2) {
+	if (!c) return VKV_ERR_INVALID;
+	if (nranks < 1 || rank < 0 || rank >= nranks || block_log2 < 5 || block_log2 > 24)
+		return fail(c, VKV_ERR_INVALID, "interleaved shard: rank %d of %d, block 2^%u (need 2^5..2^24 draws)", rank, nranks, block_log2);
+	c->sharded = nranks > 1;
+	c->shard_first = 0; c->shard_count = 0;
+	c->shard_block_log2 = nranks > 1 ? block_log2 : 0; c->shard_rank = (uint32_t)rank; c->shard_nranks = (uint32_t)nranks;
 	return VKV_OK;
 }
 

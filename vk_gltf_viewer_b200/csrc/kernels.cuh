@@ -11,6 +11,9 @@ struct CullParams {
 	PyramidDesc pyr;
 	uint32_t n;                  // number of draws this launch tests when in_list is NULL (upper bound of the work size otherwise)
 	uint32_t first;              // first MeshletDraw of this GPU's shard (in_list == NULL): draw ids stay global
+	uint32_t shard_block_log2;   // interleaved sharding: blocks of 2^k draws dealt round-robin to the ranks (0 = contiguous)
+	uint32_t shard_rank, shard_nranks;
+	uint32_t total;              // meshletDrawCount (bound for interleaved ids)
 	const uint32_t* in_list;     // pass B: the draws pass A rejected by occlusion; NULL = all draws [0,n)
 	const uint32_t* in_count;    // device count of in_list
 	uint32_t* out_visible;
@@ -46,7 +49,7 @@ struct HizParams {
 };
 
 cudaError_t launch_cull(const CullParams& p, int num_sms, cudaStream_t stream);
-cudaError_t launch_iota(uint32_t* out, uint32_t first, uint32_t n, uint32_t* count, int num_sms, cudaStream_t stream);
+cudaError_t launch_iota(const CullParams& p, uint32_t* out, uint32_t* count, int num_sms, cudaStream_t stream);
 cudaError_t launch_prepare_transforms(const float* transforms, const vkv_Camera* camera, uint32_t n, float* mvp, uint32_t* detNeg,
                                       int num_sms, cudaStream_t stream);
 cudaError_t launch_raster(const RasterParams& p, int num_sms, cudaStream_t stream);

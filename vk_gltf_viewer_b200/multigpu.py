@@ -23,6 +23,11 @@ def shard_range(n_draws: int, rank: int, world: int):
     return lo, hi - lo
 
 
+def interleaved_owner(draw_ids, world: int, block_log2: int = 11):
+    """rank owning each MeshletDraw under vkv_set_shard_interleaved: block b = id >> block_log2 belongs to rank b mod world"""
+    return (np.asarray(draw_ids, dtype=np.uint64) >> np.uint64(block_log2)) % np.uint64(world)
+
+
 def view_shard(n_views: int, rank: int, world: int):
     """round-robin view assignment: view i -> rank i mod world"""
     return list(range(rank, n_views, world))
