@@ -222,7 +222,8 @@ RasterParams make_raster(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, const
 
 HizParams make_hiz(vkv_ctx* c) {
 	HizParams h{};
-	h.vis = c->vis; h.pyramid = c->pyramid; h.pyr = c->pyr; h.W = c->W; h.H = c->H; h.exact_levels = c->exact_levels;
+	h.vis = c->vis; h.pyramid = c->pyramid; h.pyr = c->pyr; h.W = c->W; h.H = c->H; h.exact_levels = c->exact_levels; h.done = (getenv("VKV_HIZ_NOTAIL") || getenv("VKV_HIZ_SPLIT")) ? nullptr : &c->counters->hiz_done; /* diagnosis switches */
+	h.split_tail = getenv("VKV_HIZ_SPLIT") ? 1 : 0;
 	return h;
 }
 

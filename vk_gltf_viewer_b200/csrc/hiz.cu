@@ -2,21 +2,205 @@
 // Replaces shaders/hiz_reduce.comp.glsl:21-31 and its per-mip dispatch loop (application.cpp:951-1003): the reference
 // issues one 32x32-group dispatch per mip with a full barrier between mips (9-12 serialised launches); here the
 // leading "exact 2x" mips are produced by ONE tiled launch straight from the visbuffer (depth extraction fused into
-// the level-0 read), and the remaining small mips by ONE single-block launch that restates the min-sampler footprint
-// rule texel by texel (i0 = floor(u*S - 0.5), {i0, i0+1} minus zero-weight texels, CLAMP_TO_EDGE).
+// the level-0 read); the block of that launch that finishes LAST then produces the remaining small mips, staged in shared
+// memory level after level, restating the min-sampler footprint rule texel by texel (i0 = floor(u*S - 0.5),
+// {i0, i0+1} minus zero-weight texels, CLAMP_TO_EDGE).  One launch per pyramid build.
 #include "kernels.cuh"
+#ifdef VKV_HIZ_DEBUG
+#include <cstdio>
+#define TS(i) do { if (threadIdx.x == 0) dbg_ts[i] = clock64(); } while (0)
+#else
+#define TS(i)
+#endif
+
 
 namespace {
 
 constexpr int kTileW = 64, kTileH = 16; // source pixels per warp tile; yields 32x8, 16x4, 8x2, 4x1 texels of mips 0..3
-constexpr int kHizWarps = 8;
+constexpr int kHizWarps = 32; // 1024 threads: the last block also runs the serial small-mip tail, which wants the whole SM
 
 __device__ __forceinline__ float min4(float a, float b, float c, float d) { return gmin(gmin(gmin(a, b), c), d); }
+
+// Remaining mips, ONE block, level after level (each level is a few thousand texels at most and depends on the previous).
+// first_level = index of the first pyramid mip to produce here.  Everything the serial chain touches lives in shared memory:
+//   * the pyramid geometry (dynamic indexing of kernel parameters costs a constant-cache miss per level),
+//   * the separable sampler footprints of ALL tail levels, evaluated up front (columns depend on x only, rows on y only),
+//   * the source mip of the first tail level, staged with coalesced 16-byte L2 loads when it fits (4K / 1080p: 240x135),
+//   * every produced level (two ping-pong buffers; levels shrink 4x).
+constexpr uint32_t kTailSrc = 33792;                     // floats: staged source of the first tail level (240x135 = 32400)
+constexpr uint32_t kTailBufA = 8192, kTailBufB = 2304;   // floats: 120x67 and 60x33
+constexpr uint32_t kFpCap = 1024;                        // ushort2 entries: column + row footprints of all tail levels
+constexpr size_t kTailSmemBytes = (kTailSrc + kTailBufA + kTailBufB) * 4 + kFpCap * 4 + 64 * 4;
+
+struct TailSmem {
+	float* src; float* bufA; float* bufB; ushort2* fp; uint32_t* geo;
+	__device__ explicit TailSmem(unsigned char* base) {
+		src = (float*)base; bufA = src + kTailSrc; bufB = bufA + kTailBufA; fp = (ushort2*)(bufB + kTailBufB); geo = (uint32_t*)(fp + kFpCap);
+	}
+};
+
+__device__ __forceinline__ void hiz_tail(const HizParams& p, uint32_t first_level, const TailSmem& sm) {
+#ifdef VKV_HIZ_DEBUG
+	__shared__ long long dbg_ts[24];
+#endif
+	TS(0);
+	// geometry -> shared: geo[k] = off, geo[16+k] = w, geo[32+k] = h, geo[48+k] = footprint table offset of level k
+	if (threadIdx.x < 16) {
+		sm.geo[threadIdx.x] = p.pyr.off[threadIdx.x];
+		sm.geo[16 + threadIdx.x] = p.pyr.w[threadIdx.x];
+		sm.geo[32 + threadIdx.x] = p.pyr.h[threadIdx.x];
+	}
+	if (threadIdx.x == 0) { // table offsets; 0xffffffff = level does not fit (evaluated per texel instead)
+		uint32_t o = 0;
+		for (uint32_t k = 0; k < 16; ++k) {
+			const uint32_t dw = p.W >> (k + 1), dh = p.H >> (k + 1);
+			if (k >= first_level && k >= 1 && k < p.pyr.levels && dw && dh && o + dw + dh <= kFpCap) { sm.geo[48 + k] = o; o += dw + dh; }
+			else sm.geo[48 + k] = 0xffffffffu;
+		}
+	}
+	__syncthreads();
+	TS(1);
+	const uint32_t levels = p.pyr.levels;
+	{ // footprint tables of all tail levels: 4 warps per level, so the per-level latency chains run side by side
+		const uint32_t wid = threadIdx.x >> 5, part = wid & 3u, groups = max(1u, blockDim.x >> 7);
+		for (uint32_t k = (first_level < 1 ? 1 : first_level) + (wid >> 2); k < levels; k += groups) {
+			const uint32_t fo = sm.geo[48 + k];
+			if (fo == 0xffffffffu) continue;
+			const uint32_t dw = p.W >> (k + 1), dh = p.H >> (k + 1), sw = sm.geo[16 + k - 1], sh = sm.geo[32 + k - 1];
+			// hiz_reduce.comp.glsl:28: uv = (pos + 0.5) / imageSize, through the min-sampler footprint rule
+			for (uint32_t e = part * 32 + (threadIdx.x & 31); e < dw + dh; e += 128) {
+				const bool col = e < dw;
+				const uint32_t pos = col ? e : e - dw;
+				int lo, hi;
+				footprint(((float)pos + 0.5f) / (float)(col ? dw : dh), col ? sw : sh, lo, hi);
+				sm.fp[fo + e] = make_ushort2((unsigned short)lo, (unsigned short)hi);
+			}
+		}
+	}
+	TS(2);
+	// stage the first level's source
+	const float* ssrc = nullptr;   // shared-memory copy of mip k-1 (row stride = its width), or NULL
+	if (first_level >= 1 && first_level < levels) {
+		const uint32_t sw = sm.geo[16 + first_level - 1], sh = sm.geo[32 + first_level - 1], n = sw * sh, off = sm.geo[first_level - 1];
+		if (n <= kTailSrc && (off & 3) == 0) {
+			const float4* g = (const float4*)(p.pyramid + off);
+			for (uint32_t t = threadIdx.x; t < (n >> 2); t += blockDim.x) ((float4*)sm.src)[t] = __ldcg(g + t); // written by other blocks: L2
+			for (uint32_t t = (n & ~3u) + threadIdx.x; t < n; t += blockDim.x) sm.src[t] = __ldcg(p.pyramid + off + t);
+			ssrc = sm.src;
+		}
+	}
+	__syncthreads();
+	TS(3);
+
+	float* cur = sm.bufA; uint32_t curCap = kTailBufA;
+	float* oth = sm.bufB; uint32_t othCap = kTailBufB;
+	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+	for (uint32_t k = first_level; k < levels; ++k) {
+		const uint32_t i = k + 1;                       // reference view index of the destination (application.cpp:964)
+		const uint32_t dw = p.W >> i, dh = p.H >> i;    // levelSize
+		if (dw == 0 || dh == 0) continue;               // zero-sized dispatch: mip keeps its contents (SURVEY Q5)
+		float* dst = p.pyramid + sm.geo[k];
+		const uint32_t dstride = sm.geo[16 + k];
+		float* sdst = (dw * dh <= curCap && dstride == dw) ? cur : nullptr;
+		if (k == 0) {
+			// source = depth image itself (only when no level was exact, e.g. odd W/H): read depth from the visbuffer keys
+			for (uint32_t t = threadIdx.x; t < dw * dh; t += blockDim.x) {
+				const uint32_t x = t % dw, y = t / dw;
+				const float u = ((float)x + 0.5f) / (float)dw, v = ((float)y + 0.5f) / (float)dh;
+				int x0, x1, y0, y1;
+				footprint(u, p.W, x0, x1);
+				footprint(v, p.H, y0, y1);
+				float m = depth_of_key(p.vis[(size_t)y0 * p.W + x0]);
+				m = gmin(m, depth_of_key(p.vis[(size_t)y0 * p.W + x1]));
+				m = gmin(m, depth_of_key(p.vis[(size_t)y1 * p.W + x0]));
+				m = gmin(m, depth_of_key(p.vis[(size_t)y1 * p.W + x1]));
+				dst[(size_t)y * dstride + x] = m;
+				if (sdst) sdst[t] = m;
+			}
+		} else {
+			const float* gsrc = p.pyramid + sm.geo[k - 1];
+			const uint32_t sw = sm.geo[16 + k - 1], sh = sm.geo[32 + k - 1];
+			const uint32_t fo = sm.geo[48 + k];
+			if (fo != 0xffffffffu) {
+				const ushort2* fpCols = sm.fp + fo;
+				const ushort2* fpRows = sm.fp + fo + dw;
+				for (uint32_t y = warp; y < dh; y += nwarps) {
+					const ushort2 ry = fpRows[y];
+					const uint32_t r0 = ry.x * sw, r1 = ry.y * sw;
+					// up to 4 column groups per pass: all gathers first, then all stores (the shared-memory stores would otherwise
+					// serialise against the next group's loads)
+					for (uint32_t xb = 0; xb < dw; xb += 128) {
+						float m[4];
+#pragma unroll
+						for (int j = 0; j < 4; ++j) {
+							const uint32_t x = xb + j * 32 + lane;
+							m[j] = 0.f;
+							if (x < dw) {
+								const ushort2 cx = fpCols[x];
+								float a, b, c, d;
+								if (ssrc) { a = ssrc[r0 + cx.x]; b = ssrc[r0 + cx.y]; c = ssrc[r1 + cx.x]; d = ssrc[r1 + cx.y]; }
+								else { // L2 loads (source too large to stage, or written by this block one level ago)
+									a = __ldcg(gsrc + r0 + cx.x); b = __ldcg(gsrc + r0 + cx.y); c = __ldcg(gsrc + r1 + cx.x); d = __ldcg(gsrc + r1 + cx.y);
+								}
+								m[j] = gmin(gmin(gmin(a, b), c), d);
+							}
+						}
+#pragma unroll
+						for (int j = 0; j < 4; ++j) {
+							const uint32_t x = xb + j * 32 + lane;
+							if (x < dw) {
+								dst[(size_t)y * dstride + x] = m[j];
+								if (sdst) sdst[y * dw + x] = m[j];
+							}
+						}
+					}
+				}
+			} else { // very large tail level (only for odd resolutions): per-texel evaluation
+				for (uint32_t t = threadIdx.x; t < dw * dh; t += blockDim.x) {
+					const uint32_t x = t % dw, y = t / dw;
+					const float u = ((float)x + 0.5f) / (float)dw, v = ((float)y + 0.5f) / (float)dh;
+					int x0, x1, y0, y1;
+					footprint(u, sw, x0, x1);
+					footprint(v, sh, y0, y1);
+					float a, b, c, d;
+					if (ssrc) { a = ssrc[y0 * sw + x0]; b = ssrc[y0 * sw + x1]; c = ssrc[y1 * sw + x0]; d = ssrc[y1 * sw + x1]; }
+					else {
+						a = __ldcg(gsrc + (size_t)y0 * sw + x0); b = __ldcg(gsrc + (size_t)y0 * sw + x1);
+						c = __ldcg(gsrc + (size_t)y1 * sw + x0); d = __ldcg(gsrc + (size_t)y1 * sw + x1);
+					}
+					const float m = gmin(gmin(gmin(a, b), c), d);
+					dst[(size_t)y * dstride + x] = m;
+					if (sdst) sdst[t] = m;
+				}
+			}
+		}
+		__syncthreads();
+		TS(4 + k);
+		ssrc = sdst;
+		if (sdst) { float* tp = cur; cur = oth; oth = tp; const uint32_t tc = curCap; curCap = othCap; othCap = tc; }
+	}
+#ifdef VKV_HIZ_DEBUG
+	if (threadIdx.x == 0) {
+		printf("geo %lld tables %lld stage %lld |", dbg_ts[1] - dbg_ts[0], dbg_ts[2] - dbg_ts[1], dbg_ts[3] - dbg_ts[2]);
+		long long prev = dbg_ts[3];
+		for (uint32_t k = first_level; k < levels; ++k) { printf(" L%u %lld", k, dbg_ts[4 + k] - prev); prev = dbg_ts[4 + k]; }
+		printf("\n");
+	}
+#endif
+}
+
+// tail-only launch: resolutions without any exact level (odd W or H)
+__global__ void __launch_bounds__(1024) hiz_tail_kernel(const HizParams p, uint32_t first_level) {
+	extern __shared__ __align__(16) unsigned char tailSmem[];
+	hiz_tail(p, first_level, TailSmem(tailSmem));
+}
 
 // One warp per 64x16 source tile. Lane l owns source columns 2l,2l+1 (one 16-byte load per row, 16 loads in flight).
 // Valid only for levels whose source is exactly twice the destination in both axes: the sampler footprint is then the
 // aligned 2x2 quad {2p, 2p+1} (u = 2p + 0.5 up to rounding noise << 0.5; checked exhaustively in tests/test_hiz_rule.py).
 __global__ void __launch_bounds__(kHizWarps * 32) hiz_tiled_kernel(const HizParams p) {
+	extern __shared__ __align__(16) unsigned char tailSmem[]; // used by the last block only (1 block / SM anyway: 1024 threads)
+	__shared__ uint32_t sLast;
 	const uint32_t lane = threadIdx.x & 31;
 	const uint32_t tilesX = (p.W + kTileW - 1) / kTileW, tilesY = (p.H + kTileH - 1) / kTileH;
 	const uint32_t nTiles = tilesX * tilesY;
@@ -88,67 +272,43 @@ __global__ void __launch_bounds__(kHizWarps * 32) hiz_tiled_kernel(const HizPara
 			}
 		}
 	}
-}
-
-// Remaining mips, one block, level after level (each level is a few thousand texels at most and depends on the previous).
-// first_level = index of the first pyramid mip to produce here (>= 1 unless the depth image is tiny).
-__global__ void __launch_bounds__(1024) hiz_tail_kernel(const HizParams p, uint32_t first_level) {
-	for (uint32_t k = first_level; k < p.pyr.levels; ++k) {
-		const uint32_t i = k + 1;                       // reference view index of the destination (application.cpp:964)
-		const uint32_t dw = p.W >> i, dh = p.H >> i;    // levelSize
-		if (dw == 0 || dh == 0) continue;               // zero-sized dispatch: mip keeps its contents (SURVEY Q5)
-		float* dst = p.pyramid + p.pyr.off[k];
-		const uint32_t dstride = p.pyr.w[k];
-		if (k == 0) {
-			// source = depth image itself (only when no level was exact, e.g. odd W/H): read depth from the visbuffer keys
-			for (uint32_t t = threadIdx.x; t < dw * dh; t += blockDim.x) {
-				const uint32_t x = t % dw, y = t / dw;
-				const float u = ((float)x + 0.5f) / (float)dw, v = ((float)y + 0.5f) / (float)dh;
-				int x0, x1, y0, y1;
-				footprint(u, p.W, x0, x1);
-				footprint(v, p.H, y0, y1);
-				float m = depth_of_key(p.vis[(size_t)y0 * p.W + x0]);
-				m = gmin(m, depth_of_key(p.vis[(size_t)y0 * p.W + x1]));
-				m = gmin(m, depth_of_key(p.vis[(size_t)y1 * p.W + x0]));
-				m = gmin(m, depth_of_key(p.vis[(size_t)y1 * p.W + x1]));
-				dst[(size_t)y * dstride + x] = m;
-			}
-		} else {
-			const float* src = p.pyramid + p.pyr.off[k - 1];
-			const uint32_t sw = p.pyr.w[k - 1], sh = p.pyr.h[k - 1];
-			for (uint32_t t = threadIdx.x; t < dw * dh; t += blockDim.x) {
-				const uint32_t x = t % dw, y = t / dw;
-				// hiz_reduce.comp.glsl:28 : texture(src, (vec2(pos) + 0.5) / imageSize)
-				const float u = ((float)x + 0.5f) / (float)dw, v = ((float)y + 0.5f) / (float)dh;
-				int x0, x1, y0, y1;
-				footprint(u, sw, x0, x1);
-				footprint(v, sh, y0, y1);
-				// plain (coherent) loads: the source was written by this block in the previous iteration
-				float m = src[(size_t)y0 * sw + x0];
-				m = gmin(m, src[(size_t)y0 * sw + x1]);
-				m = gmin(m, src[(size_t)y1 * sw + x0]);
-				m = gmin(m, src[(size_t)y1 * sw + x1]);
-				dst[(size_t)y * dstride + x] = m;
-			}
-		}
-		__syncthreads();
+	// the block that finishes last produces the small mips (no second launch): classic last-block-done hand-off
+	if (p.exact_levels >= p.pyr.levels || !p.done) return;
+	// bar.sync orders every thread's mip stores before thread 0's gpu-scope fence (fences are cumulative), so ONE fence per
+	// block publishes the block's tiles; a fence in all 1024 threads costs several microseconds of L1 invalidations
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		__threadfence();
+		const uint32_t ticket = atomicAdd(p.done, 1u);
+		sLast = (ticket == gridDim.x - 1) ? 1u : 0u;
+		if (sLast) { *p.done = 0u; __threadfence(); } // ready for the next launch; acquire side of the hand-off
 	}
+	__syncthreads();
+	if (!sLast) return;
+	hiz_tail(p, p.exact_levels, TailSmem(tailSmem));
 }
 
 } // namespace
 
 cudaError_t launch_hiz(const HizParams& p, int num_sms, cudaStream_t stream, int* launches) {
-	uint32_t first_tail = 0;
+	static bool attr = false;
+	if (!attr) {
+		cudaFuncSetAttribute(hiz_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTailSmemBytes);
+		cudaFuncSetAttribute(hiz_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTailSmemBytes);
+		attr = true;
+	}
 	if (p.exact_levels >= 1) {
 		const uint32_t tiles = ((p.W + kTileW - 1) / kTileW) * ((p.H + kTileH - 1) / kTileH);
 		uint32_t grid = (tiles + kHizWarps - 1) / kHizWarps;
-		if (grid > (uint32_t)num_sms * 8) grid = (uint32_t)num_sms * 8;
-		hiz_tiled_kernel<<<grid, kHizWarps * 32, 0, stream>>>(p);
+		if (grid > (uint32_t)num_sms) grid = (uint32_t)num_sms;
+		hiz_tiled_kernel<<<grid, kHizWarps * 32, kTailSmemBytes, stream>>>(p); // its last block runs the tail
 		if (launches) ++*launches;
-		first_tail = p.exact_levels;
-	}
-	if (first_tail < p.pyr.levels) {
-		hiz_tail_kernel<<<1, 1024, 0, stream>>>(p, first_tail);
+		if (!p.done && p.split_tail && p.exact_levels < p.pyr.levels) { // diagnosis: tail as a second launch
+			hiz_tail_kernel<<<1, 1024, kTailSmemBytes, stream>>>(p, p.exact_levels);
+			if (launches) ++*launches;
+		}
+	} else if (p.pyr.levels) {
+		hiz_tail_kernel<<<1, 1024, kTailSmemBytes, stream>>>(p, 0);
 		if (launches) ++*launches;
 	}
 	return cudaGetLastError();

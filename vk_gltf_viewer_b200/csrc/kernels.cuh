@@ -46,6 +46,8 @@ struct HizParams {
 	PyramidDesc pyr;
 	uint32_t W, H;
 	uint32_t exact_levels;       // leading mips whose source is exactly 2x (handled by the tiled kernel), <= 4
+	uint32_t* done;              // FrameCounters::hiz_done (zero between launches)
+	int split_tail;              // diagnosis only: run the small mips as a second launch
 };
 
 cudaError_t launch_cull(const CullParams& p, int num_sms, cudaStream_t stream);
