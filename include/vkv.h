@@ -89,6 +89,13 @@ int vkv_hiz(vkv_ctx*);
 /* rasterise an explicit MeshletDraw index list (host pointer) — test hook */
 int vkv_raster_list(vkv_ctx*, const vkv_VisbufferPushConstants* pc, const uint32_t* draw_ids, uint32_t n);
 
+/* ---- resolve: visbuffer -> RGBA8 colour image.  Replaces shaders/visbuffer/visbuffer_resolve.comp.glsl:17-41
+ * and its dispatch (application.cpp:917-949); the push constants' drawBuffer / primitiveBuffer / materialBuffer are the fields
+ * of the reference's VisbufferResolvePushConstants (visbuffer.h.glsl:49-56).  Texel = R | G<<8 | B<<16 | A<<24, sRGB-encoded
+ * fromLinear(material.albedoFactor) (srgb.h.glsl:26-32); untouched / undrawn pixels are 0. ------------------------------- */
+int vkv_resolve(vkv_ctx*, const vkv_VisbufferPushConstants* pc);
+int vkv_read_color(vkv_ctx*, uint32_t* host);                      /* W*H RGBA8 */
+
 /* ---- multi-GPU: one process (and one context) per GPU; a single huge view is sharded by MeshletDraw range and the
  * per-GPU 64-bit visbuffers are min-merged over NVLink peer memory (BASELINE config 5).  The reference is
  * single-GPU: there is no call site to cite, only the data contract — drawIndex stays the index into the GLOBAL list

@@ -536,6 +536,39 @@ int orc_raster(const vkv_VisbufferPushConstants* pc, uint32_t W, uint32_t H, con
 	return 0;
 }
 
+// srgb.h.glsl:26-32 (per channel) and the RGBA8_UNORM image store conversion
+static float from_linear(float c) {
+	bool cutoff = c < 0.0031308f;
+	float higher = 1.055f * std::pow(c, 1.f / 2.4f) - 0.055f;
+	float lower = c * 12.92f;
+	return cutoff ? lower : higher;
+}
+static uint32_t unorm8(float v) {
+	v = (v > 0.0f) ? v : 0.0f;
+	v = (v < 1.0f) ? v : 1.0f;
+	return (uint32_t)std::lrintf(v * 255.0f);
+}
+
+int orc_resolve(const vkv_VisbufferPushConstants* pc, uint32_t W, uint32_t H, const uint32_t* ids, uint32_t* out) {
+	if (pc->meshletDrawCount == 0) return 0;                       // application.cpp:930
+	const vkv_MeshletDraw* draws = (const vkv_MeshletDraw*)pc->drawBuffer;
+	const vkv_Primitive* prims = (const vkv_Primitive*)pc->primitiveBuffer;
+	const vkv_Material* mats = (const vkv_Material*)pc->materialBuffer;
+	const uint32_t covered = (W / 32u) * 32u;                      // application.cpp:943
+	for (uint32_t y = 0; y < H; ++y)
+		for (uint32_t x = 0; x < covered; ++x) {
+			size_t p = (size_t)y * W + x;
+			out[p] = 0;                                            // comp.glsl:25
+			uint32_t v = ids[p];
+			if (v == VKV_VISBUFFER_CLEAR) continue;                // :28
+			uint32_t drawIndex = v >> VKV_TRIANGLE_BITS;           // :33 unpackVisBuffer
+			const vkv_Material& m = mats[prims[draws[drawIndex].primitiveIndex].materialIndex];   // :35-37
+			out[p] = unorm8(from_linear(m.albedoFactor[0])) | (unorm8(from_linear(m.albedoFactor[1])) << 8) |
+			         (unorm8(from_linear(m.albedoFactor[2])) << 16) | (unorm8(m.albedoFactor[3]) << 24);   // :39-41
+		}
+	return 0;
+}
+
 int orc_hiz(uint32_t W, uint32_t H, const float* depth, float* pyramid, int threads) {
 	Pyr pyr;
 	pyr.levels = orc_pyramid_layout(W, H, pyr.off, pyr.w, pyr.h, &pyr.total);

@@ -90,6 +90,12 @@ int orc_hiz(uint32_t W, uint32_t H, const float* depth, float* pyramid, int thre
  * of a w x h image with CLAMP_TO_EDGE.  *ambig is OR-ed with 1 if a frac is within 1e-4 of 0. */
 float orc_sample_min(const float* img, uint32_t w, uint32_t h, float u, float v, int* ambig);
 
+/* shaders/visbuffer/visbuffer_resolve.comp.glsl:17-41 + srgb.h.glsl:26-32 + dispatch application.cpp:943
+ * (renderResolution.x / 32 groups of 32 threads: columns >= (W/32)*32 are never touched).  ids = the R32_UINT visbuffer;
+ * out = W*H RGBA8 texels (R in the low byte), in/out: untouched pixels keep their contents.  pow() is libm powf here and
+ * CUDA powf on the device: the 8-bit result may differ by one code in rare cases — tests allow +-1 per channel. */
+int orc_resolve(const vkv_VisbufferPushConstants* pc, uint32_t W, uint32_t H, const uint32_t* ids, uint32_t* out);
+
 /* 64-bit visbuffer key: (~floatBits(depth) << 32) | id */
 uint64_t orc_vis64_key(float depth, uint32_t id);
 

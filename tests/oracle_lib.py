@@ -44,6 +44,7 @@ def lib():
                                  C.c_void_p, C.c_void_p, C.POINTER(Counters), C.c_int]
         L.orc_clear.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_hiz.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_resolve.argtypes = [C.POINTER(abi.PushConstants), C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
         L.orc_sample_min.restype = C.c_float
         L.orc_sample_min.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.POINTER(C.c_int)]
         L.orc_vis64_key.restype = C.c_uint64
@@ -99,6 +100,15 @@ def raster(pc, tg: Targets, draw_ids, threads=0):
 def hiz(tg: Targets, threads=0):
     rc = lib().orc_hiz(tg.W, tg.H, tg.depth.ctypes.data, tg.pyramid.ctypes.data, threads)
     assert rc == 0
+
+
+def resolve(pc, tg: Targets, out=None):
+    """visbuffer_resolve.comp.glsl on the min-id image (what the 64-bit visbuffer's low word holds)"""
+    if out is None:
+        out = np.zeros((tg.H, tg.W), np.uint32)
+    rc = lib().orc_resolve(C.byref(pc), tg.W, tg.H, tg.ids_min.ctypes.data, out.ctypes.data)
+    assert rc == 0
+    return out
 
 
 def visible_ids(status):

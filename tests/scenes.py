@@ -85,17 +85,30 @@ def mirrored_instances():
     return s.finalize()
 
 
-def random_soup(n_tris=400, seed=3, spread=3.0, size=0.8):
-    """random intersecting triangles at random depths (some behind the camera), double sided"""
+def random_soup(n_tris=400, seed=3, spread=3.0, size=0.8, materials=1):
+    """random intersecting triangles at random depths (some behind the camera), double sided; `materials` > 1 splits them
+    over that many primitives, each with its own random albedo (resolve-pass tests)"""
     rng = np.random.default_rng(seed)
     centers = rng.uniform(-spread, spread, (n_tris, 1, 3)).astype(np.float32)
     centers[:, :, 2] = rng.uniform(-12, 4, (n_tris, 1))
     pos = (centers + rng.uniform(-size, size, (n_tris, 3, 3))).astype(np.float32).reshape(-1, 3)
-    idx = np.arange(n_tris * 3, dtype=np.uint32)
     s = Scene.new()
-    m = s.add_material(double_sided=True)
-    p = s.add_primitive(pos, idx, m)
-    s.add_node(p)
+    if materials <= 1:
+        m = s.add_material(double_sided=True)
+        p = s.add_primitive(pos, np.arange(n_tris * 3, dtype=np.uint32), m)
+        s.add_node(p)
+        return s.finalize()
+    per = (n_tris + materials - 1) // materials
+    for k in range(materials):
+        lo, hi = k * per, min(n_tris, (k + 1) * per)
+        if lo >= hi:
+            break
+        albedo = tuple(float(x) for x in rng.uniform(0.0, 1.0, 4))
+        if k == 0:
+            albedo = (0.0, 1.0, 0.002, 1.0)  # both branches of the transfer function and the exact end points
+        m = s.add_material(albedo=albedo, double_sided=True)
+        p = s.add_primitive(pos[lo * 3:hi * 3], np.arange((hi - lo) * 3, dtype=np.uint32), m)
+        s.add_node(p)
     return s.finalize()
 
 

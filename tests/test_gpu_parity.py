@@ -174,3 +174,34 @@ def test_errors():
     with pytest.raises(api.VkvError):
         r.read_status(4, 0)
     r.close()
+
+
+def _max_channel_diff(a, b):
+    d = np.abs(a.view(np.uint8).astype(np.int16) - b.view(np.uint8).astype(np.int16))
+    return int(d.max()) if d.size else 0
+
+
+@pytest.mark.parametrize("res", [(640, 480), (333, 217)])
+def test_resolve_matches_oracle(res):
+    """visbuffer -> RGBA8.  The id -> material chain is integer work (exact); the sRGB transfer function goes
+    through powf on both sides (CUDA vs libm): tolerance +-1 code per 8-bit channel, stated here and in oracle.h."""
+    W, H = res
+    s = S.random_soup(300, seed=5, spread=3.0, size=1.0, materials=7)
+    cam = S.camera(W, H)
+    r = api.Renderer(W, H)
+    pc_dev = r.upload_scene(s, cam)
+    pc_host = s.host_push_constants(cam)
+    tg = O.Targets(W, H)
+    O.frame(pc_host, tg)
+    r.frame(pc_dev)
+    r.resolve(pc_dev)
+    got = r.read_color()
+    want = O.resolve(pc_host, tg)
+    assert _max_channel_diff(got, want) <= 1
+    # structure is exact: drawn <-> non-zero alpha, cleared / uncovered columns stay 0
+    covered = (W // 32) * 32
+    assert np.array_equal(got[:, covered:], np.zeros((H, W - covered), np.uint32))
+    drawn = tg.ids_min[:, :covered] != 0xFFFFFFFF
+    assert np.array_equal((got[:, :covered] >> 24) != 0, drawn)
+    assert len(np.unique(got)) >= 4  # several materials actually show up
+    r.close()

@@ -47,6 +47,7 @@ EXPORTS = [
     "vkv_read_visbuffer64", "vkv_read_ids", "vkv_read_depth", "vkv_read_hiz_mip", "vkv_read_pyramid", "vkv_write_pyramid",
     "vkv_read_visible", "vkv_read_status", "vkv_pyramid_floats",
     "vkv_event_record", "vkv_event_elapsed", "vkv_flush_l2", "vkv_visbuffer64_ptr",
+    "vkv_resolve", "vkv_read_color",
     "vkv_set_shard", "vkv_set_shard_interleaved", "vkv_ipc_export", "vkv_ipc_attach", "vkv_ipc_detach", "vkv_merge",
 ]
 
@@ -91,6 +92,8 @@ def _lib():
         L.vkv_flush_l2.argtypes = [vp, C.c_size_t]
         L.vkv_visbuffer64_ptr.argtypes = [vp]
         L.vkv_visbuffer64_ptr.restype = u64
+        L.vkv_resolve.argtypes = [vp, PC]
+        L.vkv_read_color.argtypes = [vp, vp]
         L.vkv_set_shard.argtypes = [vp, u32, u32, i]
         L.vkv_set_shard_interleaved.argtypes = [vp, i, i, u32]
         L.vkv_ipc_export.argtypes = [vp, vp]
@@ -240,6 +243,15 @@ class Renderer:
 
     def visbuffer64_ptr(self) -> int:
         return self.L.vkv_visbuffer64_ptr(self.h)
+
+    # ---- resolve -----------------------------------------------------------------------------
+    def resolve(self, pc):
+        self._ck(self.L.vkv_resolve(self.h, C.byref(pc)))
+
+    def read_color(self):
+        out = np.empty((self.H, self.W), np.uint32)
+        self._ck(self.L.vkv_read_color(self.h, out.ctypes.data))
+        return out
 
     # ---- multi-GPU (meshlet-range sharding) ---------------------------------------------------
     def set_shard(self, first_draw=0, draw_count=0, enable=True):

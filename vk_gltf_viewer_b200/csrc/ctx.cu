@@ -43,6 +43,10 @@ struct vkv_ctx {
 	bool attached = false;
 	uint32_t* sync_flags = nullptr;   // kMaxRanks barrier slots + 1 error word, peer-mapped
 	uint32_t epoch = 0;
+	// resolve pass: RGBA8 target + per-material colour table (grow-only)
+	uint32_t* color = nullptr;
+	uint32_t* mat_colors = nullptr;
+	uint32_t mat_cap = 0;
 	// readback scratch
 	uint32_t* tmp_ids = nullptr;
 	float* tmp_depth = nullptr;
@@ -103,7 +107,8 @@ int free_targets(vkv_ctx* c) {
 	if (c->pyramid) cudaFree(c->pyramid);
 	if (c->tmp_ids) cudaFree(c->tmp_ids);
 	if (c->tmp_depth) cudaFree(c->tmp_depth);
-	c->vis = nullptr; c->pyramid = nullptr; c->tmp_ids = nullptr; c->tmp_depth = nullptr;
+	if (c->color) cudaFree(c->color);
+	c->vis = nullptr; c->pyramid = nullptr; c->tmp_ids = nullptr; c->tmp_depth = nullptr; c->color = nullptr;
 	return 0;
 }
 
@@ -320,6 +325,7 @@ void vkv_destroy(vkv_ctx* c) {
 	if (c->list_tmp) cudaFree(c->list_tmp);
 	if (c->xf_mvp) cudaFree(c->xf_mvp);
 	if (c->xf_det) cudaFree(c->xf_det);
+	if (c->mat_colors) cudaFree(c->mat_colors);
 	if (c->tmp_count) cudaFree(c->tmp_count);
 	if (c->counters) cudaFree(c->counters);
 	if (c->h_counters) cudaFreeHost(c->h_counters);
@@ -519,6 +525,55 @@ int vkv_frame(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, uint32_t flags, 
 			} else out->total_ms = el(E_BEGIN, E_HIZ_A);
 		}
 	}
+	return VKV_OK;
+}
+
+/* ---- resolve ------------------------------------------------------------------------------------- */
+
+int vkv_resolve(vkv_ctx* c, const vkv_VisbufferPushConstants* pc) {
+	if (!c) return VKV_ERR_INVALID;
+	if (!pc) return fail(c, VKV_ERR_INVALID, "push constants are NULL");
+	CK(cudaSetDevice(c->device));
+	const size_t n = (size_t)c->W * c->H;
+	if (!c->color) {
+		CK(cudaMalloc(&c->color, n * 4));
+		CK(cudaMemsetAsync(c->color, 0, n * 4, c->stream)); // image contents before the first resolve
+	}
+	if (pc->meshletDrawCount == 0) return VKV_OK; // application.cpp:930: no draw buffer -> no dispatch
+	if (!pc->drawBuffer || !pc->primitiveBuffer || !pc->materialBuffer) return fail(c, VKV_ERR_INVALID, "push constants hold a NULL buffer address");
+	// material count = extent of the allocation the material buffer lives in (the push constants do not carry it)
+	size_t bytes = 0;
+	{
+		std::lock_guard<std::mutex> lock(c->mtx);
+		auto it = c->allocs.upper_bound(pc->materialBuffer);
+		if (it != c->allocs.begin()) {
+			--it;
+			if (pc->materialBuffer < it->first + it->second) bytes = it->first + it->second - pc->materialBuffer;
+		}
+	}
+	if (bytes < sizeof(vkv_Material)) return fail(c, VKV_ERR_INVALID, "materialBuffer does not point into a vkv_upload allocation");
+	const uint32_t nm = (uint32_t)(bytes / sizeof(vkv_Material));
+	if (nm > c->mat_cap) {
+		CK(cudaStreamSynchronize(c->stream));
+		if (c->mat_colors) cudaFree(c->mat_colors);
+		c->mat_colors = nullptr; c->mat_cap = 0;
+		CK(cudaMalloc(&c->mat_colors, (size_t)(nm + 64) * 4));
+		c->mat_cap = nm + 64;
+	}
+	CK(launch_material_colors((const vkv_Material*)pc->materialBuffer, nm, c->mat_colors, c->num_sms, c->stream));
+	ResolveParams r{};
+	r.vis = c->vis; r.draws = (const vkv_MeshletDraw*)pc->drawBuffer; r.primitives = (const vkv_Primitive*)pc->primitiveBuffer;
+	r.matColors = c->mat_colors; r.color = c->color; r.W = c->W; r.H = c->H;
+	CK(launch_resolve(r, c->num_sms, c->stream));
+	return VKV_OK;
+}
+
+int vkv_read_color(vkv_ctx* c, uint32_t* host) {
+	if (!c || !host) return VKV_ERR_INVALID;
+	if (!c->color) return fail(c, VKV_ERR_INVALID, "vkv_read_color: no resolve has run since the targets were created");
+	CK(cudaSetDevice(c->device));
+	CK(cudaMemcpyAsync(host, c->color, (size_t)c->W * c->H * 4, cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
 	return VKV_OK;
 }
 

@@ -71,3 +71,15 @@ struct MergeParams {
 };
 cudaError_t launch_xgpu_barrier(const MergeParams& p, uint32_t epoch, unsigned long long timeout_ns, cudaStream_t stream);
 cudaError_t launch_merge_min(const MergeParams& p, int num_sms, cudaStream_t stream);
+
+// ---- visbuffer resolve (resolve.cu) ---------------------------------------------------------------------------------
+struct ResolveParams {
+	const unsigned long long* vis;
+	const vkv_MeshletDraw* draws;
+	const vkv_Primitive* primitives;
+	const uint32_t* matColors;   // per material: RGBA8 of fromLinear(albedoFactor)
+	uint32_t* color;             // W*H RGBA8 (R in the low byte)
+	uint32_t W, H;
+};
+cudaError_t launch_material_colors(const vkv_Material* materials, uint32_t n, uint32_t* out, int num_sms, cudaStream_t stream);
+cudaError_t launch_resolve(const ResolveParams& p, int num_sms, cudaStream_t stream);
