@@ -78,6 +78,7 @@ int vkv_sync(vkv_ctx*);
 int vkv_upload(vkv_ctx*, const void* host, size_t bytes, uint64_t* dev_addr);       /* alloc + copy; address is 256-byte aligned */
 int vkv_update(vkv_ctx*, uint64_t dev_addr, const void* host, size_t bytes);        /* rewrite (camera, transforms) — async on the ctx stream */
 int vkv_free(vkv_ctx*, uint64_t dev_addr);
+int vkv_download(vkv_ctx*, uint64_t dev_addr, void* host, size_t bytes);            /* read back part of a vkv_upload / vkv_build_draws buffer */
 
 /* ---- per frame -------------------------------------------------------------------------------------------- */
 int vkv_frame(vkv_ctx*, const vkv_VisbufferPushConstants* pc, uint32_t flags, vkv_stats* out);
@@ -88,6 +89,14 @@ int vkv_raster(vkv_ctx*, const vkv_VisbufferPushConstants* pc, int pass);
 int vkv_hiz(vkv_ctx*);
 /* rasterise an explicit MeshletDraw index list (host pointer) — test hook */
 int vkv_raster_list(vkv_ctx*, const vkv_VisbufferPushConstants* pc, const uint32_t* draw_ids, uint32_t n);
+
+/* ---- draw list on the device.  Replaces World::rebuildDrawBuffer (world.cpp:230-293): the host passes one
+ * vkv_DrawSegment per (mesh-node, primitive) in traversal order (host pointer, 8 B each) instead of 12 B per MeshletDraw;
+ * the library expands them (length = Primitive.meshletCount read on the device) into a MeshletDraw[] it owns.  The buffer is
+ * byte-identical to the reference's host-built list; *draw_buffer can go straight into the push constants, vkv_free releases it.
+ * VKV_ERR_LIMIT if the list would exceed 2^25 draws. --------------------------------------------------------------------- */
+int vkv_build_draws(vkv_ctx*, const vkv_DrawSegment* host_segments, uint32_t n_segments, uint64_t primitiveBuffer,
+                    uint64_t* draw_buffer, uint32_t* draw_count);
 
 /* ---- resolve: visbuffer -> RGBA8 colour image.  Replaces shaders/visbuffer/visbuffer_resolve.comp.glsl:17-41
  * and its dispatch (application.cpp:917-949); the push constants' drawBuffer / primitiveBuffer / materialBuffer are the fields

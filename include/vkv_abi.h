@@ -109,6 +109,13 @@ typedef struct vkv_VisbufferPushConstants {
 	uint32_t _pad1;
 } vkv_VisbufferPushConstants;
 
+/* Not a reference struct: one entry per (mesh-node, primitive) in World::rebuildDrawBuffer's traversal order
+ * (world.cpp:243-266) — what vkv_build_draws expands into MeshletDraw[] on the device. */
+typedef struct vkv_DrawSegment {
+	uint32_t primitiveIndex;
+	uint32_t transformIndex;
+} vkv_DrawSegment;
+
 VKV_STATIC_ASSERT(sizeof(vkv_Camera) == 352, "Camera");
 VKV_STATIC_ASSERT(offsetof(vkv_Camera, frustum) == 256, "Camera.frustum");
 VKV_STATIC_ASSERT(sizeof(vkv_Meshlet) == 36, "Meshlet");

@@ -205,3 +205,56 @@ def test_resolve_matches_oracle(res):
     assert np.array_equal((got[:, :covered] >> 24) != 0, drawn)
     assert len(np.unique(got)) >= 4  # several materials actually show up
     r.close()
+
+
+def _segments_of(draws):
+    """run-length encode a host-built MeshletDraw[] into (primitiveIndex, transformIndex) segments (world.cpp:252-262 emits
+    exactly one run per mesh-node x primitive)"""
+    key = draws["primitiveIndex"].astype(np.uint64) << np.uint64(32) | draws["transformIndex"].astype(np.uint64)
+    start = np.flatnonzero(np.r_[True, key[1:] != key[:-1]])
+    return np.stack([draws["primitiveIndex"][start], draws["transformIndex"][start]], axis=1).astype(np.uint32)
+
+
+@pytest.mark.parametrize("make", [lambda: Scene.lattice(5, 4, 3, 48), lambda: Scene.city(6, 5, 2000), lambda: Scene.atrium(32), lambda: Scene.icosphere(20)])
+def test_device_draw_list(make):
+    """SURVEY §8f-2: vkv_build_draws expands segments into a MeshletDraw[] byte-identical to World::rebuildDrawBuffer's"""
+    s = make()
+    W, H = 640, 360
+    cam = s.default_camera(W, H)
+    r = api.Renderer(W, H)
+    pc = r.upload_scene(s, cam)
+    host = s.draws()
+    seg = _segments_of(host)
+    addr, n = r.build_draws(seg, pc.primitiveBuffer)
+    assert n == host.shape[0]
+    got = r.download(addr, n * 12).view(abi.DRAW_DTYPE)
+    assert np.array_equal(got, host)
+    # and a frame through the device-built list is the frame through the uploaded one
+    st0 = r.frame(pc, api.FRAME_TWO_PASS)
+    a = r.read_visbuffer64()
+    pc2 = abi.PushConstants.from_buffer_copy(bytes(pc))
+    pc2.drawBuffer = addr
+    st1 = r.frame(pc2, api.FRAME_TWO_PASS)  # culls against the pyramid of the previous frame: same camera, first frame all-far
+    r.frame(pc, api.FRAME_TWO_PASS)
+    b = r.read_visbuffer64()
+    r.frame(pc2, api.FRAME_TWO_PASS)
+    assert np.array_equal(r.read_visbuffer64(), b) and st0.draws == st1.draws
+    assert a.shape == b.shape
+    r.close()
+
+
+def test_device_draw_list_limits():
+    s = Scene.lattice(2, 2, 2, 24)
+    r = api.Renderer(64, 64)
+    pc = r.upload_scene(s, s.default_camera(64, 64))
+    host = s.draws()
+    seg = _segments_of(host)
+    per = host.shape[0] // seg.shape[0]
+    reps = (1 << 25) // per + 2
+    big = np.tile(seg, (reps, 1))
+    with pytest.raises(api.VkvError) as e:
+        r.build_draws(big, pc.primitiveBuffer)
+    assert e.value.code == -5
+    addr, n = r.build_draws(np.zeros((0, 2), np.uint32), pc.primitiveBuffer)
+    assert n == 0
+    r.close()

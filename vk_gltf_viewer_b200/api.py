@@ -47,7 +47,7 @@ EXPORTS = [
     "vkv_read_visbuffer64", "vkv_read_ids", "vkv_read_depth", "vkv_read_hiz_mip", "vkv_read_pyramid", "vkv_write_pyramid",
     "vkv_read_visible", "vkv_read_status", "vkv_pyramid_floats",
     "vkv_event_record", "vkv_event_elapsed", "vkv_flush_l2", "vkv_visbuffer64_ptr",
-    "vkv_resolve", "vkv_read_color",
+    "vkv_resolve", "vkv_read_color", "vkv_build_draws", "vkv_download",
     "vkv_set_shard", "vkv_set_shard_interleaved", "vkv_ipc_export", "vkv_ipc_attach", "vkv_ipc_detach", "vkv_merge",
 ]
 
@@ -92,6 +92,8 @@ def _lib():
         L.vkv_flush_l2.argtypes = [vp, C.c_size_t]
         L.vkv_visbuffer64_ptr.argtypes = [vp]
         L.vkv_visbuffer64_ptr.restype = u64
+        L.vkv_build_draws.argtypes = [vp, vp, u32, u64, C.POINTER(u64), C.POINTER(u32)]
+        L.vkv_download.argtypes = [vp, u64, vp, C.c_size_t]
         L.vkv_resolve.argtypes = [vp, PC]
         L.vkv_read_color.argtypes = [vp, vp]
         L.vkv_set_shard.argtypes = [vp, u32, u32, i]
@@ -243,6 +245,20 @@ class Renderer:
 
     def visbuffer64_ptr(self) -> int:
         return self.L.vkv_visbuffer64_ptr(self.h)
+
+    # ---- draw list on the device -------------------------------------------------------------
+    def build_draws(self, segments, primitive_buffer: int):
+        """segments: (n, 2) uint32 array of (primitiveIndex, transformIndex) per (mesh-node, primitive) in traversal order
+        -> (device address of MeshletDraw[], count)"""
+        seg = np.ascontiguousarray(segments, np.uint32).reshape(-1, 2)
+        addr, cnt = C.c_uint64(), C.c_uint32()
+        self._ck(self.L.vkv_build_draws(self.h, seg.ctypes.data, seg.shape[0], primitive_buffer, C.byref(addr), C.byref(cnt)))
+        return addr.value, cnt.value
+
+    def download(self, addr: int, nbytes: int) -> np.ndarray:
+        out = np.empty(nbytes, np.uint8)
+        self._ck(self.L.vkv_download(self.h, addr, out.ctypes.data, nbytes))
+        return out
 
     # ---- resolve (SURVEY §8f-1) -----------------------------------------------------------------------------
     def resolve(self, pc):

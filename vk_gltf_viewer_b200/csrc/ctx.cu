@@ -528,6 +528,60 @@ int vkv_frame(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, uint32_t flags, 
 	return VKV_OK;
 }
 
+/* ---- draw list on the device -------------------------------------------------------------------------- */
+
+int vkv_build_draws(vkv_ctx* c, const vkv_DrawSegment* host_segments, uint32_t n_segments, uint64_t primitiveBuffer, uint64_t* draw_buffer, uint32_t* draw_count) {
+	if (!c || !draw_buffer || !draw_count || (!host_segments && n_segments)) return c ? fail(c, VKV_ERR_INVALID, "vkv_build_draws: NULL argument") : VKV_ERR_INVALID;
+	if (n_segments && !primitiveBuffer) return fail(c, VKV_ERR_INVALID, "vkv_build_draws: primitiveBuffer is NULL");
+	*draw_buffer = 0; *draw_count = 0;
+	CK(cudaSetDevice(c->device));
+	cudaStream_t s = c->stream;
+	vkv_DrawSegment* dseg = nullptr;
+	uint32_t* doff = nullptr;
+	auto cleanup = [&]() { if (dseg) cudaFree(dseg); if (doff) cudaFree(doff); };
+	cudaError_t e = cudaMalloc(&dseg, (size_t)(n_segments ? n_segments : 1) * sizeof(vkv_DrawSegment));
+	if (e == cudaSuccess) e = cudaMalloc(&doff, (size_t)(n_segments + 2) * 4);
+	if (e == cudaSuccess && n_segments) e = cudaMemcpyAsync(dseg, host_segments, (size_t)n_segments * sizeof(vkv_DrawSegment), cudaMemcpyHostToDevice, s);
+	if (e == cudaSuccess) e = cudaMemsetAsync(doff + n_segments + 1, 0, 4, s); // overflow flag
+	if (e == cudaSuccess) e = launch_segment_scan(dseg, n_segments, (const vkv_Primitive*)primitiveBuffer, doff, doff + n_segments + 1, s);
+	uint32_t tail[2] = {0, 0}; // total, overflow
+	if (e == cudaSuccess) e = cudaMemcpyAsync(tail, doff + n_segments, 8, cudaMemcpyDeviceToHost, s);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(s); // host_segments is borrowed; the total sizes the allocation
+	if (e != cudaSuccess) { cleanup(); return fail(c, e == cudaErrorMemoryAllocation ? VKV_ERR_OOM : VKV_ERR_CUDA, "vkv_build_draws: %s", cudaGetErrorString(e)); }
+	if (tail[1] || tail[0] > VKV_MAX_MESHLET_DRAWS) { cleanup(); return fail(c, VKV_ERR_LIMIT, "draw list exceeds 2^25 MeshletDraws (visbuffer.h.glsl:15-17)"); }
+	const uint32_t total = tail[0];
+	void* d = nullptr;
+	const size_t bytes = (size_t)total * sizeof(vkv_MeshletDraw);
+	const size_t padded = ((bytes ? bytes : 1) + 255) & ~(size_t)255;
+	e = cudaMalloc(&d, padded);
+	if (e == cudaSuccess) e = launch_expand_segments(dseg, n_segments, doff, (vkv_MeshletDraw*)d, total, c->num_sms, s);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+	cleanup();
+	if (e != cudaSuccess) { if (d) cudaFree(d); return fail(c, e == cudaErrorMemoryAllocation ? VKV_ERR_OOM : VKV_ERR_CUDA, "vkv_build_draws: %s", cudaGetErrorString(e)); }
+	{
+		std::lock_guard<std::mutex> lock(c->mtx);
+		c->allocs[(uint64_t)(uintptr_t)d] = bytes;
+	}
+	*draw_buffer = (uint64_t)(uintptr_t)d;
+	*draw_count = total;
+	return VKV_OK;
+}
+
+int vkv_download(vkv_ctx* c, uint64_t dev_addr, void* host, size_t bytes) {
+	if (!c || !host) return VKV_ERR_INVALID;
+	{
+		std::lock_guard<std::mutex> lock(c->mtx);
+		auto it = c->allocs.upper_bound(dev_addr);
+		if (it == c->allocs.begin()) return fail(c, VKV_ERR_INVALID, "vkv_download: unknown address");
+		--it;
+		if (dev_addr + bytes > it->first + it->second) return fail(c, VKV_ERR_INVALID, "vkv_download: range exceeds the allocation");
+	}
+	CK(cudaSetDevice(c->device));
+	CK(cudaMemcpyAsync(host, (const void*)(uintptr_t)dev_addr, bytes, cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	return VKV_OK;
+}
+
 /* ---- resolve ------------------------------------------------------------------------------------- */
 
 int vkv_resolve(vkv_ctx* c, const vkv_VisbufferPushConstants* pc) {

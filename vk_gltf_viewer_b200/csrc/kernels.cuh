@@ -83,3 +83,8 @@ struct ResolveParams {
 };
 cudaError_t launch_material_colors(const vkv_Material* materials, uint32_t n, uint32_t* out, int num_sms, cudaStream_t stream);
 cudaError_t launch_resolve(const ResolveParams& p, int num_sms, cudaStream_t stream);
+
+// ---- device-side draw-list generation (drawlist.cu) ---------------------------------------------------------------
+cudaError_t launch_segment_scan(const vkv_DrawSegment* seg, uint32_t n, const vkv_Primitive* prims, uint32_t* offsets, uint32_t* overflow, cudaStream_t stream);
+cudaError_t launch_expand_segments(const vkv_DrawSegment* seg, uint32_t n, const uint32_t* offsets, vkv_MeshletDraw* draws, uint32_t capacity,
+                                   int num_sms, cudaStream_t stream);
