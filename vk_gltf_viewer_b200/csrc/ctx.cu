@@ -35,6 +35,8 @@ struct vkv_ctx {
 	uint32_t* xf_det = nullptr;
 	uint32_t xf_cap = 0;
 	uint32_t xf_count = 0;
+	BigTri* big_tris = nullptr;       // large-triangle queue (raster.cu)
+	uint32_t big_cap = 1u << 20;
 	// multi-GPU: this GPU's shard of the draw list and the peers' visbuffers mapped through CUDA IPC
 	uint32_t shard_first = 0, shard_count = 0;       // contiguous shard
 	uint32_t shard_block_log2 = 0, shard_rank = 0, shard_nranks = 1; // interleaved shard (blocks of 2^k draws, round-robin)
@@ -222,7 +224,16 @@ RasterParams make_raster(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, const
 	r.list = list; r.count = count; r.work = work;
 	r.vis = c->vis; r.W = c->W; r.H = c->H;
 	r.mvp = c->xf_mvp; r.detNeg = c->xf_det;
+	r.big = c->big_tris; r.bigCap = c->big_cap; r.bigCursor = &c->counters->big_cursor; r.bigNext = &c->counters->big_next;
 	return r;
+}
+
+// raster_kernel + raster_big_kernel behind a reset of the large-triangle queue
+int enqueue_raster(vkv_ctx* c, const RasterParams& r, int* launches) {
+	CK(cudaMemsetAsync(&c->counters->big_next, 0, 4 + 8, c->stream)); // big_next, big_cursor
+	CK(launch_raster(r, c->num_sms, c->stream));
+	if (launches) *launches += 2;
+	return VKV_OK;
 }
 
 HizParams make_hiz(vkv_ctx* c) {
@@ -296,6 +307,7 @@ int vkv_create(vkv_ctx** out, int cuda_device, uint32_t width, uint32_t height) 
 		return bail(VKV_ERR_OOM);
 	}
 	cudaMemset(c->counters, 0, sizeof(FrameCounters));
+	if (cudaMalloc(&c->big_tris, (size_t)c->big_cap * sizeof(BigTri)) != cudaSuccess) { c->err = "allocating the large-triangle queue failed"; return bail(VKV_ERR_OOM); }
 	int rc = alloc_targets(c, width, height);
 	if (rc != VKV_OK) return bail(rc);
 	*out = c;
@@ -325,6 +337,7 @@ void vkv_destroy(vkv_ctx* c) {
 	if (c->list_tmp) cudaFree(c->list_tmp);
 	if (c->xf_mvp) cudaFree(c->xf_mvp);
 	if (c->xf_det) cudaFree(c->xf_det);
+	if (c->big_tris) cudaFree(c->big_tris);
 	if (c->mat_colors) cudaFree(c->mat_colors);
 	if (c->tmp_count) cudaFree(c->tmp_count);
 	if (c->counters) cudaFree(c->counters);
@@ -425,7 +438,8 @@ int vkv_raster(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, int pass) {
 	CK(cudaMemsetAsync(&c->counters->work[pass], 0, 4, c->stream));
 	rc = prepare_transforms(c, pc, nullptr);
 	if (rc) return rc;
-	CK(launch_raster(make_raster(c, pc, c->list_visible[pass], &c->counters->visible[pass], &c->counters->work[pass]), c->num_sms, c->stream));
+	rc = enqueue_raster(c, make_raster(c, pc, c->list_visible[pass], &c->counters->visible[pass], &c->counters->work[pass]), nullptr);
+	if (rc) return rc;
 	return VKV_OK;
 }
 
@@ -439,7 +453,8 @@ int vkv_raster_list(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, const uint
 	if (n) CK(cudaMemcpyAsync(c->list_tmp, draw_ids, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
 	rc = prepare_transforms(c, pc, nullptr);
 	if (rc) return rc;
-	CK(launch_raster(make_raster(c, pc, c->list_tmp, c->tmp_count, c->tmp_count + 1), c->num_sms, c->stream));
+	rc = enqueue_raster(c, make_raster(c, pc, c->list_tmp, c->tmp_count, c->tmp_count + 1), nullptr);
+	if (rc) return rc;
 	CK(cudaStreamSynchronize(c->stream)); // draw_ids / hdr are borrowed
 	return VKV_OK;
 }
@@ -482,7 +497,8 @@ int vkv_frame(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, uint32_t flags, 
 	mark(E_CULL_A);
 	rc = prepare_transforms(c, pc, &launches);
 	if (rc) return rc;
-	CK(launch_raster(make_raster(c, pc, c->list_visible[0], &c->counters->visible[0], &c->counters->work[0]), c->num_sms, s)); ++launches;
+	rc = enqueue_raster(c, make_raster(c, pc, c->list_visible[0], &c->counters->visible[0], &c->counters->work[0]), &launches);
+	if (rc) return rc;
 	mark(E_RASTER_A);
 	if (merge) { rc = enqueue_merge(c, &launches); if (rc) return rc; }
 	mark(E_MERGE_A);
@@ -494,7 +510,8 @@ int vkv_frame(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, uint32_t flags, 
 		c->status_valid[1] = p.status != nullptr;
 		if (p.n) { CK(launch_cull(p, c->num_sms, s)); ++launches; }
 		mark(E_CULL_B);
-		CK(launch_raster(make_raster(c, pc, c->list_visible[1], &c->counters->visible[1], &c->counters->work[1]), c->num_sms, s)); ++launches;
+		rc = enqueue_raster(c, make_raster(c, pc, c->list_visible[1], &c->counters->visible[1], &c->counters->work[1]), &launches);
+		if (rc) return rc;
 		mark(E_RASTER_B);
 		if (merge) { rc = enqueue_merge(c, &launches); if (rc) return rc; }
 		mark(E_MERGE_B);

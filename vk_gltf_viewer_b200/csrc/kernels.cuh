@@ -25,6 +25,23 @@ struct CullParams {
 	int skip_hiz;                // frustum only
 };
 
+// A set-up triangle (24.8 fixed-point vertices, positive area) — what the rasteriser's inner loops consume.
+struct Tri {
+	int ax, ay, bx, by, cx, cy;      // snapped vertices, 24.8 fixed point, area2 > 0
+	int xmin, xmax, ymin, ymax;      // pixel bbox clipped to the viewport
+	long long area2;
+	float za, dzb, dzc, invA;
+	uint32_t id;
+	uint32_t small;                  // vertex extent <= 2^14 sub-pixels in x and y: every edge value fits in int32
+};
+// Large-triangle queue entry: the triangle plus its slice of the global tile-work index space
+struct BigTri {
+	Tri t;
+	uint32_t tileBase;               // first tile-work index of this triangle
+	uint32_t tilesX, tilesY;         // bbox extent in kBigTileW x kBigTileH tiles
+	uint32_t pad;
+};
+
 struct RasterParams {
 	const vkv_MeshletDraw* draws;
 	const float* transforms;
@@ -38,6 +55,10 @@ struct RasterParams {
 	uint32_t W, H;
 	const float* mvp;            // per transform: viewProjection * transform (launch_prepare_transforms)
 	const uint32_t* detNeg;      // per transform: determinant(transform) < 0
+	BigTri* big;                 // large-triangle queue (filled by raster_kernel, drained by raster_big_kernel)
+	uint32_t bigCap;
+	unsigned long long* bigCursor;
+	uint32_t* bigNext;
 };
 
 struct HizParams {
@@ -54,7 +75,7 @@ cudaError_t launch_cull(const CullParams& p, int num_sms, cudaStream_t stream);
 cudaError_t launch_iota(const CullParams& p, uint32_t* out, uint32_t* count, int num_sms, cudaStream_t stream);
 cudaError_t launch_prepare_transforms(const float* transforms, const vkv_Camera* camera, uint32_t n, float* mvp, uint32_t* detNeg,
                                       int num_sms, cudaStream_t stream);
-cudaError_t launch_raster(const RasterParams& p, int num_sms, cudaStream_t stream);
+cudaError_t launch_raster(const RasterParams& p, int num_sms, cudaStream_t stream);      // raster_kernel + raster_big_kernel
 cudaError_t launch_hiz(const HizParams& p, int num_sms, cudaStream_t stream, int* launches);
 cudaError_t launch_fill64(unsigned long long* dst, size_t n, unsigned long long value, int num_sms, cudaStream_t stream);
 cudaError_t launch_fill32(uint32_t* dst, size_t n, uint32_t value, int num_sms, cudaStream_t stream);

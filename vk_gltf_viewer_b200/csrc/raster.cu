@@ -24,7 +24,17 @@ namespace {
 #endif
 constexpr int kWarpsPerBlock = VKV_RASTER_WARPS;
 constexpr int kThreads = kWarpsPerBlock * 32;
-constexpr int kSerialMaxDim = 8;   // lane-serial path: bbox <= 8x8 pixels
+#ifndef VKV_SERIAL_MAX_DIM
+#define VKV_SERIAL_MAX_DIM 8
+#endif
+constexpr int kSerialMaxDim = VKV_SERIAL_MAX_DIM;   // lane-serial path: bbox <= this many pixels in x and y
+// Large triangles are not rasterised where they are found (one warp would scan thousands of stamps while the rest of the
+// GPU idles): they go to a queue and a second kernel spreads their screen TILES over all warps.
+constexpr int kBigTileW = 128, kBigTileH = 64;   // pixels per tile-work item = 16 x 16 stamps of 8x4
+#ifndef VKV_BIG_MIN_STAMPS
+#define VKV_BIG_MIN_STAMPS 1
+#endif
+constexpr int kBigMinStamps = VKV_BIG_MIN_STAMPS;  // bbox of >= this many 8x4 stamps -> deferred
 #ifndef VKV_RASTER_BATCH
 #define VKV_RASTER_BATCH 4
 #endif
@@ -33,15 +43,6 @@ constexpr int kSerialMaxDim = 8;   // lane-serial path: bbox <= 8x8 pixels
 #endif
 constexpr int kBatch = VKV_RASTER_BATCH;           // meshlets fetched per work-stealing grab
 constexpr int kMinBlocks = VKV_RASTER_MIN_BLOCKS;  // 128 registers, no spills, 16 warps / SM (measured: 24 warps at 80 registers spill and are slower)
-
-struct Tri {
-	int ax, ay, bx, by, cx, cy;      // snapped vertices, 24.8 fixed point, area2 > 0
-	int xmin, xmax, ymin, ymax;      // pixel bbox clipped to the viewport
-	long long area2;
-	float za, dzb, dzc, invA;
-	uint32_t id;
-	uint32_t small;                  // vertex extent <= 2^14 sub-pixels in x and y: every edge value fits in int32
-};
 
 // what one lane fetches for one meshlet of a batch (mesh.glsl:31-36 resolved to addresses)
 struct alignas(16) MeshletHdr {
@@ -161,8 +162,10 @@ __device__ __forceinline__ void raster_serial(const Tri& t, unsigned long long* 
 	}
 }
 
-// Whole-warp scan in 8x4 stamps with stamp-level rejection; int64 edge functions (any triangle inside the guard band).
-__device__ __noinline__ void raster_coop(const Tri& t, unsigned long long* __restrict__ vis, uint32_t W, uint32_t lane) {
+// Whole-warp scan of the pixel rectangle [x0,x1] x [y0,y1] (inside the triangle's bbox) in 8x4 stamps with stamp-level
+// rejection; int64 edge functions evaluated from absolute pixel coordinates, so any partition of the bbox into rectangles
+// produces exactly the same fragments.
+__device__ __noinline__ void raster_coop(const Tri& t, unsigned long long* __restrict__ vis, uint32_t W, uint32_t lane, int x0, int x1, int y0, int y1) {
 	const long long e0dx = t.cx - t.bx, e0dy = t.cy - t.by;
 	const long long e1dx = t.ax - t.cx, e1dy = t.ay - t.cy;
 	const long long e2dx = t.bx - t.ax, e2dy = t.by - t.ay;
@@ -176,23 +179,40 @@ __device__ __noinline__ void raster_coop(const Tri& t, unsigned long long* __res
 	const long long m0 = max(0ll, e0dx * 3 * VKV_SUB) + max(0ll, -e0dy * 7 * VKV_SUB);
 	const long long m1 = max(0ll, e1dx * 3 * VKV_SUB) + max(0ll, -e1dy * 7 * VKV_SUB);
 	const long long m2 = max(0ll, e2dx * 3 * VKV_SUB) + max(0ll, -e2dy * 7 * VKV_SUB);
-	const long long px0 = (long long)t.xmin * VKV_SUB + VKV_SUB / 2, py0 = (long long)t.ymin * VKV_SUB + VKV_SUB / 2;
+	const long long px0 = (long long)x0 * VKV_SUB + VKV_SUB / 2, py0 = (long long)y0 * VKV_SUB + VKV_SUB / 2;
 	long long r0 = e0dx * (py0 - t.by) - e0dy * (px0 - t.bx);
 	long long r1 = e1dx * (py0 - t.cy) - e1dy * (px0 - t.cx);
 	long long r2 = e2dx * (py0 - t.ay) - e2dy * (px0 - t.ax);
-	for (int ty = t.ymin; ty <= t.ymax; ty += 4) {
+	for (int ty = y0; ty <= y1; ty += 4) {
 		long long s0 = r0, s1 = r1, s2 = r2;
-		for (int tx = t.xmin; tx <= t.xmax; tx += 8) {
+		for (int tx = x0; tx <= x1; tx += 8) {
 			if (s0 + m0 >= b0 && s1 + m1 >= b1 && s2 + m2 >= b2) {
 				const long long w0 = s0 + o0, w1 = s1 + o1, w2 = s2 + o2;
 				const int x = tx + lx, y = ty + ly;
-				if (x <= t.xmax && y <= t.ymax && w0 >= b0 && w1 >= b1 && w2 >= b2)
+				if (x <= x1 && y <= y1 && w0 >= b0 && w1 >= b1 && w2 >= b2)
 					shade(vis, W, x, y, (float)w1, (float)w2, t.invA, t.za, t.dzb, t.dzc, t.id);
 			}
 			s0 -= e0dy * 8 * VKV_SUB; s1 -= e1dy * 8 * VKV_SUB; s2 -= e2dy * 8 * VKV_SUB;
 		}
 		r0 += e0dx * 4 * VKV_SUB; r1 += e1dx * 4 * VKV_SUB; r2 += e2dx * 4 * VKV_SUB;
 	}
+}
+
+__device__ __forceinline__ bool is_big(const Tri& t) {
+	return ((t.xmax - t.xmin + 8) >> 3) * ((t.ymax - t.ymin + 4) >> 2) >= kBigMinStamps;
+}
+
+// Append a large triangle to the queue (one lane).  ONE 64-bit atomic hands out the record slot and the triangle's range of
+// tile-work indices, so record order == tile-base order and the drain kernel can binary-search it.  false = queue full.
+__device__ __forceinline__ bool push_big(const RasterParams& p, const Tri& t) {
+	const uint32_t tilesX = (uint32_t)(t.xmax / kBigTileW - t.xmin / kBigTileW + 1), tilesY = (uint32_t)(t.ymax / kBigTileH - t.ymin / kBigTileH + 1);
+	const unsigned long long old = atomicAdd(p.bigCursor, (1ull << 32) | (unsigned long long)(tilesX * tilesY));
+	const uint32_t slot = (uint32_t)(old >> 32);
+	if (slot >= p.bigCap) return false; // its tile range lies beyond every stored record's: the drain kernel never reaches it
+	BigTri b;
+	b.t = t; b.tileBase = (uint32_t)old; b.tilesX = tilesX; b.tilesY = tilesY; b.pad = 0;
+	p.big[slot] = b;
+	return true;
 }
 
 // Sutherland–Hodgman against one plane (dist >= 0 inside); intersections evaluated from the inside vertex outwards.
@@ -455,6 +475,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) raster_kernel(const Rast
 					}
 				}
 				if (kind == 1) raster_serial(tri, p.vis, p.W);
+				if (kind == 2 && is_big(tri) && push_big(p, tri)) kind = 0; // deferred to raster_big_kernel
 				uint32_t coop = __ballot_sync(0xffffffffu, kind >= 2);
 				while (coop) {
 					const int src = __ffs(coop) - 1;
@@ -464,19 +485,58 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) raster_kernel(const Rast
 						else {
 							const uint32_t ia = entry & 0xffu, ib = (entry >> 8) & 0xffu, ic = (entry >> 16) & 0xffu;
 							const float4 A = ws.cxyw[ia], B = ws.cxyw[ib], C = ws.cxyw[ic];
-							ws.nsub = clip_and_setup(make_float4(A.x, A.y, ws.cz[ia], A.z), make_float4(B.x, B.y, ws.cz[ib], B.z),
-							                         make_float4(C.x, C.y, ws.cz[ic], C.z),
-							                         (drawId << VKV_TRIANGLE_BITS) | ((entry >> 24) & 0x7fu), p.W, p.H, ws.sub);
+							int n = clip_and_setup(make_float4(A.x, A.y, ws.cz[ia], A.z), make_float4(B.x, B.y, ws.cz[ib], B.z),
+							                       make_float4(C.x, C.y, ws.cz[ic], C.z),
+							                       (drawId << VKV_TRIANGLE_BITS) | ((entry >> 24) & 0x7fu), p.W, p.H, ws.sub);
+							int kept = 0; // clipped pieces are often the largest triangles of a scene: defer those too
+							for (int k = 0; k < n; ++k) {
+								if (is_big(ws.sub[k]) && push_big(p, ws.sub[k])) continue;
+								if (kept != k) ws.sub[kept] = ws.sub[k];
+								++kept;
+							}
+							ws.nsub = kept;
 						}
 					}
 					__syncwarp();
 					const int n = ws.nsub;
-					for (int k = 0; k < n; ++k) raster_coop(ws.sub[k], p.vis, p.W, lane);
+					for (int k = 0; k < n; ++k) raster_coop(ws.sub[k], p.vis, p.W, lane, ws.sub[k].xmin, ws.sub[k].xmax, ws.sub[k].ymin, ws.sub[k].ymax);
 					__syncwarp();
 				}
 			}
 			__syncwarp();
 		}
+	}
+}
+
+// Drain of the large-triangle queue: one warp per (triangle, 128x64-pixel tile) work item.
+__global__ void __launch_bounds__(256) raster_big_kernel(const RasterParams p) {
+	__shared__ Tri sTri[8];
+	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const unsigned long long cur = *p.bigCursor;
+	const uint32_t nRec = min((uint32_t)(cur >> 32), p.bigCap);
+	if (nRec == 0) return;
+	const BigTri* last = p.big + (nRec - 1);
+	const uint32_t nTiles = last->tileBase + last->tilesX * last->tilesY;
+	for (;;) {
+		uint32_t w = 0;
+		if (lane == 0) w = atomicAdd(p.bigNext, 1u);
+		w = __shfl_sync(0xffffffffu, w, 0);
+		if (w >= nTiles) break;
+		uint32_t lo = 0, hi = nRec - 1; // last record with tileBase <= w
+		while (lo < hi) {
+			const uint32_t mid = (lo + hi + 1) >> 1;
+			if (p.big[mid].tileBase <= w) lo = mid; else hi = mid - 1;
+		}
+		const BigTri* b = p.big + lo;
+		__syncwarp();
+		if (lane < sizeof(Tri) / 4) ((uint32_t*)&sTri[warp])[lane] = ((const uint32_t*)&b->t)[lane];
+		const uint32_t local = w - b->tileBase, tilesX = b->tilesX;
+		__syncwarp();
+		const Tri& t = sTri[warp];
+		const int tx = t.xmin / kBigTileW + (int)(local % tilesX), ty = t.ymin / kBigTileH + (int)(local / tilesX);
+		const int x0 = max(t.xmin, tx * kBigTileW), x1 = min(t.xmax, tx * kBigTileW + kBigTileW - 1);
+		const int y0 = max(t.ymin, ty * kBigTileH), y1 = min(t.ymax, ty * kBigTileH + kBigTileH - 1);
+		raster_coop(t, p.vis, p.W, lane, x0, x1, y0, y1);
 	}
 }
 
@@ -515,6 +575,7 @@ cudaError_t launch_raster(const RasterParams& p, int num_sms, cudaStream_t strea
 		perSm = n < 1 ? 1 : n;
 	}
 	raster_kernel<<<num_sms * perSm, kThreads, 0, stream>>>(p);
+	raster_big_kernel<<<num_sms * 4, 256, 0, stream>>>(p); // exits at once when the queue is empty
 	return cudaGetLastError();
 }
 
