@@ -184,8 +184,11 @@ def main():
     cnt = scene.counts()
     views = [scene.default_view(i, NVIEWS) for i in range(NVIEWS)]
     steps, warm = max(1, args.steps if args.steps is not None else 200), max(3, args.warmup)
-    if shard == "views":   # rank r renders views r, r+world, ...: no data-path collective
-        my_views = [views[(rank + i * world) % NVIEWS] for i in range(warm + steps + 1)]
+    if shard == "views":   # independent views per GPU, no data-path collective.  Every rank walks the same camera
+        # sweep with the same step, phase-shifted by rank * NVIEWS / world (rank r starts at view r*64/n): frame-to-frame
+        # coherence — what the previous-frame HiZ test feeds on — is then the same at every N.  (A round-robin i mod n
+        # assignment makes each rank jump n views per frame and silently inflates pass B with N.)
+        my_views = [views[(rank * NVIEWS // world + i) % NVIEWS] for i in range(warm + steps + 1)]
     else:                  # every rank renders the SAME views, each its own range of the draw list
         my_views = [views[i % NVIEWS] for i in range(warm + steps + 1)]
 

@@ -6,8 +6,9 @@
 // read and write peer HBM directly over NVLink / NVSwitch:
 //   barrier  (1 block)   every rank's raster pass is complete and visible
 //   merge    (grid)      fused reduce-scatter + all-gather: rank r owns strip r of the image, loads that strip from all
-//                        ranks with 16-byte loads, takes the min and stores the result into strip r of EVERY rank
-//                        (P2P stores) — no staging buffer, each key crosses NVLink once in and once out per peer
+//                        ranks with 16-byte loads, takes the min and stores the result into strip r of every rank whose
+//                        value differs (P2P stores) — no staging buffer, each key crosses NVLink once in and at most
+//                        once out per peer; untouched (all-clear) regions and each pixel's winner cost no store
 //   barrier  (1 block)   all strips have landed everywhere
 // A key is (~depthBits << 32 | id): min == nearest fragment, ties == lowest id, exactly what atomicMin does inside one GPU,
 // so the merged image is bit-identical to the single-GPU one.
@@ -46,20 +47,39 @@ __device__ __forceinline__ ulonglong2 min2(ulonglong2 a, ulonglong2 b) {
 	return make_ulonglong2(a.x < b.x ? a.x : b.x, a.y < b.y ? a.y : b.y);
 }
 
+__device__ __forceinline__ bool differs(ulonglong2 a, ulonglong2 b) { return a.x != b.x || a.y != b.y; }
+
 template <int N>
 __global__ void __launch_bounds__(256) merge_min_kernel(const MergeParams p) {
 	// strip r = pairs [n2*r/N, n2*(r+1)/N) of the image viewed as 16-byte pairs (the odd last key, if any, belongs to the last rank)
+	constexpr int U = N <= 2 ? 4 : (N <= 4 ? 2 : 1); // pairs per thread per iteration: N*U 16-byte loads in flight
 	const size_t n2 = p.n >> 1;
 	const size_t lo = n2 * (size_t)p.rank / N, hi = n2 * (size_t)(p.rank + 1) / N;
-	for (size_t i = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (size_t)gridDim.x * blockDim.x) {
-		ulonglong2 v[N];
+	const size_t stride = (size_t)gridDim.x * blockDim.x;
+	for (size_t i0 = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < hi; i0 += stride * U) {
+		ulonglong2 v[U][N];
 #pragma unroll
-		for (int r = 0; r < N; ++r) v[r] = __ldcg((const ulonglong2*)p.vis[r] + i); // all loads in flight before the first use
-		ulonglong2 m = v[0];
+		for (int u = 0; u < U; ++u) {
+			const size_t i = i0 + u * stride;
 #pragma unroll
-		for (int r = 1; r < N; ++r) m = min2(m, v[r]);
+			for (int k = 0; k < N; ++k) { // peer order rotated by rank: at any moment the ranks pull from different peers
+				const int r = (p.rank + k) % N;
+				if (i < hi) v[u][k] = __ldcg((const ulonglong2*)p.vis[r] + i);
+			}
+		}
 #pragma unroll
-		for (int r = 0; r < N; ++r) __stcg((ulonglong2*)p.vis[r] + i, m);
+		for (int u = 0; u < U; ++u) {
+			const size_t i = i0 + u * stride;
+			if (i >= hi) continue;
+			ulonglong2 m = v[u][0];
+#pragma unroll
+			for (int k = 1; k < N; ++k) m = min2(m, v[u][k]);
+#pragma unroll
+			for (int k = 0; k < N; ++k) { // a rank that already holds the minimum (or where every rank is still clear) gets no store
+				const int r = (p.rank + k) % N;
+				if (differs(m, v[u][k])) __stcg((ulonglong2*)p.vis[r] + i, m);
+			}
+		}
 	}
 	if ((p.n & 1) && p.rank == N - 1 && blockIdx.x == 0 && threadIdx.x == 0) {
 		unsigned long long m = p.vis[0][p.n - 1];

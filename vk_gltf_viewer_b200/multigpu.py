@@ -29,8 +29,14 @@ def interleaved_owner(draw_ids, world: int, block_log2: int = 11):
 
 
 def view_shard(n_views: int, rank: int, world: int):
-    """round-robin view assignment: view i -> rank i mod world"""
+    """round-robin view assignment: view i -> rank i mod world (independent views: cubemap faces, shadow cascades)"""
     return list(range(rank, n_views, world))
+
+
+def sweep_start(n_views: int, rank: int, world: int) -> int:
+    """camera sweeps: every rank walks the whole ring with the same step, starting at rank * n_views / world, so the
+    frame-to-frame coherence the previous-frame HiZ test relies on does not depend on the number of GPUs"""
+    return rank * n_views // world
 
 
 def exchange_handles(handle: bytes, dist) -> list:
