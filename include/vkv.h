@@ -141,6 +141,11 @@ int vkv_event_elapsed(vkv_ctx*, int from, int to, float* ms);
 int vkv_flush_l2(vkv_ctx*, size_t bytes);
 /* device pointer of the 64-bit visbuffer (for the multi-GPU min-merge; see vkv_merge_*) */
 uint64_t vkv_visbuffer64_ptr(vkv_ctx*);
+/* arithmetic self check: the kernels divide clip.xyz by clip.w with ONE refined reciprocal per vertex / AABB corner
+ * (culling.h.glsl:49-51 and the perspective divide after visbuffer.mesh.glsl:61 are three `/` by the same w); this runs
+ * that routine against the IEEE `/` operator on 148*8*256*iters_per_thread pseudo-random operand quadruples on the GPU and
+ * returns how many quotients were compared and how many differed in any bit (must be 0). */
+int vkv_selftest_division(vkv_ctx*, uint64_t seed, uint32_t iters_per_thread, uint64_t* tested, uint64_t* mismatches);
 
 #ifdef __cplusplus
 }

@@ -258,3 +258,16 @@ def test_device_draw_list_limits():
     addr, n = r.build_draws(np.zeros((0, 2), np.uint32), pc.primitiveBuffer)
     assert n == 0
     r.close()
+
+
+def test_shared_reciprocal_division():
+    """the kernels' x/w, y/w, z/w with one refined reciprocal (common.cuh div3_shared) is bit-identical to IEEE `/`
+    (what the oracle and the reference's SPIR-V OpFDiv compute) over the whole operand range it is used for"""
+    r = api.Renderer(64, 64)
+    total = 0
+    for seed in (1, 0xC0FFEE, 0x5EED0003):
+        tested, bad = r.selftest_division(seed, 2048)
+        assert bad == 0, f"{bad} of {tested} quotients differ from IEEE division"
+        total += tested
+    assert total > 3_000_000_000
+    r.close()

@@ -6,7 +6,7 @@ rep, kern, fil = sys.argv[1:4]
 regions = []
 for a in sys.argv[4:]:
     n, r = a.split(":"); lo, hi = r.split("-"); regions.append((n, int(lo), int(hi)))
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv", "--kernel-name", f"regex:{kern}", "--launch-count", "1"], capture_output=True, text=True).stdout
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv", "--kernel-name", f"regex:{kern}", "--launch-skip", __import__("os").environ.get("SKIP","0"), "--launch-count", "1"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hdr = None; fname = ""; acc = {}; tot = [0, 0, 0]
 for r in rows:

@@ -48,6 +48,7 @@ EXPORTS = [
     "vkv_read_visible", "vkv_read_status", "vkv_pyramid_floats",
     "vkv_event_record", "vkv_event_elapsed", "vkv_flush_l2", "vkv_visbuffer64_ptr",
     "vkv_resolve", "vkv_read_color", "vkv_build_draws", "vkv_download",
+    "vkv_selftest_division",
     "vkv_set_shard", "vkv_set_shard_interleaved", "vkv_ipc_export", "vkv_ipc_attach", "vkv_ipc_detach", "vkv_merge",
 ]
 
@@ -102,6 +103,7 @@ def _lib():
         L.vkv_ipc_attach.argtypes = [vp, i, i, vp]
         L.vkv_ipc_detach.argtypes = [vp]
         L.vkv_merge.argtypes = [vp]
+        L.vkv_selftest_division.argtypes = [vp, u64, u32, C.POINTER(u64), C.POINTER(u64)]
         _bound = True
     return L
 
@@ -245,6 +247,12 @@ class Renderer:
 
     def visbuffer64_ptr(self) -> int:
         return self.L.vkv_visbuffer64_ptr(self.h)
+
+    def selftest_division(self, seed=1, iters_per_thread=64):
+        """(quotients compared, quotients that differ from IEEE `/`) of the shared-reciprocal division the kernels use"""
+        t, m = C.c_uint64(), C.c_uint64()
+        self._ck(self.L.vkv_selftest_division(self.h, seed, iters_per_thread, C.byref(t), C.byref(m)))
+        return t.value, m.value
 
     # ---- draw list on the device (SURVEY §8f-2) -------------------------------------------------------------
     def build_draws(self, segments, primitive_buffer: int):

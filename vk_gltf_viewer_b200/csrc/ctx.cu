@@ -834,4 +834,17 @@ int vkv_flush_l2(vkv_ctx* c, size_t bytes) {
 
 uint64_t vkv_visbuffer64_ptr(vkv_ctx* c) { return c ? (uint64_t)(uintptr_t)c->vis : 0; }
 
+int vkv_selftest_division(vkv_ctx* c, uint64_t seed, uint32_t iters_per_thread, uint64_t* tested, uint64_t* mismatches) {
+	if (!c || !tested || !mismatches) return VKV_ERR_INVALID;
+	CK(cudaSetDevice(c->device));
+	unsigned long long* d = (unsigned long long*)c->tmp_count; // 256-byte scratch
+	CK(cudaMemsetAsync(d, 0, 16, c->stream));
+	CK(launch_division_selftest(seed, iters_per_thread, d, c->num_sms, c->stream));
+	unsigned long long h[2] = {0, 0};
+	CK(cudaMemcpyAsync(h, d, 16, cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	*mismatches = h[0]; *tested = h[1];
+	return VKV_OK;
+}
+
 } // extern "C"

@@ -109,3 +109,6 @@ cudaError_t launch_resolve(const ResolveParams& p, int num_sms, cudaStream_t str
 cudaError_t launch_segment_scan(const vkv_DrawSegment* seg, uint32_t n, const vkv_Primitive* prims, uint32_t* offsets, uint32_t* overflow, cudaStream_t stream);
 cudaError_t launch_expand_segments(const vkv_DrawSegment* seg, uint32_t n, const uint32_t* offsets, vkv_MeshletDraw* draws, uint32_t capacity,
                                    int num_sms, cudaStream_t stream);
+
+// ---- arithmetic self checks (selftest.cu) -------------------------------------------------------------------------
+cudaError_t launch_division_selftest(uint64_t seed, uint32_t iters, unsigned long long* counters2, int num_sms, cudaStream_t stream);

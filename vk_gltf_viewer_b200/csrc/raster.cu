@@ -79,8 +79,13 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 __device__ __forceinline__ bool top_left(int dx, int dy) { return dy < 0 || (dy == 0 && dx > 0); }
 
 __device__ __forceinline__ void project(float4 c, float hw, float hh, int& fx, int& fy, float& z) {
-	const float nx = c.x / c.w, ny = c.y / c.w;
-	z = c.z / c.w;
+	// perspective divide: three IEEE divisions by the same w -> one refined reciprocal when every operand is a normal
+	// number of moderate magnitude (bit-identical to `/`, see common.cuh div3_shared), the plain divisions otherwise
+	float nx, ny;
+	const float amx = max_nan(max_nan(fabsf(c.x), fabsf(c.y)), max_nan(fabsf(c.z), fabsf(c.w)));
+	const float amn = fminf(fminf(fabsf(c.x), fabsf(c.y)), fminf(fabsf(c.z), fabsf(c.w)));
+	if (amn >= kDivLo && amx <= kDivHi) div3_shared(c.x, c.y, c.z, c.w, nx, ny, z);
+	else { nx = c.x / c.w; ny = c.y / c.w; z = c.z / c.w; }
 	const float sx = nx * hw + hw;
 	const float sy = ny * hh + hh;
 	fx = __float2int_rn(sx * (float)VKV_SUB);
