@@ -112,5 +112,57 @@ def random_soup(n_tris=400, seed=3, spread=3.0, size=0.8, materials=1):
     return s.finalize()
 
 
+def cull_stress(seed=11, instances=61):
+    """many instances of a multi-meshlet soup under random node transforms, with the meshlet AABBs OVERWRITTEN by a mix of
+    ordinary, degenerate and non-finite boxes (the cull reads nothing else of a meshlet): zero / negative / huge / tiny
+    extents, boxes that straddle or sit on the camera plane, infinities and NaNs.  Exercises every branch of the projection
+    (packed shared-reciprocal path, plain-division path, NaN ordering) and the odd tail of the two-draws-per-thread split."""
+    rng = np.random.default_rng(seed)
+    n_tris = 2600
+    centers = rng.uniform(-1.0, 1.0, (n_tris, 1, 3)).astype(np.float32)
+    pos = (centers + rng.uniform(-0.15, 0.15, (n_tris, 3, 3))).astype(np.float32).reshape(-1, 3)
+    s = Scene.new()
+    m = s.add_material(double_sided=True)
+    p = s.add_primitive(pos, np.arange(n_tris * 3, dtype=np.uint32), m)
+    wall, widx = grid_mesh(12, 12, lambda u, v: ((u * 2 - 1) * 5, (v * 2 - 1) * 4, np.zeros_like(u)))
+    s.add_node(s.add_primitive(wall, widx, m), translation=(0, 0, 1.0))
+    tri = np.array([[-0.5, -0.5, 0], [0.5, -0.5, 0], [0, 0.5, 0]], np.float32)
+    s.add_node(s.add_primitive(tri, np.arange(3, dtype=np.uint32), m), translation=(0, 2.0, 2.0))  # one more draw: odd total
+    for k in range(instances):
+        q = rng.normal(size=4)
+        q /= np.linalg.norm(q)
+        sc = rng.uniform(0.2, 1.5, 3) * rng.choice([1.0, 1.0, 1.0, -1.0], 3)
+        t = rng.uniform(-6, 6, 3)
+        t[2] = rng.uniform(-14, 5)
+        s.add_node(p, translation=tuple(map(float, t)), rotation=tuple(map(float, q)), scale=tuple(map(float, sc)))
+    s.finalize()
+    ml = s.primitive(0)["meshlets"]
+    n = ml.shape[0]
+    ext, cen = ml["aabbExtents"], ml["aabbCenter"]
+    special = np.array([0.0, -0.0, 1e-30, 1e-42, 1e20, 3e38, np.inf, -np.inf, np.nan, -1.0, 1.0, 0.5, 2.0**-64, 2.0**63], np.float32)
+    for i in range(n):
+        kind = i % 7
+        if kind == 0:
+            continue  # the builder's own box
+        if kind == 1:   # degenerate extents
+            ext[i] = rng.choice([0.0, 0.0, 1e-30, 0.25], 3)
+        elif kind == 2:  # arbitrary specials in random slots
+            for a in range(3):
+                if rng.random() < 0.5:
+                    ext[i][a] = rng.choice(special)
+                if rng.random() < 0.3:
+                    cen[i][a] = rng.choice(special)
+        elif kind == 3:  # big boxes that straddle the camera plane
+            ext[i] = rng.uniform(2, 30, 3)
+        elif kind == 4:  # exact lattice values: zero clip coordinates and exact quotients become likely
+            cen[i] = rng.integers(-2, 3, 3)
+            ext[i] = rng.choice([0.5, 1.0, 2.0], 3)
+        elif kind == 5:  # thin slabs
+            ext[i][rng.integers(0, 3)] = 0.0
+        else:            # tiny boxes: high mips never selected, level-0 footprints
+            ext[i] = rng.uniform(1e-4, 1e-2, 3)
+    return s
+
+
 def camera(W, H, eye=(0, 0, 3), center=(0, 0, 0)):
     return Camera(W, H).look_at(eye, center)

@@ -90,3 +90,18 @@ def test_pyramid_layout_matches_reference_formulas():
         assert total == sum(a * b for _, a, b in layout)
     assert abi.pyramid_layout(3840, 2160)[2] * 4 == 11059136 + 4 * 0 or True
     np.testing.assert_equal(abi.pyramid_layout(640, 480)[1][5][1:], (10, 7))
+
+
+def test_no_contracted_packed_products():
+    """ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under -fmad=false; common.cuh's mul2 is built so that
+    it cannot (fma with a run-time -0 addend).  A packed multiply in the SASS means someone reintroduced a contractible
+    product, i.e. a silently fused multiply-add on the cull path (the GPU self-test vkv_selftest_division checks the values)."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    lib = os.path.join(ROOT, "vk_gltf_viewer_b200", "libvkv.so")
+    sass = subprocess.run([cuobjdump, "-sass", lib], capture_output=True, text=True, check=True).stdout
+    assert "FFMA2" in sass and "FADD2" in sass  # the packed path is really there
+    assert "FMUL2" not in sass

@@ -112,6 +112,16 @@ def test_random_soup(seed):
     run_views(S.random_soup(seed=seed), 512, 384, [((0, 0, 3), (0, 0, 0)), ((0.5, 0.2, 2), (0, 0, -2)), ((-1, 0, -3), (0, 0, -6))], two_pass=True)
 
 
+@pytest.mark.parametrize("seed", [11, 12])
+def test_cull_stress_degenerate_boxes(seed):
+    """status byte of every draw, both passes, on boxes that are zero-sized, huge, non-finite or cross the camera plane"""
+    s = S.cull_stress(seed)
+    assert s.counts().draws % 2 == 1  # odd draw count: the two-draws-per-thread split has a one-box tail
+    views = [((0, 0, 6), (0, 0, 0)), ((0, 0, 6), (0, 0, 0)), ((0.7, 0.3, 5), (0, 0, -2)), ((-3, 1, -2), (0, 0, -6)), ((0, 0, 0), (0, 0, -1))]
+    summ = run_views(s, 800, 600, views, two_pass=True)
+    assert any(x[1] > 0 for x in summ) and any(x[2] > 0 for x in summ)  # the HiZ test rejected something and pass B recovered something
+
+
 def test_atrium_cfg2_small():
     """BASELINE config 2 geometry (int16-quantised atrium) at reduced detail; full size in test_atrium_cfg2_full"""
     s = Scene.atrium(32)

@@ -1,9 +1,16 @@
+# one GPU round: parity tests, cfg3 bench (+ variants), other configs, launch list, ncu full capture.  usage: bash tools/gpu_round.sh TAG [variant...]
+tag=${1:-rX}; shift
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q > gpurun_out/tests.log 2>&1; echo "tests exit $?" >> gpurun_out/tests.log
-python bench.py --steps 100 --warmup 3 > gpurun_out/bench3.json 2> gpurun_out/bench3.err
-python bench.py --config 1 --steps 100 --warmup 3 --no-cpu-baseline > gpurun_out/bench1.json 2>> gpurun_out/bench3.err
-python bench.py --config 2 --steps 100 --warmup 3 --no-cpu-baseline > gpurun_out/bench2.json 2>> gpurun_out/bench3.err
-python bench.py --config 4 --steps 64 --warmup 3 --no-cpu-baseline > gpurun_out/bench4.json 2>> gpurun_out/bench3.err
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r1e_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_b.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"raster|cull" -c 16 -o gpurun_out/r1e_full python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
-tail -3 gpurun_out/tests.log; cat gpurun_out/bench3.json | head -c 3000
+nvidia-smi --query-gpu=name,clocks.max.sm --format=csv,noheader > gpurun_out/${tag}_gpu.txt
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_tests.log 2>&1; echo "tests exit $?" >> gpurun_out/${tag}_tests.log
+timeout 300 python bench.py --steps 100 --warmup 3 > gpurun_out/${tag}_bench3.json 2> gpurun_out/${tag}_bench.err
+for v in "$@"; do
+  VKV_LIBVKV=variants/libvkv_$v.so timeout 200 python bench.py --config 3 --steps 60 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_var_$v.json 2>> gpurun_out/${tag}_bench.err || echo "$v failed"
+done
+for c in 1 2 4; do
+  timeout 300 python bench.py --config $c --steps 64 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_bench$c.json 2>> gpurun_out/${tag}_bench.err
+done
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_ncu_b.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"raster|cull" -c 16 -o gpurun_out/${tag}_full python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_ncu_full.log 2>&1
+tail -3 gpurun_out/${tag}_tests.log
+python tools/stages.py gpurun_out/${tag}_bench3.json gpurun_out/${tag}_var_*.json gpurun_out/${tag}_bench[124].json

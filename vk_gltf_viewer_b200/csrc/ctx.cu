@@ -211,6 +211,7 @@ CullParams make_cull(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, int pass,
 	p.pass = pass;
 	p.vp_select = pass;
 	p.skip_hiz = 0;
+	p.neg_zero2 = kNegZero2;
 	return p;
 }
 
@@ -506,6 +507,7 @@ int vkv_frame(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, uint32_t flags, 
 	mark(E_HIZ_A);
 	if (two) {
 		CullParams p = make_cull(c, pc, 1, flags);
+		p.skip_frustum = 1; // same camera buffer, same frustum planes as pass A a few launches ago: its survivors pass again
 		if (p.status) CK(cudaMemsetAsync(p.status, VKV_ST_NOT_TESTED, N, s));
 		c->status_valid[1] = p.status != nullptr;
 		if (p.n) { CK(launch_cull(p, c->num_sms, s)); ++launches; }
@@ -839,7 +841,7 @@ int vkv_selftest_division(vkv_ctx* c, uint64_t seed, uint32_t iters_per_thread, 
 	CK(cudaSetDevice(c->device));
 	unsigned long long* d = (unsigned long long*)c->tmp_count; // 256-byte scratch
 	CK(cudaMemsetAsync(d, 0, 16, c->stream));
-	CK(launch_division_selftest(seed, iters_per_thread, d, c->num_sms, c->stream));
+	CK(launch_division_selftest(seed, iters_per_thread, d, kNegZero2, c->num_sms, c->stream));
 	unsigned long long h[2] = {0, 0};
 	CK(cudaMemcpyAsync(h, d, 16, cudaMemcpyDeviceToHost, c->stream));
 	CK(cudaStreamSynchronize(c->stream));

@@ -23,6 +23,8 @@ struct CullParams {
 	int pass;                    // 0 = A, 1 = B
 	int vp_select;               // 0 = prevOcclusionViewProjection (reference), 1 = viewProjection (pass B)
 	int skip_hiz;                // frustum only
+	unsigned long long neg_zero2; // the fp32 pair (-0.0, -0.0) = 0x8000000080000000: see mul2 in cull.cu (must arrive at run time)
+	int skip_frustum;            // pass B inside vkv_frame: every input draw already passed this frame's frustum test in pass A
 };
 
 // A set-up triangle (24.8 fixed-point vertices, positive area) — what the rasteriser's inner loops consume.
@@ -111,4 +113,4 @@ cudaError_t launch_expand_segments(const vkv_DrawSegment* seg, uint32_t n, const
                                    int num_sms, cudaStream_t stream);
 
 // ---- arithmetic self checks (selftest.cu) -------------------------------------------------------------------------
-cudaError_t launch_division_selftest(uint64_t seed, uint32_t iters, unsigned long long* counters2, int num_sms, cudaStream_t stream);
+cudaError_t launch_division_selftest(uint64_t seed, uint32_t iters, unsigned long long* counters2, unsigned long long negZero2, int num_sms, cudaStream_t stream);

@@ -1,6 +1,8 @@
 // selftest.cu — device-side self checks of arithmetic building blocks the parity contract leans on.
-// vkv_selftest_division: common.cuh's div3_shared (three quotients sharing one refined reciprocal) against the `/`
-// operator (IEEE division, what the oracle's C++ computes) on pseudo-random operands covering the whole accepted range.
+// vkv_selftest_division: common.cuh's div3_shared (three quotients sharing one refined reciprocal) and its packed f32x2
+// form (refined_rcp2 / div_by2, two divisors per instruction) against the `/` operator (IEEE division, what the oracle's
+// C++ computes) on pseudo-random operands covering the whole accepted range; and the packed product-then-sum
+// add2(mul2(a, b), c) against __fadd_rn(__fmul_rn(a, b), c), i.e. that nothing contracted it into a fused multiply-add.
 #include "kernels.cuh"
 
 namespace {
@@ -26,7 +28,7 @@ __device__ __forceinline__ float operand(uint64_t r, bool narrow) {
 	return __uint_as_float(sign | (e << 23) | m);
 }
 
-__global__ void division_selftest_kernel(uint64_t seed, uint32_t itersPerThread, unsigned long long* mismatches, unsigned long long* tested) {
+__global__ void division_selftest_kernel(uint64_t seed, uint32_t itersPerThread, unsigned long long* mismatches, unsigned long long* tested, f2 nz) {
 	uint64_t s = seed ^ ((uint64_t)(blockIdx.x * blockDim.x + threadIdx.x) * 0xD1342543DE82EF95ull);
 	unsigned long long bad = 0, n = 0;
 	for (uint32_t it = 0; it < itersPerThread; ++it) {
@@ -38,6 +40,15 @@ __global__ void division_selftest_kernel(uint64_t seed, uint32_t itersPerThread,
 		const float rx = x / w, ry = y / w, rz = z / w;
 		bad += (__float_as_uint(qx) != __float_as_uint(rx)) + (__float_as_uint(qy) != __float_as_uint(ry)) + (__float_as_uint(qz) != __float_as_uint(rz));
 		n += 3;
+		// packed: (x, y) / (w, z) as one f32x2 division, then (x*y + z, w*z + x) as packed product-then-sum
+		const f2 nw = pk(-w, -z);
+		const f2 q = div_by2(pk(x, y), nw, refined_rcp2(nw, pk(1.0f, 1.0f)), nz);
+		const float px = x / w, py = y / z;
+		bad += (__float_as_uint(lo_of(q)) != __float_as_uint(px)) + (__float_as_uint(hi_of(q)) != __float_as_uint(py));
+		const f2 ms = add2(mul2(pk(x, w), pk(y, z), nz), pk(z, x));
+		const float s0 = __fadd_rn(__fmul_rn(x, y), z), s1 = __fadd_rn(__fmul_rn(w, z), x);
+		bad += (__float_as_uint(lo_of(ms)) != __float_as_uint(s0)) + (__float_as_uint(hi_of(ms)) != __float_as_uint(s1));
+		n += 4;
 	}
 	atomicAdd(mismatches, bad);
 	atomicAdd(tested, n);
@@ -45,7 +56,7 @@ __global__ void division_selftest_kernel(uint64_t seed, uint32_t itersPerThread,
 
 } // namespace
 
-cudaError_t launch_division_selftest(uint64_t seed, uint32_t iters, unsigned long long* counters2, int num_sms, cudaStream_t stream) {
-	division_selftest_kernel<<<num_sms * 8, 256, 0, stream>>>(seed, iters, counters2, counters2 + 1);
+cudaError_t launch_division_selftest(uint64_t seed, uint32_t iters, unsigned long long* counters2, unsigned long long negZero2, int num_sms, cudaStream_t stream) {
+	division_selftest_kernel<<<num_sms * 8, 256, 0, stream>>>(seed, iters, counters2, counters2 + 1, negZero2);
 	return cudaGetLastError();
 }
