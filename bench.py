@@ -297,6 +297,10 @@ def main():
         bytes_hiz = 8 * W * H + pyr_bytes  # depth is read fused from the 64-bit visbuffer: 8 B/pixel, not 4
         bytes_clear = 8 * W * H
         per_meshlet = 48 + 28 * 64 + 3 * 95
+        clear_fused = os.environ.get("VKV_SEPARATE_CLEAR", "0") != "1" and cnt.draws > 0 and (W * H) % 2 == 0  # vkv_frame: the clear rides inside the pass-A cull launch (cull.cu), its bytes are that launch's
+        if clear_fused:
+            bytes_cull_a += bytes_clear
+            bytes_clear = 0
         bytes_merge = 8 * W * H * 2 if (flags & api.FRAME_MERGE) else 0  # per GPU: strip read from n ranks + written to n ranks = 2 * 8WH
         stages = {}
         for name, b, ms in (("clear", bytes_clear, stage["clear_ms"]), ("cull_a", bytes_cull_a, stage["cull_a_ms"]),
@@ -305,7 +309,7 @@ def main():
                             ("raster_b", avg(vis_b) * per_meshlet, stage["raster_b_ms"]), ("merge_b", bytes_merge, stage["merge_b_ms"]),
                             ("hiz_b", bytes_hiz, stage["hiz_b_ms"])):
             m = ms / K
-            if m <= 0 and b == 0:
+            if (m <= 0 and b == 0) or (name == "clear" and clear_fused):
                 continue
             gbs = (b / 1e9) / (m / 1e3) if m > 0 else 0.0
             stages[name] = {"ms": round(m, 5), "bytes": int(b), "GB/s": round(gbs, 1), "frac_hbm": round(gbs / hbm, 4)}
@@ -329,7 +333,8 @@ def main():
                        "parallelism": (f"views sharded over {world} GPU(s), scene replicated, no collective" if shard == "views" else
                                        f"one view, MeshletDraw list sharded over {world} GPU(s) in interleaved 2048-draw ranges, u64 min-merge over NVLink peer memory before each HiZ build"),
                        "l2": "256 MB scratch written between timed frames (L2 flush); each frame timed by its own CUDA event pair",
-                       "visible_a_avg": vis_a / K, "occluded_a_avg": occ_a / K, "visible_b_avg": vis_b / K},
+                       "visible_a_avg": vis_a / K, "occluded_a_avg": occ_a / K, "visible_b_avg": vis_b / K,
+                       "clear": "fused into the pass-A cull launch (its 8*W*H bytes are counted there)" if clear_fused else "separate launch"},
             "e2e": {"value": frames_total / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "note": "camera + all node transforms uploaded from host every frame, frame counters read back every frame (wall clock, no L2 flush)"},
             "gpu_launches": launches,

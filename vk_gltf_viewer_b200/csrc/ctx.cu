@@ -41,6 +41,7 @@ struct vkv_ctx {
 	uint32_t shard_first = 0, shard_count = 0;       // contiguous shard
 	uint32_t shard_block_log2 = 0, shard_rank = 0, shard_nranks = 1; // interleaved shard (blocks of 2^k draws, round-robin)
 	bool sharded = false;
+	bool separate_clear = false; // VKV_SEPARATE_CLEAR=1: keep the visbuffer clear a launch of its own (A/B measurements)
 	MergeParams mp{};
 	bool attached = false;
 	uint32_t* sync_flags = nullptr;   // kMaxRanks barrier slots + 1 error word, peer-mapped
@@ -298,6 +299,7 @@ int vkv_create(vkv_ctx** out, int cuda_device, uint32_t width, uint32_t height) 
 	if (cudaSetDevice(cuda_device) != cudaSuccess) { c->err = "cudaSetDevice failed"; return bail(VKV_ERR_CUDA); }
 	cudaDeviceProp prop;
 	if (cudaGetDeviceProperties(&prop, cuda_device) == cudaSuccess) c->num_sms = prop.multiProcessorCount;
+	if (const char* e = getenv("VKV_SEPARATE_CLEAR")) c->separate_clear = e[0] == '1';
 	if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { c->err = "cudaStreamCreate failed"; return bail(VKV_ERR_CUDA); }
 	c->stream = c->own_stream;
 	for (auto& ev : c->events) cudaEventCreate(&ev);
@@ -483,14 +485,20 @@ int vkv_frame(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, uint32_t flags, 
 	auto mark = [&](int e) { if (timed) cudaEventRecord(c->stage_ev[e], s); };
 	CK(cudaMemsetAsync(c->counters, 0, sizeof(FrameCounters), s));
 	mark(E_BEGIN);
-	CK(launch_fill64(c->vis, (size_t)c->W * c->H, VKV_VIS64_CLEAR, c->num_sms, s)); ++launches; // application.cpp:782,807
+	// application.cpp:782,807 — the clear rides inside the pass-A cull launch (cull.cu) whenever there is one and the pixel
+	// count is even (16-byte stores); clear_ms then reads ~0 and cull_a_ms covers both
+	const size_t npix = (size_t)c->W * c->H;
+	CullParams pa = make_cull(c, pc, 0, (flags & VKV_FRAME_NO_CULL) ? 0 : flags);
+	const bool fuse_clear = !(flags & VKV_FRAME_NO_CULL) && pa.n > 0 && (npix & 1) == 0 && !c->separate_clear;
+	if (!fuse_clear) { CK(launch_fill64(c->vis, npix, VKV_VIS64_CLEAR, c->num_sms, s)); ++launches; }
 	mark(E_CLEAR);
 	if (flags & VKV_FRAME_NO_CULL) {
-		CullParams p = make_cull(c, pc, 0, 0);
+		const CullParams& p = pa;
 		CK(launch_iota(p, c->list_visible[0], &c->counters->visible[0], c->num_sms, s)); ++launches;
 		c->status_valid[0] = false;
 	} else {
-		CullParams p = make_cull(c, pc, 0, flags);
+		CullParams& p = pa;
+		if (fuse_clear) { p.clear_ptr = (ulonglong2*)c->vis; p.clear_n2 = npix / 2; p.clear_value = VKV_VIS64_CLEAR; }
 		if (p.status) CK(cudaMemsetAsync(p.status, VKV_ST_NOT_TESTED, N, s));
 		c->status_valid[0] = p.status != nullptr;
 		if (p.n) { CK(launch_cull(p, c->num_sms, s)); ++launches; }

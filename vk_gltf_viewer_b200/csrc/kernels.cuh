@@ -24,6 +24,9 @@ struct CullParams {
 	int vp_select;               // 0 = prevOcclusionViewProjection (reference), 1 = viewProjection (pass B)
 	int skip_hiz;                // frustum only
 	unsigned long long neg_zero2; // the fp32 pair (-0.0, -0.0) = 0x8000000080000000: see mul2 in cull.cu (must arrive at run time)
+	ulonglong2* clear_ptr;       // fused visbuffer clear (vkv_frame pass A): the launch's blocks also store clear_value over
+	size_t clear_n2;             // clear_n2 16-byte words — HBM write traffic issued under the compute-bound cull
+	unsigned long long clear_value;
 	int skip_frustum;            // pass B inside vkv_frame: every input draw already passed this frame's frustum test in pass A
 };
 
