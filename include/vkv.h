@@ -98,6 +98,30 @@ int vkv_raster_list(vkv_ctx*, const vkv_VisbufferPushConstants* pc, const uint32
 int vkv_build_draws(vkv_ctx*, const vkv_DrawSegment* host_segments, uint32_t n_segments, uint64_t primitiveBuffer,
                     uint64_t* draw_buffer, uint32_t* draw_count);
 
+/* ---- EXT_meshopt_compression decode on the device.  Replaces CompressedBufferDataAdapter::ExecuteRange
+ * (assets.cpp:111-171): per compressed buffer view, meshopt_decodeVertexBuffer / meshopt_decodeIndexBuffer /
+ * meshopt_decodeIndexSequence followed by meshopt_decodeFilterOct / Quat / Exp.  A view is fastgltf's CompressedBufferView
+ * (mc.mode, mc.filter, mc.count, mc.byteStride, mc.byteOffset, mc.byteLength) plus where its decoded bytes go.  The plan is
+ * built once per asset (descriptors + scratch on the device); vkv_meshopt_run enqueues the decode of the whole asset on the
+ * context's stream: src_dev = the compressed glTF buffer (vkv_upload), dst_dev = a vkv_alloc'ed buffer whose sub-ranges can
+ * go straight into Primitive's buffer addresses.  results[i] is meshoptimizer's return code for view i (0, -1 bad header or
+ * version, -2 truncated, -3 trailing bytes); a failed view leaves its output range undefined and does not affect the others.
+ * Filters follow meshoptimizer's scalar definitions (vertexfilter.cpp:75-160; see oracle/meshopt_decode.cpp). ------------- */
+enum { VKV_MESHOPT_ATTRIBUTES = 0, VKV_MESHOPT_TRIANGLES = 1, VKV_MESHOPT_INDICES = 2 };               /* fastgltf MeshoptCompressionMode */
+enum { VKV_MESHOPT_FILTER_NONE = 0, VKV_MESHOPT_FILTER_OCT = 1, VKV_MESHOPT_FILTER_QUAT = 2, VKV_MESHOPT_FILTER_EXP = 3 }; /* MeshoptCompressionFilter */
+typedef struct vkv_MeshoptView {
+	uint32_t mode, filter;
+	uint32_t count, stride;         /* mc.count, mc.byteStride */
+	uint64_t src_offset, src_size;  /* mc.byteOffset, mc.byteLength within the compressed buffer */
+	uint64_t dst_offset;            /* where count * stride decoded bytes go within the destination buffer (multiple of 4) */
+} vkv_MeshoptView;
+typedef struct vkv_meshopt_plan vkv_meshopt_plan;
+int vkv_meshopt_plan_create(vkv_ctx*, const vkv_MeshoptView* host_views, uint32_t n_views, vkv_meshopt_plan** out);
+int vkv_meshopt_run(vkv_ctx*, vkv_meshopt_plan*, uint64_t src_dev, size_t src_bytes, uint64_t dst_dev, size_t dst_bytes); /* async */
+int vkv_meshopt_results(vkv_ctx*, vkv_meshopt_plan*, int32_t* results);   /* n_views return codes of the last run (syncs the stream) */
+void vkv_meshopt_plan_destroy(vkv_ctx*, vkv_meshopt_plan*);
+int vkv_alloc(vkv_ctx*, size_t bytes, uint64_t* dev_addr);                /* zero-filled device buffer, same bookkeeping as vkv_upload */
+
 /* ---- resolve: visbuffer -> RGBA8 colour image.  Replaces shaders/visbuffer/visbuffer_resolve.comp.glsl:17-41
  * and its dispatch (application.cpp:917-949); the push constants' drawBuffer / primitiveBuffer / materialBuffer are the fields
  * of the reference's VisbufferResolvePushConstants (visbuffer.h.glsl:49-56).  Texel = R | G<<8 | B<<16 | A<<24, sRGB-encoded

@@ -2,7 +2,8 @@
 # build_ref.sh — compile the parts of the REFERENCE that are plain C++ into oracle/_ref/ (git-ignored, travels with gpurun).
 # TEST INFRASTRUCTURE ONLY.  Sources are compiled where they lie under /root/reference; nothing is copied into the repo.
 # Outputs:
-#   oracle/_ref/libmeshopt_ref.so  meshoptimizer @ the reference's pinned submodule (meshopt_buildMeshlets & co)
+#   oracle/_ref/libmeshopt_ref.so  meshoptimizer @ the reference's pinned submodule (meshopt_buildMeshlets & co, the codecs)
+#   oracle/_ref/libmeshopt_ref_nosimd.so  the same, -DMESHOPTIMIZER_NO_SIMD (scalar decode filters)
 #   oracle/_ref/libref_shim.so     culling.h.glsl:1-30 (isAabbInFrustum, getWorldSpaceAabbExtent) + the shared layout headers
 #                                  compiled as C++ against the reference's glm; camera.cpp:38-48,70-84 (reverseDepth,
 #                                  generateCameraFrustum); glm perspective/lookAt; fastgltf::math translate/rotate/scale.
@@ -18,6 +19,9 @@ CXX=${CXX:-g++}
 
 # 1. meshoptimizer, straight from the submodule
 $CXX -O2 -fPIC -shared -o "$OUT/libmeshopt_ref.so" "$REF"/submodules/meshoptimizer/src/*.cpp
+# the same sources with the portable scalar filter / codec paths (vertexfilter.cpp:75-160, vertexcodec.cpp:300-415): the definition
+# oracle/meshopt_decode.cpp restates (the SSE filter paths round differently and use rsqrtps, whose bits are CPU-vendor specific)
+$CXX -O2 -fPIC -shared -ffp-contract=off -DMESHOPTIMIZER_NO_SIMD -o "$OUT/libmeshopt_ref_nosimd.so" "$REF"/submodules/meshoptimizer/src/*.cpp
 
 # 2. shim.  common.h.glsl pulls <vulkan/vk.hpp> (volk, fmt, tracy) only for VkDeviceAddress: give it a one-line stand-in.
 printf '#pragma once\n#include <cstdint>\ntypedef std::uint64_t VkDeviceAddress;\n' > "$TMP/vulkan/vk.hpp"

@@ -81,6 +81,10 @@ MATERIAL_DTYPE = np.dtype(
         "itemsize": 48,
     }
 )
+# vkv_MeshoptView (include/vkv.h): fastgltf's CompressedBufferView fields + the destination offset
+MESHOPT_VIEW_DTYPE = np.dtype([("mode", "<u4"), ("filter", "<u4"), ("count", "<u4"), ("stride", "<u4"),
+                               ("src_offset", "<u8"), ("src_size", "<u8"), ("dst_offset", "<u8")])
+assert MESHOPT_VIEW_DTYPE.itemsize == 40
 assert MESHLET_DTYPE.itemsize == 36 and VERTEX_DTYPE.itemsize == 24 and DRAW_DTYPE.itemsize == 12 and MATERIAL_DTYPE.itemsize == 48
 
 

@@ -49,6 +49,7 @@ EXPORTS = [
     "vkv_event_record", "vkv_event_elapsed", "vkv_flush_l2", "vkv_visbuffer64_ptr",
     "vkv_resolve", "vkv_read_color", "vkv_build_draws", "vkv_download",
     "vkv_selftest_division",
+    "vkv_alloc", "vkv_meshopt_plan_create", "vkv_meshopt_run", "vkv_meshopt_results", "vkv_meshopt_plan_destroy",
     "vkv_set_shard", "vkv_set_shard_interleaved", "vkv_ipc_export", "vkv_ipc_attach", "vkv_ipc_detach", "vkv_merge",
 ]
 
@@ -104,6 +105,12 @@ def _lib():
         L.vkv_ipc_detach.argtypes = [vp]
         L.vkv_merge.argtypes = [vp]
         L.vkv_selftest_division.argtypes = [vp, u64, u32, C.POINTER(u64), C.POINTER(u64)]
+        L.vkv_alloc.argtypes = [vp, C.c_size_t, C.POINTER(u64)]
+        L.vkv_meshopt_plan_create.argtypes = [vp, vp, u32, C.POINTER(vp)]
+        L.vkv_meshopt_run.argtypes = [vp, vp, u64, C.c_size_t, u64, C.c_size_t]
+        L.vkv_meshopt_results.argtypes = [vp, vp, vp]
+        L.vkv_meshopt_plan_destroy.argtypes = [vp, vp]
+        L.vkv_meshopt_plan_destroy.restype = None
         _bound = True
     return L
 
@@ -143,6 +150,9 @@ class Renderer:
         addr = C.c_uint64()
         self._ck(self.L.vkv_upload(self.h, a.ctypes.data, a.nbytes, C.byref(addr)))
         return addr.value
+
+    def free(self, addr: int):
+        self._ck(self.L.vkv_free(self.h, addr))
 
     def upload_scene(self, scene, camera) -> abi.PushConstants:
         """World::addAsset + rebuildDrawBuffer + updateTransformBuffer + camera buffer: returns DEVICE push constants."""
@@ -253,6 +263,47 @@ class Renderer:
         t, m = C.c_uint64(), C.c_uint64()
         self._ck(self.L.vkv_selftest_division(self.h, seed, iters_per_thread, C.byref(t), C.byref(m)))
         return t.value, m.value
+
+    # ---- EXT_meshopt_compression decode on the device ----------------------------------------
+    def alloc(self, nbytes: int) -> int:
+        addr = C.c_uint64()
+        self._ck(self.L.vkv_alloc(self.h, nbytes, C.byref(addr)))
+        return addr.value
+
+    def meshopt_plan(self, views: np.ndarray):
+        """views: structured array of abi.MESHOPT_VIEW_DTYPE (vkv_MeshoptView) -> opaque plan handle"""
+        v = np.ascontiguousarray(views, abi.MESHOPT_VIEW_DTYPE)
+        plan = C.c_void_p()
+        self._ck(self.L.vkv_meshopt_plan_create(self.h, v.ctypes.data, v.shape[0], C.byref(plan)))
+        return plan
+
+    def meshopt_run(self, plan, src_dev: int, src_bytes: int, dst_dev: int, dst_bytes: int):
+        self._ck(self.L.vkv_meshopt_run(self.h, plan, src_dev, src_bytes, dst_dev, dst_bytes))
+
+    def meshopt_results(self, plan, n_views: int) -> np.ndarray:
+        out = np.zeros(max(1, n_views), np.int32)
+        self._ck(self.L.vkv_meshopt_results(self.h, plan, out.ctypes.data))
+        return out[:n_views]
+
+    def meshopt_plan_destroy(self, plan):
+        self.L.vkv_meshopt_plan_destroy(self.h, plan)
+
+    def meshopt_decode(self, src: np.ndarray, views: np.ndarray, dst_bytes: int):
+        """one-shot convenience (tests): upload `src`, decode every view, download -> (decoded bytes, return code per view)"""
+        src = np.ascontiguousarray(src, np.uint8)
+        s_dev = self.upload(src) if src.size else 0
+        d_dev = self.alloc(dst_bytes)
+        plan = self.meshopt_plan(views)
+        try:
+            self.meshopt_run(plan, s_dev, src.size, d_dev, dst_bytes)
+            rc = self.meshopt_results(plan, len(views))
+            out = self.download(d_dev, dst_bytes) if dst_bytes else np.zeros(0, np.uint8)
+        finally:
+            self.meshopt_plan_destroy(plan)
+            self.free(d_dev)
+            if s_dev:
+                self.free(s_dev)
+        return out, rc
 
     # ---- draw list on the device (SURVEY §8f-2) -------------------------------------------------------------
     def build_draws(self, segments, primitive_buffer: int):

@@ -7,6 +7,8 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <vector>
+#include <algorithm>
 
 #include "kernels.cuh"
 
@@ -843,6 +845,123 @@ int vkv_flush_l2(vkv_ctx* c, size_t bytes) {
 }
 
 uint64_t vkv_visbuffer64_ptr(vkv_ctx* c) { return c ? (uint64_t)(uintptr_t)c->vis : 0; }
+
+int vkv_alloc(vkv_ctx* c, size_t bytes, uint64_t* dev_addr) {
+	if (!c || !dev_addr) return c ? fail(c, VKV_ERR_INVALID, "vkv_alloc: NULL argument") : VKV_ERR_INVALID;
+	std::lock_guard<std::mutex> lock(c->mtx);
+	CK(cudaSetDevice(c->device));
+	void* d = nullptr;
+	const size_t padded = ((bytes ? bytes : 1) + 255) & ~(size_t)255;
+	CK(cudaMalloc(&d, padded));
+	CK(cudaMemsetAsync(d, 0, padded, c->stream));
+	c->allocs[(uint64_t)(uintptr_t)d] = bytes;
+	*dev_addr = (uint64_t)(uintptr_t)d;
+	return VKV_OK;
+}
+
+// ---- EXT_meshopt_compression decode (kernels in meshopt.cu) ---------------------------------------------
+struct vkv_meshopt_plan {
+	MeshoptPlan p{};
+	uint32_t n_views = 0;
+	unsigned long long src_need = 0, dst_need = 0;   // extents the views reach into the two buffers
+	std::vector<void*> dev;                          // every device allocation of the plan
+};
+
+int vkv_meshopt_plan_create(vkv_ctx* c, const vkv_MeshoptView* views, uint32_t n, vkv_meshopt_plan** out) {
+	if (!c || !out || (!views && n)) return c ? fail(c, VKV_ERR_INVALID, "vkv_meshopt_plan_create: NULL argument") : VKV_ERR_INVALID;
+	CK(cudaSetDevice(c->device));
+	std::vector<MeshoptStream> vs, is, fs;
+	std::vector<unsigned long long> elemFirst;
+	std::vector<uint32_t> blockStream;
+	unsigned long long planes = 0, felems = 0, srcNeed = 0, dstNeed = 0;
+	for (uint32_t i = 0; i < n; ++i) {
+		const vkv_MeshoptView& v = views[i];
+		MeshoptStream st{};
+		st.src_off = v.src_offset; st.src_size = v.src_size; st.dst_off = v.dst_offset;
+		st.count = v.count; st.stride = v.stride; st.mode = v.mode; st.filter = v.filter; st.view = i;
+		if (v.dst_offset % 4) return fail(c, VKV_ERR_INVALID, "meshopt view %u: dst_offset must be a multiple of 4", i);
+		if (v.src_size >= (1ull << 30)) return fail(c, VKV_ERR_LIMIT, "meshopt view %u: compressed views of 1 GiB and more are not supported", i);
+		if (v.mode == VKV_MESHOPT_ATTRIBUTES) {
+			if (v.stride == 0 || v.stride > 256 || v.stride % 4) return fail(c, VKV_ERR_INVALID, "meshopt view %u: byteStride %u (must be a multiple of 4, <= 256)", i, v.stride);
+			if ((v.filter == VKV_MESHOPT_FILTER_OCT && v.stride != 4 && v.stride != 8) || (v.filter == VKV_MESHOPT_FILTER_QUAT && v.stride != 8) || v.filter > 3)
+				return fail(c, VKV_ERR_INVALID, "meshopt view %u: filter %u does not fit byteStride %u", i, v.filter, v.stride);
+			uint32_t bs = (8192u / v.stride) & ~15u; // vertexcodec.cpp:116-126
+			st.block_size = bs < 256u ? bs : 256u;
+			const unsigned long long nb = ((unsigned long long)v.count + st.block_size - 1) / st.block_size;
+			if (blockStream.size() + nb >= (1ull << 31) || planes + nb * v.stride >= (1ull << 32)) return fail(c, VKV_ERR_LIMIT, "meshopt plan: too many vertex blocks");
+			st.first_block = (uint32_t)blockStream.size();
+			st.plane_base = (uint32_t)planes;
+			planes += nb * v.stride;
+			blockStream.insert(blockStream.end(), (size_t)nb, (uint32_t)vs.size());
+			vs.push_back(st);
+			if (v.filter) {
+				elemFirst.push_back(felems);
+				felems += v.filter == VKV_MESHOPT_FILTER_EXP ? (unsigned long long)v.count * (v.stride / 4) : v.count;
+				fs.push_back(st);
+			}
+		} else if (v.mode == VKV_MESHOPT_TRIANGLES || v.mode == VKV_MESHOPT_INDICES) {
+			if (v.stride != 2 && v.stride != 4) return fail(c, VKV_ERR_INVALID, "meshopt view %u: index size %u (must be 2 or 4)", i, v.stride);
+			if (v.mode == VKV_MESHOPT_TRIANGLES && v.count % 3) return fail(c, VKV_ERR_INVALID, "meshopt view %u: triangle view with count %u", i, v.count);
+			if (v.filter) return fail(c, VKV_ERR_INVALID, "meshopt view %u: filters apply to attribute views only", i);
+			is.push_back(st);
+		} else return fail(c, VKV_ERR_INVALID, "meshopt view %u: mode %u", i, v.mode);
+		srcNeed = std::max(srcNeed, (unsigned long long)v.src_offset + v.src_size);
+		dstNeed = std::max(dstNeed, (unsigned long long)v.dst_offset + (unsigned long long)v.count * v.stride);
+	}
+	vkv_meshopt_plan* pl = new vkv_meshopt_plan();
+	pl->n_views = n; pl->src_need = srcNeed; pl->dst_need = dstNeed;
+	auto put = [&](const void* host, size_t bytes, const void** devOut) -> cudaError_t {
+		void* d = nullptr;
+		cudaError_t e = cudaMalloc(&d, bytes ? bytes : 4);
+		if (e != cudaSuccess) return e;
+		pl->dev.push_back(d);
+		if (host && bytes) e = cudaMemcpy(d, host, bytes, cudaMemcpyHostToDevice);
+		*devOut = d;
+		return e;
+	};
+	cudaError_t e = cudaSuccess;
+	const void* d = nullptr;
+	if (e == cudaSuccess) { e = put(vs.data(), vs.size() * sizeof(MeshoptStream), &d); pl->p.vertexStreams = (const MeshoptStream*)d; pl->p.nVertexStreams = (uint32_t)vs.size(); }
+	if (e == cudaSuccess) { e = put(is.data(), is.size() * sizeof(MeshoptStream), &d); pl->p.indexStreams = (const MeshoptStream*)d; pl->p.nIndexStreams = (uint32_t)is.size(); }
+	if (e == cudaSuccess) { e = put(fs.data(), fs.size() * sizeof(MeshoptStream), &d); pl->p.filtered = (const MeshoptStream*)d; pl->p.nFiltered = (uint32_t)fs.size(); }
+	if (e == cudaSuccess) { e = put(elemFirst.data(), elemFirst.size() * 8, &d); pl->p.elemFirst = (const unsigned long long*)d; pl->p.filterElems = felems; }
+	if (e == cudaSuccess) { e = put(blockStream.data(), blockStream.size() * 4, &d); pl->p.blockStream = (const uint32_t*)d; pl->p.nBlocks = (uint32_t)blockStream.size(); }
+	if (e == cudaSuccess) { e = put(nullptr, (size_t)planes * 4, &d); pl->p.planeOff = (uint32_t*)d; }
+	if (e == cudaSuccess) { e = put(nullptr, (size_t)planes, &d); pl->p.totals = (uint32_t*)d; }  // planes / 4 words
+	if (e == cudaSuccess) { e = put(nullptr, (size_t)n * 4, &d); pl->p.status = (int32_t*)d; }
+	if (e != cudaSuccess) {
+		vkv_meshopt_plan_destroy(c, pl);
+		return fail(c, e == cudaErrorMemoryAllocation ? VKV_ERR_OOM : VKV_ERR_CUDA, "vkv_meshopt_plan_create: %s", cudaGetErrorString(e));
+	}
+	*out = pl;
+	return VKV_OK;
+}
+
+int vkv_meshopt_run(vkv_ctx* c, vkv_meshopt_plan* pl, uint64_t src_dev, size_t src_bytes, uint64_t dst_dev, size_t dst_bytes) {
+	if (!c || !pl) return c ? fail(c, VKV_ERR_INVALID, "vkv_meshopt_run: NULL argument") : VKV_ERR_INVALID;
+	if (pl->src_need > src_bytes) return fail(c, VKV_ERR_INVALID, "vkv_meshopt_run: a view reaches byte %llu of a %zu-byte source", pl->src_need, src_bytes);
+	if (pl->dst_need > dst_bytes) return fail(c, VKV_ERR_INVALID, "vkv_meshopt_run: a view reaches byte %llu of a %zu-byte destination", pl->dst_need, dst_bytes);
+	if (pl->n_views == 0) return VKV_OK;
+	if ((!src_dev && pl->src_need) || (!dst_dev && pl->dst_need) || dst_dev % 4) return fail(c, VKV_ERR_INVALID, "vkv_meshopt_run: bad buffer address");
+	CK(cudaSetDevice(c->device));
+	CK(launch_meshopt_decode(pl->p, (const uint8_t*)(uintptr_t)src_dev, (uint8_t*)(uintptr_t)dst_dev, c->num_sms, c->stream, nullptr));
+	return VKV_OK;
+}
+
+int vkv_meshopt_results(vkv_ctx* c, vkv_meshopt_plan* pl, int32_t* results) {
+	if (!c || !pl || (!results && pl->n_views)) return c ? fail(c, VKV_ERR_INVALID, "vkv_meshopt_results: NULL argument") : VKV_ERR_INVALID;
+	CK(cudaSetDevice(c->device));
+	if (pl->n_views) CK(cudaMemcpyAsync(results, pl->p.status, (size_t)pl->n_views * 4, cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	return VKV_OK;
+}
+
+void vkv_meshopt_plan_destroy(vkv_ctx* c, vkv_meshopt_plan* pl) {
+	if (!pl) return;
+	if (c) cudaSetDevice(c->device);
+	for (void* d : pl->dev) cudaFree(d);
+	delete pl;
+}
 
 int vkv_selftest_division(vkv_ctx* c, uint64_t seed, uint32_t iters_per_thread, uint64_t* tested, uint64_t* mismatches) {
 	if (!c || !tested || !mismatches) return VKV_ERR_INVALID;

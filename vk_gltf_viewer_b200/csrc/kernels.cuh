@@ -115,5 +115,27 @@ cudaError_t launch_segment_scan(const vkv_DrawSegment* seg, uint32_t n, const vk
 cudaError_t launch_expand_segments(const vkv_DrawSegment* seg, uint32_t n, const uint32_t* offsets, vkv_MeshletDraw* draws, uint32_t capacity,
                                    int num_sms, cudaStream_t stream);
 
+// ---- EXT_meshopt_compression decode (meshopt.cu) -------------------------------------------------------------------
+struct MeshoptStream {               // one compressed buffer view, as the kernels see it
+	unsigned long long src_off, src_size, dst_off;
+	uint32_t count, stride;          // elements and bytes per element (vertex size, or index size 2 / 4)
+	uint32_t mode, filter;           // vkv_MeshoptView::mode / ::filter
+	uint32_t view;                   // index into the caller's view array (status slot)
+	uint32_t block_size;             // vertex streams: vertices per block (vertexcodec.cpp:116-126)
+	uint32_t first_block;            // vertex streams: global index of the stream's first block
+	uint32_t plane_base;             // vertex streams: first entry of the stream in planeOff (a multiple of 4; totals use plane_base / 4)
+};
+struct MeshoptPlan {                 // device-resident description of a decode job (built once per asset)
+	const MeshoptStream* vertexStreams; uint32_t nVertexStreams;
+	const MeshoptStream* indexStreams; uint32_t nIndexStreams;
+	const MeshoptStream* filtered; uint32_t nFiltered;      // views with a filter, with the element prefix below
+	const unsigned long long* elemFirst; unsigned long long filterElems;
+	const uint32_t* blockStream; uint32_t nBlocks;          // vertex block -> vertex stream
+	uint32_t* planeOff;              // scratch: start of every byte plane of every block (u32 per plane)
+	uint32_t* totals;                // scratch: per block and 4 planes, the block's delta total, then its carry
+	int32_t* status;                 // per view: meshoptimizer's return code
+};
+cudaError_t launch_meshopt_decode(const MeshoptPlan& p, const uint8_t* src, uint8_t* dst, int num_sms, cudaStream_t stream, int* launches);
+
 // ---- arithmetic self checks (selftest.cu) -------------------------------------------------------------------------
 cudaError_t launch_division_selftest(uint64_t seed, uint32_t iters, unsigned long long* counters2, unsigned long long negZero2, int num_sms, cudaStream_t stream);
