@@ -7,8 +7,8 @@
 // Vertex streams (the bulk of the bytes).  A stream is a chain of blocks of <= 256 vertices; a block is `stride` byte planes;
 // a plane is <= 16 groups of 16 deltas whose encoded size (0 / 4+n / 8+n / 16 bytes) depends on the group's own bytes, so the
 // POSITION of everything is only known by walking the stream front to back.  What is serial is therefore split from what is not:
-//   vscan    one thread per stream walks the group headers and sentinel counts and records where every plane starts
-//            (u32 per plane) — the only serial step, ~20 instructions per 16 decoded bytes;
+//   vscan    one warp per stream records where every plane starts (u32 per plane): the lanes tabulate the sentinel counts of
+//            a 1 KB window for every byte offset, lane 0 walks the groups with one table lookup each — the only serial step;
 //   vdecode  one thread block per vertex block: `stride` threads re-walk their plane's <= 16 groups in parallel, then every
 //            thread decodes its vertex's byte of four planes at a time (sentinel rank by popcount), a block-wide inclusive scan
 //            with byte-wise SIMD adds (__vadd4) undoes the delta coding RELATIVE to the block start, the 8 KB tile is written
@@ -64,39 +64,96 @@ __device__ __forceinline__ uint32_t group_value(const uint8_t* p, uint32_t bits,
 }
 
 // ---- vscan: where every plane of every block starts; meshopt_decodeVertexBuffer's framing checks and return codes ----------
-__global__ void vscan_kernel(const MeshoptStream* __restrict__ streams, uint32_t nStreams, const uint8_t* __restrict__ src,
-                             uint32_t* __restrict__ planeOff, int32_t* __restrict__ status) {
-	const uint32_t sid = blockIdx.x * blockDim.x + threadIdx.x;
+// One WARP per stream.  The walk itself is a serial chain (a group's position is the sum of the sizes before it), so it is
+// made as short as a chain can be: the warp stages the next kScanWin bytes of the stream in shared memory and tabulates, for
+// EVERY byte offset of the window, the sentinel count a 2-bit and a 4-bit group starting there would have (32 lanes, a few
+// hundred instructions); lane 0 then walks groups with one shared-memory lookup and one add per group (~40 cycles, against
+// ~850 for a thread that chases bytes in global memory), records where each plane starts, and asks for the next window.
+constexpr uint32_t kScanWin = 1024;                 // offsets with tabulated counts per window
+constexpr uint32_t kScanWords = kScanWin / 4 + 4;   // staged words: the last offset reads 8 bytes + alignment slack
+constexpr int kScanWarps = 4;
+struct ScanSmem {
+	uint32_t w[kScanWords];
+	uint8_t c1[kScanWin], c2[kScanWin];
+};
+__global__ void __launch_bounds__(kScanWarps * 32) vscan_kernel(const MeshoptStream* __restrict__ streams, uint32_t nStreams, const uint8_t* __restrict__ src,
+                                                               uint32_t* __restrict__ planeOff, int32_t* __restrict__ status) {
+	__shared__ ScanSmem sm[kScanWarps];
+	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+	const uint32_t sid = blockIdx.x * kScanWarps + warp;
 	if (sid >= nStreams) return;
+	ScanSmem& S = sm[warp];
 	const MeshoptStream st = streams[sid];
 	const uint8_t* s = src + st.src_off;
-	const uint64_t size = st.src_size;
+	const uint32_t size = (uint32_t)st.src_size; // < 2^30 (checked when the plan is built)
 	const uint32_t stride = st.stride;
 	int rc = 0;
-	if (size < 1ull + stride) rc = -2;
+	if ((unsigned long long)size < 1ull + stride) rc = -2;
 	else if ((s[0] & 0xf0) != 0xa0 || (s[0] & 0x0f) > 0) rc = -1;
-	else {
-		uint64_t pos = 1;
+	if (rc == 0) {
+		// walk state (meaningful in lane 0, carried by every lane so the loop stays convergent)
+		uint32_t pos = 1, v0 = 0, k = 0, g = 0xffffffffu /* at a plane header */, hbits = 0;
+		uint32_t n = min(st.block_size, st.count), groups = round16(n) / 16, hs = (groups + 3) / 4;
 		uint32_t* po = planeOff + st.plane_base;
-		for (uint32_t v0 = 0; v0 < st.count && rc == 0; v0 += st.block_size) {
-			const uint32_t n = min(st.block_size, st.count - v0);
-			const uint32_t groups = round16(n) / 16, hs = (groups + 3) / 4;
-			for (uint32_t k = 0; k < stride && rc == 0; ++k) {
-				*po++ = (uint32_t)pos;
-				if (size - pos < hs) { rc = -2; break; }
-				const uint64_t hdr = pos;
-				pos += hs;
-				for (uint32_t g = 0; g < groups; ++g) {
-					if (size - pos < 24) { rc = -2; break; } // kByteGroupDecodeLimit
-					const uint32_t bits = (s[hdr + g / 4] >> ((g % 4) * 2)) & 3u;
-					pos += group_size(s + pos, bits);
+		bool done = st.count == 0;
+		while (!done && rc == 0) {
+			// stage [base, base + 4*kScanWords) of the stream, base = pos rounded down to a 4-byte boundary of the ADDRESS
+			const uintptr_t addr = (uintptr_t)(s + pos);
+			const uint32_t mis = (uint32_t)(addr & 3u);
+			const uint32_t* aligned = (const uint32_t*)(addr - mis);
+			const uint32_t avail = size - pos + mis;     // bytes from the aligned base to the end of the stream
+			for (uint32_t i = lane; i < kScanWords; i += 32) S.w[i] = (i * 4 < avail) ? __ldg(aligned + i) : 0u;
+			__syncwarp();
+			for (uint32_t o = lane; o < kScanWin; o += 32) {
+				const uint32_t i = o >> 2, sh = (o & 3u) * 8;
+				const uint32_t lo = __funnelshift_r(S.w[i], S.w[i + 1], sh), hi = __funnelshift_r(S.w[i + 1], S.w[i + 2], sh);
+				S.c1[o] = (uint8_t)__popc(lo & (lo >> 1) & 0x55555555u);
+				S.c2[o] = (uint8_t)(__popc(lo & (lo >> 1) & (lo >> 2) & (lo >> 3) & 0x11111111u) + __popc(hi & (hi >> 1) & (hi >> 2) & (hi >> 3) & 0x11111111u));
+			}
+			__syncwarp();
+			if (lane == 0) {
+				const uint32_t base = pos - mis; // stream offset of window byte 0
+				for (;;) {
+					const uint32_t o = pos - base;
+					if (g == 0xffffffffu) { // a plane header: hs <= 4 bytes, 2 bits per group
+						if (size - pos < hs) { rc = -2; break; }
+						if (o + 4 > kScanWin) break; // next window
+						*po++ = pos;
+						hbits = __funnelshift_r(S.w[o >> 2], S.w[(o >> 2) + 1], (o & 3u) * 8);
+						if (hs < 4) hbits &= (1u << (8 * hs)) - 1u;
+						pos += hs;
+						g = 0;
+						continue;
+					}
+					if (g < groups) {
+						if (size - pos < 24) { rc = -2; break; } // kByteGroupDecodeLimit
+						if (o >= kScanWin) break;                 // next window
+						const uint32_t bits = (hbits >> (2 * g)) & 3u;
+						pos += bits == 0 ? 0u : bits == 3 ? 16u : bits == 1 ? 4u + S.c1[o] : 8u + S.c2[o];
+						++g;
+						continue;
+					}
+					// plane finished
+					g = 0xffffffffu;
+					if (++k == stride) {
+						k = 0;
+						v0 += st.block_size;
+						if (v0 >= st.count) { done = true; break; }
+						n = min(st.block_size, st.count - v0); groups = round16(n) / 16; hs = (groups + 3) / 4;
+					}
 				}
 			}
+			pos = __shfl_sync(0xffffffffu, pos, 0); g = __shfl_sync(0xffffffffu, g, 0); k = __shfl_sync(0xffffffffu, k, 0);
+			v0 = __shfl_sync(0xffffffffu, v0, 0); hbits = __shfl_sync(0xffffffffu, hbits, 0);
+			n = __shfl_sync(0xffffffffu, n, 0); groups = __shfl_sync(0xffffffffu, groups, 0); hs = __shfl_sync(0xffffffffu, hs, 0);
+			rc = __shfl_sync(0xffffffffu, rc, 0); done = __shfl_sync(0xffffffffu, (int)done, 0) != 0;
+			po = (uint32_t*)__shfl_sync(0xffffffffu, (unsigned long long)po, 0);
+			__syncwarp();
 		}
-		const uint64_t tail = stride < 32 ? 32 : stride;
+		const uint32_t tail = stride < 32 ? 32 : stride;
 		if (rc == 0 && size - pos != tail) rc = -3;
 	}
-	status[st.view] = rc;
+	if (lane == 0) status[st.view] = rc;
 }
 
 // ---- vdecode: one thread block per vertex block -----------------------------------------------------------------------------
@@ -218,6 +275,7 @@ __device__ __forceinline__ void put_index(uint8_t* dst, size_t i, uint32_t index
 	else ((uint32_t*)dst)[i] = v;
 }
 
+// the FIFOs live in local memory (L1-resident; a shared-memory layout measured 10 % slower, see profiles/README.md)
 __device__ int decode_triangles(uint8_t* dst, uint32_t index_count, uint32_t index_size, const uint8_t* buffer, uint64_t buffer_size) {
 	// :362-540
 	if (index_count % 3 || (index_size != 2 && index_size != 4)) return -1;
@@ -376,16 +434,18 @@ __global__ void filter_kernel(const MeshoptStream* __restrict__ filtered, uint32
 } // namespace
 
 cudaError_t launch_meshopt_decode(const MeshoptPlan& p, const uint8_t* src, uint8_t* dst, int num_sms, cudaStream_t stream, int* launches) {
+	// (running the index kernel on a second stream beside the vertex kernels was measured: the single-thread chains get starved
+	// by the wide vertex blocks and the whole decode takes 2.8x longer — one stream, back to back)
 	int n = 0;
+	if (p.nIndexStreams) { idecode_kernel<<<(p.nIndexStreams + 31) / 32, 32, 0, stream>>>(p.indexStreams, p.nIndexStreams, src, dst, p.status); ++n; }
 	if (p.nVertexStreams) {
-		vscan_kernel<<<(p.nVertexStreams + 31) / 32, 32, 0, stream>>>(p.vertexStreams, p.nVertexStreams, src, p.planeOff, p.status); ++n;
+		vscan_kernel<<<(p.nVertexStreams + kScanWarps - 1) / kScanWarps, kScanWarps * 32, 0, stream>>>(p.vertexStreams, p.nVertexStreams, src, p.planeOff, p.status); ++n;
 		if (p.nBlocks) {
 			vdecode_kernel<<<p.nBlocks, kVdThreads, 0, stream>>>(p.vertexStreams, p.blockStream, src, dst, p.planeOff, p.status, p.totals); ++n;
 			vcarry_kernel<<<p.nVertexStreams, 64, 0, stream>>>(p.vertexStreams, p.nVertexStreams, src, p.status, p.totals); ++n;
 			vadd_kernel<<<p.nBlocks, kVdThreads, 0, stream>>>(p.vertexStreams, p.blockStream, dst, p.status, p.totals); ++n;
 		}
 	}
-	if (p.nIndexStreams) { idecode_kernel<<<(p.nIndexStreams + 31) / 32, 32, 0, stream>>>(p.indexStreams, p.nIndexStreams, src, dst, p.status); ++n; }
 	if (p.nFiltered && p.filterElems) {
 		unsigned long long grid = (p.filterElems + 255) / 256;
 		if (grid > (unsigned long long)num_sms * 16) grid = (unsigned long long)num_sms * 16;
