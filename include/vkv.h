@@ -122,6 +122,24 @@ int vkv_meshopt_results(vkv_ctx*, vkv_meshopt_plan*, int32_t* results);   /* n_v
 void vkv_meshopt_plan_destroy(vkv_ctx*, vkv_meshopt_plan*);
 int vkv_alloc(vkv_ctx*, size_t bytes, uint64_t* dev_addr);                /* zero-filled device buffer, same bookkeeping as vkv_upload */
 
+/* ---- meshlet partition + bounds on the device.  Stands where PrimitiveProcessingTask::processPrimitive
+ * builds meshlets and their AABBs on the host (assets.cpp:322-373).  Per primitive: a u32 triangle-list index buffer and the
+ * vertex buffer (position = three floats at the start of every `vertex_stride` bytes: glsl::Vertex, 24 B), both device
+ * addresses.  Output per primitive: Meshlet[] in the reference's 36-byte layout with aabbExtents / aabbCenter computed as
+ * assets.cpp:349-372 does, the meshlet vertex-index list (u32) and the meshlet triangle bytes (each meshlet padded to 4) —
+ * the three arrays glsl::Primitive points at.  The partition is meshoptimizer's SCAN partition (meshopt_buildMeshletsScan:
+ * triangles in index order), byte-identical to that function; the reference's meshopt_buildMeshlets + meshopt_optimizeMeshlet
+ * order heuristics are not reproduced (no golden output exists for them; any valid partition renders the same image).
+ * max_vertices <= 64, max_triangles <= 252 (the reference uses 64 / 124).  All primitives of a call share three allocations:
+ * release out[0].meshlets, out[0].vertex_indices and out[0].triangles with vkv_free. ------------------------------------ */
+typedef struct vkv_MeshletBuildInput { uint64_t indices, vertices; uint32_t index_count, vertex_count; } vkv_MeshletBuildInput;
+typedef struct vkv_MeshletBuildOutput {
+	uint64_t meshlets, vertex_indices, triangles;                       /* device addresses of this primitive's arrays */
+	uint32_t meshlet_count, vertex_index_count, triangle_bytes, reserved;
+} vkv_MeshletBuildOutput;
+int vkv_build_meshlets(vkv_ctx*, const vkv_MeshletBuildInput* host_inputs, uint32_t n, uint32_t vertex_stride, uint32_t max_vertices,
+                       uint32_t max_triangles, vkv_MeshletBuildOutput* host_outputs);
+
 /* ---- resolve: visbuffer -> RGBA8 colour image.  Replaces shaders/visbuffer/visbuffer_resolve.comp.glsl:17-41
  * and its dispatch (application.cpp:917-949); the push constants' drawBuffer / primitiveBuffer / materialBuffer are the fields
  * of the reference's VisbufferResolvePushConstants (visbuffer.h.glsl:49-56).  Texel = R | G<<8 | B<<16 | A<<24, sRGB-encoded

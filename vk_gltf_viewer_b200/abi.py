@@ -85,6 +85,11 @@ MATERIAL_DTYPE = np.dtype(
 MESHOPT_VIEW_DTYPE = np.dtype([("mode", "<u4"), ("filter", "<u4"), ("count", "<u4"), ("stride", "<u4"),
                                ("src_offset", "<u8"), ("src_size", "<u8"), ("dst_offset", "<u8")])
 assert MESHOPT_VIEW_DTYPE.itemsize == 40
+# vkv_MeshletBuildInput / vkv_MeshletBuildOutput (include/vkv.h)
+MESHLET_BUILD_INPUT_DTYPE = np.dtype([("indices", "<u8"), ("vertices", "<u8"), ("index_count", "<u4"), ("vertex_count", "<u4")])
+MESHLET_BUILD_OUTPUT_DTYPE = np.dtype([("meshlets", "<u8"), ("vertex_indices", "<u8"), ("triangles", "<u8"), ("meshlet_count", "<u4"),
+                                       ("vertex_index_count", "<u4"), ("triangle_bytes", "<u4"), ("reserved", "<u4")])
+assert MESHLET_BUILD_INPUT_DTYPE.itemsize == 24 and MESHLET_BUILD_OUTPUT_DTYPE.itemsize == 40
 assert MESHLET_DTYPE.itemsize == 36 and VERTEX_DTYPE.itemsize == 24 and DRAW_DTYPE.itemsize == 12 and MATERIAL_DTYPE.itemsize == 48
 
 

@@ -49,6 +49,7 @@ EXPORTS = [
     "vkv_event_record", "vkv_event_elapsed", "vkv_flush_l2", "vkv_visbuffer64_ptr",
     "vkv_resolve", "vkv_read_color", "vkv_build_draws", "vkv_download",
     "vkv_selftest_division",
+    "vkv_build_meshlets",
     "vkv_alloc", "vkv_meshopt_plan_create", "vkv_meshopt_run", "vkv_meshopt_results", "vkv_meshopt_plan_destroy",
     "vkv_set_shard", "vkv_set_shard_interleaved", "vkv_ipc_export", "vkv_ipc_attach", "vkv_ipc_detach", "vkv_merge",
 ]
@@ -106,6 +107,7 @@ def _lib():
         L.vkv_merge.argtypes = [vp]
         L.vkv_selftest_division.argtypes = [vp, u64, u32, C.POINTER(u64), C.POINTER(u64)]
         L.vkv_alloc.argtypes = [vp, C.c_size_t, C.POINTER(u64)]
+        L.vkv_build_meshlets.argtypes = [vp, vp, u32, u32, u32, u32, vp]
         L.vkv_meshopt_plan_create.argtypes = [vp, vp, u32, C.POINTER(vp)]
         L.vkv_meshopt_run.argtypes = [vp, vp, u64, C.c_size_t, u64, C.c_size_t]
         L.vkv_meshopt_results.argtypes = [vp, vp, vp]
@@ -263,6 +265,14 @@ class Renderer:
         t, m = C.c_uint64(), C.c_uint64()
         self._ck(self.L.vkv_selftest_division(self.h, seed, iters_per_thread, C.byref(t), C.byref(m)))
         return t.value, m.value
+
+    # ---- meshlet partition + bounds on the device -------------------------------------------
+    def build_meshlets(self, inputs: np.ndarray, vertex_stride=24, max_vertices=64, max_triangles=124) -> np.ndarray:
+        """inputs: structured array of abi.MESHLET_BUILD_INPUT_DTYPE (device addresses) -> array of abi.MESHLET_BUILD_OUTPUT_DTYPE"""
+        i = np.ascontiguousarray(inputs, abi.MESHLET_BUILD_INPUT_DTYPE)
+        o = np.zeros(max(1, i.shape[0]), abi.MESHLET_BUILD_OUTPUT_DTYPE)
+        self._ck(self.L.vkv_build_meshlets(self.h, i.ctypes.data, i.shape[0], vertex_stride, max_vertices, max_triangles, o.ctypes.data))
+        return o[:i.shape[0]]
 
     # ---- EXT_meshopt_compression decode on the device (SURVEY §8f-3) ----------------------------------------
     def alloc(self, nbytes: int) -> int:

@@ -963,6 +963,97 @@ void vkv_meshopt_plan_destroy(vkv_ctx* c, vkv_meshopt_plan* pl) {
 	delete pl;
 }
 
+// ---- meshlet partition + bounds (kernels in meshlets.cu) -------------------------------------------------
+int vkv_build_meshlets(vkv_ctx* c, const vkv_MeshletBuildInput* in, uint32_t n, uint32_t vertex_stride, uint32_t max_vertices, uint32_t max_triangles,
+                       vkv_MeshletBuildOutput* out) {
+	if (!c || !out || (!in && n)) return c ? fail(c, VKV_ERR_INVALID, "vkv_build_meshlets: NULL argument") : VKV_ERR_INVALID;
+	if (max_vertices < 3 || max_vertices > 64 || max_triangles < 1 || max_triangles > 252) return fail(c, VKV_ERR_INVALID, "vkv_build_meshlets: limits %u / %u (max 64 / 252)", max_vertices, max_triangles);
+	if (vertex_stride < 12 || vertex_stride % 4) return fail(c, VKV_ERR_INVALID, "vkv_build_meshlets: vertex_stride %u", vertex_stride);
+	CK(cudaSetDevice(c->device));
+	std::vector<MeshletBuildPrim> prims(n);
+	std::vector<uint32_t> triFirst(n + 1, 0);
+	std::vector<MeshletBuildSeg> segs;
+	unsigned long long total = 0;
+	for (uint32_t i = 0; i < n; ++i) {
+		if (in[i].index_count % 3) return fail(c, VKV_ERR_INVALID, "vkv_build_meshlets: primitive %u has %u indices", i, in[i].index_count);
+		if (in[i].index_count && (!in[i].indices || !in[i].vertices)) return fail(c, VKV_ERR_INVALID, "vkv_build_meshlets: primitive %u: NULL buffer", i);
+		prims[i] = MeshletBuildPrim{(const uint32_t*)(uintptr_t)in[i].indices, (const uint8_t*)(uintptr_t)in[i].vertices};
+		const uint32_t T = in[i].index_count / 3;
+		triFirst[i] = (uint32_t)total;
+		for (uint32_t t = 0; t < T; t += kMeshletSeg)
+			segs.push_back(MeshletBuildSeg{(uint32_t)total + t, (uint32_t)total + std::min(T, t + kMeshletSeg), i, t == 0 ? 1u : 0u});
+		total += T;
+		if (total >= (1ull << 30)) return fail(c, VKV_ERR_LIMIT, "vkv_build_meshlets: more than 2^30 triangles in one call");
+	}
+	triFirst[n] = (uint32_t)total;
+	for (uint32_t i = 0; i < n; ++i) out[i] = vkv_MeshletBuildOutput{0, 0, 0, 0, 0, 0, 0};
+	if (total == 0) return VKV_OK;
+
+	std::vector<void*> scratch;
+	auto release = [&]() { for (void* d : scratch) cudaFree(d); };
+	auto dev = [&](size_t bytes, const void* host, void** outp) -> cudaError_t {
+		void* d = nullptr;
+		cudaError_t e = cudaMalloc(&d, bytes ? bytes : 4);
+		if (e != cudaSuccess) return e;
+		scratch.push_back(d);
+		if (host) e = cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, c->stream);
+		*outp = d;
+		return e;
+	};
+#define MBCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { release(); return fail(c, e_ == cudaErrorMemoryAllocation ? VKV_ERR_OOM : VKV_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } } while (0)
+	MeshletBuildJob j{};
+	j.nPrims = n; j.totalTris = (uint32_t)total; j.nSegs = (uint32_t)segs.size(); j.maxV = max_vertices; j.maxT = max_triangles; j.vertexStride = vertex_stride;
+	void* d = nullptr;
+	MBCK(dev(prims.size() * sizeof(MeshletBuildPrim), prims.data(), &d)); j.prims = (const MeshletBuildPrim*)d;
+	MBCK(dev(triFirst.size() * 4, triFirst.data(), &d)); j.triFirst = (const uint32_t*)d;
+	MBCK(dev(segs.size() * sizeof(MeshletBuildSeg), segs.data(), &d)); j.segs = (const MeshletBuildSeg*)d;
+	MBCK(dev((size_t)total, nullptr, &d)); j.len = (uint8_t*)d;
+	MBCK(dev((size_t)total, nullptr, &d)); j.ucnt = (uint8_t*)d;
+	MBCK(dev(segs.size() * max_triangles * sizeof(MeshletBuildSegEntry), nullptr, &d)); j.table = (MeshletBuildSegEntry*)d;
+	MBCK(dev(segs.size() * sizeof(MeshletBuildSegState), nullptr, &d)); j.state = (MeshletBuildSegState*)d;
+	MBCK(dev((size_t)(n + 1) * 12, nullptr, &d)); j.primBase = (uint32_t*)d;
+	MBCK(launch_meshlet_scan(j, c->stream));
+	std::vector<uint32_t> base((size_t)(n + 1) * 3);
+	MBCK(cudaMemcpyAsync(base.data(), j.primBase, base.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+	MBCK(cudaStreamSynchronize(c->stream));
+	const uint32_t M = base[n * 3], V = base[n * 3 + 1], B = base[n * 3 + 2];
+	MBCK(dev((size_t)M * sizeof(MeshletBuildRecord), nullptr, &d)); j.rec = (MeshletBuildRecord*)d;
+	// outputs: three allocations shared by the primitives of this call, registered like vkv_upload's
+	void* outs[3] = {nullptr, nullptr, nullptr};
+	const size_t sizes[3] = {(size_t)M * sizeof(vkv_Meshlet), (size_t)V * 4, (size_t)B};
+	for (int k = 0; k < 3; ++k) {
+		const size_t padded = ((sizes[k] ? sizes[k] : 1) + 255) & ~(size_t)255;
+		cudaError_t e = cudaMalloc(&outs[k], padded);
+		if (e == cudaSuccess) e = cudaMemsetAsync(outs[k], 0, padded, c->stream);
+		if (e != cudaSuccess) {
+			for (int q = 0; q <= k; ++q) if (outs[q]) cudaFree(outs[q]);
+			release();
+			return fail(c, e == cudaErrorMemoryAllocation ? VKV_ERR_OOM : VKV_ERR_CUDA, "vkv_build_meshlets: output allocation: %s", cudaGetErrorString(e));
+		}
+	}
+	cudaError_t e = launch_meshlet_emit(j, M, (vkv_Meshlet*)outs[0], (uint32_t*)outs[1], (uint8_t*)outs[2], c->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+	release();
+	if (e != cudaSuccess) {
+		for (int k = 0; k < 3; ++k) cudaFree(outs[k]);
+		return fail(c, VKV_ERR_CUDA, "vkv_build_meshlets: %s", cudaGetErrorString(e));
+	}
+#undef MBCK
+	{
+		std::lock_guard<std::mutex> lock(c->mtx);
+		for (int k = 0; k < 3; ++k) c->allocs[(uint64_t)(uintptr_t)outs[k]] = sizes[k];
+	}
+	for (uint32_t i = 0; i < n; ++i) {
+		const uint32_t* b0 = &base[i * 3];
+		const uint32_t* b1 = &base[(i + 1) * 3];
+		out[i].meshlets = (uint64_t)(uintptr_t)outs[0] + (uint64_t)b0[0] * sizeof(vkv_Meshlet);
+		out[i].vertex_indices = (uint64_t)(uintptr_t)outs[1] + (uint64_t)b0[1] * 4;
+		out[i].triangles = (uint64_t)(uintptr_t)outs[2] + b0[2];
+		out[i].meshlet_count = b1[0] - b0[0]; out[i].vertex_index_count = b1[1] - b0[1]; out[i].triangle_bytes = b1[2] - b0[2];
+	}
+	return VKV_OK;
+}
+
 int vkv_selftest_division(vkv_ctx* c, uint64_t seed, uint32_t iters_per_thread, uint64_t* tested, uint64_t* mismatches) {
 	if (!c || !tested || !mismatches) return VKV_ERR_INVALID;
 	CK(cudaSetDevice(c->device));

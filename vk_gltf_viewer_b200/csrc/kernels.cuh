@@ -137,5 +137,28 @@ struct MeshoptPlan {                 // device-resident description of a decode 
 };
 cudaError_t launch_meshopt_decode(const MeshoptPlan& p, const uint8_t* src, uint8_t* dst, int num_sms, cudaStream_t stream, int* launches);
 
+// ---- meshlet partition + bounds (meshlets.cu) ----------------------------------------------------------------------
+constexpr uint32_t kMeshletSeg = 2048;   // triangles per chain segment
+struct MeshletBuildPrim { const uint32_t* indices; const uint8_t* vertices; };
+struct MeshletBuildSeg { uint32_t start, end; uint32_t prim; uint32_t first_of_prim; };   // global triangle range [start, end) inside one primitive
+struct MeshletBuildSegEntry { uint32_t meshlets, vertices, bytes, exit; };                 // per (segment, entry offset)
+struct MeshletBuildSegState { uint32_t entry, meshlets, vertices, bytes; };                // where the chain enters a segment, output bases there
+struct MeshletBuildRecord { uint32_t start, vertices, bytes; };                            // per meshlet: first triangle (global), output offsets (global)
+struct MeshletBuildJob {
+	const MeshletBuildPrim* prims; uint32_t nPrims;
+	const uint32_t* triFirst;        // [nPrims + 1] global index of each primitive's first triangle
+	uint32_t totalTris;
+	const MeshletBuildSeg* segs; uint32_t nSegs;
+	uint32_t maxV, maxT, vertexStride;
+	uint8_t* len; uint8_t* ucnt;     // per triangle: size and distinct-vertex count of the greedy meshlet starting there
+	MeshletBuildSegEntry* table;     // [nSegs * maxT]
+	MeshletBuildSegState* state;     // [nSegs]
+	uint32_t* primBase;              // [(nPrims + 1) * 3] meshlets / vertex indices / triangle bytes before each primitive (last = totals)
+	MeshletBuildRecord* rec;         // [total meshlets]
+};
+cudaError_t launch_meshlet_scan(const MeshletBuildJob& j, cudaStream_t stream);   // len + segment + chain -> primBase
+cudaError_t launch_meshlet_emit(const MeshletBuildJob& j, uint32_t nMeshlets, vkv_Meshlet* meshlets, uint32_t* meshletVertices, uint8_t* meshletTriangles,
+                                cudaStream_t stream);
+
 // ---- arithmetic self checks (selftest.cu) -------------------------------------------------------------------------
 cudaError_t launch_division_selftest(uint64_t seed, uint32_t iters, unsigned long long* counters2, unsigned long long negZero2, int num_sms, cudaStream_t stream);
