@@ -315,11 +315,15 @@ def main():
             stages[name] = {"ms": round(m, 5), "bytes": int(b), "GB/s": round(gbs, 1), "frac_hbm": round(gbs / hbm, 4)}
         dom = max(stages, key=lambda sname: stages[sname]["ms"])
         traffic = None
-        try:  # dram bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this workload
+        issue = None
+        try:  # dram bytes per launch (and issue-slot use) of the dominant kernel from the committed `ncu --set full` capture of this workload
             tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
             ent = tr.get(f"cfg{args.config}", {}).get(dom)
             if ent and world == 1:
                 traffic = ent["dram_read_bytes"] + ent["dram_write_bytes"]
+                if "ipc_active" in ent:  # the roofline that actually bounds an issue-bound kernel: warp-instructions per cycle per SM, peak 4
+                    issue = {"ipc_active": ent["ipc_active"], "peak": 4.0, "frac": round(ent["ipc_active"] / 4.0, 3),
+                             "warp_instructions": ent.get("warp_instructions"), "source": ent.get("capture")}
         except Exception:
             pass
         line = {
@@ -339,7 +343,7 @@ def main():
                     "note": "camera + all node transforms uploaded from host every frame, frame counters read back every frame (wall clock, no L2 flush)"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["GB/s"], "peak": hbm, "unit": "GB/s", "frac": stages[dom]["frac_hbm"],
-                         "traffic": traffic, "peak_source": peak_src,
+                         "traffic": traffic, "issue": issue, "peak_source": peak_src,
                          "note": "dominant kernel = software rasteriser: SM-issue / L2-atomic bound, working set L2 resident (dram traffic << algorithmic input bytes); "
                                  "`achieved` = input-side algorithmic bytes (SURVEY §8d) / CUDA-event time; cull / HiZ / clear fractions are in `stages`"},
             "stages": stages,
