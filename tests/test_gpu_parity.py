@@ -122,6 +122,28 @@ def test_cull_stress_degenerate_boxes(seed):
     assert any(x[1] > 0 for x in summ) and any(x[2] > 0 for x in summ)  # the HiZ test rejected something and pass B recovered something
 
 
+def test_resize_between_frames():
+    """vkv_resize (application.cpp:578-602 updateRenderResolution): targets are rebuilt, the pyramid restarts from its cleared
+    state, and the next frames are bit-exact at the new size — even (fused clear) and odd (separate clear, tail-only HiZ) extents"""
+    s = S.occluder_and_hidden()
+    r = api.Renderer(640, 480)
+    cam = Camera(640, 480).look_at((0, 0, 8), (0, 0, 0))
+    pc_dev = r.upload_scene(s, cam)
+    for (W, H) in ((640, 480), (801, 451), (1280, 720), (127, 63)):
+        r.resize(W, H)
+        cam = Camera(W, H).look_at((0, 0, 8), (0, 0, 0))
+        r.update_camera(pc_dev, cam)
+        pc_host = s.host_push_constants(cam)
+        tg = O.Targets(W, H)
+        for eye in ((0, 0, 8), (0.4, 0.1, 8)):
+            cam.look_at(eye, (0, 0, 0))
+            r.update_camera(pc_dev, cam)
+            out = O.frame(pc_host, tg, two_pass=True)
+            r.frame(pc_dev, api.FRAME_TWO_PASS)
+            compare_frame(r, tg, out, True, label=f"{W}x{H}")
+    r.close()
+
+
 def test_atrium_cfg2_small():
     """BASELINE config 2 geometry (int16-quantised atrium) at reduced detail; full size in test_atrium_cfg2_full"""
     s = Scene.atrium(32)
