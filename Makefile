@@ -26,8 +26,8 @@ $(PKG)/libvkv.so: $(CU_SRCS) $(CU_HDRS)
 $(PKG)/libvkv_host.so: $(HOST_SRCS) $(HOST_HDRS)
 	$(CXX) $(CXXFLAGS) -shared -o $@ $(HOST_SRCS) -Iinclude
 
-oracle/liboracle.so: oracle/oracle.cpp oracle/meshopt_decode.cpp oracle/meshlet_build.cpp oracle/oracle.h include/vkv_abi.h
-	$(CXX) $(CXXFLAGS) -O3 -mavx2 -shared -o $@ oracle/oracle.cpp oracle/meshopt_decode.cpp oracle/meshlet_build.cpp
+oracle/liboracle.so: oracle/oracle.cpp oracle/meshopt_decode.cpp oracle/meshlet_build.cpp oracle/accessors.cpp oracle/oracle.h include/vkv_abi.h
+	$(CXX) $(CXXFLAGS) -O3 -mavx2 -shared -o $@ oracle/oracle.cpp oracle/meshopt_decode.cpp oracle/meshlet_build.cpp oracle/accessors.cpp
 
 ref:
 	@if [ -d /root/reference ]; then sh oracle/build_ref.sh; else echo "no /root/reference here: using prebuilt oracle/_ref if present"; fi

@@ -122,6 +122,17 @@ int vkv_meshopt_results(vkv_ctx*, vkv_meshopt_plan*, int32_t* results);   /* n_v
 void vkv_meshopt_plan_destroy(vkv_ctx*, vkv_meshopt_plan*);
 int vkv_alloc(vkv_ctx*, size_t bytes, uint64_t* dev_addr);                /* zero-filled device buffer, same bookkeeping as vkv_upload */
 
+/* ---- accessor conversions on the device.  Replace the host loops that fill glsl::Vertex and the u32 index vector
+ * (assets.cpp:308-320: fastgltf::iterateAccessor<glm::vec3> on POSITION, copyFromAccessor<uint32_t> on the indices): per
+ * component fastgltf's convertComponent<float, T> (tools.hpp:266-289) — float(x), or max(float(x) / float(T max), -1) for
+ * normalized integers (KHR_mesh_quantization).  component_type is the glTF enum (5120 BYTE, 5121 UNSIGNED_BYTE, 5122 SHORT,
+ * 5123 UNSIGNED_SHORT, 5125 UNSIGNED_INT, 5126 FLOAT); byte_stride 0 = tightly packed.  The source is a device address
+ * (e.g. inside the vkv_meshopt_run destination); the result is a new allocation (vkv_free): glsl::Vertex[count] with only
+ * `position` set, as the reference leaves it, or uint32[count]. -------------------------------------------------------- */
+int vkv_assemble_vertices(vkv_ctx*, uint64_t positions_dev, uint32_t component_type, int normalized, uint32_t byte_stride, uint32_t count,
+                          uint64_t* vertices_dev);
+int vkv_widen_indices(vkv_ctx*, uint64_t indices_dev, uint32_t component_type, uint32_t count, uint64_t* indices32_dev);
+
 /* ---- meshlet partition + bounds on the device.  Stands where PrimitiveProcessingTask::processPrimitive
  * builds meshlets and their AABBs on the host (assets.cpp:322-373).  Per primitive: a u32 triangle-list index buffer and the
  * vertex buffer (position = three floats at the start of every `vertex_stride` bytes: glsl::Vertex, 24 B), both device

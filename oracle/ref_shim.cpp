@@ -6,6 +6,7 @@
 #include <cstdint>
 #include <cstring>
 
+#include <fastgltf/tools.hpp>
 #include <glm/glm.hpp>
 #include <glm/gtc/matrix_transform.hpp>
 
@@ -91,6 +92,18 @@ void ref_node_matrix(const float parent[16], const float t[3], const float r[4],
 	std::memcpy(p.data(), parent, 64);
 	auto m = fm::scale(fm::rotate(fm::translate(p, fm::fvec3(t[0], t[1], t[2])), fm::fquat(r[0], r[1], r[2], r[3])), fm::fvec3(s[0], s[1], s[2]));
 	std::memcpy(out, m.data(), 64);
+}
+
+// fastgltf::internal::convertComponent<float, T> (tools.hpp:266-289): what iterateAccessor<glm::vec3> applies to every POSITION
+// component (assets.cpp:310-314).  type: glTF componentType (5120 BYTE, 5121 UNSIGNED_BYTE, 5122 SHORT, 5123 UNSIGNED_SHORT)
+float ref_convert_component(int type, int normalized, int value) {
+	switch (type) {
+	case 5120: return fastgltf::internal::convertComponent<float, std::int8_t>((std::int8_t)value, normalized != 0);
+	case 5121: return fastgltf::internal::convertComponent<float, std::uint8_t>((std::uint8_t)value, normalized != 0);
+	case 5122: return fastgltf::internal::convertComponent<float, std::int16_t>((std::int16_t)value, normalized != 0);
+	case 5123: return fastgltf::internal::convertComponent<float, std::uint16_t>((std::uint16_t)value, normalized != 0);
+	default: return 0.0f;
+	}
 }
 
 } // extern "C"

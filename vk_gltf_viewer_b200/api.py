@@ -49,7 +49,7 @@ EXPORTS = [
     "vkv_event_record", "vkv_event_elapsed", "vkv_flush_l2", "vkv_visbuffer64_ptr",
     "vkv_resolve", "vkv_read_color", "vkv_build_draws", "vkv_download",
     "vkv_selftest_division",
-    "vkv_build_meshlets",
+    "vkv_build_meshlets", "vkv_assemble_vertices", "vkv_widen_indices",
     "vkv_alloc", "vkv_meshopt_plan_create", "vkv_meshopt_run", "vkv_meshopt_results", "vkv_meshopt_plan_destroy",
     "vkv_set_shard", "vkv_set_shard_interleaved", "vkv_ipc_export", "vkv_ipc_attach", "vkv_ipc_detach", "vkv_merge",
 ]
@@ -108,6 +108,8 @@ def _lib():
         L.vkv_selftest_division.argtypes = [vp, u64, u32, C.POINTER(u64), C.POINTER(u64)]
         L.vkv_alloc.argtypes = [vp, C.c_size_t, C.POINTER(u64)]
         L.vkv_build_meshlets.argtypes = [vp, vp, u32, u32, u32, u32, vp]
+        L.vkv_assemble_vertices.argtypes = [vp, u64, u32, i, u32, u32, C.POINTER(u64)]
+        L.vkv_widen_indices.argtypes = [vp, u64, u32, u32, C.POINTER(u64)]
         L.vkv_meshopt_plan_create.argtypes = [vp, vp, u32, C.POINTER(vp)]
         L.vkv_meshopt_run.argtypes = [vp, vp, u64, C.c_size_t, u64, C.c_size_t]
         L.vkv_meshopt_results.argtypes = [vp, vp, vp]
@@ -265,6 +267,17 @@ class Renderer:
         t, m = C.c_uint64(), C.c_uint64()
         self._ck(self.L.vkv_selftest_division(self.h, seed, iters_per_thread, C.byref(t), C.byref(m)))
         return t.value, m.value
+
+    # ---- accessor conversions on the device (assets.cpp:308-320) -------------------------------------------
+    def assemble_vertices(self, positions_dev: int, component_type: int, normalized: bool, byte_stride: int, count: int) -> int:
+        out = C.c_uint64()
+        self._ck(self.L.vkv_assemble_vertices(self.h, positions_dev, component_type, 1 if normalized else 0, byte_stride, count, C.byref(out)))
+        return out.value
+
+    def widen_indices(self, indices_dev: int, component_type: int, count: int) -> int:
+        out = C.c_uint64()
+        self._ck(self.L.vkv_widen_indices(self.h, indices_dev, component_type, count, C.byref(out)))
+        return out.value
 
     # ---- meshlet partition + bounds on the device -------------------------------------------
     def build_meshlets(self, inputs: np.ndarray, vertex_stride=24, max_vertices=64, max_triangles=124) -> np.ndarray:

@@ -963,6 +963,32 @@ void vkv_meshopt_plan_destroy(vkv_ctx* c, vkv_meshopt_plan* pl) {
 	delete pl;
 }
 
+// ---- accessor conversions (kernels in accessors.cu) ---------------------------------------------------------------------
+int vkv_assemble_vertices(vkv_ctx* c, uint64_t positions_dev, uint32_t type, int normalized, uint32_t byte_stride, uint32_t count, uint64_t* vertices_dev) {
+	if (!c || !vertices_dev) return c ? fail(c, VKV_ERR_INVALID, "vkv_assemble_vertices: NULL argument") : VKV_ERR_INVALID;
+	if (type != 5120 && type != 5121 && type != 5122 && type != 5123 && type != 5126) return fail(c, VKV_ERR_INVALID, "vkv_assemble_vertices: componentType %u", type);
+	if (count && !positions_dev) return fail(c, VKV_ERR_INVALID, "vkv_assemble_vertices: NULL source");
+	const uint32_t cs = (type == 5120 || type == 5121) ? 1u : (type == 5126 ? 4u : 2u);
+	if (byte_stride == 0) byte_stride = 3 * cs;
+	if (byte_stride < 3 * cs) return fail(c, VKV_ERR_INVALID, "vkv_assemble_vertices: byteStride %u < element size", byte_stride);
+	int rc = vkv_alloc(c, (size_t)count * 24, vertices_dev);
+	if (rc) return rc;
+	CK(cudaSetDevice(c->device));
+	CK(launch_assemble_vertices((const uint8_t*)(uintptr_t)positions_dev, (int)type, normalized, byte_stride, count, (void*)(uintptr_t)*vertices_dev, c->num_sms, c->stream));
+	return VKV_OK;
+}
+
+int vkv_widen_indices(vkv_ctx* c, uint64_t indices_dev, uint32_t type, uint32_t count, uint64_t* indices32_dev) {
+	if (!c || !indices32_dev) return c ? fail(c, VKV_ERR_INVALID, "vkv_widen_indices: NULL argument") : VKV_ERR_INVALID;
+	if (type != 5121 && type != 5123 && type != 5125) return fail(c, VKV_ERR_INVALID, "vkv_widen_indices: componentType %u", type);
+	if (count && !indices_dev) return fail(c, VKV_ERR_INVALID, "vkv_widen_indices: NULL source");
+	int rc = vkv_alloc(c, (size_t)count * 4, indices32_dev);
+	if (rc) return rc;
+	CK(cudaSetDevice(c->device));
+	CK(launch_widen_indices((const uint8_t*)(uintptr_t)indices_dev, (int)type, count, (uint32_t*)(uintptr_t)*indices32_dev, c->num_sms, c->stream));
+	return VKV_OK;
+}
+
 // ---- meshlet partition + bounds (kernels in meshlets.cu) -------------------------------------------------
 int vkv_build_meshlets(vkv_ctx* c, const vkv_MeshletBuildInput* in, uint32_t n, uint32_t vertex_stride, uint32_t max_vertices, uint32_t max_triangles,
                        vkv_MeshletBuildOutput* out) {

@@ -160,5 +160,9 @@ cudaError_t launch_meshlet_scan(const MeshletBuildJob& j, cudaStream_t stream); 
 cudaError_t launch_meshlet_emit(const MeshletBuildJob& j, uint32_t nMeshlets, vkv_Meshlet* meshlets, uint32_t* meshletVertices, uint8_t* meshletTriangles,
                                 cudaStream_t stream);
 
+// ---- accessor conversions (accessors.cu) ----------------------------------------------------------------------------
+cudaError_t launch_assemble_vertices(const uint8_t* src, int type, int normalized, uint32_t stride, uint32_t count, void* vertices, int num_sms, cudaStream_t stream);
+cudaError_t launch_widen_indices(const uint8_t* src, int type, uint32_t count, uint32_t* out, int num_sms, cudaStream_t stream);
+
 // ---- arithmetic self checks (selftest.cu) -------------------------------------------------------------------------
 cudaError_t launch_division_selftest(uint64_t seed, uint32_t iters, unsigned long long* counters2, unsigned long long negZero2, int num_sms, cudaStream_t stream);
