@@ -39,6 +39,16 @@ for k, (pos, idx) in enumerate([grid(70, lambda u, v: ((u * 2 - 1) * 3, 0.3 * np
     out[f"p{k}_index_stream"] = M.ref_encode("index", idx, idx.size, 4, vtx.shape[0], 1)
     assert np.array_equal(M.ref_decode("vertex", vtx.shape[0], 24, out[f"p{k}_vertex_stream"])[1], raw)
     assert np.array_equal(M.ref_decode("index", idx.size, 4, out[f"p{k}_index_stream"])[1].view(np.uint32), idx)
+# the same two meshes the way gltfpack writes them: POSITION as normalized SHORT VEC3 padded to 8 bytes (KHR_mesh_quantization,
+# dequantised by a node scale), indices as a 16-bit triangle list; each a compressed view of its own
+for k, (pos, idx) in enumerate([grid(70, lambda u, v: ((u * 2 - 1), 0.1 * np.sin(6 * u) * np.cos(5 * v), (v * 2 - 1))), sphere(48)]):
+    q = np.zeros((pos.shape[0], 4), np.int16)
+    q[:, :3] = np.round(np.clip(pos, -1, 1) * 32767).astype(np.int16)
+    out[f"q{k}_counts"] = np.array([pos.shape[0], idx.size], np.uint32)
+    out[f"q{k}_position_stream"] = M.ref_encode("vertex", q, q.shape[0], 8)
+    out[f"q{k}_index_stream"] = M.ref_encode("index", idx, idx.size, 2, pos.shape[0], 1)
+    assert np.array_equal(M.ref_decode("vertex", q.shape[0], 8, out[f"q{k}_position_stream"])[1], q.view(np.uint8).reshape(-1))
+    assert np.array_equal(M.ref_decode("index", idx.size, 2, out[f"q{k}_index_stream"])[1].view(np.uint16), idx.astype(np.uint16))
 path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "pipeline_asset.npz")
 np.savez_compressed(path, **out)
 print(path, os.path.getsize(path), "bytes;", {k: v.shape for k, v in out.items()})
