@@ -153,7 +153,8 @@ int ensure_draws(vkv_ctx* c, uint32_t n) {
 
 // mesh.glsl:43-44,71 once per mesh-node: needs the transform count, which the push constants do not carry — it is the
 // extent of the vkv_upload allocation the transform buffer lives in.
-int prepare_transforms(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, int* launches) {
+// `fused` != NULL: only size the buffers and hand the job to the pass-A cull launch (cull.cu) through its parameters
+int prepare_transforms(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, int* launches, CullParams* fused = nullptr) {
 	c->xf_count = 0;
 	if (!pc->meshletDrawCount) return VKV_OK;
 	size_t bytes = 0;
@@ -179,8 +180,11 @@ int prepare_transforms(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, int* la
 		CK(cudaMalloc(&c->xf_det, (size_t)cap * 4));
 		c->xf_cap = cap;
 	}
-	CK(launch_prepare_transforms((const float*)pc->transformBuffer, (const vkv_Camera*)pc->cameraBuffer, n, c->xf_mvp, c->xf_det, c->num_sms, c->stream));
-	if (launches) ++*launches;
+	if (fused) { fused->xf_mvp = c->xf_mvp; fused->xf_det = c->xf_det; fused->xf_n = n; }
+	else {
+		CK(launch_prepare_transforms((const float*)pc->transformBuffer, (const vkv_Camera*)pc->cameraBuffer, n, c->xf_mvp, c->xf_det, c->num_sms, c->stream));
+		if (launches) ++*launches;
+	}
 	c->xf_count = n;
 	return VKV_OK;
 }
@@ -490,6 +494,7 @@ int vkv_frame(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, uint32_t flags, 
 	// application.cpp:782,807 — the clear rides inside the pass-A cull launch (cull.cu) whenever there is one and the pixel
 	// count is even (16-byte stores); clear_ms then reads ~0 and cull_a_ms covers both
 	const size_t npix = (size_t)c->W * c->H;
+	bool xf_done = false;
 	CullParams pa = make_cull(c, pc, 0, (flags & VKV_FRAME_NO_CULL) ? 0 : flags);
 	const bool fuse_clear = !(flags & VKV_FRAME_NO_CULL) && pa.n > 0 && (npix & 1) == 0 && !c->separate_clear;
 	if (!fuse_clear) { CK(launch_fill64(c->vis, npix, VKV_VIS64_CLEAR, c->num_sms, s)); ++launches; }
@@ -503,11 +508,13 @@ int vkv_frame(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, uint32_t flags, 
 		if (fuse_clear) { p.clear_ptr = (ulonglong2*)c->vis; p.clear_n2 = npix / 2; p.clear_value = VKV_VIS64_CLEAR; }
 		if (p.status) CK(cudaMemsetAsync(p.status, VKV_ST_NOT_TESTED, N, s));
 		c->status_valid[0] = p.status != nullptr;
-		if (p.n) { CK(launch_cull(p, c->num_sms, s)); ++launches; }
+		if (p.n) {
+			if (!c->separate_clear) { rc = prepare_transforms(c, pc, &launches, &p); if (rc) return rc; xf_done = true; } // rides along, like the clear
+			CK(launch_cull(p, c->num_sms, s)); ++launches;
+		}
 	}
 	mark(E_CULL_A);
-	rc = prepare_transforms(c, pc, &launches);
-	if (rc) return rc;
+	if (!xf_done) { rc = prepare_transforms(c, pc, &launches); if (rc) return rc; }
 	rc = enqueue_raster(c, make_raster(c, pc, c->list_visible[0], &c->counters->visible[0], &c->counters->work[0]), &launches);
 	if (rc) return rc;
 	mark(E_RASTER_A);

@@ -27,6 +27,9 @@ struct CullParams {
 	ulonglong2* clear_ptr;       // fused visbuffer clear (vkv_frame pass A): the launch's blocks also store clear_value over
 	size_t clear_n2;             // clear_n2 16-byte words — HBM write traffic issued under the compute-bound cull
 	unsigned long long clear_value;
+	float* xf_mvp;               // fused per-transform prologue (vkv_frame pass A): mvp / determinant sign of xf_n transforms for the raster
+	uint32_t* xf_det;
+	uint32_t xf_n;
 	int skip_frustum;            // pass B inside vkv_frame: every input draw already passed this frame's frustum test in pass A
 };
 

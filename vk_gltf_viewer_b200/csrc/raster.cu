@@ -288,20 +288,8 @@ __global__ void prepare_transforms_kernel(const float* __restrict__ transforms, 
 	__shared__ float sVP[16];
 	if (threadIdx.x < 16) sVP[threadIdx.x] = __ldg(camera->viewProjection + threadIdx.x);
 	__syncthreads();
-	for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
-		float tm[16];
-#pragma unroll
-		for (int c = 0; c < 4; ++c) {
-			const float4 col = __ldg((const float4*)(transforms + (size_t)t * 16 + c * 4));
-			tm[c * 4] = col.x; tm[c * 4 + 1] = col.y; tm[c * 4 + 2] = col.z; tm[c * 4 + 3] = col.w;
-		}
-#pragma unroll
-		for (int c = 0; c < 4; ++c) {
-			const float4 r = mul44(sVP, tm[c * 4], tm[c * 4 + 1], tm[c * 4 + 2], tm[c * 4 + 3]);
-			*(float4*)(mvpOut + (size_t)t * 16 + c * 4) = r;
-		}
-		detNeg[t] = det4(tm) < 0.0f ? 1u : 0u;
-	}
+	for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x)
+		transform_prologue(transforms + (size_t)t * 16, sVP, mvpOut + (size_t)t * 16, detNeg + t);
 }
 
 __global__ void __launch_bounds__(kThreads, kMinBlocks) raster_kernel(const RasterParams p) {
