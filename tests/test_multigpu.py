@@ -138,3 +138,35 @@ def test_range_sharded_frames_match_single_list_oracle(mode):
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "mgpu ok" in out.stdout
+
+
+@pytest.mark.gpu
+def test_two_contexts_on_two_devices_in_one_process():
+    """independent views need no more than one context per GPU; a single process may hold several (vkv_create's
+    cuda_device argument).  Per-device state (function attributes, occupancy) must not leak between them: both render the same
+    two-pass frames bit-exactly, interleaved."""
+    if _ngpus() < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    from tests import oracle_lib as O
+    from tests import scenes as S
+    from vk_gltf_viewer_b200 import api
+    from vk_gltf_viewer_b200.scene import Camera
+    W, H = 640, 480
+    scene = S.occluder_and_hidden()
+    cam = Camera(W, H).look_at((0, 0, 8), (0, 0, 0))
+    rs = [api.Renderer(W, H, device=d) for d in (0, 1)]
+    pcs = [r.upload_scene(scene, cam) for r in rs]
+    pc_host = scene.host_push_constants(cam)
+    tg = O.Targets(W, H)
+    for eye in ((0, 0, 8), (0.3, 0.1, 8), (0.6, 0.0, 7.5)):
+        cam.look_at(eye, (0, 0, 0))
+        out = O.frame(pc_host, tg, two_pass=True)
+        for r, pc in zip(rs, pcs):
+            r.update_camera(pc, cam)
+            r.frame(pc, api.FRAME_TWO_PASS)
+        for r in rs:
+            assert np.array_equal(np.sort(r.read_visible(0)), out["visibleA"])
+            assert np.array_equal(r.read_visbuffer64(), tg.vis64())
+            assert np.array_equal(r.read_pyramid().view(np.uint32), tg.pyramid.view(np.uint32))
+    for r in rs:
+        r.close()

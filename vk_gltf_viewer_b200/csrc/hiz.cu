@@ -291,7 +291,11 @@ __global__ void __launch_bounds__(kHizWarps * 32) hiz_tiled_kernel(const HizPara
 } // namespace
 
 cudaError_t launch_hiz(const HizParams& p, int num_sms, cudaStream_t stream, int* launches) {
-	static bool attr = false;
+	// function attributes are per device: a process may hold contexts on several GPUs (vkv_create(device = k))
+	static bool attrSet[64] = {};
+	int dev = 0;
+	cudaGetDevice(&dev);
+	bool& attr = attrSet[dev & 63];
 	if (!attr) {
 		cudaFuncSetAttribute(hiz_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTailSmemBytes);
 		cudaFuncSetAttribute(hiz_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTailSmemBytes);

@@ -561,7 +561,10 @@ cudaError_t launch_prepare_transforms(const float* transforms, const vkv_Camera*
 }
 
 cudaError_t launch_raster(const RasterParams& p, int num_sms, cudaStream_t stream) {
-	static int perSm = 0;
+	static int perSmOf[64] = {}; // per device (a process may hold contexts on several GPUs)
+	int dev = 0;
+	cudaGetDevice(&dev);
+	int& perSm = perSmOf[dev & 63];
 	if (perSm == 0) {
 		int n = 0;
 		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, raster_kernel, kThreads, 0);
