@@ -167,6 +167,15 @@ def test_atrium_cfg2_full():
     run_views(s, 1920, 1080, orbit(s, 2, 1920, 1080), two_pass=True)
 
 
+def test_city_cfg4_full_size():
+    """BASELINE config 4 at full size: 50x40 unique buildings, 20.0 M triangles, 275 k MeshletDraws, 1920x1080, three views of
+    the 64-view sweep, two-pass — bit-exact against the oracle"""
+    s = Scene.city(50, 40, 10000, 0x5EED0004)
+    assert s.counts().triangles_instanced > 19_000_000
+    summ = run_views(s, 1920, 1080, [s.default_view(i, 64) for i in (0, 1, 2)], two_pass=True)
+    assert summ[2][0] > 10_000 and summ[2][1] > 10_000
+
+
 def test_lattice_cfg3_full_size():
     """BASELINE config 3 at full size — 10x10x10 instances of a 100,352-triangle patch (1.49 M MeshletDraws, 100.35 M triangles),
     3840x2160, two-pass: bit-exact against the oracle (the multithreaded CPU port needs about half a second per frame), plus the
