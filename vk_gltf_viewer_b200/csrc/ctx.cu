@@ -231,6 +231,7 @@ RasterParams make_raster(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, const
 	r.camera = (const vkv_Camera*)pc->cameraBuffer;
 	r.list = list; r.count = count; r.work = work;
 	r.vis = c->vis; r.W = c->W; r.H = c->H;
+	r.neg_zero2 = kNegZero2;
 	r.mvp = c->xf_mvp; r.detNeg = c->xf_det;
 	r.big = c->big_tris; r.bigCap = c->big_cap; r.bigCursor = &c->counters->big_cursor; r.bigNext = &c->counters->big_next;
 	return r;

@@ -67,6 +67,7 @@ struct RasterParams {
 	uint32_t bigCap;
 	unsigned long long* bigCursor;
 	uint32_t* bigNext;
+	unsigned long long neg_zero2; // the fp32 pair (-0.0, -0.0), see common.cuh mul2 (must arrive at run time)
 };
 
 struct HizParams {

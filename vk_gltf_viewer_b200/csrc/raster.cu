@@ -59,10 +59,12 @@ struct WarpScratch {
 	float4 cxyw[VKV_MAX_VERTICES];   // clip x, y, w and the outcode bits (what phase 1 reads: one LDS.128 per vertex)
 	int4 scr[VKV_MAX_VERTICES];      // snapped x, y (24.8), z_ndc bits, unused
 	float cz[VKV_MAX_VERTICES];      // clip z (clipper only)
-	float pos[VKV_MAX_VERTICES * 3]; // cp.async landing zone: object-space positions of the next meshlet
+	float pos[VKV_MAX_VERTICES * 3]; // cp.async landing zone: object-space positions of the next meshlet, component k of vertices (lane, lane + 32)
+	                                 // adjacent at [(k * 32 + lane) * 2 + half]: one 8-byte load gives the f32x2 pair the vertex phase works on
 	uint32_t tri_words[2][96];       // cp.async landing zone (double buffered): up to 124*3 = 372 index bytes
 	uint32_t surv[128];              // phase-1 survivors: ia | ib << 8 | ic << 16 | triangle << 24 | needsClip << 31
-	float mvp[16];                   // cp.async landing zone
+	float mvp[16];                   // (unused padding of the old layout)
+	float2 mvp2[4][4];               // cp.async landing zone: mvp[row][column], every element twice (f32x2 operand for two vertices)
 	Tri sub[8];
 	MeshletHdr hdr[kBatch];
 	int nsub;
@@ -342,11 +344,11 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) raster_kernel(const Rast
 			const uint32_t vc = h.counts & 0xffu, tc = (h.counts >> 8) & 0xffu;
 			if (lane < vc) {
 				const float* q = h.verts[vi0].position;
-				cp_async4(&ws.pos[lane * 3], q); cp_async4(&ws.pos[lane * 3 + 1], q + 1); cp_async4(&ws.pos[lane * 3 + 2], q + 2);
+				cp_async4(&ws.pos[lane * 2], q); cp_async4(&ws.pos[(32 + lane) * 2], q + 1); cp_async4(&ws.pos[(64 + lane) * 2], q + 2);
 			}
 			if (lane + 32 < vc) {
 				const float* q = h.verts[vi1].position;
-				cp_async4(&ws.pos[lane * 3 + 96], q); cp_async4(&ws.pos[lane * 3 + 97], q + 1); cp_async4(&ws.pos[lane * 3 + 98], q + 2);
+				cp_async4(&ws.pos[lane * 2 + 1], q); cp_async4(&ws.pos[(32 + lane) * 2 + 1], q + 1); cp_async4(&ws.pos[(64 + lane) * 2 + 1], q + 2);
 			}
 			const uint32_t nWords = (tc * 3 + 3) >> 2;
 			if ((((uintptr_t)h.tri) & 3) == 0) {
@@ -363,7 +365,10 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) raster_kernel(const Rast
 					ws.tri_words[buf][wi] = r;
 				}
 			}
-			if (lane < 16) cp_async4(&ws.mvp[lane], p.mvp + (size_t)h.tIdx * 16 + lane);
+			{ // mvp element e = lane >> 1 (column e >> 2, row e & 3), copied twice: lanes 2e and 2e + 1
+				const uint32_t e = lane >> 1;
+				cp_async4(&ws.mvp2[e & 3][e >> 2].x + (lane & 1), p.mvp + (size_t)h.tIdx * 16 + e);
+			}
 			cp_async_commit();
 		};
 		load_indices(ws.hdr[0]);
@@ -379,19 +384,29 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) raster_kernel(const Rast
 			cp_async_wait_all();
 			__syncwarp();
 
-			// :50-69 vertices
+			// :50-69 vertices.  A lane owns vertices `lane` and `lane + 32`; their transform, perspective divide and viewport
+			// mapping run as the two halves of packed f32x2 instructions (every half an individually rounded IEEE operation: the
+			// same values as the scalar form, half the issue slots — see common.cuh / cull.cu for the exactness argument).
 			{
-				float mvp[16];
+				const f2 nz = p.neg_zero2;
+				const f2 P0 = *(const f2*)&ws.pos[lane * 2], P1 = *(const f2*)&ws.pos[(32 + lane) * 2], P2 = *(const f2*)&ws.pos[(64 + lane) * 2];
+				f2 C[4]; // clip x, y, z, w of both vertices: ((c0*x + c1*y) + c2*z) + c3   (:61, w = 1)
 #pragma unroll
-				for (int c = 0; c < 4; ++c) {
-					const float4 col = *(const float4*)&ws.mvp[c * 4];
-					mvp[c * 4] = col.x; mvp[c * 4 + 1] = col.y; mvp[c * 4 + 2] = col.z; mvp[c * 4 + 3] = col.w;
+				for (int r = 0; r < 4; ++r) {
+					const ulonglong2 m01 = *(const ulonglong2*)&ws.mvp2[r][0], m23 = *(const ulonglong2*)&ws.mvp2[r][2];
+					C[r] = add2(add2(add2(mul2(m01.x, P0, nz), mul2(m01.y, P1, nz)), mul2(m23.x, P2, nz)), m23.y);
 				}
+				// perspective divide + viewport for both at once where both are in the shared-reciprocal range (common.cuh)
+				const f2 NW = mul2(C[3], pk(-1.0f, -1.0f), nz);
+				const f2 R = refined_rcp2(NW, pk(1.0f, 1.0f));
+				const f2 NX = div_by2(C[0], NW, R, nz), NY = div_by2(C[1], NW, R, nz), NZ = div_by2(C[2], NW, R, nz);
+				const f2 HW = pk(hw, hw), HH = pk(hh, hh), SUBP = pk((float)VKV_SUB, (float)VKV_SUB);
+				const f2 FX = mul2(add2(mul2(NX, HW, nz), HW), SUBP, nz), FY = mul2(add2(mul2(NY, HH, nz), HH), SUBP, nz);
 #pragma unroll
 				for (int half = 0; half < 2; ++half) {
 					const uint32_t v = lane + half * 32;
 					if (v < vc) {
-						const float4 c = mul44(mvp, ws.pos[v * 3], ws.pos[v * 3 + 1], ws.pos[v * 3 + 2], 1.0f); // :61
+						const float4 c = half ? make_float4(hi_of(C[0]), hi_of(C[1]), hi_of(C[2]), hi_of(C[3])) : make_float4(lo_of(C[0]), lo_of(C[1]), lo_of(C[2]), lo_of(C[3]));
 						uint32_t f = 0;
 						if (c.x < -c.w) f |= 1;
 						if (c.x > c.w) f |= 2;
@@ -404,8 +419,15 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) raster_kernel(const Rast
 						if (!(c.x == c.x && c.y == c.y && c.z == c.z && c.w == c.w)) f |= F_NAN; // NaN -> reject
 						int fx = 0, fy = 0;
 						float z = 0.f;
-						if (!(f & (F_NEEDS_CLIP | F_NAN)) && c.w > 0.f) project(c, hw, hh, fx, fy, z);
-						else if (!(f & F_NAN) && !(c.w > 0.f)) f |= F_NEEDS_CLIP; // degenerate w: let the clipper decide
+						if (!(f & (F_NEEDS_CLIP | F_NAN)) && c.w > 0.f) {
+							const float amx = max_nan(max_nan(fabsf(c.x), fabsf(c.y)), max_nan(fabsf(c.z), fabsf(c.w)));
+							const float amn = fminf(fminf(fabsf(c.x), fabsf(c.y)), fminf(fabsf(c.z), fabsf(c.w)));
+							if (amn >= kDivLo && amx <= kDivHi) { // the packed results are the IEEE quotients (vkv_selftest_division)
+								fx = __float2int_rn(half ? hi_of(FX) : lo_of(FX));
+								fy = __float2int_rn(half ? hi_of(FY) : lo_of(FY));
+								z = half ? hi_of(NZ) : lo_of(NZ);
+							} else project(c, hw, hh, fx, fy, z);
+						} else if (!(f & F_NAN) && !(c.w > 0.f)) f |= F_NEEDS_CLIP; // degenerate w: let the clipper decide
 						ws.cxyw[v] = make_float4(c.x, c.y, c.w, __uint_as_float(f));
 						ws.scr[v] = make_int4(fx, fy, __float_as_int(z), 0);
 						ws.cz[v] = c.z;
