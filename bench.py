@@ -235,15 +235,23 @@ def main():
     for k in range(steps):
         pc.cameraBuffer = cam_addrs[(warm + k) % len(cam_addrs)]
         r.flush_l2(256 << 20)
-        st = r.frame(pc, flags | api.FRAME_TIMED)
+        st = r.frame(pc, flags | api.FRAME_TIMED)   # one event pair around the frame: nothing sits between its launches
         per.append(st.total_ms)
-        for sname in stage:
-            stage[sname] += getattr(st, sname)
         vis_a += st.visible_a; vis_b += st.visible_b; occ_a += st.occluded_a
         launches += st.kernel_launches + 1  # + the L2-flush fill kernel
     barrier()
     t_end = time.time()
     dev_ms = sum(per)
+    # ---- per-stage breakdown: a second, shorter pass over the same sweep with an event after every stage (VKV_FRAME_STAGES);
+    # those events keep the pass-B cull from starting under the pyramid's tail, so the stages add up to slightly more than a frame
+    KS = min(steps, 50)
+    for k in range(KS):
+        pc.cameraBuffer = cam_addrs[(warm + k) % len(cam_addrs)]
+        r.flush_l2(256 << 20)
+        st = r.frame(pc, flags | api.FRAME_TIMED | api.FRAME_STAGES)
+        for sname in stage:
+            stage[sname] += getattr(st, sname)
+    barrier()
 
     # ---- end to end through the C ABI with HOST buffers: per step H2D camera + transforms (the reference re-uploads
     # both every frame: camera.cpp:180-193, world.cpp:321-344) and D2H of the frame's counters (vkv_stats)
@@ -308,7 +316,7 @@ def main():
                             ("hiz_a", bytes_hiz, stage["hiz_a_ms"]), ("cull_b", bytes_cull_b, stage["cull_b_ms"]),
                             ("raster_b", avg(vis_b) * per_meshlet, stage["raster_b_ms"]), ("merge_b", bytes_merge, stage["merge_b_ms"]),
                             ("hiz_b", bytes_hiz, stage["hiz_b_ms"])):
-            m = ms / K
+            m = ms / KS
             if (m <= 0 and b == 0) or (name == "clear" and clear_fused):
                 continue
             gbs = (b / 1e9) / (m / 1e3) if m > 0 else 0.0
@@ -337,6 +345,7 @@ def main():
                        "parallelism": (f"views sharded over {world} GPU(s), scene replicated, no collective" if shard == "views" else
                                        f"one view, MeshletDraw list sharded over {world} GPU(s) in interleaved 2048-draw ranges, u64 min-merge over NVLink peer memory before each HiZ build"),
                        "l2": "256 MB scratch written between timed frames (L2 flush); each frame timed by its own CUDA event pair",
+                       "stages_from": f"a second pass of {KS} frames with an event after every stage (the frame time above has none inside the frame)",
                        "visible_a_avg": vis_a / K, "occluded_a_avg": occ_a / K, "visible_b_avg": vis_b / K,
                        "clear": "fused into the pass-A cull launch (its 8*W*H bytes are counted there)" if clear_fused else "separate launch"},
             "e2e": {"value": frames_total / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -49,9 +49,11 @@ enum {
 	VKV_FRAME_TWO_PASS = 1 << 0,   /* extension: + re-test pass-A occlusion rejects against the fresh pyramid */
 	VKV_FRAME_NO_HIZ = 1 << 1,     /* camera->freezeCullingMatrix: skip the pyramid rebuild (application.cpp:951) */
 	VKV_FRAME_STATUS = 1 << 2,     /* also write the per-draw status bytes (parity / debugging) */
-	VKV_FRAME_TIMED = 1 << 3,      /* fill the *_ms fields of vkv_stats (CUDA events; syncs the stream at frame end) */
+	VKV_FRAME_TIMED = 1 << 3,      /* fill total_ms of vkv_stats (CUDA events around the frame; syncs the stream at frame end) */
 	VKV_FRAME_NO_CULL = 1 << 4,    /* rasterise every MeshletDraw (debug; what the task shader does with culling disabled) */
-	VKV_FRAME_MERGE = 1 << 5       /* multi-GPU: min-merge the visbuffer with the attached peers before each pyramid build */
+	VKV_FRAME_MERGE = 1 << 5,      /* multi-GPU: min-merge the visbuffer with the attached peers before each pyramid build */
+	VKV_FRAME_STAGES = 1 << 6      /* with VKV_FRAME_TIMED: also the per-stage *_ms fields (an event between two launches; it keeps the
+	                                  pass-B cull from overlapping the pyramid's tail, so total_ms is a few us higher than without) */
 };
 
 /* per-draw status byte (VKV_FRAME_STATUS) — same values as the oracle's */

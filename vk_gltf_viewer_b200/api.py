@@ -16,6 +16,7 @@ FRAME_TWO_PASS = 1 << 0
 FRAME_NO_HIZ = 1 << 1
 FRAME_STATUS = 1 << 2
 FRAME_TIMED = 1 << 3
+FRAME_STAGES = 1 << 6
 FRAME_NO_CULL = 1 << 4
 FRAME_MERGE = 1 << 5
 

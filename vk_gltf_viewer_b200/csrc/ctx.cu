@@ -43,6 +43,7 @@ struct vkv_ctx {
 	uint32_t shard_first = 0, shard_count = 0;       // contiguous shard
 	uint32_t shard_block_log2 = 0, shard_rank = 0, shard_nranks = 1; // interleaved shard (blocks of 2^k draws, round-robin)
 	bool sharded = false;
+	bool no_pdl = false;         // VKV_NO_PDL=1: launch the pass-B cull without programmatic stream serialization (A/B measurements)
 	bool separate_clear = false; // VKV_SEPARATE_CLEAR=1: keep the visbuffer clear a launch of its own (A/B measurements)
 	MergeParams mp{};
 	bool attached = false;
@@ -307,6 +308,7 @@ int vkv_create(vkv_ctx** out, int cuda_device, uint32_t width, uint32_t height) 
 	cudaDeviceProp prop;
 	if (cudaGetDeviceProperties(&prop, cuda_device) == cudaSuccess) c->num_sms = prop.multiProcessorCount;
 	if (const char* e = getenv("VKV_SEPARATE_CLEAR")) c->separate_clear = e[0] == '1';
+	if (const char* e = getenv("VKV_NO_PDL")) c->no_pdl = e[0] == '1';
 	if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { c->err = "cudaStreamCreate failed"; return bail(VKV_ERR_CUDA); }
 	c->stream = c->own_stream;
 	for (auto& ev : c->events) cudaEventCreate(&ev);
@@ -489,7 +491,8 @@ int vkv_frame(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, uint32_t flags, 
 	if (merge && !c->attached) return fail(c, VKV_ERR_INVALID, "VKV_FRAME_MERGE needs vkv_ipc_attach first");
 	int launches = 0;
 	enum { E_BEGIN, E_CLEAR, E_CULL_A, E_RASTER_A, E_MERGE_A, E_HIZ_A, E_CULL_B, E_RASTER_B, E_MERGE_B, E_HIZ_B, E_COUNT };
-	auto mark = [&](int e) { if (timed) cudaEventRecord(c->stage_ev[e], s); };
+	const bool stages = timed && (flags & VKV_FRAME_STAGES);
+	auto mark = [&](int e) { if (stages || (timed && e == E_BEGIN)) cudaEventRecord(c->stage_ev[e], s); };
 	CK(cudaMemsetAsync(c->counters, 0, sizeof(FrameCounters), s));
 	mark(E_BEGIN);
 	// application.cpp:782,807 — the clear rides inside the pass-A cull launch (cull.cu) whenever there is one and the pixel
@@ -528,7 +531,9 @@ int vkv_frame(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, uint32_t flags, 
 		p.skip_frustum = 1; // same camera buffer, same frustum planes as pass A a few launches ago: its survivors pass again
 		if (p.status) CK(cudaMemsetAsync(p.status, VKV_ST_NOT_TESTED, N, s));
 		c->status_valid[1] = p.status != nullptr;
-		if (p.n) { CK(launch_cull(p, c->num_sms, s)); ++launches; }
+		// nothing between the pyramid launch and this one (no stage event, no status memset, no merge): let it start under the tail
+		const bool pdl = hiz && !stages && !p.status && c->exact_levels >= 1 && !c->no_pdl;
+		if (p.n) { CK(launch_cull(p, c->num_sms, s, pdl)); ++launches; }
 		mark(E_CULL_B);
 		rc = enqueue_raster(c, make_raster(c, pc, c->list_visible[1], &c->counters->visible[1], &c->counters->work[1]), &launches);
 		if (rc) return rc;
@@ -538,6 +543,7 @@ int vkv_frame(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, uint32_t flags, 
 		if (hiz) CK(launch_hiz(make_hiz(c), c->num_sms, s, &launches));
 		mark(E_HIZ_B);
 	}
+	if (timed) cudaEventRecord(c->stage_ev[E_COUNT], s); // end of frame (the per-stage events exist only with VKV_FRAME_STAGES)
 	if (out) {
 		memset(out, 0, sizeof(*out));
 		CK(cudaMemcpyAsync(c->h_counters, c->counters, sizeof(FrameCounters), cudaMemcpyDeviceToHost, s));
@@ -553,13 +559,16 @@ int vkv_frame(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, uint32_t flags, 
 		out->kernel_launches = (uint32_t)launches;
 		if (timed) {
 			auto el = [&](int a, int b) { float ms = 0; cudaEventElapsedTime(&ms, c->stage_ev[a], c->stage_ev[b]); return ms; };
+			out->total_ms = el(E_BEGIN, E_COUNT);
+		}
+		if (stages) {
+			auto el = [&](int a, int b) { float ms = 0; cudaEventElapsedTime(&ms, c->stage_ev[a], c->stage_ev[b]); return ms; };
 			out->clear_ms = el(E_BEGIN, E_CLEAR); out->cull_a_ms = el(E_CLEAR, E_CULL_A); out->raster_a_ms = el(E_CULL_A, E_RASTER_A);
 			out->merge_a_ms = el(E_RASTER_A, E_MERGE_A); out->hiz_a_ms = el(E_MERGE_A, E_HIZ_A);
 			if (two) {
 				out->cull_b_ms = el(E_HIZ_A, E_CULL_B); out->raster_b_ms = el(E_CULL_B, E_RASTER_B);
 				out->merge_b_ms = el(E_RASTER_B, E_MERGE_B); out->hiz_b_ms = el(E_MERGE_B, E_HIZ_B);
-				out->total_ms = el(E_BEGIN, E_HIZ_B);
-			} else out->total_ms = el(E_BEGIN, E_HIZ_A);
+			}
 		}
 	}
 	return VKV_OK;

@@ -272,6 +272,10 @@ __global__ void __launch_bounds__(kHizWarps * 32) hiz_tiled_kernel(const HizPara
 			}
 		}
 	}
+	// Programmatic dependent launch: this block's tiles are written; once every block has said so (or exited) the next kernel in the
+	// stream may START if it was launched with programmatic stream serialization (vkv_frame: the pass-B cull, which does not touch
+	// the pyramid before its griddepcontrol.wait) — the serial small-mip tail below then overlaps that kernel's front half.
+	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 	// the block that finishes last produces the small mips (no second launch): classic last-block-done hand-off
 	if (p.exact_levels >= p.pyr.levels || !p.done) return;
 	// bar.sync orders every thread's mip stores before thread 0's gpu-scope fence (fences are cumulative), so ONE fence per

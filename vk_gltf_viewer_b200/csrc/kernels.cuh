@@ -80,7 +80,7 @@ struct HizParams {
 	int split_tail;              // diagnosis only: run the small mips as a second launch
 };
 
-cudaError_t launch_cull(const CullParams& p, int num_sms, cudaStream_t stream);
+cudaError_t launch_cull(const CullParams& p, int num_sms, cudaStream_t stream, bool after_hiz = false); // after_hiz: programmatic dependent launch
 cudaError_t launch_iota(const CullParams& p, uint32_t* out, uint32_t* count, int num_sms, cudaStream_t stream);
 cudaError_t launch_prepare_transforms(const float* transforms, const vkv_Camera* camera, uint32_t n, float* mvp, uint32_t* detNeg,
                                       int num_sms, cudaStream_t stream);
