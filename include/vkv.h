@@ -62,9 +62,9 @@ enum { VKV_ST_FRUSTUM_CULLED = 0, VKV_ST_OCCLUDED = 1, VKV_ST_VISIBLE = 2, VKV_S
 typedef struct vkv_stats {
 	uint32_t draws;              /* meshletDrawCount */
 	uint32_t visible_a, occluded_a, visible_b, tested_b;
-	float clear_ms, cull_a_ms, raster_a_ms, hiz_a_ms, cull_b_ms, raster_b_ms, hiz_b_ms, total_ms; /* VKV_FRAME_TIMED */
+	float clear_ms, cull_a_ms, raster_a_ms, hiz_a_ms, cull_b_ms, raster_b_ms, hiz_b_ms, total_ms; /* total_ms: VKV_FRAME_TIMED; the rest: + VKV_FRAME_STAGES */
 	uint32_t kernel_launches;    /* kernels of this library launched by the call */
-	float merge_a_ms, merge_b_ms; /* VKV_FRAME_TIMED + VKV_FRAME_MERGE */
+	float merge_a_ms, merge_b_ms; /* VKV_FRAME_TIMED + VKV_FRAME_STAGES + VKV_FRAME_MERGE */
 } vkv_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------------------------- */
