@@ -19,8 +19,17 @@ HOST_HDRS := $(wildcard $(HOSTSRC)/*.hpp) $(wildcard include/*.h)
 
 all: $(PKG)/libvkv.so $(PKG)/libvkv_host.so oracle/liboracle.so
 
-$(PKG)/libvkv.so: $(CU_SRCS) $(CU_HDRS)
-	$(NVCC) $(NVCCFLAGS) -shared -o $@ $(CU_SRCS) -Iinclude 2> $(PKG)/ptxas.log || (cat $(PKG)/ptxas.log; exit 1)
+# one object per .cu (so `make -j` compiles them side by side and a change to one kernel rebuilds one file); objects and the
+# per-file ptxas logs live in build/ (git-ignored)
+CU_OBJS   := $(patsubst $(CSRC)/%.cu,build/%.o,$(CU_SRCS))
+
+build/%.o: $(CSRC)/%.cu $(CU_HDRS)
+	@mkdir -p build
+	$(NVCC) $(NVCCFLAGS) $(EXTRA_NVCCFLAGS) -c -o $@ $< -Iinclude 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; exit 1)
+
+$(PKG)/libvkv.so: $(CU_OBJS)
+	$(NVCC) -gencode arch=compute_100a,code=sm_100a -shared -o $@ $(CU_OBJS) -ldl
+	@cat build/*.ptxas.log > $(PKG)/ptxas.log
 	@grep -E "registers|spill" $(PKG)/ptxas.log | sort | uniq -c | sort -rn | head -5 || true
 
 $(PKG)/libvkv_host.so: $(HOST_SRCS) $(HOST_HDRS)
@@ -33,6 +42,6 @@ ref:
 	@if [ -d /root/reference ]; then sh oracle/build_ref.sh; else echo "no /root/reference here: using prebuilt oracle/_ref if present"; fi
 
 clean:
-	rm -f $(PKG)/libvkv.so $(PKG)/libvkv_host.so oracle/liboracle.so $(PKG)/ptxas.log
+	rm -rf $(PKG)/libvkv.so $(PKG)/libvkv_host.so oracle/liboracle.so $(PKG)/ptxas.log build
 
 .PHONY: all ref clean

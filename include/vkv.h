@@ -144,7 +144,11 @@ int vkv_widen_indices(vkv_ctx*, uint64_t indices_dev, uint32_t component_type, u
  * triangles in index order), byte-identical to that function; the reference's meshopt_buildMeshlets + meshopt_optimizeMeshlet
  * order heuristics are not reproduced (no golden output exists for them; any valid partition renders the same image).
  * max_vertices <= 64, max_triangles <= 252 (the reference uses 64 / 124).  All primitives of a call share three allocations:
- * release out[0].meshlets, out[0].vertex_indices and out[0].triangles with vkv_free. ------------------------------------ */
+ * release out[0].meshlets, out[0].vertex_indices and out[0].triangles with vkv_free.
+ * Trust boundary: indices come from untrusted glTF.  vertex_count > 0 makes the call range-check every index on the device
+ * and fail with VKV_ERR_INVALID before any vertex is dereferenced (meshopt_buildMeshlets asserts the same, clusterizer.cpp:45);
+ * vertex_count == 0 skips the check (the caller vouches for the indices).  The per-frame path trusts primitiveIndex /
+ * meshletIndex / transformIndex / materialIndex of the buffers it is handed, exactly as the reference's shaders do. ------ */
 typedef struct vkv_MeshletBuildInput { uint64_t indices, vertices; uint32_t index_count, vertex_count; } vkv_MeshletBuildInput;
 typedef struct vkv_MeshletBuildOutput {
 	uint64_t meshlets, vertex_indices, triangles;                       /* device addresses of this primitive's arrays */

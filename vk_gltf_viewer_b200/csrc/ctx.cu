@@ -10,6 +10,8 @@
 #include <vector>
 #include <algorithm>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "kernels.cuh"
 
 struct vkv_ctx {
@@ -49,6 +51,8 @@ struct vkv_ctx {
 	bool attached = false;
 	uint32_t* sync_flags = nullptr;   // kMaxRanks barrier slots + 1 error word, peer-mapped
 	uint32_t epoch = 0;
+	bool merge_used = false;          // a barrier kernel has been enqueued since the error word was last read
+	bool merge_err_pending = false;
 	// resolve pass: RGBA8 target + per-material colour table (grow-only)
 	uint32_t* color = nullptr;
 	uint32_t* mat_colors = nullptr;
@@ -136,18 +140,29 @@ int ensure_draws(vkv_ctx* c, uint32_t n) {
 	if (n > VKV_MAX_MESHLET_DRAWS) return fail(c, VKV_ERR_LIMIT, "meshletDrawCount %u exceeds 2^25 (visbuffer.h.glsl:15-17)", n);
 	if (n <= c->cap_draws) return VKV_OK;
 	CK(cudaStreamSynchronize(c->stream));
-	uint32_t cap = n + n / 8 + 1024;
+	const uint32_t cap = n + n / 8 + 1024;
+	// allocate the whole new set first and swap it in only when every allocation succeeded: a failure in the middle leaves the
+	// context exactly as it was (old buffers, old capacity)
+	void* fresh[7] = {};
+	const size_t bytes[7] = {(size_t)cap * 4, (size_t)cap * 4, (size_t)cap * 4, (size_t)cap * 4, (size_t)cap, (size_t)cap, (size_t)cap * 4};
+	for (int i = 0; i < 7; ++i) {
+		cudaError_t e = cudaMalloc(&fresh[i], bytes[i]);
+		if (e != cudaSuccess) {
+			for (int k = 0; k < i; ++k) cudaFree(fresh[k]);
+			return fail(c, e == cudaErrorMemoryAllocation ? VKV_ERR_OOM : VKV_ERR_CUDA, "growing the per-draw buffers to %u draws: %s", cap, cudaGetErrorString(e));
+		}
+	}
 	for (int i = 0; i < 2; ++i) {
 		if (c->list_visible[i]) cudaFree(c->list_visible[i]);
 		if (c->list_occluded[i]) cudaFree(c->list_occluded[i]);
 		if (c->status[i]) cudaFree(c->status[i]);
-		CK(cudaMalloc(&c->list_visible[i], (size_t)cap * 4));
-		CK(cudaMalloc(&c->list_occluded[i], (size_t)cap * 4));
-		CK(cudaMalloc(&c->status[i], (size_t)cap));
+		c->list_visible[i] = (uint32_t*)fresh[i];
+		c->list_occluded[i] = (uint32_t*)fresh[2 + i];
+		c->status[i] = (uint8_t*)fresh[4 + i];
 		c->status_valid[i] = false;
 	}
 	if (c->list_tmp) cudaFree(c->list_tmp);
-	CK(cudaMalloc(&c->list_tmp, (size_t)cap * 4));
+	c->list_tmp = (uint32_t*)fresh[6];
 	c->cap_draws = cap;
 	return VKV_OK;
 }
@@ -173,13 +188,14 @@ int prepare_transforms(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, int* la
 	const uint32_t n = (uint32_t)n64;
 	if (n > c->xf_cap) {
 		CK(cudaStreamSynchronize(c->stream));
+		const uint32_t cap = n + n / 8 + 64;
+		float* mvp = nullptr; uint32_t* det = nullptr;
+		CK(cudaMalloc(&mvp, (size_t)cap * 64));
+		cudaError_t e2 = cudaMalloc(&det, (size_t)cap * 4);
+		if (e2 != cudaSuccess) { cudaFree(mvp); return fail(c, VKV_ERR_OOM, "growing the per-transform buffers: %s", cudaGetErrorString(e2)); }
 		if (c->xf_mvp) cudaFree(c->xf_mvp);
 		if (c->xf_det) cudaFree(c->xf_det);
-		c->xf_mvp = nullptr; c->xf_det = nullptr; c->xf_cap = 0;
-		const uint32_t cap = n + n / 8 + 64;
-		CK(cudaMalloc(&c->xf_mvp, (size_t)cap * 64));
-		CK(cudaMalloc(&c->xf_det, (size_t)cap * 4));
-		c->xf_cap = cap;
+		c->xf_mvp = mvp; c->xf_det = det; c->xf_cap = cap;
 	}
 	if (fused) { fused->xf_mvp = c->xf_mvp; fused->xf_det = c->xf_det; fused->xf_n = n; }
 	else {
@@ -282,7 +298,23 @@ int enqueue_merge(vkv_ctx* c, int* launches) {
 	CK(launch_xgpu_barrier(c->mp, ++c->epoch, timeout_ns, c->stream));
 	CK(launch_merge_min(c->mp, c->num_sms, c->stream));
 	CK(launch_xgpu_barrier(c->mp, ++c->epoch, timeout_ns, c->stream));
+	c->merge_used = true;
 	if (launches) *launches += 3;
+	return VKV_OK;
+}
+
+// The merge barriers report a peer that never arrived through an error word on the device.  Every call that synchronises the
+// stream afterwards (frame with stats, vkv_sync, the vkv_read_* family) reads it, fails once with VKV_ERR_CUDA and clears it.
+int check_merge_error(vkv_ctx* c) {
+	if (!c->merge_used || !c->sync_flags) return VKV_OK;
+	uint32_t err = 0;
+	CK(cudaMemcpyAsync(&err, c->sync_flags + kMaxRanks, 4, cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	c->merge_used = false;
+	if (err) {
+		CK(cudaMemsetAsync(c->sync_flags + kMaxRanks, 0, 4, c->stream));
+		return fail(c, VKV_ERR_CUDA, "multi-GPU merge barrier timed out (a peer did not reach the merge); the visbuffer of that frame is unmerged");
+	}
 	return VKV_OK;
 }
 
@@ -373,7 +405,7 @@ int vkv_sync(vkv_ctx* c) {
 	if (!c) return VKV_ERR_INVALID;
 	CK(cudaSetDevice(c->device));
 	CK(cudaStreamSynchronize(c->stream));
-	return VKV_OK;
+	return check_merge_error(c);
 }
 
 int vkv_upload(vkv_ctx* c, const void* host, size_t bytes, uint64_t* dev_addr) {
@@ -490,15 +522,24 @@ int vkv_frame(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, uint32_t flags, 
 	const uint32_t N = pc->meshletDrawCount;
 	if (merge && !c->attached) return fail(c, VKV_ERR_INVALID, "VKV_FRAME_MERGE needs vkv_ipc_attach first");
 	int launches = 0;
+	// NVTX ranges named like the reference's Tracy/debug-label zones (application.cpp:765 "Visbuffer pass", :952 "HiZ reduction") so a
+	// maintainer can line a trace of this library up with a trace of the Vulkan path; free when no tool is attached
+	struct Range { // closes itself on every early return
+		bool open = true;
+		explicit Range(const char* n) { nvtxRangePushA(n); }
+		void end() { if (open) { nvtxRangePop(); open = false; } }
+		~Range() { end(); }
+	};
 	enum { E_BEGIN, E_CLEAR, E_CULL_A, E_RASTER_A, E_MERGE_A, E_HIZ_A, E_CULL_B, E_RASTER_B, E_MERGE_B, E_HIZ_B, E_COUNT };
 	const bool stages = timed && (flags & VKV_FRAME_STAGES);
 	auto mark = [&](int e) { if (stages || (timed && e == E_BEGIN)) cudaEventRecord(c->stage_ev[e], s); };
+	mark(E_BEGIN); // the counter reset below is a mandatory operation of every frame: inside the timed region
 	CK(cudaMemsetAsync(c->counters, 0, sizeof(FrameCounters), s));
-	mark(E_BEGIN);
 	// application.cpp:782,807 — the clear rides inside the pass-A cull launch (cull.cu) whenever there is one and the pixel
 	// count is even (16-byte stores); clear_ms then reads ~0 and cull_a_ms covers both
 	const size_t npix = (size_t)c->W * c->H;
 	bool xf_done = false;
+	Range visA("Visbuffer pass");
 	CullParams pa = make_cull(c, pc, 0, (flags & VKV_FRAME_NO_CULL) ? 0 : flags);
 	const bool fuse_clear = !(flags & VKV_FRAME_NO_CULL) && pa.n > 0 && (npix & 1) == 0 && !c->separate_clear;
 	if (!fuse_clear) { CK(launch_fill64(c->vis, npix, VKV_VIS64_CLEAR, c->num_sms, s)); ++launches; }
@@ -524,9 +565,11 @@ int vkv_frame(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, uint32_t flags, 
 	mark(E_RASTER_A);
 	if (merge) { rc = enqueue_merge(c, &launches); if (rc) return rc; }
 	mark(E_MERGE_A);
-	if (hiz) CK(launch_hiz(make_hiz(c), c->num_sms, s, &launches));
+	visA.end();
+	if (hiz) { Range z("HiZ reduction"); CK(launch_hiz(make_hiz(c), c->num_sms, s, &launches)); }
 	mark(E_HIZ_A);
 	if (two) {
+		Range visB("Visbuffer pass (B)");
 		CullParams p = make_cull(c, pc, 1, flags);
 		p.skip_frustum = 1; // same camera buffer, same frustum planes as pass A a few launches ago: its survivors pass again
 		if (p.status) CK(cudaMemsetAsync(p.status, VKV_ST_NOT_TESTED, N, s));
@@ -540,17 +583,17 @@ int vkv_frame(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, uint32_t flags, 
 		mark(E_RASTER_B);
 		if (merge) { rc = enqueue_merge(c, &launches); if (rc) return rc; }
 		mark(E_MERGE_B);
-		if (hiz) CK(launch_hiz(make_hiz(c), c->num_sms, s, &launches));
+		visB.end();
+		if (hiz) { Range z("HiZ reduction"); CK(launch_hiz(make_hiz(c), c->num_sms, s, &launches)); }
 		mark(E_HIZ_B);
 	}
 	if (timed) cudaEventRecord(c->stage_ev[E_COUNT], s); // end of frame (the per-stage events exist only with VKV_FRAME_STAGES)
 	if (out) {
 		memset(out, 0, sizeof(*out));
 		CK(cudaMemcpyAsync(c->h_counters, c->counters, sizeof(FrameCounters), cudaMemcpyDeviceToHost, s));
-		uint32_t merge_err = 0;
-		if (merge) CK(cudaMemcpyAsync(&merge_err, c->sync_flags + kMaxRanks, 4, cudaMemcpyDeviceToHost, s));
 		CK(cudaStreamSynchronize(s));
-		if (merge_err) return fail(c, VKV_ERR_CUDA, "multi-GPU merge barrier timed out (a peer did not reach the merge)");
+		rc = check_merge_error(c); // also reported by the next vkv_sync / vkv_read_* when the caller passed no stats
+		if (rc) return rc;
 		out->draws = N;
 		out->visible_a = c->h_counters->visible[0];
 		out->occluded_a = c->h_counters->occluded[0];
@@ -655,10 +698,10 @@ int vkv_resolve(vkv_ctx* c, const vkv_VisbufferPushConstants* pc) {
 	const uint32_t nm = (uint32_t)(bytes / sizeof(vkv_Material));
 	if (nm > c->mat_cap) {
 		CK(cudaStreamSynchronize(c->stream));
+		uint32_t* fresh = nullptr;
+		CK(cudaMalloc(&fresh, (size_t)(nm + 64) * 4));
 		if (c->mat_colors) cudaFree(c->mat_colors);
-		c->mat_colors = nullptr; c->mat_cap = 0;
-		CK(cudaMalloc(&c->mat_colors, (size_t)(nm + 64) * 4));
-		c->mat_cap = nm + 64;
+		c->mat_colors = fresh; c->mat_cap = nm + 64;
 	}
 	CK(launch_material_colors((const vkv_Material*)pc->materialBuffer, nm, c->mat_colors, c->num_sms, c->stream));
 	ResolveParams r{};
@@ -735,7 +778,14 @@ int vkv_ipc_attach(vkv_ctx* c, int rank, int nranks, const void* handles) {
 		}
 		c->mp.flags[r] = (uint32_t*)pf;
 	}
+	// A new session starts from a clean barrier state: epoch 0 AND zeroed local slots + error word.  (Resetting only the epoch would
+	// leave the previous session's epochs in the slots, and `flag - epoch >= 0` would let every barrier pass at once.)  This is
+	// safe because no peer can still be signalling into these slots: a peer's stream is idle before it exports (vkv_resize /
+	// vkv_ipc_detach synchronize it) and the caller exchanges the handles between that and this call.  The caller must also
+	// rendezvous on the host between the LAST rank's attach and the first merged frame (multigpu.attach_peers: dist.barrier()).
+	CK(cudaMemset(c->sync_flags, 0, (kMaxRanks + 1) * 4));
 	c->epoch = 0;
+	c->merge_err_pending = false;
 	return VKV_OK;
 }
 
@@ -758,7 +808,7 @@ int vkv_read_visbuffer64(vkv_ctx* c, uint64_t* host) {
 	CK(cudaSetDevice(c->device));
 	CK(cudaMemcpyAsync(host, c->vis, (size_t)c->W * c->H * 8, cudaMemcpyDeviceToHost, c->stream));
 	CK(cudaStreamSynchronize(c->stream));
-	return VKV_OK;
+	return check_merge_error(c);
 }
 
 static int read_split(vkv_ctx* c, uint32_t* ids, float* depth) {
@@ -770,7 +820,7 @@ static int read_split(vkv_ctx* c, uint32_t* ids, float* depth) {
 	if (ids) CK(cudaMemcpyAsync(ids, c->tmp_ids, n * 4, cudaMemcpyDeviceToHost, c->stream));
 	if (depth) CK(cudaMemcpyAsync(depth, c->tmp_depth, n * 4, cudaMemcpyDeviceToHost, c->stream));
 	CK(cudaStreamSynchronize(c->stream));
-	return VKV_OK;
+	return check_merge_error(c);
 }
 int vkv_read_ids(vkv_ctx* c, uint32_t* host) { return (c && host) ? read_split(c, host, nullptr) : VKV_ERR_INVALID; }
 int vkv_read_depth(vkv_ctx* c, float* host) { return (c && host) ? read_split(c, nullptr, host) : VKV_ERR_INVALID; }
@@ -796,7 +846,7 @@ int vkv_read_pyramid(vkv_ctx* c, float* host, uint32_t floats) {
 	CK(cudaSetDevice(c->device));
 	CK(cudaMemcpyAsync(host, c->pyramid, (size_t)floats * 4, cudaMemcpyDeviceToHost, c->stream));
 	CK(cudaStreamSynchronize(c->stream));
-	return VKV_OK;
+	return check_merge_error(c);
 }
 
 int vkv_write_pyramid(vkv_ctx* c, const float* host, uint32_t floats) {
@@ -852,8 +902,9 @@ int vkv_flush_l2(vkv_ctx* c, size_t bytes) {
 	if (!c) return VKV_ERR_INVALID;
 	CK(cudaSetDevice(c->device));
 	if (bytes > c->flush_bytes) {
+		CK(cudaStreamSynchronize(c->stream));
 		if (c->flush_buf) cudaFree(c->flush_buf);
-		c->flush_buf = nullptr; c->flush_bytes = 0;
+		c->flush_buf = nullptr; c->flush_bytes = 0; // scratch only: nothing else refers to it, so free-then-allocate is safe
 		CK(cudaMalloc(&c->flush_buf, bytes));
 		c->flush_bytes = bytes;
 	}
@@ -1020,7 +1071,7 @@ int vkv_build_meshlets(vkv_ctx* c, const vkv_MeshletBuildInput* in, uint32_t n, 
 	for (uint32_t i = 0; i < n; ++i) {
 		if (in[i].index_count % 3) return fail(c, VKV_ERR_INVALID, "vkv_build_meshlets: primitive %u has %u indices", i, in[i].index_count);
 		if (in[i].index_count && (!in[i].indices || !in[i].vertices)) return fail(c, VKV_ERR_INVALID, "vkv_build_meshlets: primitive %u: NULL buffer", i);
-		prims[i] = MeshletBuildPrim{(const uint32_t*)(uintptr_t)in[i].indices, (const uint8_t*)(uintptr_t)in[i].vertices};
+		prims[i] = MeshletBuildPrim{(const uint32_t*)(uintptr_t)in[i].indices, (const uint8_t*)(uintptr_t)in[i].vertices, in[i].vertex_count, 0};
 		const uint32_t T = in[i].index_count / 3;
 		triFirst[i] = (uint32_t)total;
 		for (uint32_t t = 0; t < T; t += kMeshletSeg)
@@ -1055,10 +1106,18 @@ int vkv_build_meshlets(vkv_ctx* c, const vkv_MeshletBuildInput* in, uint32_t n, 
 	MBCK(dev(segs.size() * max_triangles * sizeof(MeshletBuildSegEntry), nullptr, &d)); j.table = (MeshletBuildSegEntry*)d;
 	MBCK(dev(segs.size() * sizeof(MeshletBuildSegState), nullptr, &d)); j.state = (MeshletBuildSegState*)d;
 	MBCK(dev((size_t)(n + 1) * 12, nullptr, &d)); j.primBase = (uint32_t*)d;
+	MBCK(dev(4, nullptr, &d)); j.badIndex = (uint32_t*)d;
+	MBCK(cudaMemsetAsync(j.badIndex, 0, 4, c->stream));
 	MBCK(launch_meshlet_scan(j, c->stream));
 	std::vector<uint32_t> base((size_t)(n + 1) * 3);
+	uint32_t bad = 0;
 	MBCK(cudaMemcpyAsync(base.data(), j.primBase, base.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+	MBCK(cudaMemcpyAsync(&bad, j.badIndex, 4, cudaMemcpyDeviceToHost, c->stream));
 	MBCK(cudaStreamSynchronize(c->stream));
+	if (bad) { // nothing has dereferenced a vertex yet (the scan reads indices only): reject before the emit pass would
+		release();
+		return fail(c, VKV_ERR_INVALID, "vkv_build_meshlets: primitive %u holds an index >= its vertex_count %u", bad - 1, in[bad - 1].vertex_count);
+	}
 	const uint32_t M = base[n * 3], V = base[n * 3 + 1], B = base[n * 3 + 2];
 	MBCK(dev((size_t)M * sizeof(MeshletBuildRecord), nullptr, &d)); j.rec = (MeshletBuildRecord*)d;
 	// outputs: three allocations shared by the primitives of this call, registered like vkv_upload's

@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(1024) hiz_tail_kernel(const HizParams p, uint3
 
 // One warp per 64x16 source tile. Lane l owns source columns 2l,2l+1 (one 16-byte load per row, 16 loads in flight).
 // Valid only for levels whose source is exactly twice the destination in both axes: the sampler footprint is then the
-// aligned 2x2 quad {2p, 2p+1} (u = 2p + 0.5 up to rounding noise << 0.5; checked exhaustively in tests/test_hiz_rule.py).
+// aligned 2x2 quad {2p, 2p+1} (u = 2p + 0.5 up to rounding noise << 0.5; checked exhaustively in tests/test_oracle.py).
 __global__ void __launch_bounds__(kHizWarps * 32) hiz_tiled_kernel(const HizParams p) {
 	extern __shared__ __align__(16) unsigned char tailSmem[]; // used by the last block only (1 block / SM anyway: 1024 threads)
 	__shared__ uint32_t sLast;

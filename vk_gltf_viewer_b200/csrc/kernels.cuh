@@ -50,6 +50,7 @@ struct BigTri {
 	uint32_t pad;
 };
 
+constexpr int kBigSlotShift = 40;    // FrameCounters::big_cursor = records << 40 | tile-work items (raster.cu push_big)
 struct RasterParams {
 	const vkv_MeshletDraw* draws;
 	const float* transforms;
@@ -143,7 +144,7 @@ cudaError_t launch_meshopt_decode(const MeshoptPlan& p, const uint8_t* src, uint
 
 // ---- meshlet partition + bounds (meshlets.cu) ----------------------------------------------------------------------
 constexpr uint32_t kMeshletSeg = 2048;   // triangles per chain segment
-struct MeshletBuildPrim { const uint32_t* indices; const uint8_t* vertices; };
+struct MeshletBuildPrim { const uint32_t* indices; const uint8_t* vertices; uint32_t vertexCount; uint32_t pad; };   // vertexCount 0 = unknown (indices not range-checked)
 struct MeshletBuildSeg { uint32_t start, end; uint32_t prim; uint32_t first_of_prim; };   // global triangle range [start, end) inside one primitive
 struct MeshletBuildSegEntry { uint32_t meshlets, vertices, bytes, exit; };                 // per (segment, entry offset)
 struct MeshletBuildSegState { uint32_t entry, meshlets, vertices, bytes; };                // where the chain enters a segment, output bases there
@@ -155,6 +156,7 @@ struct MeshletBuildJob {
 	const MeshletBuildSeg* segs; uint32_t nSegs;
 	uint32_t maxV, maxT, vertexStride;
 	uint8_t* len; uint8_t* ucnt;     // per triangle: size and distinct-vertex count of the greedy meshlet starting there
+	uint32_t* badIndex;              // set to primitive + 1 when an index >= that primitive's vertexCount is found (meshopt_buildMeshlets asserts this)
 	MeshletBuildSegEntry* table;     // [nSegs * maxT]
 	MeshletBuildSegState* state;     // [nSegs]
 	uint32_t* primBase;              // [(nPrims + 1) * 3] meshlets / vertex indices / triangle bytes before each primitive (last = totals)

@@ -69,12 +69,17 @@ struct VertexSet { // open addressing, linear probing
 
 // ---- len: the greedy meshlet that would start at every triangle -------------------------------------------------------------
 __global__ void __launch_bounds__(128) mb_len_kernel(const MeshletBuildPrim* __restrict__ prims, uint32_t nPrims, const uint32_t* __restrict__ triFirst,
-                                                     uint32_t totalTris, uint32_t maxV, uint32_t maxT, uint8_t* __restrict__ len, uint8_t* __restrict__ ucnt) {
+                                                     uint32_t totalTris, uint32_t maxV, uint32_t maxT, uint8_t* __restrict__ len, uint8_t* __restrict__ ucnt,
+                                                     uint32_t* __restrict__ badIndex) {
 	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
 	if (s >= totalTris) return;
 	const uint32_t p = find_owner(triFirst, nPrims, s);
 	const uint32_t* __restrict__ idx = prims[p].indices;
 	const uint32_t nT = triFirst[p + 1] - triFirst[p];
+	{ // every thread range-checks ITS triangle: the emit pass dereferences vertices[index] (untrusted glTF; clusterizer.cpp:45 asserts)
+		const uint32_t nV = prims[p].vertexCount, t = s - triFirst[p];
+		if (nV && (__ldg(idx + 3 * t) >= nV || __ldg(idx + 3 * t + 1) >= nV || __ldg(idx + 3 * t + 2) >= nV)) atomicMax(badIndex, p + 1);
+	}
 	VertexSet set;
 	set.clear();
 	uint32_t vc = 0, tc = 0;
@@ -210,7 +215,7 @@ __global__ void __launch_bounds__(128) mb_emit_kernel(const MeshletBuildPrim* __
 
 cudaError_t launch_meshlet_scan(const MeshletBuildJob& j, cudaStream_t stream) {
 	if (j.totalTris == 0) return cudaSuccess;
-	mb_len_kernel<<<(j.totalTris + 127) / 128, 128, 0, stream>>>(j.prims, j.nPrims, j.triFirst, j.totalTris, j.maxV, j.maxT, j.len, j.ucnt);
+	mb_len_kernel<<<(j.totalTris + 127) / 128, 128, 0, stream>>>(j.prims, j.nPrims, j.triFirst, j.totalTris, j.maxV, j.maxT, j.len, j.ucnt, j.badIndex);
 	const uint32_t entries = j.nSegs * j.maxT;
 	mb_segment_kernel<<<(entries + 127) / 128, 128, 0, stream>>>(j.segs, j.nSegs, j.maxT, j.len, j.ucnt, j.table);
 	mb_chain_kernel<<<1, 32, 0, stream>>>(j.segs, j.nSegs, j.maxT, j.table, j.state, j.primBase, j.nPrims);

@@ -63,7 +63,6 @@ struct WarpScratch {
 	                                 // adjacent at [(k * 32 + lane) * 2 + half]: one 8-byte load gives the f32x2 pair the vertex phase works on
 	uint32_t tri_words[2][96];       // cp.async landing zone (double buffered): up to 124*3 = 372 index bytes
 	uint32_t surv[128];              // phase-1 survivors: ia | ib << 8 | ic << 16 | triangle << 24 | needsClip << 31
-	float mvp[16];                   // (unused padding of the old layout)
 	float2 mvp2[4][4];               // cp.async landing zone: mvp[row][column], every element twice (f32x2 operand for two vertices)
 	Tri sub[8];
 	MeshletHdr hdr[kBatch];
@@ -209,15 +208,30 @@ __device__ __forceinline__ bool is_big(const Tri& t) {
 	return ((t.xmax - t.xmin + 8) >> 3) * ((t.ymax - t.ymin + 4) >> 2) >= kBigMinStamps;
 }
 
-// Append a large triangle to the queue (one lane).  ONE 64-bit atomic hands out the record slot and the triangle's range of
-// tile-work indices, so record order == tile-base order and the drain kernel can binary-search it.  false = queue full.
+// Append a large triangle to the queue (one lane).  ONE 64-bit atomic hands out the record slot (top 24 bits) and the
+// triangle's range of tile-work indices (low 40 bits), so record order == tile-base order and the drain kernel can binary-search
+// it.  40 bits cannot carry into the slot field: a triangle covers at most (32768/128) * (32768/64) = 2^17 tiles and fewer than
+// 2^23 pushes can happen per launch beyond the capacity check below.  Stored records additionally keep their whole tile range
+// below 2^32 (the drain kernel's work counter is 32 bits).  false = not queued: the caller rasterises the triangle in place.
+constexpr unsigned long long kBigTileMask = (1ull << kBigSlotShift) - 1ull;
 __device__ __forceinline__ bool push_big(const RasterParams& p, const Tri& t) {
 	const uint32_t tilesX = (uint32_t)(t.xmax / kBigTileW - t.xmin / kBigTileW + 1), tilesY = (uint32_t)(t.ymax / kBigTileH - t.ymin / kBigTileH + 1);
-	const unsigned long long old = atomicAdd(p.bigCursor, (1ull << 32) | (unsigned long long)(tilesX * tilesY));
-	const uint32_t slot = (uint32_t)(old >> 32);
-	if (slot >= p.bigCap) return false; // its tile range lies beyond every stored record's: the drain kernel never reaches it
+	const uint32_t tiles = tilesX * tilesY;
+	// full already (plain load; racy by at most one push per thread in flight, which the 24-bit slot field absorbs)
+	if ((uint32_t)(*(volatile unsigned long long*)p.bigCursor >> kBigSlotShift) >= p.bigCap) return false;
+	const unsigned long long old = atomicAdd(p.bigCursor, (1ull << kBigSlotShift) | (unsigned long long)tiles);
+	const uint32_t slot = (uint32_t)(old >> kBigSlotShift);
+	const unsigned long long base = old & kBigTileMask;
+	// beyond the capacity, or the tile range would leave 32 bits: its range lies beyond every stored record's and is never visited
+	if (slot >= p.bigCap) return false;
+	if (base + tiles > 0xffffffffull) { // keeps its slot as an empty sentinel (such slots form a suffix: bases only grow)
+		BigTri e = {};
+		e.tileBase = 0xffffffffu;
+		p.big[slot] = e;
+		return false;
+	}
 	BigTri b;
-	b.t = t; b.tileBase = (uint32_t)old; b.tilesX = tilesX; b.tilesY = tilesY; b.pad = 0;
+	b.t = t; b.tileBase = (uint32_t)base; b.tilesX = tilesX; b.tilesY = tilesY; b.pad = 0;
 	p.big[slot] = b;
 	return true;
 }
@@ -528,7 +542,16 @@ __global__ void __launch_bounds__(256) raster_big_kernel(const RasterParams p) {
 	__shared__ Tri sTri[8];
 	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const unsigned long long cur = *p.bigCursor;
-	const uint32_t nRec = min((uint32_t)(cur >> 32), p.bigCap);
+	uint32_t nRec = min((uint32_t)(cur >> kBigSlotShift), p.bigCap);
+	// records whose tile range would have left 32 bits were not stored (push_big): they form a suffix, because tile bases only grow
+	if ((cur & kBigTileMask) > 0xffffffffull) {
+		uint32_t lo = 0, hi = nRec; // first sentinel slot
+		while (lo < hi) {
+			const uint32_t mid = (lo + hi) >> 1;
+			if (p.big[mid].tilesX == 0) hi = mid; else lo = mid + 1;
+		}
+		nRec = lo;
+	}
 	if (nRec == 0) return;
 	const BigTri* last = p.big + (nRec - 1);
 	const uint32_t nTiles = last->tileBase + last->tilesX * last->tilesY;
