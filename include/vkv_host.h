@@ -26,7 +26,7 @@ typedef struct vkvh_scene vkvh_scene;
 
 /* Optional replacement meshlet builder with meshoptimizer's signatures (meshoptimizer.h: meshopt_buildMeshletsBound,
  * meshopt_buildMeshlets, meshopt_optimizeMeshlet).  Tests point these at the reference's own meshoptimizer build
- * (oracle/_ref) to obtain byte-identical inputs; the product default is the built-in builder. */
+ * (oracle/_ref) to cross-check the built-in default below; passing NULLs restores the default. */
 typedef struct vkvh_meshopt_Meshlet { unsigned vertex_offset, triangle_offset, vertex_count, triangle_count; } vkvh_meshopt_Meshlet;
 typedef size_t (*vkvh_build_bound_fn)(size_t index_count, size_t max_vertices, size_t max_triangles);
 typedef size_t (*vkvh_build_fn)(vkvh_meshopt_Meshlet* meshlets, unsigned* meshlet_vertices, unsigned char* meshlet_triangles,
@@ -34,6 +34,27 @@ typedef size_t (*vkvh_build_fn)(vkvh_meshopt_Meshlet* meshlets, unsigned* meshle
                                 size_t vertex_positions_stride, size_t max_vertices, size_t max_triangles, float cone_weight);
 typedef void (*vkvh_optimize_fn)(unsigned* meshlet_vertices, unsigned char* meshlet_triangles, size_t triangle_count, size_t vertex_count);
 void vkvh_set_meshlet_builder(vkvh_build_bound_fn bound, vkvh_build_fn build, vkvh_optimize_fn optimize);
+
+/* The built-in default (host/clusterizer.cpp): the partition the reference uploads — the algorithms of meshoptimizer 0.20's
+ * meshopt_buildMeshletsBound / meshopt_buildMeshlets / meshopt_optimizeMeshlet / meshopt_computeMeshletBounds
+ * (assets.cpp:322-346; submodules/meshoptimizer/src/clusterizer.cpp), restated here with the library's signatures and
+ * byte-identical output (tests/test_host.py checks every byte against the reference's own build of the library).
+ * vkvh_meshlets_build returns 0 for arguments the library would assert on (bad limits, an index >= vertex_count). */
+typedef struct vkvh_meshopt_Bounds {
+	float center[3], radius;              /* bounding sphere */
+	float cone_apex[3], cone_axis[3], cone_cutoff;   /* normal cone: reject when dot(normalize(apex - eye), axis) >= cutoff (meshoptimizer.h:531) */
+	signed char cone_axis_s8[3], cone_cutoff_s8;
+} vkvh_meshopt_Bounds;
+size_t vkvh_meshlets_bound(size_t index_count, size_t max_vertices, size_t max_triangles);
+size_t vkvh_meshlets_build(vkvh_meshopt_Meshlet* meshlets, unsigned* meshlet_vertices, unsigned char* meshlet_triangles, const unsigned* indices,
+                           size_t index_count, const float* vertex_positions, size_t vertex_count, size_t vertex_positions_stride,
+                           size_t max_vertices, size_t max_triangles, float cone_weight);
+void vkvh_meshlet_optimize(unsigned* meshlet_vertices, unsigned char* meshlet_triangles, size_t triangle_count, size_t vertex_count);
+void vkvh_meshlet_bounds(const unsigned* meshlet_vertices, const unsigned char* meshlet_triangles, size_t triangle_count, const float* vertex_positions,
+                         size_t vertex_count, size_t vertex_positions_stride, vkvh_meshopt_Bounds* out);
+/* 0 (default): the reference's partition as above.  1: the round-1 Morton-order greedy packer (vertex-limited 64 v / ~67 t meshlets;
+ * kept as a second, harder workload for A/B measurements).  Ignored while vkvh_set_meshlet_builder has injected a builder. */
+void vkvh_select_builder(int morton);
 
 /* --- scene construction ------------------------------------------------------------------------------------ */
 vkvh_scene* vkvh_scene_new(void);                       /* material 0 = default (assets.cpp:486-492) */

@@ -72,6 +72,113 @@ def test_builtin_builder_partitions_every_triangle_once():
     assert np.array_equal(canon(got), canon(perm))
 
 
+class _Meshlet(C.Structure):
+    _fields_ = [("vertex_offset", C.c_uint), ("triangle_offset", C.c_uint), ("vertex_count", C.c_uint), ("triangle_count", C.c_uint)]
+
+
+class _Bounds(C.Structure):
+    _fields_ = [("center", C.c_float * 3), ("radius", C.c_float), ("cone_apex", C.c_float * 3), ("cone_axis", C.c_float * 3),
+                ("cone_cutoff", C.c_float), ("cone_axis_s8", C.c_byte * 3), ("cone_cutoff_s8", C.c_byte)]
+
+
+def _run_builder(bound, build, optimize, bounds, pos, idx, max_v=64, max_t=124, cone_weight=0.0, bounds_by_value=False):
+    """assets.cpp:322-346 call sequence through one set of meshoptimizer-shaped entry points -> raw output bytes"""
+    vtx = np.zeros((pos.shape[0], 6), np.float32)   # glsl::Vertex stride: 24 bytes, position first
+    vtx[:, :3] = pos
+    for f in (bound, build):
+        f.restype = C.c_size_t
+    bound.argtypes = [C.c_size_t] * 3
+    build.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_float]
+    optimize.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]
+    optimize.restype = None
+    nmax = bound(idx.size, max_v, max_t)
+    ms = (_Meshlet * nmax)()
+    mv = np.zeros(nmax * max_v, np.uint32)
+    mt = np.zeros(nmax * max_t * 3, np.uint8)
+    n = build(ms, mv.ctypes.data, mt.ctypes.data, idx.ctypes.data, idx.size, vtx.ctypes.data, vtx.shape[0], 24, max_v, max_t, cone_weight)
+    rec = np.array([[m.vertex_offset, m.triangle_offset, m.vertex_count, m.triangle_count] for m in ms[:n]], np.int64)
+    last = rec[-1]
+    mv = mv[: last[0] + last[2]]
+    mt = mt[: last[1] + ((last[3] * 3 + 3) & ~3)]
+    bnd = []
+    for vo, to, vc, tc in rec:
+        optimize(mv.ctypes.data + 4 * int(vo), mt.ctypes.data + int(to), int(tc), int(vc))
+        a = (mv.ctypes.data + 4 * int(vo), mt.ctypes.data + int(to), int(tc), vtx.ctypes.data, vtx.shape[0], 24)
+        if bounds_by_value:   # meshoptimizer returns the 48-byte struct by value
+            bounds.restype = _Bounds
+            bounds.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t]
+            b = bounds(*a)
+        else:
+            bounds.restype = None
+            bounds.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.POINTER(_Bounds)]
+            b = _Bounds()
+            bounds(*a, C.byref(b))
+        bnd.append(bytes(b))
+    return nmax, rec, mv, mt, bnd
+
+
+def _builder_meshes():
+    rng = np.random.default_rng(11)
+    out = {}
+    out["patch224"] = S.grid_mesh(224, 224, lambda u, v: (u, 0.05 * np.sin(u * 9) * np.cos(v * 7), v))           # the cfg-3 / cfg-5 patch shape
+    pos, idx = S.grid_mesh(37, 23, lambda u, v: (u * 3, np.sin(u * 7) * np.cos(v * 3), v * 2))
+    out["shuffled"] = (pos, rng.permutation(idx.reshape(-1, 3)).reshape(-1).astype(np.uint32))              # index order must be followed exactly
+    sphere = Scene.icosphere(12)            # a closed mesh: take its triangle soup back out of the meshlets
+    ico = sphere.primitive(0)
+    pos = ico["vertices"]["position"].copy()
+    soup = np.concatenate([ico["vertex_indices"][int(m["vertexOffset"]) + ico["triangles"][int(m["triangleOffset"]): int(m["triangleOffset"]) + 3 * int(m["triangleCount"])].astype(np.int64)]
+                           for m in ico["meshlets"]]).astype(np.uint32)
+    out["icosphere"] = (pos, soup)
+    # disconnected islands + degenerate triangles + a repeated corner: exercises the kd-tree fallback, zero-area cones, dangling triangles
+    p1, i1 = S.grid_mesh(9, 9, lambda u, v: (u, v, 0 * u))
+    p2, i2 = S.grid_mesh(5, 7, lambda u, v: (u + 3, v, 0.3 * u))
+    p3 = rng.uniform(-1, 1, (60, 3)).astype(np.float32) + np.float32(8)
+    i3 = rng.integers(0, 60, 180).astype(np.uint32)
+    i3[:3] = [5, 5, 9]
+    pos = np.concatenate([p1, p2, p3])
+    idx = np.concatenate([i1, i2 + p1.shape[0], i3 + p1.shape[0] + p2.shape[0]]).astype(np.uint32)
+    out["islands"] = (pos, idx)
+    return out
+
+
+@pytest.mark.parametrize("limits", [(64, 124, 0.0), (64, 124, 0.5), (32, 20, 0.0), (255, 512, 0.25)])
+def test_builtin_clusterizer_is_byte_identical_to_the_reference_meshoptimizer(meshopt_ref, limits):
+    """a-7: the default meshlet builder (host/clusterizer.cpp) against meshoptimizer built from the reference tree: bound, every
+    meshlet record, vertex list, triangle byte (meshopt_buildMeshlets + meshopt_optimizeMeshlet, assets.cpp:331-346) and every field
+    of meshopt_computeMeshletBounds, for the reference's limits (64 / 124 / cone weight 0) and three others"""
+    from vk_gltf_viewer_b200._native import host_lib
+    H = host_lib()
+    mv_, mt_, cw = limits
+    for name, (pos, idx) in _builder_meshes().items():
+        ref = _run_builder(meshopt_ref.meshopt_buildMeshletsBound, meshopt_ref.meshopt_buildMeshlets, meshopt_ref.meshopt_optimizeMeshlet,
+                           meshopt_ref.meshopt_computeMeshletBounds, pos, idx, mv_, mt_, cw, bounds_by_value=True)
+        got = _run_builder(H.vkvh_meshlets_bound, H.vkvh_meshlets_build, H.vkvh_meshlet_optimize, H.vkvh_meshlet_bounds, pos, idx, mv_, mt_, cw)
+        assert got[0] == ref[0], name
+        assert np.array_equal(got[1], ref[1]), f"{name}: meshlet records differ"
+        assert np.array_equal(got[2], ref[2]), f"{name}: vertex lists differ"
+        assert np.array_equal(got[3], ref[3]), f"{name}: triangle bytes differ"
+        assert got[4] == ref[4], f"{name}: bounds differ in {sum(a != b for a, b in zip(got[4], ref[4]))} meshlets"
+
+
+def test_default_scene_builder_uploads_the_reference_partition(meshopt_ref):
+    """Scene.add_primitive (no injection) == the same call sequence through the reference's library, buffer for buffer"""
+    pos, idx = S.grid_mesh(96, 64, lambda u, v: (u * 2, 0.1 * np.sin(u * 11) * np.cos(v * 5), v))
+    s = Scene.new()
+    s.add_primitive(pos, idx)
+    mine = s.primitive(0)
+    set_meshlet_builder(meshopt_ref.meshopt_buildMeshletsBound, meshopt_ref.meshopt_buildMeshlets, meshopt_ref.meshopt_optimizeMeshlet)
+    try:
+        s2 = Scene.new()
+        s2.add_primitive(pos, idx)
+        ref = s2.primitive(0)
+    finally:
+        set_meshlet_builder(None, None, None)
+    for k in ("vertex_indices", "triangles", "meshlets"):
+        assert mine[k].tobytes() == ref[k].tobytes(), k
+    tc = mine["meshlets"]["triangleCount"].astype(np.int64)
+    assert 85 < tc[:-1].mean() <= 124   # vertex-limited ~95-triangle meshlets on regular grids (SURVEY §8a-1), not the Morton packer's ~67
+
+
 def test_reference_meshoptimizer_can_be_injected(meshopt_ref):
     """the reference's pinned meshoptimizer builds the meshlets (assets.cpp:322-346 call sequence) -> same invariants"""
     set_meshlet_builder(meshopt_ref.meshopt_buildMeshletsBound, meshopt_ref.meshopt_buildMeshlets, meshopt_ref.meshopt_optimizeMeshlet)

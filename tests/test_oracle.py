@@ -21,7 +21,7 @@ def test_frustum_test_matches_reference_culling_h(ref_shim):
     total = 0
     for trial in range(6):
         s = Scene.new()
-        pos, idx = S.grid_mesh(24, 24, lambda u, v: (u * 8 - 4, np.sin(u * 5 + trial) * np.cos(v * 4), v * 8 - 4))
+        pos, idx = S.grid_mesh(36, 36, lambda u, v: (u * 8 - 4, np.sin(u * 5 + trial) * np.cos(v * 4), v * 8 - 4))
         p = s.add_primitive(pos, idx)
         for _ in range(12):
             q = rng.normal(size=4); q /= np.linalg.norm(q)

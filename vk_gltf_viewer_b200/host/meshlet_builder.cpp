@@ -1,10 +1,11 @@
-// meshlet_builder.cpp — host-side meshlet partitioning (input generator; not part of the per-frame path).
+// meshlet_builder.cpp — the round-1 meshlet packer, kept as an alternative workload (vkvh_select_builder(1)).
 //
-// The reference calls meshopt_buildMeshlets(…, 64, 124, 0.0f) followed by meshopt_optimizeMeshlet
-// (assets.cpp:322-346).  meshoptimizer's partition is not pinned by any test, so any partition that
-// honours the same limits is a valid input for the hot path.  This builder is our own: triangles are ordered
-// along a Morton curve of their centroids and packed greedily until the 64-vertex / 124-triangle limit is hit.
-// Output layout is the one the reference uploads: u32 global vertex index per local slot, 3 u8 local slots per
+// The default builder is host/clusterizer.cpp, which reproduces the partition the reference uploads
+// (meshopt_buildMeshlets(…, 64, 124, 0.0f) + meshopt_optimizeMeshlet, assets.cpp:322-346) byte for byte.  This one orders the
+// triangles along a Morton curve of their centroids and packs them greedily until the 64-vertex / 124-triangle limit is hit:
+// on regular grids it yields vertex-limited 64 v / ~67 t meshlets (40 % more MeshletDraws than the reference's ~95 t ones),
+// i.e. a harder input for the same image — useful for A/B measurements, valid for the hot path (any partition within the
+// limits is).  Output layout is the one the reference uploads: u32 global vertex index per local slot, 3 u8 local slots per
 // triangle, each meshlet's triangle bytes starting on a 4-byte boundary (assets.cpp:339).
 #include "scene.hpp"
 

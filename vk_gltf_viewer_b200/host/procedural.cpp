@@ -4,6 +4,9 @@
 // (vkvh_scene_add_primitive / add_node_trs / finalize == assets.cpp:288-373 + world.cpp:187-345).
 #include "scene.hpp"
 
+#include <atomic>
+#include <thread>
+
 #include <algorithm>
 #include <cmath>
 #include <functional>
@@ -255,6 +258,11 @@ vkvh_scene* vkvh_scene_city(uint32_t nbx, uint32_t nby, uint32_t target, uint64_
 	uint32_t n = (uint32_t)std::max(2.0, std::floor(std::sqrt((double)target / 20.0)));
 	uint32_t mq = (uint32_t)std::max(2.0, std::floor(((double)target - 2.0 * n * n) / (8.0 * n)));
 	const float lot = 10.0f;
+	// geometry first (sequential: one seeded random stream), then the meshlet builds of all buildings side by side, then the
+	// primitives and nodes in the original order
+	std::vector<Mesh> meshes;
+	struct Placement { float t[3]; float r[4]; };
+	std::vector<Placement> places;
 	for (uint32_t by = 0; by < nby; ++by)
 		for (uint32_t bx = 0; bx < nbx; ++bx) {
 			const float w = rng.range(2.5f, 4.2f), dpt = rng.range(2.5f, 4.2f), h = rng.range(6.0f, 40.0f);
@@ -272,18 +280,40 @@ vkvh_scene* vkvh_scene_city(uint32_t nbx, uint32_t nby, uint32_t target, uint64_
 			loft(m, n, mq, [&](float u, float v, float* p) { p[2] = (1 - u * 2) * dpt; p[1] = v * h; p[0] = w + bump(u, v); }, false);
 			loft(m, n, mq, [&](float u, float v, float* p) { p[2] = (u * 2 - 1) * dpt; p[1] = v * h; p[0] = -w - bump(u, v); }, false);
 			loft(m, n, n, [&](float u, float v, float* p) { p[0] = (u * 2 - 1) * w; p[2] = (v * 2 - 1) * dpt; p[1] = h + 0.3f * bump(u, v); }, true);
-			int32_t prim = vkvh_scene_add_primitive(s, m.pos.data(), (uint32_t)(m.pos.size() / 3), m.idx.data(), (uint32_t)m.idx.size(), 0);
-			float t[3] = {((float)bx - (float)(nbx - 1) * 0.5f) * lot, 0.0f, ((float)by - (float)(nby - 1) * 0.5f) * lot};
+			Placement pl;
+			pl.t[0] = ((float)bx - (float)(nbx - 1) * 0.5f) * lot; pl.t[1] = 0.0f; pl.t[2] = ((float)by - (float)(nby - 1) * 0.5f) * lot;
 			float yaw = rng.range(-0.2f, 0.2f);
-			float r[4] = {0, std::sin(yaw * 0.5f), 0, std::cos(yaw * 0.5f)};
-			vkvh_scene_add_node_trs(s, -1, prim, t, r, nullptr);
+			pl.r[0] = 0; pl.r[1] = std::sin(yaw * 0.5f); pl.r[2] = 0; pl.r[3] = std::cos(yaw * 0.5f);
+			meshes.push_back(std::move(m));
+			places.push_back(pl);
 		}
 	{
 		Mesh g;
 		const float ex = (float)nbx * lot * 0.6f, ez = (float)nby * lot * 0.6f;
 		loft(g, 256, 256, [&](float u, float v, float* p) { p[0] = (u * 2 - 1) * ex; p[2] = (v * 2 - 1) * ez; p[1] = 0.0f; }, true);
-		int32_t prim = vkvh_scene_add_primitive(s, g.pos.data(), (uint32_t)(g.pos.size() / 3), g.idx.data(), (uint32_t)g.idx.size(), 0);
-		vkvh_scene_add_node_trs(s, -1, prim, nullptr, nullptr, nullptr);
+		meshes.push_back(std::move(g));
+	}
+	std::vector<vkvh::PrimitiveData> built(meshes.size());
+	std::vector<char> ok(meshes.size(), 0);
+	{
+		std::atomic<size_t> next{0};
+		auto worker = [&]() {
+			for (size_t i; (i = next.fetch_add(1)) < meshes.size();) {
+				const Mesh& m = meshes[i];
+				ok[i] = vkvh::build_primitive(built[i], vkvh::vertices_from_positions(m.pos.data(), (uint32_t)(m.pos.size() / 3)), m.idx.data(), (uint32_t)m.idx.size(), 0) ? 1 : 0;
+			}
+		};
+		const unsigned nt = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+		std::vector<std::thread> pool;
+		for (unsigned t = 1; t < nt; ++t) pool.emplace_back(worker);
+		worker();
+		for (auto& th : pool) th.join();
+	}
+	for (size_t i = 0; i < meshes.size(); ++i) {
+		if (!ok[i]) { vkvh_scene_free(s); return nullptr; }
+		const int32_t prim = vkvh::add_built_primitive(s, std::move(built[i]));
+		if (i < places.size()) vkvh_scene_add_node_trs(s, -1, prim, places[i].t, places[i].r, nullptr);
+		else vkvh_scene_add_node_trs(s, -1, prim, nullptr, nullptr, nullptr);
 	}
 	vkvh_scene_finalize(s);
 	s->kind = 4;

@@ -11,6 +11,7 @@ namespace {
 vkvh_build_bound_fn g_bound = nullptr;
 vkvh_build_fn g_build = nullptr;
 vkvh_optimize_fn g_optimize = nullptr;
+bool g_morton = false;
 } // namespace
 
 extern "C" {
@@ -18,6 +19,8 @@ extern "C" {
 void vkvh_set_meshlet_builder(vkvh_build_bound_fn bound, vkvh_build_fn build, vkvh_optimize_fn optimize) {
 	g_bound = bound; g_build = build; g_optimize = optimize;
 }
+
+void vkvh_select_builder(int morton) { g_morton = morton != 0; }
 
 vkvh_scene* vkvh_scene_new(void) {
 	auto* s = new vkvh_scene();
@@ -42,32 +45,40 @@ uint32_t vkvh_scene_add_material(vkvh_scene* s, const float albedo[4], int doubl
 	return (uint32_t)s->materials.size() - 1; // glTF material i -> i+1 (assets.cpp:292-294)
 }
 
-static int32_t add_primitive_vertices(vkvh_scene* s, std::vector<vkv_Vertex>&& vertices, const uint32_t* indices,
-                                      uint32_t index_count, uint32_t material_index) {
-	if (vertices.empty() || index_count < 3 || material_index >= s->materials.size()) return -1;
+} // extern "C"
+
+// processPrimitive (assets.cpp:288-373) for one primitive: meshlets + bounds.  Touches no scene state, so the procedural
+// generators may run it for many primitives side by side (the reference does the same through its task scheduler).
+bool vkvh::build_primitive(PrimitiveData& pd, std::vector<vkv_Vertex>&& vertices, const uint32_t* indices, uint32_t index_count, uint32_t material_index) {
+	if (vertices.empty() || index_count < 3) return false;
 	for (uint32_t i = 0; i < index_count; ++i)
-		if (indices[i] >= vertices.size()) return -1;
-	PrimitiveData pd;
+		if (indices[i] >= vertices.size()) return false;
 	pd.vertices = std::move(vertices);
 	pd.triangles = index_count / 3;
 	std::vector<uint32_t> idx(indices, indices + (index_count / 3) * 3);
 
 	std::vector<MeshletRec> recs;
-	if (g_build && g_bound) {
-		// assets.cpp:322-340, through the injected meshoptimizer-compatible entry points
+	const bool injected = g_build && g_bound;
+	if (injected || !g_morton) {
+		// assets.cpp:322-346 — through the built-in restatement of meshoptimizer's builder (host/clusterizer.cpp) or the injected
+		// meshoptimizer-compatible entry points
+		const vkvh_build_bound_fn boundFn = injected ? g_bound : vkvh_meshlets_bound;
+		const vkvh_build_fn buildFn = injected ? g_build : vkvh_meshlets_build;
+		const vkvh_optimize_fn optimizeFn = injected ? g_optimize : vkvh_meshlet_optimize;
 		const size_t maxTris = VKV_MAX_MESHLET_TRIANGLES;
-		size_t bound = g_bound(idx.size(), VKV_MAX_VERTICES, maxTris);
+		size_t bound = boundFn(idx.size(), VKV_MAX_VERTICES, maxTris);
 		std::vector<vkvh_meshopt_Meshlet> ms(bound);
 		pd.meshletVertices.resize(bound * VKV_MAX_VERTICES);
 		pd.meshletTriangles.resize(bound * maxTris * 3);
-		size_t n = g_build(ms.data(), pd.meshletVertices.data(), pd.meshletTriangles.data(), idx.data(), idx.size(),
+		size_t n = buildFn(ms.data(), pd.meshletVertices.data(), pd.meshletTriangles.data(), idx.data(), idx.size(),
 		                   pd.vertices[0].position, pd.vertices.size(), sizeof(vkv_Vertex), VKV_MAX_VERTICES, maxTris, 0.0f);
+		if (n == 0) return false;
 		const auto& last = ms[n - 1];
 		pd.meshletVertices.resize(last.vertex_count + last.vertex_offset);
 		pd.meshletTriangles.resize(((last.triangle_count * 3 + 3) & ~3u) + last.triangle_offset);
 		ms.resize(n);
 		for (auto& m : ms) {
-			if (g_optimize) g_optimize(&pd.meshletVertices[m.vertex_offset], &pd.meshletTriangles[m.triangle_offset], m.triangle_count, m.vertex_count);
+			if (optimizeFn) optimizeFn(&pd.meshletVertices[m.vertex_offset], &pd.meshletTriangles[m.triangle_offset], m.triangle_count, m.vertex_count);
 			recs.push_back({m.vertex_offset, m.triangle_offset, m.vertex_count, m.triangle_count});
 		}
 	} else {
@@ -104,20 +115,41 @@ static int32_t add_primitive_vertices(vkvh_scene* s, std::vector<vkv_Vertex>&& v
 	}
 	pd.header.meshletCount = (uint32_t)pd.meshlets.size();
 	pd.header.materialIndex = material_index;
+	return true;
+}
+
+int32_t vkvh::add_built_primitive(vkvh_scene* s, PrimitiveData&& pd) {
+	if (pd.header.materialIndex >= s->materials.size()) return -1;
 	s->primitives.push_back(std::move(pd));
 	s->finalized = false;
 	return (int32_t)s->primitives.size() - 1;
 }
 
-int32_t vkvh_scene_add_primitive(vkvh_scene* s, const float* positions, uint32_t vertex_count, const uint32_t* indices,
-                                 uint32_t index_count, uint32_t material_index) {
+static int32_t add_primitive_vertices(vkvh_scene* s, std::vector<vkv_Vertex>&& vertices, const uint32_t* indices,
+                                      uint32_t index_count, uint32_t material_index) {
+	if (material_index >= s->materials.size()) return -1;
+	PrimitiveData pd;
+	if (!build_primitive(pd, std::move(vertices), indices, index_count, material_index)) return -1;
+	return add_built_primitive(s, std::move(pd));
+}
+
+extern "C" {
+
+} // extern "C"
+std::vector<vkv_Vertex> vkvh::vertices_from_positions(const float* positions, uint32_t vertex_count) {
 	std::vector<vkv_Vertex> v(vertex_count);
 	for (uint32_t i = 0; i < vertex_count; ++i) {
 		std::memset(&v[i], 0, sizeof(vkv_Vertex));
 		v[i].position[0] = positions[i * 3]; v[i].position[1] = positions[i * 3 + 1]; v[i].position[2] = positions[i * 3 + 2];
 		v[i].color[0] = v[i].color[1] = v[i].color[2] = v[i].color[3] = 255;
 	}
-	return add_primitive_vertices(s, std::move(v), indices, index_count, material_index);
+	return v;
+}
+extern "C" {
+
+int32_t vkvh_scene_add_primitive(vkvh_scene* s, const float* positions, uint32_t vertex_count, const uint32_t* indices,
+                                 uint32_t index_count, uint32_t material_index) {
+	return add_primitive_vertices(s, vertices_from_positions(positions, vertex_count), indices, index_count, material_index);
 }
 
 int32_t vkvh_scene_add_primitive_i16(vkvh_scene* s, const int16_t* positions, uint32_t vertex_count, int normalized,

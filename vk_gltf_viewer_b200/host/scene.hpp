@@ -31,7 +31,13 @@ void build_meshlets_builtin(const std::vector<vkv_Vertex>& vertices, const std::
                             std::vector<MeshletRec>& meshlets, std::vector<uint32_t>& meshletVertices,
                             std::vector<uint8_t>& meshletTriangles);
 
+bool build_primitive(PrimitiveData& pd, std::vector<vkv_Vertex>&& vertices, const uint32_t* indices, uint32_t index_count, uint32_t material_index);
+std::vector<vkv_Vertex> vertices_from_positions(const float* positions, uint32_t vertex_count);
+
 } // namespace vkvh
+
+struct vkvh_scene;
+namespace vkvh { int32_t add_built_primitive(vkvh_scene* s, PrimitiveData&& pd); }
 
 struct vkvh_scene {
 	std::vector<vkvh::PrimitiveData> primitives;

@@ -71,6 +71,7 @@ def _lib():
                                          C.c_uint32, C.c_uint32, C.c_int]
         L.vkvh_frustum_from_vp.argtypes = [C.POINTER(C.c_float), C.c_void_p]
         L.vkvh_set_meshlet_builder.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.vkvh_select_builder.argtypes = [C.c_int]
         _bound = True
     return L
 
@@ -91,6 +92,14 @@ def set_meshlet_builder(bound_fn=None, build_fn=None, optimize_fn=None):
     def addr(f):
         return C.cast(f, C.c_void_p) if f is not None else None
     _lib().vkvh_set_meshlet_builder(addr(bound_fn), addr(build_fn), addr(optimize_fn))
+
+
+def select_builder(name: str = "meshopt"):
+    """"meshopt" (default): the reference's partition (host/clusterizer.cpp == meshopt_buildMeshlets + meshopt_optimizeMeshlet,
+    assets.cpp:331-346); "morton": the round-1 Morton-order greedy packer (64 v / ~67 t meshlets; a harder second workload)"""
+    if name not in ("meshopt", "morton"):
+        raise ValueError(name)
+    _lib().vkvh_select_builder(1 if name == "morton" else 0)
 
 
 class Camera:
