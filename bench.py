@@ -104,7 +104,53 @@ class ClockSampler:
                 "samples": len(sm), "power_w_max": max(pw) if pw else None, "scope": scope}
 
 
-def cpu_frames(scene, W, H, views, nframes, threads=0):
+def config_dict(label, W, H, cnt, passes, builder_note, world, shard):
+    """the `config` object of the JSON line: IDENTICAL on the GPU arm and on the reference arm (it names the workload and how each
+    arm runs it; per-run observations live under `run`)"""
+    return {"workload": label, "resolution": [W, H], "meshlet_draws": cnt.draws, "triangles": cnt.triangles_instanced, "passes": passes,
+            "meshlets": builder_note, "views": f"{NVIEWS}-view camera sweep, one view per step",
+            "parallelism": ((f"GPU arm: views sharded over {world} GPU(s), scene replicated, no collective" if shard == "views" else
+                             f"GPU arm: one view, MeshletDraw list sharded over {world} GPU(s) in interleaved 2048-draw ranges, screen-strip owners "
+                             "pull dirty visbuffer tiles over NVLink peer memory and all-gather the pyramid") +
+                            "; reference arm: CPU port of the same path on all host cores, rank 0 only"),
+            "l2": "GPU arm: 256 MB scratch written between timed frames (L2 flush), each frame timed by its own CUDA event pair; reference arm: n/a (CPU)"}
+
+
+def roofline(dom, stages, ent, hbm, peak_src, traffic, clocks):
+    """The dominant kernel against the limit that actually bounds it.  Cull and raster are bound by instruction ISSUE:
+    achieved = warp-instructions per launch (counted by ncu for this workload, profiles/traffic.json) / live CUDA-event duration,
+    peak = SMs x 4 schedulers x SM clock.  The HBM figure (algorithmic input bytes / time against the measured copy bandwidth) is kept
+    beside it; for the HBM-bound kernels (pyramid build, clear) it is the primary one."""
+    st = stages[dom]
+    hbm_part = {"achieved": st["GB/s"], "peak": hbm, "unit": "GB/s", "frac": st["frac_hbm"], "peak_source": peak_src,
+                "note": "input-side algorithmic bytes (SURVEY §8d) / CUDA-event time"}
+    issue_bound = dom.startswith("raster") or dom.startswith("cull")
+    if issue_bound and ent and ent.get("warp_instructions"):
+        mhz = (clocks or {}).get("sm_max_mhz") or 1965.0
+        peak = 148 * 4 * mhz * 1e6 / 1e9          # G warp-instructions / s
+        ach = ent["warp_instructions"] / (st["ms"] * 1e-3) / 1e9
+        return {"bound": "issue", "kernel": dom, "achieved": round(ach, 1), "peak": round(peak, 1), "unit": "Gwarp-inst/s", "frac": round(ach / peak, 4),
+                "traffic": traffic, "hbm": hbm_part, "warp_instructions_per_launch": ent["warp_instructions"], "instruction_count_from": ent.get("capture"),
+                "note": "software rasteriser / cull: bound by SM instruction issue (and L2 atomics), working set L2 resident (dram traffic << algorithmic "
+                        "bytes); peak = 148 SMs x 4 issue slots x SM clock; `hbm` keeps the byte-based figure; other kernels' fractions are in `stages`"}
+    return {"bound": "hbm", "kernel": dom, "traffic": traffic, **hbm_part}
+
+
+def meshlet_averages(scene):
+    """average vertices / triangles per MeshletDraw of the scene (weighted by how often each primitive is drawn)"""
+    d = scene.draws()
+    per_prim = np.bincount(d["primitiveIndex"].astype(np.int64), minlength=scene.counts().primitives)
+    v = t = n = 0.0
+    for i, draws in enumerate(per_prim):
+        if not draws:
+            continue
+        ml = scene.primitive(i)["meshlets"]
+        inst = draws / max(1, ml.shape[0])
+        v += inst * float(ml["vertexCount"].astype(np.int64).sum()); t += inst * float(ml["triangleCount"].astype(np.int64).sum()); n += draws
+    return (v / n, t / n) if n else (0.0, 0.0)
+
+
+def cpu_frames(scene, W, H, views, nframes, threads=0, warmup=1):
     """the oracle (CPU port of the reference path) timed on the host cores: two-pass frames of the same sweep"""
     from tests import oracle_lib as O
     from vk_gltf_viewer_b200.scene import Camera
@@ -112,7 +158,8 @@ def cpu_frames(scene, W, H, views, nframes, threads=0):
     cam.look_at(*views[0])
     pc = scene.host_push_constants(cam)
     tg = O.Targets(W, H)
-    O.frame(pc, tg, two_pass=True, threads=threads)  # warm-up: fills the pyramid the first timed frame culls against
+    for _ in range(max(1, warmup)):   # the first one also fills the pyramid the first timed frame culls against
+        O.frame(pc, tg, two_pass=True, threads=threads)
     times = []
     for k in range(nframes):
         cam.look_at(*views[(k + 1) % len(views)])
@@ -133,7 +180,14 @@ def main():
                     help="multi-GPU: independent views per GPU (default, cfg 1-4) or one view sharded by MeshletDraw range (cfg 5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--one-pass", action="store_true", help="reference one-pass mode instead of the two-pass extension")
+    ap.add_argument("--meshlets", default="meshopt", choices=["meshopt", "morton"],
+                    help="meshlet builder of the synthetic scene: the reference's partition (meshopt_buildMeshlets + optimizeMeshlet, default) "
+                         "or the round-1 Morton packer (40 %% more, smaller meshlets)")
     args = ap.parse_args()
+    from vk_gltf_viewer_b200.scene import select_builder
+    select_builder(args.meshlets)
+    builder_note = ("meshopt_buildMeshlets(64,124,0)+meshopt_optimizeMeshlet partition (assets.cpp:331-346), host/clusterizer.cpp" if args.meshlets == "meshopt"
+                    else "Morton-order greedy packer (host/meshlet_builder.cpp)")
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -149,17 +203,16 @@ def main():
         cnt = scene.counts()
         views = [scene.default_view(i, NVIEWS) for i in range(NVIEWS)]
         steps = max(1, args.steps if args.steps is not None else 20)
-        for _ in range(max(0, args.warmup - 1)):
-            pass  # cpu_frames always runs one warm-up frame (it also seeds the pyramid); extra warm-ups add nothing on a CPU
-        times = cpu_frames(scene, W, H, views, steps)
+        warm = max(1, min(args.warmup, 3))   # every warm-up is a full CPU frame (~0.5 s at cfg 3): at most 3, reported as run
+        times = cpu_frames(scene, W, H, views, steps, warmup=warm)
         total = sum(times)
         fps = steps / total
         line = {
             "impl": "reference", "metric": "frames/s (two-pass cull + HiZ + visbuffer)", "value": fps, "unit": "frames/s",
-            "n_gpus": args.gpus, "steps": steps, "warmup": max(1, args.warmup), "ms_per_step": 1e3 * total / steps, "higher_is_better": True,
+            "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": 1e3 * total / steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32+u64", "data": "synthetic",
             "gtris_per_s": cnt.triangles_instanced * fps / 1e9,
-            "config": {"workload": label, "resolution": [W, H], "meshlet_draws": cnt.draws, "triangles": cnt.triangles_instanced, "passes": 2},
+            "config": config_dict(label, W, H, cnt, 2, builder_note, max(1, args.gpus), "range" if (args.shard == "range" or (args.shard == "auto" and args.config == 5)) else "views"),
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": ncores, "kind": "port",
                              "sample": f"{steps} full two-pass frames of the same camera sweep (CPU oracle, all host threads)"},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -253,30 +306,45 @@ def main():
             stage[sname] += getattr(st, sname)
     barrier()
 
-    # ---- end to end through the C ABI with HOST buffers: per step H2D camera + transforms (the reference re-uploads
-    # both every frame: camera.cpp:180-193, world.cpp:321-344) and D2H of the frame's counters (vkv_stats)
+    # ---- end to end through the C ABI with HOST buffers (pinned): per step H2D camera + transforms (the reference re-uploads
+    # both every frame: camera.cpp:180-193, world.cpp:321-344) and D2H of the frame's counters (vkv_stats); `e2e_readback` adds the
+    # D2H of the whole R32_UINT id image (vkv_read_ids), i.e. "result back on the host" for a CPU consumer
+    import torch
     transforms = np.ascontiguousarray(scene.transforms())
+    pin_tr = torch.from_numpy(transforms.reshape(-1).copy()).pin_memory()
+    pin_cam = torch.zeros(352, dtype=torch.uint8).pin_memory()
+    pin_ids = torch.zeros(W * H, dtype=torch.int32).pin_memory()
+    cam_np = pin_cam.numpy()
     own_cam = r.upload(np.frombuffer(cam.raw(), np.uint8))
     pc.cameraBuffer = own_cam
     h2d = 352 + transforms.nbytes
     d2h = 256
-    barrier()
-    t0 = time.perf_counter()
-    for k in range(steps):
-        cam.look_at(*my_views[1 + (warm + k) % (len(my_views) - 1)])
-        r._ck(r.L.vkv_update(r.h, own_cam, cam.raw(), 352))
-        r._ck(r.L.vkv_update(r.h, pc.transformBuffer, transforms.ctypes.data, transforms.nbytes))
-        r.frame(pc, flags)  # returns vkv_stats: blocking D2H of the counters
-    barrier()
-    e2e_s = time.perf_counter() - t0
+
+    def e2e_loop(n, readback):
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(n):
+            cam.look_at(*my_views[1 + (warm + k) % (len(my_views) - 1)])
+            cam_np[:] = np.frombuffer(cam.raw(), np.uint8)
+            r._ck(r.L.vkv_update(r.h, own_cam, pin_cam.data_ptr(), 352))
+            r._ck(r.L.vkv_update(r.h, pc.transformBuffer, pin_tr.data_ptr(), transforms.nbytes))
+            r.frame(pc, flags)  # returns vkv_stats: blocking D2H of the counters
+            if readback:
+                r._ck(r.L.vkv_read_ids(r.h, pin_ids.data_ptr()))
+        barrier()
+        return time.perf_counter() - t0
+
+    e2e_s = e2e_loop(steps, False)
+    KR = min(steps, 50)
+    e2e_rb_s = e2e_loop(KR, True)
 
     clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
 
     if dist is not None:
         import torch
-        t = torch.tensor([dev_ms, e2e_s], device="cuda", dtype=torch.float64)
+        t = torch.tensor([dev_ms, e2e_s, e2e_rb_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_s = t.tolist()
+        dev_ms, e2e_s, e2e_rb_s = t.tolist()
         ln = torch.tensor([launches, vis_a, vis_b, occ_a], device="cuda", dtype=torch.int64)
         dist.all_reduce(ln)
         launches = int(ln[0].item())
@@ -304,7 +372,8 @@ def main():
         bytes_cull_b = 4 * avg(occ_a) + 12 * avg(occ_a) + U + 4 * avg(vis_b)
         bytes_hiz = 8 * W * H + pyr_bytes  # depth is read fused from the 64-bit visbuffer: 8 B/pixel, not 4
         bytes_clear = 8 * W * H
-        per_meshlet = 48 + 28 * 64 + 3 * 95
+        avg_v, avg_t = meshlet_averages(scene)
+        per_meshlet = 48 + 64 + 28 * avg_v + 3 * avg_t   # headers + transform + (4 B index + 24 B vertex stride) per vertex + 3 B per triangle
         clear_fused = os.environ.get("VKV_SEPARATE_CLEAR", "0") != "1" and cnt.draws > 0 and (W * H) % 2 == 0  # vkv_frame: the clear rides inside the pass-A cull launch (cull.cu), its bytes are that launch's
         if clear_fused:
             bytes_cull_a += bytes_clear
@@ -323,15 +392,13 @@ def main():
             stages[name] = {"ms": round(m, 5), "bytes": int(b), "GB/s": round(gbs, 1), "frac_hbm": round(gbs / hbm, 4)}
         dom = max(stages, key=lambda sname: stages[sname]["ms"])
         traffic = None
-        issue = None
-        try:  # dram bytes per launch (and issue-slot use) of the dominant kernel from the committed `ncu --set full` capture of this workload
+        issue_of = None
+        try:  # dram bytes and warp-instructions per launch of the dominant kernel from the committed `ncu --set full` capture of this workload
             tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            ent = tr.get(f"cfg{args.config}", {}).get(dom)
+            ent = tr.get(f"cfg{args.config}" + ("" if args.meshlets == "meshopt" else "_morton"), {}).get(dom)
             if ent and world == 1:
                 traffic = ent["dram_read_bytes"] + ent["dram_write_bytes"]
-                if "ipc_active" in ent:  # the roofline that actually bounds an issue-bound kernel: warp-instructions per cycle per SM, peak 4
-                    issue = {"ipc_active": ent["ipc_active"], "peak": 4.0, "frac": round(ent["ipc_active"] / 4.0, 3),
-                             "warp_instructions": ent.get("warp_instructions"), "source": ent.get("capture")}
+                issue_of = ent
         except Exception:
             pass
         line = {
@@ -340,21 +407,18 @@ def main():
             "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak" if shard == "views" else "strong", "vs_baseline": None,
             "dtype": "f32+u64", "data": "synthetic",
             "gtris_per_s": cnt.triangles_instanced * fps / 1e9,
-            "config": {"workload": label, "resolution": [W, H], "meshlet_draws": cnt.draws, "triangles": cnt.triangles_instanced,
-                       "passes": 1 if args.one_pass else 2,
-                       "parallelism": (f"views sharded over {world} GPU(s), scene replicated, no collective" if shard == "views" else
-                                       f"one view, MeshletDraw list sharded over {world} GPU(s) in interleaved 2048-draw ranges, u64 min-merge over NVLink peer memory before each HiZ build"),
-                       "l2": "256 MB scratch written between timed frames (L2 flush); each frame timed by its own CUDA event pair",
-                       "stages_from": f"a second pass of {KS} frames with an event after every stage (the frame time above has none inside the frame)",
-                       "visible_a_avg": vis_a / K, "occluded_a_avg": occ_a / K, "visible_b_avg": vis_b / K,
-                       "clear": "fused into the pass-A cull launch (its 8*W*H bytes are counted there)" if clear_fused else "separate launch"},
+            "config": config_dict(label, W, H, cnt, 1 if args.one_pass else 2, builder_note, world, shard),
+            "run": {"stages_from": f"a second pass of {KS} frames with an event after every stage (the frame time above has none inside the frame)",
+                    "visible_a_avg": vis_a / K, "occluded_a_avg": occ_a / K, "visible_b_avg": vis_b / K,
+                    "avg_vertices_per_meshlet": round(avg_v, 2), "avg_triangles_per_meshlet": round(avg_t, 2),
+                    "clear": "fused into the pass-A cull launch (its 8*W*H bytes are counted there)" if clear_fused else "separate launch"},
             "e2e": {"value": frames_total / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "note": "camera + all node transforms uploaded from host every frame, frame counters read back every frame (wall clock, no L2 flush)"},
+                    "note": "camera + all node transforms uploaded from pinned host memory every frame, frame counters read back every frame (wall clock, no L2 flush)"},
+            "e2e_readback": {"value": (world * KR if shard == "views" else KR) / e2e_rb_s, "unit": "frames/s", "steps": KR, "h2d_bytes_per_step": h2d,
+                             "d2h_bytes_per_step": d2h + 4 * W * H,
+                             "note": "as e2e, plus the whole R32_UINT id image copied to pinned host memory every frame (vkv_read_ids): PCIe-bound"},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["GB/s"], "peak": hbm, "unit": "GB/s", "frac": stages[dom]["frac_hbm"],
-                         "traffic": traffic, "issue": issue, "peak_source": peak_src,
-                         "note": "dominant kernel = software rasteriser: SM-issue / L2-atomic bound, working set L2 resident (dram traffic << algorithmic input bytes); "
-                                 "`achieved` = input-side algorithmic bytes (SURVEY §8d) / CUDA-event time; cull / HiZ / clear fractions are in `stages`"},
+            "roofline": roofline(dom, stages, issue_of, hbm, peak_src, traffic, clocks),
             "stages": stages,
             "clocks": clocks,
         }
