@@ -158,6 +158,7 @@ def cpu_frames(scene, W, H, views, nframes, threads=0, warmup=1):
     cam.look_at(*views[0])
     pc = scene.host_push_constants(cam)
     tg = O.Targets(W, H)
+    O.lib().orc_set_diagnostics(0)    # time the path, not the oracle's ambiguity bookkeeping
     for _ in range(max(1, warmup)):   # the first one also fills the pyramid the first timed frame culls against
         O.frame(pc, tg, two_pass=True, threads=threads)
     times = []

@@ -4,9 +4,10 @@
 # Outputs:
 #   oracle/_ref/libmeshopt_ref.so  meshoptimizer @ the reference's pinned submodule (meshopt_buildMeshlets & co, the codecs)
 #   oracle/_ref/libmeshopt_ref_nosimd.so  the same, -DMESHOPTIMIZER_NO_SIMD (scalar decode filters)
-#   oracle/_ref/libref_shim.so     culling.h.glsl:1-30 (isAabbInFrustum, getWorldSpaceAabbExtent) + the shared layout headers
-#                                  compiled as C++ against the reference's glm; camera.cpp:38-48,70-84 (reverseDepth,
-#                                  generateCameraFrustum); glm perspective/lookAt; fastgltf::math translate/rotate/scale.
+#   oracle/_ref/libref_shim.so     culling.h.glsl (isAabbInFrustum, getWorldSpaceAabbExtent, aabbPositions, projectAabb) and
+#                                  visbuffer.task.glsl:57-61 (mip selection) + the shared layout headers compiled as C++ against
+#                                  the reference's glm; camera.cpp:38-48,70-84 (reverseDepth, generateCameraFrustum); glm
+#                                  perspective/lookAt; fastgltf::math translate/rotate/scale.
 # The GLSL task/mesh/fragment/compute shaders themselves cannot be built or run here (no glslang, no Vulkan ICD) — see DESIGN.md.
 set -e
 REF=${REF:-/root/reference}
@@ -28,10 +29,26 @@ printf '#pragma once\n#include <cstdint>\ntypedef std::uint64_t VkDeviceAddress;
 # culling.h.glsl is dual GLSL/C++ up to line 30; the rest (array constructors) is GLSL-only. Compile the C++-valid head in place.
 # The only edit is mechanical: GLSL swizzle `plane.xyz` -> `vec3(plane)` (glm has no .xyz member without MS extensions).
 { sed -n '1,30p' "$REF/shaders/culling.h.glsl" | sed 's/plane\.xyz/vec3(plane)/g'; printf 'GLSL_NAMESPACE_END\n#endif\n'; } > "$TMP/culling_head.h.glsl"
+# culling.h.glsl:31-56 (aabbPositions, projectAabb) is GLSL-only syntax; four mechanical rewrites make it C++ against glm, the
+# arithmetic untouched: the array constructor `vec3[8](...)` -> a braced initialiser, the array return type `vec3[2]` ->
+# std::array<vec3, 2>, the swizzle `clip.xy` -> vec2(clip), `return vec3[2](a, b)` -> `return {a, b}`.
+{ printf '#pragma once\nGLSL_NAMESPACE_BEGIN\n'
+  sed -n '31,56p' "$REF/shaders/culling.h.glsl" | sed \
+    -e 's/const vec3 aabbPositions\[8\] = vec3\[8\](/const vec3 aabbPositions[8] = {/' \
+    -e 's/^);$/};/' \
+    -e 's/^vec3\[2\] projectAabb/inline std::array<vec3, 2> projectAabb/' \
+    -e 's/clip\.xy/vec2(clip)/g' \
+    -e 's/return vec3\[2\](ssMin, ssMax);/return {ssMin, ssMax};/'
+  printf 'GLSL_NAMESPACE_END\n'; } > "$TMP/culling_tail.h.glsl"
+# visbuffer.task.glsl:57-61 (mip selection + sample position) as a function body; two rewrites: `X.xy` -> vec2(X), and max( -> glm::max(
+# (inside namespace glsl both std::max and glm::max are visible on the C++ side; glm::max(x, y) = x < y ? y : x is GLSL's definition)
+{ printf 'GLSL_NAMESPACE_BEGIN\ninline void taskMipAndCenter(const std::array<vec3, 2>& projectedAabb, ivec2 pyramidSize, float& levelOut, vec2& centerOut) {\n'
+  sed -n '57,61p' "$REF/shaders/visbuffer/visbuffer.task.glsl" | sed -e 's/\(projectedAabb\[[01]\]\)\.xy/vec2(\1)/g' -e 's/\bmax(/glm::max(/g'
+  printf '\tlevelOut = level; centerOut = projectedCenter;\n}\nGLSL_NAMESPACE_END\n'; } > "$TMP/task_lines.inc"
 # camera.cpp free functions reverseDepth (38-48) and generateCameraFrustum (70-84)
 { printf '#define ZoneScoped\n#include <array>\n#include <glm/glm.hpp>\n'; sed -n '38,48p;70,84p' "$REF/src/vk_gltf_viewer/camera.cpp"; } > "$TMP/camera_fns.inc"
 
-$CXX -std=c++20 -O2 -fPIC -shared -ffp-contract=off \
+$CXX -std=c++20 -O2 -fPIC -shared -ffp-contract=off -pthread \
     -I"$TMP" -I"$REF/shaders" -I"$REF/submodules/glm" -I"$REF/submodules/fastgltf/include" \
     -o "$OUT/libref_shim.so" "$HERE/ref_shim.cpp"
 echo "built: $(ls "$OUT")"

@@ -123,6 +123,15 @@ struct Pyr {
 	uint32_t levels, off[17], w[16], h[16], total;
 };
 
+// Diagnostics (the ORC_AMBIG_* flags) cost about as much again as the decision itself; bench.py's timed CPU baseline switches
+// them off (orc_set_diagnostics(0)) so that the baseline measures the path, not the bookkeeping.
+bool g_diagnostics = true;
+
+// How far a DIFFERENT but equally valid evaluation of the same GLSL (another association order of the mat4*vec4 sums, an
+// FMA-contracting compiler) can move a result: kNoise relative roundings of the LARGEST term of each sum, propagated to first
+// order.  A result closer than that to one of the shader's thresholds is "ambiguous": flagged, never silently decided.
+constexpr float kNoise = 8.0f * 5.9604645e-8f;   // 8 roundings of 2^-24
+
 // visbuffer.task.glsl:44-65 for one MeshletDraw
 uint8_t cull_one(const vkv_VisbufferPushConstants* pc, uint32_t drawIdx, const vkv_Camera& cam, const float* occVP,
                  const Pyr& pyr, const float* pyramid) {
@@ -134,6 +143,7 @@ uint8_t cull_one(const vkv_VisbufferPushConstants* pc, uint32_t drawIdx, const v
 	const vkv_Primitive& prim = prims[d.primitiveIndex];                        // :46
 	const vkv_Meshlet& ml = ((const vkv_Meshlet*)prim.meshletBuffer)[d.meshletIndex]; // :47
 	uint8_t flags = 0;
+	const bool diag = g_diagnostics;
 
 	// :50  worldAabbCenter = (T * vec4(center,1)).xyz
 	V4 wc4 = mul44(T, V4{ml.aabbCenter[0], ml.aabbCenter[1], ml.aabbCenter[2], 1.0f});
@@ -144,18 +154,31 @@ uint8_t cull_one(const vkv_VisbufferPushConstants* pc, uint32_t drawIdx, const v
 	we.x = (std::fabs(T[0]) * e.x + std::fabs(T[4]) * e.y) + std::fabs(T[8]) * e.z;
 	we.y = (std::fabs(T[1]) * e.x + std::fabs(T[5]) * e.y) + std::fabs(T[9]) * e.z;
 	we.z = (std::fabs(T[2]) * e.x + std::fabs(T[6]) * e.y) + std::fabs(T[10]) * e.z;
+	// rounding noise of a corner coordinate per axis: the terms of the centre's sum plus the extent
+	float posErr[3] = {0.f, 0.f, 0.f};
+	if (diag) {
+		const float c[3] = {ml.aabbCenter[0], ml.aabbCenter[1], ml.aabbCenter[2]};
+		const float w3[3] = {we.x, we.y, we.z};
+		for (int r = 0; r < 3; ++r)
+			posErr[r] = kNoise * (((std::fabs(T[r] * c[0]) + std::fabs(T[4 + r] * c[1])) + std::fabs(T[8 + r] * c[2])) + std::fabs(T[12 + r]) + w3[r]);
+	}
 
 	// :52 -> culling.h.glsl:8-19
 	for (int i = 0; i < 6; ++i) {
 		const float* p = cam.frustum[i];
 		float radius = dot3(we, V3{std::fabs(p[0]), std::fabs(p[1]), std::fabs(p[2])});
 		float distance = dot3(V3{p[0], p[1], p[2]}, wc) - p[3];
-		if (near_rel(-radius, distance, 4.0f)) flags |= ORC_AMBIG_FRUSTUM;
+		if (diag) {
+			const float terms = ((std::fabs(p[0] * wc.x) + std::fabs(p[1] * wc.y)) + std::fabs(p[2] * wc.z)) + std::fabs(p[3]) + std::fabs(radius);
+			const float moved = (std::fabs(p[0]) * posErr[0] + std::fabs(p[1]) * posErr[1]) + std::fabs(p[2]) * posErr[2];
+			if (std::fabs(-radius - distance) <= kNoise * terms + moved) flags |= ORC_AMBIG_FRUSTUM;
+		}
 		if (-radius > distance) return ORC_FRUSTUM_CULLED | flags;
 	}
 
 	// :56 -> culling.h.glsl:44-56
 	V3 ssMin{1.f, 1.f, 1.f}, ssMax{-1.f, -1.f, -1.f};
+	float uvErr = 0.f, zErr = 0.f;   // noise of any corner's uv / depth (first order)
 	for (int i = 0; i < 8; ++i) {
 		V4 pos{kAabbPositions[i][0] * we.x + wc.x, kAabbPositions[i][1] * we.y + wc.y, kAabbPositions[i][2] * we.z + wc.z, 1.0f};
 		V4 clip = mul44(occVP, pos);
@@ -165,6 +188,19 @@ uint8_t cull_one(const vkv_VisbufferPushConstants* pc, uint32_t drawIdx, const v
 		float uvx = ndcx * 0.5f + 0.5f;
 		float uvy = ndcy * 0.5f + 0.5f;
 		float z = clip.z / clip.w;
+		if (diag) {
+			float cerr[4];
+			for (int r = 0; r < 4; ++r) {
+				const float terms = ((std::fabs(occVP[r] * pos.x) + std::fabs(occVP[4 + r] * pos.y)) + std::fabs(occVP[8 + r] * pos.z)) + std::fabs(occVP[12 + r]);
+				const float moved = (std::fabs(occVP[r]) * posErr[0] + std::fabs(occVP[4 + r]) * posErr[1]) + std::fabs(occVP[8 + r]) * posErr[2];
+				cerr[r] = kNoise * terms + moved;
+			}
+			const float iw = 1.0f / std::fabs(clip.w);
+			const float ex = (cerr[0] + std::fabs(clip.x * iw) * cerr[3]) * iw, ey = (cerr[1] + std::fabs(clip.y * iw) * cerr[3]) * iw;
+			const float ez = (cerr[2] + std::fabs(z) * cerr[3]) * iw + kNoise * std::fabs(z);
+			uvErr = std::fmax(uvErr, 0.5f * std::fmax(ex, ey) + kNoise);
+			zErr = std::fmax(zErr, ez);
+		}
 		ssMin.x = gmin(ssMin.x, uvx); ssMin.y = gmin(ssMin.y, uvy); ssMin.z = gmin(ssMin.z, z);
 		ssMax.x = gmax(ssMax.x, uvx); ssMax.y = gmax(ssMax.y, uvy); ssMax.z = gmax(ssMax.z, z);
 	}
@@ -174,24 +210,34 @@ uint8_t cull_one(const vkv_VisbufferPushConstants* pc, uint32_t drawIdx, const v
 	float m = gmax(width, height);
 	// floor(log2(m)) as the exact binary exponent; the sampler clamps lod to [minLod,maxLod]=[0,16] and to
 	// the existing mips (application.cpp:451-452).  NaN / <=0 -> level 0 ; +inf -> last mip.
-	int level;
-	if (!(m > 0.0f)) level = 0;
-	else if (std::isinf(m)) level = 16;
-	else {
-		level = std::ilogb(m);
-		float up = std::nextafter(std::nextafter(m, INFINITY), INFINITY);
-		if (std::ilogb(up) != level) flags |= ORC_AMBIG_LEVEL;
-		if (level < 0) level = 0;
-		if (level > 16) level = 16;
+	auto level_of = [&](float v) {
+		int l;
+		if (!(v > 0.0f)) l = 0;
+		else if (std::isinf(v)) l = 16;
+		else { l = std::ilogb(v); if (l < 0) l = 0; if (l > 16) l = 16; }
+		if (l > (int)pyr.levels - 1) l = (int)pyr.levels - 1;
+		return l;
+	};
+	const int level = level_of(m);
+	if (diag) {
+		// SURVEY Q6 (an implementation's log2 may round up just below a power of two) and the noise of the extent itself
+		const float mErr = 2.0f * uvErr * (float)(int)std::max(pyr.w[0], pyr.h[0]) + 2.0f * 1.1920929e-7f * std::fabs(m);
+		if (level_of(m + mErr) != level || level_of(m - mErr) != level) flags |= ORC_AMBIG_LEVEL;
 	}
-	if (level > (int)pyr.levels - 1) level = (int)pyr.levels - 1;
 	// :61-62
 	float cx = (ssMin.x + ssMax.x) * 0.5f;
 	float cy = (ssMin.y + ssMax.y) * 0.5f;
 	int amb = 0;
 	float depth = sample_min(pyramid + pyr.off[level], pyr.w[level], pyr.h[level], cx, cy, &amb);
-	if (amb) flags |= ORC_AMBIG_FOOTPRINT;
-	if (near_rel(depth, ssMax.z, 4.0f)) flags |= ORC_AMBIG_HIZ;
+	if (diag) {
+		// the footprint {floor(u), floor(u)+1} changes when u = c*size - 0.5 moves across an integer
+		auto crosses = [&](float c, uint32_t size) {
+			const float u = c * (float)size - 0.5f, du = uvErr * (float)size + 4.0f * 1.1920929e-7f * std::fabs(u) + 1e-6f;
+			return std::floor(u - du) != std::floor(u + du) || u - std::floor(u) == 0.0f;
+		};
+		if (amb || crosses(cx, pyr.w[level]) || crosses(cy, pyr.h[level])) flags |= ORC_AMBIG_FOOTPRINT;
+		if (std::fabs(depth - ssMax.z) <= zErr + 4.0f * 1.1920929e-7f * std::fmax(std::fabs(depth), std::fabs(ssMax.z))) flags |= ORC_AMBIG_HIZ;
+	}
 	// :64
 	bool visible = depth < ssMax.z;
 	return (visible ? ORC_VISIBLE : ORC_OCCLUDED) | flags;
@@ -421,6 +467,8 @@ uint32_t orc_pyramid_layout(uint32_t W, uint32_t H, uint32_t offsets[17], uint32
 	if (total) *total = off;
 	return levels;
 }
+
+void orc_set_diagnostics(int on) { g_diagnostics = on != 0; }
 
 float orc_sample_min(const float* img, uint32_t w, uint32_t h, float u, float v, int* ambig) {
 	return sample_min(img, w, h, u, v, ambig);

@@ -4,14 +4,17 @@
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it,
  * and only as the checker (or as the timed CPU baseline), never on the product path.
  *
- * PARITY UNPINNED for cull / raster / HiZ: the reference ships no tests, golden images or
- * known-answer vectors for these stages, and its shaders cannot be run in
- * this image (no Vulkan loader / lavapipe / glslang).  What *is* pinned:
- *   - culling.h.glsl:8-29 (isAabbInFrustum, getWorldSpaceAabbExtent) compile as C++ against the
- *     reference's glm; oracle/build_ref.sh builds them into oracle/_ref/ and
- *     tests/test_oracle_vs_ref.py checks this restatement against them bit-for-bit;
- *   - the data layouts (include/vkv_abi.h static_asserts == the reference headers compiled as C++);
- *   - meshoptimizer / glm used as input generators from the reference's pinned submodules.
+ * PARITY UNPINNED for the sampler footprint rule, raster and HiZ outputs: the reference ships no tests, golden images or
+ * known-answer vectors for these stages, and its shaders cannot be run in this image (no Vulkan loader /
+ * lavapipe / glslang).  What IS pinned against the reference's own text, compiled as C++ against its glm by
+ * oracle/build_ref.sh into oracle/_ref/ (tests/test_oracle.py):
+ *   - the whole per-draw decision of the task shader except the texture fetch: culling.h.glsl (isAabbInFrustum,
+ *     getWorldSpaceAabbExtent, aabbPositions, projectAabb), visbuffer.task.glsl:50-52,56-61,64 — on every MeshletDraw of all
+ *     five BASELINE configs at full size the oracle's class differs from the glm-evaluated reference only on draws it flags
+ *     ORC_AMBIG_* / ORC_CROSSES_CAMERA (0-7 draws in 10 M, all flagged);
+ *   - the data layouts (include/vkv_abi.h static_asserts == the reference headers compiled as C++), packVisBuffer;
+ *   - camera.cpp's reverseDepth / generateCameraFrustum, glm perspective / lookAt, fastgltf::math node matrices, fastgltf's
+ *     convertComponent; meshoptimizer's codecs, scan partition, buildMeshlets / optimizeMeshlet / computeMeshletBounds.
  *
  * Arithmetic policy, compiled with -ffp-contract=off and no fast-math:
  *   fp32 round-to-nearest, no FMA contraction;
@@ -44,9 +47,9 @@ enum {
 	/* diagnostic flags (ambiguous = a comparison within a few ulp of its threshold; excluded-and-counted class) */
 	ORC_AMBIG_FRUSTUM = 1 << 2,
 	ORC_AMBIG_HIZ = 1 << 3,
-	ORC_AMBIG_LEVEL = 1 << 4,   /* max(w,h) within 2 ulp below a power of two */
+	ORC_AMBIG_LEVEL = 1 << 4,   /* max(w,h) within rounding noise of a power of two */
 	ORC_CROSSES_CAMERA = 1 << 5, /* some AABB corner has clip.w <= 0 */
-	ORC_AMBIG_FOOTPRINT = 1 << 6 /* sampler frac within 1e-4 of 0 */
+	ORC_AMBIG_FOOTPRINT = 1 << 6 /* sample position within rounding noise of a texel-footprint change (or frac within 1e-4 of 0) */
 };
 
 typedef struct orc_counters {
@@ -56,6 +59,13 @@ typedef struct orc_counters {
 	uint64_t meshlets, triangles_in, triangles_culled_facing, triangles_rejected, triangles_clipped,
 	         triangles_degenerate, triangles_rasterised, fragments, fragments_passed, tie_pixels;
 } orc_counters;
+
+/* The ORC_AMBIG_* flags say "a different but equally valid evaluation of the same GLSL could decide this draw differently":
+ * every threshold comparison of the task shader is checked against the first-order rounding noise of its inputs (8 roundings of
+ * the largest term of each mat4*vec4 sum, propagated through the divide).  tests/test_oracle.py holds the oracle to that
+ * definition against the reference's shader text compiled with glm, which associates those sums differently.
+ * on = 0 skips the bookkeeping (the timed CPU baseline); decisions are unaffected. */
+void orc_set_diagnostics(int on);
 
 /* Pyramid storage: one contiguous float array, mip k at offsets[k], extent w[k] x h[k].
  * Returns mipLevels (application.cpp:472-473); total floats in *total. */

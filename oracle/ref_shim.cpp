@@ -13,7 +13,14 @@
 #include "mesh_common.h.glsl"          // reference: glsl::Camera, Meshlet, Vertex, MeshletDraw, Primitive, Material
 #include "visbuffer/visbuffer.h.glsl"  // reference: glsl::VisbufferPushConstants, packVisBuffer
 #include "culling_head.h.glsl"         // reference: culling.h.glsl:1-30 (generated slice, see build_ref.sh)
+#include "culling_tail.h.glsl"         // reference: culling.h.glsl:31-56 aabbPositions + projectAabb (generated slice, array syntax rewritten)
+#include "task_lines.inc"              // reference: visbuffer.task.glsl:57-61 mip selection + sample position (generated slice)
 #include "camera_fns.inc"              // reference: camera.cpp reverseDepth + generateCameraFrustum
+
+#include <atomic>
+#include <cmath>
+#include <thread>
+#include <vector>
 
 #include <fastgltf/math.hpp>
 
@@ -41,6 +48,69 @@ void ref_transform_point(const float m[16], const float p[3], float out[3]) {
 	std::memcpy(&t, m, 64);
 	glm::vec4 r = t * glm::vec4(p[0], p[1], p[2], 1.0f);
 	out[0] = r.x; out[1] = r.y; out[2] = r.z;
+}
+
+// culling.h.glsl:44-56 alone
+void ref_project_aabb(const float c[3], const float e[3], const float vp[16], float out[6]) {
+	glm::mat4 m;
+	std::memcpy(&m, vp, 64);
+	auto r = glsl::projectAabb(glm::vec3(c[0], c[1], c[2]), glm::vec3(e[0], e[1], e[2]), m);
+	out[0] = r[0].x; out[1] = r[0].y; out[2] = r[0].z; out[3] = r[1].x; out[4] = r[1].y; out[5] = r[1].z;
+}
+
+// The task shader's per-draw decision (visbuffer.task.glsl:44-64) evaluated with the REFERENCE's code as glm evaluates it on the
+// C++ side: transform * vec4(center, 1), getWorldSpaceAabbExtent, isAabbInFrustum, projectAabb and the mip-selection lines are
+// the reference's own text.  Only the texture fetch is not reference code: `sample` is the oracle's min-sampler
+// (orc_sample_min), and the lod clamp follows the sampler state (application.cpp:451-452: lod in [0,16], then existing mips;
+// NaN -> 0).  status[i] = 0 frustum-culled, 1 occluded, 2 visible — the oracle's ORC_* values.
+// NOTE glm pairs the adds of mat4*vec4 as (c0x + c1y) + (c2z + c3w); the oracle's policy is left to right.  The two evaluations
+// may therefore differ in the last bits, which is exactly what the oracle's ORC_AMBIG_* / ORC_CROSSES_CAMERA flags are for.
+typedef float (*ref_sample_fn)(const float* img, uint32_t w, uint32_t h, float u, float v, int* ambig);
+void ref_task_cull(const glsl::VisbufferPushConstants* pc, const float* pyramid, const uint32_t* mipOff, const uint32_t* mipW, const uint32_t* mipH,
+                   uint32_t levels, int vp_select, ref_sample_fn sample, uint8_t* status, int threads) {
+	const auto* draws = reinterpret_cast<const glsl::MeshletDraw*>(pc->drawBuffer);
+	const auto* transforms = reinterpret_cast<const glm::mat4*>(pc->transformBuffer);
+	const auto* prims = reinterpret_cast<const glsl::Primitive*>(pc->primitiveBuffer);
+	const glsl::Camera camera = *reinterpret_cast<const glsl::Camera*>(pc->cameraBuffer);
+	const glm::ivec2 pyramidSize((int)mipW[0], (int)mipH[0]);
+	const uint32_t N = pc->meshletDrawCount;
+	std::atomic<uint32_t> next{0};
+	auto work = [&]() {
+		for (;;) {
+			const uint32_t b = next.fetch_add(4096);
+			if (b >= N) break;
+			const uint32_t e = b + 4096 < N ? b + 4096 : N;
+			for (uint32_t i = b; i < e; ++i) {
+				const glsl::MeshletDraw draw = draws[i];
+				const glm::mat4 transformMatrix = transforms[draw.transformIndex];
+				const glsl::Primitive& primitive = prims[draw.primitiveIndex];
+				const glsl::Meshlet meshlet = reinterpret_cast<const glsl::Meshlet*>(primitive.meshletBuffer)[draw.meshletIndex];
+				const glm::vec3 worldAabbCenter = glm::vec3(transformMatrix * glm::vec4(meshlet.aabbCenter, 1.0f));              // task.glsl:50
+				const glm::vec3 worldAabbExtent = glsl::getWorldSpaceAabbExtent(meshlet.aabbExtents, transformMatrix);          // :51
+				glm::vec4 fr[6];
+				for (int k = 0; k < 6; ++k) fr[k] = camera.frustum[k];
+				bool visible = glsl::isAabbInFrustum(worldAabbCenter, worldAabbExtent, fr);                                      // :52
+				if (!visible) { status[i] = 0; continue; }
+				const auto projectedAabb = glsl::projectAabb(worldAabbCenter, worldAabbExtent,
+				                                             vp_select ? camera.viewProjection : camera.prevOcclusionViewProjection);      // :56
+				float level;
+				glm::vec2 center;
+				glsl::taskMipAndCenter(projectedAabb, pyramidSize, level, center);                                                 // :57-61
+				int lod = 0;
+				if (level == level) { const float cl = level < 0.f ? 0.f : (level > 16.f ? 16.f : level); lod = (int)cl; }
+				if (lod > (int)levels - 1) lod = (int)levels - 1;
+				const float depth = sample(pyramid + mipOff[lod], mipW[lod], mipH[lod], center.x, center.y, nullptr);          // :62
+				visible = visible && depth < projectedAabb[1].z;                                                                   // :64
+				status[i] = visible ? 2 : 1;
+			}
+		}
+	};
+	int nt = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+	if (nt < 1) nt = 1;
+	std::vector<std::thread> pool;
+	for (int t = 1; t < nt; ++t) pool.emplace_back(work);
+	work();
+	for (auto& t : pool) t.join();
 }
 
 uint32_t ref_pack_visbuffer(uint32_t drawIndex, uint32_t primitiveId) { return glsl::packVisBuffer(drawIndex, primitiveId); }

@@ -178,17 +178,17 @@ def test_city_cfg4_full_size():
 
 def test_lattice_cfg5_full_size():
     """BASELINE config 5 at full size on ONE GPU: 22x22x21 instances (10,164) of the 100,352-triangle patch = 1.02 billion
-    triangles, 15.1 M MeshletDraws (of the 2^25 the 25-bit draw index allows), 7680x4320 (12 pyramid mips), two frames, two-pass —
+    triangles, 10.8 M MeshletDraws with the reference's meshlet partition (of the 2^25 the 25-bit draw index allows), 7680x4320 (12 pyramid mips), two frames, two-pass —
     bit-exact against the oracle.  (The 8-GPU range-sharded form of the same scene is bench.py --config 5 --gpus 8; its merge is
     checked in tests/test_multigpu.py.)"""
     s = Scene.lattice(22, 22, 21, 224, 0x5EED0003)
     assert s.counts().triangles_instanced > 1_000_000_000 and s.counts().draws < (1 << 25)
     summ = run_views(s, 7680, 4320, [s.default_view(i, 64) for i in (0, 1)], two_pass=True)
-    assert summ[1][1] > 10_000_000
+    assert summ[1][1] > 0.9 * s.counts().draws  # the second frame is occlusion-culled hard
 
 
 def test_lattice_cfg3_full_size():
-    """BASELINE config 3 at full size — 10x10x10 instances of a 100,352-triangle patch (1.49 M MeshletDraws, 100.35 M triangles),
+    """BASELINE config 3 at full size — 10x10x10 instances of a 100,352-triangle patch (1.06 M MeshletDraws, 100.35 M triangles),
     3840x2160, two-pass: bit-exact against the oracle (the multithreaded CPU port needs about half a second per frame), plus the
     size-independent properties of the path: disjoint pass lists, pass B drawn from pass A's rejects, every visbuffer id owned by
     a surviving draw, and bit-identical results when the sequence is rendered again in a fresh context."""
@@ -197,7 +197,7 @@ def test_lattice_cfg3_full_size():
     W, H = 3840, 2160
     views = [s.default_view(i, 64) for i in (0, 1)]
     summ = run_views(s, W, H, views, two_pass=True)
-    assert summ[1][1] > 1_000_000  # the second frame is occlusion-culled hard
+    assert summ[1][1] > 0.8 * s.counts().draws  # the second frame is occlusion-culled hard
     # determinism: the same sequence in a second context gives the same bits (64-bit atomicMin is order independent, the lists are sets)
     finals = []
     for rep in range(2):
