@@ -59,6 +59,25 @@ def main():
         nA = torch.tensor([r.read_visible(0).size, r.read_visible(1).size], device="cuda")
         dist.all_reduce(nA)
         assert nA.tolist() == [out["visibleA"].size, out["visibleB"].size]
+    if mode == "p2p":
+        # a resize detaches the peers (the visbuffer is reallocated); re-export + re-attach must start from a clean
+        # barrier state (stale epochs in the flag slots would let every barrier pass at once) — the next merged frames must still
+        # be bit-exact
+        dist.barrier()
+        r.resize(W, H)
+        multigpu.attach_peers(r, dist)
+        tg = O.Targets(W, H)   # vkv_resize restarts the pyramid from its cleared state
+        cam = Camera(W, H).look_at(*views[0])
+        r.update_camera(pc_dev, cam)
+        pc_host = scene.host_push_constants(cam)
+        for k, (eye, center) in enumerate(views[:2]):
+            if k:
+                cam.look_at(eye, center)
+                r.update_camera(pc_dev, cam)
+            O.frame(pc_host, tg, two_pass=True)
+            r.frame(pc_dev, api.FRAME_TWO_PASS | api.FRAME_MERGE)
+            assert np.array_equal(r.read_visbuffer64(), tg.vis64()), f"rank {rank}: merged visbuffer differs after resize + re-attach (view {k})"
+            assert np.array_equal(r.read_pyramid().view(np.uint32), tg.pyramid.view(np.uint32))
     r.ipc_detach()
     r.close()
     dist.barrier()

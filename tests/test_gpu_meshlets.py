@@ -129,3 +129,21 @@ def test_argument_validation():
     out = r.build_meshlets(inp)
     assert out[0]["meshlet_count"] == 0
     r.close()
+
+
+def test_out_of_range_index_is_rejected_before_any_vertex_is_read():
+    """vkv_build_meshlets range-checks the indices on the device when vertex_count is given (untrusted glTF) and fails
+    with VKV_ERR_INVALID; vertex_count == 0 skips the check"""
+    r = api.Renderer(64, 64)
+    pos = np.zeros((10, 6), np.float32)
+    idx = np.array([0, 1, 2, 2, 3, 11, 4, 5, 6], np.uint32)   # 11 >= 10 vertices
+    inp = np.zeros(1, abi.MESHLET_BUILD_INPUT_DTYPE)
+    inp["indices"] = r.upload(idx); inp["vertices"] = r.upload(pos); inp["index_count"] = idx.size; inp["vertex_count"] = 10
+    with pytest.raises(api.VkvError) as e:
+        r.build_meshlets(inp)
+    assert e.value.code == -2 and "index" in str(e.value)
+    idx[5] = 9
+    inp["indices"] = r.upload(idx)
+    out = r.build_meshlets(inp)
+    assert out["meshlet_count"][0] == 1
+    r.close()

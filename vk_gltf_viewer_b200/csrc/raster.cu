@@ -39,10 +39,11 @@ constexpr int kBigMinStamps = VKV_BIG_MIN_STAMPS;  // bbox of >= this many 8x4 s
 #define VKV_RASTER_BATCH 4
 #endif
 #ifndef VKV_RASTER_MIN_BLOCKS
-#define VKV_RASTER_MIN_BLOCKS 2
+#define VKV_RASTER_MIN_BLOCKS 4
 #endif
 constexpr int kBatch = VKV_RASTER_BATCH;           // meshlets fetched per work-stealing grab
-constexpr int kMinBlocks = VKV_RASTER_MIN_BLOCKS;  // 128 registers, no spills, 16 warps / SM (measured: 24 warps at 80 registers spill and are slower)
+constexpr int kMinBlocks = VKV_RASTER_MIN_BLOCKS;  // blocks of 8 warps per SM the hot kernel is compiled for
+constexpr int kDrainThreads = 256;
 
 // what one lane fetches for one meshlet of a batch (mesh.glsl:31-36 resolved to addresses)
 struct alignas(16) MeshletHdr {
@@ -64,10 +65,9 @@ struct WarpScratch {
 	uint32_t tri_words[2][96];       // cp.async landing zone (double buffered): up to 124*3 = 372 index bytes
 	uint32_t surv[128];              // phase-1 survivors: ia | ib << 8 | ic << 16 | triangle << 24 | needsClip << 31
 	float2 mvp2[4][4];               // cp.async landing zone: mvp[row][column], every element twice (f32x2 operand for two vertices)
-	Tri sub[8];
 	MeshletHdr hdr[kBatch];
-	int nsub;
 };
+struct SlowScratch { Tri sub[8]; int nsub; }; // the overflow re-walk's clipper output (raster_big_kernel only)
 
 enum { F_NEEDS_CLIP = 64, F_NAN = 128 };
 
@@ -308,17 +308,34 @@ __global__ void prepare_transforms_kernel(const float* __restrict__ transforms, 
 		transform_prologue(transforms + (size_t)t * 16, sVP, mvpOut + (size_t)t * 16, detNeg + t);
 }
 
-__global__ void __launch_bounds__(kThreads, kMinBlocks) raster_kernel(const RasterParams p) {
-	__shared__ WarpScratch scratch[kWarpsPerBlock];
-	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	WarpScratch& ws = scratch[warp];
+// Append a triangle that needs the clipper to the clip queue (one lane).  false = queue full.
+__device__ __forceinline__ bool push_clip(const RasterParams& p, const float4& A, const float4& B, const float4& C, uint32_t id) {
+	if (*(volatile uint32_t*)p.clipCount >= p.clipCap) return false; // keeps the counter from running away once full
+	const uint32_t slot = atomicAdd(p.clipCount, 1u);
+	if (slot >= p.clipCap) return false;
+	ClipTri c;
+	c.a = A; c.b = B; c.c = C; c.id = id; c.pad[0] = c.pad[1] = c.pad[2] = 0;
+	p.clip[slot] = c;
+	return true;
+}
+
+// The meshlet loop, in two instantiations of the same text:
+//   kHot = true   raster_kernel.  Everything a lane can finish alone — vertex transform, facing cull, set-up, the lane-serial
+//                 scan of small triangles.  What it cannot (triangles that need the clipper, triangles larger than the serial
+//                 limit) is QUEUED for raster_big_kernel, so neither the clipper's stack arrays nor the cooperative scan's
+//                 64-bit edge functions count against this kernel's registers: 3 blocks of 8 warps per SM instead of 2.
+//   kHot = false  the overflow re-walk inside raster_big_kernel (only when a queue was full): the same loop, skipping what the
+//                 hot kernel already drew and clipping / scanning everything else in place.  A triangle drawn twice is harmless:
+//                 the visibility write is an atomic min.
+template <bool kHot>
+__device__ __forceinline__ void meshlet_loop(const RasterParams& p, WarpScratch& ws, SlowScratch* slow, uint32_t* __restrict__ workCursor, uint32_t lane) {
 	const uint32_t count = __ldg(p.count);
 	const float hw = (float)p.W * 0.5f, hh = (float)p.H * 0.5f;
 	const uint32_t below = (1u << lane) - 1u;
 
 	for (;;) {
 		uint32_t base = 0;
-		if (lane == 0) base = atomicAdd(p.work, (uint32_t)kBatch);
+		if (lane == 0) base = atomicAdd(workCursor, (uint32_t)kBatch);
 		base = __shfl_sync(0xffffffffu, base, 0);
 		if (base >= count) break;
 		const uint32_t nb = min((uint32_t)kBatch, count - base);
@@ -489,13 +506,13 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) raster_kernel(const Rast
 			// phase 2: survivors only — edge setup and rasterisation
 			for (uint32_t sbase = 0; sbase < nSurv; sbase += 32) {
 				const uint32_t s = sbase + lane;
-				int kind = 0; // 0 nothing, 1 serial, 2 cooperative, 3 clip
+				int kind = 0; // 0 nothing, 1 lane-serial, 2 larger than the serial limit, 3 needs the clipper
 				Tri tri;
-				uint32_t entry = 0;
+				uint32_t entry = 0, id = 0;
 				if (s < nSurv) {
 					entry = ws.surv[s];
 					const uint32_t ia = entry & 0xffu, ib = (entry >> 8) & 0xffu, ic = (entry >> 16) & 0xffu;
-					const uint32_t id = (drawId << VKV_TRIANGLE_BITS) | ((entry >> 24) & 0x7fu); // frag.glsl:36
+					id = (drawId << VKV_TRIANGLE_BITS) | ((entry >> 24) & 0x7fu); // frag.glsl:36
 					if (entry & 0x80000000u) kind = 3;
 					else {
 						const int4 a = ws.scr[ia], b = ws.scr[ib], c = ws.scr[ic];
@@ -503,33 +520,34 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) raster_kernel(const Rast
 							kind = (tri.small && tri.xmax - tri.xmin < kSerialMaxDim && tri.ymax - tri.ymin < kSerialMaxDim) ? 1 : 2;
 					}
 				}
-				if (kind == 1) raster_serial(tri, p.vis, p.W);
-				if (kind == 2 && is_big(tri) && push_big(p, tri)) kind = 0; // deferred to raster_big_kernel
-				uint32_t coop = __ballot_sync(0xffffffffu, kind >= 2);
-				while (coop) {
-					const int src = __ffs(coop) - 1;
-					coop &= coop - 1;
-					if ((int)lane == src) {
-						if (kind == 2) { ws.sub[0] = tri; ws.nsub = 1; }
-						else {
-							const uint32_t ia = entry & 0xffu, ib = (entry >> 8) & 0xffu, ic = (entry >> 16) & 0xffu;
-							const float4 A = ws.cxyw[ia], B = ws.cxyw[ib], C = ws.cxyw[ic];
-							int n = clip_and_setup(make_float4(A.x, A.y, ws.cz[ia], A.z), make_float4(B.x, B.y, ws.cz[ib], B.z),
-							                       make_float4(C.x, C.y, ws.cz[ic], C.z),
-							                       (drawId << VKV_TRIANGLE_BITS) | ((entry >> 24) & 0x7fu), p.W, p.H, ws.sub);
-							int kept = 0; // clipped pieces are often the largest triangles of a scene: defer those too
-							for (int k = 0; k < n; ++k) {
-								if (is_big(ws.sub[k]) && push_big(p, ws.sub[k])) continue;
-								if (kept != k) ws.sub[kept] = ws.sub[k];
-								++kept;
-							}
-							ws.nsub = kept;
-						}
+				if (kHot) {
+					if (kind == 1) raster_serial(tri, p.vis, p.W);
+					else if (kind == 2) { if (!push_big(p, tri)) *p.overflow = 1u; }
+					else if (kind == 3) {
+						const uint32_t ia = entry & 0xffu, ib = (entry >> 8) & 0xffu, ic = (entry >> 16) & 0xffu;
+						const float4 A = ws.cxyw[ia], B = ws.cxyw[ib], C = ws.cxyw[ic];
+						if (!push_clip(p, make_float4(A.x, A.y, ws.cz[ia], A.z), make_float4(B.x, B.y, ws.cz[ib], B.z), make_float4(C.x, C.y, ws.cz[ic], C.z), id))
+							*p.overflow = 1u;
 					}
-					__syncwarp();
-					const int n = ws.nsub;
-					for (int k = 0; k < n; ++k) raster_coop(ws.sub[k], p.vis, p.W, lane, ws.sub[k].xmin, ws.sub[k].xmax, ws.sub[k].ymin, ws.sub[k].ymax);
-					__syncwarp();
+				} else { // overflow re-walk: everything the hot kernel did NOT draw itself, in place, one triangle at a time
+					uint32_t todo = __ballot_sync(0xffffffffu, kind >= 2);
+					while (todo) {
+						const int src = __ffs(todo) - 1;
+						todo &= todo - 1;
+						if ((int)lane == src) {
+							if (kind == 2) { slow->sub[0] = tri; slow->nsub = 1; }
+							else {
+								const uint32_t ia = entry & 0xffu, ib = (entry >> 8) & 0xffu, ic = (entry >> 16) & 0xffu;
+								const float4 A = ws.cxyw[ia], B = ws.cxyw[ib], C = ws.cxyw[ic];
+								slow->nsub = clip_and_setup(make_float4(A.x, A.y, ws.cz[ia], A.z), make_float4(B.x, B.y, ws.cz[ib], B.z),
+								                            make_float4(C.x, C.y, ws.cz[ic], C.z), id, p.W, p.H, slow->sub);
+							}
+						}
+						__syncwarp();
+						const int n = slow->nsub;
+						for (int k = 0; k < n; ++k) raster_coop(slow->sub[k], p.vis, p.W, lane, slow->sub[k].xmin, slow->sub[k].xmax, slow->sub[k].ymin, slow->sub[k].ymax);
+						__syncwarp();
+					}
 				}
 			}
 			__syncwarp();
@@ -537,13 +555,67 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) raster_kernel(const Rast
 	}
 }
 
-// Drain of the large-triangle queue: one warp per (triangle, 128x64-pixel tile) work item.
-__global__ void __launch_bounds__(256) raster_big_kernel(const RasterParams p) {
-	__shared__ Tri sTri[8];
+__global__ void __launch_bounds__(kThreads, kMinBlocks) raster_kernel(const RasterParams p) {
+	__shared__ WarpScratch scratch[kWarpsPerBlock];
+	meshlet_loop<true>(p, scratch[threadIdx.x >> 5], nullptr, p.work, threadIdx.x & 31);
+}
+
+// Grid barrier of the drain kernel (all its blocks are co-resident: the launch sizes the grid from the occupancy query).
+__device__ __forceinline__ void drain_grid_barrier(uint32_t* counter) {
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		__threadfence();
+		atomicAdd(counter, 1u);
+		while (*(volatile uint32_t*)counter < gridDim.x) __nanosleep(64);
+		__threadfence();
+	}
+	__syncthreads();
+}
+
+// Drain of the two queues raster_kernel leaves behind:
+//   1. clip queue: one warp per triangle — one lane clips and sets the pieces up; a piece spanning several 128x64 tiles joins
+//      the large-triangle queue, the others are scanned by the warp at once.  (Skipped, barrier included, when the queue is empty.)
+//   2. large-triangle queue: one warp per (triangle, 128x64-pixel tile) work item.
+//   3. only if a queue overflowed: the re-walk of the meshlet list (meshlet_loop<false>), one warp per block.
+__global__ void __launch_bounds__(kDrainThreads, 3) raster_big_kernel(const RasterParams p) {
+	__shared__ Tri sTri[kDrainThreads / 32];
+	__shared__ Tri sSub[kDrainThreads / 32][8];
 	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const unsigned long long cur = *p.bigCursor;
+
+	const uint32_t nClip = min(*p.clipCount, p.clipCap);
+	if (nClip) {
+		__shared__ int sN[kDrainThreads / 32];
+		for (;;) {
+			uint32_t ci = 0;
+			if (lane == 0) ci = atomicAdd(p.clipNext, 1u);
+			ci = __shfl_sync(0xffffffffu, ci, 0);
+			if (ci >= nClip) break;
+			__syncwarp();
+			if (lane == 0) {
+				const ClipTri c = p.clip[ci];
+				const int n = clip_and_setup(c.a, c.b, c.c, c.id, p.W, p.H, sSub[warp]);
+				int kept = 0; // clipped pieces are often the largest triangles of a scene: spread those over the GPU too
+				for (int k = 0; k < n; ++k) {
+					const Tri& t = sSub[warp][k];
+					const bool multiTile = (t.xmax / kBigTileW != t.xmin / kBigTileW) || (t.ymax / kBigTileH != t.ymin / kBigTileH);
+					if (multiTile && push_big(p, t)) continue;
+					if (kept != k) sSub[warp][kept] = t;
+					++kept;
+				}
+				sN[warp] = kept;
+			}
+			__syncwarp();
+			const int n = sN[warp];
+			for (int k = 0; k < n; ++k) {
+				const Tri& t = sSub[warp][k];
+				raster_coop(t, p.vis, p.W, lane, t.xmin, t.xmax, t.ymin, t.ymax);
+			}
+		}
+		drain_grid_barrier(p.drainBarrier); // every piece has been queued before anyone reads the queue's extent
+	}
+
+	const unsigned long long cur = *(volatile unsigned long long*)p.bigCursor;
 	uint32_t nRec = min((uint32_t)(cur >> kBigSlotShift), p.bigCap);
-	// records whose tile range would have left 32 bits were not stored (push_big): they form a suffix, because tile bases only grow
 	if ((cur & kBigTileMask) > 0xffffffffull) {
 		uint32_t lo = 0, hi = nRec; // first sentinel slot
 		while (lo < hi) {
@@ -552,29 +624,36 @@ __global__ void __launch_bounds__(256) raster_big_kernel(const RasterParams p) {
 		}
 		nRec = lo;
 	}
-	if (nRec == 0) return;
-	const BigTri* last = p.big + (nRec - 1);
-	const uint32_t nTiles = last->tileBase + last->tilesX * last->tilesY;
-	for (;;) {
-		uint32_t w = 0;
-		if (lane == 0) w = atomicAdd(p.bigNext, 1u);
-		w = __shfl_sync(0xffffffffu, w, 0);
-		if (w >= nTiles) break;
-		uint32_t lo = 0, hi = nRec - 1; // last record with tileBase <= w
-		while (lo < hi) {
-			const uint32_t mid = (lo + hi + 1) >> 1;
-			if (p.big[mid].tileBase <= w) lo = mid; else hi = mid - 1;
+	if (nRec) {
+		const BigTri* last = p.big + (nRec - 1);
+		const uint32_t nTiles = last->tileBase + last->tilesX * last->tilesY;
+		for (;;) {
+			uint32_t w = 0;
+			if (lane == 0) w = atomicAdd(p.bigNext, 1u);
+			w = __shfl_sync(0xffffffffu, w, 0);
+			if (w >= nTiles) break;
+			uint32_t lo = 0, hi = nRec - 1; // last record with tileBase <= w
+			while (lo < hi) {
+				const uint32_t mid = (lo + hi + 1) >> 1;
+				if (p.big[mid].tileBase <= w) lo = mid; else hi = mid - 1;
+			}
+			const BigTri* b = p.big + lo;
+			__syncwarp();
+			if (lane < sizeof(Tri) / 4) ((uint32_t*)&sTri[warp])[lane] = ((const uint32_t*)&b->t)[lane];
+			const uint32_t local = w - b->tileBase, tilesX = b->tilesX;
+			__syncwarp();
+			const Tri& t = sTri[warp];
+			const int tx = t.xmin / kBigTileW + (int)(local % tilesX), ty = t.ymin / kBigTileH + (int)(local / tilesX);
+			const int x0 = max(t.xmin, tx * kBigTileW), x1 = min(t.xmax, tx * kBigTileW + kBigTileW - 1);
+			const int y0 = max(t.ymin, ty * kBigTileH), y1 = min(t.ymax, ty * kBigTileH + kBigTileH - 1);
+			raster_coop(t, p.vis, p.W, lane, x0, x1, y0, y1);
 		}
-		const BigTri* b = p.big + lo;
-		__syncwarp();
-		if (lane < sizeof(Tri) / 4) ((uint32_t*)&sTri[warp])[lane] = ((const uint32_t*)&b->t)[lane];
-		const uint32_t local = w - b->tileBase, tilesX = b->tilesX;
-		__syncwarp();
-		const Tri& t = sTri[warp];
-		const int tx = t.xmin / kBigTileW + (int)(local % tilesX), ty = t.ymin / kBigTileH + (int)(local / tilesX);
-		const int x0 = max(t.xmin, tx * kBigTileW), x1 = min(t.xmax, tx * kBigTileW + kBigTileW - 1);
-		const int y0 = max(t.ymin, ty * kBigTileH), y1 = min(t.ymax, ty * kBigTileH + kBigTileH - 1);
-		raster_coop(t, p.vis, p.W, lane, x0, x1, y0, y1);
+	}
+
+	if (*(volatile uint32_t*)p.overflow) { // a queue was full: rare, slow, correct
+		__shared__ WarpScratch slow;
+		__shared__ SlowScratch slowSub;
+		if (warp == 0) meshlet_loop<false>(p, slow, &slowSub, p.slowWork, lane);
 	}
 }
 
@@ -606,17 +685,21 @@ cudaError_t launch_prepare_transforms(const float* transforms, const vkv_Camera*
 }
 
 cudaError_t launch_raster(const RasterParams& p, int num_sms, cudaStream_t stream) {
-	static int perSmOf[64] = {}; // per device (a process may hold contexts on several GPUs)
+	static int perSmOf[64][2] = {}; // per device (a process may hold contexts on several GPUs): hot kernel, drain kernel
 	int dev = 0;
 	cudaGetDevice(&dev);
-	int& perSm = perSmOf[dev & 63];
-	if (perSm == 0) {
+	int* perSm = perSmOf[dev & 63];
+	if (perSm[0] == 0) {
 		int n = 0;
 		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, raster_kernel, kThreads, 0);
-		perSm = n < 1 ? 1 : n;
+		perSm[0] = n < 1 ? 1 : n;
+		n = 0;
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, raster_big_kernel, kDrainThreads, 0);
+		perSm[1] = n < 1 ? 1 : (n > 4 ? 4 : n);
 	}
-	raster_kernel<<<num_sms * perSm, kThreads, 0, stream>>>(p);
-	raster_big_kernel<<<num_sms * 4, 256, 0, stream>>>(p); // exits at once when the queue is empty
+	raster_kernel<<<num_sms * perSm[0], kThreads, 0, stream>>>(p);
+	// every block co-resident (its clip phase ends in a grid barrier); exits at once when both queues are empty
+	raster_big_kernel<<<num_sms * perSm[1], kDrainThreads, 0, stream>>>(p);
 	return cudaGetLastError();
 }
 
