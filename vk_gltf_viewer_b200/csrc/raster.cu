@@ -333,12 +333,16 @@ __device__ __forceinline__ void meshlet_loop(const RasterParams& p, WarpScratch&
 	const float hw = (float)p.W * 0.5f, hh = (float)p.H * 0.5f;
 	const uint32_t below = (1u << lane) - 1u;
 
+	// meshlets per work-stealing grab: kBatch when there is plenty of work (the header chain's latency is paid once per batch);
+	// fewer when the list is short, so that a small scene spreads over all warps instead of queueing 4 deep behind a few
+	const uint32_t totalWarps = gridDim.x * (blockDim.x >> 5);
+	const uint32_t batch = kHot ? min((uint32_t)kBatch, max(1u, count / totalWarps)) : (uint32_t)kBatch;
 	for (;;) {
 		uint32_t base = 0;
-		if (lane == 0) base = atomicAdd(workCursor, (uint32_t)kBatch);
+		if (lane == 0) base = atomicAdd(workCursor, batch);
 		base = __shfl_sync(0xffffffffu, base, 0);
 		if (base >= count) break;
-		const uint32_t nb = min((uint32_t)kBatch, count - base);
+		const uint32_t nb = min(batch, count - base);
 		// one lane per meshlet walks the dependent chain list -> draw -> primitive -> meshlet (mesh.glsl:31-36)
 		if (lane < nb) {
 			const uint32_t drawId = __ldg(p.list + base + lane);
@@ -555,6 +559,11 @@ __device__ __forceinline__ void meshlet_loop(const RasterParams& p, WarpScratch&
 	}
 }
 
+// out of line: the re-walk's register appetite (and, under the drain kernel's register cap, its spills) stays inside this function
+__device__ __noinline__ void rewalk(const RasterParams& p, WarpScratch& ws, SlowScratch* slow, uint32_t lane) {
+	meshlet_loop<false>(p, ws, slow, p.slowWork, lane);
+}
+
 __global__ void __launch_bounds__(kThreads, kMinBlocks) raster_kernel(const RasterParams p) {
 	__shared__ WarpScratch scratch[kWarpsPerBlock];
 	meshlet_loop<true>(p, scratch[threadIdx.x >> 5], nullptr, p.work, threadIdx.x & 31);
@@ -582,7 +591,12 @@ __global__ void __launch_bounds__(kDrainThreads, 3) raster_big_kernel(const Rast
 	__shared__ Tri sSub[kDrainThreads / 32][8];
 	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-	const uint32_t nClip = min(*p.clipCount, p.clipCap);
+	// the three words that decide what there is to do, fetched together (one L2 round trip, not three): all are final when this
+	// kernel starts, except the queue cursor when the clip phase below appends pieces (re-read behind its barrier)
+	const uint32_t clipCountNow = *(volatile uint32_t*)p.clipCount;
+	unsigned long long cur = *(volatile unsigned long long*)p.bigCursor;
+	const uint32_t overflowed = *(volatile uint32_t*)p.overflow;
+	const uint32_t nClip = min(clipCountNow, p.clipCap);
 	if (nClip) {
 		__shared__ int sN[kDrainThreads / 32];
 		for (;;) {
@@ -612,9 +626,9 @@ __global__ void __launch_bounds__(kDrainThreads, 3) raster_big_kernel(const Rast
 			}
 		}
 		drain_grid_barrier(p.drainBarrier); // every piece has been queued before anyone reads the queue's extent
+		cur = *(volatile unsigned long long*)p.bigCursor;
 	}
 
-	const unsigned long long cur = *(volatile unsigned long long*)p.bigCursor;
 	uint32_t nRec = min((uint32_t)(cur >> kBigSlotShift), p.bigCap);
 	if ((cur & kBigTileMask) > 0xffffffffull) {
 		uint32_t lo = 0, hi = nRec; // first sentinel slot
@@ -650,10 +664,10 @@ __global__ void __launch_bounds__(kDrainThreads, 3) raster_big_kernel(const Rast
 		}
 	}
 
-	if (*(volatile uint32_t*)p.overflow) { // a queue was full: rare, slow, correct
+	if (overflowed) { // a queue was full: rare, slow, correct
 		__shared__ WarpScratch slow;
 		__shared__ SlowScratch slowSub;
-		if (warp == 0) meshlet_loop<false>(p, slow, &slowSub, p.slowWork, lane);
+		if (warp == 0) rewalk(p, slow, &slowSub, lane);
 	}
 }
 
