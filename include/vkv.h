@@ -52,6 +52,9 @@ enum {
 	VKV_FRAME_TIMED = 1 << 3,      /* fill total_ms of vkv_stats (CUDA events around the frame; syncs the stream at frame end) */
 	VKV_FRAME_NO_CULL = 1 << 4,    /* rasterise every MeshletDraw (debug; what the task shader does with culling disabled) */
 	VKV_FRAME_MERGE = 1 << 5,      /* multi-GPU: min-merge the visbuffer with the attached peers before each pyramid build */
+	VKV_FRAME_MERGE_STRIPS = 1 << 7, /* multi-GPU: screen-strip ownership — each rank pulls the tiles its peers drew into its strip, builds
+	                                  the strip's exact mips and stores the changed texels into every rank's pyramid; the merged
+	                                  visbuffer stays distributed (rank r holds strip r), the pyramid is complete everywhere */
 	VKV_FRAME_STAGES = 1 << 6      /* with VKV_FRAME_TIMED: also the per-stage *_ms fields (an event between two launches; it keeps the
 	                                  pass-B cull from overlapping the pyramid's tail, so total_ms is a few us higher than without) */
 };
@@ -180,6 +183,15 @@ int vkv_ipc_attach(vkv_ctx*, int rank, int nranks, const void* handles);
 int vkv_ipc_detach(vkv_ctx*);
 /* all ranks call it at the same point of their stream: barrier, fused reduce-scatter + all-gather u64 min, barrier */
 int vkv_merge(vkv_ctx*);
+/* Strip ownership (VKV_FRAME_MERGE_STRIPS).  The screen is cut into nranks horizontal strips of whole 16-row tile rows; rank r owns
+ * rows [first_row, end_row).  After a strip-mode frame rank r's visbuffer holds the MERGED keys in its own strip only (its other
+ * rows hold what this rank drew); the pyramid is complete and identical on every rank.  vkv_gather_strips (a collective: all ranks
+ * call it at the same point) pulls the other strips from their owners so that every rank holds the whole merged image. */
+int vkv_strip_rows(vkv_ctx*, int rank, int nranks, uint32_t* first_row, uint32_t* end_row);
+int vkv_gather_strips(vkv_ctx*);
+/* order-independent 64-bit digest computed on the device: what = 0: visbuffer keys of rows [first_row, end_row);
+ * what = 1: the whole pyramid (rows ignored).  Equal inputs at equal positions give equal digests on any GPU (parity checks). */
+int vkv_hash(vkv_ctx*, int what, uint32_t first_row, uint32_t end_row, uint64_t* out);
 
 /* ---- results (blocking device->host copies on the ctx stream) ------------------------------------------- */
 int vkv_read_visbuffer64(vkv_ctx*, uint64_t* host);                /* W*H keys: (~floatBits(depth) << 32) | packVisBuffer */

@@ -22,7 +22,7 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     mode = sys.argv[1] if len(sys.argv) > 1 else "p2p"
-    W, H = 1280, 720
+    W, H = (1000, 500) if mode.endswith("e2") else (1280, 720)   # 1000x500: two exact mips only, a ragged last tile row
     scene = Scene.lattice(4, 3, 4, 48)
     views = [scene.default_view(i, 24) for i in range(3)]
     cam = Camera(W, H).look_at(*views[0])
@@ -30,7 +30,7 @@ def main():
     pc_dev = r.upload_scene(scene, cam)
     pc_host = scene.host_push_constants(cam)
     N = pc_host.meshletDrawCount
-    if mode.endswith("interleaved"):   # blocks of 32 draws dealt round-robin (small scene: make the interleave real)
+    if mode.endswith("interleaved") or mode in ("strips", "strips-e2"):   # blocks of 32 draws dealt round-robin (small scene: make the interleave real)
         r.set_shard_interleaved(rank, world, 5)
         mine = lambda ids: ids[multigpu.interleaved_owner(ids, world, 5) == rank]
     else:
@@ -43,8 +43,25 @@ def main():
         if k:
             cam.look_at(eye, center)
             r.update_camera(pc_dev, cam)
+        prev_pyramid = tg.pyramid.copy()
         out = O.frame(pc_host, tg, two_pass=True)
-        if mode.startswith("p2p"):
+        if mode.startswith("strips"):
+            # screen-strip ownership: the merged keys live in each owner's strip, the pyramid is complete on every rank
+            st = r.frame(pc_dev, api.FRAME_TWO_PASS | api.FRAME_MERGE_STRIPS | api.FRAME_STATUS)
+            y0, y1 = r.strip_rows(rank, world)
+            own = r.read_visbuffer64()[y0:y1]
+            assert np.array_equal(own, tg.vis64()[y0:y1]), f"rank {rank} view {k}: own strip rows [{y0},{y1}) differ from the single-list oracle ({int((own != tg.vis64()[y0:y1]).sum())} keys)"
+            assert np.array_equal(r.read_pyramid().view(np.uint32), tg.pyramid.view(np.uint32)), f"rank {rank} view {k}: pyramid differs (strip mode)"
+            # digests: the strip and the pyramid hash like the same data rendered by one GPU would (what bench.py's merge_parity compares)
+            r1 = api.Renderer(W, H, device=local)
+            pc1 = r1.upload_scene(scene, cam)
+            r1._ck(r1.L.vkv_write_pyramid(r1.h, prev_pyramid.ctypes.data, prev_pyramid.size))
+            r1.frame(pc1, api.FRAME_TWO_PASS)
+            assert r1.hash(0, y0, y1) == r.hash(0, y0, y1) and r1.hash(1) == r.hash(1), f"rank {rank} view {k}: digests differ"
+            assert r1.hash(0, 0, H) != r.hash(0, y0, y1) or (y0, y1) == (0, H)
+            r1.close()
+            r.gather_strips()   # whole image everywhere, for the comparison below
+        elif mode.startswith("p2p"):
             st = r.frame(pc_dev, api.FRAME_TWO_PASS | api.FRAME_MERGE | api.FRAME_STATUS)
         else:  # library collective as the cross-check: stage by stage with ncclAllReduce(min) in place of vkv_merge
             r.clear()

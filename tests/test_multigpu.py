@@ -125,7 +125,7 @@ def _ngpus():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", ["p2p", "nccl", "p2p-interleaved"])
+@pytest.mark.parametrize("mode", ["p2p", "nccl", "p2p-interleaved", "strips", "strips-contiguous", "strips-e2"])
 def test_range_sharded_frames_match_single_list_oracle(mode):
     n = _ngpus()
     if n < 2:

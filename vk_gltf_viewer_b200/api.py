@@ -19,6 +19,7 @@ FRAME_TIMED = 1 << 3
 FRAME_STAGES = 1 << 6
 FRAME_NO_CULL = 1 << 4
 FRAME_MERGE = 1 << 5
+FRAME_MERGE_STRIPS = 1 << 7
 
 ST_FRUSTUM_CULLED, ST_OCCLUDED, ST_VISIBLE, ST_NOT_TESTED = 0, 1, 2, 3
 
@@ -53,6 +54,7 @@ EXPORTS = [
     "vkv_build_meshlets", "vkv_assemble_vertices", "vkv_widen_indices",
     "vkv_alloc", "vkv_meshopt_plan_create", "vkv_meshopt_run", "vkv_meshopt_results", "vkv_meshopt_plan_destroy",
     "vkv_set_shard", "vkv_set_shard_interleaved", "vkv_ipc_export", "vkv_ipc_attach", "vkv_ipc_detach", "vkv_merge",
+    "vkv_strip_rows", "vkv_gather_strips", "vkv_hash",
 ]
 
 _bound = False
@@ -106,6 +108,9 @@ def _lib():
         L.vkv_ipc_attach.argtypes = [vp, i, i, vp]
         L.vkv_ipc_detach.argtypes = [vp]
         L.vkv_merge.argtypes = [vp]
+        L.vkv_strip_rows.argtypes = [vp, i, i, C.POINTER(u32), C.POINTER(u32)]
+        L.vkv_gather_strips.argtypes = [vp]
+        L.vkv_hash.argtypes = [vp, i, u32, u32, C.POINTER(u64)]
         L.vkv_selftest_division.argtypes = [vp, u64, u32, C.POINTER(u64), C.POINTER(u64)]
         L.vkv_alloc.argtypes = [vp, C.c_size_t, C.POINTER(u64)]
         L.vkv_build_meshlets.argtypes = [vp, vp, u32, u32, u32, u32, vp]
@@ -374,3 +379,19 @@ class Renderer:
 
     def merge(self):
         self._ck(self.L.vkv_merge(self.h))
+
+    def strip_rows(self, rank: int, nranks: int):
+        """rows [first, end) of the screen strip `rank` owns under FRAME_MERGE_STRIPS"""
+        a, b = C.c_uint32(), C.c_uint32()
+        self._ck(self.L.vkv_strip_rows(self.h, rank, nranks, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def gather_strips(self):
+        """collective: pull the strips this rank does not own from their owners (whole merged image on every rank)"""
+        self._ck(self.L.vkv_gather_strips(self.h))
+
+    def hash(self, what: int, first_row: int = 0, end_row: int = 0) -> int:
+        """device-side order-independent digest: what=0 visbuffer rows [first_row, end_row), what=1 the pyramid"""
+        h = C.c_uint64()
+        self._ck(self.L.vkv_hash(self.h, what, first_row, end_row, C.byref(h)))
+        return h.value

@@ -52,7 +52,14 @@ struct vkv_ctx {
 	bool separate_clear = false; // VKV_SEPARATE_CLEAR=1: keep the visbuffer clear a launch of its own (A/B measurements)
 	MergeParams mp{};
 	bool attached = false;
-	uint32_t* sync_flags = nullptr;   // kMaxRanks barrier slots + 1 error word, peer-mapped
+	// exchange block: ONE allocation the peers map through CUDA IPC — barrier slots (kMaxRanks u32 + 1 error word, first 256 B),
+	// the dirty-tile flags of both passes (strip mode), the pyramid.  Rebuilt with the targets (vkv_resize).
+	unsigned char* xchg = nullptr;
+	size_t xchg_bytes = 0;
+	uint32_t* sync_flags = nullptr;   // = xchg
+	uint8_t* dirty = nullptr;         // = xchg + 256: [2][dirty_stride]
+	uint32_t dirty_stride = 0, tiles_x = 0, tiles_y = 0;
+	size_t pyramid_offset = 0;        // of the pyramid inside xchg
 	uint32_t epoch = 0;
 	bool merge_used = false;          // a barrier kernel has been enqueued since the error word was last read
 	bool merge_err_pending = false;
@@ -117,7 +124,8 @@ void fill_pyramid_desc(uint32_t W, uint32_t H, PyramidDesc& d, uint32_t& exact) 
 
 int free_targets(vkv_ctx* c) {
 	if (c->vis) cudaFree(c->vis);
-	if (c->pyramid) cudaFree(c->pyramid);
+	if (c->xchg) cudaFree(c->xchg);
+	c->xchg = nullptr; c->sync_flags = nullptr; c->dirty = nullptr;
 	if (c->tmp_ids) cudaFree(c->tmp_ids);
 	if (c->tmp_depth) cudaFree(c->tmp_depth);
 	if (c->color) cudaFree(c->color);
@@ -131,10 +139,17 @@ int alloc_targets(vkv_ctx* c, uint32_t W, uint32_t H) {
 	c->W = W; c->H = H;
 	fill_pyramid_desc(W, H, c->pyr, c->exact_levels);
 	CK(cudaMalloc(&c->vis, (size_t)W * H * 8));
-	CK(cudaMalloc(&c->pyramid, (size_t)(c->pyr.total ? c->pyr.total : 1) * 4));
-	// initial contents: visbuffer cleared; pyramid 0.0 everywhere = "far" (nothing occludes)
+	c->tiles_x = (W + 63) / 64; c->tiles_y = (H + 15) / 16;                       // 64x16-pixel tiles (hiz_tile.cuh)
+	c->dirty_stride = (c->tiles_x * c->tiles_y + 15u) & ~15u;
+	c->pyramid_offset = (256 + 2 * (size_t)c->dirty_stride + 255) & ~(size_t)255;
+	c->xchg_bytes = c->pyramid_offset + (((size_t)c->pyr.total + 2) & ~(size_t)1) * 4;   // an even number of floats (vkv_hash reads u64 words)
+	CK(cudaMalloc(&c->xchg, c->xchg_bytes));
+	c->sync_flags = (uint32_t*)c->xchg;
+	c->dirty = c->xchg + 256;
+	c->pyramid = (float*)(c->xchg + c->pyramid_offset);
+	// initial contents: visbuffer cleared; pyramid 0.0 everywhere = "far" (nothing occludes); barrier slots and flags zero
 	CK(launch_fill64(c->vis, (size_t)W * H, VKV_VIS64_CLEAR, c->num_sms, c->stream));
-	CK(cudaMemsetAsync(c->pyramid, 0, (size_t)(c->pyr.total ? c->pyr.total : 1) * 4, c->stream));
+	CK(cudaMemsetAsync(c->xchg, 0, c->xchg_bytes, c->stream));
 	CK(cudaStreamSynchronize(c->stream));
 	return VKV_OK;
 }
@@ -242,8 +257,9 @@ CullParams make_cull(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, int pass,
 	return p;
 }
 
-RasterParams make_raster(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, const uint32_t* list, const uint32_t* count, uint32_t* work) {
+RasterParams make_raster(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, const uint32_t* list, const uint32_t* count, uint32_t* work, int mark_pass = -1) {
 	RasterParams r{};
+	if (mark_pass >= 0) { r.dirty = c->dirty + (size_t)mark_pass * c->dirty_stride; r.dirtyTilesX = c->tiles_x; } // strip mode
 	r.draws = (const vkv_MeshletDraw*)pc->drawBuffer;
 	r.transforms = (const float*)pc->transformBuffer;
 	r.primitives = (const vkv_Primitive*)pc->primitiveBuffer;
@@ -289,7 +305,7 @@ void detach_peers(vkv_ctx* c) {
 	for (int r = 0; r < c->mp.nranks; ++r) {
 		if (r == c->mp.rank) continue;
 		if (c->mp.vis[r]) cudaIpcCloseMemHandle(c->mp.vis[r]);
-		if (c->mp.flags[r]) cudaIpcCloseMemHandle(c->mp.flags[r]);
+		if (c->mp.flags[r]) cudaIpcCloseMemHandle(c->mp.flags[r]); // the peer's exchange block (flags, dirty, pyramid share one mapping)
 	}
 	memset(&c->mp, 0, sizeof(c->mp));
 	c->attached = false;
@@ -305,6 +321,25 @@ int enqueue_merge(vkv_ctx* c, int* launches) {
 	CK(launch_xgpu_barrier(c->mp, ++c->epoch, timeout_ns, c->stream));
 	c->merge_used = true;
 	if (launches) *launches += 3;
+	return VKV_OK;
+}
+
+// strip mode (strips.cu): barrier -> [pull dirty tiles of my strip, min, exact mips, changed texels to every pyramid] -> barrier ->
+// small mips locally
+int enqueue_strip_exchange(vkv_ctx* c, int pass, int* launches) {
+	if (!c->attached) return fail(c, VKV_ERR_INVALID, "strip exchange requested but no peers are attached (vkv_ipc_attach)");
+	const unsigned long long timeout_ns = 5ull * 1000 * 1000 * 1000;
+	StripParams sp{};
+	sp.mp = c->mp; sp.mp.n = (size_t)c->W * c->H;
+	sp.W = c->W; sp.H = c->H; sp.pyr = c->pyr; sp.exact_levels = c->exact_levels;
+	sp.tilesX = c->tiles_x; sp.tilesY = c->tiles_y; sp.dirtyStride = c->dirty_stride; sp.pass = pass;
+	CK(launch_xgpu_barrier(c->mp, ++c->epoch, timeout_ns, c->stream));
+	CK(launch_strip_merge_hiz(sp, c->num_sms, c->stream));
+	CK(launch_xgpu_barrier(c->mp, ++c->epoch, timeout_ns, c->stream));
+	HizParams h = make_hiz(c);
+	CK(launch_hiz_tail(h, c->stream));
+	c->merge_used = true;
+	if (launches) *launches += 3 + (c->exact_levels < c->pyr.levels ? 1 : 0);
 	return VKV_OK;
 }
 
@@ -381,7 +416,6 @@ void vkv_destroy(vkv_ctx* c) {
 	cudaSetDevice(c->device);
 	if (c->stream) cudaStreamSynchronize(c->stream);
 	detach_peers(c);
-	if (c->sync_flags) cudaFree(c->sync_flags);
 	free_targets(c);
 	for (int i = 0; i < 2; ++i) {
 		if (c->list_visible[i]) cudaFree(c->list_visible[i]);
@@ -528,10 +562,12 @@ int vkv_frame(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, uint32_t flags, 
 	cudaStream_t s = c->stream;
 	const bool timed = (flags & VKV_FRAME_TIMED) && out;
 	const bool two = (flags & VKV_FRAME_TWO_PASS) && !(flags & VKV_FRAME_NO_CULL);
-	const bool merge = (flags & VKV_FRAME_MERGE) != 0;
+	const bool strips = (flags & VKV_FRAME_MERGE_STRIPS) != 0;
+	const bool merge = (flags & VKV_FRAME_MERGE) != 0 && !strips;
 	const bool hiz = !(flags & VKV_FRAME_NO_HIZ);
 	const uint32_t N = pc->meshletDrawCount;
-	if (merge && !c->attached) return fail(c, VKV_ERR_INVALID, "VKV_FRAME_MERGE needs vkv_ipc_attach first");
+	if ((merge || strips) && !c->attached) return fail(c, VKV_ERR_INVALID, "VKV_FRAME_MERGE / VKV_FRAME_MERGE_STRIPS need vkv_ipc_attach first");
+	if (strips && (c->exact_levels < 1 || !hiz)) return fail(c, VKV_ERR_INVALID, "VKV_FRAME_MERGE_STRIPS needs an even resolution (one exact pyramid mip) and the pyramid rebuild");
 	int launches = 0;
 	// NVTX ranges named like the reference's Tracy/debug-label zones (application.cpp:765 "Visbuffer pass", :952 "HiZ reduction") so a
 	// maintainer can line a trace of this library up with a trace of the Vulkan path; free when no tool is attached
@@ -562,6 +598,7 @@ int vkv_frame(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, uint32_t flags, 
 	} else {
 		CullParams& p = pa;
 		if (fuse_clear) { p.clear_ptr = (ulonglong2*)c->vis; p.clear_n2 = npix / 2; p.clear_value = VKV_VIS64_CLEAR; }
+		if (strips && p.n) { p.zero_ptr = (uint4*)c->dirty; p.zero_n16 = 2 * c->dirty_stride / 16; } // the dirty-tile flags ride along too
 		if (p.status) CK(cudaMemsetAsync(p.status, VKV_ST_NOT_TESTED, N, s));
 		c->status_valid[0] = p.status != nullptr;
 		if (p.n) {
@@ -570,14 +607,16 @@ int vkv_frame(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, uint32_t flags, 
 		}
 	}
 	mark(E_CULL_A);
+	if (strips && !pa.zero_ptr) CK(cudaMemsetAsync(c->dirty, 0, 2 * (size_t)c->dirty_stride, s));
 	if (!xf_done) { rc = prepare_transforms(c, pc, &launches); if (rc) return rc; }
-	rc = enqueue_raster(c, make_raster(c, pc, c->list_visible[0], &c->counters->visible[0], &c->counters->work[0]), &launches);
+	rc = enqueue_raster(c, make_raster(c, pc, c->list_visible[0], &c->counters->visible[0], &c->counters->work[0], strips ? 0 : -1), &launches);
 	if (rc) return rc;
 	mark(E_RASTER_A);
 	if (merge) { rc = enqueue_merge(c, &launches); if (rc) return rc; }
+	if (strips) { rc = enqueue_strip_exchange(c, 0, &launches); if (rc) return rc; } // merge + exact mips + all-gather + small mips
 	mark(E_MERGE_A);
 	visA.end();
-	if (hiz) { Range z("HiZ reduction"); CK(launch_hiz(make_hiz(c), c->num_sms, s, &launches)); }
+	if (hiz && !strips) { Range z("HiZ reduction"); CK(launch_hiz(make_hiz(c), c->num_sms, s, &launches)); }
 	mark(E_HIZ_A);
 	if (two) {
 		Range visB("Visbuffer pass (B)");
@@ -586,16 +625,17 @@ int vkv_frame(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, uint32_t flags, 
 		if (p.status) CK(cudaMemsetAsync(p.status, VKV_ST_NOT_TESTED, N, s));
 		c->status_valid[1] = p.status != nullptr;
 		// nothing between the pyramid launch and this one (no stage event, no status memset, no merge): let it start under the tail
-		const bool pdl = hiz && !stages && !p.status && c->exact_levels >= 1 && !c->no_pdl;
+		const bool pdl = hiz && !stages && !p.status && c->exact_levels >= 1 && !c->no_pdl && !strips;
 		if (p.n) { CK(launch_cull(p, c->num_sms, s, pdl)); ++launches; }
 		mark(E_CULL_B);
-		rc = enqueue_raster(c, make_raster(c, pc, c->list_visible[1], &c->counters->visible[1], &c->counters->work[1]), &launches);
+		rc = enqueue_raster(c, make_raster(c, pc, c->list_visible[1], &c->counters->visible[1], &c->counters->work[1], strips ? 1 : -1), &launches);
 		if (rc) return rc;
 		mark(E_RASTER_B);
 		if (merge) { rc = enqueue_merge(c, &launches); if (rc) return rc; }
+		if (strips) { rc = enqueue_strip_exchange(c, 1, &launches); if (rc) return rc; }
 		mark(E_MERGE_B);
 		visB.end();
-		if (hiz) { Range z("HiZ reduction"); CK(launch_hiz(make_hiz(c), c->num_sms, s, &launches)); }
+		if (hiz && !strips) { Range z("HiZ reduction"); CK(launch_hiz(make_hiz(c), c->num_sms, s, &launches)); }
 		mark(E_HIZ_B);
 	}
 	if (timed) cudaEventRecord(c->stage_ev[E_COUNT], s); // end of frame (the per-stage events exist only with VKV_FRAME_STAGES)
@@ -755,14 +795,10 @@ int vkv_set_shard_interleaved(vkv_ctx* c, int rank, int nranks, uint32_t block_l
 int vkv_ipc_export(vkv_ctx* c, void* handle128) {
 	if (!c || !handle128) return VKV_ERR_INVALID;
 	CK(cudaSetDevice(c->device));
-	if (!c->sync_flags) {
-		CK(cudaMalloc(&c->sync_flags, (kMaxRanks + 1) * 4));
-		CK(cudaMemset(c->sync_flags, 0, (kMaxRanks + 1) * 4));
-	}
 	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle layout");
 	cudaIpcMemHandle_t h[2];
 	CK(cudaIpcGetMemHandle(&h[0], c->vis));
-	CK(cudaIpcGetMemHandle(&h[1], c->sync_flags));
+	CK(cudaIpcGetMemHandle(&h[1], c->xchg));
 	memcpy(handle128, h, 128);
 	return VKV_OK;
 }
@@ -770,7 +806,6 @@ int vkv_ipc_export(vkv_ctx* c, void* handle128) {
 int vkv_ipc_attach(vkv_ctx* c, int rank, int nranks, const void* handles) {
 	if (!c || !handles) return VKV_ERR_INVALID;
 	if (nranks < 1 || nranks > kMaxRanks || rank < 0 || rank >= nranks) return fail(c, VKV_ERR_INVALID, "rank %d of %d out of range (max %d ranks)", rank, nranks, kMaxRanks);
-	if (!c->sync_flags) return fail(c, VKV_ERR_INVALID, "vkv_ipc_attach: call vkv_ipc_export first");
 	CK(cudaSetDevice(c->device));
 	CK(cudaStreamSynchronize(c->stream));
 	detach_peers(c);
@@ -779,7 +814,7 @@ int vkv_ipc_attach(vkv_ctx* c, int rank, int nranks, const void* handles) {
 	c->attached = true; // from here on detach_peers() closes whatever was opened
 	const cudaIpcMemHandle_t* h = (const cudaIpcMemHandle_t*)handles;
 	for (int r = 0; r < nranks; ++r) {
-		if (r == rank) { c->mp.vis[r] = c->vis; c->mp.flags[r] = c->sync_flags; continue; }
+		if (r == rank) { c->mp.vis[r] = c->vis; c->mp.flags[r] = c->sync_flags; c->mp.dirty[r] = c->dirty; c->mp.pyr[r] = c->pyramid; continue; }
 		void *pv = nullptr, *pf = nullptr;
 		cudaError_t e = cudaIpcOpenMemHandle(&pv, h[2 * r], cudaIpcMemLazyEnablePeerAccess);
 		if (e == cudaSuccess) { c->mp.vis[r] = (unsigned long long*)pv; e = cudaIpcOpenMemHandle(&pf, h[2 * r + 1], cudaIpcMemLazyEnablePeerAccess); }
@@ -788,6 +823,9 @@ int vkv_ipc_attach(vkv_ctx* c, int rank, int nranks, const void* handles) {
 			return fail(c, VKV_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
 		}
 		c->mp.flags[r] = (uint32_t*)pf;
+		// same resolution on every rank (the caller's contract), hence the same layout inside the peer's exchange block
+		c->mp.dirty[r] = (uint8_t*)pf + 256;
+		c->mp.pyr[r] = (float*)((unsigned char*)pf + c->pyramid_offset);
 	}
 	// A new session starts from a clean barrier state: epoch 0 AND zeroed local slots + error word.  (Resetting only the epoch would
 	// leave the previous session's epochs in the slots, and `flag - epoch >= 0` would let every barrier pass at once.)  This is
@@ -812,6 +850,48 @@ int vkv_merge(vkv_ctx* c) {
 	if (!c) return VKV_ERR_INVALID;
 	CK(cudaSetDevice(c->device));
 	return enqueue_merge(c, nullptr);
+}
+
+int vkv_strip_rows(vkv_ctx* c, int rank, int nranks, uint32_t* first_row, uint32_t* end_row) {
+	if (!c || !first_row || !end_row || nranks < 1 || rank < 0 || rank >= nranks) return c ? fail(c, VKV_ERR_INVALID, "vkv_strip_rows: bad argument") : VKV_ERR_INVALID;
+	const uint32_t y0 = strip_first_row(c->tiles_y, rank, nranks) * 16u, y1 = strip_first_row(c->tiles_y, rank + 1, nranks) * 16u;
+	*first_row = y0 < c->H ? y0 : c->H;
+	*end_row = y1 < c->H ? y1 : c->H;
+	return VKV_OK;
+}
+
+int vkv_gather_strips(vkv_ctx* c) {
+	if (!c) return VKV_ERR_INVALID;
+	if (!c->attached) return fail(c, VKV_ERR_INVALID, "vkv_gather_strips: no peers are attached (vkv_ipc_attach)");
+	CK(cudaSetDevice(c->device));
+	const unsigned long long timeout_ns = 5ull * 1000 * 1000 * 1000;
+	StripParams sp{};
+	sp.mp = c->mp; sp.mp.n = (size_t)c->W * c->H;
+	sp.W = c->W; sp.H = c->H; sp.pyr = c->pyr; sp.exact_levels = c->exact_levels;
+	sp.tilesX = c->tiles_x; sp.tilesY = c->tiles_y; sp.dirtyStride = c->dirty_stride;
+	CK(launch_xgpu_barrier(c->mp, ++c->epoch, timeout_ns, c->stream));   // every owner's strip is final
+	CK(launch_strip_gather(sp, c->num_sms, c->stream));
+	CK(launch_xgpu_barrier(c->mp, ++c->epoch, timeout_ns, c->stream));   // nobody overwrites a strip a peer is still reading
+	c->merge_used = true;
+	return VKV_OK;
+}
+
+int vkv_hash(vkv_ctx* c, int what, uint32_t first_row, uint32_t end_row, uint64_t* out) {
+	if (!c || !out) return VKV_ERR_INVALID;
+	CK(cudaSetDevice(c->device));
+	unsigned long long* d = (unsigned long long*)c->tmp_count; // 256-byte scratch
+	CK(cudaMemsetAsync(d, 0, 8, c->stream));
+	if (what == 0) {
+		if (first_row > end_row || end_row > c->H) return fail(c, VKV_ERR_INVALID, "vkv_hash: rows [%u, %u) outside the %u-row image", first_row, end_row, c->H);
+		CK(launch_hash64(c->vis, (size_t)first_row * c->W, (size_t)(end_row - first_row) * c->W, d, c->num_sms, c->stream));
+	} else if (what == 1) { // the pyramid as u64 words (its allocation is padded with a zero float to an even count)
+		CK(launch_hash64((const unsigned long long*)c->pyramid, 0, ((size_t)c->pyr.total + 1) / 2, d, c->num_sms, c->stream));
+	} else return fail(c, VKV_ERR_INVALID, "vkv_hash: what must be 0 (visbuffer rows) or 1 (pyramid)");
+	unsigned long long h = 0;
+	CK(cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	*out = h;
+	return check_merge_error(c);
 }
 
 int vkv_read_visbuffer64(vkv_ctx* c, uint64_t* host) {

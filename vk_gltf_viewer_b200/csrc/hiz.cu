@@ -6,6 +6,7 @@
 // memory level after level, restating the min-sampler footprint rule texel by texel (i0 = floor(u*S - 0.5),
 // {i0, i0+1} minus zero-weight texels, CLAMP_TO_EDGE).  One launch per pyramid build.
 #include "kernels.cuh"
+#include "hiz_tile.cuh"
 #ifdef VKV_HIZ_DEBUG
 #include <cstdio>
 #define TS(i) do { if (threadIdx.x == 0) dbg_ts[i] = clock64(); } while (0)
@@ -16,10 +17,7 @@
 
 namespace {
 
-constexpr int kTileW = 64, kTileH = 16; // source pixels per warp tile; yields 32x8, 16x4, 8x2, 4x1 texels of mips 0..3
 constexpr int kHizWarps = 32; // 1024 threads: the last block also runs the serial small-mip tail, which wants the whole SM
-
-__device__ __forceinline__ float min4(float a, float b, float c, float d) { return gmin(gmin(gmin(a, b), c), d); }
 
 // Remaining mips, ONE block, level after level (each level is a few thousand texels at most and depends on the previous).
 // first_level = index of the first pyramid mip to produce here.  Everything the serial chain touches lives in shared memory:
@@ -195,82 +193,22 @@ __global__ void __launch_bounds__(1024) hiz_tail_kernel(const HizParams p, uint3
 	hiz_tail(p, first_level, TailSmem(tailSmem));
 }
 
-// One warp per 64x16 source tile. Lane l owns source columns 2l,2l+1 (one 16-byte load per row, 16 loads in flight).
-// Valid only for levels whose source is exactly twice the destination in both axes: the sampler footprint is then the
-// aligned 2x2 quad {2p, 2p+1} (u = 2p + 0.5 up to rounding noise << 0.5; checked exhaustively in tests/test_oracle.py).
+// One warp per 64x16 source tile (hiz_tile.cuh).  Valid only for levels whose source is exactly twice the destination in both axes:
+// the sampler footprint is then the aligned 2x2 quad {2p, 2p+1} (u = 2p + 0.5 up to rounding noise << 0.5; checked exhaustively
+// in tests/test_oracle.py).
 __global__ void __launch_bounds__(kHizWarps * 32) hiz_tiled_kernel(const HizParams p) {
 	extern __shared__ __align__(16) unsigned char tailSmem[]; // used by the last block only (1 block / SM anyway: 1024 threads)
 	__shared__ uint32_t sLast;
 	const uint32_t lane = threadIdx.x & 31;
 	const uint32_t tilesX = (p.W + kTileW - 1) / kTileW, tilesY = (p.H + kTileH - 1) / kTileH;
 	const uint32_t nTiles = tilesX * tilesY;
-	const uint32_t E = p.exact_levels;
+	const HizTileGeo geo = {p.W, p.H, p.exact_levels, {p.pyr.off[0], p.pyr.off[1], p.pyr.off[2], p.pyr.off[3]}, {p.pyr.w[0], p.pyr.w[1], p.pyr.w[2], p.pyr.w[3]}};
+	float* const pyramid = p.pyramid;
 	for (uint32_t tile = blockIdx.x * kHizWarps + (threadIdx.x >> 5); tile < nTiles; tile += gridDim.x * kHizWarps) {
 		const uint32_t tx = tile % tilesX, ty = tile / tilesX;
-		const uint32_t x0 = tx * kTileW + lane * 2, y0 = ty * kTileH;
-		const bool colIn = x0 < p.W; // W is even whenever E >= 1, so the pair is in or out together
-		float m0[8];
-		{
-			ulonglong2 v[kTileH];
-#pragma unroll
-			for (int r = 0; r < kTileH; ++r) {
-				v[r] = make_ulonglong2(0ull, 0ull); // key 0 == depth +NaN pattern never produced; replaced below by +inf
-				if (colIn && y0 + r < p.H) v[r] = __ldcs((const ulonglong2*)(p.vis + (size_t)(y0 + r) * p.W + x0));
-			}
-#pragma unroll
-			for (int r = 0; r < 8; ++r) {
-				const bool in = colIn && (y0 + 2 * r + 1 < p.H);
-				const float a = depth_of_key(v[2 * r].x), b = depth_of_key(v[2 * r].y);
-				const float c = depth_of_key(v[2 * r + 1].x), d = depth_of_key(v[2 * r + 1].y);
-				m0[r] = in ? min4(a, b, c, d) : __int_as_float(0x7f800000);
-			}
-		}
-		// mip 0: 32 x 8 per tile
-		{
-			float* dst = p.pyramid + p.pyr.off[0];
-			const uint32_t mw = p.pyr.w[0], mx = tx * 32 + lane, my0 = ty * 8;
-#pragma unroll
-			for (int r = 0; r < 8; ++r)
-				if (mx < (p.W >> 1) && my0 + r < (p.H >> 1)) dst[(size_t)(my0 + r) * mw + mx] = m0[r];
-		}
-		if (E < 2) continue;
-		float m1[4];
-#pragma unroll
-		for (int r = 0; r < 4; ++r) {
-			const float v = gmin(m0[2 * r], m0[2 * r + 1]);
-			m1[r] = gmin(v, __shfl_xor_sync(0xffffffffu, v, 1));
-		}
-		if ((lane & 1) == 0) {
-			float* dst = p.pyramid + p.pyr.off[1];
-			const uint32_t mw = p.pyr.w[1], mx = tx * 16 + (lane >> 1), my0 = ty * 4;
-#pragma unroll
-			for (int r = 0; r < 4; ++r)
-				if (mx < (p.W >> 2) && my0 + r < (p.H >> 2)) dst[(size_t)(my0 + r) * mw + mx] = m1[r];
-		}
-		if (E < 3) continue;
-		float m2[2];
-#pragma unroll
-		for (int r = 0; r < 2; ++r) {
-			const float v = gmin(m1[2 * r], m1[2 * r + 1]);
-			m2[r] = gmin(v, __shfl_xor_sync(0xffffffffu, v, 2));
-		}
-		if ((lane & 3) == 0) {
-			float* dst = p.pyramid + p.pyr.off[2];
-			const uint32_t mw = p.pyr.w[2], mx = tx * 8 + (lane >> 2), my0 = ty * 2;
-#pragma unroll
-			for (int r = 0; r < 2; ++r)
-				if (mx < (p.W >> 3) && my0 + r < (p.H >> 3)) dst[(size_t)(my0 + r) * mw + mx] = m2[r];
-		}
-		if (E < 4) continue;
-		{
-			const float v = gmin(m2[0], m2[1]);
-			const float m3 = gmin(v, __shfl_xor_sync(0xffffffffu, v, 4));
-			if ((lane & 7) == 0) {
-				float* dst = p.pyramid + p.pyr.off[3];
-				const uint32_t mw = p.pyr.w[3], mx = tx * 4 + (lane >> 3), my = ty;
-				if (mx < (p.W >> 4) && my < (p.H >> 4)) dst[(size_t)my * mw + mx] = m3;
-			}
-		}
+		ulonglong2 v[kTileH];
+		hiz_tile_load(p.vis, geo, tx, ty, lane, v);
+		hiz_tile_reduce(v, geo, tx, ty, lane, [&](uint32_t idx, float m) { pyramid[idx] = m; });
 	}
 	// Programmatic dependent launch: this block's tiles are written; once every block has said so (or exited) the next kernel in the
 	// stream may START if it was launched with programmatic stream serialization (vkv_frame: the pass-B cull, which does not touch
@@ -319,5 +257,19 @@ cudaError_t launch_hiz(const HizParams& p, int num_sms, cudaStream_t stream, int
 		hiz_tail_kernel<<<1, 1024, kTailSmemBytes, stream>>>(p, 0);
 		if (launches) ++*launches;
 	}
+	return cudaGetLastError();
+}
+
+// the small mips alone (strip mode: every rank rebuilds them from the all-gathered last exact mip)
+cudaError_t launch_hiz_tail(const HizParams& p, cudaStream_t stream) {
+	static bool attrSet[64] = {};
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if (!attrSet[dev & 63]) {
+		cudaFuncSetAttribute(hiz_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTailSmemBytes);
+		attrSet[dev & 63] = true;
+	}
+	if (p.exact_levels >= p.pyr.levels) return cudaSuccess;
+	hiz_tail_kernel<<<1, 1024, kTailSmemBytes, stream>>>(p, p.exact_levels);
 	return cudaGetLastError();
 }

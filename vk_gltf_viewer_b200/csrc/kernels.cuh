@@ -31,6 +31,8 @@ struct CullParams {
 	uint32_t* xf_det;
 	uint32_t xf_n;
 	int skip_frustum;            // pass B inside vkv_frame: every input draw already passed this frame's frustum test in pass A
+	uint4* zero_ptr;             // strip mode: the dirty-tile flags of both passes, zeroed by the same launch
+	uint32_t zero_n16;
 };
 
 // A set-up triangle (24.8 fixed-point vertices, positive area) — what the rasteriser's inner loops consume.
@@ -82,6 +84,8 @@ struct RasterParams {
 	uint32_t* drainBarrier;
 	uint32_t* slowWork;
 	unsigned long long neg_zero2; // the fp32 pair (-0.0, -0.0), see common.cuh mul2 (must arrive at run time)
+	uint8_t* dirty;              // strip mode: one byte per 64x16-pixel tile, set for every tile a drawn triangle's bbox touches (NULL otherwise)
+	uint32_t dirtyTilesX;
 };
 
 struct HizParams {
@@ -109,12 +113,30 @@ constexpr int kMaxRanks = 16;
 struct MergeParams {
 	unsigned long long* vis[kMaxRanks];   // every rank's W*H visbuffer (index == rank; [rank] is the local one)
 	uint32_t* flags[kMaxRanks];           // every rank's barrier slots (kMaxRanks u32 each)
+	float* pyr[kMaxRanks];                // every rank's pyramid (strip mode: strip owners store their mips into all of them)
+	uint8_t* dirty[kMaxRanks];            // every rank's dirty-tile flags: [pass][tile], one byte per 64x16-pixel tile
 	int rank, nranks;
 	size_t n;                             // W*H
 	uint32_t* error;                      // local: set to 1 when a barrier timed out
 };
 cudaError_t launch_xgpu_barrier(const MergeParams& p, uint32_t epoch, unsigned long long timeout_ns, cudaStream_t stream);
 cudaError_t launch_merge_min(const MergeParams& p, int num_sms, cudaStream_t stream);
+
+// ---- strip mode (strips.cu): rank r owns the tile rows [tileRows*r/n, tileRows*(r+1)/n) of the screen -------------------------
+struct StripParams {
+	MergeParams mp;
+	uint32_t W, H;
+	PyramidDesc pyr;
+	uint32_t exact_levels;
+	uint32_t tilesX, tilesY;              // 64x16-pixel tiles
+	uint32_t dirtyStride;                 // bytes per pass in the dirty array (tilesX * tilesY rounded up to 16)
+	int pass;                             // which dirty set the peers' contributions are read from
+};
+__host__ __device__ inline uint32_t strip_first_row(uint32_t tilesY, int rank, int nranks) { return (uint32_t)((unsigned long long)tilesY * (unsigned)rank / (unsigned)nranks); }
+cudaError_t launch_strip_merge_hiz(const StripParams& p, int num_sms, cudaStream_t stream);
+cudaError_t launch_strip_gather(const StripParams& p, int num_sms, cudaStream_t stream);
+cudaError_t launch_hash64(const unsigned long long* data, size_t first, size_t count, unsigned long long* out, int num_sms, cudaStream_t stream);
+cudaError_t launch_hiz_tail(const HizParams& p, cudaStream_t stream);
 
 // ---- visbuffer resolve (resolve.cu) ---------------------------------------------------------------------------------
 struct ResolveParams {

@@ -308,6 +308,26 @@ __global__ void prepare_transforms_kernel(const float* __restrict__ transforms, 
 		transform_prologue(transforms + (size_t)t * 16, sVP, mvpOut + (size_t)t * 16, detNeg + t);
 }
 
+// Strip mode (strips.cu): every 64x16-pixel tile a drawn triangle's pixel bounding box touches gets its dirty byte set, so that
+// the strip owners pull only tiles somebody drew into.  Conservative (the box, not the coverage) and idempotent.
+__device__ __forceinline__ void mark_small(const RasterParams& p, const Tri& t) { // bbox <= 8x8 pixels: at most 2x2 tiles
+	const uint32_t tx0 = (uint32_t)t.xmin >> 6, tx1 = (uint32_t)t.xmax >> 6, ty0 = (uint32_t)t.ymin >> 4, ty1 = (uint32_t)t.ymax >> 4;
+	uint8_t* d = p.dirty + ty0 * p.dirtyTilesX;
+	d[tx0] = 1;
+	if (tx1 != tx0) d[tx1] = 1;
+	if (ty1 != ty0) {
+		d += p.dirtyTilesX;
+		d[tx0] = 1;
+		if (tx1 != tx0) d[tx1] = 1;
+	}
+}
+__device__ __forceinline__ void mark_rect(const RasterParams& p, int x0, int x1, int y0, int y1, uint32_t lane) { // whole warp
+	if (!p.dirty || x0 > x1 || y0 > y1) return;
+	const uint32_t tx0 = (uint32_t)x0 >> 6, tx1 = (uint32_t)x1 >> 6, ty0 = (uint32_t)y0 >> 4, ty1 = (uint32_t)y1 >> 4;
+	for (uint32_t ty = ty0; ty <= ty1; ++ty)
+		for (uint32_t tx = tx0 + lane; tx <= tx1; tx += 32) p.dirty[ty * p.dirtyTilesX + tx] = 1;
+}
+
 // Append a triangle that needs the clipper to the clip queue (one lane).  false = queue full.
 __device__ __forceinline__ bool push_clip(const RasterParams& p, const float4& A, const float4& B, const float4& C, uint32_t id) {
 	if (*(volatile uint32_t*)p.clipCount >= p.clipCap) return false; // keeps the counter from running away once full
@@ -525,8 +545,10 @@ __device__ __forceinline__ void meshlet_loop(const RasterParams& p, WarpScratch&
 					}
 				}
 				if (kHot) {
-					if (kind == 1) raster_serial(tri, p.vis, p.W);
-					else if (kind == 2) { if (!push_big(p, tri)) *p.overflow = 1u; }
+					if (kind == 1) {
+						if (p.dirty) mark_small(p, tri);
+						raster_serial(tri, p.vis, p.W);
+					} else if (kind == 2) { if (!push_big(p, tri)) *p.overflow = 1u; }
 					else if (kind == 3) {
 						const uint32_t ia = entry & 0xffu, ib = (entry >> 8) & 0xffu, ic = (entry >> 16) & 0xffu;
 						const float4 A = ws.cxyw[ia], B = ws.cxyw[ib], C = ws.cxyw[ic];
@@ -549,7 +571,10 @@ __device__ __forceinline__ void meshlet_loop(const RasterParams& p, WarpScratch&
 						}
 						__syncwarp();
 						const int n = slow->nsub;
-						for (int k = 0; k < n; ++k) raster_coop(slow->sub[k], p.vis, p.W, lane, slow->sub[k].xmin, slow->sub[k].xmax, slow->sub[k].ymin, slow->sub[k].ymax);
+						for (int k = 0; k < n; ++k) {
+							mark_rect(p, slow->sub[k].xmin, slow->sub[k].xmax, slow->sub[k].ymin, slow->sub[k].ymax, lane);
+							raster_coop(slow->sub[k], p.vis, p.W, lane, slow->sub[k].xmin, slow->sub[k].xmax, slow->sub[k].ymin, slow->sub[k].ymax);
+						}
 						__syncwarp();
 					}
 				}
@@ -622,6 +647,7 @@ __global__ void __launch_bounds__(kDrainThreads, 3) raster_big_kernel(const Rast
 			const int n = sN[warp];
 			for (int k = 0; k < n; ++k) {
 				const Tri& t = sSub[warp][k];
+				mark_rect(p, t.xmin, t.xmax, t.ymin, t.ymax, lane);
 				raster_coop(t, p.vis, p.W, lane, t.xmin, t.xmax, t.ymin, t.ymax);
 			}
 		}
@@ -660,6 +686,7 @@ __global__ void __launch_bounds__(kDrainThreads, 3) raster_big_kernel(const Rast
 			const int tx = t.xmin / kBigTileW + (int)(local % tilesX), ty = t.ymin / kBigTileH + (int)(local / tilesX);
 			const int x0 = max(t.xmin, tx * kBigTileW), x1 = min(t.xmax, tx * kBigTileW + kBigTileW - 1);
 			const int y0 = max(t.ymin, ty * kBigTileH), y1 = min(t.ymax, ty * kBigTileH + kBigTileH - 1);
+			mark_rect(p, x0, x1, y0, y1, lane);
 			raster_coop(t, p.vis, p.W, lane, x0, x1, y0, y1);
 		}
 	}

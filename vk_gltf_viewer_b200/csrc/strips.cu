@@ -1,0 +1,141 @@
+// strips.cu — the exchange step of the meshlet-range-sharded path, by screen-strip ownership ("cheaper variant").
+//
+// Every rank culls and rasterises ITS range of the draw list into its own full-resolution 64-bit visbuffer (raster.cu marks
+// every 64x16-pixel tile a drawn triangle's bounding box touches).  The screen is cut into n horizontal strips of whole tile
+// rows; rank r OWNS strip r.  After a cross-GPU barrier ONE kernel per rank does, for every tile of its strip:
+//   reduce-scatter   read the peers' dirty flags of the tile, pull only the tiles some peer actually drew into (16-byte loads
+//                    over NVLink / NVSwitch peer memory), min them into the owner's keys, store the merged rows back locally;
+//   HiZ per strip    the exact-2x mips of the merged tile, straight from the registers that hold it (hiz_tile.cuh);
+//   all-gather       every mip texel that CHANGED is stored into every rank's pyramid (peer stores).
+// After a second barrier each rank rebuilds the few small mips locally from the all-gathered last exact mip (hiz.cu's tail).
+// The full-resolution keys never travel whole: per frame a rank receives the tiles its peers touched inside its strip
+// (against 2*(n-1)/n * 8*W*H bytes for an all-reduce of the visbuffer) and sends 4 bytes per changed pyramid texel per peer.
+// The merged visbuffer stays distributed — rank r holds rows of strip r — which is what a per-strip consumer (resolve) wants;
+// vkv_gather_strips assembles the whole image on every rank for readers that need it.
+//
+// A key is (~depthBits << 32 | id): min == nearest fragment, ties == lowest id, exactly what atomicMin does inside one GPU, so
+// strip r on rank r is bit-identical to the same rows of a single-GPU frame, and so is the pyramid on every rank.
+// The reference is single-GPU: there is no reference call site for this file.
+#include "hiz_tile.cuh"
+#include "kernels.cuh"
+
+namespace {
+
+constexpr int kStripThreads = 256;
+
+__device__ __forceinline__ ulonglong2 min2(ulonglong2 a, ulonglong2 b) { return make_ulonglong2(a.x < b.x ? a.x : b.x, a.y < b.y ? a.y : b.y); }
+
+// one warp per tile of this rank's strip
+__global__ void __launch_bounds__(kStripThreads) strip_merge_hiz_kernel(const StripParams p) {
+	const uint32_t lane = threadIdx.x & 31;
+	const int N = p.mp.nranks, me = p.mp.rank;
+	const uint32_t row0 = strip_first_row(p.tilesY, me, N), row1 = strip_first_row(p.tilesY, me + 1, N);
+	const uint32_t nTiles = (row1 - row0) * p.tilesX;
+	const HizTileGeo geo = {p.W, p.H, p.exact_levels, {p.pyr.off[0], p.pyr.off[1], p.pyr.off[2], p.pyr.off[3]}, {p.pyr.w[0], p.pyr.w[1], p.pyr.w[2], p.pyr.w[3]}};
+	unsigned long long* const vis = p.mp.vis[me];
+	const float* const localPyr = p.mp.pyr[me];
+	for (uint32_t t = blockIdx.x * (kStripThreads / 32) + (threadIdx.x >> 5); t < nTiles; t += gridDim.x * (kStripThreads / 32)) {
+		const uint32_t tx = t % p.tilesX, ty = row0 + t / p.tilesX;
+		const uint32_t tile = ty * p.tilesX + tx;
+		// which peers drew into this tile in this pass?  lane k asks rank k (a byte over NVLink; the owner's own flag is irrelevant)
+		uint32_t dirty = 0;
+		if ((int)lane < N && (int)lane != me) dirty = *(volatile const uint8_t*)(p.mp.dirty[lane] + (size_t)p.pass * p.dirtyStride + tile);
+		uint32_t peers = __ballot_sync(0xffffffffu, dirty != 0);
+
+		ulonglong2 v[kTileH];
+		hiz_tile_load(vis, geo, tx, ty, lane, v);
+		if (peers) {
+			const uint32_t x0 = tx * kTileW + lane * 2, y0 = ty * kTileH;
+			const bool colIn = x0 < p.W;
+			bool changed = false;
+			while (peers) {
+				const int r = __ffs(peers) - 1;
+				peers &= peers - 1;
+				const unsigned long long* pv = p.mp.vis[r];
+#pragma unroll
+				for (int half = 0; half < 2; ++half) { // 8 rows = 8 independent 16-byte peer loads in flight per lane
+					ulonglong2 q[8];
+#pragma unroll
+					for (int k = 0; k < 8; ++k) {
+						const int row = half * 8 + k;
+						q[k] = make_ulonglong2(~0ull, ~0ull);
+						if (colIn && y0 + row < p.H) q[k] = __ldcg((const ulonglong2*)(pv + (size_t)(y0 + row) * p.W + x0));
+					}
+#pragma unroll
+					for (int k = 0; k < 8; ++k) {
+						const int row = half * 8 + k;
+						const ulonglong2 m = min2(v[row], q[k]);
+						changed |= (m.x != v[row].x) | (m.y != v[row].y);
+						v[row] = m;
+					}
+				}
+			}
+			if (__any_sync(0xffffffffu, changed)) { // the merged rows become the owner's visbuffer
+#pragma unroll
+				for (int row = 0; row < kTileH; ++row)
+					if (colIn && y0 + row < p.H) *(ulonglong2*)(vis + (size_t)(y0 + row) * p.W + x0) = v[row];
+			}
+		}
+		// exact mips of the merged tile -> every rank's pyramid, changed texels only (all pyramids are identical before this frame's
+		// stores, so the local copy tells whether a texel changes anywhere)
+		hiz_tile_reduce(v, geo, tx, ty, lane, [&](uint32_t idx, float m) {
+			if (__float_as_uint(__ldcg(localPyr + idx)) != __float_as_uint(m)) {
+				for (int r = 0; r < N; ++r) __stcg(p.mp.pyr[r] + idx, m);
+			}
+		});
+	}
+}
+
+// all-gather of the merged strips: every rank pulls the strips it does not own from their owners (readers that want the whole
+// image on one GPU: parity tests, vkv_read_visbuffer64 after a strip-mode frame)
+__global__ void __launch_bounds__(256) strip_gather_kernel(const StripParams p) {
+	const int N = p.mp.nranks, me = p.mp.rank;
+	unsigned long long* const vis = p.mp.vis[me];
+	for (int k = 1; k < N; ++k) {
+		const int r = (me + k) % N;
+		const size_t y0 = (size_t)strip_first_row(p.tilesY, r, N) * kTileH, y1 = min((size_t)p.H, (size_t)strip_first_row(p.tilesY, r + 1, N) * kTileH);
+		const size_t lo = y0 * p.W, hi = y1 * p.W; // whole rows: contiguous keys
+		const unsigned long long* src = p.mp.vis[r];
+		for (size_t i = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (size_t)gridDim.x * blockDim.x) vis[i] = __ldcg(src + i);
+	}
+}
+
+// order-independent 64-bit digest of data[first, first + count): sum over i of mix(data[i] + golden * (first + i)) mod 2^64
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
+	x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
+	x ^= x >> 27; x *= 0x94d049bb133111ebull;
+	x ^= x >> 31;
+	return x;
+}
+__global__ void __launch_bounds__(256) hash64_kernel(const unsigned long long* __restrict__ data, size_t first, size_t count, unsigned long long* out) {
+	unsigned long long acc = 0;
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x)
+		acc += mix64(data[first + i] + 0x9e3779b97f4a7c15ull * (unsigned long long)(first + i + 1));
+	for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+	if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+
+} // namespace
+
+cudaError_t launch_strip_merge_hiz(const StripParams& p, int num_sms, cudaStream_t stream) {
+	const uint32_t rows = strip_first_row(p.tilesY, p.mp.rank + 1, p.mp.nranks) - strip_first_row(p.tilesY, p.mp.rank, p.mp.nranks);
+	const uint32_t tiles = rows * p.tilesX;
+	if (tiles == 0) return cudaSuccess;
+	uint32_t grid = (tiles + kStripThreads / 32 - 1) / (kStripThreads / 32);
+	if (grid > (uint32_t)num_sms * 8) grid = (uint32_t)num_sms * 8;
+	strip_merge_hiz_kernel<<<grid, kStripThreads, 0, stream>>>(p);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_strip_gather(const StripParams& p, int num_sms, cudaStream_t stream) {
+	strip_gather_kernel<<<num_sms * 4, 256, 0, stream>>>(p);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_hash64(const unsigned long long* data, size_t first, size_t count, unsigned long long* out, int num_sms, cudaStream_t stream) {
+	if (count == 0) return cudaSuccess;
+	size_t grid = (count + 255) / 256;
+	if (grid > (size_t)num_sms * 8) grid = (size_t)num_sms * 8;
+	hash64_kernel<<<(unsigned)grid, 256, 0, stream>>>(data, first, count, out);
+	return cudaGetLastError();
+}
