@@ -136,6 +136,112 @@ def roofline(dom, stages, ent, hbm, peak_src, traffic, clocks):
     return {"bound": "hbm", "kernel": dom, "traffic": traffic, **hbm_part}
 
 
+def range_sharded_leg(rank, world, local_rank, dist, steps, builder_note):
+    """BASELINE config 5 on `world` GPUs: ONE view of the 1.02-billion-triangle lattice at 7680x4320, the MeshletDraw list dealt to
+    the ranks in interleaved 2048-draw blocks, screen-strip owners pulling dirty tiles over NVLink and all-gathering the pyramid
+    (VKV_FRAME_MERGE_STRIPS, csrc/strips.cu).  Returns the `range_sharded` object of the JSON line (every rank computes it; rank 0
+    prints): device-timed ms per frame (max over ranks), the merge stages, the same frames on ONE GPU for the speed-up, the
+    NVLink bytes per frame against the all-reduce bound, and `merge_parity`: on EVERY rank, after the same three views rendered
+    from a cleared pyramid, the 64-bit digest of the rank's own strip and of the whole pyramid must equal the digests of the same
+    frames rendered unsharded by that rank alone."""
+    import torch
+    from vk_gltf_viewer_b200 import api, multigpu
+    from vk_gltf_viewer_b200.scene import Camera
+    label, spec, (W, H) = CONFIGS[5]
+    scene = build_scene(spec)
+    cnt = scene.counts()
+    views = [scene.default_view(i, NVIEWS) for i in range(NVIEWS)]
+    r = api.Renderer(W, H, device=local_rank)
+    cam = Camera(W, H)
+    cam.look_at(*views[0])
+    pc = r.upload_scene(scene, cam)
+    cam_addrs = []
+    for v in views[1:steps + 8]:
+        cam.look_at(*v)
+        cam_addrs.append(r.upload(np.frombuffer(cam.raw(), np.uint8)))
+    first_cam = pc.cameraBuffer
+    zeros = np.zeros(r.pyramid_floats, np.float32)
+
+    def sync_all():
+        r.sync()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def sweep(flags, n, timed=False, stages=None):
+        """n frames of the sweep from a cleared pyramid; returns the summed device ms (FRAME_TIMED) and the last stats"""
+        r._ck(r.L.vkv_write_pyramid(r.h, zeros.ctypes.data, zeros.size))
+        pc.cameraBuffer = first_cam
+        r.frame(pc, flags)
+        total, st, pulled, sent = 0.0, None, 0, 0
+        for k in range(n):
+            pc.cameraBuffer = cam_addrs[k % len(cam_addrs)]
+            if timed:
+                r.flush_l2(256 << 20)
+            st = r.frame(pc, flags | (api.FRAME_TIMED if timed else 0) | (api.FRAME_STAGES if stages is not None else 0))
+            total += st.total_ms
+            pulled += st.strip_tiles_pulled; sent += st.strip_texels_sent
+            if stages is not None:
+                for name in stages:
+                    stages[name] += getattr(st, name)
+        return total, st, pulled, sent
+
+    sharded = api.FRAME_TWO_PASS | api.FRAME_MERGE_STRIPS
+    single = api.FRAME_TWO_PASS
+    r.set_shard_interleaved(rank, world, 11)
+    multigpu.attach_peers(r, dist)
+    # ---- parity first (three views from a cleared pyramid, sharded vs the same rank alone)
+    y0, y1 = r.strip_rows(rank, world)
+    sync_all()
+    sweep(sharded, 2)
+    h_strip, h_pyr = r.hash(0, y0, y1), r.hash(1)
+    sync_all()
+    r.set_shard_interleaved(0, 1, 11)   # the whole list on this GPU, no exchange
+    sweep(single, 2)
+    ok = (h_strip == r.hash(0, y0, y1)) and (h_pyr == r.hash(1))
+    # ---- one GPU: the same frames, device-timed (every rank measures; they are independent here)
+    n1 = max(3, min(steps, 10))
+    sweep(single, 3)
+    n1_ms, _, _, _ = sweep(single, n1, timed=True)
+    sync_all()
+    # ---- sharded: device-timed
+    r.set_shard_interleaved(rank, world, 11)
+    sweep(sharded, 3)
+    sync_all()
+    ms, st, pulled, sent = sweep(sharded, steps, timed=True)
+    sync_all()
+    names = ("cull_a_ms", "raster_a_ms", "merge_a_ms", "hiz_a_ms", "cull_b_ms", "raster_b_ms", "merge_b_ms", "hiz_b_ms")
+    stg = {k: 0.0 for k in names}
+    ks = min(steps, 20)
+    sweep(sharded, ks, timed=True, stages=stg)
+    sync_all()
+    t = torch.tensor([ms / steps, n1_ms / n1] + [stg[k] / ks for k in names], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    tr = torch.tensor([pulled / steps, sent / steps], device="cuda", dtype=torch.float64)
+    trmax = tr.clone()
+    dist.all_reduce(tr)                          # whole job
+    dist.all_reduce(trmax, op=dist.ReduceOp.MAX)  # busiest rank
+    okt = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+    r.ipc_detach()
+    r.close()
+    vals = t.tolist()
+    bound = 2.0 * (world - 1) / world * 8 * W * H
+    per_rank_bytes = float(trmax[0]) * 8192 + float(trmax[1]) * 4
+    out = {"workload": label, "resolution": [W, H], "meshlet_draws": cnt.draws, "triangles": cnt.triangles_instanced, "meshlets": builder_note,
+           "n_gpus": world, "steps": steps, "ms_per_frame": vals[0], "frames_per_s": 1e3 / vals[0], "gtris_per_s": cnt.triangles_instanced / vals[0] / 1e6,
+           "n1_ms_per_frame": vals[1], "speedup_vs_n1": vals[1] / vals[0], "merge_parity": bool(int(okt.item())),
+           "merge_parity_how": "per rank: vkv_hash of its own strip rows and of the whole pyramid after 3 views from a cleared pyramid == the same frames rendered unsharded on that rank",
+           "stages_ms_max_over_ranks": {k[:-3]: round(v, 5) for k, v in zip(names, vals[2:])},
+           "merge_a_ms": vals[2 + names.index("merge_a_ms")], "merge_b_ms": vals[2 + names.index("merge_b_ms")],
+           "nvlink": {"tiles_pulled_per_frame_all_ranks": float(tr[0]), "pyramid_texels_sent_per_frame_all_ranks": float(tr[1]),
+                      "bytes_per_frame_busiest_rank": per_rank_bytes, "allreduce_bound_bytes_per_rank": bound,
+                      "fraction_of_allreduce_bound": per_rank_bytes / bound,
+                      "note": "received: 8 KB per (64x16-pixel tile, peer that drew into it) inside the rank's strip; sent: 4 B per changed pyramid texel per peer; "
+                              "bound = 2*(n-1)/n * 8*W*H, what a ring all-reduce of the 64-bit visbuffer moves per rank per merge (two merges per frame)"},
+           "scaling": "strong", "l2": "256 MB scratch written between timed frames"}
+    return out
+
+
 def meshlet_averages(scene):
     """average vertices / triangles per MeshletDraw of the scene (weighted by how often each primitive is drawn)"""
     d = scene.draws()
@@ -179,7 +285,10 @@ def main():
     ap.add_argument("--config", type=int, default=3)
     ap.add_argument("--shard", default="auto", choices=["auto", "views", "range"],
                     help="multi-GPU: independent views per GPU (default, cfg 1-4) or one view sharded by MeshletDraw range (cfg 5)")
+    ap.add_argument("--merge", default="strips", choices=["strips", "allreduce"],
+                    help="range sharding: screen-strip owners pull dirty tiles + all-gather the pyramid (default) or the round-1 u64 min all-reduce of the whole visbuffer")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-range-leg", action="store_true", help="multi-GPU default run: skip the cfg-5 range-sharded leg (`range_sharded` key)")
     ap.add_argument("--one-pass", action="store_true", help="reference one-pass mode instead of the two-pass extension")
     ap.add_argument("--meshlets", default="meshopt", choices=["meshopt", "morton"],
                     help="meshlet builder of the synthetic scene: the reference's partition (meshopt_buildMeshlets + optimizeMeshlet, default) "
@@ -247,6 +356,7 @@ def main():
         my_views = [views[i % NVIEWS] for i in range(warm + steps + 1)]
 
     r = api.Renderer(W, H, device=local_rank)
+    pyr_floats = r.pyramid_floats
     cam = Camera(W, H)
     cam.look_at(*my_views[0])
     pc = r.upload_scene(scene, cam)
@@ -254,7 +364,7 @@ def main():
     if shard == "range" and world > 1:
         r.set_shard_interleaved(rank, world, 11)  # 2048-draw blocks round-robin: balances the surviving work (a contiguous half does not)
         multigpu.attach_peers(r, dist)
-        flags |= api.FRAME_MERGE
+        flags |= api.FRAME_MERGE if args.merge == "allreduce" else api.FRAME_MERGE_STRIPS
     # all cameras of the sweep resident in HBM: the device-timed loop switches the camera ADDRESS per frame
     cam_addrs = []
     for v in my_views[1:]:
@@ -341,6 +451,17 @@ def main():
 
     clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
 
+    # ---- N > 1: after the view-sharded measurement, the meshlet-range-sharded configuration (BASELINE config 5) with its exchange
+    # step, parity-checked against one GPU — so that the driver's scaling record carries both multi-GPU paths
+    range_leg = None
+    if dist is not None and shard == "views" and not args.no_range_leg:
+        r.close()
+        try:
+            range_leg = range_sharded_leg(rank, world, local_rank, dist, min(steps, 20), builder_note)
+        except Exception as e:  # noqa: BLE001 — the headline line must still print; the failure is reported in it
+            range_leg = {"error": repr(e), "merge_parity": False}
+        r = None
+
     if dist is not None:
         import torch
         t = torch.tensor([dev_ms, e2e_s, e2e_rb_s], device="cuda", dtype=torch.float64)
@@ -367,7 +488,7 @@ def main():
         per_gpu = 1.0 / world if shard == "range" else 1.0
         N = cnt.draws * per_gpu
         U = cnt.meshlets_unique * 36 + cnt.transforms * 64 + cnt.primitives * 64 + 352
-        pyr_bytes = 4 * r.pyramid_floats
+        pyr_bytes = 4 * pyr_floats
         avg = lambda x: x / K * per_gpu
         bytes_cull_a = 12 * N + U + 4 * (avg(vis_a) + avg(occ_a))
         bytes_cull_b = 4 * avg(occ_a) + 12 * avg(occ_a) + U + 4 * avg(vis_b)
@@ -379,7 +500,9 @@ def main():
         if clear_fused:
             bytes_cull_a += bytes_clear
             bytes_clear = 0
-        bytes_merge = 8 * W * H * 2 if (flags & api.FRAME_MERGE) else 0  # per GPU: strip read from n ranks + written to n ranks = 2 * 8WH
+        bytes_merge = 8 * W * H * 2 if (flags & api.FRAME_MERGE) else 0  # all-reduce merge, per GPU: strip read from n ranks + written to n ranks = 2 * 8WH
+        if flags & api.FRAME_MERGE_STRIPS:  # strip mode: the owner reads its own strip once (+ the dirty peer tiles, reported separately)
+            bytes_merge = 8 * W * H / world
         stages = {}
         for name, b, ms in (("clear", bytes_clear, stage["clear_ms"]), ("cull_a", bytes_cull_a, stage["cull_a_ms"]),
                             ("raster_a", avg(vis_a) * per_meshlet, stage["raster_a_ms"]), ("merge_a", bytes_merge, stage["merge_a_ms"]),
@@ -423,6 +546,8 @@ def main():
             "stages": stages,
             "clocks": clocks,
         }
+        if range_leg is not None:
+            line["range_sharded"] = range_leg
         if not args.no_cpu_baseline:
             nfr = 2 if args.config in (3, 5) else 5
             ct = cpu_frames(scene, W, H, views, nfr)
@@ -430,7 +555,8 @@ def main():
             line["cpu_baseline"] = {"value": cfps, "unit": "frames/s", "cores": ncores, "kind": "port",
                                     "sample": f"{nfr} full two-pass frames of the same sweep after 1 warm-up frame (CPU oracle, all host threads)"}
         print(json.dumps(line))
-    r.close()
+    if r is not None:
+        r.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

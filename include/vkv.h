@@ -67,7 +67,10 @@ typedef struct vkv_stats {
 	uint32_t visible_a, occluded_a, visible_b, tested_b;
 	float clear_ms, cull_a_ms, raster_a_ms, hiz_a_ms, cull_b_ms, raster_b_ms, hiz_b_ms, total_ms; /* total_ms: VKV_FRAME_TIMED; the rest: + VKV_FRAME_STAGES */
 	uint32_t kernel_launches;    /* kernels of this library launched by the call */
-	float merge_a_ms, merge_b_ms; /* VKV_FRAME_TIMED + VKV_FRAME_STAGES + VKV_FRAME_MERGE */
+	float merge_a_ms, merge_b_ms; /* VKV_FRAME_TIMED + VKV_FRAME_STAGES + VKV_FRAME_MERGE / VKV_FRAME_MERGE_STRIPS (strip mode: barrier + pull-merge +
+	                                 exact mips + all-gather + barrier; hiz_*_ms is then the small-mip tail alone) */
+	uint32_t strip_tiles_pulled; /* VKV_FRAME_MERGE_STRIPS, both passes: (64x16-pixel tile, peer) pairs this rank pulled over NVLink, 8 KB each */
+	uint32_t strip_texels_sent;  /* ... and pyramid texels it stored into its peers, 4 B each */
 } vkv_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------------------------- */

@@ -333,6 +333,7 @@ int enqueue_strip_exchange(vkv_ctx* c, int pass, int* launches) {
 	sp.mp = c->mp; sp.mp.n = (size_t)c->W * c->H;
 	sp.W = c->W; sp.H = c->H; sp.pyr = c->pyr; sp.exact_levels = c->exact_levels;
 	sp.tilesX = c->tiles_x; sp.tilesY = c->tiles_y; sp.dirtyStride = c->dirty_stride; sp.pass = pass;
+	sp.stats = &c->counters->strip_tiles_pulled;
 	CK(launch_xgpu_barrier(c->mp, ++c->epoch, timeout_ns, c->stream));
 	CK(launch_strip_merge_hiz(sp, c->num_sms, c->stream));
 	CK(launch_xgpu_barrier(c->mp, ++c->epoch, timeout_ns, c->stream));
@@ -651,6 +652,8 @@ int vkv_frame(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, uint32_t flags, 
 		out->visible_b = c->h_counters->visible[1];
 		out->tested_b = two ? c->h_counters->occluded[0] : 0;
 		out->kernel_launches = (uint32_t)launches;
+		out->strip_tiles_pulled = c->h_counters->strip_tiles_pulled;
+		out->strip_texels_sent = c->h_counters->strip_texels_sent;
 		if (timed) {
 			auto el = [&](int a, int b) { float ms = 0; cudaEventElapsedTime(&ms, c->stage_ev[a], c->stage_ev[b]); return ms; };
 			out->total_ms = el(E_BEGIN, E_COUNT);

@@ -131,6 +131,7 @@ struct StripParams {
 	uint32_t tilesX, tilesY;              // 64x16-pixel tiles
 	uint32_t dirtyStride;                 // bytes per pass in the dirty array (tilesX * tilesY rounded up to 16)
 	int pass;                             // which dirty set the peers' contributions are read from
+	uint32_t* stats;                      // [0] += tiles pulled from peers, [1] += pyramid texels stored to peers (may be NULL)
 };
 __host__ __device__ inline uint32_t strip_first_row(uint32_t tilesY, int rank, int nranks) { return (uint32_t)((unsigned long long)tilesY * (unsigned)rank / (unsigned)nranks); }
 cudaError_t launch_strip_merge_hiz(const StripParams& p, int num_sms, cudaStream_t stream);

@@ -34,6 +34,7 @@ __global__ void __launch_bounds__(kStripThreads) strip_merge_hiz_kernel(const St
 	const HizTileGeo geo = {p.W, p.H, p.exact_levels, {p.pyr.off[0], p.pyr.off[1], p.pyr.off[2], p.pyr.off[3]}, {p.pyr.w[0], p.pyr.w[1], p.pyr.w[2], p.pyr.w[3]}};
 	unsigned long long* const vis = p.mp.vis[me];
 	const float* const localPyr = p.mp.pyr[me];
+	uint32_t pulled = 0, sent = 0; // this warp's tiles pulled over NVLink / this lane's texels stored to peers (statistics)
 	for (uint32_t t = blockIdx.x * (kStripThreads / 32) + (threadIdx.x >> 5); t < nTiles; t += gridDim.x * (kStripThreads / 32)) {
 		const uint32_t tx = t % p.tilesX, ty = row0 + t / p.tilesX;
 		const uint32_t tile = ty * p.tilesX + tx;
@@ -44,6 +45,7 @@ __global__ void __launch_bounds__(kStripThreads) strip_merge_hiz_kernel(const St
 
 		ulonglong2 v[kTileH];
 		hiz_tile_load(vis, geo, tx, ty, lane, v);
+		pulled += __popc(peers);
 		if (peers) {
 			const uint32_t x0 = tx * kTileW + lane * 2, y0 = ty * kTileH;
 			const bool colIn = x0 < p.W;
@@ -81,8 +83,16 @@ __global__ void __launch_bounds__(kStripThreads) strip_merge_hiz_kernel(const St
 		hiz_tile_reduce(v, geo, tx, ty, lane, [&](uint32_t idx, float m) {
 			if (__float_as_uint(__ldcg(localPyr + idx)) != __float_as_uint(m)) {
 				for (int r = 0; r < N; ++r) __stcg(p.mp.pyr[r] + idx, m);
+				sent += (uint32_t)(N - 1);
 			}
 		});
+	}
+	if (p.stats) {
+		for (int o = 16; o; o >>= 1) sent += __shfl_xor_sync(0xffffffffu, sent, o);
+		if (lane == 0) {
+			if (pulled) atomicAdd(p.stats, pulled);
+			if (sent) atomicAdd(p.stats + 1, sent);
+		}
 	}
 }
 
