@@ -362,13 +362,14 @@ def test_shared_reciprocal_division():
     r.close()
 
 
-@pytest.mark.parametrize("cap", ["1", "3", "64"])
-def test_raster_queue_overflow_falls_back_to_the_rewalk(monkeypatch, cap):
-    """raster_kernel queues what a lane cannot finish alone (the clipper's pieces, triangles above the lane-serial limit) for
-    raster_big_kernel; with a tiny queue (VKV_BIG_CAP, read at vkv_create) it overflows on these scenes and the drain kernel's
-    re-walk of the meshlet list must produce the same bits: near-plane clipping + guard band (ground plane under the camera), two
-    huge triangles (full-screen quad), an interior scene (atrium) and ordinary small triangles (lattice)"""
-    monkeypatch.setenv("VKV_BIG_CAP", cap)
+@pytest.mark.parametrize("caps", [("3", "2"), ("1", "100000"), ("100000", "1")])
+def test_raster_queue_overflow_falls_back_to_the_rewalk(monkeypatch, caps):
+    """raster_kernel queues what a lane cannot finish alone (triangles for the clipper, triangles above the lane-serial limit) for
+    raster_big_kernel; with tiny queues (VKV_BIG_CAP / VKV_CLIP_CAP, read at vkv_create) both overflow on these scenes and the drain
+    kernel's re-walk of the meshlet list must produce the same bits: near-plane clipping + guard band (ground plane under the
+    camera), two huge triangles (full-screen quad), an interior scene (atrium) and ordinary small triangles (lattice)"""
+    monkeypatch.setenv("VKV_BIG_CAP", caps[0])
+    monkeypatch.setenv("VKV_CLIP_CAP", caps[1])
     run_views(S.ground_plane(24, 40.0), 640, 480, [((0, 0, 3), (0, -0.2, 0)), ((0, 2, 0), (0.3, -1, 0.2))], two_pass=True)
     run_views(S.fullscreen_quad(), 800, 600, [((0, 0, 3), (0, 0, 0))])
     s = Scene.atrium(16)

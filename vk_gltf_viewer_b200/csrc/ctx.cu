@@ -42,6 +42,8 @@ struct vkv_ctx {
 	uint32_t xf_count = 0;
 	BigTri* big_tris = nullptr;       // large-triangle queue (raster.cu)
 	uint32_t big_cap = 1u << 20;      // VKV_BIG_CAP overrides (tests force the overflow path with a tiny queue)
+	ClipTri* clip_tris = nullptr;     // clip queue (raster.cu)
+	uint32_t clip_cap = 1u << 18;     // VKV_CLIP_CAP overrides
 	// multi-GPU: this GPU's shard of the draw list and the peers' visbuffers mapped through CUDA IPC
 	uint32_t shard_first = 0, shard_count = 0;       // contiguous shard
 	uint32_t shard_block_log2 = 0, shard_rank = 0, shard_nranks = 1; // interleaved shard (blocks of 2^k draws, round-robin)
@@ -268,13 +270,14 @@ RasterParams make_raster(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, const
 	r.neg_zero2 = kNegZero2;
 	r.mvp = c->xf_mvp; r.detNeg = c->xf_det;
 	r.big = c->big_tris; r.bigCap = c->big_cap; r.bigCursor = &c->counters->big_cursor; r.bigNext = &c->counters->big_next;
-	r.overflow = &c->counters->raster_overflow; r.slowWork = &c->counters->slow_work;
+	r.clip = c->clip_tris; r.clipCap = c->clip_cap; r.clipCount = &c->counters->clip_count; r.clipNext = &c->counters->clip_next;
+	r.overflow = &c->counters->raster_overflow; r.drainBarrier = &c->counters->drain_barrier; r.slowWork = &c->counters->slow_work;
 	return r;
 }
 
 // raster_kernel + raster_big_kernel behind a reset of the large-triangle queue
 int enqueue_raster(vkv_ctx* c, const RasterParams& r, int* launches) {
-	CK(cudaMemsetAsync(&c->counters->big_next, 0, offsetof(FrameCounters, raster_reset_end) - offsetof(FrameCounters, big_next), c->stream)); // queue, cursors, overflow flag
+	CK(cudaMemsetAsync(&c->counters->big_next, 0, offsetof(FrameCounters, raster_reset_end) - offsetof(FrameCounters, big_next), c->stream)); // queues, cursors, barrier
 	CK(launch_raster(r, c->num_sms, c->stream));
 	if (launches) *launches += 2;
 	return VKV_OK;
@@ -390,7 +393,11 @@ int vkv_create(vkv_ctx** out, int cuda_device, uint32_t width, uint32_t height) 
 	}
 	cudaMemset(c->counters, 0, sizeof(FrameCounters));
 	if (const char* e = getenv("VKV_BIG_CAP")) c->big_cap = (uint32_t)std::max(1L, std::min(1L << 22, atol(e)));
-	if (cudaMalloc(&c->big_tris, (size_t)c->big_cap * sizeof(BigTri)) != cudaSuccess) { c->err = "allocating the large-triangle queue failed"; return bail(VKV_ERR_OOM); }
+	if (const char* e = getenv("VKV_CLIP_CAP")) c->clip_cap = (uint32_t)std::max(1L, std::min(1L << 22, atol(e)));
+	if (cudaMalloc(&c->big_tris, (size_t)c->big_cap * sizeof(BigTri)) != cudaSuccess || cudaMalloc(&c->clip_tris, (size_t)c->clip_cap * sizeof(ClipTri)) != cudaSuccess) {
+		c->err = "allocating the large-triangle / clip queues failed";
+		return bail(VKV_ERR_OOM);
+	}
 	int rc = alloc_targets(c, width, height);
 	if (rc != VKV_OK) return bail(rc);
 	*out = c;
@@ -420,6 +427,7 @@ void vkv_destroy(vkv_ctx* c) {
 	if (c->xf_mvp) cudaFree(c->xf_mvp);
 	if (c->xf_det) cudaFree(c->xf_det);
 	if (c->big_tris) cudaFree(c->big_tris);
+	if (c->clip_tris) cudaFree(c->clip_tris);
 	if (c->mat_colors) cudaFree(c->mat_colors);
 	if (c->tmp_count) cudaFree(c->tmp_count);
 	if (c->counters) cudaFree(c->counters);

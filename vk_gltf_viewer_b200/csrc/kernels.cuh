@@ -52,6 +52,12 @@ struct BigTri {
 	uint32_t pad;
 };
 
+// A triangle some vertex of which is outside the near / far / guard-band planes: clip coordinates, waiting for the clipper
+struct ClipTri {
+	float4 a, b, c;                  // clip x, y, z, w
+	uint32_t id;
+	uint32_t pad[3];
+};
 constexpr int kBigSlotShift = 40;    // FrameCounters::big_cursor = records << 40 | tile-work items (raster.cu push_big)
 struct RasterParams {
 	const vkv_MeshletDraw* draws;
@@ -70,8 +76,13 @@ struct RasterParams {
 	uint32_t bigCap;
 	unsigned long long* bigCursor;
 	uint32_t* bigNext;
-	uint32_t* overflow;          // set when the queue was full
-	uint32_t* slowWork;          // work-stealing cursor of the overflow re-walk
+	ClipTri* clip;               // clip queue (filled by raster_kernel, drained by raster_big_kernel's first phase)
+	uint32_t clipCap;
+	uint32_t* clipCount;
+	uint32_t* clipNext;
+	uint32_t* overflow;          // set when either queue was full
+	uint32_t* drainBarrier;
+	uint32_t* slowWork;
 	unsigned long long neg_zero2; // the fp32 pair (-0.0, -0.0), see common.cuh mul2 (must arrive at run time)
 	uint8_t* dirty;              // strip mode: one byte per 64x16-pixel tile, set for every tile a drawn triangle's bbox touches (NULL otherwise)
 	uint32_t dirtyTilesX;

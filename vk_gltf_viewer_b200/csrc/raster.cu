@@ -328,23 +328,22 @@ __device__ __forceinline__ void mark_rect(const RasterParams& p, int x0, int x1,
 		for (uint32_t tx = tx0 + lane; tx <= tx1; tx += 32) p.dirty[ty * p.dirtyTilesX + tx] = 1;
 }
 
-// A triangle that needs the clipper, inside the hot kernel (one lane, out of line): clip, set the pieces up and queue every piece
-// for the drain kernel.  Rare and slow by design — compiled under the hot kernel's register cap it spills inside this function,
-// which costs the other 31 lanes of the warp some waiting and the fast path nothing.  false = the queue was full.
-__device__ __noinline__ bool clip_and_push(const RasterParams& p, float4 A, float4 B, float4 C, uint32_t id) {
-	Tri sub[8];
-	const int n = clip_and_setup(A, B, C, id, p.W, p.H, sub);
-	bool ok = true;
-	for (int k = 0; k < n; ++k) ok = push_big(p, sub[k]) && ok;
-	return ok;
+// Append a triangle that needs the clipper to the clip queue (one lane).  false = queue full.
+__device__ __forceinline__ bool push_clip(const RasterParams& p, const float4& A, const float4& B, const float4& C, uint32_t id) {
+	if (*(volatile uint32_t*)p.clipCount >= p.clipCap) return false; // keeps the counter from running away once full
+	const uint32_t slot = atomicAdd(p.clipCount, 1u);
+	if (slot >= p.clipCap) return false;
+	ClipTri c;
+	c.a = A; c.b = B; c.c = C; c.id = id; c.pad[0] = c.pad[1] = c.pad[2] = 0;
+	p.clip[slot] = c;
+	return true;
 }
 
 // The meshlet loop, in two instantiations of the same text:
 //   kHot = true   raster_kernel.  Everything a lane can finish alone — vertex transform, facing cull, set-up, the lane-serial
-//                 scan of small triangles.  Triangles larger than the serial limit are QUEUED for raster_big_kernel; triangles
-//                 that need the clipper go through an out-of-line call whose pieces are queued too.  Neither the clipper's
-//                 stack arrays nor the cooperative scan's 64-bit edge functions count against this kernel's registers:
-//                 4 blocks of 8 warps per SM instead of 2.
+//                 scan of small triangles.  What it cannot (triangles that need the clipper, triangles larger than the serial
+//                 limit) is QUEUED for raster_big_kernel, so neither the clipper's stack arrays nor the cooperative scan's
+//                 64-bit edge functions count against this kernel's registers: 3 blocks of 8 warps per SM instead of 2.
 //   kHot = false  the overflow re-walk inside raster_big_kernel (only when a queue was full): the same loop, skipping what the
 //                 hot kernel already drew and clipping / scanning everything else in place.  A triangle drawn twice is harmless:
 //                 the visibility write is an atomic min.
@@ -553,7 +552,7 @@ __device__ __forceinline__ void meshlet_loop(const RasterParams& p, WarpScratch&
 					else if (kind == 3) {
 						const uint32_t ia = entry & 0xffu, ib = (entry >> 8) & 0xffu, ic = (entry >> 16) & 0xffu;
 						const float4 A = ws.cxyw[ia], B = ws.cxyw[ib], C = ws.cxyw[ic];
-						if (!clip_and_push(p, make_float4(A.x, A.y, ws.cz[ia], A.z), make_float4(B.x, B.y, ws.cz[ib], B.z), make_float4(C.x, C.y, ws.cz[ic], C.z), id))
+						if (!push_clip(p, make_float4(A.x, A.y, ws.cz[ia], A.z), make_float4(B.x, B.y, ws.cz[ib], B.z), make_float4(C.x, C.y, ws.cz[ic], C.z), id))
 							*p.overflow = 1u;
 					}
 				} else { // overflow re-walk: everything the hot kernel did NOT draw itself, in place, one triangle at a time
@@ -595,16 +594,67 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) raster_kernel(const Rast
 	meshlet_loop<true>(p, scratch[threadIdx.x >> 5], nullptr, p.work, threadIdx.x & 31);
 }
 
-// Drain of the queue raster_kernel leaves behind:
-//   1. large-triangle queue (everything above the lane-serial limit, every piece the clipper produced): one warp per
-//      (triangle, 128x64-pixel tile) work item;
-//   2. only if the queue overflowed: the re-walk of the meshlet list (meshlet_loop<false>), one warp per block.
+// Grid barrier of the drain kernel (all its blocks are co-resident: the launch sizes the grid from the occupancy query).
+__device__ __forceinline__ void drain_grid_barrier(uint32_t* counter) {
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		__threadfence();
+		atomicAdd(counter, 1u);
+		while (*(volatile uint32_t*)counter < gridDim.x) __nanosleep(64);
+		__threadfence();
+	}
+	__syncthreads();
+}
+
+// Drain of the two queues raster_kernel leaves behind:
+//   1. clip queue: one warp per triangle — one lane clips and sets the pieces up; a piece spanning several 128x64 tiles joins
+//      the large-triangle queue, the others are scanned by the warp at once.  (Skipped, barrier included, when the queue is empty.)
+//   2. large-triangle queue: one warp per (triangle, 128x64-pixel tile) work item.
+//   3. only if a queue overflowed: the re-walk of the meshlet list (meshlet_loop<false>), one warp per block.
 __global__ void __launch_bounds__(kDrainThreads, 3) raster_big_kernel(const RasterParams p) {
 	__shared__ Tri sTri[kDrainThreads / 32];
+	__shared__ Tri sSub[kDrainThreads / 32][8];
 	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	// the two words that decide what there is to do, fetched together (one L2 round trip): both are final when this kernel starts
-	const unsigned long long cur = *(volatile unsigned long long*)p.bigCursor;
+
+	// the three words that decide what there is to do, fetched together (one L2 round trip, not three): all are final when this
+	// kernel starts, except the queue cursor when the clip phase below appends pieces (re-read behind its barrier)
+	const uint32_t clipCountNow = *(volatile uint32_t*)p.clipCount;
+	unsigned long long cur = *(volatile unsigned long long*)p.bigCursor;
 	const uint32_t overflowed = *(volatile uint32_t*)p.overflow;
+	const uint32_t nClip = min(clipCountNow, p.clipCap);
+	if (nClip) {
+		__shared__ int sN[kDrainThreads / 32];
+		for (;;) {
+			uint32_t ci = 0;
+			if (lane == 0) ci = atomicAdd(p.clipNext, 1u);
+			ci = __shfl_sync(0xffffffffu, ci, 0);
+			if (ci >= nClip) break;
+			__syncwarp();
+			if (lane == 0) {
+				const ClipTri c = p.clip[ci];
+				const int n = clip_and_setup(c.a, c.b, c.c, c.id, p.W, p.H, sSub[warp]);
+				int kept = 0; // clipped pieces are often the largest triangles of a scene: spread those over the GPU too
+				for (int k = 0; k < n; ++k) {
+					const Tri& t = sSub[warp][k];
+					const bool multiTile = (t.xmax / kBigTileW != t.xmin / kBigTileW) || (t.ymax / kBigTileH != t.ymin / kBigTileH);
+					if (multiTile && push_big(p, t)) continue;
+					if (kept != k) sSub[warp][kept] = t;
+					++kept;
+				}
+				sN[warp] = kept;
+			}
+			__syncwarp();
+			const int n = sN[warp];
+			for (int k = 0; k < n; ++k) {
+				const Tri& t = sSub[warp][k];
+				mark_rect(p, t.xmin, t.xmax, t.ymin, t.ymax, lane);
+				raster_coop(t, p.vis, p.W, lane, t.xmin, t.xmax, t.ymin, t.ymax);
+			}
+		}
+		drain_grid_barrier(p.drainBarrier); // every piece has been queued before anyone reads the queue's extent
+		cur = *(volatile unsigned long long*)p.bigCursor;
+	}
+
 	uint32_t nRec = min((uint32_t)(cur >> kBigSlotShift), p.bigCap);
 	if ((cur & kBigTileMask) > 0xffffffffull) {
 		uint32_t lo = 0, hi = nRec; // first sentinel slot
