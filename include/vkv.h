@@ -55,12 +55,16 @@ enum {
 	VKV_FRAME_MERGE_STRIPS = 1 << 7, /* multi-GPU: screen-strip ownership — each rank pulls the tiles its peers drew into its strip, builds
 	                                  the strip's exact mips and stores the changed texels into every rank's pyramid; the merged
 	                                  visbuffer stays distributed (rank r holds strip r), the pyramid is complete everywhere */
+	VKV_FRAME_CONE_CULL = 1 << 8,  /* extension, OFF in parity mode: reject meshlets whose normal cone faces away from the camera before the
+	                                  occlusion test (needs vkv_set_cone_table).  Removes only meshlets none of whose triangles the mesh
+	                                  shader's facing test would keep: the visbuffer is unchanged, the visible lists get shorter */
 	VKV_FRAME_STAGES = 1 << 6      /* with VKV_FRAME_TIMED: also the per-stage *_ms fields (an event between two launches; it keeps the
 	                                  pass-B cull from overlapping the pyramid's tail, so total_ms is a few us higher than without) */
 };
 
 /* per-draw status byte (VKV_FRAME_STATUS) — same values as the oracle's */
-enum { VKV_ST_FRUSTUM_CULLED = 0, VKV_ST_OCCLUDED = 1, VKV_ST_VISIBLE = 2, VKV_ST_NOT_TESTED = 3 };
+enum { VKV_ST_FRUSTUM_CULLED = 0, VKV_ST_OCCLUDED = 1, VKV_ST_VISIBLE = 2, VKV_ST_NOT_TESTED = 3,
+       VKV_ST_CONE_CULLED = 0x80 /* VKV_FRAME_CONE_CULL: rejected by the normal cone (class bits 0: culled before the occlusion test) */ };
 
 typedef struct vkv_stats {
 	uint32_t draws;              /* meshletDrawCount */
@@ -90,6 +94,9 @@ int vkv_download(vkv_ctx*, uint64_t dev_addr, void* host, size_t bytes);        
 
 /* ---- per frame -------------------------------------------------------------------------------------------- */
 int vkv_frame(vkv_ctx*, const vkv_VisbufferPushConstants* pc, uint32_t flags, vkv_stats* out);
+/* Side buffer of the optional cone cull (VKV_FRAME_CONE_CULL): device address of a table with one entry per primitive — the address
+ * of that primitive's vkv_MeshletCone[meshletCount] (vkv_abi.h; vkvh_scene_upload_cones builds both).  0 removes it. */
+int vkv_set_cone_table(vkv_ctx*, uint64_t table_dev_addr);
 /* individually callable stages (per-stage timing / parity).  pass: 0 = A (reference), 1 = B (two-pass extension) */
 int vkv_clear(vkv_ctx*);
 int vkv_cull(vkv_ctx*, const vkv_VisbufferPushConstants* pc, int pass, uint32_t flags, uint32_t* n_visible);

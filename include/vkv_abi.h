@@ -134,6 +134,22 @@ VKV_STATIC_ASSERT(sizeof(vkv_VisbufferPushConstants) == 56, "VisbufferPushConsta
 VKV_STATIC_ASSERT(offsetof(vkv_VisbufferPushConstants, transformBuffer) == 16, "PC.transformBuffer");
 VKV_STATIC_ASSERT(offsetof(vkv_VisbufferPushConstants, depthPyramid) == 48, "PC.depthPyramid");
 
+/* ---- extension (not a reference struct): the normal cone of a meshlet, the side buffer of the optional cone cull ----------------
+ * meshopt_Bounds' cone fields (meshoptimizer.h:507-541), which the reference computes nowhere (assets.cpp:323 runs the builder
+ * with cone weight 0 and never calls meshopt_computeMeshletBounds).  The 36-byte Meshlet record cannot change, so the cones live
+ * in a buffer of their own: one array per primitive, indexed like the primitive's Meshlet[], found through a table of device
+ * addresses indexed by primitiveIndex (vkv_set_cone_table).  A meshlet is backfacing as a whole when
+ *   dot(normalize(cone_apex - eye), cone_axis) >= cone_cutoff            (meshoptimizer.h:531)
+ * with eye the camera position in the mesh's OWN space.  cutoff >= 2 disables the test for the meshlet (double-sided material,
+ * normals spread over more than a hemisphere). */
+typedef struct vkv_MeshletCone {
+	float apex[3];
+	float cutoff;
+	float axis[3];
+	float reserved;
+} vkv_MeshletCone;
+VKV_STATIC_ASSERT(sizeof(vkv_MeshletCone) == 32, "MeshletCone");
+
 /* visbuffer.h.glsl:58-60 */
 static inline uint32_t vkv_pack_visbuffer(uint32_t drawIndex, uint32_t primitiveId) {
 	return (drawIndex << VKV_TRIANGLE_BITS) | primitiveId;

@@ -110,6 +110,14 @@ int vkvh_scene_host_pc(vkvh_scene*, const vkv_Camera* camera, vkv_VisbufferPushC
 typedef int (*vkvh_upload_fn)(void* user, const void* host, size_t bytes, uint64_t* dev_addr);
 int vkvh_scene_upload(vkvh_scene*, vkvh_upload_fn upload, void* user, const vkv_Camera* camera, vkv_VisbufferPushConstants* out);
 
+/* --- normal cones (extension: the side buffer of the optional cone cull, vkv_abi.h vkv_MeshletCone) -----------------------
+ * Computed per meshlet with meshopt_computeMeshletBounds' algorithm when a primitive is added.  The table has one entry per
+ * primitive: the address of its vkv_MeshletCone[meshletCount].  Primitives with a double-sided material get cutoff = 2 (never
+ * rejected).  _host: HOST addresses (for the CPU oracle; valid while the scene lives); _upload: device addresses through the
+ * vkv_upload-shaped callback, *table_addr then goes to vkv_set_cone_table. */
+int vkvh_scene_host_cones(vkvh_scene*, const uint64_t** table);
+int vkvh_scene_upload_cones(vkvh_scene*, vkvh_upload_fn upload, void* user, uint64_t* table_addr);
+
 /* --- camera (camera.cpp:170-193) ----------------------------------------------------------------------------- */
 /* first!=0: all four matrices are set to the new viewProjection (headless start).
  * otherwise prev* <- current, then viewProjection/occlusionViewProjection/frustum are rewritten. */

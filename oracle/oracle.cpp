@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <limits>
 #include <cstring>
 #include <functional>
 #include <thread>
@@ -133,8 +134,32 @@ bool g_diagnostics = true;
 constexpr float kNoise = 8.0f * 5.9604645e-8f;   // 8 roundings of 2^-24
 
 // visbuffer.task.glsl:44-65 for one MeshletDraw
+// Optional normal-cone stage (extension, NOT in the reference — assets.cpp:323 disables cones): the camera position in each
+// mesh-node's own space, from rows x, y, w of viewProjection * transform (the same expression, in the same association, as
+// common.cuh transform_prologue), and the per-primitive cone arrays.
+struct ConeCtx { const uint64_t* table; const V4* eye; };
+
+V4 mesh_space_eye(const float* VP, const float* T) {
+	float m[16];
+	mul44m(VP, T, m);
+	const V3 r0{m[0], m[4], m[8]}, r1{m[1], m[5], m[9]}, r2{m[3], m[7], m[11]};
+	const float b0 = -m[12], b1 = -m[13], b2 = -m[15];
+	const V3 x12{r1.y * r2.z - r1.z * r2.y, r1.z * r2.x - r1.x * r2.z, r1.x * r2.y - r1.y * r2.x};
+	const V3 x20{r2.y * r0.z - r2.z * r0.y, r2.z * r0.x - r2.x * r0.z, r2.x * r0.y - r2.y * r0.x};
+	const V3 x01{r0.y * r1.z - r0.z * r1.y, r0.z * r1.x - r0.x * r1.z, r0.x * r1.y - r0.y * r1.x};
+	const float D = dot3(r0, x12);
+	V4 e;
+	e.x = ((b0 * x12.x + b1 * x20.x) + b2 * x01.x) / D;
+	e.y = ((b0 * x12.y + b1 * x20.y) + b2 * x01.y) / D;
+	e.z = ((b0 * x12.z + b1 * x20.z) + b2 * x01.z) / D;
+	e.w = 0.0f;
+	if (!(D != 0.0f) || !(std::fabs(D) <= 3.4028234e38f)) e.x = e.y = e.z = std::numeric_limits<float>::quiet_NaN();
+	return e;
+}
+constexpr float kConeMargin = 1.0e-3f; // == common.cuh
+
 uint8_t cull_one(const vkv_VisbufferPushConstants* pc, uint32_t drawIdx, const vkv_Camera& cam, const float* occVP,
-                 const Pyr& pyr, const float* pyramid) {
+                 const Pyr& pyr, const float* pyramid, const ConeCtx* cone = nullptr) {
 	const vkv_MeshletDraw* draws = (const vkv_MeshletDraw*)pc->drawBuffer;
 	const float* transforms = (const float*)pc->transformBuffer;
 	const vkv_Primitive* prims = (const vkv_Primitive*)pc->primitiveBuffer;
@@ -174,6 +199,15 @@ uint8_t cull_one(const vkv_VisbufferPushConstants* pc, uint32_t drawIdx, const v
 			if (std::fabs(-radius - distance) <= kNoise * terms + moved) flags |= ORC_AMBIG_FRUSTUM;
 		}
 		if (-radius > distance) return ORC_FRUSTUM_CULLED | flags;
+	}
+
+	if (cone) { // dot(apex - eye, axis) >= (cutoff + margin) * |apex - eye|   (meshoptimizer.h:531 without the normalisation)
+		const vkv_MeshletCone& cn = ((const vkv_MeshletCone*)cone->table[d.primitiveIndex])[d.meshletIndex];
+		const V4 eye = cone->eye[d.transformIndex];
+		const float dx = cn.apex[0] - eye.x, dy = cn.apex[1] - eye.y, dz = cn.apex[2] - eye.z;
+		const float len2 = (dx * dx + dy * dy) + dz * dz;
+		const float dp = (dx * cn.axis[0] + dy * cn.axis[1]) + dz * cn.axis[2];
+		if (dp >= (cn.cutoff + kConeMargin) * std::sqrt(len2)) return ORC_FRUSTUM_CULLED | ORC_CONE_CULLED | flags;
 	}
 
 	// :56 -> culling.h.glsl:44-56
@@ -478,12 +512,28 @@ uint64_t orc_vis64_key(float depth, uint32_t id) { return ((uint64_t)(~fbits(dep
 
 int orc_cull(const vkv_VisbufferPushConstants* pc, uint32_t W, uint32_t H, const float* pyramid, int vp_select,
              const uint8_t* only_status, uint8_t* status, orc_counters* ctr, int threads) {
+	return orc_cull_cone(pc, W, H, pyramid, vp_select, only_status, status, ctr, threads, nullptr);
+}
+
+int orc_cull_cone(const vkv_VisbufferPushConstants* pc, uint32_t W, uint32_t H, const float* pyramid, int vp_select,
+                  const uint8_t* only_status, uint8_t* status, orc_counters* ctr, int threads, const uint64_t* cone_table) {
 	Pyr pyr;
 	pyr.levels = orc_pyramid_layout(W, H, pyr.off, pyr.w, pyr.h, &pyr.total);
 	if (pyr.levels == 0) return -1;
 	const vkv_Camera cam = *(const vkv_Camera*)pc->cameraBuffer; // task.glsl:31
 	const float* occVP = vp_select == 0 ? cam.prevOcclusionViewProjection : cam.viewProjection;
 	const uint32_t N = pc->meshletDrawCount;
+	std::vector<V4> eyes;
+	ConeCtx coneCtx{cone_table, nullptr};
+	if (cone_table) { // the current camera's position per mesh node (the raster that follows uses viewProjection, whichever VP the HiZ test uses)
+		const vkv_MeshletDraw* draws = (const vkv_MeshletDraw*)pc->drawBuffer;
+		uint32_t nT = 0;
+		for (uint32_t i = 0; i < N; ++i) nT = std::max(nT, draws[i].transformIndex + 1);
+		eyes.resize(nT);
+		for (uint32_t t = 0; t < nT; ++t) eyes[t] = mesh_space_eye(cam.viewProjection, (const float*)pc->transformBuffer + (size_t)t * 16);
+		coneCtx.eye = eyes.data();
+	}
+	const ConeCtx* cone = cone_table ? &coneCtx : nullptr;
 	// chunks of maxMeshlets draws = one reference task workgroup (task.glsl:28-29)
 	const size_t chunks = (N + VKV_MAX_MESHLETS_PER_TASK - 1) / VKV_MAX_MESHLETS_PER_TASK;
 	parallel_for(chunks, threads, [&](size_t b, size_t e, int) {
@@ -491,7 +541,7 @@ int orc_cull(const vkv_VisbufferPushConstants* pc, uint32_t W, uint32_t H, const
 			uint32_t lo = (uint32_t)c * VKV_MAX_MESHLETS_PER_TASK, hi = std::min<uint32_t>(N, lo + VKV_MAX_MESHLETS_PER_TASK);
 			for (uint32_t i = lo; i < hi; ++i) {
 				if (only_status && (only_status[i] & ORC_STATUS_MASK) != ORC_OCCLUDED) { status[i] = ORC_NOT_TESTED; continue; }
-				status[i] = cull_one(pc, i, cam, occVP, pyr, pyramid);
+				status[i] = cull_one(pc, i, cam, occVP, pyr, pyramid, cone);
 			}
 		}
 	});

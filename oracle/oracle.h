@@ -49,7 +49,8 @@ enum {
 	ORC_AMBIG_HIZ = 1 << 3,
 	ORC_AMBIG_LEVEL = 1 << 4,   /* max(w,h) within rounding noise of a power of two */
 	ORC_CROSSES_CAMERA = 1 << 5, /* some AABB corner has clip.w <= 0 */
-	ORC_AMBIG_FOOTPRINT = 1 << 6 /* sample position within rounding noise of a texel-footprint change (or frac within 1e-4 of 0) */
+	ORC_AMBIG_FOOTPRINT = 1 << 6, /* sample position within rounding noise of a texel-footprint change (or frac within 1e-4 of 0) */
+	ORC_CONE_CULLED = 1 << 7      /* orc_cull_cone only: rejected by the normal cone (class ORC_FRUSTUM_CULLED) == VKV_ST_CONE_CULLED */
 };
 
 typedef struct orc_counters {
@@ -78,6 +79,12 @@ uint32_t orc_pyramid_layout(uint32_t W, uint32_t H, uint32_t offsets[17], uint32
  * status[N] receives the per-draw result; threads<=0 -> hardware_concurrency. */
 int orc_cull(const vkv_VisbufferPushConstants* pc, uint32_t W, uint32_t H, const float* pyramid,
              int vp_select, const uint8_t* only_status, uint8_t* status, orc_counters* ctr, int threads);
+
+/* orc_cull plus the optional normal-cone stage between the frustum and the occlusion test (extension; the reference has no cone
+ * cull): cone_table[primitiveIndex] = host address of that primitive's vkv_MeshletCone[] (vkvh_scene_host_cones); NULL = orc_cull.
+ * Pass B (only_status != NULL) never needs it: its inputs passed the cone test in pass A. */
+int orc_cull_cone(const vkv_VisbufferPushConstants* pc, uint32_t W, uint32_t H, const float* pyramid,
+                  int vp_select, const uint8_t* only_status, uint8_t* status, orc_counters* ctr, int threads, const uint64_t* cone_table);
 
 /* visbuffer.mesh.glsl:30-104 + fixed-function state (application.cpp:326-340,772-841;
  * pipeline_builder.cpp:225-277) + visbuffer.frag.glsl:36.

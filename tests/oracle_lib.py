@@ -14,6 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 FRUSTUM_CULLED, OCCLUDED, VISIBLE, NOT_TESTED, STATUS_MASK = 0, 1, 2, 3, 3
 AMBIG_FRUSTUM, AMBIG_HIZ, AMBIG_LEVEL, CROSSES_CAMERA, AMBIG_FOOTPRINT = 4, 8, 16, 32, 64
+CONE_CULLED = 128
 
 
 class Counters(C.Structure):
@@ -40,6 +41,8 @@ def lib():
         L.orc_pyramid_layout.restype = C.c_uint32
         L.orc_cull.argtypes = [C.POINTER(abi.PushConstants), C.c_uint32, C.c_uint32, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                C.POINTER(Counters), C.c_int]
+        L.orc_cull_cone.argtypes = L.orc_cull.argtypes + [C.c_void_p]
+        L.orc_set_diagnostics.argtypes = [C.c_int]
         L.orc_raster.argtypes = [C.POINTER(abi.PushConstants), C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.POINTER(Counters), C.c_int]
         L.orc_clear.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -78,12 +81,14 @@ class Targets:
         return (hi << np.uint64(32)) | self.ids_min.astype(np.uint64)
 
 
-def cull(pc, W, H, pyramid, vp_select=0, only_status=None, threads=0):
+def cull(pc, W, H, pyramid, vp_select=0, only_status=None, threads=0, cones=None):
+    """cones: host cone table (Scene.host_cones()) -> the optional normal-cone stage runs between the frustum and the HiZ test"""
     n = pc.meshletDrawCount
     status = np.zeros(n, np.uint8)
     ctr = Counters()
-    rc = lib().orc_cull(C.byref(pc), W, H, pyramid.ctypes.data, vp_select,
-                        only_status.ctypes.data if only_status is not None else None, status.ctypes.data, C.byref(ctr), threads)
+    rc = lib().orc_cull_cone(C.byref(pc), W, H, pyramid.ctypes.data, vp_select,
+                             only_status.ctypes.data if only_status is not None else None, status.ctypes.data, C.byref(ctr), threads,
+                             cones)
     assert rc == 0
     return status, ctr
 
@@ -115,11 +120,11 @@ def visible_ids(status):
     return np.nonzero((status & STATUS_MASK) == VISIBLE)[0].astype(np.uint32)
 
 
-def frame(pc, tg: Targets, two_pass=False, threads=0):
+def frame(pc, tg: Targets, two_pass=False, threads=0, cones=None):
     """One frame as the reference records it (cull with the previous pyramid -> raster -> HiZ rebuild), or the two-pass
     extension: A = reference pass; HiZ; B = re-test A's occlusion rejects with the current VP/pyramid; raster; HiZ."""
     tg.clear()
-    stA, cA = cull(pc, tg.W, tg.H, tg.pyramid, 0, None, threads)
+    stA, cA = cull(pc, tg.W, tg.H, tg.pyramid, 0, None, threads, cones)
     visA = visible_ids(stA)
     rA = raster(pc, tg, visA, threads)
     hiz(tg, threads)

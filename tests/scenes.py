@@ -166,3 +166,12 @@ def cull_stress(seed=11, instances=61):
 
 def camera(W, H, eye=(0, 0, 3), center=(0, 0, 0)):
     return Camera(W, H).look_at(eye, center)
+
+
+def icosphere_soup(frequency):
+    """(positions, flat u32 index list) of the procedural icosphere, taken back out of its meshlets (copies: the scene may go away)"""
+    sphere = Scene.icosphere(frequency)
+    src = sphere.primitive(0)
+    soup = np.concatenate([src["vertex_indices"][int(m["vertexOffset"]) + src["triangles"][int(m["triangleOffset"]): int(m["triangleOffset"]) + 3 * int(m["triangleCount"])].astype(np.int64)]
+                           for m in src["meshlets"]]).astype(np.uint32)
+    return src["vertices"]["position"].copy(), soup

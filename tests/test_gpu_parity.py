@@ -376,3 +376,55 @@ def test_raster_queue_overflow_falls_back_to_the_rewalk(monkeypatch, caps):
     run_views(s, 960, 540, orbit(s, 2, 960, 540), two_pass=True)
     s = Scene.lattice(3, 2, 2, 24)
     run_views(s, 640, 360, orbit(s, 2, 640, 360), two_pass=True)
+
+
+@pytest.mark.parametrize("make,views", [
+    (lambda: Scene.icosphere(40), [((0, 0, 3), (0, 0, 0)), ((1.2, 0.5, 2.6), (0, 0, 0)), ((-2.0, -1.0, -2.0), (0, 0, 0))]),
+    (lambda: S.mirrored_instances(), [((0, 0, 4), (0, 0, 0)), ((2, 1, 3), (0, 0, 0)), ((0, 0, -4), (0, 0, 0))]),
+    (lambda: Scene.city(6, 5, 2000), None),
+])
+def test_cone_cull_matches_the_oracle_and_leaves_the_image_alone(make, views):
+    """optional normal-cone cull (VKV_FRAME_CONE_CULL; north_star's second cull test, which the reference disables at assets.cpp:323):
+    per-draw status bytes — VKV_ST_CONE_CULLED included — equal the oracle's with its cone stage on; the 64-bit visbuffer and the
+    pyramid equal BOTH the oracle's with the stage on and the CUDA frame with the stage off; the stage does reject meshlets."""
+    scene = make()
+    W, H = 800, 600
+    if views is None:
+        views = [scene.default_view(i, 16) for i in range(3)]
+    cam = Camera(W, H).look_at(*views[0])
+    r_on, r_off = api.Renderer(W, H), api.Renderer(W, H)
+    pc_on, pc_off = r_on.upload_scene(scene, cam), r_off.upload_scene(scene, cam)
+    r_on.upload_cones(scene)
+    pc_host = scene.host_push_constants(cam)
+    cones = scene.host_cones()
+    tg = O.Targets(W, H)
+    n = pc_host.meshletDrawCount
+    rejected = 0
+    for k, v in enumerate(views):
+        if k:
+            cam.look_at(*v)
+            r_on.update_camera(pc_on, cam); r_off.update_camera(pc_off, cam)
+        out = O.frame(pc_host, tg, two_pass=True, cones=cones)
+        st = r_on.frame(pc_on, api.FRAME_TWO_PASS | api.FRAME_STATUS | api.FRAME_CONE_CULL)
+        r_off.frame(pc_off, api.FRAME_TWO_PASS)
+        got = r_on.read_status(n, 0)
+        assert np.array_equal(got, out["statusA"] & (O.STATUS_MASK | O.CONE_CULLED)), f"view {k}: status bytes differ in {(got != (out['statusA'] & (O.STATUS_MASK | O.CONE_CULLED))).sum()} draws"
+        rejected += int((got == api.ST_CONE_CULLED).sum())
+        assert np.array_equal(np.sort(r_on.read_visible(0)), out["visibleA"]) and np.array_equal(np.sort(r_on.read_visible(1)), out["visibleB"])
+        vis = r_on.read_visbuffer64()
+        assert np.array_equal(vis, tg.vis64()) and np.array_equal(vis, r_off.read_visbuffer64()), f"view {k}: the cone stage changed the image"
+        assert np.array_equal(r_on.read_pyramid().view(np.uint32), r_off.read_pyramid().view(np.uint32))
+        assert st.visible_a <= r_off.read_visible(0).size
+    assert rejected > 0
+    r_on.close(); r_off.close()
+
+
+def test_cone_cull_needs_its_table():
+    s = Scene.icosphere(8)
+    cam = Camera(320, 240).look_at((0, 0, 3), (0, 0, 0))
+    r = api.Renderer(320, 240)
+    pc = r.upload_scene(s, cam)
+    with pytest.raises(api.VkvError) as e:
+        r.frame(pc, api.FRAME_CONE_CULL)
+    assert e.value.code == -2
+    r.close()

@@ -334,3 +334,67 @@ def test_task_shader_decisions_match_the_reference_text(ref_shim, name):
         assert r["unexplained"] == 0, (name, vp_select, r)
         assert r["occluded"] > 0 or name in ("cfg1",), "the pyramid must actually reject something for the comparison to mean anything"
         assert r["flagged"] <= 0.02 * r["draws"] + 8, "ambiguity flags must stay the exception"
+
+
+# ------------------------------------------------------------------------------------------ optional normal-cone cull (extension)
+def _cone_scenes():
+    rng = np.random.default_rng(3)
+    out = {"icosphere": Scene.icosphere(24), "mirrored": S.mirrored_instances(), "lattice": Scene.lattice(3, 2, 3, 24)}
+    s = Scene.new()                                                   # closed bumpy blobs under arbitrary node matrices: rotation,
+    pos, soup = S.icosphere_soup(10)                                  # NON-uniform and mirrored scale (the cone test runs in mesh space)
+    pos = pos * (1 + 0.15 * np.sin(7 * pos[:, :1]))
+    p = s.add_primitive(pos, soup)
+    for _ in range(14):
+        q = rng.normal(size=4); q /= np.linalg.norm(q)
+        s.add_node(p, translation=rng.uniform(-4, 4, 3), rotation=q, scale=rng.uniform(0.3, 1.6, 3) * rng.choice([-1, 1], 3))
+    out["blobs_trs"] = s.finalize()
+    return out
+
+
+@pytest.mark.parametrize("name", ["icosphere", "mirrored", "lattice", "blobs_trs"])
+def test_cone_cull_removes_only_meshlets_the_facing_test_would_empty(name):
+    """VERDICT r1 item 5 (north_star's normal-cone cull; the reference disables cones, assets.cpp:323): with the cone stage on,
+    (a) every cone-culled MeshletDraw, rasterised on its own, produces no triangle past the mesh shader's facing test;
+    (b) the frame's visbuffer and pyramid are bit-identical to the frame without the stage, over several views;
+    (c) the stage does reject meshlets on closed single-sided objects."""
+    scene = _cone_scenes()[name]
+    W, H = 480, 360
+    views = [scene.default_view(i, 7) for i in range(3)] if name in ("icosphere", "lattice") else [((0, 0, 9), (0, 0, 0)), ((5, 2, 7), (0, 0, 0)), ((-6, -1, -5), (0, 0, 0))]
+    if name == "lattice":   # its patches are one-sided height fields: seen from below they all face away
+        c = scene.default_view(0, 7)[1]
+        views.append(((c[0] + 1.0, c[1] - 40.0, c[2] + 2.0), c))
+    cones = scene.host_cones()
+    cam = Camera(W, H).look_at(*views[0])
+    pc = scene.host_push_constants(cam)
+    tg_on, tg_off = O.Targets(W, H), O.Targets(W, H)
+    culled_total = 0
+    for k, v in enumerate(views):
+        if k:
+            cam.look_at(*v)
+        on = O.frame(pc, tg_on, two_pass=True, cones=cones)
+        off = O.frame(pc, tg_off, two_pass=True)
+        cone_ids = np.nonzero(on["statusA"] & O.CONE_CULLED)[0].astype(np.uint32)
+        culled_total += cone_ids.size
+        assert ((on["statusA"][cone_ids] & O.STATUS_MASK) == O.FRUSTUM_CULLED).all()
+        assert np.array_equal(tg_on.vis64(), tg_off.vis64()) and np.array_equal(tg_on.pyramid.view(np.uint32), tg_off.pyramid.view(np.uint32)), f"view {k}"
+        assert set(on["visibleA"]).issubset(set(off["visibleA"]) | set(off["visibleB"]))
+        if cone_ids.size:
+            scratch = O.Targets(W, H)
+            ctr = O.raster(pc, scratch, cone_ids)
+            assert ctr.triangles_rasterised == 0 and ctr.fragments == 0 and ctr.triangles_clipped == 0, ctr.as_dict()
+            assert ctr.triangles_culled_facing + ctr.triangles_degenerate + ctr.triangles_rejected == ctr.triangles_in
+    assert culled_total > 0, "the cone stage never fired"
+    if name == "icosphere":
+        assert culled_total > 0.25 * 3 * pc.meshletDrawCount   # roughly the far hemisphere
+
+
+def test_cone_cull_is_off_for_double_sided_materials():
+    s = Scene.new()
+    m = s.add_material(double_sided=True)
+    pos, soup = S.icosphere_soup(8)
+    s.add_node(s.add_primitive(pos, soup, m))
+    s.finalize()
+    cam = Camera(320, 240).look_at((0, 0, 3), (0, 0, 0))
+    pc = s.host_push_constants(cam)
+    st, _ = O.cull(pc, 320, 240, O.Targets(320, 240).pyramid, cones=s.host_cones())
+    assert not (st & O.CONE_CULLED).any()

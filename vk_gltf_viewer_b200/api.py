@@ -20,8 +20,10 @@ FRAME_STAGES = 1 << 6
 FRAME_NO_CULL = 1 << 4
 FRAME_MERGE = 1 << 5
 FRAME_MERGE_STRIPS = 1 << 7
+FRAME_CONE_CULL = 1 << 8
 
 ST_FRUSTUM_CULLED, ST_OCCLUDED, ST_VISIBLE, ST_NOT_TESTED = 0, 1, 2, 3
+ST_CONE_CULLED = 0x80
 
 
 class VkvError(RuntimeError):
@@ -55,7 +57,7 @@ EXPORTS = [
     "vkv_build_meshlets", "vkv_assemble_vertices", "vkv_widen_indices",
     "vkv_alloc", "vkv_meshopt_plan_create", "vkv_meshopt_run", "vkv_meshopt_results", "vkv_meshopt_plan_destroy",
     "vkv_set_shard", "vkv_set_shard_interleaved", "vkv_ipc_export", "vkv_ipc_attach", "vkv_ipc_detach", "vkv_merge",
-    "vkv_strip_rows", "vkv_gather_strips", "vkv_hash",
+    "vkv_strip_rows", "vkv_gather_strips", "vkv_hash", "vkv_set_cone_table",
 ]
 
 _bound = False
@@ -112,6 +114,7 @@ def _lib():
         L.vkv_strip_rows.argtypes = [vp, i, i, C.POINTER(u32), C.POINTER(u32)]
         L.vkv_gather_strips.argtypes = [vp]
         L.vkv_hash.argtypes = [vp, i, u32, u32, C.POINTER(u64)]
+        L.vkv_set_cone_table.argtypes = [vp, u64]
         L.vkv_selftest_division.argtypes = [vp, u64, u32, C.POINTER(u64), C.POINTER(u64)]
         L.vkv_alloc.argtypes = [vp, C.c_size_t, C.POINTER(u64)]
         L.vkv_build_meshlets.argtypes = [vp, vp, u32, u32, u32, u32, vp]
@@ -172,6 +175,14 @@ class Renderer:
         pc = scene.upload(cb, None, camera)
         self._camera_addr = pc.cameraBuffer
         return pc
+
+    def upload_cones(self, scene) -> int:
+        """the side buffer of the optional cone cull (FRAME_CONE_CULL): upload the scene's normal cones and register the table"""
+        def cb(user, host, nbytes, out):
+            return self.L.vkv_upload(self.h, host, nbytes, out)
+        table = scene.upload_cones(cb)
+        self._ck(self.L.vkv_set_cone_table(self.h, table))
+        return table
 
     def update_camera(self, pc: abi.PushConstants, camera):
         """Camera::updateCamera's mapped write (camera.cpp:180-193)."""

@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <iterator>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -38,6 +39,8 @@ struct vkv_ctx {
 	// per-transform mvp / determinant sign (mesh.glsl:44,71 hoisted; grow-only)
 	float* xf_mvp = nullptr;
 	uint32_t* xf_det = nullptr;
+	float4* xf_eye = nullptr;         // camera position in each mesh-node's own space (cone cull)
+	uint64_t cone_table = 0;          // vkv_set_cone_table
 	uint32_t xf_cap = 0;
 	uint32_t xf_count = 0;
 	BigTri* big_tris = nullptr;       // large-triangle queue (raster.cu)
@@ -188,7 +191,7 @@ int ensure_draws(vkv_ctx* c, uint32_t n) {
 // mesh.glsl:43-44,71 once per mesh-node: needs the transform count, which the push constants do not carry — it is the
 // extent of the vkv_upload allocation the transform buffer lives in.
 // `fused` != NULL: only size the buffers and hand the job to the pass-A cull launch (cull.cu) through its parameters
-int prepare_transforms(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, int* launches, CullParams* fused = nullptr) {
+int prepare_transforms(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, int* launches, CullParams* fused = nullptr, bool want_eye = false) {
 	c->xf_count = 0;
 	if (!pc->meshletDrawCount) return VKV_OK;
 	size_t bytes = 0;
@@ -207,17 +210,20 @@ int prepare_transforms(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, int* la
 	if (n > c->xf_cap) {
 		CK(cudaStreamSynchronize(c->stream));
 		const uint32_t cap = n + n / 8 + 64;
-		float* mvp = nullptr; uint32_t* det = nullptr;
+		float* mvp = nullptr; uint32_t* det = nullptr; float4* eye = nullptr;
 		CK(cudaMalloc(&mvp, (size_t)cap * 64));
 		cudaError_t e2 = cudaMalloc(&det, (size_t)cap * 4);
-		if (e2 != cudaSuccess) { cudaFree(mvp); return fail(c, VKV_ERR_OOM, "growing the per-transform buffers: %s", cudaGetErrorString(e2)); }
+		if (e2 == cudaSuccess) e2 = cudaMalloc(&eye, (size_t)cap * 16);
+		if (e2 != cudaSuccess) { cudaFree(mvp); if (det) cudaFree(det); return fail(c, VKV_ERR_OOM, "growing the per-transform buffers: %s", cudaGetErrorString(e2)); }
 		if (c->xf_mvp) cudaFree(c->xf_mvp);
 		if (c->xf_det) cudaFree(c->xf_det);
-		c->xf_mvp = mvp; c->xf_det = det; c->xf_cap = cap;
+		if (c->xf_eye) cudaFree(c->xf_eye);
+		c->xf_mvp = mvp; c->xf_det = det; c->xf_eye = eye; c->xf_cap = cap;
 	}
 	if (fused) { fused->xf_mvp = c->xf_mvp; fused->xf_det = c->xf_det; fused->xf_n = n; }
 	else {
-		CK(launch_prepare_transforms((const float*)pc->transformBuffer, (const vkv_Camera*)pc->cameraBuffer, n, c->xf_mvp, c->xf_det, c->num_sms, c->stream));
+		CK(launch_prepare_transforms((const float*)pc->transformBuffer, (const vkv_Camera*)pc->cameraBuffer, n, c->xf_mvp, c->xf_det, want_eye ? c->xf_eye : nullptr,
+		                             c->num_sms, c->stream));
 		if (launches) ++*launches;
 	}
 	c->xf_count = n;
@@ -250,6 +256,7 @@ CullParams make_cull(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, int pass,
 	p.out_occluded = c->list_occluded[pass];
 	p.counters = c->counters;
 	p.status = (flags & VKV_FRAME_STATUS) ? c->status[pass] : nullptr;
+	if ((flags & VKV_FRAME_CONE_CULL) && pass == 0) { p.cone_table = (const unsigned long long*)(uintptr_t)c->cone_table; p.xf_eye = c->xf_eye; }
 	p.pass = pass;
 	p.vp_select = pass;
 	p.skip_hiz = 0;
@@ -426,6 +433,7 @@ void vkv_destroy(vkv_ctx* c) {
 	if (c->list_tmp) cudaFree(c->list_tmp);
 	if (c->xf_mvp) cudaFree(c->xf_mvp);
 	if (c->xf_det) cudaFree(c->xf_det);
+	if (c->xf_eye) cudaFree(c->xf_eye);
 	if (c->big_tris) cudaFree(c->big_tris);
 	if (c->clip_tris) cudaFree(c->clip_tris);
 	if (c->mat_colors) cudaFree(c->mat_colors);
@@ -494,6 +502,18 @@ int vkv_free(vkv_ctx* c, uint64_t dev_addr) {
 	return VKV_OK;
 }
 
+int vkv_set_cone_table(vkv_ctx* c, uint64_t table_dev_addr) {
+	if (!c) return VKV_ERR_INVALID;
+	if (table_dev_addr) {
+		std::lock_guard<std::mutex> lock(c->mtx);
+		auto it = c->allocs.upper_bound(table_dev_addr);
+		if (it == c->allocs.begin() || table_dev_addr >= std::prev(it)->first + std::prev(it)->second)
+			return fail(c, VKV_ERR_INVALID, "vkv_set_cone_table: the table does not lie in a vkv_upload allocation");
+	}
+	c->cone_table = table_dev_addr;
+	return VKV_OK;
+}
+
 int vkv_clear(vkv_ctx* c) {
 	if (!c) return VKV_ERR_INVALID;
 	CK(cudaSetDevice(c->device));
@@ -508,6 +528,11 @@ int vkv_cull(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, int pass, uint32_
 	CK(cudaSetDevice(c->device));
 	CK(cudaMemsetAsync(&c->counters->visible[pass], 0, 4, c->stream));
 	CK(cudaMemsetAsync(&c->counters->occluded[pass], 0, 4, c->stream));
+	if ((flags & VKV_FRAME_CONE_CULL) && pass == 0) {
+		if (!c->cone_table) return fail(c, VKV_ERR_INVALID, "VKV_FRAME_CONE_CULL needs vkv_set_cone_table first");
+		rc = prepare_transforms(c, pc, nullptr, nullptr, true);
+		if (rc) return rc;
+	}
 	CullParams p = make_cull(c, pc, pass, flags);
 	if (p.status) CK(cudaMemsetAsync(p.status, VKV_ST_NOT_TESTED, pc->meshletDrawCount, c->stream));
 	c->status_valid[pass] = p.status != nullptr;
@@ -568,6 +593,8 @@ int vkv_frame(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, uint32_t flags, 
 	const bool hiz = !(flags & VKV_FRAME_NO_HIZ);
 	const uint32_t N = pc->meshletDrawCount;
 	if ((merge || strips) && !c->attached) return fail(c, VKV_ERR_INVALID, "VKV_FRAME_MERGE / VKV_FRAME_MERGE_STRIPS need vkv_ipc_attach first");
+	const bool cone = (flags & VKV_FRAME_CONE_CULL) && !(flags & VKV_FRAME_NO_CULL);
+	if (cone && !c->cone_table) return fail(c, VKV_ERR_INVALID, "VKV_FRAME_CONE_CULL needs vkv_set_cone_table first");
 	if (strips && (c->exact_levels < 1 || !hiz)) return fail(c, VKV_ERR_INVALID, "VKV_FRAME_MERGE_STRIPS needs an even resolution (one exact pyramid mip) and the pyramid rebuild");
 	int launches = 0;
 	// NVTX ranges named like the reference's Tracy/debug-label zones (application.cpp:765 "Visbuffer pass", :952 "HiZ reduction") so a
@@ -603,7 +630,9 @@ int vkv_frame(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, uint32_t flags, 
 		if (p.status) CK(cudaMemsetAsync(p.status, VKV_ST_NOT_TESTED, N, s));
 		c->status_valid[0] = p.status != nullptr;
 		if (p.n) {
-			if (!c->separate_clear) { rc = prepare_transforms(c, pc, &launches, &p); if (rc) return rc; xf_done = true; } // rides along, like the clear
+			// the cone test reads the per-node eye positions in THIS launch: they need a launch of their own ahead of it
+			if (cone) { rc = prepare_transforms(c, pc, &launches, nullptr, true); if (rc) return rc; xf_done = true; p.xf_eye = c->xf_eye; }
+			else if (!c->separate_clear) { rc = prepare_transforms(c, pc, &launches, &p); if (rc) return rc; xf_done = true; } // rides along, like the clear
 			CK(launch_cull(p, c->num_sms, s)); ++launches;
 		}
 	}

@@ -31,6 +31,8 @@ struct CullParams {
 	uint32_t* xf_det;
 	uint32_t xf_n;
 	int skip_frustum;            // pass B inside vkv_frame: every input draw already passed this frame's frustum test in pass A
+	const unsigned long long* cone_table; // optional cone cull: per primitive the address of its vkv_MeshletCone[] (NULL = off)
+	const float4* xf_eye;        // per transform: camera position in mesh space (transform_prologue), valid BEFORE this launch
 	uint4* zero_ptr;             // strip mode: the dirty-tile flags of both passes, zeroed by the same launch
 	uint32_t zero_n16;
 };
@@ -100,7 +102,7 @@ struct HizParams {
 
 cudaError_t launch_cull(const CullParams& p, int num_sms, cudaStream_t stream, bool after_hiz = false); // after_hiz: programmatic dependent launch
 cudaError_t launch_iota(const CullParams& p, uint32_t* out, uint32_t* count, int num_sms, cudaStream_t stream);
-cudaError_t launch_prepare_transforms(const float* transforms, const vkv_Camera* camera, uint32_t n, float* mvp, uint32_t* detNeg,
+cudaError_t launch_prepare_transforms(const float* transforms, const vkv_Camera* camera, uint32_t n, float* mvp, uint32_t* detNeg, float4* eye,
                                       int num_sms, cudaStream_t stream);
 cudaError_t launch_raster(const RasterParams& p, int num_sms, cudaStream_t stream);      // raster_kernel + raster_big_kernel
 cudaError_t launch_hiz(const HizParams& p, int num_sms, cudaStream_t stream, int* launches);

@@ -300,12 +300,12 @@ __device__ __noinline__ int clip_and_setup(float4 A, float4 B, float4 C, uint32_
 // mvp = viewProjection * transform (column by column) and the sign of determinant(transform).  Same arithmetic as before,
 // computed once per mesh-node instead of once per meshlet.
 __global__ void prepare_transforms_kernel(const float* __restrict__ transforms, const vkv_Camera* __restrict__ camera, uint32_t n,
-                                          float* __restrict__ mvpOut, uint32_t* __restrict__ detNeg) {
+                                          float* __restrict__ mvpOut, uint32_t* __restrict__ detNeg, float4* __restrict__ eye) {
 	__shared__ float sVP[16];
 	if (threadIdx.x < 16) sVP[threadIdx.x] = __ldg(camera->viewProjection + threadIdx.x);
 	__syncthreads();
 	for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x)
-		transform_prologue(transforms + (size_t)t * 16, sVP, mvpOut + (size_t)t * 16, detNeg + t);
+		transform_prologue(transforms + (size_t)t * 16, sVP, mvpOut + (size_t)t * 16, detNeg + t, eye ? eye + t : nullptr);
 }
 
 // Strip mode (strips.cu): every 64x16-pixel tile a drawn triangle's pixel bounding box touches gets its dirty byte set, so that
@@ -611,7 +611,10 @@ __device__ __forceinline__ void drain_grid_barrier(uint32_t* counter) {
 //      the large-triangle queue, the others are scanned by the warp at once.  (Skipped, barrier included, when the queue is empty.)
 //   2. large-triangle queue: one warp per (triangle, 128x64-pixel tile) work item.
 //   3. only if a queue overflowed: the re-walk of the meshlet list (meshlet_loop<false>), one warp per block.
-__global__ void __launch_bounds__(kDrainThreads, 3) raster_big_kernel(const RasterParams p) {
+#ifndef VKV_DRAIN_MINB
+#define VKV_DRAIN_MINB 3
+#endif
+__global__ void __launch_bounds__(kDrainThreads, VKV_DRAIN_MINB) raster_big_kernel(const RasterParams p) {
 	__shared__ Tri sTri[kDrainThreads / 32];
 	__shared__ Tri sSub[kDrainThreads / 32][8];
 	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -672,10 +675,17 @@ __global__ void __launch_bounds__(kDrainThreads, 3) raster_big_kernel(const Rast
 			if (lane == 0) w = atomicAdd(p.bigNext, 1u);
 			w = __shfl_sync(0xffffffffu, w, 0);
 			if (w >= nTiles) break;
-			uint32_t lo = 0, hi = nRec - 1; // last record with tileBase <= w
+			// last record with tileBase <= w: a 32-way search, every lane probing one position per round (4 dependent L2 round trips
+			// for a million records instead of 20 — the drain of a scene full of medium triangles is bound by this latency)
+			uint32_t lo = 0, hi = nRec - 1;
 			while (lo < hi) {
-				const uint32_t mid = (lo + hi + 1) >> 1;
-				if (p.big[mid].tileBase <= w) lo = mid; else hi = mid - 1;
+				const uint32_t span = hi - lo, step = span / 32u + 1u;          // probes lo + step, lo + 2*step, ... (clamped to hi)
+				const uint32_t probe = min(hi, lo + (lane + 1u) * step);
+				const uint32_t ok = __ballot_sync(0xffffffffu, p.big[probe].tileBase <= w); // monotone: a prefix of the lanes
+				const uint32_t k = __popc(ok);                                   // probes 1..k hold, probe k+1 (if any) does not
+				const uint32_t newLo = k ? min(hi, lo + k * step) : lo;
+				const uint32_t newHi = k < 32u ? min(hi, lo + (k + 1u) * step) - 1u : hi;
+				lo = newLo; hi = newHi < newLo ? newLo : newHi;
 			}
 			const BigTri* b = p.big + lo;
 			__syncwarp();
@@ -691,11 +701,13 @@ __global__ void __launch_bounds__(kDrainThreads, 3) raster_big_kernel(const Rast
 		}
 	}
 
+#ifndef VKV_DRAIN_NO_REWALK
 	if (overflowed) { // a queue was full: rare, slow, correct
 		__shared__ WarpScratch slow;
 		__shared__ SlowScratch slowSub;
 		if (warp == 0) rewalk(p, slow, &slowSub, lane);
 	}
+#endif
 }
 
 __global__ void fill64_kernel(ulonglong2* __restrict__ dst, size_t n2, unsigned long long v, unsigned long long* tail, size_t ntail) {
@@ -716,12 +728,12 @@ __global__ void split_vis_kernel(const unsigned long long* __restrict__ vis, siz
 
 } // namespace
 
-cudaError_t launch_prepare_transforms(const float* transforms, const vkv_Camera* camera, uint32_t n, float* mvp, uint32_t* detNeg,
+cudaError_t launch_prepare_transforms(const float* transforms, const vkv_Camera* camera, uint32_t n, float* mvp, uint32_t* detNeg, float4* eye,
                                       int num_sms, cudaStream_t stream) {
 	if (n == 0) return cudaSuccess;
 	uint32_t grid = (n + 127) / 128;
 	if (grid > (uint32_t)num_sms * 8) grid = (uint32_t)num_sms * 8;
-	prepare_transforms_kernel<<<grid, 128, 0, stream>>>(transforms, camera, n, mvp, detNeg);
+	prepare_transforms_kernel<<<grid, 128, 0, stream>>>(transforms, camera, n, mvp, detNeg, eye);
 	return cudaGetLastError();
 }
 

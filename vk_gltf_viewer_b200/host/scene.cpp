@@ -107,6 +107,14 @@ bool vkvh::build_primitive(PrimitiveData& pd, std::vector<vkv_Vertex>&& vertices
 			pmin[k] = std::min(pmin[k], mn[k]); pmax[k] = std::max(pmax[k], mx[k]);
 		}
 		pd.meshlets.push_back(m);
+		// extension: the meshlet's normal cone (meshopt_computeMeshletBounds; the reference never computes it, assets.cpp:323)
+		vkvh_meshopt_Bounds b;
+		vkvh_meshlet_bounds(&pd.meshletVertices[r.vertex_offset], &pd.meshletTriangles[r.triangle_offset], r.triangle_count, pd.vertices[0].position,
+		                    pd.vertices.size(), sizeof(vkv_Vertex), &b);
+		vkv_MeshletCone cn{};
+		for (int k = 0; k < 3; ++k) { cn.apex[k] = b.cone_apex[k]; cn.axis[k] = b.cone_axis[k]; }
+		cn.cutoff = b.cone_cutoff >= 1.0f ? 2.0f : b.cone_cutoff; // 1 = "normals wider than a hemisphere": never reject
+		pd.cones.push_back(cn);
 	}
 	// assets.cpp:303-306 (accessor min/max -> primitive AABB)
 	for (int k = 0; k < 3; ++k) {
@@ -249,6 +257,40 @@ int vkvh_scene_host_pc(vkvh_scene* s, const vkv_Camera* camera, vkv_VisbufferPus
 	out->cameraBuffer = (uint64_t)(uintptr_t)camera;
 	out->materialBuffer = (uint64_t)(uintptr_t)s->materials.data();
 	return 0;
+}
+
+static void material_adjusted_cones(vkvh_scene* s) {
+	s->hostCones.assign(s->primitives.size(), {});
+	s->hostConeTable.assign(s->primitives.size(), 0);
+	for (size_t i = 0; i < s->primitives.size(); ++i) {
+		const auto& p = s->primitives[i];
+		s->hostCones[i] = p.cones;
+		if (s->materials[p.header.materialIndex].doubleSided)
+			for (auto& c : s->hostCones[i]) c.cutoff = 2.0f; // mesh.glsl:86: no facing cull for double-sided materials
+		s->hostConeTable[i] = (uint64_t)(uintptr_t)s->hostCones[i].data();
+	}
+}
+
+int vkvh_scene_host_cones(vkvh_scene* s, const uint64_t** table) {
+	if (!s || !table) return -1;
+	material_adjusted_cones(s);
+	*table = s->hostConeTable.data();
+	return 0;
+}
+
+int vkvh_scene_upload_cones(vkvh_scene* s, vkvh_upload_fn upload, void* user, uint64_t* table_addr) {
+	if (!s || !upload || !table_addr) return -1;
+	material_adjusted_cones(s);
+	// one allocation for all cones, one for the table
+	std::vector<vkv_MeshletCone> all;
+	std::vector<uint64_t> first(s->primitives.size());
+	for (size_t i = 0; i < s->primitives.size(); ++i) { first[i] = all.size(); all.insert(all.end(), s->hostCones[i].begin(), s->hostCones[i].end()); }
+	uint64_t base = 0;
+	int rc = upload(user, all.data(), all.size() * sizeof(vkv_MeshletCone), &base);
+	if (rc) return rc;
+	std::vector<uint64_t> table(s->primitives.size());
+	for (size_t i = 0; i < table.size(); ++i) table[i] = base + first[i] * sizeof(vkv_MeshletCone);
+	return upload(user, table.data(), table.size() * 8, table_addr);
 }
 
 int vkvh_scene_upload(vkvh_scene* s, vkvh_upload_fn upload, void* user, const vkv_Camera* camera, vkv_VisbufferPushConstants* out) {

@@ -16,6 +16,7 @@ struct PrimitiveData {
 	std::vector<uint32_t> meshletVertices;   // Primitive.vertexIndexBuffer
 	std::vector<uint8_t> meshletTriangles;   // Primitive.primitiveIndexBuffer
 	std::vector<vkv_Meshlet> meshlets;       // Primitive.meshletBuffer
+	std::vector<vkv_MeshletCone> cones;      // extension: normal cone per meshlet (meshopt_computeMeshletBounds), side buffer of the cone cull
 	vkv_Primitive header{};                  // addresses filled per address space
 	uint64_t triangles = 0;
 };
@@ -47,6 +48,8 @@ struct vkvh_scene {
 	std::vector<vkv_MeshletDraw> draws;
 	std::vector<float> transforms; // 16 per mesh node, traversal order
 	std::vector<vkv_Primitive> hostPrimitives;
+	std::vector<std::vector<vkv_MeshletCone>> hostCones; // per primitive, material-adjusted (double-sided -> disabled)
+	std::vector<uint64_t> hostConeTable;
 	bool finalized = false;
 	// default-view hints set by the procedural generators
 	int kind = 0; // 0 custom, 1 icosphere, 2 atrium, 3 lattice, 4 city

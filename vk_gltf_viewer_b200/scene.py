@@ -72,6 +72,8 @@ def _lib():
         L.vkvh_frustum_from_vp.argtypes = [C.POINTER(C.c_float), C.c_void_p]
         L.vkvh_set_meshlet_builder.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.vkvh_select_builder.argtypes = [C.c_int]
+        L.vkvh_scene_host_cones.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        L.vkvh_scene_upload_cones.argtypes = [C.c_void_p, UPLOAD_FN, C.c_void_p, C.POINTER(C.c_uint64)]
         _bound = True
     return L
 
@@ -236,6 +238,21 @@ class Scene:
             raise RuntimeError("host_pc failed")
         self._keep.append(camera)
         return pc
+
+    def host_cones(self) -> int:
+        """host address of the per-primitive cone table (for the CPU oracle's optional cone stage); valid while the scene lives"""
+        t = C.c_void_p()
+        if _lib().vkvh_scene_host_cones(self.h, C.byref(t)):
+            raise RuntimeError("host_cones failed")
+        return t.value
+
+    def upload_cones(self, upload_fn, user=None) -> int:
+        """upload the cone arrays + table through `upload_fn` (vkv_upload's shape); returns the table's device address"""
+        addr = C.c_uint64()
+        cb = UPLOAD_FN(upload_fn)
+        if _lib().vkvh_scene_upload_cones(self.h, cb, user, C.byref(addr)):
+            raise RuntimeError("cone upload failed")
+        return addr.value
 
     def upload(self, upload_fn, user, camera: Camera) -> abi.PushConstants:
         """Upload every buffer through `upload_fn` (vkv_upload's shape) and return DEVICE push constants."""
