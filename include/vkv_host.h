@@ -71,6 +71,17 @@ int32_t vkvh_scene_add_primitive_i16(vkvh_scene*, const int16_t* positions, uint
 /* adds a mesh node with TRS (translation xyz, rotation quaternion xyzw, scale xyz); parent = -1 for a root. Returns node index.
  * primitive < 0 -> transform-only node. */
 int32_t vkvh_scene_add_node_trs(vkvh_scene*, int32_t parent, int32_t primitive, const float t[3], const float r[4], const float s[3]);
+/* a glTF node with a MESH: all n_primitives primitives share the node's transform slot (world.cpp:246-262); has_mesh != 0 with
+ * n_primitives == 0 is a mesh without drawable primitives — it still takes a transform slot, as in the reference */
+int32_t vkvh_scene_add_node_mesh(vkvh_scene*, int32_t parent, const int32_t* primitives, uint32_t n_primitives, int has_mesh,
+                                 const float t[3], const float r[4], const float s[3]);
+/* glTF 2.0 binary (GLB) ingest — what AssetLoadTask::loadGltf + processPrimitive + World::addAsset read of an asset
+ * (assets.cpp:288-373,526-552; world.cpp:187-293): buffers (the BIN chunk, base64 data URIs), bufferViews with byteStride,
+ * POSITION accessors of any component type incl. KHR_mesh_quantization (fastgltf's convertComponent rules), u8 / u16 / u32 or
+ * generated indices, materials (baseColorFactor, alphaCutoff, doubleSided; index + 1), meshes with several primitives, node TRS
+ * or matrices (decomposed like fastgltf::math::decomposeTransformMatrix), scenes[scene].nodes.  Returns a finalized scene or NULL
+ * with a message in err (EXT_meshopt_compression views, sparse accessors and external files are refused with a reason). */
+vkvh_scene* vkvh_scene_load_glb(const void* data, size_t bytes, char* err, size_t errcap);
 /* walks the node tree depth-first and emits MeshletDraw[] + transforms[] (world.cpp:230-345) */
 int vkvh_scene_finalize(vkvh_scene*);
 

@@ -30,7 +30,13 @@ constexpr int kThreads = kWarpsPerBlock * 32;
 constexpr int kSerialMaxDim = VKV_SERIAL_MAX_DIM;   // lane-serial path: bbox <= this many pixels in x and y
 // Large triangles are not rasterised where they are found (one warp would scan thousands of stamps while the rest of the
 // GPU idles): they go to a queue and a second kernel spreads their screen TILES over all warps.
-constexpr int kBigTileW = 128, kBigTileH = 64;   // pixels per tile-work item = 16 x 16 stamps of 8x4
+#ifndef VKV_BIG_TILE_W
+#define VKV_BIG_TILE_W 128
+#endif
+#ifndef VKV_BIG_TILE_H
+#define VKV_BIG_TILE_H 64
+#endif
+constexpr int kBigTileW = VKV_BIG_TILE_W, kBigTileH = VKV_BIG_TILE_H;   // pixels per tile-work item (128 x 64 = 16 x 16 stamps of 8x4)
 #ifndef VKV_BIG_MIN_STAMPS
 #define VKV_BIG_MIN_STAMPS 1
 #endif
@@ -617,6 +623,9 @@ __device__ __forceinline__ void drain_grid_barrier(uint32_t* counter) {
 __global__ void __launch_bounds__(kDrainThreads, VKV_DRAIN_MINB) raster_big_kernel(const RasterParams p) {
 	__shared__ Tri sTri[kDrainThreads / 32];
 	__shared__ Tri sSub[kDrainThreads / 32][8];
+#ifdef VKV_DRAIN_BATCHED
+	__shared__ Tri sTriB[kDrainThreads / 32][32];
+#endif
 	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
 	// the three words that decide what there is to do, fetched together (one L2 round trip, not three): all are final when this
@@ -670,6 +679,48 @@ __global__ void __launch_bounds__(kDrainThreads, VKV_DRAIN_MINB) raster_big_kern
 	if (nRec) {
 		const BigTri* last = p.big + (nRec - 1);
 		const uint32_t nTiles = last->tileBase + last->tilesX * last->tilesY;
+#ifdef VKV_DRAIN_BATCHED
+		// A warp claims up to 32 work items with ONE atomic; every lane finds the record of its own item (32 binary searches side by
+		// side) and stages the triangle in shared memory; then the warp scans the items one after the other with nothing but the
+		// visibility atomics on the memory path.  A scene full of medium triangles (one item each) is bound by exactly these
+		// round trips; a scene of a few huge triangles keeps the claim small so that the last tiles still spread over the GPU.
+		const uint32_t totalWarps = gridDim.x * (kDrainThreads / 32);
+		const uint32_t claim = min(32u, max(1u, nTiles / (totalWarps * 4u)));
+		for (;;) {
+			uint32_t base = 0;
+			if (lane == 0) base = atomicAdd(p.bigNext, claim);
+			base = __shfl_sync(0xffffffffu, base, 0);
+			if (base >= nTiles) break;
+			const uint32_t n = min(claim, nTiles - base);
+			uint32_t local = 0, tilesX = 1;
+			__syncwarp();
+			if (lane < n) {
+				const uint32_t w = base + lane;
+				uint32_t lo = 0, hi = nRec - 1; // last record with tileBase <= w
+				while (lo < hi) {
+					const uint32_t mid = (lo + hi + 1) >> 1;
+					if (__ldg(&p.big[mid].tileBase) <= w) lo = mid; else hi = mid - 1;
+				}
+				const BigTri* b = p.big + lo;
+				const unsigned long long* src = (const unsigned long long*)&b->t;
+				unsigned long long* dst = (unsigned long long*)&sTriB[warp][lane];
+#pragma unroll
+				for (int k = 0; k < (int)(sizeof(Tri) / 8); ++k) dst[k] = __ldg(src + k);
+				local = w - __ldg(&b->tileBase);
+				tilesX = __ldg(&b->tilesX);
+			}
+			__syncwarp();
+			for (uint32_t i = 0; i < n; ++i) {
+				const Tri& t = sTriB[warp][i];
+				const uint32_t li = __shfl_sync(0xffffffffu, local, i), txs = __shfl_sync(0xffffffffu, tilesX, i);
+				const int tx = t.xmin / kBigTileW + (int)(li % txs), ty = t.ymin / kBigTileH + (int)(li / txs);
+				const int x0 = max(t.xmin, tx * kBigTileW), x1 = min(t.xmax, tx * kBigTileW + kBigTileW - 1);
+				const int y0 = max(t.ymin, ty * kBigTileH), y1 = min(t.ymax, ty * kBigTileH + kBigTileH - 1);
+				mark_rect(p, x0, x1, y0, y1, lane);
+				raster_coop(t, p.vis, p.W, lane, x0, x1, y0, y1);
+			}
+		}
+#else
 		for (;;) {
 			uint32_t w = 0;
 			if (lane == 0) w = atomicAdd(p.bigNext, 1u);
@@ -699,6 +750,7 @@ __global__ void __launch_bounds__(kDrainThreads, VKV_DRAIN_MINB) raster_big_kern
 			mark_rect(p, x0, x1, y0, y1, lane);
 			raster_coop(t, p.vis, p.W, lane, x0, x1, y0, y1);
 		}
+#endif
 	}
 
 #ifndef VKV_DRAIN_NO_REWALK

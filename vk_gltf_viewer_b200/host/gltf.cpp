@@ -1,0 +1,392 @@
+// gltf.cpp — glTF 2.0 binary (GLB) ingest for the host input generators (not part of the per-frame path).
+//
+// The reference loads assets through fastgltf (assets.cpp:526-552: Options::GenerateMeshIndices | DecomposeNodeMatrices, extensions
+// KHR_mesh_quantization / EXT_meshopt_compression / …) and turns every glTF primitive into the buffers of glsl::Primitive
+// (assets.cpp:288-373), every scene node into a transform + MeshletDraws (world.cpp:187-293).  fastgltf's parser cannot be built in
+// this image (it needs simdjson, fetched at CMake time — SURVEY D7), so this file is the small GLB / JSON reader the survey allows:
+// it reads the SAME fields the reference consumes and feeds them to the same host code as the procedural generators
+// (vkvh::build_primitive, vkvh_scene_add_node_*), with fastgltf's conversion rules restated:
+//   * POSITION through iterateAccessor<vec3>: per component convertComponent<float, T> (tools.hpp:266-289) — float(x), or
+//     max(float(x) / float(T max), -1) for normalized integers (KHR_mesh_quantization), honouring byteStride;
+//   * indices through copyFromAccessor<uint32_t> (u8 / u16 / u32 widened); a primitive without indices gets 0..n-1
+//     (Options::GenerateMeshIndices);
+//   * the primitive's AABB from the accessor's min / max (assets.cpp:303-306), zero when absent (getAccessorMinMax's default);
+//   * material index + 1, 0 = default material (assets.cpp:292-294, 486-492); baseColorFactor, alphaCutoff, doubleSided;
+//   * node matrices decomposed into TRS exactly like fastgltf::math::decomposeTransformMatrix (math.hpp:854-891), nodes walked
+//     depth first from scenes[scene].nodes, one transform per node WITH a mesh, all primitives of the mesh sharing it
+//     (world.cpp:242-264).
+// Not read (nothing on the geometry path consumes them): textures, samplers, animations, skins, cameras, lights, sparse accessors
+// (rejected), non-triangle modes (skipped, as the mesh shader path only draws triangle lists).  EXT_meshopt_compression views are
+// rejected here with a message pointing at the device decoder (vkv_meshopt_*), which takes the compressed views as they are.
+#include "scene.hpp"
+
+#include <cstdio>
+#include <cstdlib>
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+
+namespace vkvh {
+namespace {
+
+// ---- a minimal JSON document ---------------------------------------------------------------------------------------------
+struct Json {
+	enum Kind { Null, Bool, Number, String, Array, Object } kind = Null;
+	double num = 0;
+	bool b = false;
+	std::string str;
+	std::vector<Json> arr;
+	std::vector<std::pair<std::string, Json>> obj;
+
+	const Json* get(const char* key) const {
+		if (kind != Object) return nullptr;
+		for (const auto& kv : obj)
+			if (kv.first == key) return &kv.second;
+		return nullptr;
+	}
+	bool has(const char* key) const { return get(key) != nullptr; }
+	double number(const char* key, double dflt) const { const Json* j = get(key); return (j && j->kind == Number) ? j->num : dflt; }
+	long long integer(const char* key, long long dflt) const { const Json* j = get(key); return (j && j->kind == Number) ? (long long)j->num : dflt; }
+	bool boolean(const char* key, bool dflt) const { const Json* j = get(key); return (j && j->kind == Bool) ? j->b : dflt; }
+	size_t size() const { return kind == Array ? arr.size() : 0; }
+};
+
+class JsonParser {
+public:
+	JsonParser(const char* p, size_t n) : p_(p), end_(p + n) {}
+	bool parse(Json& out) { skip(); return value(out, 0) && (skip(), true); }
+private:
+	void skip() { while (p_ < end_ && (*p_ == ' ' || *p_ == '\n' || *p_ == '\r' || *p_ == '\t')) ++p_; }
+	bool lit(const char* s) { size_t n = std::strlen(s); if ((size_t)(end_ - p_) < n || std::memcmp(p_, s, n)) return false; p_ += n; return true; }
+	bool string(std::string& out) {
+		if (p_ >= end_ || *p_ != '"') return false;
+		++p_;
+		while (p_ < end_ && *p_ != '"') {
+			if (*p_ == '\\') {
+				if (++p_ >= end_) return false;
+				switch (*p_) {
+				case 'n': out += '\n'; break; case 't': out += '\t'; break; case 'r': out += '\r'; break;
+				case 'b': out += '\b'; break; case 'f': out += '\f'; break;
+				case 'u': { // keep the BMP code point as UTF-8 (names only; nothing numeric depends on it)
+					if (end_ - p_ < 5) return false;
+					unsigned cp = (unsigned)std::strtoul(std::string(p_ + 1, 4).c_str(), nullptr, 16);
+					p_ += 4;
+					if (cp < 0x80) out += (char)cp;
+					else if (cp < 0x800) { out += (char)(0xC0 | (cp >> 6)); out += (char)(0x80 | (cp & 0x3F)); }
+					else { out += (char)(0xE0 | (cp >> 12)); out += (char)(0x80 | ((cp >> 6) & 0x3F)); out += (char)(0x80 | (cp & 0x3F)); }
+					break;
+				}
+				default: out += *p_;
+				}
+				++p_;
+			} else out += *p_++;
+		}
+		if (p_ >= end_) return false;
+		++p_;
+		return true;
+	}
+	bool value(Json& out, int depth) {
+		if (depth > 64 || p_ >= end_) return false;
+		const char c = *p_;
+		if (c == '{') {
+			out.kind = Json::Object; ++p_; skip();
+			if (p_ < end_ && *p_ == '}') { ++p_; return true; }
+			for (;;) {
+				std::string key; skip();
+				if (!string(key)) return false;
+				skip(); if (p_ >= end_ || *p_ != ':') return false; ++p_; skip();
+				out.obj.emplace_back(std::move(key), Json());
+				if (!value(out.obj.back().second, depth + 1)) return false;
+				skip(); if (p_ >= end_) return false;
+				if (*p_ == ',') { ++p_; continue; }
+				if (*p_ == '}') { ++p_; return true; }
+				return false;
+			}
+		}
+		if (c == '[') {
+			out.kind = Json::Array; ++p_; skip();
+			if (p_ < end_ && *p_ == ']') { ++p_; return true; }
+			for (;;) {
+				out.arr.emplace_back(); skip();
+				if (!value(out.arr.back(), depth + 1)) return false;
+				skip(); if (p_ >= end_) return false;
+				if (*p_ == ',') { ++p_; continue; }
+				if (*p_ == ']') { ++p_; return true; }
+				return false;
+			}
+		}
+		if (c == '"') { out.kind = Json::String; return string(out.str); }
+		if (c == 't') { out.kind = Json::Bool; out.b = true; return lit("true"); }
+		if (c == 'f') { out.kind = Json::Bool; out.b = false; return lit("false"); }
+		if (c == 'n') { out.kind = Json::Null; return lit("null"); }
+		char* e = nullptr;
+		std::string tmp(p_, (size_t)std::min<ptrdiff_t>(end_ - p_, 64));
+		out.num = std::strtod(tmp.c_str(), &e);
+		if (e == tmp.c_str()) return false;
+		out.kind = Json::Number;
+		p_ += e - tmp.c_str();
+		return true;
+	}
+	const char* p_; const char* end_;
+};
+
+struct Fail { std::string msg; };
+[[noreturn]] void fail(const std::string& m) { throw Fail{m}; }
+
+std::vector<uint8_t> base64(const std::string& s, size_t from) {
+	std::vector<uint8_t> out;
+	unsigned acc = 0; int bits = 0;
+	for (size_t i = from; i < s.size(); ++i) {
+		const char c = s[i];
+		int v;
+		if (c >= 'A' && c <= 'Z') v = c - 'A'; else if (c >= 'a' && c <= 'z') v = c - 'a' + 26; else if (c >= '0' && c <= '9') v = c - '0' + 52;
+		else if (c == '+') v = 62; else if (c == '/') v = 63; else if (c == '=') break; else continue;
+		acc = (acc << 6) | (unsigned)v; bits += 6;
+		if (bits >= 8) { bits -= 8; out.push_back((uint8_t)(acc >> bits)); }
+	}
+	return out;
+}
+
+struct View { const uint8_t* data; size_t size; size_t stride; }; // stride 0 = tightly packed
+struct Acc { View view; size_t offset, count; int ctype; bool normalized; int comps; const Json* json; };
+
+size_t ctype_size(int t) { return (t == 5120 || t == 5121) ? 1 : (t == 5122 || t == 5123) ? 2 : (t == 5125 || t == 5126) ? 4 : 0; }
+
+// fastgltf::internal::convertComponent<float, T> (tools.hpp:266-289)
+float to_float(const uint8_t* p, int ctype, bool normalized) {
+	switch (ctype) {
+	case 5120: { int8_t v; std::memcpy(&v, p, 1); return normalized ? std::max((float)v / 127.0f, -1.0f) : (float)v; }
+	case 5121: { uint8_t v = *p; return normalized ? (float)v / 255.0f : (float)v; }
+	case 5122: { int16_t v; std::memcpy(&v, p, 2); return normalized ? std::max((float)v / 32767.0f, -1.0f) : (float)v; }
+	case 5123: { uint16_t v; std::memcpy(&v, p, 2); return normalized ? (float)v / 65535.0f : (float)v; }
+	case 5125: { uint32_t v; std::memcpy(&v, p, 4); return normalized ? (float)v / 4294967295.0f : (float)v; }
+	default: { float v; std::memcpy(&v, p, 4); return v; }
+	}
+}
+
+// fastgltf::math::decomposeTransformMatrix (math.hpp:854-891), operation for operation
+void decompose(const float* m16, float t[3], float r[4], float s[3]) {
+	float m[16];
+	std::memcpy(m, m16, 64);
+	t[0] = m[12]; t[1] = m[13]; t[2] = m[14];
+	m[12] = m[13] = m[14] = 0.f;
+	for (int c = 0; c < 3; ++c) {
+		const float* col = m + c * 4;
+		float sum = col[0] * col[0];
+		for (int i = 1; i < 4; ++i) sum += col[i] * col[i];
+		s[c] = std::sqrt(sum);
+	}
+	for (int c = 0; c < 3; ++c)
+		for (int i = 0; i < 4; ++i) m[c * 4 + i] /= s[c];
+	auto at = [&](int c, int rr) { return m[c * 4 + rr]; };
+	float q[4] = {std::max(.0f, 1.f + at(0, 0) - at(1, 1) - at(2, 2)), std::max(.0f, 1.f - at(0, 0) + at(1, 1) - at(2, 2)),
+	              std::max(.0f, 1.f - at(0, 0) - at(1, 1) + at(2, 2)), std::max(.0f, 1.f + at(0, 0) + at(1, 1) + at(2, 2))};
+	for (int i = 0; i < 4; ++i) q[i] = static_cast<float>(std::sqrt(static_cast<double>(q[i]))) / 2;
+	q[0] = std::copysignf(q[0], at(1, 2) - at(2, 1));
+	q[1] = std::copysignf(q[1], at(2, 0) - at(0, 2));
+	q[2] = std::copysignf(q[2], at(0, 1) - at(1, 0));
+	std::memcpy(r, q, 16);
+}
+
+struct Loader {
+	const uint8_t* bin = nullptr; size_t binSize = 0;
+	Json doc;
+	std::vector<std::vector<uint8_t>> owned; // decoded data-URI buffers
+	std::vector<View> buffers;
+
+	View bufferView(long long idx) {
+		const Json* bvs = doc.get("bufferViews");
+		if (!bvs || idx < 0 || (size_t)idx >= bvs->size()) fail("bufferView index out of range");
+		const Json& bv = bvs->arr[(size_t)idx];
+		if (const Json* ext = bv.get("extensions"))
+			if (ext->has("EXT_meshopt_compression"))
+				fail("bufferView " + std::to_string(idx) + " is EXT_meshopt_compression-compressed: decode it on the device (vkv_meshopt_plan_create / vkv_meshopt_run take the compressed views as they are)");
+		const long long b = bv.integer("buffer", -1);
+		if (b < 0 || (size_t)b >= buffers.size()) fail("bufferView.buffer out of range");
+		const size_t off = (size_t)bv.integer("byteOffset", 0), len = (size_t)bv.integer("byteLength", 0);
+		if (off + len > buffers[(size_t)b].size) fail("bufferView exceeds its buffer");
+		return View{buffers[(size_t)b].data + off, len, (size_t)bv.integer("byteStride", 0)};
+	}
+	Acc accessor(long long idx) {
+		const Json* as = doc.get("accessors");
+		if (!as || idx < 0 || (size_t)idx >= as->size()) fail("accessor index out of range");
+		const Json& a = as->arr[(size_t)idx];
+		if (a.has("sparse")) fail("sparse accessors are not supported");
+		if (!a.has("bufferView")) fail("accessor without bufferView");
+		Acc r;
+		r.json = &a;
+		r.view = bufferView(a.integer("bufferView", -1));
+		r.offset = (size_t)a.integer("byteOffset", 0);
+		r.count = (size_t)a.integer("count", 0);
+		r.ctype = (int)a.integer("componentType", 0);
+		r.normalized = a.boolean("normalized", false);
+		const Json* ty = a.get("type");
+		const std::string t = ty && ty->kind == Json::String ? ty->str : "";
+		r.comps = t == "SCALAR" ? 1 : t == "VEC2" ? 2 : t == "VEC3" ? 3 : t == "VEC4" ? 4 : 0;
+		const size_t cs = ctype_size(r.ctype);
+		if (!cs || !r.comps) fail("accessor with an unsupported componentType / type");
+		const size_t stride = r.view.stride ? r.view.stride : cs * r.comps;
+		if (r.count && r.offset + (r.count - 1) * stride + cs * r.comps > r.view.size) fail("accessor exceeds its bufferView");
+		return r;
+	}
+};
+
+} // namespace
+} // namespace vkvh
+
+extern "C" {
+
+vkvh_scene* vkvh_scene_load_glb(const void* data, size_t bytes, char* err, size_t errcap) {
+	using namespace vkvh;
+	auto report = [&](const std::string& m) { if (err && errcap) std::snprintf(err, errcap, "%s", m.c_str()); };
+	vkvh_scene* s = nullptr;
+	try {
+		const uint8_t* p = (const uint8_t*)data;
+		auto u32 = [&](size_t o) { uint32_t v; std::memcpy(&v, p + o, 4); return v; };
+		if (!p || bytes < 20 || u32(0) != 0x46546C67u) fail("not a GLB container (magic)");
+		if (u32(4) != 2) fail("GLB version " + std::to_string(u32(4)) + " (only 2 is supported)");
+		const size_t total = u32(8);
+		if (total > bytes) fail("GLB length field exceeds the data");
+		Loader L;
+		size_t o = 12;
+		const char* json = nullptr; size_t jsonLen = 0;
+		while (o + 8 <= total) {
+			const size_t len = u32(o), type = u32(o + 4);
+			if (o + 8 + len > total) fail("GLB chunk exceeds the container");
+			if (type == 0x4E4F534Au && !json) { json = (const char*)p + o + 8; jsonLen = len; }
+			else if (type == 0x004E4942u && !L.bin) { L.bin = p + o + 8; L.binSize = len; }
+			o += 8 + ((len + 3) & ~(size_t)3);
+		}
+		if (!json) fail("GLB without a JSON chunk");
+		if (!JsonParser(json, jsonLen).parse(L.doc) || L.doc.kind != Json::Object) fail("malformed glTF JSON");
+
+		if (const Json* bufs = L.doc.get("buffers"))
+			for (size_t i = 0; i < bufs->size(); ++i) {
+				const Json& b = bufs->arr[i];
+				const Json* uri = b.get("uri");
+				if (!uri) { // the GLB-stored buffer
+					if (i != 0 || !L.bin) fail("buffer without uri that is not the GLB BIN chunk");
+					if ((size_t)b.integer("byteLength", 0) > L.binSize) fail("buffers[0].byteLength exceeds the BIN chunk");
+					L.buffers.push_back(View{L.bin, (size_t)b.integer("byteLength", 0), 0});
+				} else {
+					const std::string& u = uri->str;
+					const size_t comma = u.find(',');
+					if (u.compare(0, 5, "data:") != 0 || comma == std::string::npos || u.find(";base64") == std::string::npos)
+						fail("external buffer uri '" + u.substr(0, 40) + "': only the GLB chunk and base64 data URIs are read here");
+					L.owned.push_back(base64(u, comma + 1));
+					L.buffers.push_back(View{L.owned.back().data(), L.owned.back().size(), 0});
+				}
+			}
+
+		s = vkvh_scene_new();
+		// materials (world.cpp:132-178 / assets.cpp:486-492: glTF material i -> index i + 1)
+		if (const Json* mats = L.doc.get("materials"))
+			for (const Json& m : mats->arr) {
+				float albedo[4] = {1, 1, 1, 1};
+				if (const Json* pbr = m.get("pbrMetallicRoughness"))
+					if (const Json* f = pbr->get("baseColorFactor"))
+						for (size_t k = 0; k < 4 && k < f->size(); ++k) albedo[k] = (float)f->arr[k].num;
+				const uint32_t idx = vkvh_scene_add_material(s, albedo, m.boolean("doubleSided", false) ? 1 : 0);
+				s->materials[idx].alphaCutoff = (float)m.number("alphaCutoff", 0.5);
+			}
+
+		// meshes -> primitives (assets.cpp:288-373), flattened in mesh order like the reference's primitiveBuffers
+		std::vector<std::vector<int32_t>> meshPrims;
+		if (const Json* meshes = L.doc.get("meshes"))
+			for (const Json& mesh : meshes->arr) {
+				meshPrims.emplace_back();
+				const Json* prims = mesh.get("primitives");
+				if (!prims) continue;
+				for (const Json& pr : prims->arr) {
+					if (pr.integer("mode", 4) != 4) continue; // only triangle lists reach the mesh-shader path
+					const Json* attrs = pr.get("attributes");
+					if (!attrs || !attrs->has("POSITION")) fail("primitive without POSITION");
+					const Acc pos = L.accessor(attrs->integer("POSITION", -1));
+					if (pos.comps != 3) fail("POSITION accessor is not VEC3");
+					const size_t cs = ctype_size(pos.ctype), stride = pos.view.stride ? pos.view.stride : cs * 3;
+					std::vector<vkv_Vertex> verts(pos.count);
+					for (size_t i = 0; i < pos.count; ++i) {
+						std::memset(&verts[i], 0, sizeof(vkv_Vertex));
+						const uint8_t* e = pos.view.data + pos.offset + i * stride;
+						for (int k = 0; k < 3; ++k) verts[i].position[k] = to_float(e + k * cs, pos.ctype, pos.normalized);
+						verts[i].color[0] = verts[i].color[1] = verts[i].color[2] = verts[i].color[3] = 255;
+					}
+					std::vector<uint32_t> idx;
+					if (pr.has("indices")) {
+						const Acc ia = L.accessor(pr.integer("indices", -1));
+						if (ia.comps != 1 || (ia.ctype != 5121 && ia.ctype != 5123 && ia.ctype != 5125)) fail("index accessor must be SCALAR u8 / u16 / u32");
+						const size_t is = ctype_size(ia.ctype), istride = ia.view.stride ? ia.view.stride : is;
+						idx.resize(ia.count);
+						for (size_t i = 0; i < ia.count; ++i) {
+							const uint8_t* e = ia.view.data + ia.offset + i * istride;
+							uint32_t v = 0;
+							std::memcpy(&v, e, is);
+							idx[i] = v;
+						}
+					} else { // Options::GenerateMeshIndices
+						idx.resize(pos.count);
+						for (size_t i = 0; i < pos.count; ++i) idx[i] = (uint32_t)i;
+					}
+					const long long mat = pr.integer("material", -1);
+					const uint32_t materialIndex = mat >= 0 ? (uint32_t)mat + 1 : 0u;
+					if (materialIndex >= s->materials.size()) fail("primitive.material out of range");
+					PrimitiveData pd;
+					if (!build_primitive(pd, std::move(verts), idx.data(), (uint32_t)idx.size(), materialIndex)) fail("primitive with no triangles or an index out of range");
+					// assets.cpp:303-306: the primitive's AABB comes from the accessor's min / max (zero vectors when absent)
+					float mn[3] = {0, 0, 0}, mx[3] = {0, 0, 0};
+					const Json* jmin = pos.json->get("min"); const Json* jmax = pos.json->get("max");
+					if (jmin && jmin->size() == 3) for (int k = 0; k < 3; ++k) mn[k] = (float)jmin->arr[k].num;
+					if (jmax && jmax->size() == 3) for (int k = 0; k < 3; ++k) mx[k] = (float)jmax->arr[k].num;
+					for (int k = 0; k < 3; ++k) {
+						pd.header.aabbCenter[k] = (mn[k] + mx[k]) / 2.f;
+						pd.header.aabbExtents[k] = mx[k] - pd.header.aabbCenter[k];
+					}
+					meshPrims.back().push_back(add_built_primitive(s, std::move(pd)));
+				}
+			}
+
+		// nodes (world.cpp:187-228): TRS as given, matrices decomposed (Options::DecomposeNodeMatrices); scene roots in order
+		const Json* nodes = L.doc.get("nodes");
+		const size_t nNodes = nodes ? nodes->size() : 0;
+		std::function<void(size_t, int32_t, int)> addNode = [&](size_t ni, int32_t parent, int depth) {
+			if (ni >= nNodes || depth > 256) fail("node index out of range or node hierarchy too deep / cyclic");
+			const Json& n = nodes->arr[ni];
+			float t[3] = {0, 0, 0}, r[4] = {0, 0, 0, 1}, sc[3] = {1, 1, 1};
+			if (const Json* m = n.get("matrix")) {
+				if (m->size() != 16) fail("node.matrix must have 16 elements");
+				float mm[16];
+				for (int k = 0; k < 16; ++k) mm[k] = (float)m->arr[(size_t)k].num;
+				decompose(mm, t, r, sc);
+			} else {
+				if (const Json* v = n.get("translation")) for (size_t k = 0; k < 3 && k < v->size(); ++k) t[k] = (float)v->arr[k].num;
+				if (const Json* v = n.get("rotation")) for (size_t k = 0; k < 4 && k < v->size(); ++k) r[k] = (float)v->arr[k].num;
+				if (const Json* v = n.get("scale")) for (size_t k = 0; k < 3 && k < v->size(); ++k) sc[k] = (float)v->arr[k].num;
+			}
+			const long long mesh = n.integer("mesh", -1);
+			if (mesh >= 0 && (size_t)mesh >= meshPrims.size()) fail("node.mesh out of range");
+			const int32_t self = vkvh_scene_add_node_mesh(s, parent, mesh >= 0 ? meshPrims[(size_t)mesh].data() : nullptr,
+			                                             mesh >= 0 ? (uint32_t)meshPrims[(size_t)mesh].size() : 0u, mesh >= 0 ? 1 : 0, t, r, sc);
+			if (self < 0) fail("invalid node");
+			if (const Json* ch = n.get("children"))
+				for (const Json& c : ch->arr) addNode((size_t)c.num, self, depth + 1);
+		};
+		const Json* scenes = L.doc.get("scenes");
+		if (scenes && scenes->size()) {
+			const size_t si = (size_t)L.doc.integer("scene", 0);
+			if (si >= scenes->size()) fail("scene index out of range");
+			if (const Json* roots = scenes->arr[si].get("nodes"))
+				for (const Json& rn : roots->arr) addNode((size_t)rn.num, -1, 0);
+		}
+		if (vkvh_scene_finalize(s) != 0) fail("the draw list exceeds 2^25 MeshletDraws (visbuffer.h.glsl:15-17)");
+		return s;
+	} catch (const vkvh::Fail& f) {
+		report(f.msg);
+	} catch (const std::exception& e) {
+		report(std::string("glTF load failed: ") + e.what());
+	}
+	if (s) vkvh_scene_free(s);
+	return nullptr;
+}
+
+} // extern "C"

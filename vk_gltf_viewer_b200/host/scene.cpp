@@ -177,9 +177,17 @@ int32_t vkvh_scene_add_primitive_i16(vkvh_scene* s, const int16_t* positions, ui
 }
 
 int32_t vkvh_scene_add_node_trs(vkvh_scene* s, int32_t parent, int32_t primitive, const float t[3], const float r[4], const float sc[3]) {
-	if (parent >= (int32_t)s->nodes.size() || primitive >= (int32_t)s->primitives.size()) return -1;
+	return vkvh_scene_add_node_mesh(s, parent, primitive >= 0 ? &primitive : nullptr, primitive >= 0 ? 1u : 0u, primitive >= 0 ? 1 : 0, t, r, sc);
+}
+
+int32_t vkvh_scene_add_node_mesh(vkvh_scene* s, int32_t parent, const int32_t* primitives, uint32_t n_primitives, int has_mesh, const float t[3],
+                                 const float r[4], const float sc[3]) {
+	if (parent >= (int32_t)s->nodes.size() || (n_primitives && !primitives)) return -1;
+	for (uint32_t i = 0; i < n_primitives; ++i)
+		if (primitives[i] < 0 || primitives[i] >= (int32_t)s->primitives.size()) return -1;
 	Node n;
-	n.parent = parent; n.primitive = primitive;
+	n.parent = parent; n.hasMesh = has_mesh != 0 || n_primitives > 0;
+	n.primitives.assign(primitives, primitives + n_primitives);
 	if (t) std::memcpy(n.t, t, 12);
 	if (r) std::memcpy(n.r, r, 16);
 	if (sc) std::memcpy(n.s, sc, 12);
@@ -197,10 +205,12 @@ int vkvh_scene_finalize(vkvh_scene* s) {
 	std::function<void(int32_t, const mat4&)> walk = [&](int32_t ni, const mat4& parent) {
 		const Node& n = s->nodes[ni];
 		mat4 m = scale(rotate(translate(parent, n.t), n.r), n.s);
-		if (n.primitive >= 0) {
+		if (n.hasMesh) {
 			uint32_t ti = transformCount++;
-			const auto& pd = s->primitives[n.primitive];
-			for (uint32_t i = 0; i < pd.header.meshletCount; ++i) s->draws.push_back(vkv_MeshletDraw{(uint32_t)n.primitive, i, ti});
+			for (int32_t prim : n.primitives) {
+				const auto& pd = s->primitives[prim];
+				for (uint32_t i = 0; i < pd.header.meshletCount; ++i) s->draws.push_back(vkv_MeshletDraw{(uint32_t)prim, i, ti});
+			}
 			s->transforms.insert(s->transforms.end(), m.m, m.m + 16);
 		}
 		for (int32_t c : n.children) walk(c, m);

@@ -23,7 +23,8 @@ struct PrimitiveData {
 
 struct Node {
 	int32_t parent = -1;
-	int32_t primitive = -1;
+	bool hasMesh = false;                    // takes a transform slot (world.cpp:246-252), even when its mesh has no drawable primitive
+	std::vector<int32_t> primitives;         // the node's mesh: every primitive shares the node's transform (world.cpp:253-262)
 	float t[3] = {0, 0, 0}, r[4] = {0, 0, 0, 1}, s[3] = {1, 1, 1};
 	std::vector<int32_t> children;
 };

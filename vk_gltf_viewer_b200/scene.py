@@ -72,6 +72,10 @@ def _lib():
         L.vkvh_frustum_from_vp.argtypes = [C.POINTER(C.c_float), C.c_void_p]
         L.vkvh_set_meshlet_builder.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.vkvh_select_builder.argtypes = [C.c_int]
+        L.vkvh_scene_load_glb.restype = C.c_void_p
+        L.vkvh_scene_load_glb.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]
+        L.vkvh_scene_add_node_mesh.restype = C.c_int32
+        L.vkvh_scene_add_node_mesh.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.vkvh_scene_host_cones.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         L.vkvh_scene_upload_cones.argtypes = [C.c_void_p, UPLOAD_FN, C.c_void_p, C.POINTER(C.c_uint64)]
         _bound = True
@@ -161,6 +165,24 @@ class Scene:
     @classmethod
     def city(cls, nbx=50, nby=40, tris_per_building=10000, seed=0x5EED0004):
         return cls(_lib().vkvh_scene_city(nbx, nby, tris_per_building, seed))
+
+    @classmethod
+    def from_glb(cls, data: bytes):
+        """glTF 2.0 binary ingest (host/gltf.cpp: what the reference reads of an asset through fastgltf)"""
+        err = C.create_string_buffer(512)
+        h = _lib().vkvh_scene_load_glb(data, len(data), err, len(err))
+        if not h:
+            raise ValueError(err.value.decode() or "glTF load failed")
+        return cls(h)
+
+    def add_mesh_node(self, primitives, parent=-1, translation=(0, 0, 0), rotation=(0, 0, 0, 1), scale=(1, 1, 1)) -> int:
+        """a node whose mesh has several primitives: they share one transform slot (world.cpp:246-262)"""
+        p = np.ascontiguousarray(primitives, np.int32)
+        t, r, s = _f3(translation), (C.c_float * 4)(*[float(x) for x in rotation]), _f3(scale)
+        n = _lib().vkvh_scene_add_node_mesh(self.h, parent, p.ctypes.data if p.size else None, p.size, 1, t, r, s)
+        if n < 0:
+            raise ValueError("invalid node")
+        return n
 
     def add_material(self, albedo=(1, 1, 1, 1), double_sided=False) -> int:
         return _lib().vkvh_scene_add_material(self.h, (C.c_float * 4)(*albedo), int(double_sided))
