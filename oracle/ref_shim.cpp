@@ -164,6 +164,18 @@ void ref_node_matrix(const float parent[16], const float t[3], const float r[4],
 	std::memcpy(out, m.data(), 64);
 }
 
+// fastgltf::math::decomposeTransformMatrix (math.hpp:854-891): what Options::DecomposeNodeMatrices applies to node.matrix
+void ref_decompose(const float m[16], float t[3], float r[4], float s[3]) {
+	namespace fm = fastgltf::math;
+	fm::fmat4x4 mat;
+	std::memcpy(mat.data(), m, 64);
+	fm::fvec3 scale, translation;
+	fm::fquat rotation;
+	fm::decomposeTransformMatrix(mat, scale, rotation, translation);
+	for (int i = 0; i < 3; ++i) { t[i] = translation[i]; s[i] = scale[i]; }
+	for (int i = 0; i < 4; ++i) r[i] = rotation[i];
+}
+
 // fastgltf::internal::convertComponent<float, T> (tools.hpp:266-289): what iterateAccessor<glm::vec3> applies to every POSITION
 // component (assets.cpp:310-314).  type: glTF componentType (5120 BYTE, 5121 UNSIGNED_BYTE, 5122 SHORT, 5123 UNSIGNED_SHORT)
 float ref_convert_component(int type, int normalized, int value) {

@@ -1,0 +1,107 @@
+"""A tiny glTF 2.0 binary (GLB) writer for the ingest tests: procedurally generated glTF scenes (BASELINE.json: "synthetic
+procedurally generated glTF scenes").  It writes what the reference reads of an asset (assets.cpp:288-373, world.cpp:187-293):
+buffers, bufferViews (optionally strided), accessors (float or KHR_mesh_quantization integers, u8 / u16 / u32 indices), materials,
+meshes with several primitives, nodes (TRS or matrix), one scene."""
+import json
+import struct
+
+import numpy as np
+
+CT = {np.dtype(np.int8): 5120, np.dtype(np.uint8): 5121, np.dtype(np.int16): 5122, np.dtype(np.uint16): 5123,
+      np.dtype(np.uint32): 5125, np.dtype(np.float32): 5126}
+
+
+class GlbWriter:
+    def __init__(self):
+        self.bin = bytearray()
+        self.doc = {"asset": {"version": "2.0"}, "buffers": [{}], "bufferViews": [], "accessors": [], "materials": [], "meshes": [],
+                    "nodes": [], "scenes": [{"nodes": []}], "scene": 0, "extensionsUsed": []}
+
+    def _view(self, raw: bytes, stride=0) -> int:
+        while len(self.bin) % 4:
+            self.bin.append(0)
+        v = {"buffer": 0, "byteOffset": len(self.bin), "byteLength": len(raw)}
+        if stride:
+            v["byteStride"] = stride
+        self.bin += raw
+        self.doc["bufferViews"].append(v)
+        return len(self.doc["bufferViews"]) - 1
+
+    def positions(self, pos, normalized=False, stride=0, minmax=True) -> int:
+        """pos: (n,3) float32 or an integer dtype (KHR_mesh_quantization); stride > element size interleaves padding"""
+        p = np.ascontiguousarray(pos)
+        elem = p.dtype.itemsize * 3
+        if stride:
+            raw = bytearray(stride * p.shape[0])
+            for i in range(p.shape[0]):
+                raw[i * stride: i * stride + elem] = p[i].tobytes()
+            raw = bytes(raw)
+        else:
+            raw = p.tobytes()
+        a = {"bufferView": self._view(raw, stride), "componentType": CT[p.dtype], "count": int(p.shape[0]), "type": "VEC3"}
+        if normalized:
+            a["normalized"] = True
+        if p.dtype != np.float32 and "KHR_mesh_quantization" not in self.doc["extensionsUsed"]:
+            self.doc["extensionsUsed"].append("KHR_mesh_quantization")
+        if minmax:
+            a["min"] = [float(x) if p.dtype == np.float32 else int(x) for x in p.min(0)]
+            a["max"] = [float(x) if p.dtype == np.float32 else int(x) for x in p.max(0)]
+        self.doc["accessors"].append(a)
+        return len(self.doc["accessors"]) - 1
+
+    def indices(self, idx) -> int:
+        i = np.ascontiguousarray(idx).reshape(-1)
+        self.doc["accessors"].append({"bufferView": self._view(i.tobytes()), "componentType": CT[i.dtype], "count": int(i.size), "type": "SCALAR"})
+        return len(self.doc["accessors"]) - 1
+
+    def material(self, base_color=(1, 1, 1, 1), double_sided=False, alpha_cutoff=None) -> int:
+        m = {"pbrMetallicRoughness": {"baseColorFactor": [float(x) for x in base_color]}, "doubleSided": bool(double_sided)}
+        if alpha_cutoff is not None:
+            m["alphaCutoff"] = float(alpha_cutoff)
+        self.doc["materials"].append(m)
+        return len(self.doc["materials"]) - 1
+
+    def mesh(self, primitives) -> int:
+        """primitives: list of dicts {position: accessor, indices: accessor or None, material: index or None, mode: int}"""
+        ps = []
+        for p in primitives:
+            d = {"attributes": {"POSITION": p["position"]}}
+            if p.get("indices") is not None:
+                d["indices"] = p["indices"]
+            if p.get("material") is not None:
+                d["material"] = p["material"]
+            if "mode" in p:
+                d["mode"] = p["mode"]
+            ps.append(d)
+        self.doc["meshes"].append({"primitives": ps})
+        return len(self.doc["meshes"]) - 1
+
+    def node(self, mesh=None, parent=None, translation=None, rotation=None, scale=None, matrix=None) -> int:
+        n = {}
+        if mesh is not None:
+            n["mesh"] = mesh
+        if matrix is not None:
+            n["matrix"] = [float(x) for x in np.asarray(matrix, np.float32).reshape(-1)]   # column-major, as glTF stores it
+        else:
+            if translation is not None: n["translation"] = [float(x) for x in translation]
+            if rotation is not None: n["rotation"] = [float(x) for x in rotation]
+            if scale is not None: n["scale"] = [float(x) for x in scale]
+        self.doc["nodes"].append(n)
+        i = len(self.doc["nodes"]) - 1
+        if parent is None:
+            self.doc["scenes"][0]["nodes"].append(i)
+        else:
+            self.doc["nodes"][parent].setdefault("children", []).append(i)
+        return i
+
+    def glb(self) -> bytes:
+        doc = dict(self.doc)
+        doc["buffers"] = [{"byteLength": len(self.bin)}]
+        for k in ("materials", "extensionsUsed"):
+            if not doc[k]:
+                del doc[k]
+        js = json.dumps(doc, separators=(",", ":")).encode()
+        js += b" " * (-len(js) % 4)
+        bn = bytes(self.bin) + b"\0" * (-len(self.bin) % 4)
+        total = 12 + 8 + len(js) + 8 + len(bn)
+        return struct.pack("<III", 0x46546C67, 2, total) + struct.pack("<II", len(js), 0x4E4F534A) + js + struct.pack("<II", len(bn), 0x004E4942) + bn

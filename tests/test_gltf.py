@@ -1,0 +1,136 @@
+"""glTF ingest (host/gltf.cpp): a procedurally generated GLB must produce, byte for byte, the buffers the same scene built through
+the direct host API produces — vertices (float and KHR_mesh_quantization integers, strided views), widened / generated indices,
+meshlets, materials (index + 1), multi-primitive meshes sharing one transform, node TRS and decomposed matrices, draw order."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from tests import scenes as S
+from tests.gltf_writer import GlbWriter
+from vk_gltf_viewer_b200.scene import Scene
+
+
+def same_scene(a: Scene, b: Scene):
+    ca, cb = a.counts(), b.counts()
+    for f in ("primitives", "materials", "transforms", "draws", "nodes", "triangles_unique", "triangles_instanced", "meshlets_unique", "vertices_unique"):
+        assert getattr(ca, f) == getattr(cb, f), f
+    assert a.draws().tobytes() == b.draws().tobytes()
+    assert a.transforms().tobytes() == b.transforms().tobytes()
+    assert a.materials().tobytes() == b.materials().tobytes()
+    for i in range(ca.primitives):
+        pa, pb = a.primitive(i), b.primitive(i)
+        for k in ("vertex_indices", "triangles", "vertices", "meshlets"):
+            assert pa[k].tobytes() == pb[k].tobytes(), (i, k)
+        assert pa["header"].materialIndex == pb["header"].materialIndex and pa["header"].meshletCount == pb["header"].meshletCount
+
+
+def test_glb_scene_equals_the_directly_built_scene():
+    rng = np.random.default_rng(9)
+    posA, idxA = S.grid_mesh(30, 22, lambda u, v: (u * 3, 0.2 * np.sin(u * 9) * np.cos(v * 5), v * 2))
+    posB, idxB = S.grid_mesh(9, 9, lambda u, v: (u, v, 0 * u))
+    qC = rng.integers(-2000, 2000, (40, 3)).astype(np.int16)          # KHR_mesh_quantization, not normalized
+    idxC = rng.integers(0, 40, 90).astype(np.uint32)
+    qD = rng.integers(-32768, 32767, (25, 3)).astype(np.int16)        # normalized
+    idxD = rng.integers(0, 25, 60).astype(np.uint32)
+
+    w = GlbWriter()
+    m0 = w.material((0.8, 0.2, 0.1, 1.0), double_sided=False)
+    m1 = w.material((0.1, 0.9, 0.3, 0.5), double_sided=True)
+    a = {"position": w.positions(posA), "indices": w.indices(idxA.astype(np.uint32)), "material": m0}
+    b = {"position": w.positions(posB, stride=20), "indices": w.indices(idxB.astype(np.uint16)), "material": m1}   # strided view, u16 indices
+    c = {"position": w.positions(qC), "indices": w.indices(idxC.astype(np.uint8)), "material": None}                # int16 positions, u8 indices, default material
+    d = {"position": w.positions(qD, normalized=True), "indices": w.indices(idxD.astype(np.uint16)), "material": m0}
+    lines = {"position": w.positions(posB), "indices": w.indices(idxB.astype(np.uint16)), "mode": 1}                # LINES: not drawn by the path
+    mesh0, mesh1, mesh2 = w.mesh([a, b]), w.mesh([c, lines]), w.mesh([d])
+    q = rng.normal(size=4); q /= np.linalg.norm(q)
+    root = w.node(translation=(1, 2, 3))                                                      # transform only
+    n1 = w.node(mesh0, parent=root, rotation=q, scale=(2, 0.5, 1.5))
+    w.node(mesh1, parent=n1, translation=(0.5, 0, -1))
+    w.node(mesh2, translation=(-4, 0, 0), scale=(100, 100, -100))                             # second root, mirrored
+    w.node(mesh0, parent=root)                                                                  # instancing: mesh0 again
+    got = Scene.from_glb(w.glb())
+
+    ref = Scene.new()
+    r0, r1 = ref.add_material((0.8, 0.2, 0.1, 1.0), False), ref.add_material((0.1, 0.9, 0.3, 0.5), True)
+    pa = ref.add_primitive(posA, idxA, r0)
+    pb = ref.add_primitive(posB, idxB, r1)
+    pc = ref.add_primitive_i16(qC, idxC, 0)
+    pd = ref.add_primitive_i16(qD, idxD, r0, normalized=True)
+    rr = ref.add_node(-1, translation=(1, 2, 3))
+    k1 = ref.add_mesh_node([pa, pb], parent=rr, rotation=q, scale=(2, 0.5, 1.5))
+    ref.add_mesh_node([pc], parent=k1, translation=(0.5, 0, -1))
+    ref.add_mesh_node([pa, pb], parent=rr)
+    ref.add_mesh_node([pd], translation=(-4, 0, 0), scale=(100, 100, -100))
+    ref.finalize()
+    # glTF child order: root's children are n1, then the second mesh0 instance; the second ROOT comes after the whole first tree
+    same_scene(got, ref)
+    # assets.cpp:303-306: primitive AABB from the accessor min / max
+    h = got.primitive(0)["header"]
+    mn, mx = posA.min(0), posA.max(0)
+    c = (mn + mx) / np.float32(2)
+    assert np.allclose(list(h.aabbCenter), c, rtol=0, atol=0) and np.allclose(list(h.aabbExtents), mx - c, rtol=0, atol=0)
+
+
+def test_generated_indices_and_missing_minmax():
+    pos = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0]], np.float32)
+    w = GlbWriter()
+    w.node(w.mesh([{"position": w.positions(pos, minmax=False), "indices": None}]))
+    s = Scene.from_glb(w.glb())
+    ref = Scene.new()
+    ref.add_node(ref.add_primitive(pos, np.arange(6, dtype=np.uint32)))
+    ref.finalize()
+    same_scene(s, ref)
+    h = s.primitive(0)["header"]
+    assert list(h.aabbCenter) == [0, 0, 0] and list(h.aabbExtents) == [0, 0, 0]   # getAccessorMinMax's default: zero vectors
+
+
+def test_matrix_nodes_decompose_like_fastgltf(ref_shim):
+    """node.matrix goes through the restated fastgltf::math::decomposeTransformMatrix (Options::DecomposeNodeMatrices); the result
+    equals fastgltf's own decomposition (oracle/_ref) fed through the same TRS path, bit for bit"""
+    rng = np.random.default_rng(21)
+    pos, idx = S.grid_mesh(4, 4, lambda u, v: (u, v, 0 * u))
+    ref_shim.ref_decompose.restype = None
+    w = GlbWriter()
+    mesh = w.mesh([{"position": w.positions(pos), "indices": w.indices(idx.astype(np.uint16))}])
+    ref = Scene.new()
+    p = ref.add_primitive(pos, idx)
+    for k in range(12):
+        q = rng.normal(size=4); q /= np.linalg.norm(q)
+        x, y, z, ww = q
+        R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * ww), 2 * (x * z + y * ww)],
+                      [2 * (x * y + z * ww), 1 - 2 * (x * x + z * z), 2 * (y * z - x * ww)],
+                      [2 * (x * z - y * ww), 2 * (y * z + x * ww), 1 - 2 * (x * x + y * y)]])
+        M = np.eye(4)
+        M[:3, :3] = R @ np.diag(rng.uniform(0.2, 3, 3))
+        M[:3, 3] = rng.uniform(-5, 5, 3)
+        m = np.ascontiguousarray(M.T.astype(np.float32).reshape(-1))     # column-major
+        w.node(mesh, matrix=m)
+        t, r, s = (C.c_float * 3)(), (C.c_float * 4)(), (C.c_float * 3)()
+        ref_shim.ref_decompose(m.ctypes.data_as(C.POINTER(C.c_float)), t, r, s)
+        ref.add_node(p, translation=tuple(t), rotation=tuple(r), scale=tuple(s))
+    ref.finalize()
+    same_scene(Scene.from_glb(w.glb()), ref)
+
+
+@pytest.mark.parametrize("breakage,needle", [
+    ("magic", "magic"), ("truncated", "exceeds"), ("meshopt", "EXT_meshopt_compression"), ("sparse", "sparse"), ("badindex", "index out of range"),
+])
+def test_malformed_assets_are_refused_with_a_reason(breakage, needle):
+    pos, idx = S.grid_mesh(3, 3, lambda u, v: (u, v, 0 * u))
+    w = GlbWriter()
+    if breakage == "badindex":
+        idx = idx.copy(); idx[4] = 1000
+    w.node(w.mesh([{"position": w.positions(pos), "indices": w.indices(idx.astype(np.uint16))}]))
+    if breakage == "meshopt":
+        w.doc["bufferViews"][0]["extensions"] = {"EXT_meshopt_compression": {"buffer": 0, "byteLength": 10, "byteStride": 12, "count": 1, "mode": "ATTRIBUTES"}}
+    if breakage == "sparse":
+        w.doc["accessors"][0]["sparse"] = {"count": 1}
+    data = bytearray(w.glb())
+    if breakage == "magic":
+        data[0] = 0
+    if breakage == "truncated":
+        data = data[:len(data) - 40]
+    with pytest.raises(ValueError) as e:
+        Scene.from_glb(bytes(data))
+    assert needle in str(e.value)
