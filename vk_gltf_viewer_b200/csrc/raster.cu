@@ -623,7 +623,7 @@ __device__ __forceinline__ void drain_grid_barrier(uint32_t* counter) {
 __global__ void __launch_bounds__(kDrainThreads, VKV_DRAIN_MINB) raster_big_kernel(const RasterParams p) {
 	__shared__ Tri sTri[kDrainThreads / 32];
 	__shared__ Tri sSub[kDrainThreads / 32][8];
-#ifdef VKV_DRAIN_BATCHED
+#ifndef VKV_DRAIN_UNBATCHED
 	__shared__ Tri sTriB[kDrainThreads / 32][32];
 #endif
 	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -679,7 +679,7 @@ __global__ void __launch_bounds__(kDrainThreads, VKV_DRAIN_MINB) raster_big_kern
 	if (nRec) {
 		const BigTri* last = p.big + (nRec - 1);
 		const uint32_t nTiles = last->tileBase + last->tilesX * last->tilesY;
-#ifdef VKV_DRAIN_BATCHED
+#ifndef VKV_DRAIN_UNBATCHED
 		// A warp claims up to 32 work items with ONE atomic; every lane finds the record of its own item (32 binary searches side by
 		// side) and stages the triangle in shared memory; then the warp scans the items one after the other with nothing but the
 		// visibility atomics on the memory path.  A scene full of medium triangles (one item each) is bound by exactly these
