@@ -97,6 +97,11 @@ int vkv_frame(vkv_ctx*, const vkv_VisbufferPushConstants* pc, uint32_t flags, vk
 /* Side buffer of the optional cone cull (VKV_FRAME_CONE_CULL): device address of a table with one entry per primitive — the address
  * of that primitive's vkv_MeshletCone[meshletCount] (vkv_abi.h; vkvh_scene_upload_cones builds both).  0 removes it. */
 int vkv_set_cone_table(vkv_ctx*, uint64_t table_dev_addr);
+/* KHR_mesh_quantization positions dequantised in registers (extension): device address of a vkv_QuantizedPositions table
+ * with one entry per primitive (vkv_abi.h; vkvh_scene_upload_quantized builds it).  The rasteriser then reads 8 bytes per vertex —
+ * the accessor's own int16 data — instead of the expanded 24-byte Vertex record, and converts exactly as fastgltf does on the
+ * host: the image is bit-identical.  Culling is unaffected (it reads meshlet bounds only).  0 removes the table. */
+int vkv_set_quantized_positions(vkv_ctx*, uint64_t table_dev_addr);
 /* individually callable stages (per-stage timing / parity).  pass: 0 = A (reference), 1 = B (two-pass extension) */
 int vkv_clear(vkv_ctx*);
 int vkv_cull(vkv_ctx*, const vkv_VisbufferPushConstants* pc, int pass, uint32_t flags, uint32_t* n_visible);

@@ -150,6 +150,19 @@ typedef struct vkv_MeshletCone {
 } vkv_MeshletCone;
 VKV_STATIC_ASSERT(sizeof(vkv_MeshletCone) == 32, "MeshletCone");
 
+/* ---- extension (not a reference struct): KHR_mesh_quantization positions kept in their 16-bit form --------------------------------
+ * The reference expands every POSITION accessor to f32 on the host (assets.cpp:310-314, fastgltf convertComponent) and uploads
+ * 24-byte Vertex records of which the geometry path reads 12 bytes.  With this side table (one entry per primitive, indexed by
+ * primitiveIndex; vkv_set_quantized_positions) the rasteriser reads 8 bytes per vertex — int16 x, y, z, 0 — and applies
+ * convertComponent in registers: float(x), or max(float(x) / 32767, -1) when normalized.  Same floats, a third of the bytes.
+ * positions == 0: the primitive has no 16-bit form, its Vertex buffer is read as usual. */
+typedef struct vkv_QuantizedPositions {
+	uint64_t positions;      /* device address of int16[4 * vertexCount] */
+	uint32_t normalized;     /* accessor.normalized */
+	uint32_t reserved;
+} vkv_QuantizedPositions;
+VKV_STATIC_ASSERT(sizeof(vkv_QuantizedPositions) == 16, "QuantizedPositions");
+
 /* visbuffer.h.glsl:58-60 */
 static inline uint32_t vkv_pack_visbuffer(uint32_t drawIndex, uint32_t primitiveId) {
 	return (drawIndex << VKV_TRIANGLE_BITS) | primitiveId;

@@ -129,6 +129,14 @@ int vkvh_scene_upload(vkvh_scene*, vkvh_upload_fn upload, void* user, const vkv_
 int vkvh_scene_host_cones(vkvh_scene*, const uint64_t** table);
 int vkvh_scene_upload_cones(vkvh_scene*, vkvh_upload_fn upload, void* user, uint64_t* table_addr);
 
+/* --- 16-bit positions (extension: the side buffer of the in-register dequantisation, vkv_abi.h vkv_QuantizedPositions) ------
+ * Primitives added through vkvh_scene_add_primitive_i16 (or loaded from SHORT accessors) keep their 16-bit data; this uploads it
+ * (8 bytes per vertex) and a per-primitive table whose device address goes to vkv_set_quantized_positions. */
+int vkvh_scene_upload_quantized(vkvh_scene*, vkvh_upload_fn upload, void* user, uint64_t* table_addr);
+/* cfg 4 with KHR_mesh_quantization-style geometry: every building's positions snapped to int16 units of 1/512, the node scale
+ * carrying the dequantisation (what gltfpack emits); same layout and triangle counts as vkvh_scene_city */
+vkvh_scene* vkvh_scene_city_quantized(uint32_t nbx, uint32_t nby, uint32_t target_tris_per_building, uint64_t seed);
+
 /* --- camera (camera.cpp:170-193) ----------------------------------------------------------------------------- */
 /* first!=0: all four matrices are set to the new viewProjection (headless start).
  * otherwise prev* <- current, then viewProjection/occlusionViewProjection/frustum are rewritten. */

@@ -57,7 +57,7 @@ EXPORTS = [
     "vkv_build_meshlets", "vkv_assemble_vertices", "vkv_widen_indices",
     "vkv_alloc", "vkv_meshopt_plan_create", "vkv_meshopt_run", "vkv_meshopt_results", "vkv_meshopt_plan_destroy",
     "vkv_set_shard", "vkv_set_shard_interleaved", "vkv_ipc_export", "vkv_ipc_attach", "vkv_ipc_detach", "vkv_merge",
-    "vkv_strip_rows", "vkv_gather_strips", "vkv_hash", "vkv_set_cone_table",
+    "vkv_strip_rows", "vkv_gather_strips", "vkv_hash", "vkv_set_cone_table", "vkv_set_quantized_positions",
 ]
 
 _bound = False
@@ -115,6 +115,7 @@ def _lib():
         L.vkv_gather_strips.argtypes = [vp]
         L.vkv_hash.argtypes = [vp, i, u32, u32, C.POINTER(u64)]
         L.vkv_set_cone_table.argtypes = [vp, u64]
+        L.vkv_set_quantized_positions.argtypes = [vp, u64]
         L.vkv_selftest_division.argtypes = [vp, u64, u32, C.POINTER(u64), C.POINTER(u64)]
         L.vkv_alloc.argtypes = [vp, C.c_size_t, C.POINTER(u64)]
         L.vkv_build_meshlets.argtypes = [vp, vp, u32, u32, u32, u32, vp]
@@ -183,6 +184,18 @@ class Renderer:
         table = scene.upload_cones(cb)
         self._ck(self.L.vkv_set_cone_table(self.h, table))
         return table
+
+    def upload_quantized(self, scene) -> int:
+        """KHR_mesh_quantization positions in their 16-bit form (8 B per vertex) + the per-primitive table: the rasteriser reads these
+        instead of the expanded Vertex records and dequantises in registers (bit-identical image)"""
+        def cb(user, host, nbytes, out):
+            return self.L.vkv_upload(self.h, host, nbytes, out)
+        table = scene.upload_quantized(cb)
+        self._ck(self.L.vkv_set_quantized_positions(self.h, table))
+        return table
+
+    def set_quantized_positions(self, table: int):
+        self._ck(self.L.vkv_set_quantized_positions(self.h, table))
 
     def update_camera(self, pc: abi.PushConstants, camera):
         """Camera::updateCamera's mapped write (camera.cpp:180-193)."""

@@ -41,6 +41,7 @@ struct vkv_ctx {
 	uint32_t* xf_det = nullptr;
 	float4* xf_eye = nullptr;         // camera position in each mesh-node's own space (cone cull)
 	uint64_t cone_table = 0;          // vkv_set_cone_table
+	uint64_t qtable = 0;              // vkv_set_quantized_positions
 	uint32_t xf_cap = 0;
 	uint32_t xf_count = 0;
 	BigTri* big_tris = nullptr;       // large-triangle queue (raster.cu)
@@ -278,6 +279,7 @@ RasterParams make_raster(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, const
 	r.mvp = c->xf_mvp; r.detNeg = c->xf_det;
 	r.big = c->big_tris; r.bigCap = c->big_cap; r.bigCursor = &c->counters->big_cursor; r.bigNext = &c->counters->big_next;
 	r.clip = c->clip_tris; r.clipCap = c->clip_cap; r.clipCount = &c->counters->clip_count; r.clipNext = &c->counters->clip_next;
+	r.qtable = (const vkv_QuantizedPositions*)(uintptr_t)c->qtable;
 	r.overflow = &c->counters->raster_overflow; r.drainBarrier = &c->counters->drain_barrier; r.slowWork = &c->counters->slow_work;
 	return r;
 }
@@ -341,11 +343,23 @@ int enqueue_strip_exchange(vkv_ctx* c, int pass, int* launches) {
 	sp.W = c->W; sp.H = c->H; sp.pyr = c->pyr; sp.exact_levels = c->exact_levels;
 	sp.tilesX = c->tiles_x; sp.tilesY = c->tiles_y; sp.dirtyStride = c->dirty_stride; sp.pass = pass;
 	sp.stats = &c->counters->strip_tiles_pulled;
+	static const bool timing = getenv("VKV_STRIP_TIMING") != nullptr; // diagnosis: events between the four launches, printed by rank 0
+	if (timing) cudaEventRecord(c->events[8], c->stream);
 	CK(launch_xgpu_barrier(c->mp, ++c->epoch, timeout_ns, c->stream));
+	if (timing) cudaEventRecord(c->events[9], c->stream);
 	CK(launch_strip_merge_hiz(sp, c->num_sms, c->stream));
+	if (timing) cudaEventRecord(c->events[10], c->stream);
 	CK(launch_xgpu_barrier(c->mp, ++c->epoch, timeout_ns, c->stream));
+	if (timing) cudaEventRecord(c->events[11], c->stream);
 	HizParams h = make_hiz(c);
 	CK(launch_hiz_tail(h, c->stream));
+	if (timing) {
+		cudaEventRecord(c->events[12], c->stream);
+		cudaEventSynchronize(c->events[12]);
+		float t[4];
+		for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&t[i], c->events[8 + i], c->events[9 + i]);
+		if (c->mp.rank == 0) fprintf(stderr, "[strip pass %d] barrier %.1f us  merge+mips %.1f us  barrier %.1f us  tail %.1f us\n", pass, t[0] * 1e3f, t[1] * 1e3f, t[2] * 1e3f, t[3] * 1e3f);
+	}
 	c->merge_used = true;
 	if (launches) *launches += 3 + (c->exact_levels < c->pyr.levels ? 1 : 0);
 	return VKV_OK;
@@ -511,6 +525,18 @@ int vkv_set_cone_table(vkv_ctx* c, uint64_t table_dev_addr) {
 			return fail(c, VKV_ERR_INVALID, "vkv_set_cone_table: the table does not lie in a vkv_upload allocation");
 	}
 	c->cone_table = table_dev_addr;
+	return VKV_OK;
+}
+
+int vkv_set_quantized_positions(vkv_ctx* c, uint64_t table_dev_addr) {
+	if (!c) return VKV_ERR_INVALID;
+	if (table_dev_addr) {
+		std::lock_guard<std::mutex> lock(c->mtx);
+		auto it = c->allocs.upper_bound(table_dev_addr);
+		if (it == c->allocs.begin() || table_dev_addr >= std::prev(it)->first + std::prev(it)->second)
+			return fail(c, VKV_ERR_INVALID, "vkv_set_quantized_positions: the table does not lie in a vkv_upload allocation");
+	}
+	c->qtable = table_dev_addr;
 	return VKV_OK;
 }
 

@@ -86,6 +86,7 @@ struct RasterParams {
 	uint32_t* drainBarrier;
 	uint32_t* slowWork;
 	unsigned long long neg_zero2; // the fp32 pair (-0.0, -0.0), see common.cuh mul2 (must arrive at run time)
+	const vkv_QuantizedPositions* qtable; // optional: per primitive, its POSITION accessor in 16-bit form (NULL = read the f32 Vertex records)
 	uint8_t* dirty;              // strip mode: one byte per 64x16-pixel tile, set for every tile a drawn triangle's bbox touches (NULL otherwise)
 	uint32_t dirtyTilesX;
 };

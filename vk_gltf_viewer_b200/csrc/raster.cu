@@ -55,10 +55,10 @@ constexpr int kDrainThreads = 256;
 struct alignas(16) MeshletHdr {
 	const uint32_t* vidx;      // primitive.vertexIndexBuffer + meshlet.vertexOffset
 	const uint8_t* tri;        // primitive.primitiveIndexBuffer + meshlet.triangleOffset
-	const vkv_Vertex* verts;   // primitive.vertexBuffer
+	const void* verts;         // primitive.vertexBuffer (vkv_Vertex[]), or the 16-bit positions (int16 x, y, z, 0 per vertex) when bit 18 of counts is set
 	uint32_t drawId;
 	uint32_t tIdx;
-	uint32_t counts;           // vertexCount | triangleCount << 8 | doubleSided << 16 | detNegative << 17
+	uint32_t counts;           // vertexCount | triangleCount << 8 | doubleSided << 16 | detNegative << 17 | quantized << 18 | normalized << 19
 	uint32_t pad[3];
 };
 
@@ -79,6 +79,9 @@ enum { F_NEEDS_CLIP = 64, F_NAN = 128 };
 
 __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
 	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
@@ -387,9 +390,13 @@ __device__ __forceinline__ void meshlet_loop(const RasterParams& p, WarpScratch&
 			MeshletHdr h;
 			h.vidx = (const uint32_t*)b0.x + vertexOffset;
 			h.tri = (const uint8_t*)b0.y + triangleOffset;
-			h.verts = (const vkv_Vertex*)b1.x;
+			h.verts = (const void*)b1.x;
 			h.drawId = drawId; h.tIdx = tIdx;
 			h.counts = vc | (tc << 8) | (ds << 16) | (dn << 17);
+			if (p.qtable) { // KHR_mesh_quantization kept in its 16-bit form: 8 bytes per vertex instead of a 24-byte record
+				const ulonglong2 q = __ldg((const ulonglong2*)(p.qtable + primIdx)); // positions | normalized, reserved
+				if (q.x) { h.verts = (const void*)q.x; h.counts |= (1u << 18) | (((uint32_t)q.y & 1u) << 19); }
+			}
 			ws.hdr[lane] = h;
 		}
 		__syncwarp();
@@ -403,13 +410,20 @@ __device__ __forceinline__ void meshlet_loop(const RasterParams& p, WarpScratch&
 		// positions (vi0/vi1 hold the meshlet's indices), triangle index words and mvp: global -> shared, asynchronously
 		auto issue_copies = [&](const MeshletHdr& h, uint32_t buf) {
 			const uint32_t vc = h.counts & 0xffu, tc = (h.counts >> 8) & 0xffu;
-			if (lane < vc) {
-				const float* q = h.verts[vi0].position;
-				cp_async4(&ws.pos[lane * 2], q); cp_async4(&ws.pos[(32 + lane) * 2], q + 1); cp_async4(&ws.pos[(64 + lane) * 2], q + 2);
-			}
-			if (lane + 32 < vc) {
-				const float* q = h.verts[vi1].position;
-				cp_async4(&ws.pos[lane * 2 + 1], q); cp_async4(&ws.pos[(32 + lane) * 2 + 1], q + 1); cp_async4(&ws.pos[(64 + lane) * 2 + 1], q + 2);
+			if (h.counts & (1u << 18)) { // 16-bit positions: one 8-byte copy per vertex into the same landing zone, vertex v at bytes [8v, 8v + 8)
+				const uint2* qv = (const uint2*)h.verts;
+				if (lane < vc) cp_async8((uint2*)ws.pos + lane, qv + vi0);
+				if (lane + 32 < vc) cp_async8((uint2*)ws.pos + 32 + lane, qv + vi1);
+			} else {
+				const vkv_Vertex* fv = (const vkv_Vertex*)h.verts;
+				if (lane < vc) {
+					const float* q = fv[vi0].position;
+					cp_async4(&ws.pos[lane * 2], q); cp_async4(&ws.pos[(32 + lane) * 2], q + 1); cp_async4(&ws.pos[(64 + lane) * 2], q + 2);
+				}
+				if (lane + 32 < vc) {
+					const float* q = fv[vi1].position;
+					cp_async4(&ws.pos[lane * 2 + 1], q); cp_async4(&ws.pos[(32 + lane) * 2 + 1], q + 1); cp_async4(&ws.pos[(64 + lane) * 2 + 1], q + 2);
+				}
 			}
 			const uint32_t nWords = (tc * 3 + 3) >> 2;
 			if ((((uintptr_t)h.tri) & 3) == 0) {
@@ -450,7 +464,21 @@ __device__ __forceinline__ void meshlet_loop(const RasterParams& p, WarpScratch&
 			// same values as the scalar form, half the issue slots — see common.cuh / cull.cu for the exactness argument).
 			{
 				const f2 nz = p.neg_zero2;
-				const f2 P0 = *(const f2*)&ws.pos[lane * 2], P1 = *(const f2*)&ws.pos[(32 + lane) * 2], P2 = *(const f2*)&ws.pos[(64 + lane) * 2];
+				f2 P0, P1, P2;
+				if (h.counts & (1u << 18)) {
+					// dequantise in registers: fastgltf's convertComponent<float, int16_t> (tools.hpp:266-289) — float(x), or
+					// max(float(x) / 32767, -1) for a normalized accessor — the very floats the host expansion writes into Vertex.position
+					const uint2 a = ((const uint2*)ws.pos)[lane], b = ((const uint2*)ws.pos)[32 + lane];
+					float ax = (float)(short)(a.x & 0xffffu), ay = (float)(short)(a.x >> 16), az = (float)(short)(a.y & 0xffffu);
+					float bx = (float)(short)(b.x & 0xffffu), by = (float)(short)(b.x >> 16), bz = (float)(short)(b.y & 0xffffu);
+					if (h.counts & (1u << 19)) {
+						ax = fmaxf(__fdiv_rn(ax, 32767.0f), -1.0f); ay = fmaxf(__fdiv_rn(ay, 32767.0f), -1.0f); az = fmaxf(__fdiv_rn(az, 32767.0f), -1.0f);
+						bx = fmaxf(__fdiv_rn(bx, 32767.0f), -1.0f); by = fmaxf(__fdiv_rn(by, 32767.0f), -1.0f); bz = fmaxf(__fdiv_rn(bz, 32767.0f), -1.0f);
+					}
+					P0 = pk(ax, bx); P1 = pk(ay, by); P2 = pk(az, bz);
+				} else {
+					P0 = *(const f2*)&ws.pos[lane * 2]; P1 = *(const f2*)&ws.pos[(32 + lane) * 2]; P2 = *(const f2*)&ws.pos[(64 + lane) * 2];
+				}
 				f2 C[4]; // clip x, y, z, w of both vertices: ((c0*x + c1*y) + c2*z) + c3   (:61, w = 1)
 #pragma unroll
 				for (int r = 0; r < 4; ++r) {

@@ -25,61 +25,89 @@ constexpr int kStripThreads = 256;
 
 __device__ __forceinline__ ulonglong2 min2(ulonglong2 a, ulonglong2 b) { return make_ulonglong2(a.x < b.x ? a.x : b.x, a.y < b.y ? a.y : b.y); }
 
-// one warp per tile of this rank's strip
-__global__ void __launch_bounds__(kStripThreads) strip_merge_hiz_kernel(const StripParams p) {
-	const uint32_t lane = threadIdx.x & 31;
+// One block per chunk of kChunk consecutive tiles of this rank's strip, one warp per tile.
+//   0. the block fetches its peers' dirty bytes of the chunk (ONE NVLink round trip per block, not one per tile);
+//   1. merge: for every tile some peer drew into, 8 rows at a time — own rows and the peer's rows in flight together (16-byte loads,
+//      8 per lane per round trip), min, rows that changed stored back;
+//   2. pyramid: the merged tile re-read from the local L2 (it was just written) and reduced in registers (hiz_tile.cuh), every texel
+//      that differs from the local pyramid stored into every rank's pyramid.
+// Keeping 1 and 2 apart (instead of holding the 16 merged rows in registers across both) is what lets three blocks share an SM.
+constexpr uint32_t kChunk = 16;
+
+__global__ void __launch_bounds__(kStripThreads, 3) strip_merge_hiz_kernel(const StripParams p) {
+	__shared__ uint8_t sDirty[kMaxRanks][kChunk];
+	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int N = p.mp.nranks, me = p.mp.rank;
 	const uint32_t row0 = strip_first_row(p.tilesY, me, N), row1 = strip_first_row(p.tilesY, me + 1, N);
 	const uint32_t nTiles = (row1 - row0) * p.tilesX;
+	const uint32_t chunk0 = blockIdx.x * kChunk;
+	{ // 0. dirty bytes: thread (r, j) asks rank r about tile chunk0 + j
+		const uint32_t r = threadIdx.x / kChunk, j = threadIdx.x % kChunk;
+		if ((int)r < N && chunk0 + j < nTiles) {
+			uint8_t d = 0;
+			if ((int)r != me) {
+				const uint32_t t = chunk0 + j, tile = (row0 + t / p.tilesX) * p.tilesX + t % p.tilesX;
+				d = *(volatile const uint8_t*)(p.mp.dirty[r] + (size_t)p.pass * p.dirtyStride + tile);
+			}
+			sDirty[r][j] = d;
+		}
+	}
+	__syncthreads();
 	const HizTileGeo geo = {p.W, p.H, p.exact_levels, {p.pyr.off[0], p.pyr.off[1], p.pyr.off[2], p.pyr.off[3]}, {p.pyr.w[0], p.pyr.w[1], p.pyr.w[2], p.pyr.w[3]}};
 	unsigned long long* const vis = p.mp.vis[me];
 	const float* const localPyr = p.mp.pyr[me];
 	uint32_t pulled = 0, sent = 0; // this warp's tiles pulled over NVLink / this lane's texels stored to peers (statistics)
-	for (uint32_t t = blockIdx.x * (kStripThreads / 32) + (threadIdx.x >> 5); t < nTiles; t += gridDim.x * (kStripThreads / 32)) {
+	for (uint32_t j = warp; j < kChunk && chunk0 + j < nTiles; j += kStripThreads / 32) {
+		const uint32_t t = chunk0 + j;
 		const uint32_t tx = t % p.tilesX, ty = row0 + t / p.tilesX;
-		const uint32_t tile = ty * p.tilesX + tx;
-		// which peers drew into this tile in this pass?  lane k asks rank k (a byte over NVLink; the owner's own flag is irrelevant)
-		uint32_t dirty = 0;
-		if ((int)lane < N && (int)lane != me) dirty = *(volatile const uint8_t*)(p.mp.dirty[lane] + (size_t)p.pass * p.dirtyStride + tile);
-		uint32_t peers = __ballot_sync(0xffffffffu, dirty != 0);
-
-		ulonglong2 v[kTileH];
-		hiz_tile_load(vis, geo, tx, ty, lane, v);
+		uint32_t peers = 0;
+		for (int r = 0; r < N; ++r) peers |= sDirty[r][j] ? (1u << r) : 0u;
 		pulled += __popc(peers);
-		if (peers) {
-			const uint32_t x0 = tx * kTileW + lane * 2, y0 = ty * kTileH;
-			const bool colIn = x0 < p.W;
-			bool changed = false;
-			while (peers) {
-				const int r = __ffs(peers) - 1;
-				peers &= peers - 1;
-				const unsigned long long* pv = p.mp.vis[r];
+		const uint32_t x0 = tx * kTileW + lane * 2, y0 = ty * kTileH;
+		const bool colIn = x0 < p.W;
+		// 1. merge
+		if (peers && colIn) {
+#pragma unroll 1
+			for (int half = 0; half < 2; ++half) {
+				ulonglong2 acc[8]; // the owner's rows, then the running minimum
 #pragma unroll
-				for (int half = 0; half < 2; ++half) { // 8 rows = 8 independent 16-byte peer loads in flight per lane
+				for (int k = 0; k < 8; ++k) {
+					const uint32_t y = y0 + half * 8 + k;
+					acc[k] = make_ulonglong2(~0ull, ~0ull);
+					if (y < p.H) acc[k] = __ldcg((const ulonglong2*)(vis + (size_t)y * p.W + x0));
+				}
+				uint32_t changed = 0; // bit k: row k took a peer's key
+				for (uint32_t m = peers; m; m &= m - 1) {
+					const unsigned long long* pv = p.mp.vis[__ffs(m) - 1];
 					ulonglong2 q[8];
 #pragma unroll
 					for (int k = 0; k < 8; ++k) {
-						const int row = half * 8 + k;
+						const uint32_t y = y0 + half * 8 + k;
 						q[k] = make_ulonglong2(~0ull, ~0ull);
-						if (colIn && y0 + row < p.H) q[k] = __ldcg((const ulonglong2*)(pv + (size_t)(y0 + row) * p.W + x0));
+						if (y < p.H) q[k] = __ldcg((const ulonglong2*)(pv + (size_t)y * p.W + x0));
 					}
 #pragma unroll
 					for (int k = 0; k < 8; ++k) {
-						const int row = half * 8 + k;
-						const ulonglong2 m = min2(v[row], q[k]);
-						changed |= (m.x != v[row].x) | (m.y != v[row].y);
-						v[row] = m;
+						if (q[k].x < acc[k].x) { acc[k].x = q[k].x; changed |= 1u << k; }
+						if (q[k].y < acc[k].y) { acc[k].y = q[k].y; changed |= 1u << k; }
 					}
 				}
-			}
-			if (__any_sync(0xffffffffu, changed)) { // the merged rows become the owner's visbuffer
 #pragma unroll
-				for (int row = 0; row < kTileH; ++row)
-					if (colIn && y0 + row < p.H) *(ulonglong2*)(vis + (size_t)(y0 + row) * p.W + x0) = v[row];
+				for (int k = 0; k < 8; ++k)
+					if (changed & (1u << k)) __stcg((ulonglong2*)(vis + (size_t)(y0 + half * 8 + k) * p.W + x0), acc[k]);
 			}
 		}
-		// exact mips of the merged tile -> every rank's pyramid, changed texels only (all pyramids are identical before this frame's
+		__syncwarp();
+		// 2. exact mips of the merged tile -> every rank's pyramid, changed texels only (all pyramids are identical before this frame's
 		// stores, so the local copy tells whether a texel changes anywhere)
+		ulonglong2 v[kTileH];
+		{
+#pragma unroll
+			for (int r = 0; r < kTileH; ++r) {
+				v[r] = make_ulonglong2(0ull, 0ull);
+				if (colIn && y0 + r < p.H) v[r] = __ldcg((const ulonglong2*)(vis + (size_t)(y0 + r) * p.W + x0)); // L2: this warp may just have written it
+			}
+		}
 		hiz_tile_reduce(v, geo, tx, ty, lane, [&](uint32_t idx, float m) {
 			if (__float_as_uint(__ldcg(localPyr + idx)) != __float_as_uint(m)) {
 				for (int r = 0; r < N; ++r) __stcg(p.mp.pyr[r] + idx, m);
@@ -131,9 +159,9 @@ cudaError_t launch_strip_merge_hiz(const StripParams& p, int num_sms, cudaStream
 	const uint32_t rows = strip_first_row(p.tilesY, p.mp.rank + 1, p.mp.nranks) - strip_first_row(p.tilesY, p.mp.rank, p.mp.nranks);
 	const uint32_t tiles = rows * p.tilesX;
 	if (tiles == 0) return cudaSuccess;
-	uint32_t grid = (tiles + kStripThreads / 32 - 1) / (kStripThreads / 32);
-	if (grid > (uint32_t)num_sms * 8) grid = (uint32_t)num_sms * 8;
-	strip_merge_hiz_kernel<<<grid, kStripThreads, 0, stream>>>(p);
+	static_assert(kChunk * kMaxRanks <= kStripThreads, "one thread per (rank, tile of the chunk) in the flag fetch");
+	(void)num_sms;
+	strip_merge_hiz_kernel<<<(tiles + kChunk - 1) / kChunk, kStripThreads, 0, stream>>>(p);
 	return cudaGetLastError();
 }
 

@@ -342,6 +342,11 @@ vkvh_scene* vkvh_scene_load_glb(const void* data, size_t bytes, char* err, size_
 						pd.header.aabbCenter[k] = (mn[k] + mx[k]) / 2.f;
 						pd.header.aabbExtents[k] = mx[k] - pd.header.aabbCenter[k];
 					}
+					if (pos.ctype == 5122) { // SHORT positions: keep the 16-bit form for the in-register dequantisation (vkv_set_quantized_positions)
+						pd.qpos.assign(pos.count * 4, 0);
+						for (size_t i = 0; i < pos.count; ++i) std::memcpy(&pd.qpos[i * 4], pos.view.data + pos.offset + i * stride, 6);
+						pd.qnormalized = pos.normalized;
+					}
 					meshPrims.back().push_back(add_built_primitive(s, std::move(pd)));
 				}
 			}

@@ -251,7 +251,12 @@ vkvh_scene* vkvh_scene_lattice(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t q
 // ------------------------------------------------------------------------------------------------------------
 // cfg 4: city of nbx x nby UNIQUE buildings (no instancing) + tessellated ground.
 // ------------------------------------------------------------------------------------------------------------
-vkvh_scene* vkvh_scene_city(uint32_t nbx, uint32_t nby, uint32_t target, uint64_t seed) {
+constexpr float kBuildingQuant = 512.0f, kGroundQuant = 64.0f; // int16 units per scene unit (buildings reach 40, the ground 300)
+static vkvh_scene* city_impl(uint32_t nbx, uint32_t nby, uint32_t target, uint64_t seed, bool quantized);
+vkvh_scene* vkvh_scene_city(uint32_t nbx, uint32_t nby, uint32_t target, uint64_t seed) { return city_impl(nbx, nby, target, seed, false); }
+vkvh_scene* vkvh_scene_city_quantized(uint32_t nbx, uint32_t nby, uint32_t target, uint64_t seed) { return city_impl(nbx, nby, target, seed, true); }
+
+static vkvh_scene* city_impl(uint32_t nbx, uint32_t nby, uint32_t target, uint64_t seed, bool quantized) {
 	vkvh_scene* s = vkvh_scene_new();
 	SplitMix64 rng(seed);
 	// facade n x m quads on 4 sides + n x n roof: 8nm + 2n^2 ~= target, with m ~= 2.25 n
@@ -300,7 +305,24 @@ vkvh_scene* vkvh_scene_city(uint32_t nbx, uint32_t nby, uint32_t target, uint64_
 		auto worker = [&]() {
 			for (size_t i; (i = next.fetch_add(1)) < meshes.size();) {
 				const Mesh& m = meshes[i];
-				ok[i] = vkvh::build_primitive(built[i], vkvh::vertices_from_positions(m.pos.data(), (uint32_t)(m.pos.size() / 3)), m.idx.data(), (uint32_t)m.idx.size(), 0) ? 1 : 0;
+				const uint32_t nv = (uint32_t)(m.pos.size() / 3);
+				if (!quantized) {
+					ok[i] = vkvh::build_primitive(built[i], vkvh::vertices_from_positions(m.pos.data(), nv), m.idx.data(), (uint32_t)m.idx.size(), 0) ? 1 : 0;
+					continue;
+				}
+				// KHR_mesh_quantization as gltfpack writes it: SHORT positions in units of 1 / qscale, the node scale undoes it
+				const float qs = i < places.size() ? kBuildingQuant : kGroundQuant;
+				std::vector<int16_t> q((size_t)nv * 4, 0);
+				std::vector<float> fq(m.pos.size());
+				for (uint32_t v = 0; v < nv; ++v)
+					for (int k = 0; k < 3; ++k) {
+						const long r = std::lrintf(m.pos[v * 3 + k] * qs);
+						q[v * 4 + k] = (int16_t)std::max(-32767L, std::min(32767L, r));
+						fq[v * 3 + k] = (float)q[v * 4 + k]; // convertComponent<float, int16_t>, not normalized
+					}
+				ok[i] = vkvh::build_primitive(built[i], vkvh::vertices_from_positions(fq.data(), nv), m.idx.data(), (uint32_t)m.idx.size(), 0) ? 1 : 0;
+				built[i].qpos = std::move(q);
+				built[i].qnormalized = false;
 			}
 		};
 		const unsigned nt = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
@@ -312,8 +334,10 @@ vkvh_scene* vkvh_scene_city(uint32_t nbx, uint32_t nby, uint32_t target, uint64_
 	for (size_t i = 0; i < meshes.size(); ++i) {
 		if (!ok[i]) { vkvh_scene_free(s); return nullptr; }
 		const int32_t prim = vkvh::add_built_primitive(s, std::move(built[i]));
-		if (i < places.size()) vkvh_scene_add_node_trs(s, -1, prim, places[i].t, places[i].r, nullptr);
-		else vkvh_scene_add_node_trs(s, -1, prim, nullptr, nullptr, nullptr);
+		const float inv = 1.0f / (i < places.size() ? kBuildingQuant : kGroundQuant);
+		const float sc[3] = {inv, inv, inv};
+		if (i < places.size()) vkvh_scene_add_node_trs(s, -1, prim, places[i].t, places[i].r, quantized ? sc : nullptr);
+		else vkvh_scene_add_node_trs(s, -1, prim, nullptr, nullptr, quantized ? sc : nullptr);
 	}
 	vkvh_scene_finalize(s);
 	s->kind = 4;

@@ -173,7 +173,30 @@ int32_t vkvh_scene_add_primitive_i16(vkvh_scene* s, const int16_t* positions, ui
 		}
 		v[i].color[0] = v[i].color[1] = v[i].color[2] = v[i].color[3] = 255;
 	}
-	return add_primitive_vertices(s, std::move(v), indices, index_count, material_index);
+	const int32_t idx = add_primitive_vertices(s, std::move(v), indices, index_count, material_index);
+	if (idx >= 0) { // keep the accessor's own 16-bit data: the rasteriser can read it instead of the expanded 24-byte Vertex records
+		auto& pd = s->primitives[idx];
+		pd.qpos.resize((size_t)vertex_count * 4);
+		for (uint32_t i = 0; i < vertex_count; ++i) {
+			pd.qpos[i * 4 + 0] = positions[i * 3 + 0]; pd.qpos[i * 4 + 1] = positions[i * 3 + 1]; pd.qpos[i * 4 + 2] = positions[i * 3 + 2]; pd.qpos[i * 4 + 3] = 0;
+		}
+		pd.qnormalized = normalized != 0;
+	}
+	return idx;
+}
+
+int vkvh_scene_upload_quantized(vkvh_scene* s, vkvh_upload_fn upload, void* user, uint64_t* table_addr) {
+	if (!s || !upload || !table_addr) return -1;
+	std::vector<vkv_QuantizedPositions> table(s->primitives.size());
+	for (size_t i = 0; i < s->primitives.size(); ++i) {
+		const auto& p = s->primitives[i];
+		table[i] = vkv_QuantizedPositions{0, 0, 0};
+		if (p.qpos.empty()) continue;
+		int rc = upload(user, p.qpos.data(), p.qpos.size() * 2, &table[i].positions);
+		if (rc) return rc;
+		table[i].normalized = p.qnormalized ? 1u : 0u;
+	}
+	return upload(user, table.data(), table.size() * sizeof(vkv_QuantizedPositions), table_addr);
 }
 
 int32_t vkvh_scene_add_node_trs(vkvh_scene* s, int32_t parent, int32_t primitive, const float t[3], const float r[4], const float sc[3]) {

@@ -16,6 +16,8 @@ struct PrimitiveData {
 	std::vector<uint32_t> meshletVertices;   // Primitive.vertexIndexBuffer
 	std::vector<uint8_t> meshletTriangles;   // Primitive.primitiveIndexBuffer
 	std::vector<vkv_Meshlet> meshlets;       // Primitive.meshletBuffer
+	std::vector<int16_t> qpos;               // extension: the accessor's original SHORT positions, 4 per vertex (x, y, z, 0), when the asset
+	bool qnormalized = false;                // is KHR_mesh_quantization'd — the side buffer of the in-register dequantisation (vkv_set_quantized_positions)
 	std::vector<vkv_MeshletCone> cones;      // extension: normal cone per meshlet (meshopt_computeMeshletBounds), side buffer of the cone cull
 	vkv_Primitive header{};                  // addresses filled per address space
 	uint64_t triangles = 0;

@@ -72,6 +72,9 @@ def _lib():
         L.vkvh_frustum_from_vp.argtypes = [C.POINTER(C.c_float), C.c_void_p]
         L.vkvh_set_meshlet_builder.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.vkvh_select_builder.argtypes = [C.c_int]
+        L.vkvh_scene_upload_quantized.argtypes = [C.c_void_p, UPLOAD_FN, C.c_void_p, C.POINTER(C.c_uint64)]
+        L.vkvh_scene_city_quantized.restype = C.c_void_p
+        L.vkvh_scene_city_quantized.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64]
         L.vkvh_scene_load_glb.restype = C.c_void_p
         L.vkvh_scene_load_glb.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]
         L.vkvh_scene_add_node_mesh.restype = C.c_int32
@@ -183,6 +186,18 @@ class Scene:
         if n < 0:
             raise ValueError("invalid node")
         return n
+
+    @classmethod
+    def city_quantized(cls, nbx=50, nby=40, tris_per_building=10000, seed=0x5EED0004):
+        """cfg 4 with KHR_mesh_quantization-style int16 positions (node scale carries the dequantisation)"""
+        return cls(_lib().vkvh_scene_city_quantized(nbx, nby, tris_per_building, seed))
+
+    def upload_quantized(self, upload_fn, user=None) -> int:
+        addr = C.c_uint64()
+        cb = UPLOAD_FN(upload_fn)
+        if _lib().vkvh_scene_upload_quantized(self.h, cb, user, C.byref(addr)):
+            raise RuntimeError("quantized-position upload failed")
+        return addr.value
 
     def add_material(self, albedo=(1, 1, 1, 1), double_sided=False) -> int:
         return _lib().vkvh_scene_add_material(self.h, (C.c_float * 4)(*albedo), int(double_sided))
