@@ -34,6 +34,8 @@ CONFIGS = {
     2: ("cfg2: atrium 262,144 tris int16-quantised, 1920x1080", dict(kind="atrium", detail=128), (1920, 1080)),
     3: ("cfg3: 10x10x10 lattice of a 224x224-quad patch (100.35M tris), 3840x2160, two-pass HiZ", dict(kind="lattice", n=(10, 10, 10), quads=224), (3840, 2160)),
     4: ("cfg4: city 50x40 unique buildings x ~10k tris (~20M tris), 1920x1080, 64-view sweep", dict(kind="city", n=(50, 40), tris=10000), (1920, 1080)),
+    # cfg 4 with KHR_mesh_quantization-style int16 positions (--positions f32|i16 then selects what the rasteriser reads)
+    41: ("cfg4q: city 50x40 unique buildings x ~10k tris (~20M tris), int16-quantised, 1920x1080, 64-view sweep", dict(kind="cityq", n=(50, 40), tris=10000), (1920, 1080)),
     5: ("cfg5: 22x22x21 lattice (1.02B tris), 7680x4320", dict(kind="lattice", n=(22, 22, 21), quads=224), (7680, 4320)),
 }
 NVIEWS = 64
@@ -50,6 +52,8 @@ def build_scene(spec):
         return Scene.lattice(*spec["n"], spec["quads"], 0x5EED0003)
     if k == "city":
         return Scene.city(*spec["n"], spec["tris"], 0x5EED0004)
+    if k == "cityq":
+        return Scene.city_quantized(*spec["n"], spec["tris"], 0x5EED0004)
     raise ValueError(k)
 
 
@@ -282,11 +286,15 @@ def main():
     ap.add_argument("--steps", type=int, default=None, help="timed steps (default: 200 frames on the GPU arm, 20 on the CPU reference arm)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", type=int, default=3)
+    ap.add_argument("--config", type=int, default=3, choices=sorted(CONFIGS))
     ap.add_argument("--shard", default="auto", choices=["auto", "views", "range"],
                     help="multi-GPU: independent views per GPU (default, cfg 1-4) or one view sharded by MeshletDraw range (cfg 5)")
     ap.add_argument("--merge", default="strips", choices=["strips", "allreduce"],
                     help="range sharding: screen-strip owners pull dirty tiles + all-gather the pyramid (default) or the round-1 u64 min all-reduce of the whole visbuffer")
+    ap.add_argument("--positions", default="f32", choices=["f32", "i16"],
+                    help="what the rasteriser reads: the expanded f32 Vertex records the reference uploads (default) or, for KHR_mesh_quantization "
+                         "scenes (cfg 2, cfg 41), the accessor's own int16 data dequantised in registers (extension, bit-identical image)")
+    ap.add_argument("--cone-cull", action="store_true", help="enable the optional normal-cone backface cull (extension, identical image)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-range-leg", action="store_true", help="multi-GPU default run: skip the cfg-5 range-sharded leg (`range_sharded` key)")
     ap.add_argument("--one-pass", action="store_true", help="reference one-pass mode instead of the two-pass extension")
@@ -361,6 +369,11 @@ def main():
     cam.look_at(*my_views[0])
     pc = r.upload_scene(scene, cam)
     flags = api.FRAME_ONE_PASS if args.one_pass else api.FRAME_TWO_PASS
+    if args.positions == "i16":
+        r.upload_quantized(scene)
+    if args.cone_cull:
+        r.upload_cones(scene)
+        flags |= api.FRAME_CONE_CULL
     if shard == "range" and world > 1:
         r.set_shard_interleaved(rank, world, 11)  # 2048-draw blocks round-robin: balances the surviving work (a contiguous half does not)
         multigpu.attach_peers(r, dist)
@@ -532,7 +545,7 @@ def main():
             "dtype": "f32+u64", "data": "synthetic",
             "gtris_per_s": cnt.triangles_instanced * fps / 1e9,
             "config": config_dict(label, W, H, cnt, 1 if args.one_pass else 2, builder_note, world, shard),
-            "run": {"stages_from": f"a second pass of {KS} frames with an event after every stage (the frame time above has none inside the frame)",
+            "run": {"positions": args.positions, "cone_cull": bool(args.cone_cull), "stages_from": f"a second pass of {KS} frames with an event after every stage (the frame time above has none inside the frame)",
                     "visible_a_avg": vis_a / K, "occluded_a_avg": occ_a / K, "visible_b_avg": vis_b / K,
                     "avg_vertices_per_meshlet": round(avg_v, 2), "avg_triangles_per_meshlet": round(avg_t, 2),
                     "clear": "fused into the pass-A cull launch (its 8*W*H bytes are counted there)" if clear_fused else "separate launch"},

@@ -428,3 +428,46 @@ def test_cone_cull_needs_its_table():
         r.frame(pc, api.FRAME_CONE_CULL)
     assert e.value.code == -2
     r.close()
+
+
+def _normalized_i16_scene():
+    """KHR_mesh_quantization with a NORMALIZED SHORT accessor (max(x / 32767, -1)), -32768 included, under a scaled node"""
+    rng = np.random.default_rng(4)
+    pos, idx = S.grid_mesh(40, 40, lambda u, v: (u * 2 - 1, v * 2 - 1, 0.3 * np.sin(u * 8) * np.cos(v * 6)))
+    q = np.clip(np.rint(pos * 32767), -32768, 32767).astype(np.int16)
+    q[0] = (-32768, -32768, 0)
+    s = Scene.new()
+    m = s.add_material(double_sided=True)
+    p = s.add_primitive_i16(q, idx, m, normalized=True)
+    for _ in range(5):
+        s.add_node(p, translation=rng.uniform(-2, 2, 3), scale=rng.uniform(0.5, 2.5, 3))
+    return s.finalize()
+
+
+@pytest.mark.parametrize("make", [lambda: Scene.atrium(24), lambda: Scene.city_quantized(6, 5, 2000), _normalized_i16_scene])
+def test_int16_positions_dequantised_in_registers_give_the_same_bits(make):
+    """SURVEY D4 / north_star: with vkv_set_quantized_positions the rasteriser reads the accessor's own int16 data (8 B per vertex) and
+    applies fastgltf's convertComponent in registers; the reference expands on the host (assets.cpp:310-314).  Same floats, hence the
+    same 64-bit visbuffer and pyramid as the f32 Vertex path AND as the oracle, which only ever sees the expanded f32 records."""
+    scene = make()
+    W, H = 960, 540
+    views = [scene.default_view(i, 12) for i in range(3)] if scene.counts().primitives > 1 else [((0, 0, 6), (0, 0, 0)), ((2, 1, 5), (0, 0, 0))]
+    cam = Camera(W, H).look_at(*views[0])
+    r_q, r_f = api.Renderer(W, H), api.Renderer(W, H)
+    pc_q, pc_f = r_q.upload_scene(scene, cam), r_f.upload_scene(scene, cam)
+    assert r_q.upload_quantized(scene) != 0
+    pc_host = scene.host_push_constants(cam)
+    tg = O.Targets(W, H)
+    for k, v in enumerate(views):
+        if k:
+            cam.look_at(*v)
+            r_q.update_camera(pc_q, cam); r_f.update_camera(pc_f, cam)
+        out = O.frame(pc_host, tg, two_pass=True)
+        r_q.frame(pc_q, api.FRAME_TWO_PASS); r_f.frame(pc_f, api.FRAME_TWO_PASS)
+        compare_frame(r_q, tg, out, True, label=f"int16 view {k}")
+        assert np.array_equal(r_q.read_visbuffer64(), r_f.read_visbuffer64())
+    # removing the table restores the f32 path
+    r_q.set_quantized_positions(0)
+    r_q.frame(pc_q, api.FRAME_TWO_PASS); r_f.frame(pc_f, api.FRAME_TWO_PASS)
+    assert np.array_equal(r_q.read_visbuffer64(), r_f.read_visbuffer64())
+    r_q.close(); r_f.close()

@@ -193,6 +193,41 @@ __global__ void __launch_bounds__(1024) hiz_tail_kernel(const HizParams p, uint3
 	hiz_tail(p, first_level, TailSmem(tailSmem));
 }
 
+// Tail whose FIRST level is too large for one block to take in its stride: at 8K the first non-exact mip is 240x135 texels read
+// from a 480x270 source that does not fit the shared-memory stage — 32 texels per thread, each four dependent L2 loads, ~25 us for
+// one block.  Here that level is spread over the grid (the generic sampler rule per texel, the arithmetic of hiz_tail's per-texel
+// branch); the block that finishes last runs the remaining small levels as before.
+__global__ void __launch_bounds__(1024) hiz_tail_spread_kernel(const HizParams p, uint32_t first_level) {
+	extern __shared__ __align__(16) unsigned char tailSmem[];
+	__shared__ uint32_t sLast;
+	const uint32_t k = first_level, dw = p.W >> (k + 1), dh = p.H >> (k + 1);
+	if (dw && dh) {
+		const float* gsrc = p.pyramid + p.pyr.off[k - 1];
+		const uint32_t sw = p.pyr.w[k - 1], sh = p.pyr.h[k - 1], dstride = p.pyr.w[k];
+		float* dst = p.pyramid + p.pyr.off[k];
+		for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < dw * dh; t += gridDim.x * blockDim.x) {
+			const uint32_t x = t % dw, y = t / dw;
+			const float u = ((float)x + 0.5f) / (float)dw, v = ((float)y + 0.5f) / (float)dh; // hiz_reduce.comp.glsl:28
+			int x0, x1, y0, y1;
+			footprint(u, sw, x0, x1);
+			footprint(v, sh, y0, y1);
+			const float a = __ldcg(gsrc + (size_t)y0 * sw + x0), b = __ldcg(gsrc + (size_t)y0 * sw + x1);
+			const float c = __ldcg(gsrc + (size_t)y1 * sw + x0), d = __ldcg(gsrc + (size_t)y1 * sw + x1);
+			dst[(size_t)y * dstride + x] = gmin(gmin(gmin(a, b), c), d);
+		}
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		__threadfence();
+		const uint32_t ticket = atomicAdd(p.done, 1u);
+		sLast = (ticket == gridDim.x - 1) ? 1u : 0u;
+		if (sLast) { *p.done = 0u; __threadfence(); }
+	}
+	__syncthreads();
+	if (!sLast) return;
+	hiz_tail(p, first_level + 1, TailSmem(tailSmem));
+}
+
 // One warp per 64x16 source tile (hiz_tile.cuh).  Valid only for levels whose source is exactly twice the destination in both axes:
 // the sampler footprint is then the aligned 2x2 quad {2p, 2p+1} (u = 2p + 0.5 up to rounding noise << 0.5; checked exhaustively
 // in tests/test_oracle.py).
@@ -208,7 +243,7 @@ __global__ void __launch_bounds__(kHizWarps * 32) hiz_tiled_kernel(const HizPara
 		const uint32_t tx = tile % tilesX, ty = tile / tilesX;
 		ulonglong2 v[kTileH];
 		hiz_tile_load(p.vis, geo, tx, ty, lane, v);
-		hiz_tile_reduce(v, geo, tx, ty, lane, [&](uint32_t idx, float m) { pyramid[idx] = m; });
+		hiz_tile_reduce(v, geo, tx, ty, lane, [&](int, uint32_t idx, float m) { pyramid[idx] = m; });
 	}
 	// Programmatic dependent launch: this block's tiles are written; once every block has said so (or exited) the next kernel in the
 	// stream may START if it was launched with programmatic stream serialization (vkv_frame: the pass-B cull, which does not touch
@@ -232,6 +267,16 @@ __global__ void __launch_bounds__(kHizWarps * 32) hiz_tiled_kernel(const HizPara
 
 } // namespace
 
+// does the first tail level overwhelm a single block?  (its source does not fit the shared-memory stage: 8K and up)
+static bool tail_wants_spreading(const HizParams& p) {
+	const uint32_t k = p.exact_levels;
+	return k >= 1 && k < p.pyr.levels && p.done != nullptr && (size_t)p.pyr.w[k - 1] * p.pyr.h[k - 1] > kTailSrc;
+}
+static void launch_tail(const HizParams& p, cudaStream_t stream) {
+	if (tail_wants_spreading(p)) hiz_tail_spread_kernel<<<32, 1024, kTailSmemBytes, stream>>>(p, p.exact_levels);
+	else hiz_tail_kernel<<<1, 1024, kTailSmemBytes, stream>>>(p, p.exact_levels);
+}
+
 cudaError_t launch_hiz(const HizParams& p, int num_sms, cudaStream_t stream, int* launches) {
 	// function attributes are per device: a process may hold contexts on several GPUs (vkv_create(device = k))
 	static bool attrSet[64] = {};
@@ -241,12 +286,21 @@ cudaError_t launch_hiz(const HizParams& p, int num_sms, cudaStream_t stream, int
 	if (!attr) {
 		cudaFuncSetAttribute(hiz_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTailSmemBytes);
 		cudaFuncSetAttribute(hiz_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTailSmemBytes);
+		cudaFuncSetAttribute(hiz_tail_spread_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTailSmemBytes);
 		attr = true;
 	}
 	if (p.exact_levels >= 1) {
 		const uint32_t tiles = ((p.W + kTileW - 1) / kTileW) * ((p.H + kTileH - 1) / kTileH);
 		uint32_t grid = (tiles + kHizWarps - 1) / kHizWarps;
 		if (grid > (uint32_t)num_sms) grid = (uint32_t)num_sms;
+		if (tail_wants_spreading(p)) { // 8K and up: tiles without the in-kernel tail, then the tail with its first level spread over 32 blocks
+			HizParams q = p;
+			q.done = nullptr;
+			hiz_tiled_kernel<<<grid, kHizWarps * 32, kTailSmemBytes, stream>>>(q);
+			launch_tail(p, stream);
+			if (launches) *launches += 2;
+			return cudaGetLastError();
+		}
 		hiz_tiled_kernel<<<grid, kHizWarps * 32, kTailSmemBytes, stream>>>(p); // its last block runs the tail
 		if (launches) ++*launches;
 		if (!p.done && p.split_tail && p.exact_levels < p.pyr.levels) { // diagnosis: tail as a second launch
@@ -267,9 +321,10 @@ cudaError_t launch_hiz_tail(const HizParams& p, cudaStream_t stream) {
 	cudaGetDevice(&dev);
 	if (!attrSet[dev & 63]) {
 		cudaFuncSetAttribute(hiz_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTailSmemBytes);
+		cudaFuncSetAttribute(hiz_tail_spread_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTailSmemBytes);
 		attrSet[dev & 63] = true;
 	}
 	if (p.exact_levels >= p.pyr.levels) return cudaSuccess;
-	hiz_tail_kernel<<<1, 1024, kTailSmemBytes, stream>>>(p, p.exact_levels);
+	launch_tail(p, stream);
 	return cudaGetLastError();
 }

@@ -5,7 +5,8 @@
 #pragma once
 #include "common.cuh"
 
-constexpr int kTileW = 64, kTileH = 16; // source pixels per warp tile; yields 32x8, 16x4, 8x2, 4x1 texels of mips 0..3
+constexpr int kTileW = 64, kTileH = 16;
+constexpr int kTileSlots = 15;          // mip texels one lane can own in a tile: 8 + 4 + 2 + 1 // source pixels per warp tile; yields 32x8, 16x4, 8x2, 4x1 texels of mips 0..3
 
 struct HizTileGeo {
 	uint32_t W, H, E;          // render resolution, number of exact levels (1..4)
@@ -26,7 +27,8 @@ __device__ __forceinline__ void hiz_tile_load(const unsigned long long* __restri
 	}
 }
 
-// store(index into the pyramid, value) is called for every texel of mips 0..E-1 this lane owns
+// store(slot, index into the pyramid, value) is called for every texel of mips 0..E-1 this lane owns; slot is a compile-time
+// constant after unrolling (mip 0: 0..7, mip 1: 8..11, mip 2: 12..13, mip 3: 14), so a caller may keep per-slot state in registers
 template <class Store>
 __device__ __forceinline__ void hiz_tile_reduce(const ulonglong2 (&v)[kTileH], const HizTileGeo& g, uint32_t tx, uint32_t ty, uint32_t lane, Store&& store) {
 	const uint32_t x0 = tx * kTileW + lane * 2, y0 = ty * kTileH;
@@ -43,7 +45,7 @@ __device__ __forceinline__ void hiz_tile_reduce(const ulonglong2 (&v)[kTileH], c
 		const uint32_t mx = tx * 32 + lane, my0 = ty * 8;
 #pragma unroll
 		for (int r = 0; r < 8; ++r)
-			if (mx < (g.W >> 1) && my0 + r < (g.H >> 1)) store(g.off[0] + (my0 + r) * g.w[0] + mx, m0[r]);
+			if (mx < (g.W >> 1) && my0 + r < (g.H >> 1)) store(r, g.off[0] + (my0 + r) * g.w[0] + mx, m0[r]);
 	}
 	if (g.E < 2) return;
 	float m1[4];
@@ -56,7 +58,7 @@ __device__ __forceinline__ void hiz_tile_reduce(const ulonglong2 (&v)[kTileH], c
 		const uint32_t mx = tx * 16 + (lane >> 1), my0 = ty * 4;
 #pragma unroll
 		for (int r = 0; r < 4; ++r)
-			if (mx < (g.W >> 2) && my0 + r < (g.H >> 2)) store(g.off[1] + (my0 + r) * g.w[1] + mx, m1[r]);
+			if (mx < (g.W >> 2) && my0 + r < (g.H >> 2)) store(8 + r, g.off[1] + (my0 + r) * g.w[1] + mx, m1[r]);
 	}
 	if (g.E < 3) return;
 	float m2[2];
@@ -69,7 +71,7 @@ __device__ __forceinline__ void hiz_tile_reduce(const ulonglong2 (&v)[kTileH], c
 		const uint32_t mx = tx * 8 + (lane >> 2), my0 = ty * 2;
 #pragma unroll
 		for (int r = 0; r < 2; ++r)
-			if (mx < (g.W >> 3) && my0 + r < (g.H >> 3)) store(g.off[2] + (my0 + r) * g.w[2] + mx, m2[r]);
+			if (mx < (g.W >> 3) && my0 + r < (g.H >> 3)) store(12 + r, g.off[2] + (my0 + r) * g.w[2] + mx, m2[r]);
 	}
 	if (g.E < 4) return;
 	{
@@ -77,7 +79,7 @@ __device__ __forceinline__ void hiz_tile_reduce(const ulonglong2 (&v)[kTileH], c
 		const float m3 = gmin(t, __shfl_xor_sync(0xffffffffu, t, 4));
 		if ((lane & 7) == 0) {
 			const uint32_t mx = tx * 4 + (lane >> 3), my = ty;
-			if (mx < (g.W >> 4) && my < (g.H >> 4)) store(g.off[3] + my * g.w[3] + mx, m3);
+			if (mx < (g.W >> 4) && my < (g.H >> 4)) store(14, g.off[3] + my * g.w[3] + mx, m3);
 		}
 	}
 }

@@ -31,10 +31,10 @@ __device__ __forceinline__ ulonglong2 min2(ulonglong2 a, ulonglong2 b) { return 
 //      8 per lane per round trip), min, rows that changed stored back;
 //   2. pyramid: the merged tile re-read from the local L2 (it was just written) and reduced in registers (hiz_tile.cuh), every texel
 //      that differs from the local pyramid stored into every rank's pyramid.
-// Keeping 1 and 2 apart (instead of holding the 16 merged rows in registers across both) is what lets three blocks share an SM.
+// Keeping 1 and 2 apart (instead of holding the 16 merged rows in registers across both) is what lets two blocks (instead of one) share an SM.
 constexpr uint32_t kChunk = 16;
 
-__global__ void __launch_bounds__(kStripThreads, 3) strip_merge_hiz_kernel(const StripParams p) {
+__global__ void __launch_bounds__(kStripThreads, 2) strip_merge_hiz_kernel(const StripParams p) {
 	__shared__ uint8_t sDirty[kMaxRanks][kChunk];
 	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int N = p.mp.nranks, me = p.mp.rank;
@@ -44,12 +44,8 @@ __global__ void __launch_bounds__(kStripThreads, 3) strip_merge_hiz_kernel(const
 	{ // 0. dirty bytes: thread (r, j) asks rank r about tile chunk0 + j
 		const uint32_t r = threadIdx.x / kChunk, j = threadIdx.x % kChunk;
 		if ((int)r < N && chunk0 + j < nTiles) {
-			uint8_t d = 0;
-			if ((int)r != me) {
-				const uint32_t t = chunk0 + j, tile = (row0 + t / p.tilesX) * p.tilesX + t % p.tilesX;
-				d = *(volatile const uint8_t*)(p.mp.dirty[r] + (size_t)p.pass * p.dirtyStride + tile);
-			}
-			sDirty[r][j] = d;
+			const uint32_t t = chunk0 + j, tile = (row0 + t / p.tilesX) * p.tilesX + t % p.tilesX;
+			sDirty[r][j] = *(volatile const uint8_t*)(p.mp.dirty[r] + (size_t)p.pass * p.dirtyStride + tile); // r == me: this rank's own marks (local)
 		}
 	}
 	__syncthreads();
@@ -61,7 +57,10 @@ __global__ void __launch_bounds__(kStripThreads, 3) strip_merge_hiz_kernel(const
 		const uint32_t t = chunk0 + j;
 		const uint32_t tx = t % p.tilesX, ty = row0 + t / p.tilesX;
 		uint32_t peers = 0;
-		for (int r = 0; r < N; ++r) peers |= sDirty[r][j] ? (1u << r) : 0u;
+		for (int r = 0; r < N; ++r) peers |= (r != me && sDirty[r][j]) ? (1u << r) : 0u;
+		// second pass of a frame: a tile neither a peer nor this rank drew into since the first exchange still holds the merged keys
+		// the first exchange built its mips from — nothing to pull, nothing to rebuild
+		if (p.pass == 1 && !peers && !sDirty[me][j]) continue;
 		pulled += __popc(peers);
 		const uint32_t x0 = tx * kTileW + lane * 2, y0 = ty * kTileH;
 		const bool colIn = x0 < p.W;
@@ -108,12 +107,21 @@ __global__ void __launch_bounds__(kStripThreads, 3) strip_merge_hiz_kernel(const
 				if (colIn && y0 + r < p.H) v[r] = __ldcg((const ulonglong2*)(vis + (size_t)(y0 + r) * p.W + x0)); // L2: this warp may just have written it
 			}
 		}
-		hiz_tile_reduce(v, geo, tx, ty, lane, [&](uint32_t idx, float m) {
-			if (__float_as_uint(__ldcg(localPyr + idx)) != __float_as_uint(m)) {
-				for (int r = 0; r < N; ++r) __stcg(p.mp.pyr[r] + idx, m);
+		uint32_t idxOf[kTileSlots];
+		float valOf[kTileSlots];
+		uint32_t have = 0; // bit s: this lane owns a texel in slot s
+		hiz_tile_reduce(v, geo, tx, ty, lane, [&](int slot, uint32_t idx, float m) { idxOf[slot] = idx; valOf[slot] = m; have |= 1u << slot; });
+		// all the old texels first (independent loads, one L2 round trip), then the stores of those that changed: checking and storing
+		// texel by texel would chain 15 round trips, because a store into pyr[me] may alias the next load
+		uint32_t oldOf[kTileSlots];
+#pragma unroll
+		for (int sl = 0; sl < kTileSlots; ++sl) oldOf[sl] = (have >> sl) & 1u ? __float_as_uint(__ldcg(localPyr + idxOf[sl])) : 0u;
+#pragma unroll
+		for (int sl = 0; sl < kTileSlots; ++sl)
+			if (((have >> sl) & 1u) && oldOf[sl] != __float_as_uint(valOf[sl])) {
+				for (int r = 0; r < N; ++r) __stcg(p.mp.pyr[r] + idxOf[sl], valOf[sl]);
 				sent += (uint32_t)(N - 1);
 			}
-		});
 	}
 	if (p.stats) {
 		for (int o = 16; o; o >>= 1) sent += __shfl_xor_sync(0xffffffffu, sent, o);
