@@ -343,25 +343,26 @@ int enqueue_strip_exchange(vkv_ctx* c, int pass, int* launches) {
 	sp.W = c->W; sp.H = c->H; sp.pyr = c->pyr; sp.exact_levels = c->exact_levels;
 	sp.tilesX = c->tiles_x; sp.tilesY = c->tiles_y; sp.dirtyStride = c->dirty_stride; sp.pass = pass;
 	sp.stats = &c->counters->strip_tiles_pulled;
-	static const bool timing = getenv("VKV_STRIP_TIMING") != nullptr; // diagnosis: events between the four launches, printed by rank 0
+	// two launches per exchange: the cross-GPU barriers ride inside them (strips.cu, hiz.cu)
+	sp.epoch_in = ++c->epoch; sp.epoch_out = ++c->epoch;
+	sp.done = &c->counters->strip_done; sp.timeout_ns = timeout_ns;
+	static const bool timing = getenv("VKV_STRIP_TIMING") != nullptr; // diagnosis: events between the launches, printed by rank 0
 	if (timing) cudaEventRecord(c->events[8], c->stream);
-	CK(launch_xgpu_barrier(c->mp, ++c->epoch, timeout_ns, c->stream));
-	if (timing) cudaEventRecord(c->events[9], c->stream);
 	CK(launch_strip_merge_hiz(sp, c->num_sms, c->stream));
-	if (timing) cudaEventRecord(c->events[10], c->stream);
-	CK(launch_xgpu_barrier(c->mp, ++c->epoch, timeout_ns, c->stream));
-	if (timing) cudaEventRecord(c->events[11], c->stream);
+	if (timing) cudaEventRecord(c->events[9], c->stream);
 	HizParams h = make_hiz(c);
-	CK(launch_hiz_tail(h, c->stream));
+	h.wait_flags = c->sync_flags; h.wait_epoch = sp.epoch_out; h.wait_ranks = c->mp.nranks; h.wait_error = c->sync_flags + kMaxRanks; h.wait_timeout_ns = timeout_ns;
+	if (c->exact_levels < c->pyr.levels) CK(launch_hiz_tail(h, c->stream));
+	else CK(launch_xgpu_barrier(c->mp, sp.epoch_out, timeout_ns, c->stream)); // no small mips (tiny targets): the out-barrier needs a launch of its own
 	if (timing) {
-		cudaEventRecord(c->events[12], c->stream);
-		cudaEventSynchronize(c->events[12]);
-		float t[4];
-		for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&t[i], c->events[8 + i], c->events[9 + i]);
-		if (c->mp.rank == 0) fprintf(stderr, "[strip pass %d] barrier %.1f us  merge+mips %.1f us  barrier %.1f us  tail %.1f us\n", pass, t[0] * 1e3f, t[1] * 1e3f, t[2] * 1e3f, t[3] * 1e3f);
+		cudaEventRecord(c->events[10], c->stream);
+		cudaEventSynchronize(c->events[10]);
+		float t[2];
+		for (int i = 0; i < 2; ++i) cudaEventElapsedTime(&t[i], c->events[8 + i], c->events[9 + i]);
+		if (c->mp.rank == 0) fprintf(stderr, "[strip pass %d] barrier + merge + mips %.1f us   barrier + tail %.1f us\n", pass, t[0] * 1e3f, t[1] * 1e3f);
 	}
 	c->merge_used = true;
-	if (launches) *launches += 3 + (c->exact_levels < c->pyr.levels ? 1 : 0);
+	if (launches) *launches += 2;
 	return VKV_OK;
 }
 

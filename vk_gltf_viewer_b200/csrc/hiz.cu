@@ -7,6 +7,7 @@
 // {i0, i0+1} minus zero-weight texels, CLAMP_TO_EDGE).  One launch per pyramid build.
 #include "kernels.cuh"
 #include "hiz_tile.cuh"
+#include "xgpu.cuh"
 #ifdef VKV_HIZ_DEBUG
 #include <cstdio>
 #define TS(i) do { if (threadIdx.x == 0) dbg_ts[i] = clock64(); } while (0)
@@ -188,8 +189,16 @@ __device__ __forceinline__ void hiz_tail(const HizParams& p, uint32_t first_leve
 }
 
 // tail-only launch: resolutions without any exact level (odd W or H)
+// strip mode: the exact mips this tail reads were stored by ALL ranks' strip kernels — wait for their signals first
+__device__ __forceinline__ void tail_wait_for_peers(const HizParams& p) {
+	if (!p.wait_flags) return;
+	if ((int)threadIdx.x < p.wait_ranks) xgpu_wait(p.wait_flags, threadIdx.x, p.wait_epoch, p.wait_timeout_ns, p.wait_error);
+	__syncthreads();
+}
+
 __global__ void __launch_bounds__(1024) hiz_tail_kernel(const HizParams p, uint32_t first_level) {
 	extern __shared__ __align__(16) unsigned char tailSmem[];
+	tail_wait_for_peers(p);
 	hiz_tail(p, first_level, TailSmem(tailSmem));
 }
 
@@ -200,6 +209,7 @@ __global__ void __launch_bounds__(1024) hiz_tail_kernel(const HizParams p, uint3
 __global__ void __launch_bounds__(1024) hiz_tail_spread_kernel(const HizParams p, uint32_t first_level) {
 	extern __shared__ __align__(16) unsigned char tailSmem[];
 	__shared__ uint32_t sLast;
+	tail_wait_for_peers(p);
 	const uint32_t k = first_level, dw = p.W >> (k + 1), dh = p.H >> (k + 1);
 	if (dw && dh) {
 		const float* gsrc = p.pyramid + p.pyr.off[k - 1];

@@ -99,6 +99,12 @@ struct HizParams {
 	uint32_t exact_levels;       // leading mips whose source is exactly 2x (handled by the tiled kernel), <= 4
 	uint32_t* done;              // FrameCounters::hiz_done (zero between launches)
 	int split_tail;              // diagnosis only: run the small mips as a second launch
+	// strip mode: the small-mip tail first waits for every rank's "my strip's mips are stored everywhere" signal (xgpu.cuh)
+	const uint32_t* wait_flags;  // this rank's flag slots (NULL = no wait)
+	uint32_t wait_epoch;
+	int wait_ranks;
+	uint32_t* wait_error;
+	unsigned long long wait_timeout_ns;
 };
 
 cudaError_t launch_cull(const CullParams& p, int num_sms, cudaStream_t stream, bool after_hiz = false); // after_hiz: programmatic dependent launch
@@ -135,6 +141,11 @@ struct StripParams {
 	uint32_t dirtyStride;                 // bytes per pass in the dirty array (tilesX * tilesY rounded up to 16)
 	int pass;                             // which dirty set the peers' contributions are read from
 	uint32_t* stats;                      // [0] += tiles pulled from peers, [1] += pyramid texels stored to peers (may be NULL)
+	// the two cross-GPU barriers of an exchange ride inside the kernels instead of being launches of their own:
+	uint32_t epoch_in;                    // every block waits until all ranks have signalled this epoch (their raster pass is complete)
+	uint32_t epoch_out;                   // signalled by the block that finishes last (this rank's strip is merged, its mips stored everywhere)
+	uint32_t* done;                       // last-block ticket (zero between launches)
+	unsigned long long timeout_ns;
 };
 __host__ __device__ inline uint32_t strip_first_row(uint32_t tilesY, int rank, int nranks) { return (uint32_t)((unsigned long long)tilesY * (unsigned)rank / (unsigned)nranks); }
 cudaError_t launch_strip_merge_hiz(const StripParams& p, int num_sms, cudaStream_t stream);

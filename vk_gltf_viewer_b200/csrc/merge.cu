@@ -13,34 +13,17 @@
 // A key is (~depthBits << 32 | id): min == nearest fragment, ties == lowest id, exactly what atomicMin does inside one GPU,
 // so the merged image is bit-identical to the single-GPU one.
 #include "kernels.cuh"
+#include "xgpu.cuh"
 
 namespace {
 
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-	unsigned long long t;
-	asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-	return t;
-}
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-	uint32_t v;
-	asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-	return v;
-}
-
 // Thread t signals rank t (writes `epoch` into slot [rank] of rank t's flag array) and waits for rank t's signal in the
-// local array.  Epochs only grow, and a peer can be at most one barrier ahead, so ">= epoch" is the arrival test.
+// local array (xgpu.cuh).
 __global__ void xgpu_barrier_kernel(const MergeParams p, uint32_t epoch, unsigned long long timeout_ns) {
 	const int t = threadIdx.x;
 	if (t >= p.nranks) return;
-	__threadfence_system();
-	st_release_sys(p.flags[t] + p.rank, epoch);
-	const unsigned long long t0 = globaltimer_ns();
-	const uint32_t* slot = p.flags[p.rank] + t;
-	while ((int32_t)(ld_acquire_sys(slot) - epoch) < 0) {
-		if (globaltimer_ns() - t0 > timeout_ns) { *p.error = 1u; break; } // a peer never arrived: report instead of hanging the GPU
-		__nanosleep(200);
-	}
+	xgpu_signal(p.flags, p.rank, t, epoch);
+	xgpu_wait(p.flags[p.rank], t, epoch, timeout_ns, p.error);
 }
 
 __device__ __forceinline__ ulonglong2 min2(ulonglong2 a, ulonglong2 b) {

@@ -18,6 +18,7 @@
 // The reference is single-GPU: there is no reference call site for this file.
 #include "hiz_tile.cuh"
 #include "kernels.cuh"
+#include "xgpu.cuh"
 
 namespace {
 
@@ -41,6 +42,11 @@ __global__ void __launch_bounds__(kStripThreads, 2) strip_merge_hiz_kernel(const
 	const uint32_t row0 = strip_first_row(p.tilesY, me, N), row1 = strip_first_row(p.tilesY, me + 1, N);
 	const uint32_t nTiles = (row1 - row0) * p.tilesX;
 	const uint32_t chunk0 = blockIdx.x * kChunk;
+	// barrier in: this kernel starts when THIS rank's raster pass is complete (stream order); block 0 says so to every rank, and
+	// every block waits until all ranks have said so (polling this rank's own slots)
+	if (blockIdx.x == 0 && (int)threadIdx.x < N) xgpu_signal(p.mp.flags, me, threadIdx.x, p.epoch_in);
+	if ((int)threadIdx.x < N) xgpu_wait(p.mp.flags[me], threadIdx.x, p.epoch_in, p.timeout_ns, p.mp.error);
+	__syncthreads();
 	{ // 0. dirty bytes: thread (r, j) asks rank r about tile chunk0 + j
 		const uint32_t r = threadIdx.x / kChunk, j = threadIdx.x % kChunk;
 		if ((int)r < N && chunk0 + j < nTiles) {
@@ -130,6 +136,18 @@ __global__ void __launch_bounds__(kStripThreads, 2) strip_merge_hiz_kernel(const
 			if (sent) atomicAdd(p.stats + 1, sent);
 		}
 	}
+	// barrier out: the block that finishes last tells every rank that this rank's strip is merged and its mips are stored everywhere
+	// (the small-mip tail that follows on each rank waits for all these signals)
+	__shared__ uint32_t sLast;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		__threadfence_system(); // this block's peer stores before the ticket
+		const uint32_t ticket = atomicAdd(p.done, 1u);
+		sLast = (ticket == gridDim.x - 1) ? 1u : 0u;
+		if (sLast) *p.done = 0u;
+	}
+	__syncthreads();
+	if (sLast && (int)threadIdx.x < N) xgpu_signal(p.mp.flags, me, threadIdx.x, p.epoch_out);
 }
 
 // all-gather of the merged strips: every rank pulls the strips it does not own from their owners (readers that want the whole
