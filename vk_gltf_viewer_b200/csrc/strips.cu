@@ -26,7 +26,7 @@ constexpr int kStripThreads = 256;
 
 __device__ __forceinline__ ulonglong2 min2(ulonglong2 a, ulonglong2 b) { return make_ulonglong2(a.x < b.x ? a.x : b.x, a.y < b.y ? a.y : b.y); }
 
-// One block per chunk of kChunk consecutive tiles of this rank's strip, one warp per tile.
+// Persistent blocks, each taking chunks of kChunk consecutive tiles of this rank's strip, one warp per tile.
 //   0. the block fetches its peers' dirty bytes of the chunk (ONE NVLink round trip per block, not one per tile);
 //   1. merge: for every tile some peer drew into, 8 rows at a time — own rows and the peer's rows in flight together (16-byte loads,
 //      8 per lane per round trip), min, rows that changed stored back;
@@ -41,12 +41,18 @@ __global__ void __launch_bounds__(kStripThreads, 2) strip_merge_hiz_kernel(const
 	const int N = p.mp.nranks, me = p.mp.rank;
 	const uint32_t row0 = strip_first_row(p.tilesY, me, N), row1 = strip_first_row(p.tilesY, me + 1, N);
 	const uint32_t nTiles = (row1 - row0) * p.tilesX;
-	const uint32_t chunk0 = blockIdx.x * kChunk;
 	// barrier in: this kernel starts when THIS rank's raster pass is complete (stream order); block 0 says so to every rank, and
 	// every block waits until all ranks have said so (polling this rank's own slots)
 	if (blockIdx.x == 0 && (int)threadIdx.x < N) xgpu_signal(p.mp.flags, me, threadIdx.x, p.epoch_in);
 	if ((int)threadIdx.x < N) xgpu_wait(p.mp.flags[me], threadIdx.x, p.epoch_in, p.timeout_ns, p.mp.error);
 	__syncthreads();
+	const HizTileGeo geo = {p.W, p.H, p.exact_levels, {p.pyr.off[0], p.pyr.off[1], p.pyr.off[2], p.pyr.off[3]}, {p.pyr.w[0], p.pyr.w[1], p.pyr.w[2], p.pyr.w[3]}};
+	unsigned long long* const vis = p.mp.vis[me];
+	const float* const localPyr = p.mp.pyr[me];
+	uint32_t pulled = 0, sent = 0; // this warp's tiles pulled over NVLink / this lane's texels stored to peers (statistics)
+	// persistent blocks: the system-scope fence and flag traffic of the two barriers are paid once per block, not once per chunk
+	for (uint32_t chunk0 = blockIdx.x * kChunk; chunk0 < nTiles; chunk0 += gridDim.x * kChunk) {
+	__syncthreads(); // the previous chunk's readers of sDirty are done
 	{ // 0. dirty bytes: thread (r, j) asks rank r about tile chunk0 + j
 		const uint32_t r = threadIdx.x / kChunk, j = threadIdx.x % kChunk;
 		if ((int)r < N && chunk0 + j < nTiles) {
@@ -55,10 +61,6 @@ __global__ void __launch_bounds__(kStripThreads, 2) strip_merge_hiz_kernel(const
 		}
 	}
 	__syncthreads();
-	const HizTileGeo geo = {p.W, p.H, p.exact_levels, {p.pyr.off[0], p.pyr.off[1], p.pyr.off[2], p.pyr.off[3]}, {p.pyr.w[0], p.pyr.w[1], p.pyr.w[2], p.pyr.w[3]}};
-	unsigned long long* const vis = p.mp.vis[me];
-	const float* const localPyr = p.mp.pyr[me];
-	uint32_t pulled = 0, sent = 0; // this warp's tiles pulled over NVLink / this lane's texels stored to peers (statistics)
 	for (uint32_t j = warp; j < kChunk && chunk0 + j < nTiles; j += kStripThreads / 32) {
 		const uint32_t t = chunk0 + j;
 		const uint32_t tx = t % p.tilesX, ty = row0 + t / p.tilesX;
@@ -129,6 +131,7 @@ __global__ void __launch_bounds__(kStripThreads, 2) strip_merge_hiz_kernel(const
 				sent += (uint32_t)(N - 1);
 			}
 	}
+	} // chunks
 	if (p.stats) {
 		for (int o = 16; o; o >>= 1) sent += __shfl_xor_sync(0xffffffffu, sent, o);
 		if (lane == 0) {
@@ -186,8 +189,9 @@ cudaError_t launch_strip_merge_hiz(const StripParams& p, int num_sms, cudaStream
 	const uint32_t tiles = rows * p.tilesX;
 	if (tiles == 0) return cudaSuccess;
 	static_assert(kChunk * kMaxRanks <= kStripThreads, "one thread per (rank, tile of the chunk) in the flag fetch");
-	(void)num_sms;
-	strip_merge_hiz_kernel<<<(tiles + kChunk - 1) / kChunk, kStripThreads, 0, stream>>>(p);
+	uint32_t grid = (tiles + kChunk - 1) / kChunk;
+	if (grid > (uint32_t)num_sms * 2) grid = (uint32_t)num_sms * 2; // persistent: two blocks per SM (128 registers)
+	strip_merge_hiz_kernel<<<grid, kStripThreads, 0, stream>>>(p);
 	return cudaGetLastError();
 }
 
