@@ -83,3 +83,31 @@ __device__ __forceinline__ void hiz_tile_reduce(const ulonglong2 (&v)[kTileH], c
 		}
 	}
 }
+
+// The pyramid indices of the texels hiz_tile_reduce will hand to `store` for this (tile, lane), without the data: visit(slot, index).
+// Mirrors hiz_tile_reduce's conditions exactly (same slots, same bounds).
+template <class Visit>
+__device__ __forceinline__ void hiz_tile_slots(const HizTileGeo& g, uint32_t tx, uint32_t ty, uint32_t lane, Visit&& visit) {
+	{
+		const uint32_t mx = tx * 32 + lane, my0 = ty * 8;
+#pragma unroll
+		for (int r = 0; r < 8; ++r)
+			if (mx < (g.W >> 1) && my0 + r < (g.H >> 1)) visit(r, g.off[0] + (my0 + r) * g.w[0] + mx);
+	}
+	if (g.E >= 2 && (lane & 1) == 0) {
+		const uint32_t mx = tx * 16 + (lane >> 1), my0 = ty * 4;
+#pragma unroll
+		for (int r = 0; r < 4; ++r)
+			if (mx < (g.W >> 2) && my0 + r < (g.H >> 2)) visit(8 + r, g.off[1] + (my0 + r) * g.w[1] + mx);
+	}
+	if (g.E >= 3 && (lane & 3) == 0) {
+		const uint32_t mx = tx * 8 + (lane >> 2), my0 = ty * 2;
+#pragma unroll
+		for (int r = 0; r < 2; ++r)
+			if (mx < (g.W >> 3) && my0 + r < (g.H >> 3)) visit(12 + r, g.off[2] + (my0 + r) * g.w[2] + mx);
+	}
+	if (g.E >= 4 && (lane & 7) == 0) {
+		const uint32_t mx = tx * 4 + (lane >> 3), my = ty;
+		if (mx < (g.W >> 4) && my < (g.H >> 4)) visit(14, g.off[3] + my * g.w[3] + mx);
+	}
+}

@@ -26,17 +26,18 @@ constexpr int kStripThreads = 256;
 
 __device__ __forceinline__ ulonglong2 min2(ulonglong2 a, ulonglong2 b) { return make_ulonglong2(a.x < b.x ? a.x : b.x, a.y < b.y ? a.y : b.y); }
 
-// Persistent blocks, each taking chunks of kChunk consecutive tiles of this rank's strip, one warp per tile.
-//   0. the block fetches its peers' dirty bytes of the chunk (ONE NVLink round trip per block, not one per tile);
-//   1. merge: for every tile some peer drew into, 8 rows at a time — own rows and the peer's rows in flight together (16-byte loads,
-//      8 per lane per round trip), min, rows that changed stored back;
-//   2. pyramid: the merged tile re-read from the local L2 (it was just written) and reduced in registers (hiz_tile.cuh), every texel
-//      that differs from the local pyramid stored into every rank's pyramid.
-// Keeping 1 and 2 apart (instead of holding the 16 merged rows in registers across both) is what lets two blocks (instead of one) share an SM.
-constexpr uint32_t kChunk = 16;
+// Persistent blocks (two per SM), each owning a contiguous range of the tiles of this rank's strip, one warp per tile.
+//   0. the block fetches, for ALL its tiles at once, which ranks drew into them (one NVLink round trip per block);
+//   1. merge: for every tile some peer drew into, 8 rows at a time — the owner's rows, then each peer's rows (16-byte loads,
+//      8 in flight per lane), min, rows that changed stored back;
+//   2. pyramid: the merged tile's 16 rows AND the 15 pyramid texels this lane may produce are requested together (one round trip),
+//      the tile is reduced in registers (hiz_tile.cuh), and every texel that differs from the local pyramid is stored into
+//      every rank's pyramid.
+// Keeping 1 and 2 apart (instead of holding the 16 merged rows in registers across both) keeps the kernel at two blocks per SM.
+constexpr uint32_t kRound = 512; // tiles whose masks fit the shared-memory table at once
 
 __global__ void __launch_bounds__(kStripThreads, 2) strip_merge_hiz_kernel(const StripParams p) {
-	__shared__ uint8_t sDirty[kMaxRanks][kChunk];
+	__shared__ uint32_t sMask[kRound]; // bit r: rank r drew into the tile in this pass (bit `me`: this rank did)
 	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int N = p.mp.nranks, me = p.mp.rank;
 	const uint32_t row0 = strip_first_row(p.tilesY, me, N), row1 = strip_first_row(p.tilesY, me + 1, N);
@@ -50,88 +51,85 @@ __global__ void __launch_bounds__(kStripThreads, 2) strip_merge_hiz_kernel(const
 	unsigned long long* const vis = p.mp.vis[me];
 	const float* const localPyr = p.mp.pyr[me];
 	uint32_t pulled = 0, sent = 0; // this warp's tiles pulled over NVLink / this lane's texels stored to peers (statistics)
-	// persistent blocks: the system-scope fence and flag traffic of the two barriers are paid once per block, not once per chunk
-	for (uint32_t chunk0 = blockIdx.x * kChunk; chunk0 < nTiles; chunk0 += gridDim.x * kChunk) {
-	__syncthreads(); // the previous chunk's readers of sDirty are done
-	{ // 0. dirty bytes: thread (r, j) asks rank r about tile chunk0 + j
-		const uint32_t r = threadIdx.x / kChunk, j = threadIdx.x % kChunk;
-		if ((int)r < N && chunk0 + j < nTiles) {
-			const uint32_t t = chunk0 + j, tile = (row0 + t / p.tilesX) * p.tilesX + t % p.tilesX;
-			sDirty[r][j] = *(volatile const uint8_t*)(p.mp.dirty[r] + (size_t)p.pass * p.dirtyStride + tile); // r == me: this rank's own marks (local)
+	const uint32_t perBlock = (nTiles + gridDim.x - 1) / gridDim.x;
+	const uint32_t first = blockIdx.x * perBlock, last = min(nTiles, first + perBlock);
+	for (uint32_t base = first; base < last; base += kRound) {
+		const uint32_t cnt = min(kRound, last - base);
+		__syncthreads(); // the previous round's readers of sMask are done
+		for (uint32_t j = threadIdx.x; j < cnt; j += kStripThreads) sMask[j] = 0u;
+		__syncthreads();
+		// 0. dirty bytes of the whole round: work item (r, j) asks rank r about tile base + j (r == me: this rank's own marks, local)
+		for (uint32_t w = threadIdx.x; w < cnt * (uint32_t)N; w += kStripThreads) {
+			const uint32_t r = w / cnt, j = w % cnt, t = base + j;
+			const uint32_t tile = (row0 + t / p.tilesX) * p.tilesX + t % p.tilesX;
+			if (*(volatile const uint8_t*)(p.mp.dirty[r] + (size_t)p.pass * p.dirtyStride + tile)) atomicOr(&sMask[j], 1u << r);
 		}
-	}
-	__syncthreads();
-	for (uint32_t j = warp; j < kChunk && chunk0 + j < nTiles; j += kStripThreads / 32) {
-		const uint32_t t = chunk0 + j;
-		const uint32_t tx = t % p.tilesX, ty = row0 + t / p.tilesX;
-		uint32_t peers = 0;
-		for (int r = 0; r < N; ++r) peers |= (r != me && sDirty[r][j]) ? (1u << r) : 0u;
-		// second pass of a frame: a tile neither a peer nor this rank drew into since the first exchange still holds the merged keys
-		// the first exchange built its mips from — nothing to pull, nothing to rebuild
-		if (p.pass == 1 && !peers && !sDirty[me][j]) continue;
-		pulled += __popc(peers);
-		const uint32_t x0 = tx * kTileW + lane * 2, y0 = ty * kTileH;
-		const bool colIn = x0 < p.W;
-		// 1. merge
-		if (peers && colIn) {
+		__syncthreads();
+		for (uint32_t j = warp; j < cnt; j += kStripThreads / 32) {
+			const uint32_t t = base + j;
+			const uint32_t tx = t % p.tilesX, ty = row0 + t / p.tilesX;
+			const uint32_t mask = sMask[j], peers = mask & ~(1u << me);
+			// second pass of a frame: a tile neither a peer nor this rank drew into since the first exchange still holds the merged
+			// keys the first exchange built its mips from — nothing to pull, nothing to rebuild
+			if (p.pass == 1 && !mask) continue;
+			pulled += __popc(peers);
+			const uint32_t x0 = tx * kTileW + lane * 2, y0 = ty * kTileH;
+			const bool colIn = x0 < p.W;
+			// 1. merge
+			if (peers && colIn) {
 #pragma unroll 1
-			for (int half = 0; half < 2; ++half) {
-				ulonglong2 acc[8]; // the owner's rows, then the running minimum
-#pragma unroll
-				for (int k = 0; k < 8; ++k) {
-					const uint32_t y = y0 + half * 8 + k;
-					acc[k] = make_ulonglong2(~0ull, ~0ull);
-					if (y < p.H) acc[k] = __ldcg((const ulonglong2*)(vis + (size_t)y * p.W + x0));
-				}
-				uint32_t changed = 0; // bit k: row k took a peer's key
-				for (uint32_t m = peers; m; m &= m - 1) {
-					const unsigned long long* pv = p.mp.vis[__ffs(m) - 1];
-					ulonglong2 q[8];
+				for (int half = 0; half < 2; ++half) {
+					ulonglong2 acc[8]; // the owner's rows, then the running minimum
 #pragma unroll
 					for (int k = 0; k < 8; ++k) {
 						const uint32_t y = y0 + half * 8 + k;
-						q[k] = make_ulonglong2(~0ull, ~0ull);
-						if (y < p.H) q[k] = __ldcg((const ulonglong2*)(pv + (size_t)y * p.W + x0));
+						acc[k] = make_ulonglong2(~0ull, ~0ull);
+						if (y < p.H) acc[k] = __ldcg((const ulonglong2*)(vis + (size_t)y * p.W + x0));
+					}
+					uint32_t changed = 0; // bit k: row k took a peer's key
+					for (uint32_t m = peers; m; m &= m - 1) {
+						const unsigned long long* pv = p.mp.vis[__ffs(m) - 1];
+						ulonglong2 q[8];
+#pragma unroll
+						for (int k = 0; k < 8; ++k) {
+							const uint32_t y = y0 + half * 8 + k;
+							q[k] = make_ulonglong2(~0ull, ~0ull);
+							if (y < p.H) q[k] = __ldcg((const ulonglong2*)(pv + (size_t)y * p.W + x0));
+						}
+#pragma unroll
+						for (int k = 0; k < 8; ++k) {
+							if (q[k].x < acc[k].x) { acc[k].x = q[k].x; changed |= 1u << k; }
+							if (q[k].y < acc[k].y) { acc[k].y = q[k].y; changed |= 1u << k; }
+						}
 					}
 #pragma unroll
-					for (int k = 0; k < 8; ++k) {
-						if (q[k].x < acc[k].x) { acc[k].x = q[k].x; changed |= 1u << k; }
-						if (q[k].y < acc[k].y) { acc[k].y = q[k].y; changed |= 1u << k; }
-					}
+					for (int k = 0; k < 8; ++k)
+						if (changed & (1u << k)) __stcg((ulonglong2*)(vis + (size_t)(y0 + half * 8 + k) * p.W + x0), acc[k]);
 				}
-#pragma unroll
-				for (int k = 0; k < 8; ++k)
-					if (changed & (1u << k)) __stcg((ulonglong2*)(vis + (size_t)(y0 + half * 8 + k) * p.W + x0), acc[k]);
 			}
-		}
-		__syncwarp();
-		// 2. exact mips of the merged tile -> every rank's pyramid, changed texels only (all pyramids are identical before this frame's
-		// stores, so the local copy tells whether a texel changes anywhere)
-		ulonglong2 v[kTileH];
-		{
+			__syncwarp();
+			// 2. exact mips of the merged tile -> every rank's pyramid, changed texels only (all pyramids are identical before this
+			// frame's stores, so the local copy tells whether a texel changes anywhere).  Which texels this lane owns depends on the
+			// tile and the lane only, so their old values are requested together with the tile's rows.
+			ulonglong2 v[kTileH];
 #pragma unroll
 			for (int r = 0; r < kTileH; ++r) {
 				v[r] = make_ulonglong2(0ull, 0ull);
 				if (colIn && y0 + r < p.H) v[r] = __ldcg((const ulonglong2*)(vis + (size_t)(y0 + r) * p.W + x0)); // L2: this warp may just have written it
 			}
+			uint32_t idxOf[kTileSlots], oldOf[kTileSlots];
+			uint32_t have = 0; // bit s: this lane owns a texel in slot s
+			hiz_tile_slots(geo, tx, ty, lane, [&](int slot, uint32_t idx) { idxOf[slot] = idx; have |= 1u << slot; });
+#pragma unroll
+			for (int sl = 0; sl < kTileSlots; ++sl) oldOf[sl] = (have >> sl) & 1u ? __float_as_uint(__ldcg(localPyr + idxOf[sl])) : 0u;
+			hiz_tile_reduce(v, geo, tx, ty, lane, [&](int slot, uint32_t idx, float m) {
+				if (oldOf[slot] != __float_as_uint(m)) {
+					for (int r = 0; r < N; ++r) __stcg(p.mp.pyr[r] + idx, m);
+					sent += (uint32_t)(N - 1);
+				}
+			});
 		}
-		uint32_t idxOf[kTileSlots];
-		float valOf[kTileSlots];
-		uint32_t have = 0; // bit s: this lane owns a texel in slot s
-		hiz_tile_reduce(v, geo, tx, ty, lane, [&](int slot, uint32_t idx, float m) { idxOf[slot] = idx; valOf[slot] = m; have |= 1u << slot; });
-		// all the old texels first (independent loads, one L2 round trip), then the stores of those that changed: checking and storing
-		// texel by texel would chain 15 round trips, because a store into pyr[me] may alias the next load
-		uint32_t oldOf[kTileSlots];
-#pragma unroll
-		for (int sl = 0; sl < kTileSlots; ++sl) oldOf[sl] = (have >> sl) & 1u ? __float_as_uint(__ldcg(localPyr + idxOf[sl])) : 0u;
-#pragma unroll
-		for (int sl = 0; sl < kTileSlots; ++sl)
-			if (((have >> sl) & 1u) && oldOf[sl] != __float_as_uint(valOf[sl])) {
-				for (int r = 0; r < N; ++r) __stcg(p.mp.pyr[r] + idxOf[sl], valOf[sl]);
-				sent += (uint32_t)(N - 1);
-			}
 	}
-	} // chunks
 	if (p.stats) {
 		for (int o = 16; o; o >>= 1) sent += __shfl_xor_sync(0xffffffffu, sent, o);
 		if (lane == 0) {
@@ -188,8 +186,7 @@ cudaError_t launch_strip_merge_hiz(const StripParams& p, int num_sms, cudaStream
 	const uint32_t rows = strip_first_row(p.tilesY, p.mp.rank + 1, p.mp.nranks) - strip_first_row(p.tilesY, p.mp.rank, p.mp.nranks);
 	const uint32_t tiles = rows * p.tilesX;
 	if (tiles == 0) return cudaSuccess;
-	static_assert(kChunk * kMaxRanks <= kStripThreads, "one thread per (rank, tile of the chunk) in the flag fetch");
-	uint32_t grid = (tiles + kChunk - 1) / kChunk;
+	uint32_t grid = (tiles + 7) / 8;                                 // at least a tile per warp
 	if (grid > (uint32_t)num_sms * 2) grid = (uint32_t)num_sms * 2; // persistent: two blocks per SM (128 registers)
 	strip_merge_hiz_kernel<<<grid, kStripThreads, 0, stream>>>(p);
 	return cudaGetLastError();
