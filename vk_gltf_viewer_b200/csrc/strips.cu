@@ -26,17 +26,18 @@ constexpr int kStripThreads = 256;
 
 __device__ __forceinline__ ulonglong2 min2(ulonglong2 a, ulonglong2 b) { return make_ulonglong2(a.x < b.x ? a.x : b.x, a.y < b.y ? a.y : b.y); }
 
-// Persistent blocks (two per SM), each owning a contiguous range of the tiles of this rank's strip, one warp per tile.
+// Persistent blocks (four per SM), each owning a contiguous range of the tiles of this rank's strip, one warp per tile.
 //   0. the block fetches, for ALL its tiles at once, which ranks drew into them (one NVLink round trip per block);
-//   1. merge: for every tile some peer drew into, 8 rows at a time — the owner's rows, then each peer's rows (16-byte loads,
-//      8 in flight per lane), min, rows that changed stored back;
+//   1. merge: for every tile some peer drew into, 4 rows at a time — the owner's rows, then each peer's rows (16-byte loads,
+//      4 in flight per lane), min, rows that changed stored back;
 //   2. pyramid: the merged tile's 16 rows AND the 15 pyramid texels this lane may produce are requested together (one round trip),
 //      the tile is reduced in registers (hiz_tile.cuh), and every texel that differs from the local pyramid is stored into
 //      every rank's pyramid.
-// Keeping 1 and 2 apart (instead of holding the 16 merged rows in registers across both) keeps the kernel at two blocks per SM.
+// Keeping 1 and 2 apart (instead of holding the 16 merged rows in registers across both) keeps the kernel at 64 registers: the
+// strip is read from DRAM (an 8K visbuffer is twice the L2), and it takes 32 warps per SM with a tile each in flight to keep DRAM busy.
 constexpr uint32_t kRound = 512; // tiles whose masks fit the shared-memory table at once
 
-__global__ void __launch_bounds__(kStripThreads, 2) strip_merge_hiz_kernel(const StripParams p) {
+__global__ void __launch_bounds__(kStripThreads, 4) strip_merge_hiz_kernel(const StripParams p) {
 	__shared__ uint32_t sMask[kRound]; // bit r: rank r drew into the tile in this pass (bit `me`: this rank did)
 	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int N = p.mp.nranks, me = p.mp.rank;
@@ -77,34 +78,35 @@ __global__ void __launch_bounds__(kStripThreads, 2) strip_merge_hiz_kernel(const
 			const bool colIn = x0 < p.W;
 			// 1. merge
 			if (peers && colIn) {
+				constexpr int kRows = 4; // rows per round trip: small enough to leave the kernel at 64 registers (4 blocks per SM)
 #pragma unroll 1
-				for (int half = 0; half < 2; ++half) {
-					ulonglong2 acc[8]; // the owner's rows, then the running minimum
+				for (int part = 0; part < kTileH / kRows; ++part) {
+					ulonglong2 acc[kRows]; // the owner's rows, then the running minimum
 #pragma unroll
-					for (int k = 0; k < 8; ++k) {
-						const uint32_t y = y0 + half * 8 + k;
+					for (int k = 0; k < kRows; ++k) {
+						const uint32_t y = y0 + part * kRows + k;
 						acc[k] = make_ulonglong2(~0ull, ~0ull);
 						if (y < p.H) acc[k] = __ldcg((const ulonglong2*)(vis + (size_t)y * p.W + x0));
 					}
 					uint32_t changed = 0; // bit k: row k took a peer's key
 					for (uint32_t m = peers; m; m &= m - 1) {
 						const unsigned long long* pv = p.mp.vis[__ffs(m) - 1];
-						ulonglong2 q[8];
+						ulonglong2 q[kRows];
 #pragma unroll
-						for (int k = 0; k < 8; ++k) {
-							const uint32_t y = y0 + half * 8 + k;
+						for (int k = 0; k < kRows; ++k) {
+							const uint32_t y = y0 + part * kRows + k;
 							q[k] = make_ulonglong2(~0ull, ~0ull);
 							if (y < p.H) q[k] = __ldcg((const ulonglong2*)(pv + (size_t)y * p.W + x0));
 						}
 #pragma unroll
-						for (int k = 0; k < 8; ++k) {
+						for (int k = 0; k < kRows; ++k) {
 							if (q[k].x < acc[k].x) { acc[k].x = q[k].x; changed |= 1u << k; }
 							if (q[k].y < acc[k].y) { acc[k].y = q[k].y; changed |= 1u << k; }
 						}
 					}
 #pragma unroll
-					for (int k = 0; k < 8; ++k)
-						if (changed & (1u << k)) __stcg((ulonglong2*)(vis + (size_t)(y0 + half * 8 + k) * p.W + x0), acc[k]);
+					for (int k = 0; k < kRows; ++k)
+						if (changed & (1u << k)) __stcg((ulonglong2*)(vis + (size_t)(y0 + part * kRows + k) * p.W + x0), acc[k]);
 				}
 			}
 			__syncwarp();
@@ -187,7 +189,7 @@ cudaError_t launch_strip_merge_hiz(const StripParams& p, int num_sms, cudaStream
 	const uint32_t tiles = rows * p.tilesX;
 	if (tiles == 0) return cudaSuccess;
 	uint32_t grid = (tiles + 7) / 8;                                 // at least a tile per warp
-	if (grid > (uint32_t)num_sms * 2) grid = (uint32_t)num_sms * 2; // persistent: two blocks per SM (128 registers)
+	if (grid > (uint32_t)num_sms * 4) grid = (uint32_t)num_sms * 4; // persistent: four blocks per SM (64 registers)
 	strip_merge_hiz_kernel<<<grid, kStripThreads, 0, stream>>>(p);
 	return cudaGetLastError();
 }
