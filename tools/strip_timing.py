@@ -7,6 +7,7 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 W, H = 7680, 4320
+NF = int(os.environ.get('NF', '4'))
 scene = Scene.lattice(22, 22, 21, 224, 0x5EED0003)
 views = [scene.default_view(i, 64) for i in range(8)]
 cam = Camera(W, H).look_at(*views[0])
@@ -14,8 +15,10 @@ r = api.Renderer(W, H, device=local)
 pc = r.upload_scene(scene, cam)
 r.set_shard_interleaved(rank, world, 11)
 multigpu.attach_peers(r, dist)
-for k in range(6):
+for k in range(NF):
     cam.look_at(*views[k]); r.update_camera(pc, cam)
     st = r.frame(pc, api.FRAME_TWO_PASS | api.FRAME_MERGE_STRIPS | api.FRAME_TIMED | api.FRAME_STAGES)
-    if rank == 0: print(f"frame {k}: total {st.total_ms:.3f} cullA {st.cull_a_ms:.3f} rasterA {st.raster_a_ms:.3f} mergeA {st.merge_a_ms:.3f} cullB {st.cull_b_ms:.3f} rasterB {st.raster_b_ms:.3f} mergeB {st.merge_b_ms:.3f} pulled {st.strip_tiles_pulled} sent {st.strip_texels_sent}", file=sys.stderr)
+    import time
+    time.sleep(0.02 * rank)
+    if True: print(f"[rank {rank}] " +f"frame {k}: total {st.total_ms:.3f} cullA {st.cull_a_ms:.3f} rasterA {st.raster_a_ms:.3f} mergeA {st.merge_a_ms:.3f} cullB {st.cull_b_ms:.3f} rasterB {st.raster_b_ms:.3f} mergeB {st.merge_b_ms:.3f} pulled {st.strip_tiles_pulled} sent {st.strip_texels_sent}", file=sys.stderr)
 dist.barrier(); r.ipc_detach(); r.close(); dist.destroy_process_group()
