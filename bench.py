@@ -142,7 +142,7 @@ def roofline(dom, stages, ent, hbm, peak_src, traffic, clocks):
 
 def range_sharded_leg(rank, world, local_rank, dist, steps, builder_note):
     """BASELINE config 5 on `world` GPUs: ONE view of the 1.02-billion-triangle lattice at 7680x4320, the MeshletDraw list dealt to
-    the ranks in interleaved 2048-draw blocks, screen-strip owners pulling dirty tiles over NVLink and all-gathering the pyramid
+    the ranks in interleaved 2048-draw blocks, owners of interleaved 16-row screen strips pulling dirty tiles over NVLink and all-gathering the pyramid
     (VKV_FRAME_MERGE_STRIPS, csrc/strips.cu).  Returns the `range_sharded` object of the JSON line (every rank computes it; rank 0
     prints): device-timed ms per frame (max over ranks), the merge stages, the same frames on ONE GPU for the speed-up, the
     NVLink bytes per frame against the all-reduce bound, and `merge_parity`: on EVERY rank, after the same three views rendered
@@ -194,14 +194,13 @@ def range_sharded_leg(rank, world, local_rank, dist, steps, builder_note):
     r.set_shard_interleaved(rank, world, 11)
     multigpu.attach_peers(r, dist)
     # ---- parity first (three views from a cleared pyramid, sharded vs the same rank alone)
-    y0, y1 = r.strip_rows(rank, world)
     sync_all()
     sweep(sharded, 2)
-    h_strip, h_pyr = r.hash(0, y0, y1), r.hash(1)
+    h_strip, h_pyr = r.hash(0, rank, world), r.hash(1)
     sync_all()
     r.set_shard_interleaved(0, 1, 11)   # the whole list on this GPU, no exchange
     sweep(single, 2)
-    ok = (h_strip == r.hash(0, y0, y1)) and (h_pyr == r.hash(1))
+    ok = (h_strip == r.hash(0, rank, world)) and (h_pyr == r.hash(1))
     # ---- one GPU: the same frames, device-timed (every rank measures; they are independent here)
     n1 = max(3, min(steps, 10))
     sweep(single, 3)
@@ -234,7 +233,7 @@ def range_sharded_leg(rank, world, local_rank, dist, steps, builder_note):
     out = {"workload": label, "resolution": [W, H], "meshlet_draws": cnt.draws, "triangles": cnt.triangles_instanced, "meshlets": builder_note,
            "n_gpus": world, "steps": steps, "ms_per_frame": vals[0], "frames_per_s": 1e3 / vals[0], "gtris_per_s": cnt.triangles_instanced / vals[0] / 1e6,
            "n1_ms_per_frame": vals[1], "speedup_vs_n1": vals[1] / vals[0], "merge_parity": bool(int(okt.item())),
-           "merge_parity_how": "per rank: vkv_hash of its own strip rows and of the whole pyramid after 3 views from a cleared pyramid == the same frames rendered unsharded on that rank",
+           "merge_parity_how": "per rank: vkv_hash of the visbuffer rows it owns and of the whole pyramid after 3 views from a cleared pyramid == the same frames rendered unsharded on that rank",
            "stages_ms_max_over_ranks": {k[:-3]: round(v, 5) for k, v in zip(names, vals[2:])},
            "merge_a_ms": vals[2 + names.index("merge_a_ms")], "merge_b_ms": vals[2 + names.index("merge_b_ms")],
            "nvlink": {"tiles_pulled_per_frame_all_ranks": float(tr[0]), "pyramid_texels_sent_per_frame_all_ranks": float(tr[1]),

@@ -52,9 +52,9 @@ enum {
 	VKV_FRAME_TIMED = 1 << 3,      /* fill total_ms of vkv_stats (CUDA events around the frame; syncs the stream at frame end) */
 	VKV_FRAME_NO_CULL = 1 << 4,    /* rasterise every MeshletDraw (debug; what the task shader does with culling disabled) */
 	VKV_FRAME_MERGE = 1 << 5,      /* multi-GPU: min-merge the visbuffer with the attached peers before each pyramid build */
-	VKV_FRAME_MERGE_STRIPS = 1 << 7, /* multi-GPU: screen-strip ownership — each rank pulls the tiles its peers drew into its strip, builds
-	                                  the strip's exact mips and stores the changed texels into every rank's pyramid; the merged
-	                                  visbuffer stays distributed (rank r holds strip r), the pyramid is complete everywhere */
+	VKV_FRAME_MERGE_STRIPS = 1 << 7, /* multi-GPU: screen-strip ownership — each rank pulls the tiles its peers drew into the tile rows it owns,
+	                                  builds their exact mips and stores the changed texels into every rank's pyramid; the merged
+	                                  visbuffer stays distributed (vkv_strip_owner), the pyramid is complete everywhere */
 	VKV_FRAME_CONE_CULL = 1 << 8,  /* extension, OFF in parity mode: reject meshlets whose normal cone faces away from the camera before the
 	                                  occlusion test (needs vkv_set_cone_table).  Removes only meshlets none of whose triangles the mesh
 	                                  shader's facing test would keep: the visbuffer is unchanged, the visible lists get shorter */
@@ -198,15 +198,18 @@ int vkv_ipc_attach(vkv_ctx*, int rank, int nranks, const void* handles);
 int vkv_ipc_detach(vkv_ctx*);
 /* all ranks call it at the same point of their stream: barrier, fused reduce-scatter + all-gather u64 min, barrier */
 int vkv_merge(vkv_ctx*);
-/* Strip ownership (VKV_FRAME_MERGE_STRIPS).  The screen is cut into nranks horizontal strips of whole 16-row tile rows; rank r owns
- * rows [first_row, end_row).  After a strip-mode frame rank r's visbuffer holds the MERGED keys in its own strip only (its other
- * rows hold what this rank drew); the pyramid is complete and identical on every rank.  vkv_gather_strips (a collective: all ranks
- * call it at the same point) pulls the other strips from their owners so that every rank holds the whole merged image. */
-int vkv_strip_rows(vkv_ctx*, int rank, int nranks, uint32_t* first_row, uint32_t* end_row);
+/* Strip ownership (VKV_FRAME_MERGE_STRIPS).  The screen is cut into rows of 64x16-pixel tiles dealt round-robin: tile row t (pixel rows
+ * 16t .. 16t+15) belongs to rank t % nranks — interleaved, so every rank gets its share of busy and of empty rows.  After a strip-mode
+ * frame a rank's visbuffer holds the MERGED keys in the rows it owns (its other rows hold what this rank drew); the pyramid is
+ * complete and identical on every rank.  vkv_strip_owner returns the owning rank of a pixel row (or a negative vkv_status).
+ * vkv_gather_strips (a collective: all ranks call it at the same point) pulls the rows a rank does not own from their owners, so
+ * that every rank holds the whole merged image. */
+int vkv_strip_owner(vkv_ctx*, uint32_t pixel_row, int nranks);
 int vkv_gather_strips(vkv_ctx*);
-/* order-independent 64-bit digest computed on the device: what = 0: visbuffer keys of rows [first_row, end_row);
- * what = 1: the whole pyramid (rows ignored).  Equal inputs at equal positions give equal digests on any GPU (parity checks). */
-int vkv_hash(vkv_ctx*, int what, uint32_t first_row, uint32_t end_row, uint64_t* out);
+/* order-independent 64-bit digest computed on the device: what = 0: the visbuffer keys of the rows `rank` owns among `nranks`
+ * (nranks = 1: the whole image); what = 1: the whole pyramid (rank / nranks ignored).  Equal data at equal positions give equal
+ * digests on any GPU (parity checks between a sharded frame and the same frame rendered by one GPU). */
+int vkv_hash(vkv_ctx*, int what, int rank, int nranks, uint64_t* out);
 
 /* ---- results (blocking device->host copies on the ctx stream) ------------------------------------------- */
 int vkv_read_visbuffer64(vkv_ctx*, uint64_t* host);                /* W*H keys: (~floatBits(depth) << 32) | packVisBuffer */

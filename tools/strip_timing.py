@@ -15,10 +15,13 @@ r = api.Renderer(W, H, device=local)
 pc = r.upload_scene(scene, cam)
 r.set_shard_interleaved(rank, world, 11)
 multigpu.attach_peers(r, dist)
+lines = []
 for k in range(NF):
     cam.look_at(*views[k]); r.update_camera(pc, cam)
     st = r.frame(pc, api.FRAME_TWO_PASS | api.FRAME_MERGE_STRIPS | api.FRAME_TIMED | api.FRAME_STAGES)
-    import time
-    time.sleep(0.02 * rank)
-    if True: print(f"[rank {rank}] " +f"frame {k}: total {st.total_ms:.3f} cullA {st.cull_a_ms:.3f} rasterA {st.raster_a_ms:.3f} mergeA {st.merge_a_ms:.3f} cullB {st.cull_b_ms:.3f} rasterB {st.raster_b_ms:.3f} mergeB {st.merge_b_ms:.3f} pulled {st.strip_tiles_pulled} sent {st.strip_texels_sent}", file=sys.stderr)
+    lines.append(f"[rank {rank}] " +f"frame {k}: total {st.total_ms:.3f} cullA {st.cull_a_ms:.3f} rasterA {st.raster_a_ms:.3f} mergeA {st.merge_a_ms:.3f} cullB {st.cull_b_ms:.3f} rasterB {st.raster_b_ms:.3f} mergeB {st.merge_b_ms:.3f} pulled {st.strip_tiles_pulled} sent {st.strip_texels_sent}")
+dist.barrier()
+import time
+time.sleep(0.05 * rank)
+print("\n".join(lines[-2:]), file=sys.stderr)
 dist.barrier(); r.ipc_detach(); r.close(); dist.destroy_process_group()

@@ -57,7 +57,7 @@ EXPORTS = [
     "vkv_build_meshlets", "vkv_assemble_vertices", "vkv_widen_indices",
     "vkv_alloc", "vkv_meshopt_plan_create", "vkv_meshopt_run", "vkv_meshopt_results", "vkv_meshopt_plan_destroy",
     "vkv_set_shard", "vkv_set_shard_interleaved", "vkv_ipc_export", "vkv_ipc_attach", "vkv_ipc_detach", "vkv_merge",
-    "vkv_strip_rows", "vkv_gather_strips", "vkv_hash", "vkv_set_cone_table", "vkv_set_quantized_positions",
+    "vkv_strip_owner", "vkv_gather_strips", "vkv_hash", "vkv_set_cone_table", "vkv_set_quantized_positions",
 ]
 
 _bound = False
@@ -111,9 +111,9 @@ def _lib():
         L.vkv_ipc_attach.argtypes = [vp, i, i, vp]
         L.vkv_ipc_detach.argtypes = [vp]
         L.vkv_merge.argtypes = [vp]
-        L.vkv_strip_rows.argtypes = [vp, i, i, C.POINTER(u32), C.POINTER(u32)]
+        L.vkv_strip_owner.argtypes = [vp, u32, i]
         L.vkv_gather_strips.argtypes = [vp]
-        L.vkv_hash.argtypes = [vp, i, u32, u32, C.POINTER(u64)]
+        L.vkv_hash.argtypes = [vp, i, i, i, C.POINTER(u64)]
         L.vkv_set_cone_table.argtypes = [vp, u64]
         L.vkv_set_quantized_positions.argtypes = [vp, u64]
         L.vkv_selftest_division.argtypes = [vp, u64, u32, C.POINTER(u64), C.POINTER(u64)]
@@ -405,18 +405,17 @@ class Renderer:
     def merge(self):
         self._ck(self.L.vkv_merge(self.h))
 
-    def strip_rows(self, rank: int, nranks: int):
-        """rows [first, end) of the screen strip `rank` owns under FRAME_MERGE_STRIPS"""
-        a, b = C.c_uint32(), C.c_uint32()
-        self._ck(self.L.vkv_strip_rows(self.h, rank, nranks, C.byref(a), C.byref(b)))
-        return a.value, b.value
+    def owned_rows(self, rank: int, nranks: int) -> np.ndarray:
+        """boolean mask over the H pixel rows: True where `rank` owns the row under FRAME_MERGE_STRIPS (tile row t -> rank t % nranks)"""
+        assert self.L.vkv_strip_owner(self.h, 0, nranks) == 0 and (self.H < 17 or nranks < 2 or self.L.vkv_strip_owner(self.h, 16, nranks) == 1)
+        return ((np.arange(self.H) // 16) % nranks) == rank
 
     def gather_strips(self):
         """collective: pull the strips this rank does not own from their owners (whole merged image on every rank)"""
         self._ck(self.L.vkv_gather_strips(self.h))
 
-    def hash(self, what: int, first_row: int = 0, end_row: int = 0) -> int:
-        """device-side order-independent digest: what=0 visbuffer rows [first_row, end_row), what=1 the pyramid"""
+    def hash(self, what: int, rank: int = 0, nranks: int = 1) -> int:
+        """device-side order-independent digest: what=0 the visbuffer rows `rank` owns among `nranks` (1 = whole image), what=1 the pyramid"""
         h = C.c_uint64()
-        self._ck(self.L.vkv_hash(self.h, what, first_row, end_row, C.byref(h)))
+        self._ck(self.L.vkv_hash(self.h, what, rank, nranks, C.byref(h)))
         return h.value

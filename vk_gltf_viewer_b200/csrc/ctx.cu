@@ -911,12 +911,10 @@ int vkv_merge(vkv_ctx* c) {
 	return enqueue_merge(c, nullptr);
 }
 
-int vkv_strip_rows(vkv_ctx* c, int rank, int nranks, uint32_t* first_row, uint32_t* end_row) {
-	if (!c || !first_row || !end_row || nranks < 1 || rank < 0 || rank >= nranks) return c ? fail(c, VKV_ERR_INVALID, "vkv_strip_rows: bad argument") : VKV_ERR_INVALID;
-	const uint32_t y0 = strip_first_row(c->tiles_y, rank, nranks) * 16u, y1 = strip_first_row(c->tiles_y, rank + 1, nranks) * 16u;
-	*first_row = y0 < c->H ? y0 : c->H;
-	*end_row = y1 < c->H ? y1 : c->H;
-	return VKV_OK;
+int vkv_strip_owner(vkv_ctx* c, uint32_t pixel_row, int nranks) {
+	if (!c) return VKV_ERR_INVALID;
+	if (nranks < 1 || pixel_row >= c->H) return fail(c, VKV_ERR_INVALID, "vkv_strip_owner: row %u of %u, %d ranks", pixel_row, c->H, nranks);
+	return strip_owner_of_tile_row(pixel_row / 16u, nranks);
 }
 
 int vkv_gather_strips(vkv_ctx* c) {
@@ -935,17 +933,17 @@ int vkv_gather_strips(vkv_ctx* c) {
 	return VKV_OK;
 }
 
-int vkv_hash(vkv_ctx* c, int what, uint32_t first_row, uint32_t end_row, uint64_t* out) {
+int vkv_hash(vkv_ctx* c, int what, int rank, int nranks, uint64_t* out) {
 	if (!c || !out) return VKV_ERR_INVALID;
 	CK(cudaSetDevice(c->device));
 	unsigned long long* d = (unsigned long long*)c->tmp_count; // 256-byte scratch
 	CK(cudaMemsetAsync(d, 0, 8, c->stream));
 	if (what == 0) {
-		if (first_row > end_row || end_row > c->H) return fail(c, VKV_ERR_INVALID, "vkv_hash: rows [%u, %u) outside the %u-row image", first_row, end_row, c->H);
-		CK(launch_hash64(c->vis, (size_t)first_row * c->W, (size_t)(end_row - first_row) * c->W, d, c->num_sms, c->stream));
+		if (nranks < 1 || rank < 0 || rank >= nranks) return fail(c, VKV_ERR_INVALID, "vkv_hash: rank %d of %d", rank, nranks);
+		CK(launch_hash_owned(c->vis, c->W, c->H, rank, nranks, d, c->num_sms, c->stream));
 	} else if (what == 1) { // the pyramid as u64 words (its allocation is padded with a zero float to an even count)
 		CK(launch_hash64((const unsigned long long*)c->pyramid, 0, ((size_t)c->pyr.total + 1) / 2, d, c->num_sms, c->stream));
-	} else return fail(c, VKV_ERR_INVALID, "vkv_hash: what must be 0 (visbuffer rows) or 1 (pyramid)");
+	} else return fail(c, VKV_ERR_INVALID, "vkv_hash: what must be 0 (visbuffer rows of a rank) or 1 (pyramid)");
 	unsigned long long h = 0;
 	CK(cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, c->stream));
 	CK(cudaStreamSynchronize(c->stream));

@@ -131,7 +131,7 @@ struct MergeParams {
 cudaError_t launch_xgpu_barrier(const MergeParams& p, uint32_t epoch, unsigned long long timeout_ns, cudaStream_t stream);
 cudaError_t launch_merge_min(const MergeParams& p, int num_sms, cudaStream_t stream);
 
-// ---- strip mode (strips.cu): rank r owns the tile rows [tileRows*r/n, tileRows*(r+1)/n) of the screen -------------------------
+// ---- strip mode (strips.cu): rank r owns every n-th row of 64x16-pixel tiles ---------------------------------------------------
 struct StripParams {
 	MergeParams mp;
 	uint32_t W, H;
@@ -147,10 +147,17 @@ struct StripParams {
 	uint32_t* done;                       // last-block ticket (zero between launches)
 	unsigned long long timeout_ns;
 };
-__host__ __device__ inline uint32_t strip_first_row(uint32_t tilesY, int rank, int nranks) { return (uint32_t)((unsigned long long)tilesY * (unsigned)rank / (unsigned)nranks); }
+// ownership: tile row tr (16 pixel rows) belongs to rank tr % n — strips INTERLEAVED over the screen, so that every rank gets its
+// share of the busy rows and of the empty ones without any coordination (a contiguous split left the rank holding the sky idle and
+// the one holding the densest rows pulling three times the average)
+__host__ __device__ inline int strip_owner_of_tile_row(uint32_t tileRow, int nranks) { return (int)(tileRow % (uint32_t)nranks); }
+__host__ __device__ inline uint32_t strip_tile_rows_owned(uint32_t tilesY, int rank, int nranks) {
+	return (uint32_t)rank < tilesY ? (tilesY - (uint32_t)rank + (uint32_t)nranks - 1u) / (uint32_t)nranks : 0u;
+}
 cudaError_t launch_strip_merge_hiz(const StripParams& p, int num_sms, cudaStream_t stream);
 cudaError_t launch_strip_gather(const StripParams& p, int num_sms, cudaStream_t stream);
 cudaError_t launch_hash64(const unsigned long long* data, size_t first, size_t count, unsigned long long* out, int num_sms, cudaStream_t stream);
+cudaError_t launch_hash_owned(const unsigned long long* vis, uint32_t W, uint32_t H, int rank, int nranks, unsigned long long* out, int num_sms, cudaStream_t stream);
 cudaError_t launch_hiz_tail(const HizParams& p, cudaStream_t stream);
 
 // ---- visbuffer resolve (resolve.cu) ---------------------------------------------------------------------------------

@@ -1,8 +1,8 @@
 // strips.cu — the exchange step of the meshlet-range-sharded path, by screen-strip ownership ("cheaper variant").
 //
 // Every rank culls and rasterises ITS range of the draw list into its own full-resolution 64-bit visbuffer (raster.cu marks
-// every 64x16-pixel tile a drawn triangle's bounding box touches).  The screen is cut into n horizontal strips of whole tile
-// rows; rank r OWNS strip r.  After a cross-GPU barrier ONE kernel per rank does, for every tile of its strip:
+// every 64x16-pixel tile a drawn triangle's bounding box touches).  The screen is cut into rows of tiles (16 pixel rows each) dealt
+// round-robin: rank r OWNS tile rows r, r + n, r + 2n, … ("its strips").  ONE kernel per rank does, for every tile it owns:
 //   reduce-scatter   read the peers' dirty flags of the tile, pull only the tiles some peer actually drew into (16-byte loads
 //                    over NVLink / NVSwitch peer memory), min them into the owner's keys, store the merged rows back locally;
 //   HiZ per strip    the exact-2x mips of the merged tile, straight from the registers that hold it (hiz_tile.cuh);
@@ -41,8 +41,7 @@ __global__ void __launch_bounds__(kStripThreads, 4) strip_merge_hiz_kernel(const
 	__shared__ uint32_t sMask[kRound]; // bit r: rank r drew into the tile in this pass (bit `me`: this rank did)
 	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int N = p.mp.nranks, me = p.mp.rank;
-	const uint32_t row0 = strip_first_row(p.tilesY, me, N), row1 = strip_first_row(p.tilesY, me + 1, N);
-	const uint32_t nTiles = (row1 - row0) * p.tilesX;
+	const uint32_t nTiles = strip_tile_rows_owned(p.tilesY, me, N) * p.tilesX; // tile t of this rank: tile row me + N * (t / tilesX)
 	// barrier in: this kernel starts when THIS rank's raster pass is complete (stream order); block 0 says so to every rank, and
 	// every block waits until all ranks have said so (polling this rank's own slots)
 #ifndef VKV_X_NO_IN
@@ -64,13 +63,13 @@ __global__ void __launch_bounds__(kStripThreads, 4) strip_merge_hiz_kernel(const
 		// 0. dirty bytes of the whole round: work item (r, j) asks rank r about tile base + j (r == me: this rank's own marks, local)
 		for (uint32_t w = threadIdx.x; w < cnt * (uint32_t)N; w += kStripThreads) {
 			const uint32_t r = w / cnt, j = w % cnt, t = base + j;
-			const uint32_t tile = (row0 + t / p.tilesX) * p.tilesX + t % p.tilesX;
+			const uint32_t tile = ((uint32_t)me + (uint32_t)N * (t / p.tilesX)) * p.tilesX + t % p.tilesX;
 			if (*(volatile const uint8_t*)(p.mp.dirty[r] + (size_t)p.pass * p.dirtyStride + tile)) atomicOr(&sMask[j], 1u << r);
 		}
 		__syncthreads();
 		for (uint32_t j = warp; j < cnt; j += kStripThreads / 32) {
 			const uint32_t t = base + j;
-			const uint32_t tx = t % p.tilesX, ty = row0 + t / p.tilesX;
+			const uint32_t tx = t % p.tilesX, ty = (uint32_t)me + (uint32_t)N * (t / p.tilesX);
 			const uint32_t mask = sMask[j], peers = mask & ~(1u << me);
 			// second pass of a frame: a tile neither a peer nor this rank drew into since the first exchange still holds the merged
 			// keys the first exchange built its mips from — nothing to pull, nothing to rebuild
@@ -161,13 +160,12 @@ __global__ void __launch_bounds__(kStripThreads, 4) strip_merge_hiz_kernel(const
 // image on one GPU: parity tests, vkv_read_visbuffer64 after a strip-mode frame)
 __global__ void __launch_bounds__(256) strip_gather_kernel(const StripParams p) {
 	const int N = p.mp.nranks, me = p.mp.rank;
-	unsigned long long* const vis = p.mp.vis[me];
-	for (int k = 1; k < N; ++k) {
-		const int r = (me + k) % N;
-		const size_t y0 = (size_t)strip_first_row(p.tilesY, r, N) * kTileH, y1 = min((size_t)p.H, (size_t)strip_first_row(p.tilesY, r + 1, N) * kTileH);
-		const size_t lo = y0 * p.W, hi = y1 * p.W; // whole rows: contiguous keys
-		const unsigned long long* src = p.mp.vis[r];
-		for (size_t i = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (size_t)gridDim.x * blockDim.x) vis[i] = __ldcg(src + i);
+	ulonglong2* const vis = (ulonglong2*)p.mp.vis[me];
+	const size_t rowPairs = p.W / 2, total = rowPairs * p.H; // W is even in strip mode (one exact mip at least)
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+		const uint32_t y = (uint32_t)(i / rowPairs);
+		const int owner = strip_owner_of_tile_row(y / kTileH, N);
+		if (owner != me) vis[i] = __ldcg((const ulonglong2*)p.mp.vis[owner] + i);
 	}
 }
 
@@ -186,11 +184,27 @@ __global__ void __launch_bounds__(256) hash64_kernel(const unsigned long long* _
 	if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
 }
 
+// digest of the rows `rank` owns among `nranks` (position-dependent like hash64_kernel: equal rows at equal positions give equal sums)
+__global__ void __launch_bounds__(256) hash_owned_kernel(const unsigned long long* __restrict__ vis, uint32_t W, uint32_t H, int rank, int nranks, unsigned long long* out) {
+	unsigned long long acc = 0;
+	const size_t total = (size_t)W * H;
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+		const uint32_t y = (uint32_t)(i / W);
+		if (strip_owner_of_tile_row(y / kTileH, nranks) == rank) acc += mix64(vis[i] + 0x9e3779b97f4a7c15ull * (unsigned long long)(i + 1));
+	}
+	for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+	if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+
 } // namespace
 
+cudaError_t launch_hash_owned(const unsigned long long* vis, uint32_t W, uint32_t H, int rank, int nranks, unsigned long long* out, int num_sms, cudaStream_t stream) {
+	hash_owned_kernel<<<num_sms * 8, 256, 0, stream>>>(vis, W, H, rank, nranks, out);
+	return cudaGetLastError();
+}
+
 cudaError_t launch_strip_merge_hiz(const StripParams& p, int num_sms, cudaStream_t stream) {
-	const uint32_t rows = strip_first_row(p.tilesY, p.mp.rank + 1, p.mp.nranks) - strip_first_row(p.tilesY, p.mp.rank, p.mp.nranks);
-	const uint32_t tiles = rows * p.tilesX;
+	const uint32_t tiles = strip_tile_rows_owned(p.tilesY, p.mp.rank, p.mp.nranks) * p.tilesX;
 	if (tiles == 0) return cudaSuccess;
 	uint32_t grid = (tiles + 7) / 8;                                 // at least a tile per warp
 	if (grid > (uint32_t)num_sms * 4) grid = (uint32_t)num_sms * 4; // persistent: four blocks per SM (64 registers)
