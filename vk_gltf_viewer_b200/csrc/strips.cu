@@ -28,8 +28,8 @@ __device__ __forceinline__ ulonglong2 min2(ulonglong2 a, ulonglong2 b) { return 
 
 // Persistent blocks (four per SM), each owning a contiguous range of the tiles of this rank's strip, one warp per tile.
 //   0. the block fetches, for ALL its tiles at once, which ranks drew into them (one NVLink round trip per block);
-//   1. merge: for every tile some peer drew into, 4 rows at a time — the owner's rows, then each peer's rows (16-byte loads,
-//      4 in flight per lane), min, rows that changed stored back;
+//   1. merge: one warp per (tile, peer that drew into it) — the peer's rows (16-byte loads, 8 in flight per lane) are reduced into
+//      the owner's keys with 64-bit atomic mins, all pairs of the block in flight together;
 //   2. pyramid: the merged tile's 16 rows AND the 15 pyramid texels this lane may produce are requested together (one round trip),
 //      the tile is reduced in registers (hiz_tile.cuh), and every texel that differs from the local pyramid is stored into
 //      every rank's pyramid.
@@ -39,6 +39,8 @@ constexpr uint32_t kRound = 512; // tiles whose masks fit the shared-memory tabl
 
 __global__ void __launch_bounds__(kStripThreads, 4) strip_merge_hiz_kernel(const StripParams p) {
 	__shared__ uint32_t sMask[kRound]; // bit r: rank r drew into the tile in this pass (bit `me`: this rank did)
+	__shared__ unsigned short sPair[kRound * (kMaxRanks - 1)]; // (tile of the round << 4) | peer, for every pair to pull
+	__shared__ uint32_t sPairs;
 	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int N = p.mp.nranks, me = p.mp.rank;
 	const uint32_t nTiles = strip_tile_rows_owned(p.tilesY, me, N) * p.tilesX; // tile t of this rank: tile row me + N * (t / tilesX)
@@ -67,50 +69,54 @@ __global__ void __launch_bounds__(kStripThreads, 4) strip_merge_hiz_kernel(const
 			if (*(volatile const uint8_t*)(p.mp.dirty[r] + (size_t)p.pass * p.dirtyStride + tile)) atomicOr(&sMask[j], 1u << r);
 		}
 		__syncthreads();
+		// 1. merge, one warp per (tile, peer that drew into it): the peer's rows (16-byte loads over NVLink, 8 in flight per lane) go into
+		// the owner's keys with the same 64-bit atomic min the rasteriser uses — every pair of the block is in flight at once, where a
+		// warp walking the peers of its tile one after the other would chain up to 2 x 7 NVLink round trips
+		if (threadIdx.x == 0) sPairs = 0u;
+		__syncthreads();
+		for (uint32_t j = threadIdx.x; j < cnt; j += kStripThreads) {
+			const uint32_t peers = sMask[j] & ~(1u << me);
+			if (!peers) continue;
+			uint32_t at = atomicAdd(&sPairs, (uint32_t)__popc(peers));
+			for (uint32_t m = peers; m; m &= m - 1) sPair[at++] = (unsigned short)((j << 4) | (uint32_t)(__ffs(m) - 1));
+		}
+		__syncthreads();
+		const uint32_t nPairs = sPairs;
+		for (uint32_t u = warp; u < nPairs; u += kStripThreads / 32) {
+			const uint32_t j = sPair[u] >> 4, r = sPair[u] & 15u, t = base + j;
+			const uint32_t tx = t % p.tilesX, ty = (uint32_t)me + (uint32_t)N * (t / p.tilesX);
+			const uint32_t x0 = tx * kTileW + lane * 2, y0 = ty * kTileH;
+			if (x0 >= p.W) continue;
+			const unsigned long long* pv = p.mp.vis[r];
+#pragma unroll 1
+			for (int half = 0; half < 2; ++half) {
+				ulonglong2 q[8];
+#pragma unroll
+				for (int k = 0; k < 8; ++k) {
+					const uint32_t y = y0 + half * 8 + k;
+					q[k] = make_ulonglong2(~0ull, ~0ull);
+					if (y < p.H) q[k] = __ldcg((const ulonglong2*)(pv + (size_t)y * p.W + x0));
+				}
+#pragma unroll
+				for (int k = 0; k < 8; ++k) {
+					unsigned long long* dst = vis + (size_t)(y0 + half * 8 + k) * p.W + x0;
+					if (q[k].x != ~0ull) atomicMin(dst, q[k].x);      // clear keys cannot win
+					if (q[k].y != ~0ull) atomicMin(dst + 1, q[k].y);
+				}
+			}
+		}
+		if (nPairs) __threadfence(); // this warp's reductions are performed before the block's tiles are re-read below
+		__syncthreads();
+		if (warp == 0 && lane == 0) pulled += nPairs;
 		for (uint32_t j = warp; j < cnt; j += kStripThreads / 32) {
 			const uint32_t t = base + j;
 			const uint32_t tx = t % p.tilesX, ty = (uint32_t)me + (uint32_t)N * (t / p.tilesX);
-			const uint32_t mask = sMask[j], peers = mask & ~(1u << me);
+			const uint32_t mask = sMask[j];
 			// second pass of a frame: a tile neither a peer nor this rank drew into since the first exchange still holds the merged
 			// keys the first exchange built its mips from — nothing to pull, nothing to rebuild
 			if (p.pass == 1 && !mask) continue;
-			pulled += __popc(peers);
 			const uint32_t x0 = tx * kTileW + lane * 2, y0 = ty * kTileH;
 			const bool colIn = x0 < p.W;
-			// 1. merge
-			if (peers && colIn) {
-				constexpr int kRows = 4; // rows per round trip: small enough to leave the kernel at 64 registers (4 blocks per SM)
-#pragma unroll 1
-				for (int part = 0; part < kTileH / kRows; ++part) {
-					ulonglong2 acc[kRows]; // the owner's rows, then the running minimum
-#pragma unroll
-					for (int k = 0; k < kRows; ++k) {
-						const uint32_t y = y0 + part * kRows + k;
-						acc[k] = make_ulonglong2(~0ull, ~0ull);
-						if (y < p.H) acc[k] = __ldcg((const ulonglong2*)(vis + (size_t)y * p.W + x0));
-					}
-					uint32_t changed = 0; // bit k: row k took a peer's key
-					for (uint32_t m = peers; m; m &= m - 1) {
-						const unsigned long long* pv = p.mp.vis[__ffs(m) - 1];
-						ulonglong2 q[kRows];
-#pragma unroll
-						for (int k = 0; k < kRows; ++k) {
-							const uint32_t y = y0 + part * kRows + k;
-							q[k] = make_ulonglong2(~0ull, ~0ull);
-							if (y < p.H) q[k] = __ldcg((const ulonglong2*)(pv + (size_t)y * p.W + x0));
-						}
-#pragma unroll
-						for (int k = 0; k < kRows; ++k) {
-							if (q[k].x < acc[k].x) { acc[k].x = q[k].x; changed |= 1u << k; }
-							if (q[k].y < acc[k].y) { acc[k].y = q[k].y; changed |= 1u << k; }
-						}
-					}
-#pragma unroll
-					for (int k = 0; k < kRows; ++k)
-						if (changed & (1u << k)) __stcg((ulonglong2*)(vis + (size_t)(y0 + part * kRows + k) * p.W + x0), acc[k]);
-				}
-			}
-			__syncwarp();
 			// 2. exact mips of the merged tile -> every rank's pyramid, changed texels only (all pyramids are identical before this
 			// frame's stores, so the local copy tells whether a texel changes anywhere).  Which texels this lane owns depends on the
 			// tile and the lane only, so their old values are requested together with the tile's rows.
@@ -136,7 +142,7 @@ __global__ void __launch_bounds__(kStripThreads, 4) strip_merge_hiz_kernel(const
 	if (p.stats) {
 		for (int o = 16; o; o >>= 1) sent += __shfl_xor_sync(0xffffffffu, sent, o);
 		if (lane == 0) {
-			if (pulled) atomicAdd(p.stats, pulled);
+			if (pulled) atomicAdd(p.stats, pulled); // non-zero in warp 0 only
 			if (sent) atomicAdd(p.stats + 1, sent);
 		}
 	}
