@@ -39,6 +39,7 @@ CONFIGS = {
     5: ("cfg5: 22x22x21 lattice (1.02B tris), 7680x4320", dict(kind="lattice", n=(22, 22, 21), quads=224), (7680, 4320)),
 }
 NVIEWS = 64
+SHARD_BLOCK_LOG2 = int(os.environ.get("VKV_SHARD_BLOCK_LOG2", "8"))   # range sharding: blocks of 2^k MeshletDraws dealt round-robin to the ranks
 
 
 def build_scene(spec):
@@ -114,7 +115,7 @@ def config_dict(label, W, H, cnt, passes, builder_note, world, shard):
     return {"workload": label, "resolution": [W, H], "meshlet_draws": cnt.draws, "triangles": cnt.triangles_instanced, "passes": passes,
             "meshlets": builder_note, "views": f"{NVIEWS}-view camera sweep, one view per step",
             "parallelism": ((f"GPU arm: views sharded over {world} GPU(s), scene replicated, no collective" if shard == "views" else
-                             f"GPU arm: one view, MeshletDraw list sharded over {world} GPU(s) in interleaved 2048-draw ranges, screen-strip owners "
+                             f"GPU arm: one view, MeshletDraw list sharded over {world} GPU(s) in interleaved 256-draw blocks, screen-strip owners "
                              "pull dirty visbuffer tiles over NVLink peer memory and all-gather the pyramid") +
                             "; reference arm: CPU port of the same path on all host cores, rank 0 only"),
             "l2": "GPU arm: 256 MB scratch written between timed frames (L2 flush), each frame timed by its own CUDA event pair; reference arm: n/a (CPU)"}
@@ -142,7 +143,7 @@ def roofline(dom, stages, ent, hbm, peak_src, traffic, clocks):
 
 def range_sharded_leg(rank, world, local_rank, dist, steps, builder_note):
     """BASELINE config 5 on `world` GPUs: ONE view of the 1.02-billion-triangle lattice at 7680x4320, the MeshletDraw list dealt to
-    the ranks in interleaved 2048-draw blocks, owners of interleaved 16-row screen strips pulling dirty tiles over NVLink and all-gathering the pyramid
+    the ranks in interleaved 256-draw blocks, owners of interleaved 16-row screen strips pulling dirty tiles over NVLink and all-gathering the pyramid
     (VKV_FRAME_MERGE_STRIPS, csrc/strips.cu).  Returns the `range_sharded` object of the JSON line (every rank computes it; rank 0
     prints): device-timed ms per frame (max over ranks), the merge stages, the same frames on ONE GPU for the speed-up, the
     NVLink bytes per frame against the all-reduce bound, and `merge_parity`: on EVERY rank, after the same three views rendered
@@ -191,14 +192,14 @@ def range_sharded_leg(rank, world, local_rank, dist, steps, builder_note):
 
     sharded = api.FRAME_TWO_PASS | api.FRAME_MERGE_STRIPS
     single = api.FRAME_TWO_PASS
-    r.set_shard_interleaved(rank, world, 11)
+    r.set_shard_interleaved(rank, world, SHARD_BLOCK_LOG2)
     multigpu.attach_peers(r, dist)
     # ---- parity first (three views from a cleared pyramid, sharded vs the same rank alone)
     sync_all()
     sweep(sharded, 2)
     h_strip, h_pyr = r.hash(0, rank, world), r.hash(1)
     sync_all()
-    r.set_shard_interleaved(0, 1, 11)   # the whole list on this GPU, no exchange
+    r.set_shard_interleaved(0, 1, SHARD_BLOCK_LOG2)   # the whole list on this GPU, no exchange
     sweep(single, 2)
     ok = (h_strip == r.hash(0, rank, world)) and (h_pyr == r.hash(1))
     # ---- one GPU: the same frames, device-timed (every rank measures; they are independent here)
@@ -207,7 +208,7 @@ def range_sharded_leg(rank, world, local_rank, dist, steps, builder_note):
     n1_ms, _, _, _ = sweep(single, n1, timed=True)
     sync_all()
     # ---- sharded: device-timed
-    r.set_shard_interleaved(rank, world, 11)
+    r.set_shard_interleaved(rank, world, SHARD_BLOCK_LOG2)
     sweep(sharded, 3)
     sync_all()
     ms, st, pulled, sent = sweep(sharded, steps, timed=True)
@@ -374,7 +375,7 @@ def main():
         r.upload_cones(scene)
         flags |= api.FRAME_CONE_CULL
     if shard == "range" and world > 1:
-        r.set_shard_interleaved(rank, world, 11)  # 2048-draw blocks round-robin: balances the surviving work (a contiguous half does not)
+        r.set_shard_interleaved(rank, world, SHARD_BLOCK_LOG2)  # 2048-draw blocks round-robin: balances the surviving work (a contiguous half does not)
         multigpu.attach_peers(r, dist)
         flags |= api.FRAME_MERGE if args.merge == "allreduce" else api.FRAME_MERGE_STRIPS
     # all cameras of the sweep resident in HBM: the device-timed loop switches the camera ADDRESS per frame

@@ -46,11 +46,9 @@ __global__ void __launch_bounds__(kStripThreads, 4) strip_merge_hiz_kernel(const
 	const uint32_t nTiles = strip_tile_rows_owned(p.tilesY, me, N) * p.tilesX; // tile t of this rank: tile row me + N * (t / tilesX)
 	// barrier in: this kernel starts when THIS rank's raster pass is complete (stream order); block 0 says so to every rank, and
 	// every block waits until all ranks have said so (polling this rank's own slots)
-#ifndef VKV_X_NO_IN
 	if (blockIdx.x == 0 && (int)threadIdx.x < N) xgpu_signal(p.mp.flags, me, threadIdx.x, p.epoch_in);
 	if ((int)threadIdx.x < N) xgpu_wait(p.mp.flags[me], threadIdx.x, p.epoch_in, p.timeout_ns, p.mp.error);
 	__syncthreads();
-#endif
 	const HizTileGeo geo = {p.W, p.H, p.exact_levels, {p.pyr.off[0], p.pyr.off[1], p.pyr.off[2], p.pyr.off[3]}, {p.pyr.w[0], p.pyr.w[1], p.pyr.w[2], p.pyr.w[3]}};
 	unsigned long long* const vis = p.mp.vis[me];
 	const float* const localPyr = p.mp.pyr[me];
@@ -151,9 +149,7 @@ __global__ void __launch_bounds__(kStripThreads, 4) strip_merge_hiz_kernel(const
 	__shared__ uint32_t sLast;
 	__syncthreads();
 	if (threadIdx.x == 0) {
-#ifndef VKV_X_NO_FENCE
 		__threadfence_system(); // this block's peer stores before the ticket
-#endif
 		const uint32_t ticket = atomicAdd(p.done, 1u);
 		sLast = (ticket == gridDim.x - 1) ? 1u : 0u;
 		if (sLast) *p.done = 0u;
