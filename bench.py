@@ -39,7 +39,7 @@ CONFIGS = {
     5: ("cfg5: 22x22x21 lattice (1.02B tris), 7680x4320", dict(kind="lattice", n=(22, 22, 21), quads=224), (7680, 4320)),
 }
 NVIEWS = 64
-SHARD_BLOCK_LOG2 = int(os.environ.get("VKV_SHARD_BLOCK_LOG2", "8"))   # range sharding: blocks of 2^k MeshletDraws dealt round-robin to the ranks
+SHARD_BLOCK_LOG2 = int(os.environ.get("VKV_SHARD_BLOCK_LOG2", "11"))   # range sharding: blocks of 2^k MeshletDraws dealt round-robin to the ranks
 
 
 def build_scene(spec):
@@ -115,7 +115,7 @@ def config_dict(label, W, H, cnt, passes, builder_note, world, shard):
     return {"workload": label, "resolution": [W, H], "meshlet_draws": cnt.draws, "triangles": cnt.triangles_instanced, "passes": passes,
             "meshlets": builder_note, "views": f"{NVIEWS}-view camera sweep, one view per step",
             "parallelism": ((f"GPU arm: views sharded over {world} GPU(s), scene replicated, no collective" if shard == "views" else
-                             f"GPU arm: one view, MeshletDraw list sharded over {world} GPU(s) in interleaved 256-draw blocks, screen-strip owners "
+                             f"GPU arm: one view, MeshletDraw list sharded over {world} GPU(s) in interleaved 2048-draw blocks, screen-strip owners "
                              "pull dirty visbuffer tiles over NVLink peer memory and all-gather the pyramid") +
                             "; reference arm: CPU port of the same path on all host cores, rank 0 only"),
             "l2": "GPU arm: 256 MB scratch written between timed frames (L2 flush), each frame timed by its own CUDA event pair; reference arm: n/a (CPU)"}
@@ -143,7 +143,7 @@ def roofline(dom, stages, ent, hbm, peak_src, traffic, clocks):
 
 def range_sharded_leg(rank, world, local_rank, dist, steps, builder_note):
     """BASELINE config 5 on `world` GPUs: ONE view of the 1.02-billion-triangle lattice at 7680x4320, the MeshletDraw list dealt to
-    the ranks in interleaved 256-draw blocks, owners of interleaved 16-row screen strips pulling dirty tiles over NVLink and all-gathering the pyramid
+    the ranks in interleaved 2048-draw blocks, owners of interleaved 16-row screen strips pulling dirty tiles over NVLink and all-gathering the pyramid
     (VKV_FRAME_MERGE_STRIPS, csrc/strips.cu).  Returns the `range_sharded` object of the JSON line (every rank computes it; rank 0
     prints): device-timed ms per frame (max over ranks), the merge stages, the same frames on ONE GPU for the speed-up, the
     NVLink bytes per frame against the all-reduce bound, and `merge_parity`: on EVERY rank, after the same three views rendered

@@ -13,7 +13,7 @@ views = [scene.default_view(i, 64) for i in range(8)]
 cam = Camera(W, H).look_at(*views[0])
 r = api.Renderer(W, H, device=local)
 pc = r.upload_scene(scene, cam)
-r.set_shard_interleaved(rank, world, int(os.environ.get("VKV_SHARD_BLOCK_LOG2", "8")))
+r.set_shard_interleaved(rank, world, int(os.environ.get("VKV_SHARD_BLOCK_LOG2", "11")))
 multigpu.attach_peers(r, dist)
 lines = []
 for k in range(NF):
