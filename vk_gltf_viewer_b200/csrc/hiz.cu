@@ -247,6 +247,8 @@ __global__ void __launch_bounds__(kHizWarps * 32) hiz_tiled_kernel(const HizPara
 	const uint32_t lane = threadIdx.x & 31;
 	const uint32_t tilesX = (p.W + kTileW - 1) / kTileW, tilesY = (p.H + kTileH - 1) / kTileH;
 	const uint32_t nTiles = tilesX * tilesY;
+	// launched with programmatic stream serialization behind the raster's drain kernel (vkv_frame): set up early, start when it is done
+	asm volatile("griddepcontrol.wait;" ::: "memory");
 	const HizTileGeo geo = {p.W, p.H, p.exact_levels, {p.pyr.off[0], p.pyr.off[1], p.pyr.off[2], p.pyr.off[3]}, {p.pyr.w[0], p.pyr.w[1], p.pyr.w[2], p.pyr.w[3]}};
 	float* const pyramid = p.pyramid;
 	for (uint32_t tile = blockIdx.x * kHizWarps + (threadIdx.x >> 5); tile < nTiles; tile += gridDim.x * kHizWarps) {
@@ -287,6 +289,16 @@ static void launch_tail(const HizParams& p, cudaStream_t stream) {
 	else hiz_tail_kernel<<<1, 1024, kTailSmemBytes, stream>>>(p, p.exact_levels);
 }
 
+static cudaError_t launch_tiled(const HizParams& p, uint32_t grid, cudaStream_t stream) {
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kHizWarps * 32); cfg.dynamicSmemBytes = kTailSmemBytes; cfg.stream = stream;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attr[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = attr; cfg.numAttrs = 1;
+	return cudaLaunchKernelEx(&cfg, hiz_tiled_kernel, p);
+}
+
 cudaError_t launch_hiz(const HizParams& p, int num_sms, cudaStream_t stream, int* launches) {
 	// function attributes are per device: a process may hold contexts on several GPUs (vkv_create(device = k))
 	static bool attrSet[64] = {};
@@ -306,12 +318,12 @@ cudaError_t launch_hiz(const HizParams& p, int num_sms, cudaStream_t stream, int
 		if (tail_wants_spreading(p)) { // 8K and up: tiles without the in-kernel tail, then the tail with its first level spread over 32 blocks
 			HizParams q = p;
 			q.done = nullptr;
-			hiz_tiled_kernel<<<grid, kHizWarps * 32, kTailSmemBytes, stream>>>(q);
+			launch_tiled(q, grid, stream);
 			launch_tail(p, stream);
 			if (launches) *launches += 2;
 			return cudaGetLastError();
 		}
-		hiz_tiled_kernel<<<grid, kHizWarps * 32, kTailSmemBytes, stream>>>(p); // its last block runs the tail
+		launch_tiled(p, grid, stream); // its last block runs the tail
 		if (launches) ++*launches;
 		if (!p.done && p.split_tail && p.exact_levels < p.pyr.levels) { // diagnosis: tail as a second launch
 			hiz_tail_kernel<<<1, 1024, kTailSmemBytes, stream>>>(p, p.exact_levels);

@@ -72,6 +72,12 @@ struct WarpScratch {
 	uint32_t surv[128];              // phase-1 survivors: ia | ib << 8 | ic << 16 | triangle << 24 | needsClip << 31
 	float2 mvp2[4][4];               // cp.async landing zone: mvp[row][column], every element twice (f32x2 operand for two vertices)
 	MeshletHdr hdr[kBatch];
+#ifdef VKV_RASTER_BULK
+	// bulk-async (TMA) landing zones: the 16-byte-aligned windows enclosing a meshlet's triangle bytes / vertex-index list, double buffered
+	alignas(16) unsigned char tri_raw[2][416];   // <= 15 + 124 * 3 bytes, rounded up to 16
+	alignas(16) unsigned char vidx_raw[2][288];  // <= 12 + 64 * 4 bytes, rounded up to 16
+	alignas(8) unsigned long long mbar[4];       // completion barriers: tri_raw[0], tri_raw[1], vidx_raw[0], vidx_raw[1]
+#endif
 };
 struct SlowScratch { Tri sub[8]; int nsub; }; // the overflow re-walk's clipper output (raster_big_kernel only)
 
@@ -85,6 +91,21 @@ __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+#ifdef VKV_RASTER_BULK
+// cp.async.bulk (the TMA unit's linear copy): one elected lane moves a 16-byte-aligned window global -> shared and an mbarrier counts
+// the bytes in; SASS: UBLKCP + SYNCS.  The vertex positions stay with LDGSTS: they are a gather through the index list.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)) : "memory"); }
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // earlier generic-proxy reads of the landing zone are ordered before the async write
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+	asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@!p bra WAIT_%=;\n}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+#endif
 
 __device__ __forceinline__ bool top_left(int dx, int dy) { return dy < 0 || (dy == 0 && dx > 0); }
 
@@ -361,6 +382,14 @@ __device__ __forceinline__ void meshlet_loop(const RasterParams& p, WarpScratch&
 	const uint32_t count = __ldg(p.count);
 	const float hw = (float)p.W * 0.5f, hh = (float)p.H * 0.5f;
 	const uint32_t below = (1u << lane) - 1u;
+#ifdef VKV_RASTER_BULK
+	if (lane == 0) {
+		for (int b = 0; b < 4; ++b) mbar_init(&ws.mbar[b]);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncwarp();
+	uint32_t phases = 0; // bit b: the parity mbar[b]'s next completion will have
+#endif
 
 	// meshlets per work-stealing grab: kBatch when there is plenty of work (the header chain's latency is paid once per batch);
 	// fewer when the list is short, so that a small scene spreads over all warps instead of queueing 4 deep behind a few
@@ -402,14 +431,35 @@ __device__ __forceinline__ void meshlet_loop(const RasterParams& p, WarpScratch&
 		__syncwarp();
 
 		uint32_t vi0 = 0, vi1 = 0; // vertex indices (slots lane, lane+32) of the meshlet whose copies are issued next
-		auto load_indices = [&](const MeshletHdr& h) {
+#ifdef VKV_RASTER_BULK
+		// the index list as ONE bulk copy issued by lane 0 into vidx_raw[buf]; fetch_indices() reads it back once its barrier completes
+		auto load_indices = [&](const MeshletHdr& h, uint32_t buf) {
+			if (lane == 0) {
+				const uintptr_t a = (uintptr_t)h.vidx;
+				const uint32_t off = (uint32_t)(a & 15), bytes = (off + (h.counts & 0xffu) * 4u + 15u) & ~15u;
+				bulk_load(ws.vidx_raw[buf], (const void*)(a - off), bytes, &ws.mbar[2 + buf]);
+			}
+		};
+		auto fetch_indices = [&](const MeshletHdr& h, uint32_t buf) {
+			mbar_wait(&ws.mbar[2 + buf], (phases >> (2 + buf)) & 1u);
+			phases ^= 1u << (2 + buf);
+			const uint32_t vc = h.counts & 0xffu;
+			const uint32_t* v = (const uint32_t*)(ws.vidx_raw[buf] + ((uintptr_t)h.vidx & 15));
+			if (lane < vc) vi0 = v[lane];
+			if (lane + 32 < vc) vi1 = v[lane + 32];
+		};
+#else
+		auto load_indices = [&](const MeshletHdr& h, uint32_t) {
 			const uint32_t vc = h.counts & 0xffu;
 			if (lane < vc) vi0 = __ldg(h.vidx + lane);
 			if (lane + 32 < vc) vi1 = __ldg(h.vidx + lane + 32);
 		};
+		auto fetch_indices = [&](const MeshletHdr&, uint32_t) {};
+#endif
 		// positions (vi0/vi1 hold the meshlet's indices), triangle index words and mvp: global -> shared, asynchronously
 		auto issue_copies = [&](const MeshletHdr& h, uint32_t buf) {
 			const uint32_t vc = h.counts & 0xffu, tc = (h.counts >> 8) & 0xffu;
+			fetch_indices(h, buf);
 			if (h.counts & (1u << 18)) { // 16-bit positions: one 8-byte copy per vertex into the same landing zone, vertex v at bytes [8v, 8v + 8)
 				const uint2* qv = (const uint2*)h.verts;
 				if (lane < vc) cp_async8((uint2*)ws.pos + lane, qv + vi0);
@@ -425,8 +475,18 @@ __device__ __forceinline__ void meshlet_loop(const RasterParams& p, WarpScratch&
 					cp_async4(&ws.pos[lane * 2 + 1], q); cp_async4(&ws.pos[(32 + lane) * 2 + 1], q + 1); cp_async4(&ws.pos[(64 + lane) * 2 + 1], q + 2);
 				}
 			}
+#ifdef VKV_RASTER_BULK
+			if (lane == 0) { // the triangle bytes as ONE bulk copy of their enclosing 16-byte-aligned window (any alignment of the slice)
+				const uintptr_t a = (uintptr_t)h.tri;
+				const uint32_t off = (uint32_t)(a & 15), bytes = (off + tc * 3u + 15u) & ~15u;
+				bulk_load(ws.tri_raw[buf], (const void*)(a - off), bytes, &ws.mbar[buf]);
+			}
+			const uint32_t nWords = 0;
+			if (false) {
+#else
 			const uint32_t nWords = (tc * 3 + 3) >> 2;
 			if ((((uintptr_t)h.tri) & 3) == 0) {
+#endif
 				const uint32_t* w = (const uint32_t*)h.tri;
 #pragma unroll
 				for (uint32_t k = 0; k < 96; k += 32)
@@ -446,7 +506,7 @@ __device__ __forceinline__ void meshlet_loop(const RasterParams& p, WarpScratch&
 			}
 			cp_async_commit();
 		};
-		load_indices(ws.hdr[0]);
+		load_indices(ws.hdr[0], 0);
 		issue_copies(ws.hdr[0], 0);
 
 		for (uint32_t j = 0; j < nb; ++j) {
@@ -455,8 +515,12 @@ __device__ __forceinline__ void meshlet_loop(const RasterParams& p, WarpScratch&
 			const uint32_t vc = h.counts & 0xffu, tc = (h.counts >> 8) & 0xffu;
 			const bool doubleSided = (h.counts >> 16) & 1u, detNeg = (h.counts >> 17) & 1u;
 			// vertex indices of meshlet j+1: in flight during this meshlet's vertex phase
-			if (j + 1 < nb) load_indices(ws.hdr[j + 1]);
+			if (j + 1 < nb) load_indices(ws.hdr[j + 1], (j + 1) & 1);
 			cp_async_wait_all();
+#ifdef VKV_RASTER_BULK
+			mbar_wait(&ws.mbar[j & 1], (phases >> (j & 1)) & 1u);
+			phases ^= 1u << (j & 1);
+#endif
 			__syncwarp();
 
 			// :50-69 vertices.  A lane owns vertices `lane` and `lane + 32`; their transform, perspective divide and viewport
@@ -528,7 +592,11 @@ __device__ __forceinline__ void meshlet_loop(const RasterParams& p, WarpScratch&
 			if (j + 1 < nb) issue_copies(ws.hdr[j + 1], (j + 1) & 1);
 
 			// :73-103 triangles, phase 1: facing cull + trivial reject + bbox test, survivors compacted
+#ifdef VKV_RASTER_BULK
+			const uint8_t* tb = ws.tri_raw[j & 1] + ((uintptr_t)h.tri & 15);
+#else
 			const uint8_t* tb = (const uint8_t*)ws.tri_words[j & 1];
+#endif
 			uint32_t nSurv = 0;
 			for (uint32_t tbase = 0; tbase < tc; tbase += 32) {
 				const uint32_t t = tbase + lane;
@@ -626,6 +694,10 @@ __device__ __noinline__ void rewalk(const RasterParams& p, WarpScratch& ws, Slow
 __global__ void __launch_bounds__(kThreads, kMinBlocks) raster_kernel(const RasterParams p) {
 	__shared__ WarpScratch scratch[kWarpsPerBlock];
 	meshlet_loop<true>(p, scratch[threadIdx.x >> 5], nullptr, p.work, threadIdx.x & 31);
+	// Programmatic dependent launch: this warp is out of work.  Once every block has said so (or exited), the drain kernel behind
+	// this one — launched with programmatic stream serialization — may have its blocks placed on the SMs that fall idle during
+	// this kernel's tail; they wait in griddepcontrol.wait until the whole grid has completed and its writes are visible.
+	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
 // Grid barrier of the drain kernel (all its blocks are co-resident: the launch sizes the grid from the occupancy query).
@@ -655,7 +727,8 @@ __global__ void __launch_bounds__(kDrainThreads, VKV_DRAIN_MINB) raster_big_kern
 	__shared__ Tri sTriB[kDrainThreads / 32][32];
 #endif
 	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-
+	asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); // the pyramid build behind this kernel may set its blocks up early too
+	asm volatile("griddepcontrol.wait;" ::: "memory");              // raster_kernel has completed, its queue and its visbuffer writes are visible
 	// the three words that decide what there is to do, fetched together (one L2 round trip, not three): all are final when this
 	// kernel starts, except the queue cursor when the clip phase below appends pieces (re-read behind its barrier)
 	const uint32_t clipCountNow = *(volatile uint32_t*)p.clipCount;
@@ -831,9 +904,15 @@ cudaError_t launch_raster(const RasterParams& p, int num_sms, cudaStream_t strea
 		perSm[1] = n < 1 ? 1 : (n > 4 ? 4 : n);
 	}
 	raster_kernel<<<num_sms * perSm[0], kThreads, 0, stream>>>(p);
-	// every block co-resident (its clip phase ends in a grid barrier); exits at once when both queues are empty
-	raster_big_kernel<<<num_sms * perSm[1], kDrainThreads, 0, stream>>>(p);
-	return cudaGetLastError();
+	// every block co-resident (its clip phase ends in a grid barrier); exits at once when both queues are empty.  Launched with
+	// programmatic stream serialization: its blocks are set up under raster_kernel's tail (see there) instead of after it.
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3(num_sms * perSm[1]); cfg.blockDim = dim3(kDrainThreads); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attr[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = attr; cfg.numAttrs = 1;
+	return cudaLaunchKernelEx(&cfg, raster_big_kernel, p);
 }
 
 cudaError_t launch_fill64(unsigned long long* dst, size_t n, unsigned long long value, int num_sms, cudaStream_t stream) {
