@@ -285,9 +285,11 @@ RasterParams make_raster(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, const
 }
 
 // raster_kernel + raster_big_kernel behind a reset of the large-triangle queue
-int enqueue_raster(vkv_ctx* c, const RasterParams& r, int* launches) {
-	CK(cudaMemsetAsync(&c->counters->big_next, 0, offsetof(FrameCounters, raster_reset_end) - offsetof(FrameCounters, big_next), c->stream)); // queues, cursors, barrier
-	CK(launch_raster(r, c->num_sms, c->stream));
+// after_cull: the cull launch right before this call has zeroed the raster's counters itself (CullParams::reset_ptr) and nothing
+// sits between the two launches: the raster kernel is launched with programmatic stream serialization
+int enqueue_raster(vkv_ctx* c, const RasterParams& r, int* launches, bool after_cull = false) {
+	if (!after_cull) CK(cudaMemsetAsync(&c->counters->big_next, 0, offsetof(FrameCounters, raster_reset_end) - offsetof(FrameCounters, big_next), c->stream)); // queues, cursors, barrier
+	CK(launch_raster(r, c->num_sms, c->stream, after_cull));
 	if (launches) *launches += 2;
 	return VKV_OK;
 }
@@ -656,6 +658,10 @@ int vkv_frame(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, uint32_t flags, 
 		if (strips && p.n) { p.zero_ptr = (uint4*)c->dirty; p.zero_n16 = 2 * c->dirty_stride / 16; } // the dirty-tile flags ride along too
 		if (p.status) CK(cudaMemsetAsync(p.status, VKV_ST_NOT_TESTED, N, s));
 		c->status_valid[0] = p.status != nullptr;
+		if (p.n && !stages) { // (a stage event between cull and raster would separate the two launches anyway)
+			p.reset_ptr = &c->counters->big_next;
+			p.reset_words = (uint32_t)((offsetof(FrameCounters, raster_reset_end) - offsetof(FrameCounters, big_next)) / 4);
+		}
 		if (p.n) {
 			// the cone test reads the per-node eye positions in THIS launch: they need a launch of their own ahead of it
 			if (cone) { rc = prepare_transforms(c, pc, &launches, nullptr, true); if (rc) return rc; xf_done = true; p.xf_eye = c->xf_eye; }
@@ -665,8 +671,10 @@ int vkv_frame(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, uint32_t flags, 
 	}
 	mark(E_CULL_A);
 	if (strips && !pa.zero_ptr) CK(cudaMemsetAsync(c->dirty, 0, 2 * (size_t)c->dirty_stride, s));
+	// cull A -> raster A back to back (no transform launch, no dirty-flag memset in between): the cull zeroed the raster's counters
+	const bool chainA = pa.reset_ptr != nullptr && xf_done && !(strips && !pa.zero_ptr);
 	if (!xf_done) { rc = prepare_transforms(c, pc, &launches); if (rc) return rc; }
-	rc = enqueue_raster(c, make_raster(c, pc, c->list_visible[0], &c->counters->visible[0], &c->counters->work[0], strips ? 0 : -1), &launches);
+	rc = enqueue_raster(c, make_raster(c, pc, c->list_visible[0], &c->counters->visible[0], &c->counters->work[0], strips ? 0 : -1), &launches, chainA);
 	if (rc) return rc;
 	mark(E_RASTER_A);
 	if (merge) { rc = enqueue_merge(c, &launches); if (rc) return rc; }
@@ -683,9 +691,14 @@ int vkv_frame(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, uint32_t flags, 
 		c->status_valid[1] = p.status != nullptr;
 		// nothing between the pyramid launch and this one (no stage event, no status memset, no merge): let it start under the tail
 		const bool pdl = hiz && !stages && !p.status && c->exact_levels >= 1 && !c->no_pdl && !strips;
+		const bool chainB = p.n && !stages;
+		if (chainB) {
+			p.reset_ptr = &c->counters->big_next;
+			p.reset_words = (uint32_t)((offsetof(FrameCounters, raster_reset_end) - offsetof(FrameCounters, big_next)) / 4);
+		}
 		if (p.n) { CK(launch_cull(p, c->num_sms, s, pdl)); ++launches; }
 		mark(E_CULL_B);
-		rc = enqueue_raster(c, make_raster(c, pc, c->list_visible[1], &c->counters->visible[1], &c->counters->work[1], strips ? 1 : -1), &launches);
+		rc = enqueue_raster(c, make_raster(c, pc, c->list_visible[1], &c->counters->visible[1], &c->counters->work[1], strips ? 1 : -1), &launches, chainB);
 		if (rc) return rc;
 		mark(E_RASTER_B);
 		if (merge) { rc = enqueue_merge(c, &launches); if (rc) return rc; }

@@ -33,6 +33,8 @@ struct CullParams {
 	int skip_frustum;            // pass B inside vkv_frame: every input draw already passed this frame's frustum test in pass A
 	const unsigned long long* cone_table; // optional cone cull: per primitive the address of its vkv_MeshletCone[] (NULL = off)
 	const float4* xf_eye;        // per transform: camera position in mesh space (transform_prologue), valid BEFORE this launch
+	uint32_t* reset_ptr;         // vkv_frame: the raster's queue counters (FrameCounters::big_next ..), zeroed by this launch instead of a memset
+	uint32_t reset_words;        // node of their own — so that the raster launch can follow this one directly (programmatic dependent launch)
 	uint4* zero_ptr;             // strip mode: the dirty-tile flags of both passes, zeroed by the same launch
 	uint32_t zero_n16;
 };
@@ -111,7 +113,7 @@ cudaError_t launch_cull(const CullParams& p, int num_sms, cudaStream_t stream, b
 cudaError_t launch_iota(const CullParams& p, uint32_t* out, uint32_t* count, int num_sms, cudaStream_t stream);
 cudaError_t launch_prepare_transforms(const float* transforms, const vkv_Camera* camera, uint32_t n, float* mvp, uint32_t* detNeg, float4* eye,
                                       int num_sms, cudaStream_t stream);
-cudaError_t launch_raster(const RasterParams& p, int num_sms, cudaStream_t stream);      // raster_kernel + raster_big_kernel
+cudaError_t launch_raster(const RasterParams& p, int num_sms, cudaStream_t stream, bool after_cull = false); // raster_kernel + raster_big_kernel; after_cull: programmatic dependent launch behind cull_kernel
 cudaError_t launch_hiz(const HizParams& p, int num_sms, cudaStream_t stream, int* launches);
 cudaError_t launch_fill64(unsigned long long* dst, size_t n, unsigned long long value, int num_sms, cudaStream_t stream);
 cudaError_t launch_fill32(uint32_t* dst, size_t n, uint32_t value, int num_sms, cudaStream_t stream);

@@ -693,6 +693,7 @@ __device__ __noinline__ void rewalk(const RasterParams& p, WarpScratch& ws, Slow
 
 __global__ void __launch_bounds__(kThreads, kMinBlocks) raster_kernel(const RasterParams p) {
 	__shared__ WarpScratch scratch[kWarpsPerBlock];
+	asm volatile("griddepcontrol.wait;" ::: "memory"); // vkv_frame launches this kernel right behind the cull: the survivor list is complete from here on
 	meshlet_loop<true>(p, scratch[threadIdx.x >> 5], nullptr, p.work, threadIdx.x & 31);
 	// Programmatic dependent launch: this warp is out of work.  Once every block has said so (or exited), the drain kernel behind
 	// this one — launched with programmatic stream serialization — may have its blocks placed on the SMs that fall idle during
@@ -890,7 +891,7 @@ cudaError_t launch_prepare_transforms(const float* transforms, const vkv_Camera*
 	return cudaGetLastError();
 }
 
-cudaError_t launch_raster(const RasterParams& p, int num_sms, cudaStream_t stream) {
+cudaError_t launch_raster(const RasterParams& p, int num_sms, cudaStream_t stream, bool after_cull) {
 	static int perSmOf[64][2] = {}; // per device (a process may hold contexts on several GPUs): hot kernel, drain kernel
 	int dev = 0;
 	cudaGetDevice(&dev);
@@ -903,7 +904,16 @@ cudaError_t launch_raster(const RasterParams& p, int num_sms, cudaStream_t strea
 		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, raster_big_kernel, kDrainThreads, 0);
 		perSm[1] = n < 1 ? 1 : (n > 4 ? 4 : n);
 	}
-	raster_kernel<<<num_sms * perSm[0], kThreads, 0, stream>>>(p);
+	cudaLaunchAttribute pdl[1];
+	pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	pdl[0].val.programmaticStreamSerializationAllowed = 1;
+	if (after_cull) {
+		cudaLaunchConfig_t hot = {};
+		hot.gridDim = dim3(num_sms * perSm[0]); hot.blockDim = dim3(kThreads); hot.dynamicSmemBytes = 0; hot.stream = stream;
+		hot.attrs = pdl; hot.numAttrs = 1;
+		cudaError_t e = cudaLaunchKernelEx(&hot, raster_kernel, p);
+		if (e != cudaSuccess) return e;
+	} else raster_kernel<<<num_sms * perSm[0], kThreads, 0, stream>>>(p);
 	// every block co-resident (its clip phase ends in a grid barrier); exits at once when both queues are empty.  Launched with
 	// programmatic stream serialization: its blocks are set up under raster_kernel's tail (see there) instead of after it.
 	cudaLaunchConfig_t cfg = {};
