@@ -434,31 +434,62 @@ def main():
     # both every frame: camera.cpp:180-193, world.cpp:321-344) and D2H of the frame's counters (vkv_stats); `e2e_readback` adds the
     # D2H of the whole R32_UINT id image (vkv_read_ids), i.e. "result back on the host" for a CPU consumer
     import torch
+    FO = 3  # frames in flight = the reference's Application::frameOverlap (application.hpp:146): per-slot camera / transform buffers, slot k
+    # is waited for (vkv_frame_wait <-> the frame fence, application.cpp:642-660) just before it is reused
     transforms = np.ascontiguousarray(scene.transforms())
     pin_tr = torch.from_numpy(transforms.reshape(-1).copy()).pin_memory()
-    pin_cam = torch.zeros(352, dtype=torch.uint8).pin_memory()
+    pin_cam = [torch.zeros(352, dtype=torch.uint8).pin_memory() for _ in range(FO)]
     pin_ids = torch.zeros(W * H, dtype=torch.int32).pin_memory()
-    cam_np = pin_cam.numpy()
-    own_cam = r.upload(np.frombuffer(cam.raw(), np.uint8))
-    pc.cameraBuffer = own_cam
+    cam_np = [t.numpy() for t in pin_cam]
+    slot_cam = [r.upload(np.frombuffer(cam.raw(), np.uint8)) for _ in range(FO)]
+    slot_tr = [pc.transformBuffer] + [r.upload(transforms.reshape(-1).view(np.uint8)) for _ in range(FO - 1)]
     h2d = 352 + transforms.nbytes
     d2h = 256
+    e2e_visible = [0]
 
     def e2e_loop(n, readback):
+        """every step: camera + node transforms copied from pinned host memory (vkv_update_staged), the frame, its counters copied back
+        and consumed on the host (vkv_frame_wait) — FO frames in flight, as Application::run() keeps them"""
         barrier()
         t0 = time.perf_counter()
+        tickets = [0] * FO
         for k in range(n):
+            sl = k % FO
+            if tickets[sl]:
+                e2e_visible[0] += r.frame_wait(tickets[sl]).visible_a   # the slot's fence: its buffers and pinned staging are free again
             cam.look_at(*my_views[1 + (warm + k) % (len(my_views) - 1)])
-            cam_np[:] = np.frombuffer(cam.raw(), np.uint8)
-            r._ck(r.L.vkv_update(r.h, own_cam, pin_cam.data_ptr(), 352))
-            r._ck(r.L.vkv_update(r.h, pc.transformBuffer, pin_tr.data_ptr(), transforms.nbytes))
-            r.frame(pc, flags)  # returns vkv_stats: blocking D2H of the counters
-            if readback:
+            cam_np[sl][:] = np.frombuffer(cam.raw(), np.uint8)
+            r.update_staged(slot_cam[sl], pin_cam[sl].data_ptr(), 352)
+            r.update_staged(slot_tr[sl], pin_tr.data_ptr(), transforms.nbytes)
+            pc.cameraBuffer, pc.transformBuffer = slot_cam[sl], slot_tr[sl]
+            if readback:  # a CPU consumer of the id image cannot run ahead of it: blocking frame + blocking image copy
+                r.frame(pc, flags)
                 r._ck(r.L.vkv_read_ids(r.h, pin_ids.data_ptr()))
+            else:
+                tickets[sl] = r.frame_submit(pc, flags)
+        for t in tickets:
+            if t:
+                e2e_visible[0] += r.frame_wait(t).visible_a
         barrier()
         return time.perf_counter() - t0
 
+    def e2e_blocking_loop(n):
+        """the same uploads and read-back with ONE frame in flight (vkv_update + blocking vkv_frame): round 1's e2e definition"""
+        barrier()
+        t0 = time.perf_counter()
+        pc.cameraBuffer, pc.transformBuffer = slot_cam[0], slot_tr[0]
+        for k in range(n):
+            cam.look_at(*my_views[1 + (warm + k) % (len(my_views) - 1)])
+            cam_np[0][:] = np.frombuffer(cam.raw(), np.uint8)
+            r._ck(r.L.vkv_update(r.h, slot_cam[0], pin_cam[0].data_ptr(), 352))
+            r._ck(r.L.vkv_update(r.h, slot_tr[0], pin_tr.data_ptr(), transforms.nbytes))
+            r.frame(pc, flags)
+        barrier()
+        return time.perf_counter() - t0
+
+    e2e_loop(min(steps, 8), False)  # warm the slots
     e2e_s = e2e_loop(steps, False)
+    e2e_blk_s = e2e_blocking_loop(steps)
     KR = min(steps, 50)
     e2e_rb_s = e2e_loop(KR, True)
 
@@ -477,9 +508,9 @@ def main():
 
     if dist is not None:
         import torch
-        t = torch.tensor([dev_ms, e2e_s, e2e_rb_s], device="cuda", dtype=torch.float64)
+        t = torch.tensor([dev_ms, e2e_s, e2e_rb_s, e2e_blk_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_s, e2e_rb_s = t.tolist()
+        dev_ms, e2e_s, e2e_rb_s, e2e_blk_s = t.tolist()
         ln = torch.tensor([launches, vis_a, vis_b, occ_a], device="cuda", dtype=torch.int64)
         dist.all_reduce(ln)
         launches = int(ln[0].item())
@@ -550,7 +581,10 @@ def main():
                     "avg_vertices_per_meshlet": round(avg_v, 2), "avg_triangles_per_meshlet": round(avg_t, 2),
                     "clear": "fused into the pass-A cull launch (its 8*W*H bytes are counted there)" if clear_fused else "separate launch"},
             "e2e": {"value": frames_total / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "note": "camera + all node transforms uploaded from pinned host memory every frame, frame counters read back every frame (wall clock, no L2 flush)"},
+                    "frames_in_flight": FO, "one_frame_in_flight": frames_total / e2e_blk_s,
+                    "note": "wall clock, no L2 flush; every frame: camera + all node transforms copied from pinned host memory (vkv_update_staged), frame "
+                            "(vkv_frame_submit), its counters copied back and read on the host (vkv_frame_wait); frames in flight = the reference's frameOverlap "
+                            "(application.hpp:146). one_frame_in_flight = the same with vkv_update + blocking vkv_frame"},
             "e2e_readback": {"value": (world * KR if shard == "views" else KR) / e2e_rb_s, "unit": "frames/s", "steps": KR, "h2d_bytes_per_step": h2d,
                              "d2h_bytes_per_step": d2h + 4 * W * H,
                              "note": "as e2e, plus the whole R32_UINT id image copied to pinned host memory every frame (vkv_read_ids): PCIe-bound"},

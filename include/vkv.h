@@ -94,6 +94,20 @@ int vkv_download(vkv_ctx*, uint64_t dev_addr, void* host, size_t bytes);        
 
 /* ---- per frame -------------------------------------------------------------------------------------------- */
 int vkv_frame(vkv_ctx*, const vkv_VisbufferPushConstants* pc, uint32_t flags, vkv_stats* out);
+/* Frames in flight.  The reference never waits for the frame it has just recorded: Application::run() keeps frameOverlap frames in
+ * flight, each with its own camera buffer / draw buffer / command pool, and waits on the fence of the frame slot it is about to reuse
+ * (application.cpp:133,153,167,642; camera.cpp:86, world.cpp:5-6).  The same shape here:
+ *   vkv_update_staged  copies from PINNED host memory on the context's upload stream, i.e. beside the kernels of the frame before;
+ *                      everything enqueued afterwards on the context (frames, stage calls, reads) waits for it.  The caller owns the
+ *                      hazard the reference owns too: the destination must not be read by a frame still in flight (use one camera /
+ *                      transform buffer per frame slot), and the pinned source must stay untouched until that frame has been waited for.
+ *   vkv_frame_submit   vkv_frame without the wait: enqueues the frame and the device->host copy of its counters, returns a ticket (!= 0).
+ *                      At most 4 tickets may be outstanding (VKV_ERR_LIMIT).  VKV_FRAME_TIMED / _STAGES are refused (blocking by nature).
+ *   vkv_frame_wait     blocks until that frame and its counters have arrived; fills `out` (may be NULL) exactly as vkv_frame does
+ *                      (the *_ms fields stay 0) and releases the ticket. */
+int vkv_update_staged(vkv_ctx*, uint64_t dev_addr, const void* pinned_host, size_t bytes);
+int vkv_frame_submit(vkv_ctx*, const vkv_VisbufferPushConstants* pc, uint32_t flags, uint32_t* ticket);
+int vkv_frame_wait(vkv_ctx*, uint32_t ticket, vkv_stats* out);
 /* Side buffer of the optional cone cull (VKV_FRAME_CONE_CULL): device address of a table with one entry per primitive — the address
  * of that primitive's vkv_MeshletCone[meshletCount] (vkv_abi.h; vkvh_scene_upload_cones builds both).  0 removes it. */
 int vkv_set_cone_table(vkv_ctx*, uint64_t table_dev_addr);

@@ -48,7 +48,7 @@ class Stats(C.Structure):
 EXPORTS = [
     "vkv_create", "vkv_resize", "vkv_destroy", "vkv_last_error", "vkv_set_stream", "vkv_sync",
     "vkv_upload", "vkv_update", "vkv_free",
-    "vkv_frame", "vkv_clear", "vkv_cull", "vkv_raster", "vkv_hiz", "vkv_raster_list",
+    "vkv_frame", "vkv_frame_submit", "vkv_frame_wait", "vkv_update_staged", "vkv_clear", "vkv_cull", "vkv_raster", "vkv_hiz", "vkv_raster_list",
     "vkv_read_visbuffer64", "vkv_read_ids", "vkv_read_depth", "vkv_read_hiz_mip", "vkv_read_pyramid", "vkv_write_pyramid",
     "vkv_read_visible", "vkv_read_status", "vkv_pyramid_floats",
     "vkv_event_record", "vkv_event_elapsed", "vkv_flush_l2", "vkv_visbuffer64_ptr",
@@ -81,6 +81,9 @@ def _lib():
         L.vkv_update.argtypes = [vp, u64, vp, C.c_size_t]
         L.vkv_free.argtypes = [vp, u64]
         L.vkv_frame.argtypes = [vp, PC, u32, C.POINTER(Stats)]
+        L.vkv_frame_submit.argtypes = [vp, PC, u32, C.POINTER(u32)]
+        L.vkv_frame_wait.argtypes = [vp, u32, C.POINTER(Stats)]
+        L.vkv_update_staged.argtypes = [vp, u64, vp, C.c_size_t]
         L.vkv_clear.argtypes = [vp]
         L.vkv_cull.argtypes = [vp, PC, i, u32, C.POINTER(u32)]
         L.vkv_raster.argtypes = [vp, PC, i]
@@ -212,6 +215,21 @@ class Renderer:
         st = Stats() if stats else None
         self._ck(self.L.vkv_frame(self.h, C.byref(pc), flags, C.byref(st) if st is not None else None))
         return st
+
+    # frames in flight (application.cpp:133,642: frameOverlap frame slots, each waited for just before it is reused)
+    def frame_submit(self, pc, flags=FRAME_ONE_PASS) -> int:
+        t = C.c_uint32()
+        self._ck(self.L.vkv_frame_submit(self.h, C.byref(pc), flags, C.byref(t)))
+        return t.value
+
+    def frame_wait(self, ticket: int, stats=True):
+        st = Stats() if stats else None
+        self._ck(self.L.vkv_frame_wait(self.h, ticket, C.byref(st) if st is not None else None))
+        return st
+
+    def update_staged(self, dev_addr: int, pinned_ptr: int, nbytes: int):
+        """H2D from PINNED host memory on the upload stream (beside the previous frame's kernels); the next frame waits for it."""
+        self._ck(self.L.vkv_update_staged(self.h, dev_addr, pinned_ptr, nbytes))
 
     def clear(self):
         self._ck(self.L.vkv_clear(self.h))

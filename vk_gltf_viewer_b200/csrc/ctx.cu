@@ -78,6 +78,15 @@ struct vkv_ctx {
 	size_t flush_bytes = 0;
 	cudaEvent_t events[16] = {};
 	cudaEvent_t stage_ev[12] = {};
+	// frames in flight (vkv_frame_submit / vkv_frame_wait, vkv_update_staged): the reference keeps frameOverlap frames in flight with
+	// per-frame camera / draw buffers and fences (application.cpp:133,153,642); here a ring of pinned counter blocks + events
+	static constexpr uint32_t kFlights = 4;
+	struct Flight { cudaEvent_t done = nullptr; FrameCounters* h = nullptr; uint32_t ticket = 0, draws = 0, launches = 0; bool two = false; };
+	Flight flight[kFlights];
+	uint32_t next_ticket = 1;
+	cudaStream_t upload_stream = nullptr; // staged uploads run beside the previous frame's kernels
+	cudaEvent_t upload_ev = nullptr;
+	bool upload_pending = false;
 	std::map<uint64_t, size_t> allocs;
 	std::mutex mtx;
 	std::string err;
@@ -301,6 +310,15 @@ HizParams make_hiz(vkv_ctx* c) {
 	return h;
 }
 
+// staged uploads (vkv_update_staged) become visible to everything enqueued on the context's stream from here on
+int join_uploads(vkv_ctx* c) {
+	if (!c->upload_pending) return VKV_OK;
+	CK(cudaEventRecord(c->upload_ev, c->upload_stream));
+	CK(cudaStreamWaitEvent(c->stream, c->upload_ev, 0));
+	c->upload_pending = false;
+	return VKV_OK;
+}
+
 int check_pc(vkv_ctx* c, const vkv_VisbufferPushConstants* pc) {
 	if (!c) return VKV_ERR_INVALID;
 	if (!pc) return fail(c, VKV_ERR_INVALID, "push constants are NULL");
@@ -416,6 +434,13 @@ int vkv_create(vkv_ctx** out, int cuda_device, uint32_t width, uint32_t height) 
 		return bail(VKV_ERR_OOM);
 	}
 	cudaMemset(c->counters, 0, sizeof(FrameCounters));
+	for (auto& f : c->flight)
+		if (cudaEventCreateWithFlags(&f.done, cudaEventDisableTiming) != cudaSuccess || cudaMallocHost(&f.h, sizeof(FrameCounters)) != cudaSuccess) {
+			c->err = "allocating the frames-in-flight ring failed";
+			return bail(VKV_ERR_OOM);
+		}
+	if (cudaStreamCreateWithFlags(&c->upload_stream, cudaStreamNonBlocking) != cudaSuccess ||
+	    cudaEventCreateWithFlags(&c->upload_ev, cudaEventDisableTiming) != cudaSuccess) { c->err = "creating the upload stream failed"; return bail(VKV_ERR_CUDA); }
 	if (const char* e = getenv("VKV_BIG_CAP")) c->big_cap = (uint32_t)std::max(1L, std::min(1L << 22, atol(e)));
 	if (const char* e = getenv("VKV_CLIP_CAP")) c->clip_cap = (uint32_t)std::max(1L, std::min(1L << 22, atol(e)));
 	if (cudaMalloc(&c->big_tris, (size_t)c->big_cap * sizeof(BigTri)) != cudaSuccess || cudaMalloc(&c->clip_tris, (size_t)c->clip_cap * sizeof(ClipTri)) != cudaSuccess) {
@@ -457,6 +482,9 @@ void vkv_destroy(vkv_ctx* c) {
 	if (c->tmp_count) cudaFree(c->tmp_count);
 	if (c->counters) cudaFree(c->counters);
 	if (c->h_counters) cudaFreeHost(c->h_counters);
+	if (c->upload_stream) { cudaStreamSynchronize(c->upload_stream); cudaStreamDestroy(c->upload_stream); }
+	if (c->upload_ev) cudaEventDestroy(c->upload_ev);
+	for (auto& f : c->flight) { if (f.done) cudaEventDestroy(f.done); if (f.h) cudaFreeHost(f.h); }
 	if (c->flush_buf) cudaFree(c->flush_buf);
 	for (auto& kv : c->allocs) cudaFree((void*)(uintptr_t)kv.first);
 	for (auto& ev : c->events) if (ev) cudaEventDestroy(ev);
@@ -475,6 +503,7 @@ int vkv_set_stream(vkv_ctx* c, void* s) {
 int vkv_sync(vkv_ctx* c) {
 	if (!c) return VKV_ERR_INVALID;
 	CK(cudaSetDevice(c->device));
+	{ int rc = join_uploads(c); if (rc) return rc; }
 	CK(cudaStreamSynchronize(c->stream));
 	return check_merge_error(c);
 }
@@ -504,6 +533,21 @@ int vkv_update(vkv_ctx* c, uint64_t dev_addr, const void* host, size_t bytes) {
 	}
 	CK(cudaSetDevice(c->device));
 	CK(cudaMemcpyAsync((void*)(uintptr_t)dev_addr, host, bytes, cudaMemcpyHostToDevice, c->stream));
+	return VKV_OK;
+}
+
+int vkv_update_staged(vkv_ctx* c, uint64_t dev_addr, const void* pinned_host, size_t bytes) {
+	if (!c || !pinned_host) return VKV_ERR_INVALID;
+	{
+		std::lock_guard<std::mutex> lock(c->mtx);
+		auto it = c->allocs.upper_bound(dev_addr);
+		if (it == c->allocs.begin()) return fail(c, VKV_ERR_INVALID, "vkv_update_staged: unknown address");
+		--it;
+		if (dev_addr + bytes > it->first + it->second) return fail(c, VKV_ERR_INVALID, "vkv_update_staged: range exceeds the allocation");
+	}
+	CK(cudaSetDevice(c->device));
+	CK(cudaMemcpyAsync((void*)(uintptr_t)dev_addr, pinned_host, bytes, cudaMemcpyHostToDevice, c->upload_stream));
+	c->upload_pending = true; // the next frame / stage call on the context's stream waits for it (join_uploads)
 	return VKV_OK;
 }
 
@@ -610,10 +654,13 @@ int vkv_hiz(vkv_ctx* c) {
 	return VKV_OK;
 }
 
-int vkv_frame(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, uint32_t flags, vkv_stats* out) {
+namespace {
+int frame_impl(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, uint32_t flags, vkv_stats* out, uint32_t* launches_out) {
 	int rc = check_pc(c, pc);
 	if (rc) return rc;
 	CK(cudaSetDevice(c->device));
+	rc = join_uploads(c);
+	if (rc) return rc;
 	cudaStream_t s = c->stream;
 	const bool timed = (flags & VKV_FRAME_TIMED) && out;
 	const bool two = (flags & VKV_FRAME_TWO_PASS) && !(flags & VKV_FRAME_NO_CULL);
@@ -709,6 +756,7 @@ int vkv_frame(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, uint32_t flags, 
 		mark(E_HIZ_B);
 	}
 	if (timed) cudaEventRecord(c->stage_ev[E_COUNT], s); // end of frame (the per-stage events exist only with VKV_FRAME_STAGES)
+	if (launches_out) *launches_out = (uint32_t)launches;
 	if (out) {
 		memset(out, 0, sizeof(*out));
 		CK(cudaMemcpyAsync(c->h_counters, c->counters, sizeof(FrameCounters), cudaMemcpyDeviceToHost, s));
@@ -737,6 +785,50 @@ int vkv_frame(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, uint32_t flags, 
 			}
 		}
 	}
+	return VKV_OK;
+}
+} // namespace
+
+int vkv_frame(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, uint32_t flags, vkv_stats* out) { return frame_impl(c, pc, flags, out, nullptr); }
+
+/* Frames in flight.  The reference never waits for the frame it has just recorded: it keeps frameOverlap frames in flight, each with its
+ * own camera / draw buffers, and waits on the fence of the frame it is about to reuse (application.cpp:133,642-660).  vkv_frame_submit
+ * enqueues a frame plus the device->host copy of its counters into a pinned ring slot and returns; vkv_frame_wait blocks on that slot. */
+int vkv_frame_submit(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, uint32_t flags, uint32_t* ticket) {
+	if (!c || !ticket) return c ? fail(c, VKV_ERR_INVALID, "vkv_frame_submit: NULL argument") : VKV_ERR_INVALID;
+	if (flags & (VKV_FRAME_TIMED | VKV_FRAME_STAGES)) return fail(c, VKV_ERR_INVALID, "vkv_frame_submit: timed frames are blocking frames (vkv_frame)");
+	vkv_ctx::Flight& f = c->flight[c->next_ticket % vkv_ctx::kFlights];
+	if (f.ticket) return fail(c, VKV_ERR_LIMIT, "vkv_frame_submit: %u frames in flight already; vkv_frame_wait for ticket %u first", vkv_ctx::kFlights, f.ticket);
+	uint32_t launches = 0;
+	int rc = frame_impl(c, pc, flags, nullptr, &launches);
+	if (rc) return rc;
+	CK(cudaMemcpyAsync(f.h, c->counters, sizeof(FrameCounters), cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaEventRecord(f.done, c->stream));
+	f.ticket = c->next_ticket; f.draws = pc->meshletDrawCount; f.launches = launches;
+	f.two = (flags & VKV_FRAME_TWO_PASS) && !(flags & VKV_FRAME_NO_CULL);
+	*ticket = f.ticket;
+	if (++c->next_ticket == 0) c->next_ticket = 1; // 0 marks a free slot
+	return VKV_OK;
+}
+
+int vkv_frame_wait(vkv_ctx* c, uint32_t ticket, vkv_stats* out) {
+	if (!c || !ticket) return VKV_ERR_INVALID;
+	vkv_ctx::Flight& f = c->flight[ticket % vkv_ctx::kFlights];
+	if (f.ticket != ticket) return fail(c, VKV_ERR_INVALID, "vkv_frame_wait: ticket %u is not in flight", ticket);
+	CK(cudaSetDevice(c->device));
+	CK(cudaEventSynchronize(f.done));
+	if (out) {
+		memset(out, 0, sizeof(*out));
+		out->draws = f.draws;
+		out->visible_a = f.h->visible[0];
+		out->occluded_a = f.h->occluded[0];
+		out->visible_b = f.h->visible[1];
+		out->tested_b = f.two ? f.h->occluded[0] : 0;
+		out->kernel_launches = f.launches;
+		out->strip_tiles_pulled = f.h->strip_tiles_pulled;
+		out->strip_texels_sent = f.h->strip_texels_sent;
+	}
+	f.ticket = 0;
 	return VKV_OK;
 }
 
