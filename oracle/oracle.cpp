@@ -580,9 +580,15 @@ int orc_raster(const vkv_VisbufferPushConstants* pc, uint32_t W, uint32_t H, con
 	if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
 	if (threads < 1) threads = 1;
 	const vkv_Camera cam = *(const vkv_Camera*)pc->cameraBuffer;
-	// Phase 1: geometry + triangle setup, parallel over contiguous chunks of the draw list (order preserved)
+	// Phase 1: geometry + triangle setup, parallel over contiguous chunks of the draw list (order preserved).  Every chunk also bins
+	// its triangles by the horizontal bands of phase 2 (indices in submission order), so a band walks only what can touch it.
 	const int nchunks = std::max(1, std::min<int>(threads * 4, (int)n_draws));
+	const int bands = std::max(1, std::min<int>(threads * 8, (int)H));
+	std::vector<uint16_t> band_of(H);
+	for (int b = 0; b < bands; ++b)
+		for (size_t y = (size_t)H * b / bands, e = (size_t)H * (b + 1) / bands; y < e; ++y) band_of[y] = (uint16_t)b;
 	std::vector<std::vector<SetupTri>> lists(nchunks);
+	std::vector<std::vector<std::vector<uint32_t>>> bins(nchunks, std::vector<std::vector<uint32_t>>(bands));
 	std::vector<RasterStats> stats(nchunks);
 	std::atomic<int> next{0};
 	auto work1 = [&] {
@@ -590,7 +596,16 @@ int orc_raster(const vkv_VisbufferPushConstants* pc, uint32_t W, uint32_t H, con
 			int c = next.fetch_add(1);
 			if (c >= nchunks) break;
 			size_t b = (size_t)n_draws * c / nchunks, e = (size_t)n_draws * (c + 1) / nchunks;
-			for (size_t i = b; i < e; ++i) meshlet_setup(pc, draw_ids[i], cam, W, H, lists[c], stats[c]);
+			std::vector<SetupTri>& L = lists[c];
+			for (size_t i = b; i < e; ++i) {
+				const size_t first = L.size();
+				meshlet_setup(pc, draw_ids[i], cam, W, H, L, stats[c]);
+				for (size_t k = first; k < L.size(); ++k) {
+					const int ya = std::max(L[k].ymin, 0), yb = std::min(L[k].ymax, (int)H - 1);
+					if (ya > yb) continue;
+					for (int bb = band_of[ya]; bb <= band_of[yb]; ++bb) bins[c][bb].push_back((uint32_t)k);
+				}
+			}
 		}
 	};
 	{
@@ -599,9 +614,8 @@ int orc_raster(const vkv_VisbufferPushConstants* pc, uint32_t W, uint32_t H, con
 		work1();
 		for (auto& th : pool) th.join();
 	}
-	// Phase 2: pixels, parallel over horizontal bands; each band walks all triangles in submission order,
-	// so the result equals a sequential rasteriser.
-	const int bands = std::max(1, std::min<int>(threads * 8, (int)H));
+	// Phase 2: pixels, parallel over horizontal bands; each band walks its triangles in submission order (chunk by chunk, index by
+	// index), so the result equals a sequential rasteriser.
 	std::vector<uint64_t> frags(bands, 0), passed(bands, 0);
 	std::atomic<int> nextb{0};
 	auto work2 = [&] {
@@ -610,8 +624,7 @@ int orc_raster(const vkv_VisbufferPushConstants* pc, uint32_t W, uint32_t H, con
 			if (b >= bands) break;
 			int y0 = (int)((size_t)H * b / bands), y1 = (int)((size_t)H * (b + 1) / bands);
 			for (int c = 0; c < nchunks; ++c)
-				for (const SetupTri& t : lists[c])
-					if (t.ymax >= y0 && t.ymin < y1) raster_rows(t, y0, y1, W, depth, ids_ref, ids_min, tie, frags[b], passed[b]);
+				for (uint32_t k : bins[c][b]) raster_rows(lists[c][k], y0, y1, W, depth, ids_ref, ids_min, tie, frags[b], passed[b]);
 		}
 	};
 	{
