@@ -260,7 +260,7 @@ def meshlet_averages(scene):
     return (v / n, t / n) if n else (0.0, 0.0)
 
 
-def cpu_frames(scene, W, H, views, nframes, threads=0, warmup=1):
+def cpu_frames(scene, W, H, views, nframes, threads=0, warmup=1, stage_s=None):
     """the oracle (CPU port of the reference path) timed on the host cores: two-pass frames of the same sweep"""
     from tests import oracle_lib as O
     from vk_gltf_viewer_b200.scene import Camera
@@ -275,7 +275,7 @@ def cpu_frames(scene, W, H, views, nframes, threads=0, warmup=1):
     for k in range(nframes):
         cam.look_at(*views[(k + 1) % len(views)])
         t0 = time.perf_counter()
-        O.frame(pc, tg, two_pass=True, threads=threads)
+        O.frame(pc, tg, two_pass=True, threads=threads, stage_s=stage_s)
         times.append(time.perf_counter() - t0)
     return times
 
@@ -322,7 +322,8 @@ def main():
         views = [scene.default_view(i, NVIEWS) for i in range(NVIEWS)]
         steps = max(1, args.steps if args.steps is not None else 20)
         warm = max(1, min(args.warmup, 3))   # every warm-up is a full CPU frame (~0.5 s at cfg 3): at most 3, reported as run
-        times = cpu_frames(scene, W, H, views, steps, warmup=warm)
+        cpu_stage = {}
+        times = cpu_frames(scene, W, H, views, steps, warmup=warm, stage_s=cpu_stage)
         total = sum(times)
         fps = steps / total
         line = {
@@ -334,6 +335,7 @@ def main():
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": ncores, "kind": "port",
                              "sample": f"{steps} full two-pass frames of the same camera sweep (CPU oracle, all host threads)"},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "stages": {k: {"ms": round(1e3 * v / steps, 3)} for k, v in cpu_stage.items()},   # the same table as the GPU arm's `stages`, on the host cores
             "gpu_launches": 0,
         }
         print(json.dumps(line))
@@ -597,9 +599,11 @@ def main():
             line["range_sharded"] = range_leg
         if not args.no_cpu_baseline:
             nfr = 2 if args.config in (3, 5) else 5
-            ct = cpu_frames(scene, W, H, views, nfr)
+            cpu_stage = {}
+            ct = cpu_frames(scene, W, H, views, nfr, stage_s=cpu_stage)
             cfps = nfr / sum(ct)
             line["cpu_baseline"] = {"value": cfps, "unit": "frames/s", "cores": ncores, "kind": "port",
+                                    "stages_ms": {k: round(1e3 * v / nfr, 3) for k, v in cpu_stage.items()},
                                     "sample": f"{nfr} full two-pass frames of the same sweep after 1 warm-up frame (CPU oracle, all host threads)"}
         print(json.dumps(line))
     if r is not None:

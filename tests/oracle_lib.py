@@ -120,19 +120,29 @@ def visible_ids(status):
     return np.nonzero((status & STATUS_MASK) == VISIBLE)[0].astype(np.uint32)
 
 
-def frame(pc, tg: Targets, two_pass=False, threads=0, cones=None):
+def frame(pc, tg: Targets, two_pass=False, threads=0, cones=None, stage_s=None):
     """One frame as the reference records it (cull with the previous pyramid -> raster -> HiZ rebuild), or the two-pass
-    extension: A = reference pass; HiZ; B = re-test A's occlusion rejects with the current VP/pyramid; raster; HiZ."""
-    tg.clear()
+    extension: A = reference pass; HiZ; B = re-test A's occlusion rejects with the current VP/pyramid; raster; HiZ.
+    stage_s: optional dict accumulating wall seconds per stage (clear, cull_a, raster_a, hiz_a, cull_b, raster_b, hiz_b)."""
+    import time
+    t = [time.perf_counter()]
+
+    def lap(name):
+        if stage_s is not None:
+            now = time.perf_counter()
+            stage_s[name] = stage_s.get(name, 0.0) + (now - t[0])
+            t[0] = now
+
+    tg.clear(); lap("clear")
     stA, cA = cull(pc, tg.W, tg.H, tg.pyramid, 0, None, threads, cones)
-    visA = visible_ids(stA)
-    rA = raster(pc, tg, visA, threads)
-    hiz(tg, threads)
+    visA = visible_ids(stA); lap("cull_a")
+    rA = raster(pc, tg, visA, threads); lap("raster_a")
+    hiz(tg, threads); lap("hiz_a")
     out = {"statusA": stA, "visibleA": visA, "cullA": cA, "rasterA": rA}
     if two_pass:
         stB, cB = cull(pc, tg.W, tg.H, tg.pyramid, 1, stA, threads)
-        visB = visible_ids(stB)
-        rB = raster(pc, tg, visB, threads)
-        hiz(tg, threads)
+        visB = visible_ids(stB); lap("cull_b")
+        rB = raster(pc, tg, visB, threads); lap("raster_b")
+        hiz(tg, threads); lap("hiz_b")
         out.update({"statusB": stB, "visibleB": visB, "cullB": cB, "rasterB": rB})
     return out
