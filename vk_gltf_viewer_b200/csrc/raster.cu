@@ -42,8 +42,11 @@ constexpr int kBigTileW = VKV_BIG_TILE_W, kBigTileH = VKV_BIG_TILE_H;   // pixel
 #endif
 constexpr int kBigMinStamps = VKV_BIG_MIN_STAMPS;  // bbox of >= this many 8x4 stamps -> deferred
 #ifndef VKV_RASTER_BATCH
-#define VKV_RASTER_BATCH 4
-#endif
+#define VKV_RASTER_BATCH 2      // measured (profiles/r4b): 1 -> 0.3763 ms, 2 -> 0.3806, 3 -> 0.3952, 4 -> 0.4089, 8 -> 0.4690 on cfg 3: a meshlet
+#endif                          // occupies a warp for ~8 us, so whole batches leave the kernel's end ragged; 2 + the guided tail: 0.3658
+#ifndef VKV_RASTER_GUIDED
+#define VKV_RASTER_GUIDED 4     // guided self-scheduling: grabs shrink to single meshlets once less than this many grabs per warp are left (0 = off;
+#endif                          // profiles/r4c: 1 -> 0.3735, 2 -> 0.3682, 4 -> 0.3658)
 #ifndef VKV_RASTER_MIN_BLOCKS
 #define VKV_RASTER_MIN_BLOCKS 4
 #endif
@@ -394,12 +397,29 @@ __device__ __forceinline__ void meshlet_loop(const RasterParams& p, WarpScratch&
 	// meshlets per work-stealing grab: kBatch when there is plenty of work (the header chain's latency is paid once per batch);
 	// fewer when the list is short, so that a small scene spreads over all warps instead of queueing 4 deep behind a few
 	const uint32_t totalWarps = gridDim.x * (blockDim.x >> 5);
-	const uint32_t batch = kHot ? min((uint32_t)kBatch, max(1u, count / totalWarps)) : (uint32_t)kBatch;
+	const uint32_t batch0 = kHot ? min((uint32_t)kBatch, max(1u, count / totalWarps)) : (uint32_t)kBatch;
+	uint32_t batch = batch0;
+#if VKV_RASTER_GUIDED
+	uint32_t seen = 0; // where the cursor stood at this warp's last grab
+#endif
 	for (;;) {
+#if VKV_RASTER_GUIDED
+		// guided self-scheduling: a meshlet keeps a warp busy for microseconds, so a kernel that ends on whole batches ends ragged (the
+		// last warps still hold batch - 1 meshlets when the others run dry).  Grabs shrink as the list runs out: all warps have grabbed
+		// about once since `seen`, so about count - seen - totalWarps * batch meshlets are left; spread them VKV_RASTER_GUIDED grabs deep.
+		if (kHot) {
+			const uint32_t taken = seen + totalWarps * batch;
+			const uint32_t left = count > taken ? count - taken : 0u;
+			batch = min(batch0, max(1u, left / (totalWarps * (uint32_t)VKV_RASTER_GUIDED)));
+		}
+#endif
 		uint32_t base = 0;
 		if (lane == 0) base = atomicAdd(workCursor, batch);
 		base = __shfl_sync(0xffffffffu, base, 0);
 		if (base >= count) break;
+#if VKV_RASTER_GUIDED
+		seen = base;
+#endif
 		const uint32_t nb = min(batch, count - base);
 		// one lane per meshlet walks the dependent chain list -> draw -> primitive -> meshlet (mesh.glsl:31-36)
 		if (lane < nb) {
