@@ -506,3 +506,29 @@ def test_glb_asset_renders_bit_exactly():
     r.frame(pc, api.FRAME_TWO_PASS)
     compare_frame(r, tg, out, True, label="glb + int16")
     r.close()
+
+
+def test_partial_pass_b_pyramid_equals_the_full_rebuild(monkeypatch):
+    """vkv_frame's second pyramid build redoes only the 64x16-pixel tiles the pass-B rasteriser marked (small passes; a large pass B
+    switches the marks off on the device and every tile is redone).  VKV_HIZ_FULL_B=1 rebuilds everything: same bits, frame after frame."""
+    s = Scene.lattice(4, 3, 4, 48)
+    W, H = 1280, 720
+    views = [s.default_view(i, 24) for i in range(5)]
+    results = []
+    for full in ("0", "1"):
+        monkeypatch.setenv("VKV_HIZ_FULL_B", full)
+        cam = Camera(W, H)
+        cam.look_at(*views[0])
+        r = api.Renderer(W, H)
+        pc = r.upload_scene(s, cam)
+        frames = []
+        for v in views:
+            cam.look_at(*v)
+            r.update_camera(pc, cam)
+            st = r.frame(pc, api.FRAME_TWO_PASS)
+            frames.append((st.visible_a, st.occluded_a, st.visible_b, r.hash(0), r.hash(1)))
+        results.append((frames, r.read_pyramid().view(np.uint32).copy()))
+        r.close()
+    assert results[0][0] == results[1][0]
+    assert np.array_equal(results[0][1], results[1][1])
+    assert any(f[2] > 0 for f in results[0][0][1:])  # the camera moves: pass B draws something, so there are dirty tiles to redo

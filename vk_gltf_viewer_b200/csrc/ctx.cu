@@ -54,6 +54,7 @@ struct vkv_ctx {
 	bool sharded = false;
 	bool no_pdl = false;         // VKV_NO_PDL=1: launch the pass-B cull without programmatic stream serialization (A/B measurements)
 	bool separate_clear = false; // VKV_SEPARATE_CLEAR=1: keep the visbuffer clear a launch of its own (A/B measurements)
+	bool full_hiz_b = false;     // VKV_HIZ_FULL_B=1: the pass-B pyramid build redoes every tile, not only the ones pass B drew into (A/B measurements)
 	MergeParams mp{};
 	bool attached = false;
 	// exchange block: ONE allocation the peers map through CUDA IPC — barrier slots (kMaxRanks u32 + 1 error word, first 256 B),
@@ -276,7 +277,7 @@ CullParams make_cull(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, int pass,
 
 RasterParams make_raster(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, const uint32_t* list, const uint32_t* count, uint32_t* work, int mark_pass = -1) {
 	RasterParams r{};
-	if (mark_pass >= 0) { r.dirty = c->dirty + (size_t)mark_pass * c->dirty_stride; r.dirtyTilesX = c->tiles_x; } // strip mode
+	if (mark_pass >= 0) { r.dirty = c->dirty + (size_t)mark_pass * c->dirty_stride; r.dirtyTilesX = c->tiles_x; r.markLimit = 0xffffffffu; } // strip mode (vkv_frame lowers markLimit for the pass-B pyramid rebuild)
 	r.draws = (const vkv_MeshletDraw*)pc->drawBuffer;
 	r.transforms = (const float*)pc->transformBuffer;
 	r.primitives = (const vkv_Primitive*)pc->primitiveBuffer;
@@ -311,6 +312,11 @@ HizParams make_hiz(vkv_ctx* c) {
 }
 
 // staged uploads (vkv_update_staged) become visible to everything enqueued on the context's stream from here on
+// Pass-B pyramid rebuild: the rasteriser marks tiles (and the pyramid kernel skips clean ones) only while pass B draws at most this many
+// meshlets.  Measured (profiles/r4e, r4f): 7 k meshlets (cfg 3): pyramid B 29.1 -> 24 us for ~1-4 us of marks; 54 k (cfg 4): marks cost
+// 5-15 us and every tile is dirty anyway.
+constexpr uint32_t kPartialHizLimit = 16384;
+
 int join_uploads(vkv_ctx* c) {
 	if (!c->upload_pending) return VKV_OK;
 	CK(cudaEventRecord(c->upload_ev, c->upload_stream));
@@ -424,6 +430,7 @@ int vkv_create(vkv_ctx** out, int cuda_device, uint32_t width, uint32_t height) 
 	if (cudaGetDeviceProperties(&prop, cuda_device) == cudaSuccess) c->num_sms = prop.multiProcessorCount;
 	if (const char* e = getenv("VKV_SEPARATE_CLEAR")) c->separate_clear = e[0] == '1';
 	if (const char* e = getenv("VKV_NO_PDL")) c->no_pdl = e[0] == '1';
+	if (const char* e = getenv("VKV_HIZ_FULL_B")) c->full_hiz_b = e[0] == '1';
 	if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { c->err = "cudaStreamCreate failed"; return bail(VKV_ERR_CUDA); }
 	c->stream = c->own_stream;
 	for (auto& ev : c->events) cudaEventCreate(&ev);
@@ -743,16 +750,32 @@ int frame_impl(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, uint32_t flags,
 			p.reset_ptr = &c->counters->big_next;
 			p.reset_words = (uint32_t)((offsetof(FrameCounters, raster_reset_end) - offsetof(FrameCounters, big_next)) / 4);
 		}
+		// The second pyramid build only has to redo what pass B changes: the pass-B rasteriser marks every 64x16-pixel tile it may draw
+		// into (the dirty bytes of strip mode, set B), the tiled kernel skips the others — their exact mips were stored by the pass-A
+		// build a moment ago — and the small-mip tail runs as always.  The flags are zeroed by the pass-B cull launch.
+		const bool partialB = hiz && !strips && !merge && c->exact_levels >= 1 && !c->full_hiz_b;
+		uint8_t* const dirtyB = c->dirty + c->dirty_stride;
+		if (partialB) {
+			if (p.n) { p.zero_ptr = (uint4*)dirtyB; p.zero_n16 = c->dirty_stride / 16; }
+			else CK(cudaMemsetAsync(dirtyB, 0, c->dirty_stride, s));
+		}
 		if (p.n) { CK(launch_cull(p, c->num_sms, s, pdl)); ++launches; }
 		mark(E_CULL_B);
-		rc = enqueue_raster(c, make_raster(c, pc, c->list_visible[1], &c->counters->visible[1], &c->counters->work[1], strips ? 1 : -1), &launches, chainB);
+		RasterParams rb = make_raster(c, pc, c->list_visible[1], &c->counters->visible[1], &c->counters->work[1], (strips || partialB) ? 1 : -1);
+		if (partialB) rb.markLimit = kPartialHizLimit;
+		rc = enqueue_raster(c, rb, &launches, chainB);
 		if (rc) return rc;
 		mark(E_RASTER_B);
 		if (merge) { rc = enqueue_merge(c, &launches); if (rc) return rc; }
 		if (strips) { rc = enqueue_strip_exchange(c, 1, &launches); if (rc) return rc; }
 		mark(E_MERGE_B);
 		visB.end();
-		if (hiz && !strips) { Range z("HiZ reduction"); CK(launch_hiz(make_hiz(c), c->num_sms, s, &launches)); }
+		if (hiz && !strips) {
+			Range z("HiZ reduction");
+			HizParams hp = make_hiz(c);
+			if (partialB) { hp.tile_dirty = dirtyB; hp.dirty_count = &c->counters->visible[1]; hp.dirty_limit = kPartialHizLimit; }
+			CK(launch_hiz(hp, c->num_sms, s, &launches));
+		}
 		mark(E_HIZ_B);
 	}
 	if (timed) cudaEventRecord(c->stage_ev[E_COUNT], s); // end of frame (the per-stage events exist only with VKV_FRAME_STAGES)

@@ -251,7 +251,17 @@ __global__ void __launch_bounds__(kHizWarps * 32) hiz_tiled_kernel(const HizPara
 	asm volatile("griddepcontrol.wait;" ::: "memory");
 	const HizTileGeo geo = {p.W, p.H, p.exact_levels, {p.pyr.off[0], p.pyr.off[1], p.pyr.off[2], p.pyr.off[3]}, {p.pyr.w[0], p.pyr.w[1], p.pyr.w[2], p.pyr.w[3]}};
 	float* const pyramid = p.pyramid;
-	for (uint32_t tile = blockIdx.x * kHizWarps + (threadIdx.x >> 5); tile < nTiles; tile += gridDim.x * kHizWarps) {
+	const uint32_t firstTile = blockIdx.x * kHizWarps + (threadIdx.x >> 5), tileStride = gridDim.x * kHizWarps;
+	// Pass-B rebuild (vkv_frame, two-pass): only tiles the pass-B rasteriser marked can differ from what the pass-A build stored a few
+	// launches ago.  Lane k fetches the flag of the warp's k-th tile (one round trip for all of them), the ballot says which to redo.
+	uint32_t redo = 0xffffffffu;
+	if (p.tile_dirty && firstTile + 31ull * tileStride >= nTiles && __ldcg(p.dirty_count) <= p.dirty_limit) { // (a warp never has more than 32 tiles below 16K x 16K; beyond, rebuild all)
+		const uint32_t t = firstTile + lane * tileStride;
+		redo = __ballot_sync(0xffffffffu, t < nTiles && __ldcg(p.tile_dirty + t) != 0);
+	}
+	uint32_t k = 0;
+	for (uint32_t tile = firstTile; tile < nTiles; tile += tileStride, ++k) {
+		if (!((redo >> (k & 31u)) & 1u)) continue;
 		const uint32_t tx = tile % tilesX, ty = tile / tilesX;
 		ulonglong2 v[kTileH];
 		hiz_tile_load(p.vis, geo, tx, ty, lane, v);

@@ -91,6 +91,7 @@ struct RasterParams {
 	const vkv_QuantizedPositions* qtable; // optional: per primitive, its POSITION accessor in 16-bit form (NULL = read the f32 Vertex records)
 	uint8_t* dirty;              // strip mode: one byte per 64x16-pixel tile, set for every tile a drawn triangle's bbox touches (NULL otherwise)
 	uint32_t dirtyTilesX;
+	uint32_t markLimit;          // tiles are marked only while *count <= markLimit (strip mode: ~0u; pass-B pyramid rebuild: kPartialHizLimit)
 };
 
 struct HizParams {
@@ -101,6 +102,10 @@ struct HizParams {
 	uint32_t exact_levels;       // leading mips whose source is exactly 2x (handled by the tiled kernel), <= 4
 	uint32_t* done;              // FrameCounters::hiz_done (zero between launches)
 	int split_tail;              // diagnosis only: run the small mips as a second launch
+	const uint8_t* tile_dirty;   // pass-B rebuild: one byte per 64x16-pixel tile, set by the pass-B rasteriser for every tile it may have drawn
+	                             // into; clean tiles keep the exact mips the pass-A build stored a moment ago (NULL = rebuild every tile)
+	const uint32_t* dirty_count; // ... valid only if *dirty_count (pass B's survivor count) <= dirty_limit: the rasteriser stops marking above it
+	uint32_t dirty_limit;
 	// strip mode: the small-mip tail first waits for every rank's "my strip's mips are stored everywhere" signal (xgpu.cuh)
 	const uint32_t* wait_flags;  // this rank's flag slots (NULL = no wait)
 	uint32_t wait_epoch;
