@@ -367,6 +367,7 @@ def main():
 
     r = api.Renderer(W, H, device=local_rank)
     pyr_floats = r.pyramid_floats
+    r_layout = [(o, w, h) for (o, w, h) in r.layout]   # (offset, width, height) per mip
     cam = Camera(W, H)
     cam.look_at(*my_views[0])
     pc = r.upload_scene(scene, cam)
@@ -410,6 +411,7 @@ def main():
     stage_names = ("clear_ms", "cull_a_ms", "raster_a_ms", "merge_a_ms", "hiz_a_ms", "cull_b_ms", "raster_b_ms", "merge_b_ms", "hiz_b_ms")
     stage = {k: 0.0 for k in stage_names}
     vis_a = vis_b = occ_a = 0
+    hiz_tiles_b = 0
     launches = 0
     for k in range(steps):
         pc.cameraBuffer = cam_addrs[(warm + k) % len(cam_addrs)]
@@ -417,6 +419,7 @@ def main():
         st = r.frame(pc, flags | api.FRAME_TIMED)   # one event pair around the frame: nothing sits between its launches
         per.append(st.total_ms)
         vis_a += st.visible_a; vis_b += st.visible_b; occ_a += st.occluded_a
+        hiz_tiles_b += st.hiz_tiles_b
         launches += st.kernel_launches + 1  # + the L2-flush fill kernel
     barrier()
     t_end = time.time()
@@ -539,6 +542,12 @@ def main():
         bytes_cull_a = 12 * N + U + 4 * (avg(vis_a) + avg(occ_a))
         bytes_cull_b = 4 * avg(occ_a) + 12 * avg(occ_a) + U + 4 * avg(vis_b)
         bytes_hiz = 8 * W * H + pyr_bytes  # depth is read fused from the 64-bit visbuffer: 8 B/pixel, not 4
+        # the second build of a two-pass frame reduces only the 64x16-pixel tiles a small pass B drew into (vkv_stats.hiz_tiles_b, counted on
+        # the device): 8 KB read + 340 exact-mip texels written per tile, plus the small mips (always rebuilt: they hang off every tile)
+        tiles_all = ((W + 63) // 64) * ((H + 15) // 16)
+        tiles_b = hiz_tiles_b / K if hiz_tiles_b else tiles_all
+        frac_b = min(1.0, tiles_b / tiles_all)
+        bytes_hiz_b = frac_b * (8 * W * H + 4 * sum(w * h for (_, w, h) in r_layout[:4])) + 4 * sum(w * h for (_, w, h) in r_layout[4:])
         bytes_clear = 8 * W * H
         avg_v, avg_t = meshlet_averages(scene)
         per_meshlet = 48 + 64 + 28 * avg_v + 3 * avg_t   # headers + transform + (4 B index + 24 B vertex stride) per vertex + 3 B per triangle
@@ -554,7 +563,7 @@ def main():
                             ("raster_a", avg(vis_a) * per_meshlet, stage["raster_a_ms"]), ("merge_a", bytes_merge, stage["merge_a_ms"]),
                             ("hiz_a", bytes_hiz, stage["hiz_a_ms"]), ("cull_b", bytes_cull_b, stage["cull_b_ms"]),
                             ("raster_b", avg(vis_b) * per_meshlet, stage["raster_b_ms"]), ("merge_b", bytes_merge, stage["merge_b_ms"]),
-                            ("hiz_b", bytes_hiz, stage["hiz_b_ms"])):
+                            ("hiz_b", bytes_hiz_b, stage["hiz_b_ms"])):
             m = ms / KS
             if (m <= 0 and b == 0) or (name == "clear" and clear_fused):
                 continue
@@ -580,6 +589,7 @@ def main():
             "config": config_dict(label, W, H, cnt, 1 if args.one_pass else 2, builder_note, world, shard),
             "run": {"positions": args.positions, "cone_cull": bool(args.cone_cull), "stages_from": f"a second pass of {KS} frames with an event after every stage (the frame time above has none inside the frame)",
                     "visible_a_avg": vis_a / K, "occluded_a_avg": occ_a / K, "visible_b_avg": vis_b / K,
+                    "hiz_b_tiles_avg": round(tiles_b, 1), "hiz_tiles": tiles_all,
                     "avg_vertices_per_meshlet": round(avg_v, 2), "avg_triangles_per_meshlet": round(avg_t, 2),
                     "clear": "fused into the pass-A cull launch (its 8*W*H bytes are counted there)" if clear_fused else "separate launch"},
             "e2e": {"value": frames_total / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

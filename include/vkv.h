@@ -75,6 +75,8 @@ typedef struct vkv_stats {
 	                                 exact mips + all-gather + barrier; hiz_*_ms is then the small-mip tail alone) */
 	uint32_t strip_tiles_pulled; /* VKV_FRAME_MERGE_STRIPS, both passes: (64x16-pixel tile, peer) pairs this rank pulled over NVLink, 8 KB each */
 	uint32_t strip_texels_sent;  /* ... and pyramid texels it stored into its peers, 4 B each */
+	uint32_t hiz_tiles_b;        /* two-pass frames: 64x16-pixel tiles the SECOND pyramid build reduced — all of them, or, after a small pass B,
+	                                only the tiles that pass drew into (the first build always reduces every tile) */
 } vkv_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------------------------- */

@@ -774,6 +774,7 @@ int frame_impl(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, uint32_t flags,
 			Range z("HiZ reduction");
 			HizParams hp = make_hiz(c);
 			if (partialB) { hp.tile_dirty = dirtyB; hp.dirty_count = &c->counters->visible[1]; hp.dirty_limit = kPartialHizLimit; }
+			if (c->exact_levels >= 1) hp.tiles_done = &c->counters->hiz_tiles_b;
 			CK(launch_hiz(hp, c->num_sms, s, &launches));
 		}
 		mark(E_HIZ_B);
@@ -794,6 +795,7 @@ int frame_impl(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, uint32_t flags,
 		out->kernel_launches = (uint32_t)launches;
 		out->strip_tiles_pulled = c->h_counters->strip_tiles_pulled;
 		out->strip_texels_sent = c->h_counters->strip_texels_sent;
+		out->hiz_tiles_b = c->h_counters->hiz_tiles_b;
 		if (timed) {
 			auto el = [&](int a, int b) { float ms = 0; cudaEventElapsedTime(&ms, c->stage_ev[a], c->stage_ev[b]); return ms; };
 			out->total_ms = el(E_BEGIN, E_COUNT);
@@ -850,6 +852,7 @@ int vkv_frame_wait(vkv_ctx* c, uint32_t ticket, vkv_stats* out) {
 		out->kernel_launches = f.launches;
 		out->strip_tiles_pulled = f.h->strip_tiles_pulled;
 		out->strip_texels_sent = f.h->strip_texels_sent;
+		out->hiz_tiles_b = f.h->hiz_tiles_b;
 	}
 	f.ticket = 0;
 	return VKV_OK;

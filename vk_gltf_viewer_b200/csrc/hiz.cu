@@ -259,6 +259,12 @@ __global__ void __launch_bounds__(kHizWarps * 32) hiz_tiled_kernel(const HizPara
 		const uint32_t t = firstTile + lane * tileStride;
 		redo = __ballot_sync(0xffffffffu, t < nTiles && __ldcg(p.tile_dirty + t) != 0);
 	}
+	if (p.tiles_done) { // statistics for the byte accounting of bench.py: one reduction per warp that has work (few in a partial rebuild)
+		uint32_t mine = 0;
+		if (redo != 0xffffffffu) mine = __popc(redo);
+		else if (firstTile < nTiles) mine = (nTiles - firstTile + tileStride - 1) / tileStride;
+		if (lane == 0 && mine) atomicAdd(p.tiles_done, mine);
+	}
 	uint32_t k = 0;
 	for (uint32_t tile = firstTile; tile < nTiles; tile += tileStride, ++k) {
 		if (!((redo >> (k & 31u)) & 1u)) continue;

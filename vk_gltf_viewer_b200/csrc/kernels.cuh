@@ -106,6 +106,7 @@ struct HizParams {
 	                             // into; clean tiles keep the exact mips the pass-A build stored a moment ago (NULL = rebuild every tile)
 	const uint32_t* dirty_count; // ... valid only if *dirty_count (pass B's survivor count) <= dirty_limit: the rasteriser stops marking above it
 	uint32_t dirty_limit;
+	uint32_t* tiles_done;        // statistics (NULL = none): += the number of tiles this launch reduced
 	// strip mode: the small-mip tail first waits for every rank's "my strip's mips are stored everywhere" signal (xgpu.cuh)
 	const uint32_t* wait_flags;  // this rank's flag slots (NULL = no wait)
 	uint32_t wait_epoch;
