@@ -42,11 +42,18 @@ constexpr int kBigTileW = VKV_BIG_TILE_W, kBigTileH = VKV_BIG_TILE_H;   // pixel
 #endif
 constexpr int kBigMinStamps = VKV_BIG_MIN_STAMPS;  // bbox of >= this many 8x4 stamps -> deferred
 #ifndef VKV_RASTER_BATCH
-#define VKV_RASTER_BATCH 2      // measured (profiles/r4b): 1 -> 0.3763 ms, 2 -> 0.3806, 3 -> 0.3952, 4 -> 0.4089, 8 -> 0.4690 on cfg 3: a meshlet
-#endif                          // occupies a warp for ~8 us, so whole batches leave the kernel's end ragged; 2 + the guided tail: 0.3658
+#define VKV_RASTER_BATCH 4      // meshlets per work-stealing grab on LONG lists (>= VKV_RASTER_LONG meshlets per resident warp): cfg 5 on one GPU
+#endif                          // (1.5 M meshlets, 8K): grab 4 -> raster A 0.99 ms, grab 2 -> 1.11 ms (profiles/r4i) — the header chain and the copies
+                                // of the next meshlet hide behind more work
+#ifndef VKV_RASTER_BATCH_SHORT
+#define VKV_RASTER_BATCH_SHORT 2 // ... and on ordinary lists.  A meshlet occupies a warp for ~8 us, so whole grabs leave the kernel's end ragged; measured
+#endif                          // on cfg 3 (33 meshlets per warp; profiles/r4b): grab 1 -> 0.3763 ms, 2 -> 0.3806, 3 -> 0.3952, 4 -> 0.4089, 8 -> 0.4690
+#ifndef VKV_RASTER_LONG
+#define VKV_RASTER_LONG 64
+#endif
 #ifndef VKV_RASTER_GUIDED
-#define VKV_RASTER_GUIDED 4     // guided self-scheduling: grabs shrink to single meshlets once less than this many grabs per warp are left (0 = off;
-#endif                          // profiles/r4c: 1 -> 0.3735, 2 -> 0.3682, 4 -> 0.3658)
+#define VKV_RASTER_GUIDED 4     // guided self-scheduling: grabs shrink towards single meshlets once fewer than this many grabs per warp are left (0 = off;
+#endif                          // profiles/r4c, cfg 3, grab 2: off -> 0.3806, 1 -> 0.3735, 2 -> 0.3682, 4 -> 0.3658)
 #ifndef VKV_RASTER_MIN_BLOCKS
 #define VKV_RASTER_MIN_BLOCKS 4
 #endif
@@ -408,7 +415,8 @@ __device__ __forceinline__ void meshlet_loop(const RasterParams& p, WarpScratch&
 	// meshlets per work-stealing grab: kBatch when there is plenty of work (the header chain's latency is paid once per batch);
 	// fewer when the list is short, so that a small scene spreads over all warps instead of queueing 4 deep behind a few
 	const uint32_t totalWarps = gridDim.x * (blockDim.x >> 5);
-	const uint32_t batch0 = kHot ? min((uint32_t)kBatch, max(1u, count / totalWarps)) : (uint32_t)kBatch;
+	const uint32_t perWarp = count / totalWarps;
+	const uint32_t batch0 = !kHot ? (uint32_t)kBatch : perWarp >= (uint32_t)VKV_RASTER_LONG ? (uint32_t)kBatch : min((uint32_t)min(kBatch, VKV_RASTER_BATCH_SHORT), max(1u, perWarp));
 	uint32_t batch = batch0;
 #if VKV_RASTER_GUIDED
 	uint32_t seen = 0; // where the cursor stood at this warp's last grab
