@@ -77,6 +77,9 @@ typedef struct vkv_stats {
 	uint32_t strip_texels_sent;  /* ... and pyramid texels it stored into its peers, 4 B each */
 	uint32_t hiz_tiles_b;        /* two-pass frames: 64x16-pixel tiles the SECOND pyramid build reduced — all of them, or, after a small pass B,
 	                                only the tiles that pass drew into (the first build always reduces every tile) */
+	uint32_t drain_items_a, drain_items_b; /* what the drain kernel behind each pass's rasteriser found queued (clip triangles + large-triangle
+	                                records + 1 if a queue overflowed).  The library sizes the next frames' drain launches from it: after two
+	                                observed frames with an empty pass the launch shrinks (an empty drain is pure launch latency) */
 } vkv_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------------------------- */

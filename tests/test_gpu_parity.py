@@ -532,3 +532,31 @@ def test_partial_pass_b_pyramid_equals_the_full_rebuild(monkeypatch):
     assert results[0][0] == results[1][0]
     assert np.array_equal(results[0][1], results[1][1])
     assert any(f[2] > 0 for f in results[0][0][1:])  # the camera moves: pass B draws something, so there are dirty tiles to redo
+
+
+def test_drain_grid_follows_the_observed_queues():
+    """The drain launch behind the rasteriser is sized from what the last observed frames found queued (an empty drain is pure launch
+    latency): after two frames with empty clip / large-triangle queues it shrinks to half a block per SM.  The first frame that fills
+    the queues again still runs on the small grid and must produce the same bits; the grid grows back right after."""
+    s = S.ground_plane(24, 40.0)
+    up = ((0, 0, 3), (0, 10, 2))           # looking steeply up: two meshlets pass the box test, every triangle is rejected, nothing is queued
+    down = ((0, 0, 3), (0, -0.2, 0))       # near-plane clipping + screen-filling triangles: both queues in use
+    low = ((0, 2, 0), (0.3, -1, 0.2))
+    views = [up, up, up, down, low, up, up, up, low, down]
+    summ = run_views(s, 640, 480, views, two_pass=True)   # bit-exact against the oracle, frame by frame
+    assert summ[3][0] > summ[0][0] and summ[8][0] > 0
+    # the same sweep again, looking at what the drain kernels report
+    W, H = 640, 480
+    cam = Camera(W, H)
+    cam.look_at(*views[0])
+    r = api.Renderer(W, H)
+    pc = r.upload_scene(s, cam)
+    items = []
+    for v in views:
+        cam.look_at(*v)
+        r.update_camera(pc, cam)
+        st = r.frame(pc, api.FRAME_TWO_PASS)
+        items.append(st.drain_items_a)
+    r.close()
+    assert items[:3] == [0, 0, 0] and items[5:8] == [0, 0, 0]          # two idle frames observed -> frames 3 and 8 run on the small grid
+    assert items[3] > 0 and items[4] > 0 and items[8] > 0 and items[9] > 0

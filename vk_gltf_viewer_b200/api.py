@@ -39,6 +39,7 @@ class Stats(C.Structure):
         ("cull_b_ms", C.c_float), ("raster_b_ms", C.c_float), ("hiz_b_ms", C.c_float), ("total_ms", C.c_float),
         ("kernel_launches", C.c_uint32), ("merge_a_ms", C.c_float), ("merge_b_ms", C.c_float),
         ("strip_tiles_pulled", C.c_uint32), ("strip_texels_sent", C.c_uint32), ("hiz_tiles_b", C.c_uint32),
+        ("drain_items_a", C.c_uint32), ("drain_items_b", C.c_uint32),
     ]
 
     def as_dict(self):

@@ -54,6 +54,10 @@ struct vkv_ctx {
 	bool sharded = false;
 	bool no_pdl = false;         // VKV_NO_PDL=1: launch the pass-B cull without programmatic stream serialization (A/B measurements)
 	bool separate_clear = false; // VKV_SEPARATE_CLEAR=1: keep the visbuffer clear a launch of its own (A/B measurements)
+	// drain launches sized from what the last observed frames found queued (FrameCounters::drain_seen): idle[pass] = consecutive observed
+	// frames with empty queues in that pass; the small grid is used from 2 on.  VKV_DRAIN_FULL=1 switches the heuristic off.
+	uint32_t drain_idle[2] = {0, 0};
+	bool drain_full = false;
 	bool full_hiz_b = false;     // VKV_HIZ_FULL_B=1: the pass-B pyramid build redoes every tile, not only the ones pass B drew into (A/B measurements)
 	MergeParams mp{};
 	bool attached = false;
@@ -297,9 +301,11 @@ RasterParams make_raster(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, const
 // raster_kernel + raster_big_kernel behind a reset of the large-triangle queue
 // after_cull: the cull launch right before this call has zeroed the raster's counters itself (CullParams::reset_ptr) and nothing
 // sits between the two launches: the raster kernel is launched with programmatic stream serialization
-int enqueue_raster(vkv_ctx* c, const RasterParams& r, int* launches, bool after_cull = false) {
+int enqueue_raster(vkv_ctx* c, RasterParams r, int* launches, bool after_cull = false, int pass = -1) {
 	if (!after_cull) CK(cudaMemsetAsync(&c->counters->big_next, 0, offsetof(FrameCounters, raster_reset_end) - offsetof(FrameCounters, big_next), c->stream)); // queues, cursors, barrier
-	CK(launch_raster(r, c->num_sms, c->stream, after_cull));
+	bool small_drain = false;
+	if (pass >= 0) { r.drainSeen = &c->counters->drain_seen[pass]; small_drain = !c->drain_full && c->drain_idle[pass] >= 2; }
+	CK(launch_raster(r, c->num_sms, c->stream, after_cull, small_drain));
 	if (launches) *launches += 2;
 	return VKV_OK;
 }
@@ -309,6 +315,11 @@ HizParams make_hiz(vkv_ctx* c) {
 	h.vis = c->vis; h.pyramid = c->pyramid; h.pyr = c->pyr; h.W = c->W; h.H = c->H; h.exact_levels = c->exact_levels; h.done = (getenv("VKV_HIZ_NOTAIL") || getenv("VKV_HIZ_SPLIT")) ? nullptr : &c->counters->hiz_done; /* diagnosis switches */
 	h.split_tail = getenv("VKV_HIZ_SPLIT") ? 1 : 0;
 	return h;
+}
+
+// what a frame's drain kernels found queued -> how the next frames' drain launches are sized (enqueue_raster)
+void observe_drain(vkv_ctx* c, const FrameCounters* h, bool two) {
+	for (int pass = 0; pass < (two ? 2 : 1); ++pass) c->drain_idle[pass] = h->drain_seen[pass] ? 0u : c->drain_idle[pass] + 1u;
 }
 
 // staged uploads (vkv_update_staged) become visible to everything enqueued on the context's stream from here on
@@ -431,6 +442,7 @@ int vkv_create(vkv_ctx** out, int cuda_device, uint32_t width, uint32_t height) 
 	if (const char* e = getenv("VKV_SEPARATE_CLEAR")) c->separate_clear = e[0] == '1';
 	if (const char* e = getenv("VKV_NO_PDL")) c->no_pdl = e[0] == '1';
 	if (const char* e = getenv("VKV_HIZ_FULL_B")) c->full_hiz_b = e[0] == '1';
+	if (const char* e = getenv("VKV_DRAIN_FULL")) c->drain_full = e[0] == '1';
 	if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { c->err = "cudaStreamCreate failed"; return bail(VKV_ERR_CUDA); }
 	c->stream = c->own_stream;
 	for (auto& ev : c->events) cudaEventCreate(&ev);
@@ -728,7 +740,7 @@ int frame_impl(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, uint32_t flags,
 	// cull A -> raster A back to back (no transform launch, no dirty-flag memset in between): the cull zeroed the raster's counters
 	const bool chainA = pa.reset_ptr != nullptr && xf_done && !(strips && !pa.zero_ptr);
 	if (!xf_done) { rc = prepare_transforms(c, pc, &launches); if (rc) return rc; }
-	rc = enqueue_raster(c, make_raster(c, pc, c->list_visible[0], &c->counters->visible[0], &c->counters->work[0], strips ? 0 : -1), &launches, chainA);
+	rc = enqueue_raster(c, make_raster(c, pc, c->list_visible[0], &c->counters->visible[0], &c->counters->work[0], strips ? 0 : -1), &launches, chainA, 0);
 	if (rc) return rc;
 	mark(E_RASTER_A);
 	if (merge) { rc = enqueue_merge(c, &launches); if (rc) return rc; }
@@ -763,7 +775,7 @@ int frame_impl(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, uint32_t flags,
 		mark(E_CULL_B);
 		RasterParams rb = make_raster(c, pc, c->list_visible[1], &c->counters->visible[1], &c->counters->work[1], (strips || partialB) ? 1 : -1);
 		if (partialB) rb.markLimit = kPartialHizLimit;
-		rc = enqueue_raster(c, rb, &launches, chainB);
+		rc = enqueue_raster(c, rb, &launches, chainB, 1);
 		if (rc) return rc;
 		mark(E_RASTER_B);
 		if (merge) { rc = enqueue_merge(c, &launches); if (rc) return rc; }
@@ -796,6 +808,8 @@ int frame_impl(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, uint32_t flags,
 		out->strip_tiles_pulled = c->h_counters->strip_tiles_pulled;
 		out->strip_texels_sent = c->h_counters->strip_texels_sent;
 		out->hiz_tiles_b = c->h_counters->hiz_tiles_b;
+		out->drain_items_a = c->h_counters->drain_seen[0]; out->drain_items_b = c->h_counters->drain_seen[1];
+		observe_drain(c, c->h_counters, two);
 		if (timed) {
 			auto el = [&](int a, int b) { float ms = 0; cudaEventElapsedTime(&ms, c->stage_ev[a], c->stage_ev[b]); return ms; };
 			out->total_ms = el(E_BEGIN, E_COUNT);
@@ -853,7 +867,9 @@ int vkv_frame_wait(vkv_ctx* c, uint32_t ticket, vkv_stats* out) {
 		out->strip_tiles_pulled = f.h->strip_tiles_pulled;
 		out->strip_texels_sent = f.h->strip_texels_sent;
 		out->hiz_tiles_b = f.h->hiz_tiles_b;
+		out->drain_items_a = f.h->drain_seen[0]; out->drain_items_b = f.h->drain_seen[1];
 	}
+	observe_drain(c, f.h, f.two);
 	f.ticket = 0;
 	return VKV_OK;
 }

@@ -87,6 +87,7 @@ struct RasterParams {
 	uint32_t* overflow;          // set when either queue was full
 	uint32_t* drainBarrier;
 	uint32_t* slowWork;
+	uint32_t* drainSeen;         // statistics (NULL = none): the drain kernel stores how much it found queued
 	unsigned long long neg_zero2; // the fp32 pair (-0.0, -0.0), see common.cuh mul2 (must arrive at run time)
 	const vkv_QuantizedPositions* qtable; // optional: per primitive, its POSITION accessor in 16-bit form (NULL = read the f32 Vertex records)
 	uint8_t* dirty;              // strip mode: one byte per 64x16-pixel tile, set for every tile a drawn triangle's bbox touches (NULL otherwise)
@@ -119,7 +120,7 @@ cudaError_t launch_cull(const CullParams& p, int num_sms, cudaStream_t stream, b
 cudaError_t launch_iota(const CullParams& p, uint32_t* out, uint32_t* count, int num_sms, cudaStream_t stream);
 cudaError_t launch_prepare_transforms(const float* transforms, const vkv_Camera* camera, uint32_t n, float* mvp, uint32_t* detNeg, float4* eye,
                                       int num_sms, cudaStream_t stream);
-cudaError_t launch_raster(const RasterParams& p, int num_sms, cudaStream_t stream, bool after_cull = false); // raster_kernel + raster_big_kernel; after_cull: programmatic dependent launch behind cull_kernel
+cudaError_t launch_raster(const RasterParams& p, int num_sms, cudaStream_t stream, bool after_cull = false, bool small_drain = false); // raster_kernel + raster_big_kernel; after_cull: programmatic dependent launch behind cull_kernel
 cudaError_t launch_hiz(const HizParams& p, int num_sms, cudaStream_t stream, int* launches);
 cudaError_t launch_fill64(unsigned long long* dst, size_t n, unsigned long long value, int num_sms, cudaStream_t stream);
 cudaError_t launch_fill32(uint32_t* dst, size_t n, uint32_t value, int num_sms, cudaStream_t stream);

@@ -16,6 +16,7 @@
 //     int32 edge functions, large or clipped ones by the whole warp in 8x4 stamps with int64 edge functions;
 //   * visibility: ONE fire-and-forget 64-bit RED.MIN per covered pixel on (~depthBits << 32 | drawId << 7 | triangle).
 #include "kernels.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -775,6 +776,7 @@ __global__ void __launch_bounds__(kDrainThreads, VKV_DRAIN_MINB) raster_big_kern
 	unsigned long long cur = *(volatile unsigned long long*)p.bigCursor;
 	const uint32_t overflowed = *(volatile uint32_t*)p.overflow;
 	const bool marking = marking_on(p);
+	if (p.drainSeen && blockIdx.x == 0 && threadIdx.x == 0) *p.drainSeen = clipCountNow + (uint32_t)(cur >> kBigSlotShift) + overflowed;
 	const uint32_t nClip = min(clipCountNow, p.clipCap);
 	if (nClip) {
 		__shared__ int sN[kDrainThreads / 32];
@@ -931,7 +933,7 @@ cudaError_t launch_prepare_transforms(const float* transforms, const vkv_Camera*
 	return cudaGetLastError();
 }
 
-cudaError_t launch_raster(const RasterParams& p, int num_sms, cudaStream_t stream, bool after_cull) {
+cudaError_t launch_raster(const RasterParams& p, int num_sms, cudaStream_t stream, bool after_cull, bool small_drain) {
 	static int perSmOf[64][2] = {}; // per device (a process may hold contexts on several GPUs): hot kernel, drain kernel
 	int dev = 0;
 	cudaGetDevice(&dev);
@@ -943,6 +945,7 @@ cudaError_t launch_raster(const RasterParams& p, int num_sms, cudaStream_t strea
 		n = 0;
 		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, raster_big_kernel, kDrainThreads, 0);
 		perSm[1] = n < 1 ? 1 : (n > 4 ? 4 : n);
+		if (const char* e = getenv("VKV_DRAIN_BLOCKS_PER_SM")) { const int v = atoi(e); if (v >= 1 && v < perSm[1]) perSm[1] = v; } // measurement switch
 	}
 	cudaLaunchAttribute pdl[1];
 	pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -957,7 +960,13 @@ cudaError_t launch_raster(const RasterParams& p, int num_sms, cudaStream_t strea
 	// every block co-resident (its clip phase ends in a grid barrier); exits at once when both queues are empty.  Launched with
 	// programmatic stream serialization: its blocks are set up under raster_kernel's tail (see there) instead of after it.
 	cudaLaunchConfig_t cfg = {};
-	cfg.gridDim = dim3(num_sms * perSm[1]); cfg.blockDim = dim3(kDrainThreads); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+	// small_drain: the caller has seen this pass's queues empty in the frames before.  An empty drain is pure latency between the rasteriser and
+	// the pyramid build, and most of it is block turnover: 444 / 296 / 148 / 74 blocks cost 15 / 12 / 7 / 5 us per frame on cfg 3 (profiles/r4m).
+	// Half a block per SM still drains an occasional clipped or large triangle; a scene that fills the queues gets the full grid back from
+	// the next observed frame on (cfg 2 with one block per SM: 0.260 against 0.217 ms).
+	cfg.gridDim = dim3(small_drain ? max(1, num_sms / 2) : num_sms * perSm[1]); cfg.blockDim = dim3(kDrainThreads); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+	static const int gridOverride = getenv("VKV_DRAIN_GRID") ? atoi(getenv("VKV_DRAIN_GRID")) : 0; // measurement switch
+	if (gridOverride > 0 && gridOverride < (int)cfg.gridDim.x) cfg.gridDim = dim3(gridOverride);
 	cudaLaunchAttribute attr[1];
 	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
 	attr[0].val.programmaticStreamSerializationAllowed = 1;
