@@ -301,10 +301,11 @@ RasterParams make_raster(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, const
 // raster_kernel + raster_big_kernel behind a reset of the large-triangle queue
 // after_cull: the cull launch right before this call has zeroed the raster's counters itself (CullParams::reset_ptr) and nothing
 // sits between the two launches: the raster kernel is launched with programmatic stream serialization
-int enqueue_raster(vkv_ctx* c, RasterParams r, int* launches, bool after_cull = false, int pass = -1) {
+int enqueue_raster(vkv_ctx* c, RasterParams r, int* launches, bool after_cull = false, int pass = -1, bool multi_gpu = false) {
 	if (!after_cull) CK(cudaMemsetAsync(&c->counters->big_next, 0, offsetof(FrameCounters, raster_reset_end) - offsetof(FrameCounters, big_next), c->stream)); // queues, cursors, barrier
 	bool small_drain = false;
-	if (pass >= 0) { r.drainSeen = &c->counters->drain_seen[pass]; small_drain = !c->drain_full && c->drain_idle[pass] >= 2; }
+	// (single-GPU frames only: the multi-GPU exchange paths keep the launch shape they were validated with)
+	if (pass >= 0) { r.drainSeen = &c->counters->drain_seen[pass]; small_drain = !c->drain_full && !multi_gpu && c->drain_idle[pass] >= 2; }
 	CK(launch_raster(r, c->num_sms, c->stream, after_cull, small_drain));
 	if (launches) *launches += 2;
 	return VKV_OK;
@@ -740,7 +741,7 @@ int frame_impl(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, uint32_t flags,
 	// cull A -> raster A back to back (no transform launch, no dirty-flag memset in between): the cull zeroed the raster's counters
 	const bool chainA = pa.reset_ptr != nullptr && xf_done && !(strips && !pa.zero_ptr);
 	if (!xf_done) { rc = prepare_transforms(c, pc, &launches); if (rc) return rc; }
-	rc = enqueue_raster(c, make_raster(c, pc, c->list_visible[0], &c->counters->visible[0], &c->counters->work[0], strips ? 0 : -1), &launches, chainA, 0);
+	rc = enqueue_raster(c, make_raster(c, pc, c->list_visible[0], &c->counters->visible[0], &c->counters->work[0], strips ? 0 : -1), &launches, chainA, 0, merge || strips);
 	if (rc) return rc;
 	mark(E_RASTER_A);
 	if (merge) { rc = enqueue_merge(c, &launches); if (rc) return rc; }
@@ -775,7 +776,7 @@ int frame_impl(vkv_ctx* c, const vkv_VisbufferPushConstants* pc, uint32_t flags,
 		mark(E_CULL_B);
 		RasterParams rb = make_raster(c, pc, c->list_visible[1], &c->counters->visible[1], &c->counters->work[1], (strips || partialB) ? 1 : -1);
 		if (partialB) rb.markLimit = kPartialHizLimit;
-		rc = enqueue_raster(c, rb, &launches, chainB, 1);
+		rc = enqueue_raster(c, rb, &launches, chainB, 1, merge || strips);
 		if (rc) return rc;
 		mark(E_RASTER_B);
 		if (merge) { rc = enqueue_merge(c, &launches); if (rc) return rc; }
