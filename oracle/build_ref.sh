@@ -5,7 +5,8 @@
 #   oracle/_ref/libmeshopt_ref.so  meshoptimizer @ the reference's pinned submodule (meshopt_buildMeshlets & co, the codecs)
 #   oracle/_ref/libmeshopt_ref_nosimd.so  the same, -DMESHOPTIMIZER_NO_SIMD (scalar decode filters)
 #   oracle/_ref/libref_shim.so     culling.h.glsl (isAabbInFrustum, getWorldSpaceAabbExtent, aabbPositions, projectAabb) and
-#                                  visbuffer.task.glsl:57-61 (mip selection) + the shared layout headers compiled as C++ against
+#                                  visbuffer.task.glsl:57-61 (mip selection), visbuffer.mesh.glsl:44,61,65,71,90-98 (vertex transform,
+#                                  determinants, facing decision) + the shared layout headers compiled as C++ against
 #                                  the reference's glm; camera.cpp:38-48,70-84 (reverseDepth, generateCameraFrustum); glm
 #                                  perspective/lookAt; fastgltf::math translate/rotate/scale.
 # The GLSL task/mesh/fragment/compute shaders themselves cannot be built or run here (no glslang, no Vulkan ICD) — see DESIGN.md.
@@ -45,6 +46,20 @@ printf '#pragma once\n#include <cstdint>\ntypedef std::uint64_t VkDeviceAddress;
 { printf 'GLSL_NAMESPACE_BEGIN\ninline void taskMipAndCenter(const std::array<vec3, 2>& projectedAabb, ivec2 pyramidSize, float& levelOut, vec2& centerOut) {\n'
   sed -n '57,61p' "$REF/shaders/visbuffer/visbuffer.task.glsl" | sed -e 's/\(projectedAabb\[[01]\]\)\.xy/vec2(\1)/g' -e 's/\bmax(/glm::max(/g'
   printf '\tlevelOut = level; centerOut = projectedCenter;\n}\nGLSL_NAMESPACE_END\n'; } > "$TMP/task_lines.inc"
+# visbuffer.mesh.glsl: the arithmetic lines of the mesh shader as three inline functions — :44 (mvp), :61 + :65 (clip position, clipVertices),
+# :71 + :90-98 (determinants and the facing decision).  Rewrites, arithmetic untouched: the buffer-reference chain
+# `pushConstants.cameraBuffer.camera.` -> `camera.`, the swizzle `pos.xyw` -> vec3(pos.x, pos.y, pos.w), `clipVertices[vidx] =` -> `clipVertex =`,
+# `clipVertices[indices.k]` -> `cv[indices.k]`, and the built-in output `gl_MeshPrimitivesEXT[pidx].gl_CullPrimitiveEXT =` -> `culled =`.
+MESH="$REF/shaders/visbuffer/visbuffer.mesh.glsl"
+{ printf 'GLSL_NAMESPACE_BEGIN\ninline mat4 meshMvp(const Camera& camera, const mat4& transformMatrix) {\n'
+  sed -n '44p' "$MESH" | sed -e 's/pushConstants\.cameraBuffer\.camera\./camera./'
+  printf '\treturn mvp;\n}\ninline vec4 meshVertex(const mat4& mvp, const Vertex& vertex, vec3& clipVertex) {\n'
+  sed -n '61p;65p' "$MESH" | sed -e 's/clipVertices\[vidx\] = pos\.xyw;/clipVertex = vec3(pos.x, pos.y, pos.w);/'
+  printf '\treturn pos;\n}\ninline float meshTransformDet(const mat4& transformMatrix) {\n'
+  sed -n '71p' "$MESH"
+  printf '\treturn transformDet;\n}\ninline bool meshCull(const vec3* cv, uvec3 indices, float transformDet, float& detOut) {\n\tbool culled;\n'
+  sed -n '90,98p' "$MESH" | sed -e 's/clipVertices\[/cv[/g' -e 's/gl_MeshPrimitivesEXT\[pidx\]\.gl_CullPrimitiveEXT =/culled =/'
+  printf '\tdetOut = det;\n\treturn culled;\n}\nGLSL_NAMESPACE_END\n'; } > "$TMP/mesh_lines.inc"
 # camera.cpp free functions reverseDepth (38-48) and generateCameraFrustum (70-84)
 { printf '#define ZoneScoped\n#include <array>\n#include <glm/glm.hpp>\n'; sed -n '38,48p;70,84p' "$REF/src/vk_gltf_viewer/camera.cpp"; } > "$TMP/camera_fns.inc"
 

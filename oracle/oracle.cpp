@@ -647,6 +647,91 @@ int orc_raster(const vkv_VisbufferPushConstants* pc, uint32_t W, uint32_t H, con
 	return 0;
 }
 
+// The mesh shader's per-vertex / per-triangle results for the given MeshletDraws, in the layout of ref_shim.cpp's ref_mesh_shader
+// (the same lines of visbuffer.mesh.glsl evaluated by the reference's text against glm), for tests/test_oracle.py:
+//   clip[d][v]   gl_Position of meshlet vertex v (:61)               64 slots x 4 floats
+//   cull[d][t]   gl_CullPrimitiveEXT of triangle t (:86-102)         126 slots; 0 / 1, 0xff = beyond triangleCount
+//   det[d][t]    determinant(mat3(v0, v1, v2)) (:93)                 the oracle's association (det3 above)
+//   tdet[d]      determinant(transformMatrix) (:71)
+//   noise[d][t]  first-order bound on how far an equally valid evaluation of the same GLSL can move det: kNoise roundings of the largest
+//                term of every sum (mat4*mat4, mat4*vec4, the six triple products), propagated through the determinant's cofactors
+//   ambig[d][t]  1 = |det| <= noise (or |transformDet| within its own noise): such an evaluation could decide the triangle differently
+void orc_mesh_shader(const vkv_VisbufferPushConstants* pc, const uint32_t* draw_ids, uint32_t n, float* clip, uint8_t* cull, float* det,
+                     float* tdet, uint8_t* ambig, float* noise) {
+	const vkv_Camera cam = *(const vkv_Camera*)pc->cameraBuffer;
+	constexpr uint32_t kSlots = 126; // mesh_common.h.glsl maxPrimitives
+	for (uint32_t d = 0; d < n; ++d) {
+		const vkv_MeshletDraw dr = ((const vkv_MeshletDraw*)pc->drawBuffer)[draw_ids[d]];
+		const vkv_Primitive& prim = ((const vkv_Primitive*)pc->primitiveBuffer)[dr.primitiveIndex];
+		const vkv_Meshlet& ml = ((const vkv_Meshlet*)prim.meshletBuffer)[dr.meshletIndex];
+		const vkv_Material& mat = ((const vkv_Material*)pc->materialBuffer)[prim.materialIndex];
+		const float* T = (const float*)pc->transformBuffer + (size_t)dr.transformIndex * 16;
+		float mvp[16], mvpErr[16];
+		mul44m(cam.viewProjection, T, mvp);
+		for (int c = 0; c < 4; ++c)
+			for (int r = 0; r < 4; ++r) {
+				float terms = 0.f;
+				for (int k = 0; k < 4; ++k) terms += std::fabs(cam.viewProjection[k * 4 + r] * T[c * 4 + k]);
+				mvpErr[c * 4 + r] = kNoise * terms;
+			}
+		const uint32_t* vidx = (const uint32_t*)prim.vertexIndexBuffer;
+		const vkv_Vertex* verts = (const vkv_Vertex*)prim.vertexBuffer;
+		const uint8_t* tris = (const uint8_t*)prim.primitiveIndexBuffer;
+		V4 cv[VKV_MAX_VERTICES];
+		float cErr[VKV_MAX_VERTICES][4];
+		const uint32_t vc = ml.vertexCount < VKV_MAX_VERTICES ? ml.vertexCount : VKV_MAX_VERTICES;
+		for (uint32_t v = 0; v < vc; ++v) {
+			const float* p = verts[vidx[ml.vertexOffset + v]].position;
+			cv[v] = mul44(mvp, V4{p[0], p[1], p[2], 1.0f});
+			std::memcpy(clip + ((size_t)d * VKV_MAX_VERTICES + v) * 4, &cv[v], 16);
+			for (int r = 0; r < 4; ++r) {
+				const float terms = ((std::fabs(mvp[r] * p[0]) + std::fabs(mvp[4 + r] * p[1])) + std::fabs(mvp[8 + r] * p[2])) + std::fabs(mvp[12 + r]);
+				const float moved = ((mvpErr[r] * std::fabs(p[0]) + mvpErr[4 + r] * std::fabs(p[1])) + mvpErr[8 + r] * std::fabs(p[2])) + mvpErr[12 + r];
+				cErr[v][r] = kNoise * terms + moved;
+			}
+		}
+		const float transformDet = det4(T);
+		tdet[d] = transformDet;
+		// noise of det4: the cofactor sum's terms are at most |m0 d0| + ... ; each d_k is itself a sum of six triple products
+		float tdetTerms = 0.f;
+		{
+			float a[16];
+			for (int i = 0; i < 16; ++i) a[i] = std::fabs(T[i]);
+			// permanent of |T| bounds the sum of the absolute values of all 24 products
+			auto perm3 = [&](int c0, int c1, int c2, int skipRow) {
+				int rows[3], k = 0;
+				for (int r = 0; r < 4; ++r) if (r != skipRow) rows[k++] = r;
+				auto A = [&](int c, int r) { return a[c * 4 + rows[r]]; };
+				return A(c0, 0) * (A(c1, 1) * A(c2, 2) + A(c1, 2) * A(c2, 1)) + A(c0, 1) * (A(c1, 0) * A(c2, 2) + A(c1, 2) * A(c2, 0)) +
+				       A(c0, 2) * (A(c1, 0) * A(c2, 1) + A(c1, 1) * A(c2, 0));
+			};
+			for (int r = 0; r < 4; ++r) tdetTerms += a[r] * perm3(1, 2, 3, r);
+		}
+		const bool tdetAmbig = std::fabs(transformDet) <= 2.0f * kNoise * tdetTerms;
+		for (uint32_t t = 0; t < kSlots; ++t) {
+			uint8_t& c = cull[(size_t)d * kSlots + t];
+			c = 0xff; det[(size_t)d * kSlots + t] = 0.f; ambig[(size_t)d * kSlots + t] = 0; noise[(size_t)d * kSlots + t] = 0.f;
+			if (t >= ml.triangleCount) continue;
+			const uint32_t ia = tris[ml.triangleOffset + t * 3 + 0], ib = tris[ml.triangleOffset + t * 3 + 1], ic = tris[ml.triangleOffset + t * 3 + 2];
+			if (mat.doubleSided != 0 || ia >= vc || ib >= vc || ic >= vc) { c = 0; continue; }
+			const V3 a{cv[ia].x, cv[ia].y, cv[ia].w}, b{cv[ib].x, cv[ib].y, cv[ib].w}, cc{cv[ic].x, cv[ic].y, cv[ic].w};
+			const float dt = det3(a, b, cc);
+			det[(size_t)d * kSlots + t] = dt;
+			c = ((transformDet < 0.0f) ? (dt < 0.0f) : (dt > 0.0f)) ? 1 : 0;
+			// first-order bound: |d det| <= sum_i |cofactor_i| * err_i  +  roundings of the six triple products
+			auto absv = [](V3 v) { return V3{std::fabs(v.x), std::fabs(v.y), std::fabs(v.z)}; };
+			auto permCross = [](V3 u, V3 v) { return V3{u.y * v.z + u.z * v.y, u.z * v.x + u.x * v.z, u.x * v.y + u.y * v.x}; }; // |cross| bound
+			const V3 A = absv(a), B = absv(b), C = absv(cc);
+			const V3 eA{cErr[ia][0], cErr[ia][1], cErr[ia][3]}, eB{cErr[ib][0], cErr[ib][1], cErr[ib][3]}, eC{cErr[ic][0], cErr[ic][1], cErr[ic][3]};
+			const float moved = dot3(eA, permCross(B, C)) + dot3(eB, permCross(A, C)) + dot3(eC, permCross(A, B));
+			const float terms = dot3(A, permCross(B, C)); // sum of the absolute values of the six triple products
+			const float bound = 2.0f * kNoise * terms + 2.0f * moved;
+			noise[(size_t)d * kSlots + t] = bound;
+			if (tdetAmbig || std::fabs(dt) <= bound) ambig[(size_t)d * kSlots + t] = 1;
+		}
+	}
+}
+
 // srgb.h.glsl:26-32 (per channel) and the RGBA8_UNORM image store conversion
 static float from_linear(float c) {
 	bool cutoff = c < 0.0031308f;

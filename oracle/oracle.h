@@ -4,14 +4,21 @@
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it,
  * and only as the checker (or as the timed CPU baseline), never on the product path.
  *
- * PARITY UNPINNED for the sampler footprint rule, raster and HiZ outputs: the reference ships no tests, golden images or
- * known-answer vectors for these stages, and its shaders cannot be run in this image (no Vulkan loader /
- * lavapipe / glslang).  What IS pinned against the reference's own text, compiled as C++ against its glm by
+ * PARITY UNPINNED for the sampler footprint rule, the fixed-function rasteriser and (through the sampler rule) the HiZ outputs: the
+ * reference ships no tests, golden images or known-answer vectors for these stages, its shaders cannot be run in
+ * this image (no Vulkan loader / lavapipe / glslang), and for these three there is no reference CODE at all — they are Vulkan
+ * fixed-function behaviour.  What IS pinned against the reference's own text, compiled as C++ against its glm by
  * oracle/build_ref.sh into oracle/_ref/ (tests/test_oracle.py):
  *   - the whole per-draw decision of the task shader except the texture fetch: culling.h.glsl (isAabbInFrustum,
  *     getWorldSpaceAabbExtent, aabbPositions, projectAabb), visbuffer.task.glsl:50-52,56-61,64 — on every MeshletDraw of all
  *     five BASELINE configs at full size the oracle's class differs from the glm-evaluated reference only on draws it flags
  *     ORC_AMBIG_* / ORC_CROSSES_CAMERA (0-7 draws in 10 M, all flagged);
+ *   - the mesh shader's arithmetic: visbuffer.mesh.glsl:44 (mvp), :61 (gl_Position), :71 (transformDet), :86-98 (the facing decision
+ *     on determinant(mat3(v0.xyw, v1.xyw, v2.xyw))) — clip positions agree with the glm-evaluated lines to < 4e-7 of the vertex's largest
+ *     coordinate, determinants within 2.2 % of orc_mesh_shader's first-order noise bound, gl_CullPrimitiveEXT differs only by sign
+ *     flips inside that bound (none unflagged).  NOTE what that test measures about the REFERENCE: the determinant of three nearly
+ *     parallel (x, y, w) vectors cancels catastrophically for small distant triangles — 0.9 % (cfg 3) to 3.9 % (cfg 5) of the facing
+ *     decisions depend on how the compiler associates the products.  The oracle's association (below) is the definition here;
  *   - the data layouts (include/vkv_abi.h static_asserts == the reference headers compiled as C++), packVisBuffer;
  *   - camera.cpp's reverseDepth / generateCameraFrustum, glm perspective / lookAt, fastgltf::math node matrices, fastgltf's
  *     convertComponent; meshoptimizer's codecs, scan partition, buildMeshlets / optimizeMeshlet / computeMeshletBounds.
@@ -106,6 +113,13 @@ int orc_hiz(uint32_t W, uint32_t H, const float* depth, float* pyramid, int thre
 /* The sampler itself, exposed for unit tests: min over the <=2x2 non-zero-weight texels around (u,v)
  * of a w x h image with CLAMP_TO_EDGE.  *ambig is OR-ed with 1 if a frac is within 1e-4 of 0. */
 float orc_sample_min(const float* img, uint32_t w, uint32_t h, float u, float v, int* ambig);
+
+/* The mesh shader's per-vertex / per-triangle results for n MeshletDraws (visbuffer.mesh.glsl:43-44 mvp, :61 gl_Position, :71 transformDet,
+ * :86-102 gl_CullPrimitiveEXT), laid out per draw as clip[64][4], cull[126] (0 / 1, 0xff beyond triangleCount), det[126], tdet, ambig[126],
+ * noise[126] (noise = first-order bound on how far an equally valid evaluation of the same GLSL can move det; ambig = |det| <= noise, or
+ * transformDet within its own noise: such an evaluation may decide the triangle differently).  tests/test_oracle.py holds this against the reference's own lines compiled with glm. */
+void orc_mesh_shader(const vkv_VisbufferPushConstants* pc, const uint32_t* draw_ids, uint32_t n, float* clip, uint8_t* cull, float* det,
+                     float* tdet, uint8_t* ambig, float* noise);
 
 /* shaders/visbuffer/visbuffer_resolve.comp.glsl:17-41 + srgb.h.glsl:26-32 + dispatch application.cpp:943
  * (renderResolution.x / 32 groups of 32 threads: columns >= (W/32)*32 are never touched).  ids = the R32_UINT visbuffer;

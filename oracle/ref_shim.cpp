@@ -15,6 +15,7 @@
 #include "culling_head.h.glsl"         // reference: culling.h.glsl:1-30 (generated slice, see build_ref.sh)
 #include "culling_tail.h.glsl"         // reference: culling.h.glsl:31-56 aabbPositions + projectAabb (generated slice, array syntax rewritten)
 #include "task_lines.inc"              // reference: visbuffer.task.glsl:57-61 mip selection + sample position (generated slice)
+#include "mesh_lines.inc"              // reference: visbuffer.mesh.glsl:44,61,65,71,90-98 vertex transform, determinants, facing decision (generated slice)
 #include "camera_fns.inc"              // reference: camera.cpp reverseDepth + generateCameraFrustum
 
 #include <atomic>
@@ -111,6 +112,49 @@ void ref_task_cull(const glsl::VisbufferPushConstants* pc, const float* pyramid,
 	for (int t = 1; t < nt; ++t) pool.emplace_back(work);
 	work();
 	for (auto& t : pool) t.join();
+}
+
+// The mesh shader's arithmetic (visbuffer.mesh.glsl:43-44 mvp, :61 clip position, :65 clipVertices, :71 transformDet, :86-98 the facing
+// decision) evaluated with the REFERENCE's own lines as glm evaluates them on the C++ side, for the given MeshletDraws.  Per draw d:
+// clip[d][v] = gl_Position of meshlet vertex v (4 floats, maxVertices = 64 slots), cull[d][t] = gl_CullPrimitiveEXT of triangle t
+// (126 slots; 0 / 1, 0xff = slot beyond triangleCount), det[d][t] = the determinant the decision was taken on, tdet[d] = transformDet.
+// NOTE glm's mat4*mat4, mat4*vec4 and determinant associate differently from the oracle's stated policy; the test allows the
+// decisions to differ only where the oracle flags the determinant as within rounding noise of zero.
+void ref_mesh_shader(const glsl::VisbufferPushConstants* pc, const uint32_t* draw_ids, uint32_t n, float* clip, uint8_t* cull, float* det, float* tdet) {
+	const auto* draws = reinterpret_cast<const glsl::MeshletDraw*>(pc->drawBuffer);
+	const auto* transforms = reinterpret_cast<const glm::mat4*>(pc->transformBuffer);
+	const auto* prims = reinterpret_cast<const glsl::Primitive*>(pc->primitiveBuffer);
+	const auto* materials = reinterpret_cast<const glsl::Material*>(pc->materialBuffer);
+	const glsl::Camera camera = *reinterpret_cast<const glsl::Camera*>(pc->cameraBuffer);
+	for (uint32_t d = 0; d < n; ++d) {
+		const glsl::MeshletDraw draw = draws[draw_ids[d]];                                                                       // :31
+		const glsl::Primitive& primitive = prims[draw.primitiveIndex];                                                           // :33
+		const glsl::Meshlet meshlet = reinterpret_cast<const glsl::Meshlet*>(primitive.meshletBuffer)[draw.meshletIndex];        // :34
+		const glsl::Material& material = materials[primitive.materialIndex];                                                     // :35
+		const glm::mat4 transformMatrix = transforms[draw.transformIndex];                                                       // :43
+		const glm::mat4 mvp = glsl::meshMvp(camera, transformMatrix);                                                            // :44
+		const auto* vertexIndices = reinterpret_cast<const uint32_t*>(primitive.vertexIndexBuffer);
+		const auto* vertices = reinterpret_cast<const glsl::Vertex*>(primitive.vertexBuffer);
+		const auto* primitiveIndices = reinterpret_cast<const uint8_t*>(primitive.primitiveIndexBuffer);
+		glm::vec3 clipVertices[glsl::maxVertices];
+		for (uint32_t v = 0; v < meshlet.vertexCount && v < glsl::maxVertices; ++v) {
+			const glsl::Vertex& vertex = vertices[vertexIndices[meshlet.vertexOffset + v]];                                      // :57-58
+			const glm::vec4 pos = glsl::meshVertex(mvp, vertex, clipVertices[v]);                                                // :61,65
+			std::memcpy(clip + ((size_t)d * glsl::maxVertices + v) * 4, &pos, 16);
+		}
+		const float transformDet = glsl::meshTransformDet(transformMatrix);                                                      // :71
+		tdet[d] = transformDet;
+		for (uint32_t t = 0; t < glsl::maxPrimitives; ++t) {
+			uint8_t& c = cull[(size_t)d * glsl::maxPrimitives + t];
+			float& dt = det[(size_t)d * glsl::maxPrimitives + t];
+			c = 0xff; dt = 0.0f;
+			if (t >= meshlet.triangleCount) continue;
+			const glm::uvec3 indices(primitiveIndices[meshlet.triangleOffset + t * 3 + 0], primitiveIndices[meshlet.triangleOffset + t * 3 + 1],
+			                         primitiveIndices[meshlet.triangleOffset + t * 3 + 2]);                                       // :77-80
+			if (!material.doubleSided) c = glsl::meshCull(clipVertices, indices, transformDet, dt) ? 1 : 0;                       // :86-98
+			else c = 0;                                                                                                          // :99-102
+		}
+	}
 }
 
 uint32_t ref_pack_visbuffer(uint32_t drawIndex, uint32_t primitiveId) { return glsl::packVisBuffer(drawIndex, primitiveId); }

@@ -50,10 +50,24 @@ def lib():
         L.orc_resolve.argtypes = [C.POINTER(abi.PushConstants), C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
         L.orc_sample_min.restype = C.c_float
         L.orc_sample_min.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.POINTER(C.c_int)]
+        L.orc_mesh_shader.restype = None
+        L.orc_mesh_shader.argtypes = [C.POINTER(abi.PushConstants), C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_vis64_key.restype = C.c_uint64
         L.orc_vis64_key.argtypes = [C.c_float, C.c_uint32]
         _lib = L
     return _lib
+
+
+def mesh_shader(pc, draw_ids):
+    """visbuffer.mesh.glsl:43-102 for the given MeshletDraws -> clip [n,64,4] f32, cull [n,126] u8 (0 / 1, 0xff = no such triangle),
+    det [n,126] f32, transformDet [n] f32, ambig [n,126] u8 (|det| <= noise), noise [n,126] f32 (first-order rounding-noise bound of det)"""
+    ids = np.ascontiguousarray(draw_ids, np.uint32)
+    n = ids.size
+    clip = np.zeros((n, 64, 4), np.float32); cull = np.zeros((n, 126), np.uint8); det = np.zeros((n, 126), np.float32)
+    tdet = np.zeros(n, np.float32); ambig = np.zeros((n, 126), np.uint8); noise = np.zeros((n, 126), np.float32)
+    lib().orc_mesh_shader(C.byref(pc), ids.ctypes.data, n, clip.ctypes.data, cull.ctypes.data, det.ctypes.data, tdet.ctypes.data, ambig.ctypes.data,
+                          noise.ctypes.data)
+    return clip, cull, det, tdet, ambig, noise
 
 
 class Targets:

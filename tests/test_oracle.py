@@ -336,6 +336,76 @@ def test_task_shader_decisions_match_the_reference_text(ref_shim, name):
         assert r["flagged"] <= 0.02 * r["draws"] + 8, "ambiguity flags must stay the exception"
 
 
+# ------------------------------------------------------------------------------------------ reference-pinned: the mesh shader's arithmetic
+def _ref_mesh_shader(ref_shim, pc, draw_ids):
+    """visbuffer.mesh.glsl:44,61,65,71,90-98 evaluated with the reference's own lines against glm (oracle/ref_shim.cpp::ref_mesh_shader)"""
+    ids = np.ascontiguousarray(draw_ids, np.uint32)
+    n = ids.size
+    clip = np.zeros((n, 64, 4), np.float32); cull = np.zeros((n, 126), np.uint8); det = np.zeros((n, 126), np.float32); tdet = np.zeros(n, np.float32)
+    ref_shim.ref_mesh_shader.restype = None
+    ref_shim.ref_mesh_shader.argtypes = [C.POINTER(abi.PushConstants), C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    ref_shim.ref_mesh_shader(C.byref(pc), ids.ctypes.data, n, clip.ctypes.data, cull.ctypes.data, det.ctypes.data, tdet.ctypes.data)
+    return clip, cull, det, tdet
+
+
+@pytest.mark.parametrize("name", sorted(PIN_CONFIGS) + ["mirrored", "blobs_trs"])
+def test_mesh_shader_arithmetic_matches_the_reference_text(ref_shim, name):
+    """The mesh shader's arithmetic — mvp = viewProjection * transform (visbuffer.mesh.glsl:44), gl_Position = mvp * vec4(position, 1) (:61),
+    transformDet (:71) and the facing decision on determinant(mat3(v0.xyw, v1.xyw, v2.xyw)) (:86-98) — compiled from the REFERENCE's
+    shader text against glm, on the surviving meshlets of every BASELINE config at full size (up to 40 000 of them, seeded) plus as many
+    drawn from the whole list (behind the camera, outside the frustum), and on mirrored / non-uniformly scaled nodes.  glm associates
+    mat4*mat4, mat4*vec4 and the determinant differently from the oracle's stated policy, so the claim is:
+      * clip positions agree to a rounding or two of the vertex's largest coordinate;
+      * the determinants agree within the oracle's own first-order noise bound (`noise`), i.e. both sides evaluate the same formula;
+      * gl_CullPrimitiveEXT differs only by sign flips of determinants inside that bound (never an unflagged triangle).
+    How often it does flip is a property of the reference's test, not of either evaluation: the determinant of three nearly parallel
+    (x, y, w) vectors cancels catastrophically for small, distant triangles.  The count is printed and bounded."""
+    if name in PIN_CONFIGS:
+        make, (W, H) = PIN_CONFIGS[name]
+        scene = make()
+        view = scene.default_view(1, 64)
+    else:
+        scene, (W, H) = _cone_scenes()[name], (480, 360)
+        view = ((5, 2, 7), (0, 0, 0))
+    cam = Camera(W, H).look_at(*view)
+    pc = scene.host_push_constants(cam)
+    tg = O.Targets(W, H)
+    st, _ = O.cull(pc, W, H, tg.pyramid, 0)               # cleared pyramid: every draw inside the frustum survives
+    visible = O.visible_ids(st)
+    rng = np.random.default_rng(0x5EED)
+    cap = 40000
+    ids = np.concatenate([visible if visible.size <= cap else rng.choice(visible, cap, replace=False),
+                          rng.choice(pc.meshletDrawCount, min(cap, pc.meshletDrawCount), replace=False).astype(np.uint32)])
+    tot = dict(draws=int(ids.size), triangles=0, differ=0, unexplained=0, within_noise=0, culled=0, clip_identical=0, clip_total=0, det_identical=0)
+    worst_clip, worst_det = 0.0, 0.0
+    for b in range(0, ids.size, 8192):                    # chunks: 1 KB of clip positions per draw
+        chunk = ids[b:b + 8192]
+        clip_o, cull_o, det_o, tdet_o, ambig, noise = O.mesh_shader(pc, chunk)
+        clip_r, cull_r, det_r, tdet_r = _ref_mesh_shader(ref_shim, pc, chunk)
+        assert np.array_equal(cull_o == 0xff, cull_r == 0xff)                      # same meshlets, same triangle counts
+        assert np.array_equal(np.sign(tdet_o), np.sign(tdet_r))
+        valid = (cull_o != 0xff) & (noise > 0)                                     # (noise == 0: double-sided material, no determinant taken)
+        differ = valid & (cull_o != cull_r)
+        tot["triangles"] += int(valid.sum()); tot["differ"] += int(differ.sum()); tot["unexplained"] += int((differ & (ambig == 0)).sum())
+        tot["within_noise"] += int((valid & (ambig != 0)).sum()); tot["culled"] += int((valid & (cull_o == 1)).sum())
+        tot["det_identical"] += int((valid & (det_o.view(np.uint32) == det_r.view(np.uint32))).sum())
+        # the two determinants are the same formula: they agree within the first-order bound, everywhere
+        ratio = np.where(valid, np.abs(det_o.astype(np.float64) - det_r) / np.where(valid, noise, 1), 0)
+        worst_det = max(worst_det, float(ratio.max()))
+        # clip positions: glm pairs the adds of mat4*vec4 — agreement to a few roundings of the largest coordinate of the vertex
+        scale = np.maximum(np.abs(clip_o).max(axis=2, keepdims=True), np.abs(clip_r).max(axis=2, keepdims=True))
+        rel = np.where(scale > 0, np.abs(clip_o - clip_r) / np.where(scale > 0, scale, 1), 0)
+        worst_clip = max(worst_clip, float(rel.max()))
+        tot["clip_identical"] += int((clip_o.view(np.uint32) == clip_r.view(np.uint32)).sum()); tot["clip_total"] += int(clip_o.size)
+    print(f"\n{name}: oracle vs reference-text mesh shader: {tot}; worst clip difference {worst_clip:.2e} of the vertex's largest coordinate, "
+          f"worst |det difference| / noise bound {worst_det:.3f}")
+    assert tot["unexplained"] == 0, (name, tot)
+    assert worst_clip < 1e-6, (name, worst_clip)           # < 9 ulp of the largest coordinate
+    assert worst_det <= 1.0, (name, worst_det)             # the bound holds: same formula, different association
+    assert tot["differ"] <= 0.05 * tot["triangles"], (name, tot)
+    assert tot["culled"] > 0 or name == "mirrored"
+
+
 # ------------------------------------------------------------------------------------------ optional normal-cone cull (extension)
 def _cone_scenes():
     rng = np.random.default_rng(3)
