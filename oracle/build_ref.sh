@@ -60,6 +60,8 @@ MESH="$REF/shaders/visbuffer/visbuffer.mesh.glsl"
   printf '\treturn transformDet;\n}\ninline bool meshCull(const vec3* cv, uvec3 indices, float transformDet, float& detOut) {\n\tbool culled;\n'
   sed -n '90,98p' "$MESH" | sed -e 's/clipVertices\[/cv[/g' -e 's/gl_MeshPrimitivesEXT\[pidx\]\.gl_CullPrimitiveEXT =/culled =/'
   printf '\tdetOut = det;\n\treturn culled;\n}\nGLSL_NAMESPACE_END\n'; } > "$TMP/mesh_lines.inc"
+# srgb.h.glsl is dual GLSL / C++ except for its swizzles: `X.rgb` -> vec3(X) (glm has no .rgb member without swizzle extensions)
+sed -e 's/\([A-Za-z]*\)\.rgb/vec3(\1)/g' "$REF/shaders/srgb.h.glsl" > "$TMP/srgb_lines.h.glsl"
 # camera.cpp free functions reverseDepth (38-48) and generateCameraFrustum (70-84)
 { printf '#define ZoneScoped\n#include <array>\n#include <glm/glm.hpp>\n'; sed -n '38,48p;70,84p' "$REF/src/vk_gltf_viewer/camera.cpp"; } > "$TMP/camera_fns.inc"
 

@@ -745,6 +745,8 @@ static uint32_t unorm8(float v) {
 	return (uint32_t)std::lrintf(v * 255.0f);
 }
 
+float orc_from_linear(float c) { return from_linear(c); } // for the pin against the reference's srgb.h.glsl (tests/test_oracle.py)
+
 int orc_resolve(const vkv_VisbufferPushConstants* pc, uint32_t W, uint32_t H, const uint32_t* ids, uint32_t* out) {
 	if (pc->meshletDrawCount == 0) return 0;                       // application.cpp:930
 	const vkv_MeshletDraw* draws = (const vkv_MeshletDraw*)pc->drawBuffer;

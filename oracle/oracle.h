@@ -19,7 +19,8 @@
  *     flips inside that bound (none unflagged).  NOTE what that test measures about the REFERENCE: the determinant of three nearly
  *     parallel (x, y, w) vectors cancels catastrophically for small distant triangles — 0.9 % (cfg 3) to 3.9 % (cfg 5) of the facing
  *     decisions depend on how the compiler associates the products.  The oracle's association (below) is the definition here;
- *   - the data layouts (include/vkv_abi.h static_asserts == the reference headers compiled as C++), packVisBuffer;
+ *   - the data layouts (include/vkv_abi.h static_asserts == the reference headers compiled as C++), packVisBuffer / unpackVisBuffer,
+ *     the resolve pass's fromLinear (srgb.h.glsl compiled against glm: bit-identical);
  *   - camera.cpp's reverseDepth / generateCameraFrustum, glm perspective / lookAt, fastgltf::math node matrices, fastgltf's
  *     convertComponent; meshoptimizer's codecs, scan partition, buildMeshlets / optimizeMeshlet / computeMeshletBounds.
  *
@@ -113,6 +114,7 @@ int orc_hiz(uint32_t W, uint32_t H, const float* depth, float* pyramid, int thre
 /* The sampler itself, exposed for unit tests: min over the <=2x2 non-zero-weight texels around (u,v)
  * of a w x h image with CLAMP_TO_EDGE.  *ambig is OR-ed with 1 if a frac is within 1e-4 of 0. */
 float orc_sample_min(const float* img, uint32_t w, uint32_t h, float u, float v, int* ambig);
+float orc_from_linear(float c); /* srgb.h.glsl:26-32, one channel */
 
 /* The mesh shader's per-vertex / per-triangle results for n MeshletDraws (visbuffer.mesh.glsl:43-44 mvp, :61 gl_Position, :71 transformDet,
  * :86-102 gl_CullPrimitiveEXT), laid out per draw as clip[64][4], cull[126] (0 / 1, 0xff beyond triangleCount), det[126], tdet, ambig[126],

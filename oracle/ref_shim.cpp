@@ -17,6 +17,7 @@
 #include "task_lines.inc"              // reference: visbuffer.task.glsl:57-61 mip selection + sample position (generated slice)
 #include "mesh_lines.inc"              // reference: visbuffer.mesh.glsl:44,61,65,71,90-98 vertex transform, determinants, facing decision (generated slice)
 #include "camera_fns.inc"              // reference: camera.cpp reverseDepth + generateCameraFrustum
+#include "srgb_lines.h.glsl"           // reference: srgb.h.glsl fromLinear / toLinear (generated: the `.rgb` swizzles rewritten)
 
 #include <atomic>
 #include <cmath>
@@ -156,6 +157,15 @@ void ref_mesh_shader(const glsl::VisbufferPushConstants* pc, const uint32_t* dra
 		}
 	}
 }
+
+// visbuffer_resolve.comp.glsl:39 `vec4 resolved = fromLinear(material.albedoFactor)` with the reference's srgb.h.glsl:26-32 against glm
+void ref_from_linear(const float in[4], float out[4]) {
+	const glm::vec4 r = glsl::fromLinear(glm::vec4(in[0], in[1], in[2], in[3]));
+	out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+// visbuffer.h.glsl:62-65
+void ref_unpack_visbuffer(uint32_t v, uint32_t* drawIndex, uint32_t* primitiveId) { glsl::unpackVisBuffer(v, *drawIndex, *primitiveId); }
+uint32_t ref_visbuffer_clear_value() { return glsl::visbufferClearValue; }
 
 uint32_t ref_pack_visbuffer(uint32_t drawIndex, uint32_t primitiveId) { return glsl::packVisBuffer(drawIndex, primitiveId); }
 

@@ -406,6 +406,36 @@ def test_mesh_shader_arithmetic_matches_the_reference_text(ref_shim, name):
     assert tot["culled"] > 0 or name == "mirrored"
 
 
+# ------------------------------------------------------------------------------------------ reference-pinned: the resolve pass's arithmetic
+def test_resolve_arithmetic_matches_the_reference_text(ref_shim):
+    """visbuffer_resolve.comp.glsl:33,39: unpackVisBuffer (visbuffer.h.glsl:62-65), the clear value (:67) and fromLinear(albedoFactor)
+    (srgb.h.glsl:26-32) compiled from the reference's text against glm: the oracle's per-channel restatement gives the same bits."""
+    L = O.lib()
+    L.orc_from_linear.restype = C.c_float
+    L.orc_from_linear.argtypes = [C.c_float]
+    ref_shim.ref_from_linear.restype = None
+    ref_shim.ref_from_linear.argtypes = [C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(7)
+    edge = np.array([0.0, 0.0031308, np.nextafter(np.float32(0.0031308), np.float32(0)), np.nextafter(np.float32(0.0031308), np.float32(1)),
+                     1.0, 0.5, 1e-6, 0.2, 0.999999, 2.0, 16.0], np.float32)
+    vals = np.concatenate([edge, rng.random(20000).astype(np.float32), (rng.random(2000) * 0.01).astype(np.float32)])
+    vals = vals[: vals.size // 4 * 4].reshape(-1, 4)
+    out = np.zeros(4, np.float32)
+    for row in vals:
+        row = np.ascontiguousarray(row)
+        ref_shim.ref_from_linear(row.ctypes.data, out.ctypes.data)
+        mine = np.array([L.orc_from_linear(float(row[k])) for k in range(3)], np.float32)
+        assert np.array_equal(mine.view(np.uint32), out[:3].view(np.uint32)), (row, mine, out)
+        assert out[3] == row[3]                                        # alpha passes through (srgb.h.glsl:31)
+    ref_shim.ref_unpack_visbuffer.argtypes = [C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    ref_shim.ref_visbuffer_clear_value.restype = C.c_uint32
+    assert ref_shim.ref_visbuffer_clear_value() == abi.VISBUFFER_CLEAR
+    for v in [0, 1, 127, 128, 0x12345678, 0xFFFFFFFE, *rng.integers(0, 2**32, 500, dtype=np.uint64).tolist()]:
+        d, t = C.c_uint32(), C.c_uint32()
+        ref_shim.ref_unpack_visbuffer(int(v), C.byref(d), C.byref(t))
+        assert (d.value, t.value) == (int(v) >> abi.TRIANGLE_BITS, int(v) & ((1 << abi.TRIANGLE_BITS) - 1))   # what orc_resolve / resolve.cu compute
+
+
 # ------------------------------------------------------------------------------------------ optional normal-cone cull (extension)
 def _cone_scenes():
     rng = np.random.default_rng(3)
