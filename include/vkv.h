@@ -109,7 +109,8 @@ int vkv_frame(vkv_ctx*, const vkv_VisbufferPushConstants* pc, uint32_t flags, vk
  *   vkv_frame_submit   vkv_frame without the wait: enqueues the frame and the device->host copy of its counters, returns a ticket (!= 0).
  *                      At most 4 tickets may be outstanding (VKV_ERR_LIMIT).  VKV_FRAME_TIMED / _STAGES are refused (blocking by nature).
  *   vkv_frame_wait     blocks until that frame and its counters have arrived; fills `out` (may be NULL) exactly as vkv_frame does
- *                      (the *_ms fields stay 0) and releases the ticket. */
+ *                      (the *_ms fields stay 0) and releases the ticket.  It does not drain the stream: a multi-GPU barrier timeout of a
+ *                      submitted frame is reported by the next vkv_sync / vkv_read_* / blocking vkv_frame, as for vkv_frame(out = NULL). */
 int vkv_update_staged(vkv_ctx*, uint64_t dev_addr, const void* pinned_host, size_t bytes);
 int vkv_frame_submit(vkv_ctx*, const vkv_VisbufferPushConstants* pc, uint32_t flags, uint32_t* ticket);
 int vkv_frame_wait(vkv_ctx*, uint32_t ticket, vkv_stats* out);
