@@ -80,8 +80,13 @@ int32_t vkvh_scene_add_node_mesh(vkvh_scene*, int32_t parent, const int32_t* pri
  * POSITION accessors of any component type incl. KHR_mesh_quantization (fastgltf's convertComponent rules), u8 / u16 / u32 or
  * generated indices, materials (baseColorFactor, alphaCutoff, doubleSided; index + 1), meshes with several primitives, node TRS
  * or matrices (decomposed like fastgltf::math::decomposeTransformMatrix), scenes[scene].nodes.  Returns a finalized scene or NULL
- * with a message in err (EXT_meshopt_compression views, sparse accessors and external files are refused with a reason). */
+ * with a message in err (EXT_meshopt_compression views are refused with a reason: they are decoded on the device; external files need
+ * vkvh_scene_load_file, which knows the asset's folder). */
 vkvh_scene* vkvh_scene_load_glb(const void* data, size_t bytes, char* err, size_t errcap);
+/* The same for an asset FILE, .glb or .gltf (AssetLoadTask::loadGltf, assets.cpp:526-552: MappedGltfFile::FromPath + Parser::loadGltf with
+ * the asset's folder) including what BufferLoadTask does (assets.cpp:36-68): buffers whose uri names a local file are read from the
+ * asset's folder (percent-decoded, byteLength bytes).  Sparse accessors are densified as fastgltf's iterateAccessor reads them. */
+vkvh_scene* vkvh_scene_load_file(const char* path, char* err, size_t errcap);
 /* walks the node tree depth-first and emits MeshletDraw[] + transforms[] (world.cpp:230-345) */
 int vkvh_scene_finalize(vkvh_scene*);
 

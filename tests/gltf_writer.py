@@ -94,9 +94,34 @@ class GlbWriter:
             self.doc["nodes"][parent].setdefault("children", []).append(i)
         return i
 
-    def glb(self) -> bytes:
+    def sparse_positions(self, base, indices, values, with_base=True) -> int:
+        """a VEC3 float accessor whose elements `indices` are overridden by `values` (glTF 2.0 sparse accessor); with_base=False: no
+        bufferView, the untouched elements read as zeros"""
+        b = np.ascontiguousarray(base, np.float32)
+        i = np.ascontiguousarray(indices)
+        v = np.ascontiguousarray(values, np.float32)
+        a = {"componentType": 5126, "count": int(b.shape[0]), "type": "VEC3",
+             "sparse": {"count": int(i.size), "indices": {"bufferView": self._view(i.tobytes()), "componentType": CT[i.dtype]},
+                        "values": {"bufferView": self._view(v.tobytes())}}}
+        if with_base:
+            a["bufferView"] = self._view(b.tobytes())
+        self.doc["accessors"].append(a)
+        return len(self.doc["accessors"]) - 1
+
+    def gltf(self, uri=None) -> tuple:
+        """the same asset as a .gltf JSON document: (json bytes, bin bytes) with buffers[0].uri = `uri`, or, uri=None, a base64 data uri"""
+        import base64
         doc = dict(self.doc)
-        doc["buffers"] = [{"byteLength": len(self.bin)}]
+        bn = bytes(self.bin)
+        doc["buffers"] = [{"byteLength": len(bn), "uri": uri if uri is not None else "data:application/octet-stream;base64," + base64.b64encode(bn).decode()}]
+        for k in ("materials", "extensionsUsed"):
+            if not doc[k]:
+                del doc[k]
+        return json.dumps(doc, indent=1).encode(), bn
+
+    def glb(self, extra_buffers=()) -> bytes:
+        doc = dict(self.doc)
+        doc["buffers"] = [{"byteLength": len(self.bin)}] + list(extra_buffers)
         for k in ("materials", "extensionsUsed"):
             if not doc[k]:
                 del doc[k]

@@ -114,7 +114,7 @@ def test_matrix_nodes_decompose_like_fastgltf(ref_shim):
 
 
 @pytest.mark.parametrize("breakage,needle", [
-    ("magic", "magic"), ("truncated", "exceeds"), ("meshopt", "EXT_meshopt_compression"), ("sparse", "sparse"), ("badindex", "index out of range"),
+    ("magic", "magic"), ("truncated", "exceeds"), ("meshopt", "EXT_meshopt_compression"), ("sparse", "sparse accessor"), ("badindex", "index out of range"),
 ])
 def test_malformed_assets_are_refused_with_a_reason(breakage, needle):
     pos, idx = S.grid_mesh(3, 3, lambda u, v: (u, v, 0 * u))
@@ -134,3 +134,80 @@ def test_malformed_assets_are_refused_with_a_reason(breakage, needle):
     with pytest.raises(ValueError) as e:
         Scene.from_glb(bytes(data))
     assert needle in str(e.value)
+
+
+def _asset():
+    rng = np.random.default_rng(21)
+    posA, idxA = S.grid_mesh(14, 11, lambda u, v: (u * 2, 0.3 * np.sin(u * 7), v * 2))
+    qB = rng.integers(-900, 900, (30, 3)).astype(np.int16)
+    idxB = rng.integers(0, 30, 66).astype(np.uint32)
+    w = GlbWriter()
+    m = w.material((0.3, 0.6, 0.9, 1.0), double_sided=True)
+    mesh = w.mesh([{"position": w.positions(posA), "indices": w.indices(idxA.astype(np.uint16)), "material": m},
+                   {"position": w.positions(qB), "indices": w.indices(idxB.astype(np.uint8))}])
+    root = w.node(mesh, translation=(0, 1, 0))
+    w.node(mesh, parent=root, scale=(2, 2, -2))
+    return w
+
+
+def test_gltf_files_with_external_and_embedded_buffers_equal_the_glb(tmp_path):
+    """AssetLoadTask::loadGltf takes .gltf and .glb alike (assets.cpp:526-552) and BufferLoadTask reads buffers whose uri names a file
+    in the asset's folder (assets.cpp:36-68): the same asset as a GLB blob, a .glb file, a .gltf + .bin pair (plain and percent-encoded
+    file name) and a .gltf with a base64 data uri must give byte-identical scenes."""
+    w = _asset()
+    ref = Scene.from_glb(w.glb())
+    (tmp_path / "a.glb").write_bytes(w.glb())
+    same_scene(Scene.from_file(tmp_path / "a.glb"), ref)
+    js, bn = w.gltf(uri="a.bin")
+    (tmp_path / "a.gltf").write_bytes(js); (tmp_path / "a.bin").write_bytes(bn + b"trailing bytes beyond byteLength are not read")
+    same_scene(Scene.from_file(tmp_path / "a.gltf"), ref)
+    js, bn = w.gltf(uri="my%20buffers/geo%2B1.bin")                    # fastgltf::URI::fspath(): percent-decoded
+    (tmp_path / "my buffers").mkdir()
+    (tmp_path / "b.gltf").write_bytes(b"\xef\xbb\xbf" + js); (tmp_path / "my buffers" / "geo+1.bin").write_bytes(bn)
+    same_scene(Scene.from_file(tmp_path / "b.gltf"), ref)
+    js, _ = w.gltf(uri=None)                                             # embedded: data:application/octet-stream;base64,...
+    (tmp_path / "c.gltf").write_bytes(js)
+    same_scene(Scene.from_file(tmp_path / "c.gltf"), ref)
+    # failures carry the reference's messages
+    with pytest.raises(ValueError, match="Failed to open glTF file"):
+        Scene.from_file(tmp_path / "missing.gltf")
+    js, _ = w.gltf(uri="gone.bin")
+    (tmp_path / "d.gltf").write_bytes(js)
+    with pytest.raises(ValueError, match="Failed to open buffer"):
+        Scene.from_file(tmp_path / "d.gltf")
+    js, bn = w.gltf(uri="short.bin")
+    (tmp_path / "e.gltf").write_bytes(js); (tmp_path / "short.bin").write_bytes(bn[:100])
+    with pytest.raises(ValueError, match="Failed to open buffer|shorter"):
+        Scene.from_file(tmp_path / "e.gltf")
+    js, _ = w.gltf(uri="https://example.invalid/a.bin")
+    (tmp_path / "f.gltf").write_bytes(js)
+    with pytest.raises(ValueError, match="only local files"):
+        Scene.from_file(tmp_path / "f.gltf")
+    with pytest.raises(ValueError, match="no asset folder"):              # a blob has no folder to resolve a file name against
+        Scene.from_glb(w.glb(extra_buffers=[{"byteLength": 4, "uri": "x.bin"}]))
+    (tmp_path / "x.bin").write_bytes(b"\0\0\0\0")                         # ... a GLB FILE has one: its second buffer is read from beside it
+    (tmp_path / "h.glb").write_bytes(w.glb(extra_buffers=[{"byteLength": 4, "uri": "x.bin"}]))
+    same_scene(Scene.from_file(tmp_path / "h.glb"), ref)
+    (tmp_path / "g.gltf").write_bytes(b"{ not json")
+    with pytest.raises(ValueError, match="malformed glTF JSON"):
+        Scene.from_file(tmp_path / "g.gltf")
+
+
+@pytest.mark.parametrize("with_base", [True, False])
+def test_sparse_accessors_are_read_like_iterate_accessor(with_base):
+    """glTF 2.0 sparse accessors as fastgltf's iterateAccessor hands them to assets.cpp:310-314: the (index, value) pairs override the base
+    view's elements — or zeros when the accessor has no bufferView."""
+    pos, idx = S.grid_mesh(8, 6, lambda u, v: (u, v, 0 * u))
+    rng = np.random.default_rng(5)
+    where = np.sort(rng.choice(pos.shape[0], 9, replace=False)).astype(np.uint16)
+    vals = rng.normal(size=(9, 3)).astype(np.float32)
+    w = GlbWriter()
+    w.node(w.mesh([{"position": w.sparse_positions(pos, where, vals, with_base=with_base), "indices": w.indices(idx.astype(np.uint16))}]))
+    got = Scene.from_glb(w.glb())
+    want = pos.copy() if with_base else np.zeros_like(pos)
+    want[where] = vals
+    ref = Scene.new()
+    ref.add_node(ref.add_primitive(want, idx, 0))
+    ref.finalize()
+    # (no accessor min / max on either side: primitive AABBs are zero vectors, assets.cpp:303-306)
+    same_scene(got, ref)

@@ -21,6 +21,7 @@
 #include "scene.hpp"
 
 #include <cstdio>
+#include <deque>
 #include <cstdlib>
 #include <functional>
 #include <map>
@@ -189,11 +190,38 @@ void decompose(const float* m16, float t[3], float r[4], float s[3]) {
 	std::memcpy(r, q, 16);
 }
 
+// fastgltf::URI::fspath(): the percent-decoded path of a local uri
+std::string percent_decode(const std::string& u) {
+	std::string out;
+	for (size_t i = 0; i < u.size(); ++i) {
+		auto hex = [](char c) { return c >= '0' && c <= '9' ? c - '0' : c >= 'a' && c <= 'f' ? c - 'a' + 10 : c >= 'A' && c <= 'F' ? c - 'A' + 10 : -1; };
+		if (u[i] == '%' && i + 2 < u.size() && hex(u[i + 1]) >= 0 && hex(u[i + 2]) >= 0) { out.push_back((char)(hex(u[i + 1]) * 16 + hex(u[i + 2]))); i += 2; }
+		else out.push_back(u[i]);
+	}
+	return out;
+}
+
+bool read_file(const std::string& path, std::vector<uint8_t>& out, size_t limit = (size_t)-1) {
+	FILE* f = std::fopen(path.c_str(), "rb");
+	if (!f) return false;
+	std::fseek(f, 0, SEEK_END);
+	long n = std::ftell(f);
+	std::fseek(f, 0, SEEK_SET);
+	if (n < 0) { std::fclose(f); return false; }
+	size_t want = (size_t)n < limit ? (size_t)n : limit;
+	out.resize(want);
+	const size_t got = want ? std::fread(out.data(), 1, want, f) : 0;
+	std::fclose(f);
+	return got == want;
+}
+
 struct Loader {
 	const uint8_t* bin = nullptr; size_t binSize = 0;
 	Json doc;
-	std::vector<std::vector<uint8_t>> owned; // decoded data-URI buffers
+	std::deque<std::vector<uint8_t>> owned; // decoded data-URI buffers, external files, densified sparse accessors (addresses stay put)
 	std::vector<View> buffers;
+	std::string baseDir;                    // folder of the asset file (assetPath.parent_path(), assets.cpp:548,558); empty = no file access
+	bool haveDir = false;
 
 	View bufferView(long long idx) {
 		const Json* bvs = doc.get("bufferViews");
@@ -212,11 +240,10 @@ struct Loader {
 		const Json* as = doc.get("accessors");
 		if (!as || idx < 0 || (size_t)idx >= as->size()) fail("accessor index out of range");
 		const Json& a = as->arr[(size_t)idx];
-		if (a.has("sparse")) fail("sparse accessors are not supported");
-		if (!a.has("bufferView")) fail("accessor without bufferView");
+		const Json* sparse = a.get("sparse");
+		if (!a.has("bufferView") && !sparse) fail("accessor without bufferView");
 		Acc r;
 		r.json = &a;
-		r.view = bufferView(a.integer("bufferView", -1));
 		r.offset = (size_t)a.integer("byteOffset", 0);
 		r.count = (size_t)a.integer("count", 0);
 		r.ctype = (int)a.integer("componentType", 0);
@@ -226,8 +253,39 @@ struct Loader {
 		r.comps = t == "SCALAR" ? 1 : t == "VEC2" ? 2 : t == "VEC3" ? 3 : t == "VEC4" ? 4 : 0;
 		const size_t cs = ctype_size(r.ctype);
 		if (!cs || !r.comps) fail("accessor with an unsupported componentType / type");
-		const size_t stride = r.view.stride ? r.view.stride : cs * r.comps;
-		if (r.count && r.offset + (r.count - 1) * stride + cs * r.comps > r.view.size) fail("accessor exceeds its bufferView");
+		const size_t elem = cs * r.comps;
+		if (a.has("bufferView")) {
+			r.view = bufferView(a.integer("bufferView", -1));
+			const size_t stride = r.view.stride ? r.view.stride : elem;
+			if (r.count && r.offset + (r.count - 1) * stride + elem > r.view.size) fail("accessor exceeds its bufferView");
+		} else r.view = View{nullptr, 0, 0};
+		if (sparse) {
+			// glTF 2.0 §3.6.2.3 as fastgltf's iterateAccessor reads it (tools.hpp: the sparse index / value pairs override the elements of
+			// the base view, or of zeros when the accessor has no bufferView): densified here into a tightly packed copy
+			const size_t n = (size_t)sparse->integer("count", 0);
+			const Json* si = sparse->get("indices"); const Json* sv = sparse->get("values");
+			if (!si || !sv) fail("sparse accessor without indices / values");
+			const int ict = (int)si->integer("componentType", 0);
+			const size_t is = ctype_size(ict);
+			if (ict != 5121 && ict != 5123 && ict != 5125) fail("sparse accessor: indices must be u8 / u16 / u32");
+			const View iv = bufferView(si->integer("bufferView", -1)), vv = bufferView(sv->integer("bufferView", -1));
+			const size_t io = (size_t)si->integer("byteOffset", 0), vo = (size_t)sv->integer("byteOffset", 0);
+			if (n > r.count || io + n * is > iv.size || vo + n * elem > vv.size) fail("sparse accessor exceeds its bufferViews");
+			owned.emplace_back(r.count * elem, (uint8_t)0);
+			std::vector<uint8_t>& dense = owned.back();
+			if (r.view.data) {
+				const size_t stride = r.view.stride ? r.view.stride : elem;
+				for (size_t i = 0; i < r.count; ++i) std::memcpy(&dense[i * elem], r.view.data + r.offset + i * stride, elem);
+			}
+			for (size_t k = 0; k < n; ++k) {
+				uint32_t at = 0;
+				std::memcpy(&at, iv.data + io + k * is, is);
+				if (at >= r.count) fail("sparse accessor: index out of range");
+				std::memcpy(&dense[(size_t)at * elem], vv.data + vo + k * elem, elem);
+			}
+			r.view = View{dense.data(), dense.size(), 0};
+			r.offset = 0;
+		}
 		return r;
 	}
 };
@@ -235,47 +293,37 @@ struct Loader {
 } // namespace
 } // namespace vkvh
 
-extern "C" {
-
-vkvh_scene* vkvh_scene_load_glb(const void* data, size_t bytes, char* err, size_t errcap) {
+// everything after the container: buffers (BIN chunk, data URIs, files beside the asset), then materials / meshes / nodes / scene
+static vkvh_scene* load_document(vkvh::Loader& L) {
 	using namespace vkvh;
-	auto report = [&](const std::string& m) { if (err && errcap) std::snprintf(err, errcap, "%s", m.c_str()); };
 	vkvh_scene* s = nullptr;
 	try {
-		const uint8_t* p = (const uint8_t*)data;
-		auto u32 = [&](size_t o) { uint32_t v; std::memcpy(&v, p + o, 4); return v; };
-		if (!p || bytes < 20 || u32(0) != 0x46546C67u) fail("not a GLB container (magic)");
-		if (u32(4) != 2) fail("GLB version " + std::to_string(u32(4)) + " (only 2 is supported)");
-		const size_t total = u32(8);
-		if (total > bytes) fail("GLB length field exceeds the data");
-		Loader L;
-		size_t o = 12;
-		const char* json = nullptr; size_t jsonLen = 0;
-		while (o + 8 <= total) {
-			const size_t len = u32(o), type = u32(o + 4);
-			if (o + 8 + len > total) fail("GLB chunk exceeds the container");
-			if (type == 0x4E4F534Au && !json) { json = (const char*)p + o + 8; jsonLen = len; }
-			else if (type == 0x004E4942u && !L.bin) { L.bin = p + o + 8; L.binSize = len; }
-			o += 8 + ((len + 3) & ~(size_t)3);
-		}
-		if (!json) fail("GLB without a JSON chunk");
-		if (!JsonParser(json, jsonLen).parse(L.doc) || L.doc.kind != Json::Object) fail("malformed glTF JSON");
-
 		if (const Json* bufs = L.doc.get("buffers"))
 			for (size_t i = 0; i < bufs->size(); ++i) {
 				const Json& b = bufs->arr[i];
 				const Json* uri = b.get("uri");
+				const size_t byteLength = (size_t)b.integer("byteLength", 0);
 				if (!uri) { // the GLB-stored buffer
 					if (i != 0 || !L.bin) fail("buffer without uri that is not the GLB BIN chunk");
-					if ((size_t)b.integer("byteLength", 0) > L.binSize) fail("buffers[0].byteLength exceeds the BIN chunk");
-					L.buffers.push_back(View{L.bin, (size_t)b.integer("byteLength", 0), 0});
+					if (byteLength > L.binSize) fail("buffers[0].byteLength exceeds the BIN chunk");
+					L.buffers.push_back(View{L.bin, byteLength, 0});
 				} else {
 					const std::string& u = uri->str;
-					const size_t comma = u.find(',');
-					if (u.compare(0, 5, "data:") != 0 || comma == std::string::npos || u.find(";base64") == std::string::npos)
-						fail("external buffer uri '" + u.substr(0, 40) + "': only the GLB chunk and base64 data URIs are read here");
-					L.owned.push_back(base64(u, comma + 1));
-					L.buffers.push_back(View{L.owned.back().data(), L.owned.back().size(), 0});
+					if (u.compare(0, 5, "data:") == 0) {
+						const size_t comma = u.find(',');
+						if (comma == std::string::npos || u.find(";base64") == std::string::npos) fail("data uri that is not base64");
+						L.owned.push_back(base64(u, comma + 1));
+					} else {
+						// BufferLoadTask (assets.cpp:36-68): folder / uri.fspath(), byteLength bytes; only local files
+						if (!L.haveDir) fail("external buffer uri '" + u.substr(0, 40) + "': no asset folder (load the file with vkvh_scene_load_file)");
+						if (u.find("://") != std::string::npos) fail("external buffer uri '" + u.substr(0, 40) + "': only local files are read (assets.cpp:52)");
+						std::string path = percent_decode(u);
+						if (path.empty() || path[0] != '/') path = L.baseDir + "/" + path;
+						L.owned.emplace_back();
+						if (!read_file(path, L.owned.back(), byteLength) || L.owned.back().size() < byteLength) fail("Failed to open buffer: " + path);
+					}
+					if (L.owned.back().size() < byteLength) fail("buffer shorter than its byteLength");
+					L.buffers.push_back(View{L.owned.back().data(), byteLength ? byteLength : L.owned.back().size(), 0});
 				}
 			}
 
@@ -385,12 +433,77 @@ vkvh_scene* vkvh_scene_load_glb(const void* data, size_t bytes, char* err, size_
 		}
 		if (vkvh_scene_finalize(s) != 0) fail("the draw list exceeds 2^25 MeshletDraws (visbuffer.h.glsl:15-17)");
 		return s;
+	} catch (...) {
+		if (s) vkvh_scene_free(s);
+		throw;
+	}
+}
+
+// GLB container (12-byte header + JSON chunk + optional BIN chunk) or a bare .gltf JSON document -> L.doc / L.bin
+static void open_container(vkvh::Loader& L, const void* data, size_t bytes, bool allowJson) {
+	using namespace vkvh;
+	const uint8_t* p = (const uint8_t*)data;
+	auto u32 = [&](size_t o) { uint32_t v; std::memcpy(&v, p + o, 4); return v; };
+	const bool glb = p && bytes >= 4 && u32(0) == 0x46546C67u;
+	const char* json = nullptr; size_t jsonLen = 0;
+	if (!glb) {
+		if (!allowJson || !p || !bytes) fail("not a GLB container (magic)");
+		json = (const char*)p; jsonLen = bytes;
+		if (jsonLen >= 3 && p[0] == 0xEF && p[1] == 0xBB && p[2] == 0xBF) { json += 3; jsonLen -= 3; } // UTF-8 byte order mark
+	} else {
+		if (bytes < 20) fail("not a GLB container (magic)");
+		if (u32(4) != 2) fail("GLB version " + std::to_string(u32(4)) + " (only 2 is supported)");
+		const size_t total = u32(8);
+		if (total > bytes) fail("GLB length field exceeds the data");
+		size_t o = 12;
+		while (o + 8 <= total) {
+			const size_t len = u32(o), type = u32(o + 4);
+			if (o + 8 + len > total) fail("GLB chunk exceeds the container");
+			if (type == 0x4E4F534Au && !json) { json = (const char*)p + o + 8; jsonLen = len; }
+			else if (type == 0x004E4942u && !L.bin) { L.bin = p + o + 8; L.binSize = len; }
+			o += 8 + ((len + 3) & ~(size_t)3);
+		}
+		if (!json) fail("GLB without a JSON chunk");
+	}
+	if (!JsonParser(json, jsonLen).parse(L.doc) || L.doc.kind != Json::Object) fail("malformed glTF JSON");
+}
+
+extern "C" {
+
+vkvh_scene* vkvh_scene_load_glb(const void* data, size_t bytes, char* err, size_t errcap) {
+	auto report = [&](const std::string& m) { if (err && errcap) std::snprintf(err, errcap, "%s", m.c_str()); };
+	try {
+		vkvh::Loader L;
+		open_container(L, data, bytes, false);
+		return load_document(L);
 	} catch (const vkvh::Fail& f) {
 		report(f.msg);
 	} catch (const std::exception& e) {
 		report(std::string("glTF load failed: ") + e.what());
 	}
-	if (s) vkvh_scene_free(s);
+	return nullptr;
+}
+
+// AssetLoadTask::loadGltf (assets.cpp:526-552: MappedGltfFile::FromPath + Parser::loadGltf(file, assetPath.parent_path(), ...), which takes
+// .gltf and .glb alike) + BufferLoadTask (assets.cpp:36-68: external buffers read from files beside the asset)
+vkvh_scene* vkvh_scene_load_file(const char* path, char* err, size_t errcap) {
+	auto report = [&](const std::string& m) { if (err && errcap) std::snprintf(err, errcap, "%s", m.c_str()); };
+	try {
+		if (!path) vkvh::fail("Failed to open glTF file");
+		std::vector<uint8_t> file;
+		if (!vkvh::read_file(path, file)) vkvh::fail(std::string("Failed to open glTF file: ") + path);   // assets.cpp:529-531
+		vkvh::Loader L;
+		const std::string p(path);
+		const size_t slash = p.find_last_of('/');
+		L.baseDir = slash == std::string::npos ? "." : (slash == 0 ? "/" : p.substr(0, slash));
+		L.haveDir = true;
+		open_container(L, file.data(), file.size(), true);
+		return load_document(L);   // (the scene copies what it keeps: `file` may go)
+	} catch (const vkvh::Fail& f) {
+		report(f.msg);
+	} catch (const std::exception& e) {
+		report(std::string("glTF load failed: ") + e.what());
+	}
 	return nullptr;
 }
 

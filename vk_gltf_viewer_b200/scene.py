@@ -77,6 +77,8 @@ def _lib():
         L.vkvh_scene_city_quantized.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64]
         L.vkvh_scene_load_glb.restype = C.c_void_p
         L.vkvh_scene_load_glb.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]
+        L.vkvh_scene_load_file.restype = C.c_void_p
+        L.vkvh_scene_load_file.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t]
         L.vkvh_scene_add_node_mesh.restype = C.c_int32
         L.vkvh_scene_add_node_mesh.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.vkvh_scene_host_cones.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
@@ -174,6 +176,15 @@ class Scene:
         """glTF 2.0 binary ingest (host/gltf.cpp: what the reference reads of an asset through fastgltf)"""
         err = C.create_string_buffer(512)
         h = _lib().vkvh_scene_load_glb(data, len(data), err, len(err))
+        if not h:
+            raise ValueError(err.value.decode() or "glTF load failed")
+        return cls(h)
+
+    @classmethod
+    def from_file(cls, path):
+        """a .glb or .gltf file, external buffers read from its folder (AssetLoadTask::loadGltf + BufferLoadTask, assets.cpp:36-68,526-552)"""
+        err = C.create_string_buffer(512)
+        h = _lib().vkvh_scene_load_file(str(path).encode(), err, len(err))
         if not h:
             raise ValueError(err.value.decode() or "glTF load failed")
         return cls(h)
