@@ -103,7 +103,8 @@ int vkv_frame(vkv_ctx*, const vkv_VisbufferPushConstants* pc, uint32_t flags, vk
  * flight, each with its own camera buffer / draw buffer / command pool, and waits on the fence of the frame slot it is about to reuse
  * (application.cpp:133,153,167,642; camera.cpp:86, world.cpp:5-6).  The same shape here:
  *   vkv_update_staged  copies from PINNED host memory on the context's upload stream, i.e. beside the kernels of the frame before;
- *                      everything enqueued afterwards on the context (frames, stage calls, reads) waits for it.  The caller owns the
+ *                      the next vkv_frame / vkv_frame_submit (and vkv_sync) waits for it.  The individually callable stages and the
+ *                      vkv_read_* / vkv_download family do NOT: pair those with vkv_update, or call vkv_sync in between.  The caller owns the
  *                      hazard the reference owns too: the destination must not be read by a frame still in flight (use one camera /
  *                      transform buffer per frame slot), and the pinned source must stay untouched until that frame has been waited for.
  *   vkv_frame_submit   vkv_frame without the wait: enqueues the frame and the device->host copy of its counters, returns a ticket (!= 0).
