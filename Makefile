@@ -1,5 +1,6 @@
 # Build everything in-tree (artefacts are git-ignored but travel to the GPU box with gpurun).
 #   make            -> libvkv.so (CUDA, sm_100a) + libvkv_host.so (host generators) + oracle/liboracle.so
+#   make examples   -> examples/headless (the reference's frame loop against libvkv, no display)
 #   make ref        -> oracle/_ref/*.so from the reference's own sources (only where /root/reference exists)
 NVCC      ?= /usr/local/cuda/bin/nvcc
 CXX       ?= g++
@@ -38,10 +39,16 @@ $(PKG)/libvkv_host.so: $(HOST_SRCS) $(HOST_HDRS)
 oracle/liboracle.so: oracle/oracle.cpp oracle/meshopt_decode.cpp oracle/meshlet_build.cpp oracle/accessors.cpp oracle/oracle.h include/vkv_abi.h
 	$(CXX) $(CXXFLAGS) -O3 -mavx2 -shared -o $@ oracle/oracle.cpp oracle/meshopt_decode.cpp oracle/meshlet_build.cpp oracle/accessors.cpp
 
+# the reference's frame loop against the C ABI, display-free (C++, the reference's language); links cudart for pinned staging memory only
+examples: examples/headless
+examples/headless: examples/headless.cpp $(PKG)/libvkv.so $(PKG)/libvkv_host.so include/vkv.h include/vkv_host.h
+	$(CXX) -O2 -std=c++17 -Wall -Wextra -o $@ $< -Iinclude -I/usr/local/cuda/include -L$(PKG) -lvkv -lvkv_host \
+	    -L/usr/local/cuda/lib64 -lcudart -Wl,-rpath,'$$ORIGIN/../$(PKG)'
+
 ref:
 	@if [ -d /root/reference ]; then sh oracle/build_ref.sh; else echo "no /root/reference here: using prebuilt oracle/_ref if present"; fi
 
 clean:
-	rm -rf $(PKG)/libvkv.so $(PKG)/libvkv_host.so oracle/liboracle.so $(PKG)/ptxas.log build
+	rm -rf $(PKG)/libvkv.so $(PKG)/libvkv_host.so oracle/liboracle.so $(PKG)/ptxas.log build examples/headless
 
-.PHONY: all ref clean
+.PHONY: all ref clean examples
