@@ -7,7 +7,8 @@
 #   oracle/_ref/libref_shim.so     culling.h.glsl (isAabbInFrustum, getWorldSpaceAabbExtent, aabbPositions, projectAabb) and
 #                                  visbuffer.task.glsl:57-61 (mip selection), visbuffer.mesh.glsl:44,61,65,71,90-98 (vertex transform,
 #                                  determinants, facing decision) + the shared layout headers compiled as C++ against
-#                                  the reference's glm; camera.cpp:38-48,70-84 (reverseDepth, generateCameraFrustum); glm
+#                                  the reference's glm; hiz_reduce.comp.glsl:11-15,21-31 + application.cpp:472-473,965,979 (the
+#                                  reduce shader's main and its dispatch sizes); camera.cpp:38-48,70-84 (reverseDepth, generateCameraFrustum); glm
 #                                  perspective/lookAt; fastgltf::math translate/rotate/scale.
 # The GLSL task/mesh/fragment/compute shaders themselves cannot be built or run here (no glslang, no Vulkan ICD) — see DESIGN.md.
 set -e
@@ -60,6 +61,28 @@ MESH="$REF/shaders/visbuffer/visbuffer.mesh.glsl"
   printf '\treturn transformDet;\n}\ninline bool meshCull(const vec3* cv, uvec3 indices, float transformDet, float& detOut) {\n\tbool culled;\n'
   sed -n '90,98p' "$MESH" | sed -e 's/clipVertices\[/cv[/g' -e 's/gl_MeshPrimitivesEXT\[pidx\]\.gl_CullPrimitiveEXT =/culled =/'
   printf '\tdetOut = det;\n\treturn culled;\n}\nGLSL_NAMESPACE_END\n'; } > "$TMP/mesh_lines.inc"
+# hiz_reduce.comp.glsl:11-15 (the push-constant struct) and :21-31 (main) against stand-ins for the built-ins (ref_shim.cpp: the two descriptor
+# heaps, gl_GlobalInvocationID, texture(), imageStore()).  Three rewrites, arithmetic untouched: `void main()` -> a named inline function,
+# the swizzle `gl_GlobalInvocationID.xy` -> uvec2(gl_GlobalInvocationID), and GLSL's implicit uvec2 -> vec2 conversion of the divisor written
+# out (`/ pushConstants.imageSize` -> `/ vec2(pushConstants.imageSize)`; glm's operators do not mix element types).
+HIZ="$REF/shaders/hiz_reduce.comp.glsl"
+{ printf 'GLSL_NAMESPACE_BEGIN\n'
+  sed -n '11,15p' "$HIZ"
+  printf 'static thread_local HiZReducePushConstants pushConstants;\n'
+  sed -n '21,31p' "$HIZ" | sed -e 's/^void main()/inline void hizReduceMain()/' -e 's/gl_GlobalInvocationID\.xy/uvec2(gl_GlobalInvocationID)/' \
+      -e 's#/ pushConstants\.imageSize)#/ vec2(pushConstants.imageSize))#'
+  printf 'GLSL_NAMESPACE_END\n'; } > "$TMP/hiz_lines.inc"
+grep -q 'vec2(pushConstants.imageSize)' "$TMP/hiz_lines.inc" && grep -q 'hizReduceMain' "$TMP/hiz_lines.inc" || { echo "hiz_reduce.comp.glsl: rewrite did not apply" >&2; exit 1; }
+# application.cpp:472-473 (mip count of the pyramid), :965 (size of the level dispatch i writes) and the two group-count expressions of
+# the vkCmdDispatch at :979, as two inline functions
+APP="$REF/src/vk_gltf_viewer/application.cpp"
+{ printf 'inline std::uint32_t hizMipLevels(glm::u32vec2 renderResolution) {\n'
+  sed -n '472,473p' "$APP"
+  printf '\treturn mipLevels;\n}\ninline void hizDispatch(glm::u32vec2 renderResolution, std::uint32_t i, glm::u32vec2& levelSizeOut, glm::u32vec2& groupsOut) {\n'
+  sed -n '965p' "$APP"
+  sed -n '979p' "$APP" | sed -e 's/vkCmdDispatch(cmd, \(.*\), \(.*\), 1);/groupsOut = glm::u32vec2(\1, \2);/'
+  printf '\tlevelSizeOut = levelSize;\n}\n'; } > "$TMP/hiz_dispatch.inc"
+grep -q 'groupsOut = glm::u32vec2(fg::alignUp' "$TMP/hiz_dispatch.inc" || { echo "application.cpp:979: rewrite did not apply" >&2; exit 1; }
 # srgb.h.glsl is dual GLSL / C++ except for its swizzles: `X.rgb` -> vec3(X) (glm has no .rgb member without swizzle extensions)
 sed -e 's/\([A-Za-z]*\)\.rgb/vec3(\1)/g' "$REF/shaders/srgb.h.glsl" > "$TMP/srgb_lines.h.glsl"
 # camera.cpp free functions reverseDepth (38-48) and generateCameraFrustum (70-84)

@@ -19,6 +19,10 @@
  *     flips inside that bound (none unflagged).  NOTE what that test measures about the REFERENCE: the determinant of three nearly
  *     parallel (x, y, w) vectors cancels catastrophically for small distant triangles — 0.9 % (cfg 3) to 3.9 % (cfg 5) of the facing
  *     decisions depend on how the compiler associates the products.  The oracle's association (below) is the definition here;
+ *   - the HiZ reduce pass except the texture fetch: hiz_reduce.comp.glsl:21-31 (main) run for every invocation of the dispatches
+ *     application.cpp:964-979 records (mip count :472-473, level size :965, group counts :979 are the reference's lines too), with
+ *     orc_sample_min behind texture(): every mip of orc_hiz has the same bits at ten resolutions up to 8K, odd and degenerate ones
+ *     included, and the shader's `>` bound check only produces stores Vulkan discards;
  *   - the data layouts (include/vkv_abi.h static_asserts == the reference headers compiled as C++), packVisBuffer / unpackVisBuffer,
  *     the resolve pass's fromLinear (srgb.h.glsl compiled against glm: bit-identical);
  *   - camera.cpp's reverseDepth / generateCameraFrustum, glm perspective / lookAt, fastgltf::math node matrices, fastgltf's

@@ -19,6 +19,30 @@
 #include "camera_fns.inc"              // reference: camera.cpp reverseDepth + generateCameraFrustum
 #include "srgb_lines.h.glsl"           // reference: srgb.h.glsl fromLinear / toLinear (generated: the `.rgb` swizzles rewritten)
 
+// ---- stand-ins for what hiz_reduce.comp.glsl reads besides its own text: the bindless heaps (resource_table.h.glsl:12-17), the compute
+// built-in, texture() and imageStore().  The sampler behind texture() is a callback (the oracle's orc_sample_min: the Vulkan min-reduction
+// sampler is fixed function, there is no reference code for it); imageStore drops out-of-bounds texels as Vulkan does ("Texel Output
+// Validation": an invalid texel coordinate makes the write have no effect) and counts them.
+#include <fastgltf/util.hpp>
+namespace fg = fastgltf;
+typedef float (*ref_sample_fn)(const float* img, uint32_t w, uint32_t h, float u, float v, int* ambig);
+namespace glsl {
+struct RefSampledImage { const float* img; uint32_t w, h; };
+struct RefStorageImage { float* img; uint32_t w, h; };
+static thread_local RefSampledImage sampled_textures_heap[2];
+static thread_local RefStorageImage writeonly_image2d_r32f_heap[2];
+static thread_local uvec3 gl_GlobalInvocationID;
+static thread_local ref_sample_fn hizSampler;
+static thread_local uint64_t hizDroppedStores;
+inline vec4 texture(const RefSampledImage& s, vec2 uv) { return vec4(hizSampler(s.img, s.w, s.h, uv.x, uv.y, nullptr), 0.f, 0.f, 1.f); }
+inline void imageStore(const RefStorageImage& im, ivec2 p, vec4 v) {
+	if (p.x < 0 || p.y < 0 || (uint32_t)p.x >= im.w || (uint32_t)p.y >= im.h) { ++hizDroppedStores; return; }
+	im.img[(size_t)p.y * im.w + p.x] = v.x;
+}
+} // namespace glsl
+#include "hiz_lines.inc"               // reference: hiz_reduce.comp.glsl:11-15,21-31 push constants + main (generated slice)
+#include "hiz_dispatch.inc"            // reference: application.cpp:472-473,965,979 mip count, level size, group counts (generated slice)
+
 #include <atomic>
 #include <cmath>
 #include <thread>
@@ -27,6 +51,37 @@
 #include <fastgltf/math.hpp>
 
 extern "C" {
+
+// The whole "HiZ reduction" zone (application.cpp:951-1003) with the reference's own shader text: for every dispatch the loop at :964-979
+// records, every invocation of every 32x32 workgroup runs hiz_reduce.comp.glsl's main.  View 0 is the depth image, view i the pyramid's
+// mip i-1 (application.cpp:503-529); the pyramid's mips live where the caller says (offset / extent per mip: Vulkan's max(1, base >> k)
+// of the (W>>1, H>>1) image, application.cpp:482-487).  Returns the reference's mip count (application.cpp:472-473); dropped[0] = stores
+// Vulkan discards (the shader's bound check is `>` where `>=` was meant: invocations at pos == imageSize run and write out of bounds).
+uint32_t ref_hiz_reduce(uint32_t W, uint32_t H, const float* depth, float* pyramid, const uint32_t* mipOff, const uint32_t* mipW, const uint32_t* mipH,
+                        uint32_t levels, ref_sample_fn sample, uint64_t* dropped) {
+	const glm::u32vec2 renderResolution(W, H);
+	const uint32_t mipLevels = hizMipLevels(renderResolution);
+	glsl::hizSampler = sample;
+	glsl::hizDroppedStores = 0;
+	for (std::uint32_t i = 1; i < mipLevels + 1 && i <= levels; ++i) { // depthPyramidViews.size() == mipLevels + 1
+		glm::u32vec2 levelSize, groups;
+		hizDispatch(renderResolution, i, levelSize, groups);
+		glsl::sampled_textures_heap[0] = (i == 1) ? glsl::RefSampledImage{depth, W, H} : glsl::RefSampledImage{pyramid + mipOff[i - 2], mipW[i - 2], mipH[i - 2]};
+		glsl::writeonly_image2d_r32f_heap[1] = glsl::RefStorageImage{pyramid + mipOff[i - 1], mipW[i - 1], mipH[i - 1]};
+		glsl::pushConstants.sourceImage = 0;
+		glsl::pushConstants.outputImage = 1;
+		glsl::pushConstants.imageSize = levelSize;
+		for (uint32_t gy = 0; gy < groups.y; ++gy)
+			for (uint32_t gx = 0; gx < groups.x; ++gx)
+				for (uint32_t ly = 0; ly < 32; ++ly)      // layout(local_size_x = 32, local_size_y = 32), comp.glsl:9
+					for (uint32_t lx = 0; lx < 32; ++lx) {
+						glsl::gl_GlobalInvocationID = glm::uvec3(gx * 32 + lx, gy * 32 + ly, 0);
+						glsl::hizReduceMain();
+					}
+	}
+	if (dropped) *dropped = glsl::hizDroppedStores;
+	return mipLevels;
+}
 
 // culling.h.glsl:8-19
 int ref_is_aabb_in_frustum(const float c[3], const float e[3], const float frustum[24]) {
@@ -67,7 +122,6 @@ void ref_project_aabb(const float c[3], const float e[3], const float vp[16], fl
 // NaN -> 0).  status[i] = 0 frustum-culled, 1 occluded, 2 visible — the oracle's ORC_* values.
 // NOTE glm pairs the adds of mat4*vec4 as (c0x + c1y) + (c2z + c3w); the oracle's policy is left to right.  The two evaluations
 // may therefore differ in the last bits, which is exactly what the oracle's ORC_AMBIG_* / ORC_CROSSES_CAMERA flags are for.
-typedef float (*ref_sample_fn)(const float* img, uint32_t w, uint32_t h, float u, float v, int* ambig);
 void ref_task_cull(const glsl::VisbufferPushConstants* pc, const float* pyramid, const uint32_t* mipOff, const uint32_t* mipW, const uint32_t* mipH,
                    uint32_t levels, int vp_select, ref_sample_fn sample, uint8_t* status, int threads) {
 	const auto* draws = reinterpret_cast<const glsl::MeshletDraw*>(pc->drawBuffer);

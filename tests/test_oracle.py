@@ -336,6 +336,41 @@ def test_task_shader_decisions_match_the_reference_text(ref_shim, name):
         assert r["flagged"] <= 0.02 * r["draws"] + 8, "ambiguity flags must stay the exception"
 
 
+# ------------------------------------------------------------------------------------------ reference-pinned: the HiZ reduce shader + its dispatch loop
+@pytest.mark.parametrize("res", [(640, 480), (1920, 1080), (3840, 2160), (7680, 4320), (1001, 777), (97, 33), (33, 1000), (2, 2), (1, 1), (64, 1)])
+def test_hiz_reduce_matches_the_reference_shader_text(ref_shim, res):
+    """hiz_reduce.comp.glsl:21-31 (main) compiled from the REFERENCE's text, run for every invocation of the dispatches that
+    application.cpp:964-979 records (level size, group counts and mip count are the reference's own lines too), with the oracle's min
+    sampler behind texture(): the oracle's pyramid must have the same bits in every mip, and the same mip count.  What this pins: the
+    sample coordinate arithmetic, which mips a resolution gets and which of them are ever written, and that the shader's
+    `>` bound check (where `>=` was meant) only produces stores Vulkan discards.  What it cannot pin: the sampler rule itself."""
+    W, H = res
+    rng = np.random.default_rng(W * 7919 + H)
+    tg = O.Targets(W, H)
+    tg.depth[:] = rng.random((H, W), dtype=np.float32)
+    tg.pyramid[:] = 7.0                                     # mips no dispatch writes keep this
+    O.hiz(tg)
+    L = O.lib()
+    off = np.array([o for o, _, _ in tg.layout], np.uint32); w = np.array([x for _, x, _ in tg.layout], np.uint32); h = np.array([y for _, _, y in tg.layout], np.uint32)
+    pyr = np.full_like(tg.pyramid, 7.0)
+    dropped = C.c_uint64(0)
+    ref_shim.ref_hiz_reduce.restype = C.c_uint32
+    ref_shim.ref_hiz_reduce.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint64)]
+    levels = ref_shim.ref_hiz_reduce(W, H, tg.depth.ctypes.data, pyr.ctypes.data, off.ctypes.data, w.ctypes.data, h.ctypes.data, tg.levels,
+                                     C.cast(L.orc_sample_min, C.c_void_p), C.byref(dropped))
+    assert levels == tg.levels, "mip count: application.cpp:472-473 vs orc_pyramid_layout"
+    assert np.array_equal(pyr.view(np.uint32), tg.pyramid.view(np.uint32))
+    # the `>` quirk: a level whose size is not a multiple of 32 has one extra row / column of invocations, all of them dropped
+    want_dropped = 0
+    for i in range(1, tg.levels + 1):
+        dw, dh = W >> i, H >> i
+        if dw == 0 or dh == 0:
+            continue
+        gw, gh = -(-dw // 32) * 32, -(-dh // 32) * 32
+        want_dropped += min(gw, dw + 1) * min(gh, dh + 1) - dw * dh
+    assert dropped.value == want_dropped
+
+
 # ------------------------------------------------------------------------------------------ reference-pinned: the mesh shader's arithmetic
 def _ref_mesh_shader(ref_shim, pc, draw_ids):
     """visbuffer.mesh.glsl:44,61,65,71,90-98 evaluated with the reference's own lines against glm (oracle/ref_shim.cpp::ref_mesh_shader)"""
