@@ -37,19 +37,18 @@ HIZ_CHAINS = [(97, 33), (480, 270)]           # 270 -> 135 -> 67: odd sources, w
 
 
 def build_raster_case(kind, p, stored_positions=None):
-    """-> (scene, push constants, W, H, positions or None); positions come from the fixture when given (rng streams are not part of the contract)"""
+    """-> (scene, camera, W, H, positions or None); positions come from the fixture when given (rng streams are not part of the contract)"""
     if kind == "scene":
         make, (W, H) = K.SCENE_CASES[p["name"]]
         scene, cam = make(W, H)
-        return scene, scene.host_push_constants(cam), W, H, None
+        return scene, cam, W, H, None
     if kind == "lattice":
         W = H = p["size"]
         P = stored_positions if stored_positions is not None else K.lattice_positions(np.random.default_rng(p["seed"]), W, H, p["ntri"])
     else:
         W, H = p["W"], p["H"]
         P = stored_positions if stored_positions is not None else K.float_positions(np.random.default_rng(p["seed"]), p["ntri"], p["scale"], inside=True)
-    scene = K.soup_scene(P)
-    return scene, scene.host_push_constants(K.identity_camera(W, H)), W, H, P
+    return K.soup_scene(P), K.identity_camera(W, H), W, H, P
 
 
 def triangles_digest(V, I):
@@ -66,8 +65,8 @@ if __name__ == "__main__":
     lp = LP.instance()
     out = {"renderer": np.frombuffer((lp.renderer + " / " + lp.version).encode(), np.uint8)}
     for name, (kind, p) in RASTER_CASES.items():
-        scene, pc, W, H, P = build_raster_case(kind, p)
-        V, I = K.oracle_triangles(scene, pc)
+        scene, cam, W, H, P = build_raster_case(kind, p)
+        V, I = K.oracle_triangles(scene, scene.host_push_constants(cam))
         ids, depth = lp.raster(W, H, V, I)
         if P is not None:
             out[f"raster_{name}_positions"] = P
