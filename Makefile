@@ -1,7 +1,7 @@
 # Build everything in-tree (artefacts are git-ignored but travel to the GPU box with gpurun).
 #   make            -> libvkv.so (CUDA, sm_100a) + libvkv_host.so (host generators) + oracle/liboracle.so
 #   make examples   -> examples/headless (the reference's frame loop against libvkv, no display)
-#   make ref        -> oracle/_ref/*.so from the reference's own sources (only where /root/reference exists)
+#   make ref        -> oracle/_ref/*.so from the reference's own sources (only where /root/reference exists) + oracle/_ref/fakex (llvmpipe pin)
 NVCC      ?= /usr/local/cuda/bin/nvcc
 CXX       ?= g++
 PKG       := vk_gltf_viewer_b200
@@ -47,8 +47,13 @@ examples/headless: examples/headless.cpp $(PKG)/libvkv.so $(PKG)/libvkv_host.so 
 
 ref:
 	@if [ -d /root/reference ]; then sh oracle/build_ref.sh; else echo "no /root/reference here: using prebuilt oracle/_ref if present"; fi
+	@sh oracle/llvmpipe/build.sh
+
+# the Xlib stand-in that lets tests drive llvmpipe (Mesa's libGL inside Nsight Compute) without an X server; test infrastructure
+llvmpipe:
+	sh oracle/llvmpipe/build.sh
 
 clean:
 	rm -rf $(PKG)/libvkv.so $(PKG)/libvkv_host.so oracle/liboracle.so $(PKG)/ptxas.log build examples/headless
 
-.PHONY: all ref clean examples
+.PHONY: all ref clean examples llvmpipe

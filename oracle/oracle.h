@@ -4,11 +4,16 @@
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it,
  * and only as the checker (or as the timed CPU baseline), never on the product path.
  *
- * PARITY UNPINNED for the sampler footprint rule, the fixed-function rasteriser and (through the sampler rule) the HiZ outputs: the
- * reference ships no tests, golden images or known-answer vectors for these stages, its shaders cannot be run in
- * this image (no Vulkan loader / lavapipe / glslang), and for these three there is no reference CODE at all — they are Vulkan
- * fixed-function behaviour.  What IS pinned against the reference's own text, compiled as C++ against its glm by
- * oracle/build_ref.sh into oracle/_ref/ (tests/test_oracle.py):
+ * PARITY UNPINNED only for the BITS of interpolated depth (Vulkan leaves that arithmetic to the implementation) and for the sentence
+ * "a MIN-reduction fetch returns the minimum over the texels with non-zero weight" (Vulkan specification; nothing here can execute it).
+ * The reference ships no tests, golden images or known-answer vectors for this path and its shaders cannot be run
+ * in this image (no Vulkan loader / lavapipe / glslang).  Two things pin the rest (tests/test_oracle.py, tests/test_llvmpipe.py):
+ *   (1) the fixed-function stages, for which no reference CODE exists — triangle coverage (pixel centres, top-left rule, 8 sub-pixel
+ *       bits, clipping), the >= depth test, the LINEAR sampler's texel footprint, mip selection — against LLVMPIPE, the rasteriser and
+ *       texture unit underneath lavapipe (Mesa 18.1.9 inside this image's Nsight Compute, driven without an X server through
+ *       oracle/llvmpipe/fakex11.c): identical coverage and ids, identical footprints at every coordinate hiz_reduce samples; depth
+ *       within ~1e-7.  llvmpipe's outputs are committed as tests/golden/llvmpipe.npz;
+ *   (2) the reference's own text, compiled as C++ against its glm by oracle/build_ref.sh into oracle/_ref/:
  *   - the whole per-draw decision of the task shader except the texture fetch: culling.h.glsl (isAabbInFrustum,
  *     getWorldSpaceAabbExtent, aabbPositions, projectAabb), visbuffer.task.glsl:50-52,56-61,64 — on every MeshletDraw of all
  *     five BASELINE configs at full size the oracle's class differs from the glm-evaluated reference only on draws it flags
