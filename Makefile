@@ -41,7 +41,9 @@ oracle/liboracle.so: oracle/oracle.cpp oracle/meshopt_decode.cpp oracle/meshlet_
 
 # the reference's frame loop against the C ABI, display-free (C++, the reference's language); links cudart for pinned staging memory only
 examples: examples/headless
-examples/headless: examples/headless.cpp $(PKG)/libvkv.so $(PKG)/libvkv_host.so include/vkv.h include/vkv_host.h
+# (links against the built libraries without listing them as prerequisites: on a box that received prebuilt .so files but no build/
+# objects this must not trigger an nvcc rebuild — run `make` first on a fresh checkout)
+examples/headless: examples/headless.cpp include/vkv.h include/vkv_host.h
 	$(CXX) -O2 -std=c++17 -Wall -Wextra -o $@ $< -Iinclude -I/usr/local/cuda/include -L$(PKG) -lvkv -lvkv_host \
 	    -L/usr/local/cuda/lib64 -lcudart -Wl,-rpath,'$$ORIGIN/../$(PKG)'
 

@@ -11,10 +11,19 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box via gpurun)")
+    config.addinivalue_line("markers", "late: collected last (see pytest_collection_modifyitems)")
     # host library + oracle are plain g++ builds: make sure they exist for the CPU suite
     need = [os.path.join(ROOT, "vk_gltf_viewer_b200", "libvkv_host.so"), os.path.join(ROOT, "oracle", "liboracle.so")]
     if not all(os.path.exists(p) for p in need):
         subprocess.check_call(["make", "-C", ROOT, "vk_gltf_viewer_b200/libvkv_host.so", "oracle/liboracle.so"])
+
+
+def pytest_collection_modifyitems(config, items):
+    """tests marked `late` run after everything else: GPU tests added after the round's GPU budget was spent (never run on a device yet)
+    must not stand in front of the measured-green ones under `pytest -x`"""
+    late = [i for i in items if i.get_closest_marker("late")]
+    if late:
+        items[:] = [i for i in items if not i.get_closest_marker("late")] + late
 
 
 def has_gpu():
