@@ -59,6 +59,8 @@ SCENE_CASES = {
     "atrium": (lambda W, H: (lambda s: (s, s.default_camera(W, H)))(Scene.atrium(32)), (640, 360)),
     "city": (lambda W, H: (lambda s: (s, s.default_camera(W, H)))(Scene.city(6, 5, 2000, 0x5EED0004)), (640, 360)),
     "lattice": (lambda W, H: (lambda s: (s, s.default_camera(W, H)))(Scene.lattice(3, 3, 3, 60, 0x5EED0003)), (960, 540)),
+    "atrium_cfg2_full": (lambda W, H: (lambda s: (s, s.default_camera(W, H)))(Scene.atrium(128)), (1920, 1080)),   # BASELINE cfg 2 as benchmarked
+    "lattice_4k": (lambda W, H: (lambda s: (s, s.default_camera(W, H)))(Scene.lattice(4, 4, 4, 100, 0x5EED0003)), (3840, 2160)),
     "ground_clipped": (lambda W, H: (S.ground_plane(8, 30.0, -1.0), Camera(W, H).look_at((0, 0, 0), (0, 0, -1))), (400, 300)),
     "mirrored": (lambda W, H: (S.mirrored_instances(), Camera(W, H).look_at((0, 0, 4), (0, 0, 0))), (320, 240)),
     "coplanar": (lambda W, H: (S.coplanar_overlap(), S.camera(W, H)), (160, 120)),

@@ -75,7 +75,8 @@ def test_coverage_and_depth_test_on_lattice_exact_triangles(lp, seed, size, ntri
     assert (ids >= 0).mean() > 0.5
 
 
-@pytest.mark.parametrize("seed,W,H,ntri,scale", [(15, 64, 64, 400, 0.45), (16, 257, 193, 3000, 0.3), (17, 640, 480, 20000, 0.05), (18, 1920, 1080, 60000, 0.02)])
+@pytest.mark.parametrize("seed,W,H,ntri,scale", [(15, 64, 64, 400, 0.45), (16, 257, 193, 3000, 0.3), (17, 640, 480, 20000, 0.05), (18, 1920, 1080, 60000, 0.02),
+                                                 (19, 7680, 4320, 40000, 0.004)])
 @pytest.mark.parametrize("inside", [True, False])
 def test_coverage_on_arbitrary_float_triangles(lp, seed, W, H, ntri, scale, inside):
     """Arbitrary fp32 vertices (w = 1), interpenetrating, depth varying over each triangle: now the viewport transform's and the snap's rounding
@@ -119,7 +120,7 @@ def test_scenes_match_llvmpipe(lp, name):
     print(f"\n{name} {W}x{H}, {V.shape[0] // 3} triangles after the facing test: {r}")
     assert r["covered"] > 1000
     assert r["coverage_differs"] == 0
-    assert r["id_differs"] <= 8 and r["depth_at_id_differs"] < 1e-5     # e.g. the atrium's touching walls
+    assert r["id_differs"] <= 8 + 1e-5 * r["covered"] and r["depth_at_id_differs"] < 1e-5     # surfaces that touch (the atrium's walls)
     assert r["depth_max"] < 5e-5 and r["depth_q50"] < 2e-6
 
 
