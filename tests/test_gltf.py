@@ -223,3 +223,18 @@ def test_mutated_assets_never_crash_the_reader_and_accepted_ones_are_safe_to_dra
     assert p.returncode == 0, p.stderr[-2000:]
     r = json.loads(p.stdout.splitlines()[0])
     assert r["iterations"] == 600 and r["accepted"] > 20 and r["refused"] > 300 and r["distinct_refusals"] >= 10
+
+
+def test_primitives_built_on_all_cores_land_in_document_order():
+    """the meshlet builds of an asset's primitives run in parallel (like the reference's PrimitiveProcessingTask, assets.cpp:192-215); the scene
+    must be the one the sequential direct API builds, byte for byte, primitive order included"""
+    w, ref = GlbWriter(), Scene.new()
+    m = w.material((0.5, 0.5, 0.5, 1.0), double_sided=False)
+    rm = ref.add_material((0.5, 0.5, 0.5, 1.0), False)
+    for k in range(13):
+        pos, idx = S.grid_mesh(10 + 3 * k, 7 + k, lambda u, v, k=k: (u * 3, 0.2 * np.sin(u * (5 + k)) * np.cos(v * 7), v * 2))
+        mesh = w.mesh([{"position": w.positions(pos), "indices": w.indices(idx.astype(np.uint32)), "material": m}])
+        w.node(mesh, translation=(k * 4.0, 0, 0))
+        ref.add_mesh_node([ref.add_primitive(pos, idx, rm)], translation=(k * 4.0, 0, 0))
+    ref.finalize()
+    same_scene(Scene.from_glb(w.glb()), ref)

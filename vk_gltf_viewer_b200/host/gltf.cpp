@@ -27,6 +27,9 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <atomic>
+#include <thread>
+#include <algorithm>
 
 namespace vkvh {
 namespace {
@@ -339,7 +342,22 @@ static vkvh_scene* load_document(vkvh::Loader& L) {
 				s->materials[idx].alphaCutoff = (float)m.number("alphaCutoff", 0.5);
 			}
 
-		// meshes -> primitives (assets.cpp:288-373), flattened in mesh order like the reference's primitiveBuffers
+		// meshes -> primitives (assets.cpp:288-373), flattened in mesh order like the reference's primitiveBuffers.  Two phases, like the
+		// reference's PrimitiveProcessingTask (assets.cpp:192-215,375-430: one task-set partition per mesh on the enkiTS pool): the accessors
+		// are read here in order (cheap, and every refusal is raised in document order), then the meshlet builds — the load-time
+		// dominator, ~1 us per triangle per core — run on all cores, and the results are appended in document order again.
+		struct Job {
+			size_t mesh;
+			std::vector<vkv_Vertex> verts;
+			std::vector<uint32_t> idx;
+			uint32_t materialIndex;
+			float center[3], extents[3];
+			std::vector<int16_t> qpos;
+			bool qnormalized = false;
+			PrimitiveData built;
+			bool ok = false;
+		};
+		std::deque<Job> jobs;
 		std::vector<std::vector<int32_t>> meshPrims;
 		if (const Json* meshes = L.doc.get("meshes"))
 			for (const Json& mesh : meshes->arr) {
@@ -353,14 +371,18 @@ static vkvh_scene* load_document(vkvh::Loader& L) {
 					const Acc pos = L.accessor(attrs->integer("POSITION", -1));
 					if (pos.comps != 3) fail("POSITION accessor is not VEC3");
 					const size_t cs = ctype_size(pos.ctype), stride = pos.view.stride ? pos.view.stride : cs * 3;
-					std::vector<vkv_Vertex> verts(pos.count);
+					jobs.emplace_back();
+					Job& job = jobs.back();
+					job.mesh = meshPrims.size() - 1;
+					std::vector<vkv_Vertex>& verts = job.verts;
+					verts.resize(pos.count);
 					for (size_t i = 0; i < pos.count; ++i) {
 						std::memset(&verts[i], 0, sizeof(vkv_Vertex));
 						const uint8_t* e = pos.view.data + pos.offset + i * stride;
 						for (int k = 0; k < 3; ++k) verts[i].position[k] = to_float(e + k * cs, pos.ctype, pos.normalized);
 						verts[i].color[0] = verts[i].color[1] = verts[i].color[2] = verts[i].color[3] = 255;
 					}
-					std::vector<uint32_t> idx;
+					std::vector<uint32_t>& idx = job.idx;
 					if (pr.has("indices")) {
 						const Acc ia = L.accessor(pr.integer("indices", -1));
 						if (ia.comps != 1 || (ia.ctype != 5121 && ia.ctype != 5123 && ia.ctype != 5125)) fail("index accessor must be SCALAR u8 / u16 / u32");
@@ -377,27 +399,49 @@ static vkvh_scene* load_document(vkvh::Loader& L) {
 						for (size_t i = 0; i < pos.count; ++i) idx[i] = (uint32_t)i;
 					}
 					const long long mat = pr.integer("material", -1);
-					const uint32_t materialIndex = mat >= 0 ? (uint32_t)mat + 1 : 0u;
-					if (materialIndex >= s->materials.size()) fail("primitive.material out of range");
-					PrimitiveData pd;
-					if (!build_primitive(pd, std::move(verts), idx.data(), (uint32_t)idx.size(), materialIndex)) fail("primitive with no triangles or an index out of range");
+					job.materialIndex = mat >= 0 ? (uint32_t)mat + 1 : 0u;
+					if (job.materialIndex >= s->materials.size()) fail("primitive.material out of range");
 					// assets.cpp:303-306: the primitive's AABB comes from the accessor's min / max (zero vectors when absent)
 					float mn[3] = {0, 0, 0}, mx[3] = {0, 0, 0};
 					const Json* jmin = pos.json->get("min"); const Json* jmax = pos.json->get("max");
 					if (jmin && jmin->size() == 3) for (int k = 0; k < 3; ++k) mn[k] = (float)jmin->arr[k].num;
 					if (jmax && jmax->size() == 3) for (int k = 0; k < 3; ++k) mx[k] = (float)jmax->arr[k].num;
 					for (int k = 0; k < 3; ++k) {
-						pd.header.aabbCenter[k] = (mn[k] + mx[k]) / 2.f;
-						pd.header.aabbExtents[k] = mx[k] - pd.header.aabbCenter[k];
+						job.center[k] = (mn[k] + mx[k]) / 2.f;
+						job.extents[k] = mx[k] - job.center[k];
 					}
 					if (pos.ctype == 5122) { // SHORT positions: keep the 16-bit form for the in-register dequantisation (vkv_set_quantized_positions)
-						pd.qpos.assign(pos.count * 4, 0);
-						for (size_t i = 0; i < pos.count; ++i) std::memcpy(&pd.qpos[i * 4], pos.view.data + pos.offset + i * stride, 6);
-						pd.qnormalized = pos.normalized;
+						job.qpos.assign(pos.count * 4, 0);
+						for (size_t i = 0; i < pos.count; ++i) std::memcpy(&job.qpos[i * 4], pos.view.data + pos.offset + i * stride, 6);
+						job.qnormalized = pos.normalized;
 					}
-					meshPrims.back().push_back(add_built_primitive(s, std::move(pd)));
 				}
 			}
+		{
+			std::atomic<size_t> next{0};
+			auto worker = [&]() {
+				for (size_t i; (i = next.fetch_add(1)) < jobs.size();) {
+					Job& job = jobs[i];
+					job.ok = build_primitive(job.built, std::move(job.verts), job.idx.data(), (uint32_t)job.idx.size(), job.materialIndex);
+					std::vector<uint32_t>().swap(job.idx);
+				}
+			};
+			// an injected meshlet builder (tests: the reference's meshoptimizer through ctypes) is called from this thread only
+			const unsigned nt = builder_is_injected() ? 1u : std::max(1u, std::min({32u, std::thread::hardware_concurrency(), (unsigned)jobs.size()}));
+			std::vector<std::thread> pool;
+			for (unsigned t = 1; t < nt; ++t) pool.emplace_back(worker);
+			worker();
+			for (auto& th : pool) th.join();
+		}
+		for (Job& job : jobs) {
+			if (!job.ok) fail("primitive with no triangles or an index out of range");
+			PrimitiveData& pd = job.built;
+			for (int k = 0; k < 3; ++k) { pd.header.aabbCenter[k] = job.center[k]; pd.header.aabbExtents[k] = job.extents[k]; }
+			pd.qpos = std::move(job.qpos);
+			pd.qnormalized = job.qnormalized;
+			meshPrims[job.mesh].push_back(add_built_primitive(s, std::move(pd)));
+		}
+		jobs.clear();
 
 		// nodes (world.cpp:187-228): TRS as given, matrices decomposed (Options::DecomposeNodeMatrices); scene roots in order
 		const Json* nodes = L.doc.get("nodes");

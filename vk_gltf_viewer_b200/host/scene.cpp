@@ -49,6 +49,8 @@ uint32_t vkvh_scene_add_material(vkvh_scene* s, const float albedo[4], int doubl
 
 // processPrimitive (assets.cpp:288-373) for one primitive: meshlets + bounds.  Touches no scene state, so the procedural
 // generators may run it for many primitives side by side (the reference does the same through its task scheduler).
+bool vkvh::builder_is_injected() { return g_build && g_bound; }
+
 bool vkvh::build_primitive(PrimitiveData& pd, std::vector<vkv_Vertex>&& vertices, const uint32_t* indices, uint32_t index_count, uint32_t material_index) {
 	if (vertices.empty() || index_count < 3) return false;
 	for (uint32_t i = 0; i < index_count; ++i)

@@ -35,6 +35,7 @@ void build_meshlets_builtin(const std::vector<vkv_Vertex>& vertices, const std::
                             std::vector<MeshletRec>& meshlets, std::vector<uint32_t>& meshletVertices,
                             std::vector<uint8_t>& meshletTriangles);
 
+bool builder_is_injected(); // vkvh_set_meshlet_builder installed foreign entry points (they are then called from one thread only)
 bool build_primitive(PrimitiveData& pd, std::vector<vkv_Vertex>&& vertices, const uint32_t* indices, uint32_t index_count, uint32_t material_index);
 std::vector<vkv_Vertex> vertices_from_positions(const float* positions, uint32_t vertex_count);
 
