@@ -42,7 +42,6 @@ def test_headless_example_rejects_unknown_arguments():
 
 
 @pytest.mark.gpu
-@pytest.mark.late
 def test_headless_example_renders(tmp_path):
     _build()
     out = tmp_path / "frame.ppm"
