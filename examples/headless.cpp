@@ -2,7 +2,8 @@
 //
 // What Application::run() does around the geometry hot path (application.cpp:620-1010), with the Vulkan task / mesh pipeline and the
 // hiz_reduce dispatches replaced by the C ABI of include/vkv.h and the asset side by include/vkv_host.h:
-//   load the asset (AssetLoadTask, assets.cpp:526-600)            vkvh_scene_load_file  (or a procedural BASELINE scene)
+//   load the asset (AssetLoadTask, assets.cpp:526-600)            vkvh_scene_load_file  (or a procedural BASELINE scene);
+//     EXT_meshopt_compression views (assets.cpp:111-171)            vkvh_set_meshopt_decoder -> vkv_meshopt_* on the device
 //   upload buffers, build the draw list (World::addAsset, ...)      vkvh_scene_upload -> vkv_upload
 //   per frame: camera + transforms, "Visbuffer pass", "HiZ reduction", frameOverlap frames in flight
 //                                                                    vkv_update_staged + vkv_frame_submit / vkv_frame_wait
@@ -25,6 +26,30 @@ namespace {
 constexpr uint32_t frameOverlap = 3; // application.hpp:146
 
 int upload_cb(void* user, const void* host, size_t bytes, uint64_t* dev) { return vkv_upload(static_cast<vkv_ctx*>(user), host, bytes, dev); }
+
+// EXT_meshopt_compression: what CompressedBufferDataAdapter does on the CPU (assets.cpp:111-171), done by libvkv's device decoder behind the
+// host reader's decoder hook — one call per compressed bufferView.  The context is created on first use and then renders the frames.
+struct DeviceDecoder { vkv_ctx** vkv; uint32_t W, H; };
+int decode_cb(void* user, uint32_t mode, uint32_t filter, uint32_t count, uint32_t stride, const void* src, size_t src_bytes, void* dst) {
+	auto* d = static_cast<DeviceDecoder*>(user);
+	if (!*d->vkv && vkv_create(d->vkv, 0, d->W, d->H) != VKV_OK) return -100;
+	vkv_ctx* c = *d->vkv;
+	std::vector<unsigned char> stream(src_bytes + 32, 0); // a little slack behind the stream, as the decoder's tests provide
+	std::memcpy(stream.data(), src, src_bytes);
+	const size_t bytes = ((size_t)count * stride + 15) & ~(size_t)15;
+	const vkv_MeshoptView view = {mode, filter, count, stride, 0, src_bytes, 0};
+	uint64_t srcDev = 0, dstDev = 0;
+	vkv_meshopt_plan* plan = nullptr;
+	int32_t rc = -100;
+	if (vkv_upload(c, stream.data(), stream.size(), &srcDev) == VKV_OK && vkv_alloc(c, bytes, &dstDev) == VKV_OK &&
+	    vkv_meshopt_plan_create(c, &view, 1, &plan) == VKV_OK && vkv_meshopt_run(c, plan, srcDev, stream.size(), dstDev, bytes) == VKV_OK &&
+	    vkv_meshopt_results(c, plan, &rc) == VKV_OK && rc == 0 && vkv_download(c, dstDev, dst, (size_t)count * stride) != VKV_OK)
+		rc = -100;
+	if (plan) vkv_meshopt_plan_destroy(c, plan);
+	if (dstDev) vkv_free(c, dstDev);
+	if (srcDev) vkv_free(c, srcDev);
+	return rc;
+}
 
 [[noreturn]] void die(int code, const char* what, const char* why) {
 	std::fprintf(stderr, "headless: %s: %s\n", what, why ? why : "");
@@ -51,6 +76,9 @@ int main(int argc, char** argv) {
 	// ---- the asset side (host only)
 	char err[512] = "";
 	vkvh_scene* scene = nullptr;
+	vkv_ctx* vkv = nullptr;
+	DeviceDecoder decoder = {&vkv, W, H};
+	vkvh_set_meshopt_decoder(decode_cb, &decoder);
 	if (!asset.empty()) scene = vkvh_scene_load_file(asset.c_str(), err, sizeof(err));
 	else if (kind == "icosphere") scene = vkvh_scene_icosphere(57);
 	else if (kind == "atrium") scene = vkvh_scene_atrium(128);
@@ -63,8 +91,7 @@ int main(int argc, char** argv) {
 	            (unsigned long long)cnt.triangles_instanced, (unsigned long long)cnt.triangles_unique, cnt.transforms);
 
 	// ---- context + uploads
-	vkv_ctx* vkv = nullptr;
-	if (vkv_create(&vkv, 0, W, H) != VKV_OK) die(3, "vkv_create", vkv_last_error(nullptr));
+	if (!vkv && vkv_create(&vkv, 0, W, H) != VKV_OK) die(3, "vkv_create", vkv_last_error(nullptr));
 	float eye[3], center[3];
 	const float up[3] = {0.f, 1.f, 0.f};
 	vkv_Camera camera;

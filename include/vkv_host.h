@@ -80,8 +80,15 @@ int32_t vkvh_scene_add_node_mesh(vkvh_scene*, int32_t parent, const int32_t* pri
  * POSITION accessors of any component type incl. KHR_mesh_quantization (fastgltf's convertComponent rules), u8 / u16 / u32 or
  * generated indices, materials (baseColorFactor, alphaCutoff, doubleSided; index + 1), meshes with several primitives, node TRS
  * or matrices (decomposed like fastgltf::math::decomposeTransformMatrix), scenes[scene].nodes.  Returns a finalized scene or NULL
- * with a message in err (EXT_meshopt_compression views are refused with a reason: they are decoded on the device; external files need
- * vkvh_scene_load_file, which knows the asset's folder). */
+ * with a message in err (external files need vkvh_scene_load_file, which knows the asset's folder).
+ * EXT_meshopt_compression (CompressedBufferDataAdapter, assets.cpp:70-171: every compressed bufferView is decoded with
+ * meshopt_decodeVertexBuffer / IndexBuffer / IndexSequence, then the Oct / Quat / Exp filter): the bytes are decoded by the decoder the
+ * caller installs — one call per compressed view, mode / filter numbered like vkv.h's VKV_MESHOPT_* (fastgltf's enums), dst holds
+ * count * stride bytes (+ 4 of slack), return 0 or meshoptimizer's error code.  libvkv's device decoder fits (vkv_upload the stream,
+ * vkv_meshopt_plan_create + vkv_meshopt_run, vkv_download); tests install the reference's meshoptimizer.  Without a decoder such assets are
+ * refused with a message that says so; a stream that fails to decode is refused too (the reference ignores the code, assets.cpp:149). */
+typedef int (*vkvh_meshopt_decode_fn)(void* user, uint32_t mode, uint32_t filter, uint32_t count, uint32_t stride, const void* src, size_t src_bytes, void* dst);
+void vkvh_set_meshopt_decoder(vkvh_meshopt_decode_fn fn, void* user);
 vkvh_scene* vkvh_scene_load_glb(const void* data, size_t bytes, char* err, size_t errcap);
 /* The same for an asset FILE, .glb or .gltf (AssetLoadTask::loadGltf, assets.cpp:526-552: MappedGltfFile::FromPath + Parser::loadGltf with
  * the asset's folder) including what BufferLoadTask does (assets.cpp:36-68): buffers whose uri names a local file are read from the

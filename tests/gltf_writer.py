@@ -54,6 +54,53 @@ class GlbWriter:
         self.doc["accessors"].append({"bufferView": self._view(i.tobytes()), "componentType": CT[i.dtype], "count": int(i.size), "type": "SCALAR"})
         return len(self.doc["accessors"]) - 1
 
+    # ---- EXT_meshopt_compression: the bufferView lives in a fallback buffer (no bytes), its extension names the compressed range
+    def _compressed_view(self, encoded: bytes, mode: str, count: int, stride: int, filt: str = "NONE", view_stride=0) -> int:
+        while len(self.bin) % 4:
+            self.bin.append(0)
+        off = len(self.bin)
+        self.bin += encoded
+        if "EXT_meshopt_compression" not in self.doc["extensionsUsed"]:
+            self.doc["extensionsUsed"].append("EXT_meshopt_compression")
+        if not hasattr(self, "fallback_bytes"):
+            self.fallback_bytes = 0
+        v = {"buffer": 1, "byteOffset": self.fallback_bytes, "byteLength": count * stride,
+             "extensions": {"EXT_meshopt_compression": {"buffer": 0, "byteOffset": off, "byteLength": len(encoded), "byteStride": stride,
+                                                         "count": count, "mode": mode, "filter": filt}}}
+        if view_stride:
+            v["byteStride"] = view_stride
+        self.fallback_bytes += (count * stride + 3) & ~3
+        self.doc["bufferViews"].append(v)
+        return len(self.doc["bufferViews"]) - 1
+
+    def positions_compressed(self, pos, encode, filt="NONE", decoded=None) -> int:
+        """pos: (n,3) float32, or int16 (padded to 8-byte elements: ATTRIBUTES strides are multiples of 4); encode(kind, data, count, stride) ->
+        stream bytes (the reference's meshoptimizer in the tests); `decoded`: what the stream decodes to when a filter changes the values (min / max)"""
+        p = np.ascontiguousarray(pos)
+        n = int(p.shape[0])
+        if p.dtype == np.float32:
+            raw, stride, vstride = p, 12, 0
+        else:
+            raw = np.zeros((n, 4), p.dtype); raw[:, :3] = p
+            stride, vstride = 4 * p.dtype.itemsize, 4 * p.dtype.itemsize
+        view = self._compressed_view(bytes(encode("vertex", raw, n, stride)), "ATTRIBUTES", n, stride, filt, vstride)
+        q = np.ascontiguousarray(decoded if decoded is not None else p)
+        a = {"bufferView": view, "componentType": CT[p.dtype], "count": n, "type": "VEC3",
+             "min": [float(x) if p.dtype == np.float32 else int(x) for x in q.min(0)], "max": [float(x) if p.dtype == np.float32 else int(x) for x in q.max(0)]}
+        if p.dtype != np.float32 and "KHR_mesh_quantization" not in self.doc["extensionsUsed"]:
+            self.doc["extensionsUsed"].append("KHR_mesh_quantization")
+        self.doc["accessors"].append(a)
+        return len(self.doc["accessors"]) - 1
+
+    def indices_compressed(self, idx, encode, nverts, mode="TRIANGLES") -> int:
+        """idx: uint16 or uint32; TRIANGLES = meshopt_encodeIndexBuffer, INDICES = meshopt_encodeIndexSequence"""
+        i = np.ascontiguousarray(idx).reshape(-1)
+        assert i.dtype in (np.uint16, np.uint32)
+        enc = encode("index" if mode == "TRIANGLES" else "sequence", i.astype(np.uint32), i.size, i.dtype.itemsize, nverts)
+        view = self._compressed_view(bytes(enc), mode, int(i.size), i.dtype.itemsize)
+        self.doc["accessors"].append({"bufferView": view, "componentType": CT[i.dtype], "count": int(i.size), "type": "SCALAR"})
+        return len(self.doc["accessors"]) - 1
+
     def material(self, base_color=(1, 1, 1, 1), double_sided=False, alpha_cutoff=None) -> int:
         m = {"pbrMetallicRoughness": {"baseColorFactor": [float(x) for x in base_color]}, "doubleSided": bool(double_sided)}
         if alpha_cutoff is not None:
@@ -122,6 +169,9 @@ class GlbWriter:
     def glb(self, extra_buffers=()) -> bytes:
         doc = dict(self.doc)
         doc["buffers"] = [{"byteLength": len(self.bin)}] + list(extra_buffers)
+        if getattr(self, "fallback_bytes", 0):
+            assert not extra_buffers
+            doc["buffers"].append({"byteLength": self.fallback_bytes, "extensions": {"EXT_meshopt_compression": {"fallback": True}}})
         for k in ("materials", "extensionsUsed"):
             if not doc[k]:
                 del doc[k]

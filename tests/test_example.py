@@ -55,3 +55,20 @@ def test_headless_example_renders(tmp_path):
     img = np.frombuffer(raw[len(head):], np.uint8).reshape(480, 640, 3)
     # the sphere is in view: a background colour plus several material colours
     assert len(np.unique(img.reshape(-1, 3), axis=0)) >= 2
+
+
+def test_headless_example_sends_compressed_views_to_the_device_decoder(tmp_path, meshopt_ref):
+    """an EXT_meshopt_compression asset: the example installs libvkv's device decoder behind the host reader's hook, so without a GPU the load
+    fails at the first compressed bufferView (and says so) instead of falling back to a CPU decoder"""
+    if not os.path.exists(os.path.join(ROOT, "vk_gltf_viewer_b200", "libvkv.so")):
+        pytest.skip("libvkv.so not built")
+    if has_gpu():
+        pytest.skip("a GPU is present")
+    from tests import meshopt_lib as M
+    from tests.test_gltf import _compressed_and_plain_assets
+    _build()
+    comp, _ = _compressed_and_plain_assets(M)
+    path = tmp_path / "compressed.glb"
+    path.write_bytes(comp)
+    p = subprocess.run([EXE, "--asset", str(path), "--frames", "1"], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 2 and "did not decode" in p.stderr, (p.returncode, p.stderr)

@@ -238,3 +238,119 @@ def test_primitives_built_on_all_cores_land_in_document_order():
         ref.add_mesh_node([ref.add_primitive(pos, idx, rm)], translation=(k * 4.0, 0, 0))
     ref.finalize()
     same_scene(Scene.from_glb(w.glb()), ref)
+
+
+# ------------------------------------------------------------------------------------------ EXT_meshopt_compression through the decoder hook
+def _compressed_and_plain_assets(M):
+    """the same geometry twice: EXT_meshopt_compression views (streams from the REFERENCE's meshoptimizer) and plain views of what they decode to"""
+    rng = np.random.default_rng(21)
+    posA, idxA = S.grid_mesh(40, 31, lambda u, v: (u * 3, 0.2 * np.sin(u * 9) * np.cos(v * 5), v * 2))
+    posA = posA.astype(np.float32)
+    qB = rng.integers(-3000, 3000, (70, 3)).astype(np.int16)
+    idxB = rng.integers(0, 70, 240).astype(np.uint16)
+    # EXPONENTIAL filter: the stream holds (exponent << 24 | mantissa) words, the decoder turns them into floats
+    L = M.ref_lib()
+    posC, idxC = S.grid_mesh(12, 12, lambda u, v: (u + 0.37, v * v, 0.5 * u * v))
+    posC = np.ascontiguousarray(posC, np.float32)
+    enc_words = np.zeros(posC.shape, np.uint32)
+    L.meshopt_encodeFilterExp(C.c_void_p(enc_words.ctypes.data), C.c_size_t(posC.shape[0]), C.c_size_t(12), C.c_int(15), C.c_void_p(posC.ctypes.data), C.c_int(0))
+    rc, dec = M.ref_decode("vertex", posC.shape[0], 12, M.ref_encode("vertex", enc_words, posC.shape[0], 12), fid=3)
+    assert rc == 0
+    posC_decoded = dec.view(np.float32).reshape(-1, 3).copy()
+    assert np.abs(posC_decoded - posC).max() < 1e-3 and not np.array_equal(posC_decoded, posC)
+
+    def tri_decoded(idx, nverts, dtype):
+        """meshopt's triangle codec keeps every triangle but may rotate its three indices: the plain asset holds what the stream decodes to"""
+        i = np.ascontiguousarray(idx, np.uint32).reshape(-1)
+        rc, out = M.ref_decode("index", i.size, np.dtype(dtype).itemsize, M.ref_encode("index", i, i.size, np.dtype(dtype).itemsize, nverts))
+        assert rc == 0
+        out = out.view(dtype)
+        assert np.array_equal(np.sort(out.reshape(-1, 3), 1), np.sort(i.reshape(-1, 3), 1))
+        return out
+
+    def build(compressed):
+        w = GlbWriter()
+        m = w.material((0.3, 0.6, 0.9, 1.0), double_sided=True)
+        if compressed:
+            a = {"position": w.positions_compressed(posA, M.ref_encode), "indices": w.indices_compressed(idxA.astype(np.uint32), M.ref_encode, posA.shape[0]), "material": m}
+            b = {"position": w.positions_compressed(qB, M.ref_encode), "indices": w.indices_compressed(idxB, M.ref_encode, 70, mode="INDICES"), "material": None}
+            c = {"position": w.positions_compressed(enc_words.view(np.float32), M.ref_encode, filt="EXPONENTIAL", decoded=posC_decoded),
+                 "indices": w.indices_compressed(idxC.astype(np.uint16), M.ref_encode, posC.shape[0]), "material": m}
+        else:
+            a = {"position": w.positions(posA), "indices": w.indices(tri_decoded(idxA, posA.shape[0], np.uint32)), "material": m}
+            b = {"position": w.positions(qB, stride=8), "indices": w.indices(idxB), "material": None}
+            c = {"position": w.positions(posC_decoded), "indices": w.indices(tri_decoded(idxC, posC.shape[0], np.uint16)), "material": m}
+        w.node(w.mesh([a, b]), translation=(1, 0, 0))
+        w.node(w.mesh([c]), scale=(2, 2, 2))
+        return w.glb()
+    return build(True), build(False)
+
+
+def _decoder_from(decode):
+    kinds = {0: "vertex", 1: "index", 2: "sequence"}
+
+    def fn(mode, filt, count, stride, src, dst):
+        rc, out = decode(kinds[mode], count, stride, np.array(src, copy=True), fid=filt)
+        if rc == 0:
+            dst[:] = out
+        return rc
+    return fn
+
+
+@pytest.mark.parametrize("which", ["reference", "oracle"])
+def test_meshopt_compressed_asset_loads_through_the_decoder_hook(meshopt_ref, which):
+    """EXT_meshopt_compression (CompressedBufferDataAdapter, assets.cpp:70-171): ATTRIBUTES (float, int16 in 8-byte elements, EXPONENTIAL filter),
+    TRIANGLES and INDICES views in a fallback buffer; with a decoder installed the scene equals the one loaded from the decoded bytes"""
+    from tests import meshopt_lib as M
+    from vk_gltf_viewer_b200 import scene as SC
+    comp, plain = _compressed_and_plain_assets(M)
+    SC.set_meshopt_decoder(_decoder_from(M.ref_decode if which == "reference" else M.oracle_decode))
+    try:
+        got = Scene.from_glb(comp)
+    finally:
+        SC.set_meshopt_decoder(None)
+    same_scene(got, Scene.from_glb(plain))
+    assert got.counts().primitives == 3 and got.counts().triangles_unique > 2500
+
+
+def test_meshopt_compressed_asset_without_a_decoder_or_with_a_broken_stream_is_refused(meshopt_ref):
+    from tests import meshopt_lib as M
+    from vk_gltf_viewer_b200 import scene as SC
+    comp, _ = _compressed_and_plain_assets(M)
+    with pytest.raises(ValueError, match="vkvh_set_meshopt_decoder"):
+        Scene.from_glb(comp)
+    bad = bytearray(comp)
+    import struct
+    jlen = struct.unpack_from("<I", comp, 12)[0]
+    bad[20 + jlen + 8] ^= 0xFF                              # first byte of the BIN chunk = header byte of the first stream
+    SC.set_meshopt_decoder(_decoder_from(M.ref_decode))
+    try:
+        with pytest.raises(ValueError, match="did not decode"):
+            Scene.from_glb(bytes(bad))
+        # a plain view must not read the fallback buffer
+        import json
+        doc = json.loads(comp[20:20 + jlen])
+        del doc["bufferViews"][0]["extensions"]
+        js = json.dumps(doc, separators=(",", ":")).encode(); js += b" " * (-len(js) % 4)
+        rest = comp[20 + jlen:]
+        with pytest.raises(ValueError, match="fallback buffer"):
+            Scene.from_glb(struct.pack("<III", 0x46546C67, 2, 20 + len(js) + len(rest)) + struct.pack("<II", len(js), 0x4E4F534A) + js + rest)
+    finally:
+        SC.set_meshopt_decoder(None)
+
+
+@pytest.mark.gpu
+@pytest.mark.late
+def test_meshopt_compressed_asset_decoded_on_the_device(meshopt_ref):
+    """the same asset with libvkv's device decoder behind the hook (api.Renderer.meshopt_decoder): identical scene"""
+    from tests import meshopt_lib as M
+    from vk_gltf_viewer_b200 import api, scene as SC
+    comp, plain = _compressed_and_plain_assets(M)
+    r = api.Renderer(64, 64)
+    SC.set_meshopt_decoder(r.meshopt_decoder())
+    try:
+        got = Scene.from_glb(comp)
+    finally:
+        SC.set_meshopt_decoder(None)
+        r.close()
+    same_scene(got, Scene.from_glb(plain))

@@ -378,6 +378,19 @@ class Renderer:
                 self.free(s_dev)
         return out, rc
 
+    def meshopt_decoder(self):
+        """a decoder for scene.set_meshopt_decoder: every compressed bufferView of an asset file is decoded by the device decoder
+        (CompressedBufferDataAdapter's job, assets.cpp:111-171, moved to the GPU) and handed back to the host reader"""
+        def decode(mode, filt, count, stride, src, dst):
+            views = np.zeros(1, abi.MESHOPT_VIEW_DTYPE)
+            views[0] = (mode, filt, count, stride, 0, src.size, 0)
+            nbytes = (count * stride + 15) & ~15
+            out, rc = self.meshopt_decode(np.concatenate([np.asarray(src, np.uint8), np.zeros(32, np.uint8)]), views, nbytes)
+            if int(rc[0]) == 0:
+                dst[:] = out[:count * stride]
+            return int(rc[0])
+        return decode
+
     # ---- draw list on the device (SURVEY §8f-2) -------------------------------------------------------------
     def build_draws(self, segments, primitive_buffer: int):
         """segments: (n, 2) uint32 array of (primitiveIndex, transformIndex) per (mesh-node, primitive) in traversal order

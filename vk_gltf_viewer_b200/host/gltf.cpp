@@ -16,8 +16,9 @@
 //     depth first from scenes[scene].nodes, one transform per node WITH a mesh, all primitives of the mesh sharing it
 //     (world.cpp:242-264).
 // Not read (nothing on the geometry path consumes them): textures, samplers, animations, skins, cameras, lights, sparse accessors
-// (rejected), non-triangle modes (skipped, as the mesh shader path only draws triangle lists).  EXT_meshopt_compression views are
-// rejected here with a message pointing at the device decoder (vkv_meshopt_*), which takes the compressed views as they are.
+// (rejected), non-triangle modes (skipped, as the mesh shader path only draws triangle lists).  EXT_meshopt_compression views
+// (CompressedBufferDataAdapter, assets.cpp:70-171) are decoded through the caller's decoder (vkvh_set_meshopt_decoder: libvkv's device
+// decoder vkv_meshopt_* in this repo); without one they are refused with a message that says so.
 #include "scene.hpp"
 
 #include <cstdio>
@@ -153,6 +154,10 @@ std::vector<uint8_t> base64(const std::string& s, size_t from) {
 }
 
 struct View { const uint8_t* data; size_t size; size_t stride; }; // stride 0 = tightly packed
+
+// EXT_meshopt_compression: the decoder is the caller's (vkvh_set_meshopt_decoder) — in this repo libvkv's device decoder
+vkvh_meshopt_decode_fn g_meshopt_decode = nullptr;
+void* g_meshopt_decode_user = nullptr;
 struct Acc { View view; size_t offset, count; int ctype; bool normalized; int comps; const Json* json; };
 
 size_t ctype_size(int t) { return (t == 5120 || t == 5121) ? 1 : (t == 5122 || t == 5123) ? 2 : (t == 5125 || t == 5126) ? 4 : 0; }
@@ -223,6 +228,7 @@ struct Loader {
 	Json doc;
 	std::deque<std::vector<uint8_t>> owned; // decoded data-URI buffers, external files, densified sparse accessors (addresses stay put)
 	std::vector<View> buffers;
+	std::map<long long, View> decoded;      // EXT_meshopt_compression views already decoded (several accessors share a view)
 	std::string baseDir;                    // folder of the asset file (assetPath.parent_path(), assets.cpp:548,558); empty = no file access
 	bool haveDir = false;
 
@@ -231,10 +237,42 @@ struct Loader {
 		if (!bvs || idx < 0 || (size_t)idx >= bvs->size()) fail("bufferView index out of range");
 		const Json& bv = bvs->arr[(size_t)idx];
 		if (const Json* ext = bv.get("extensions"))
-			if (ext->has("EXT_meshopt_compression"))
-				fail("bufferView " + std::to_string(idx) + " is EXT_meshopt_compression-compressed: decode it on the device (vkv_meshopt_plan_create / vkv_meshopt_run take the compressed views as they are)");
+			if (const Json* mc = ext->get("EXT_meshopt_compression")) {
+				// CompressedBufferDataAdapter::ExecuteRange (assets.cpp:111-171): the view's bytes are the decoded stream, count * byteStride of them
+				auto hit = decoded.find(idx);
+				if (hit != decoded.end()) return hit->second;
+				if (!g_meshopt_decode)
+					fail("bufferView " + std::to_string(idx) + " is EXT_meshopt_compression-compressed: install a decoder (vkvh_set_meshopt_decoder; libvkv's device decoder "
+					     "vkv_meshopt_plan_create / vkv_meshopt_run takes the compressed views as they are)");
+				const long long cb = mc->integer("buffer", -1);
+				if (cb < 0 || (size_t)cb >= buffers.size() || !buffers[(size_t)cb].data) fail("EXT_meshopt_compression.buffer out of range or without data");
+				const size_t coff = (size_t)mc->integer("byteOffset", 0), clen = (size_t)mc->integer("byteLength", 0);
+				if (coff > buffers[(size_t)cb].size || clen > buffers[(size_t)cb].size - coff) fail("EXT_meshopt_compression view exceeds its buffer");
+				const size_t stride = (size_t)mc->integer("byteStride", 0), count = (size_t)mc->integer("count", 0);
+				const Json* jm = mc->get("mode"); const Json* jf = mc->get("filter");
+				const std::string mode = jm && jm->kind == Json::String ? jm->str : "", filter = jf && jf->kind == Json::String ? jf->str : "NONE";
+				const int m = mode == "ATTRIBUTES" ? 0 : mode == "TRIANGLES" ? 1 : mode == "INDICES" ? 2 : -1;
+				const int f = filter == "NONE" ? 0 : filter == "OCTAHEDRAL" ? 1 : filter == "QUATERNION" ? 2 : filter == "EXPONENTIAL" ? 3 : -1;
+				// the extension's own constraints (and what meshoptimizer asserts): attributes 4-byte multiples up to 256, indices 2 or 4 bytes,
+				// whole triangles, filters only on attributes with the strides they are defined for
+				if (m < 0 || f < 0) fail("EXT_meshopt_compression with an unknown mode / filter");
+				if (m == 0 ? (stride == 0 || stride % 4 != 0 || stride > 256) : (stride != 2 && stride != 4)) fail("EXT_meshopt_compression byteStride not valid for its mode");
+				if (m == 1 && count % 3 != 0) fail("EXT_meshopt_compression TRIANGLES count is not a multiple of 3");
+				if (f != 0 && m != 0) fail("EXT_meshopt_compression filter on an index view");
+				if ((f == 1 && stride != 4 && stride != 8) || (f == 2 && stride != 8)) fail("EXT_meshopt_compression filter with a byteStride it is not defined for");
+				if (count > ((size_t)1 << 31) / (stride ? stride : 1)) fail("EXT_meshopt_compression view too large");
+				owned.emplace_back(count * stride + 4); // + 4: filters and index decoders may touch whole words at the tail
+				const int rc = g_meshopt_decode(g_meshopt_decode_user, (uint32_t)m, (uint32_t)f, (uint32_t)count, (uint32_t)stride, buffers[(size_t)cb].data + coff, clen,
+				                                owned.back().data());
+				// (the reference ignores the decoders' return codes, assets.cpp:149-150; a stream that does not decode is refused here)
+				if (rc != 0) fail("bufferView " + std::to_string(idx) + ": EXT_meshopt_compression stream did not decode (code " + std::to_string(rc) + ")");
+				const View v{owned.back().data(), count * stride, (size_t)bv.integer("byteStride", 0)};
+				decoded.emplace(idx, v);
+				return v;
+			}
 		const long long b = bv.integer("buffer", -1);
 		if (b < 0 || (size_t)b >= buffers.size()) fail("bufferView.buffer out of range");
+		if (!buffers[(size_t)b].data) fail("bufferView reads a fallback buffer (EXT_meshopt_compression placeholder without bytes)");
 		const size_t off = (size_t)bv.integer("byteOffset", 0), len = (size_t)bv.integer("byteLength", 0);
 		if (off + len > buffers[(size_t)b].size) fail("bufferView exceeds its buffer");
 		return View{buffers[(size_t)b].data + off, len, (size_t)bv.integer("byteStride", 0)};
@@ -296,6 +334,11 @@ struct Loader {
 } // namespace
 } // namespace vkvh
 
+void vkvh_set_meshopt_decoder(vkvh_meshopt_decode_fn fn, void* user) {
+	vkvh::g_meshopt_decode = fn;
+	vkvh::g_meshopt_decode_user = user;
+}
+
 // everything after the container: buffers (BIN chunk, data URIs, files beside the asset), then materials / meshes / nodes / scene
 static vkvh_scene* load_document(vkvh::Loader& L) {
 	using namespace vkvh;
@@ -306,7 +349,12 @@ static vkvh_scene* load_document(vkvh::Loader& L) {
 				const Json& b = bufs->arr[i];
 				const Json* uri = b.get("uri");
 				const size_t byteLength = (size_t)b.integer("byteLength", 0);
-				if (!uri) { // the GLB-stored buffer
+				const Json* bext = b.get("extensions");
+				const Json* bmc = bext ? bext->get("EXT_meshopt_compression") : nullptr;
+				if (!uri && bmc && bmc->boolean("fallback", false)) {
+					// fastgltf::sources::Fallback: a placeholder for decoders without the extension; it has no bytes and nothing may read it
+					L.buffers.push_back(View{nullptr, byteLength, 0});
+				} else if (!uri) { // the GLB-stored buffer
 					if (i != 0 || !L.bin) fail("buffer without uri that is not the GLB BIN chunk");
 					if (byteLength > L.binSize) fail("buffers[0].byteLength exceeds the BIN chunk");
 					L.buffers.push_back(View{L.bin, byteLength, 0});

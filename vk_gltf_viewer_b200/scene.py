@@ -72,6 +72,8 @@ def _lib():
         L.vkvh_frustum_from_vp.argtypes = [C.POINTER(C.c_float), C.c_void_p]
         L.vkvh_set_meshlet_builder.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.vkvh_select_builder.argtypes = [C.c_int]
+        L.vkvh_set_meshopt_decoder.restype = None
+        L.vkvh_set_meshopt_decoder.argtypes = [C.c_void_p, C.c_void_p]
         L.vkvh_scene_upload_quantized.argtypes = [C.c_void_p, UPLOAD_FN, C.c_void_p, C.POINTER(C.c_uint64)]
         L.vkvh_scene_city_quantized.restype = C.c_void_p
         L.vkvh_scene_city_quantized.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64]
@@ -103,6 +105,32 @@ def set_meshlet_builder(bound_fn=None, build_fn=None, optimize_fn=None):
     def addr(f):
         return C.cast(f, C.c_void_p) if f is not None else None
     _lib().vkvh_set_meshlet_builder(addr(bound_fn), addr(build_fn), addr(optimize_fn))
+
+
+MESHOPT_DECODE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p)
+_decoder_keepalive = None
+
+
+def set_meshopt_decoder(fn=None):
+    """Install the decoder the glTF reader calls for every EXT_meshopt_compression bufferView (vkvh_set_meshopt_decoder):
+    fn(mode, filter, count, stride, src: bytes-like uint8 array, dst: writable uint8 array of count * stride) -> int (0 = decoded).
+    api.Renderer.meshopt_decoder() returns one that runs libvkv's device decoder; None uninstalls (compressed assets are then refused)."""
+    global _decoder_keepalive
+    if fn is None:
+        _lib().vkvh_set_meshopt_decoder(None, None)
+        _decoder_keepalive = None
+        return
+
+    def thunk(user, mode, filt, count, stride, src, src_bytes, dst):
+        try:
+            s = np.ctypeslib.as_array(C.cast(src, C.POINTER(C.c_uint8)), shape=(src_bytes,)) if src_bytes else np.zeros(0, np.uint8)
+            d = np.ctypeslib.as_array(C.cast(dst, C.POINTER(C.c_uint8)), shape=(count * stride,)) if count * stride else np.zeros(0, np.uint8)
+            return int(fn(mode, filt, count, stride, s, d))
+        except Exception:  # noqa: BLE001 - never unwind through the C++ caller
+            return -100
+    cb = MESHOPT_DECODE_FN(thunk)
+    _lib().vkvh_set_meshopt_decoder(C.cast(cb, C.c_void_p), None)
+    _decoder_keepalive = cb
 
 
 def select_builder(name: str = "meshopt"):
