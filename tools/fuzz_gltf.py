@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Mutation fuzzer for the glTF reader (host/gltf.cpp: the one place on this path that parses untrusted bytes on the host).
 
-    python tools/fuzz_gltf.py [iterations] [seed]
+    python tools/fuzz_gltf.py [iterations] [seed] [compressed]
 
 Builds a GLB with every feature the reader handles (float / quantised / strided / sparse accessors, u8 / u16 / u32 / generated indices,
 matrix and TRS nodes, several scenes' worth of hierarchy), then mutates JSON text and binary chunk (bit flips, number replacement, token
@@ -138,7 +138,15 @@ def main():
     iters = int(sys.argv[1]) if len(sys.argv) > 1 else 5000
     seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
     from vk_gltf_viewer_b200.scene import Scene
+    from vk_gltf_viewer_b200 import scene as SC
     glb = base_glb()
+    if len(sys.argv) > 3 and sys.argv[3] == "compressed":
+        # an EXT_meshopt_compression asset (streams, fallback buffer, decoder hook) with the reference's meshoptimizer as the decoder
+        from tests import meshopt_lib as M
+        from tests.test_gltf import _compressed_and_plain_assets, _decoder_from
+        assert M.ref_lib() is not None, "needs oracle/_ref/libmeshopt_ref.so (make ref)"
+        glb, _ = _compressed_and_plain_assets(M)
+        SC.set_meshopt_decoder(_decoder_from(M.ref_decode))
     js, rest = split(glb)
     check(Scene.from_glb(glb))
     rng = np.random.default_rng(seed)

@@ -260,7 +260,9 @@ struct Loader {
 				if (m == 1 && count % 3 != 0) fail("EXT_meshopt_compression TRIANGLES count is not a multiple of 3");
 				if (f != 0 && m != 0) fail("EXT_meshopt_compression filter on an index view");
 				if ((f == 1 && stride != 4 && stride != 8) || (f == 2 && stride != 8)) fail("EXT_meshopt_compression filter with a byteStride it is not defined for");
-				if (count > ((size_t)1 << 31) / (stride ? stride : 1)) fail("EXT_meshopt_compression view too large");
+				// no meshoptimizer stream expands a thousandfold (vertex blocks: >= 1 header bit pair per 16 bytes; index codes: >= 1 byte per triangle):
+				// a view that claims more is refused before anything is allocated for it
+				if (count > ((size_t)1 << 31) / stride || count * stride > ((clen + 64) << 10)) fail("EXT_meshopt_compression view claims more output than its stream can hold");
 				owned.emplace_back(count * stride + 4); // + 4: filters and index decoders may touch whole words at the tail
 				const int rc = g_meshopt_decode(g_meshopt_decode_user, (uint32_t)m, (uint32_t)f, (uint32_t)count, (uint32_t)stride, buffers[(size_t)cb].data + coff, clen,
 				                                owned.back().data());
@@ -403,7 +405,7 @@ static vkvh_scene* load_document(vkvh::Loader& L) {
 			std::vector<int16_t> qpos;
 			bool qnormalized = false;
 			PrimitiveData built;
-			bool ok = false;
+			bool ok = false, oom = false;
 		};
 		std::deque<Job> jobs;
 		std::vector<std::vector<int32_t>> meshPrims;
@@ -470,7 +472,9 @@ static vkvh_scene* load_document(vkvh::Loader& L) {
 			auto worker = [&]() {
 				for (size_t i; (i = next.fetch_add(1)) < jobs.size();) {
 					Job& job = jobs[i];
-					job.ok = build_primitive(job.built, std::move(job.verts), job.idx.data(), (uint32_t)job.idx.size(), job.materialIndex);
+					try { // nothing may unwind out of a worker thread
+						job.ok = build_primitive(job.built, std::move(job.verts), job.idx.data(), (uint32_t)job.idx.size(), job.materialIndex);
+					} catch (const std::exception&) { job.ok = false; job.oom = true; }
 					std::vector<uint32_t>().swap(job.idx);
 				}
 			};
@@ -482,6 +486,7 @@ static vkvh_scene* load_document(vkvh::Loader& L) {
 			for (auto& th : pool) th.join();
 		}
 		for (Job& job : jobs) {
+			if (job.oom) fail("out of memory while building a primitive's meshlets");
 			if (!job.ok) fail("primitive with no triangles or an index out of range");
 			PrimitiveData& pd = job.built;
 			for (int k = 0; k < 3; ++k) { pd.header.aabbCenter[k] = job.center[k]; pd.header.aabbExtents[k] = job.extents[k]; }
