@@ -203,6 +203,17 @@ int vkv_build_meshlets(vkv_ctx*, const vkv_MeshletBuildInput* host_inputs, uint3
 int vkv_resolve(vkv_ctx*, const vkv_VisbufferPushConstants* pc);
 int vkv_read_color(vkv_ctx*, uint32_t* host);                      /* W*H RGBA8 */
 
+/* ---- motion vectors: the visbuffer pass's second colour attachment (application.cpp:250-267 R16G16_SFLOAT "Motion vectors", cleared
+ * to 0 at :786-799, handed to the upscaler at :1086-1118), derived from the finished visbuffer.  Replaces visbuffer.frag.glsl:38 and the
+ * position / prevPosition varyings of visbuffer.mesh.glsl:44-45,61-63: per covered pixel the triangle its id names is fetched again and
+ *   ((prevPosition.xy / prevPosition.w) * 0.5 - 0.5) - ((position.xy / position.w) * 0.5 - 0.5)
+ * is evaluated at the pixel centre with perspective-correct interpolation (csrc/motion_core.h states the arithmetic); uncovered pixels
+ * hold the clear value.  pc->cameraBuffer must hold the frame's Camera (prevViewProjection = the previous frame's viewProjection,
+ * camera.cpp:181).  Call it after the frame whose visbuffer it reads; with range sharding, after vkv_gather_strips / vkv_merge.
+ * Texel = half(x) | half(y) << 16. ------------------------------------------------------------------------------------------- */
+int vkv_motion_vectors(vkv_ctx*, const vkv_VisbufferPushConstants* pc);
+int vkv_read_motion(vkv_ctx*, uint16_t* host);                     /* W*H*2 halves */
+
 /* ---- multi-GPU: one process (and one context) per GPU; a single huge view is sharded by MeshletDraw range and the
  * per-GPU 64-bit visbuffers are min-merged over NVLink peer memory (BASELINE config 5).  The reference is
  * single-GPU: there is no call site to cite, only the data contract — drawIndex stays the index into the GLOBAL list

@@ -767,6 +767,73 @@ int orc_resolve(const vkv_VisbufferPushConstants* pc, uint32_t W, uint32_t H, co
 	return 0;
 }
 
+// fp32 -> fp16 with round-to-nearest-even (the R16G16_SFLOAT store of the motion-vector attachment), through exact double scaling and
+// nearbyint (the default rounding mode is to-nearest-even); NaN -> 0x7FFF
+static uint16_t to_half(float f) {
+	if (f != f) return 0x7fffu;
+	const uint16_t sign = std::signbit(f) ? 0x8000u : 0u;
+	const double a = std::fabs((double)f);
+	if (a >= 65520.0) return (uint16_t)(sign | 0x7c00u);                       // the tie between 65504 and 2^16 goes to even = infinity
+	if (a < 6.103515625e-05) return (uint16_t)(sign | (uint16_t)std::nearbyint(a * 16777216.0)); // below 2^-14: units of 2^-24 (1024 = 2^-14)
+	int e;
+	const double m = std::frexp(a, &e);                                        // a = m * 2^e, m in [0.5, 1)
+	long q = std::lrint(m * 2048.0);                                           // 11 significant bits, 1024 .. 2048
+	if (q == 2048) { q = 1024; ++e; }
+	return (uint16_t)(sign | (uint16_t)(((e + 14) << 10) + (q - 1024)));
+}
+uint16_t orc_to_half(float f) { return to_half(f); }
+
+// The visbuffer pass's second colour attachment (application.cpp:250-267 R16G16_SFLOAT, cleared to 0 at :786-799): visbuffer.frag.glsl:38
+// with the varyings of visbuffer.mesh.glsl:44-45,61-63, evaluated once per pixel for the triangle the id image names (what the depth test
+// left visible).  Perspective-correct interpolation at the pixel centre through homogeneous edge functions in (x, y, w); the common divisor of
+// the interpolated varyings cancels in the shader's ratios.  out_f: 2 floats per pixel (before the fp16 store), out_h: 2 halves per pixel.
+int orc_motion_vectors(const vkv_VisbufferPushConstants* pc, uint32_t W, uint32_t H, const uint32_t* ids, float* out_f, uint16_t* out_h) {
+	const vkv_MeshletDraw* draws = (const vkv_MeshletDraw*)pc->drawBuffer;
+	const vkv_Primitive* prims = (const vkv_Primitive*)pc->primitiveBuffer;
+	const vkv_Camera& cam = *(const vkv_Camera*)pc->cameraBuffer;
+	const float hw = (float)W * 0.5f, hh = (float)H * 0.5f;
+	for (uint32_t y = 0; y < H; ++y)
+		for (uint32_t x = 0; x < W; ++x) {
+			const size_t i = (size_t)y * W + x;
+			float mv[2] = {0.f, 0.f};                                                             // the clear value
+			const uint32_t id = ids[i];
+			if (id != VKV_VISBUFFER_CLEAR && pc->meshletDrawCount) {
+				const uint32_t drawIndex = id >> VKV_TRIANGLE_BITS, tri = id & ((1u << VKV_TRIANGLE_BITS) - 1u);
+				const vkv_MeshletDraw d = draws[drawIndex];
+				const vkv_Primitive& prim = prims[d.primitiveIndex];
+				const vkv_Meshlet& ml = ((const vkv_Meshlet*)prim.meshletBuffer)[d.meshletIndex];
+				const uint8_t* t3 = (const uint8_t*)prim.primitiveIndexBuffer + ml.triangleOffset + tri * 3;
+				const uint32_t* vidx = (const uint32_t*)prim.vertexIndexBuffer + ml.vertexOffset;
+				const vkv_Vertex* verts = (const vkv_Vertex*)prim.vertexBuffer;
+				const float* T = (const float*)pc->transformBuffer + (size_t)d.transformIndex * 16;
+				float mvp[16], prevMvp[16];
+				mul44m(cam.viewProjection, T, mvp);                                               // mesh.glsl:44
+				mul44m(cam.prevViewProjection, T, prevMvp);                                       // mesh.glsl:45
+				V4 pos[3], prev[3];
+				for (int k = 0; k < 3; ++k) {
+					const float* p = verts[vidx[t3[k]]].position;
+					pos[k] = mul44(mvp, V4{p[0], p[1], p[2], 1.0f});                              // mesh.glsl:61-62
+					prev[k] = mul44(prevMvp, V4{p[0], p[1], p[2], 1.0f});                         // mesh.glsl:63
+				}
+				const float nx = (((float)x + 0.5f) - hw) / hw, ny = (((float)y + 0.5f) - hh) / hh; // the pixel centre in NDC
+				float l[3];
+				for (int k = 0; k < 3; ++k) {
+					const V4 &u = pos[(k + 1) % 3], &v = pos[(k + 2) % 3];
+					l[k] = ((u.y * v.w - u.w * v.y) * nx + (u.w * v.x - u.x * v.w) * ny) + (u.x * v.y - u.y * v.x);
+				}
+				const float Px = (l[0] * pos[0].x + l[1] * pos[1].x) + l[2] * pos[2].x, Py = (l[0] * pos[0].y + l[1] * pos[1].y) + l[2] * pos[2].y;
+				const float Pw = (l[0] * pos[0].w + l[1] * pos[1].w) + l[2] * pos[2].w;
+				const float Qx = (l[0] * prev[0].x + l[1] * prev[1].x) + l[2] * prev[2].x, Qy = (l[0] * prev[0].y + l[1] * prev[1].y) + l[2] * prev[2].y;
+				const float Qw = (l[0] * prev[0].w + l[1] * prev[1].w) + l[2] * prev[2].w;
+				mv[0] = ((Qx / Qw) * 0.5f - 0.5f) - ((Px / Pw) * 0.5f - 0.5f);                    // frag.glsl:38
+				mv[1] = ((Qy / Qw) * 0.5f - 0.5f) - ((Py / Pw) * 0.5f - 0.5f);
+			}
+			if (out_f) { out_f[i * 2] = mv[0]; out_f[i * 2 + 1] = mv[1]; }
+			if (out_h) { out_h[i * 2] = to_half(mv[0]); out_h[i * 2 + 1] = to_half(mv[1]); }
+		}
+	return 0;
+}
+
 int orc_hiz(uint32_t W, uint32_t H, const float* depth, float* pyramid, int threads) {
 	Pyr pyr;
 	pyr.levels = orc_pyramid_layout(W, H, pyr.off, pyr.w, pyr.h, &pyr.total);

@@ -138,6 +138,13 @@ void orc_mesh_shader(const vkv_VisbufferPushConstants* pc, const uint32_t* draw_
  * CUDA powf on the device: the 8-bit result may differ by one code in rare cases — tests allow +-1 per channel. */
 int orc_resolve(const vkv_VisbufferPushConstants* pc, uint32_t W, uint32_t H, const uint32_t* ids, uint32_t* out);
 
+/* visbuffer.frag.glsl:38 + visbuffer.mesh.glsl:44-45,61-63: the motion-vector attachment (R16G16_SFLOAT, cleared to 0; application.cpp:250-267,
+ * 786-799), evaluated per pixel for the triangle `ids` names.  out_f: 2 floats per pixel before the fp16 store (may be NULL), out_h: the
+ * attachment's 2 halves per pixel (may be NULL).  PARITY: the interpolation arithmetic is implementation-defined in Vulkan; the formula here is
+ * the definition the CUDA pass is held to bit for bit, and llvmpipe running the reference's own line 38 agrees within fp32 noise. */
+int orc_motion_vectors(const vkv_VisbufferPushConstants* pc, uint32_t W, uint32_t H, const uint32_t* ids, float* out_f, uint16_t* out_h);
+uint16_t orc_to_half(float f);
+
 /* 64-bit visbuffer key: (~floatBits(depth) << 32) | id */
 uint64_t orc_vis64_key(float depth, uint32_t id);
 

@@ -67,7 +67,7 @@ SCENE_CASES = {
 }
 
 
-def oracle_triangles(scene, pc):
+def oracle_triangles(scene, pc, facing_from=None):
     """what the mesh shader hands to the fixed-function rasteriser, per the oracle (orc_mesh_shader = visbuffer.mesh.glsl:43-102, itself pinned
     against the reference's text): clip-space vertices [3n, 4] of every triangle the facing test keeps, in draw / triangle order, and the
     packVisBuffer id of each ([3n], as float32: exact below 2^24)."""
@@ -75,6 +75,8 @@ def oracle_triangles(scene, pc):
     assert n < (1 << 17), "ids must stay exact in float32"
     all_ids = np.arange(n, dtype=np.uint32)
     clip, cull = O.mesh_shader(pc, all_ids)[:2]
+    if facing_from is not None:       # positions under `pc`'s matrices, the facing decision of another camera state (motion vectors: same triangles)
+        cull = O.mesh_shader(facing_from, all_ids)[1]
     draws = scene.draws()
     prims, V, I = {}, [], []
     for d in range(n):

@@ -52,6 +52,9 @@ def lib():
         L.orc_sample_min.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.POINTER(C.c_int)]
         L.orc_mesh_shader.restype = None
         L.orc_mesh_shader.argtypes = [C.POINTER(abi.PushConstants), C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_motion_vectors.argtypes = [C.POINTER(abi.PushConstants), C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_to_half.restype = C.c_uint16
+        L.orc_to_half.argtypes = [C.c_float]
         L.orc_vis64_key.restype = C.c_uint64
         L.orc_vis64_key.argtypes = [C.c_float, C.c_uint32]
         _lib = L
@@ -128,6 +131,16 @@ def resolve(pc, tg: Targets, out=None):
     rc = lib().orc_resolve(C.byref(pc), tg.W, tg.H, tg.ids_min.ctypes.data, out.ctypes.data)
     assert rc == 0
     return out
+
+
+def motion_vectors(pc, tg: Targets, ids=None):
+    """visbuffer.frag.glsl:38 per pixel of the id image (default: the min-id image, the 64-bit visbuffer's low word)
+    -> (float32 [H, W, 2] before the fp16 store, uint16 [H, W, 2] = the R16G16_SFLOAT attachment)"""
+    ids = np.ascontiguousarray(tg.ids_min if ids is None else ids, np.uint32)
+    f = np.zeros((tg.H, tg.W, 2), np.float32)
+    h = np.zeros((tg.H, tg.W, 2), np.uint16)
+    assert lib().orc_motion_vectors(C.byref(pc), tg.W, tg.H, ids.ctypes.data, f.ctypes.data, h.ctypes.data) == 0
+    return f, h
 
 
 def visible_ids(status):

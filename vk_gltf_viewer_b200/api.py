@@ -49,7 +49,7 @@ class Stats(C.Structure):
 EXPORTS = [
     "vkv_create", "vkv_resize", "vkv_destroy", "vkv_last_error", "vkv_set_stream", "vkv_sync",
     "vkv_upload", "vkv_update", "vkv_free",
-    "vkv_frame", "vkv_frame_submit", "vkv_frame_wait", "vkv_update_staged", "vkv_clear", "vkv_cull", "vkv_raster", "vkv_hiz", "vkv_raster_list",
+    "vkv_motion_vectors", "vkv_read_motion", "vkv_frame", "vkv_frame_submit", "vkv_frame_wait", "vkv_update_staged", "vkv_clear", "vkv_cull", "vkv_raster", "vkv_hiz", "vkv_raster_list",
     "vkv_read_visbuffer64", "vkv_read_ids", "vkv_read_depth", "vkv_read_hiz_mip", "vkv_read_pyramid", "vkv_write_pyramid",
     "vkv_read_visible", "vkv_read_status", "vkv_pyramid_floats",
     "vkv_event_record", "vkv_event_elapsed", "vkv_flush_l2", "vkv_visbuffer64_ptr",
@@ -109,6 +109,8 @@ def _lib():
         L.vkv_download.argtypes = [vp, u64, vp, C.c_size_t]
         L.vkv_resolve.argtypes = [vp, PC]
         L.vkv_read_color.argtypes = [vp, vp]
+        L.vkv_motion_vectors.argtypes = [vp, PC]
+        L.vkv_read_motion.argtypes = [vp, vp]
         L.vkv_set_shard.argtypes = [vp, u32, u32, i]
         L.vkv_set_shard_interleaved.argtypes = [vp, i, i, u32]
         L.vkv_ipc_export.argtypes = [vp, vp]
@@ -408,6 +410,16 @@ class Renderer:
     # ---- resolve -----------------------------------------------------------------------------
     def resolve(self, pc):
         self._ck(self.L.vkv_resolve(self.h, C.byref(pc)))
+
+    def motion_vectors(self, pc):
+        """the visbuffer pass's motion-vector attachment (visbuffer.frag.glsl:38), derived from the finished visbuffer"""
+        self._ck(self.L.vkv_motion_vectors(self.h, C.byref(pc)))
+
+    def read_motion(self):
+        """-> uint16 [H, W, 2]: R16G16_SFLOAT texels (view as np.float16 for values)"""
+        out = np.empty((self.H, self.W, 2), np.uint16)
+        self._ck(self.L.vkv_read_motion(self.h, out.ctypes.data))
+        return out
 
     def read_color(self):
         out = np.empty((self.H, self.W), np.uint32)

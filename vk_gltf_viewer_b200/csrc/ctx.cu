@@ -74,6 +74,7 @@ struct vkv_ctx {
 	bool merge_err_pending = false;
 	// resolve pass: RGBA8 target + per-material colour table (grow-only)
 	uint32_t* color = nullptr;
+	uint32_t* motion = nullptr;       // motion-vector target (R16G16_SFLOAT texels), allocated by the first vkv_motion_vectors
 	uint32_t* mat_colors = nullptr;
 	uint32_t mat_cap = 0;
 	// readback scratch
@@ -147,6 +148,8 @@ int free_targets(vkv_ctx* c) {
 	if (c->tmp_ids) cudaFree(c->tmp_ids);
 	if (c->tmp_depth) cudaFree(c->tmp_depth);
 	if (c->color) cudaFree(c->color);
+	if (c->motion) cudaFree(c->motion);
+	c->motion = nullptr;
 	c->vis = nullptr; c->pyramid = nullptr; c->tmp_ids = nullptr; c->tmp_depth = nullptr; c->color = nullptr;
 	return 0;
 }
@@ -974,6 +977,35 @@ int vkv_read_color(vkv_ctx* c, uint32_t* host) {
 	if (!c->color) return fail(c, VKV_ERR_INVALID, "vkv_read_color: no resolve has run since the targets were created");
 	CK(cudaSetDevice(c->device));
 	CK(cudaMemcpyAsync(host, c->color, (size_t)c->W * c->H * 4, cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	return VKV_OK;
+}
+
+/* ---- motion vectors (visbuffer.frag.glsl:38) ---------------------------------------------------------------------- */
+
+int vkv_motion_vectors(vkv_ctx* c, const vkv_VisbufferPushConstants* pc) {
+	if (!c) return VKV_ERR_INVALID;
+	if (!pc) return fail(c, VKV_ERR_INVALID, "push constants are NULL");
+	CK(cudaSetDevice(c->device));
+	const size_t n = (size_t)c->W * c->H;
+	if (!c->motion) CK(cudaMalloc(&c->motion, n * 4));
+	if (pc->meshletDrawCount == 0) { // nothing can have been drawn: the cleared attachment (application.cpp:786-799)
+		CK(cudaMemsetAsync(c->motion, 0, n * 4, c->stream));
+		return VKV_OK;
+	}
+	if (!pc->drawBuffer || !pc->primitiveBuffer || !pc->transformBuffer || !pc->cameraBuffer) return fail(c, VKV_ERR_INVALID, "push constants hold a NULL buffer address");
+	MotionParams m{};
+	m.vis = c->vis; m.draws = (const vkv_MeshletDraw*)pc->drawBuffer; m.primitives = (const vkv_Primitive*)pc->primitiveBuffer;
+	m.transforms = (const float*)pc->transformBuffer; m.camera = (const vkv_Camera*)pc->cameraBuffer; m.out = c->motion; m.W = c->W; m.H = c->H;
+	CK(launch_motion(m, c->num_sms, c->stream));
+	return VKV_OK;
+}
+
+int vkv_read_motion(vkv_ctx* c, uint16_t* host) {
+	if (!c || !host) return VKV_ERR_INVALID;
+	if (!c->motion) return fail(c, VKV_ERR_INVALID, "vkv_read_motion: vkv_motion_vectors has not run since the targets were created");
+	CK(cudaSetDevice(c->device));
+	CK(cudaMemcpyAsync(host, c->motion, (size_t)c->W * c->H * 4, cudaMemcpyDeviceToHost, c->stream));
 	CK(cudaStreamSynchronize(c->stream));
 	return VKV_OK;
 }

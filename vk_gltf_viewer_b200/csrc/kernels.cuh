@@ -181,6 +181,18 @@ struct ResolveParams {
 cudaError_t launch_material_colors(const vkv_Material* materials, uint32_t n, uint32_t* out, int num_sms, cudaStream_t stream);
 cudaError_t launch_resolve(const ResolveParams& p, int num_sms, cudaStream_t stream);
 
+// ---- motion vectors from the finished visbuffer (motion.cu) --------------------------------------------------------
+struct MotionParams {
+	const unsigned long long* vis;
+	const vkv_MeshletDraw* draws;
+	const vkv_Primitive* primitives;
+	const float* transforms;     // mat4[], column-major
+	const vkv_Camera* camera;    // viewProjection / prevViewProjection
+	uint32_t* out;               // W*H texels of R16G16_SFLOAT (x in the low half)
+	uint32_t W, H;
+};
+cudaError_t launch_motion(const MotionParams& p, int num_sms, cudaStream_t stream);
+
 // ---- device-side draw-list generation (drawlist.cu) ---------------------------------------------------------------
 cudaError_t launch_segment_scan(const vkv_DrawSegment* seg, uint32_t n, const vkv_Primitive* prims, uint32_t* offsets, uint32_t* overflow, cudaStream_t stream);
 cudaError_t launch_expand_segments(const vkv_DrawSegment* seg, uint32_t n, const uint32_t* offsets, vkv_MeshletDraw* draws, uint32_t capacity,
