@@ -142,3 +142,15 @@ def test_cuda_motion_vectors_equal_the_oracle(name):
     got = r.read_motion()
     r.close()
     assert np.array_equal(got, want), int((got != want).sum())
+
+
+def test_a_camera_at_rest_has_no_motion():
+    """prevViewProjection == viewProjection: both terms of line 38 are the same expression, the difference is exactly zero"""
+    scene = Scene.icosphere(12)
+    W, H = 200, 150
+    cam = Camera(W, H).look_at((0, 0, 3), (0, 0, 0))
+    cam.look_at((0, 0, 3), (0, 0, 0))
+    pc = scene.host_push_constants(cam)
+    tg = K.oracle_images(pc, W, H)
+    f, h = O.motion_vectors(pc, tg)
+    assert (f == 0).all() and (h & 0x7fff == 0).all() and (tg.ids_min != abi.VISBUFFER_CLEAR).sum() > 1000
