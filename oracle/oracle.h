@@ -13,6 +13,9 @@
  *       texture unit underneath lavapipe (Mesa 18.1.9 inside this image's Nsight Compute, driven without an X server through
  *       oracle/llvmpipe/fakex11.c): identical coverage and ids, identical footprints at every coordinate hiz_reduce samples; depth
  *       within ~1e-7.  llvmpipe's outputs are committed as tests/golden/llvmpipe.npz;
+ *   (1b) the reference's shader text executed AS GLSL by that Mesa's compiler (tests/test_llvmpipe_glsl.py): mesh-shader clip positions,
+ *       both determinants and gl_CullPrimitiveEXT BIT-IDENTICAL to orc_mesh_shader on BASELINE cfg 1-4, task-shader classes identical on
+ *       every MeshletDraw — the arithmetic policy below is exactly Mesa's lowering of the reference's GLSL;
  *   (2) the reference's own text, compiled as C++ against its glm by oracle/build_ref.sh into oracle/_ref/:
  *   - the whole per-draw decision of the task shader except the texture fetch: culling.h.glsl (isAabbInFrustum,
  *     getWorldSpaceAabbExtent, aabbPositions, projectAabb), visbuffer.task.glsl:50-52,56-61,64 — on every MeshletDraw of all
