@@ -213,6 +213,7 @@ int vkv_read_color(vkv_ctx*, uint32_t* host);                      /* W*H RGBA8 
  * Texel = half(x) | half(y) << 16. ------------------------------------------------------------------------------------------- */
 int vkv_motion_vectors(vkv_ctx*, const vkv_VisbufferPushConstants* pc);
 int vkv_read_motion(vkv_ctx*, uint16_t* host);                     /* W*H*2 halves */
+uint64_t vkv_motion_ptr(vkv_ctx*);                                 /* device address of the W*H texels for a GPU-resident consumer; 0 before the first pass */
 
 /* ---- multi-GPU: one process (and one context) per GPU; a single huge view is sharded by MeshletDraw range and the
  * per-GPU 64-bit visbuffers are min-merged over NVLink peer memory (BASELINE config 5).  The reference is

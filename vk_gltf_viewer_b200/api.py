@@ -49,7 +49,7 @@ class Stats(C.Structure):
 EXPORTS = [
     "vkv_create", "vkv_resize", "vkv_destroy", "vkv_last_error", "vkv_set_stream", "vkv_sync",
     "vkv_upload", "vkv_update", "vkv_free",
-    "vkv_motion_vectors", "vkv_read_motion", "vkv_frame", "vkv_frame_submit", "vkv_frame_wait", "vkv_update_staged", "vkv_clear", "vkv_cull", "vkv_raster", "vkv_hiz", "vkv_raster_list",
+    "vkv_motion_vectors", "vkv_read_motion", "vkv_motion_ptr", "vkv_frame", "vkv_frame_submit", "vkv_frame_wait", "vkv_update_staged", "vkv_clear", "vkv_cull", "vkv_raster", "vkv_hiz", "vkv_raster_list",
     "vkv_read_visbuffer64", "vkv_read_ids", "vkv_read_depth", "vkv_read_hiz_mip", "vkv_read_pyramid", "vkv_write_pyramid",
     "vkv_read_visible", "vkv_read_status", "vkv_pyramid_floats",
     "vkv_event_record", "vkv_event_elapsed", "vkv_flush_l2", "vkv_visbuffer64_ptr",

@@ -1241,6 +1241,7 @@ int vkv_flush_l2(vkv_ctx* c, size_t bytes) {
 }
 
 uint64_t vkv_visbuffer64_ptr(vkv_ctx* c) { return c ? (uint64_t)(uintptr_t)c->vis : 0; }
+uint64_t vkv_motion_ptr(vkv_ctx* c) { return c ? (uint64_t)(uintptr_t)c->motion : 0; }
 
 int vkv_alloc(vkv_ctx* c, size_t bytes, uint64_t* dev_addr) {
 	if (!c || !dev_addr) return c ? fail(c, VKV_ERR_INVALID, "vkv_alloc: NULL argument") : VKV_ERR_INVALID;
