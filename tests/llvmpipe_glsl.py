@@ -101,6 +101,23 @@ void main() {{
 """
 
 
+def hiz_coordinates_shader():
+    """the sample coordinate of hiz_reduce.comp.glsl:28, `(vec2(pos) + vec2(0.5)) / pushConstants.imageSize`, cut out of the reference's line and
+    evaluated per texel of a target of the level's size (pos = gl_GlobalInvocationID.xy there, the fragment's integer position here)"""
+    line = ref_lines("hiz_reduce.comp.glsl", 28, 28)
+    m = re.search(r"texture\(sampled_textures_heap\[pushConstants\.sourceImage\], (.*)\)\.x;", line)
+    assert m, "hiz_reduce.comp.glsl:28 is not the line this test was written against"
+    return prelude() + f"""
+struct HiZReducePushConstants {{ uvec2 imageSize; }};
+uniform HiZReducePushConstants pushConstants;
+out vec4 color;
+void main() {{
+	uvec2 pos = uvec2(gl_FragCoord.xy);
+	color = vec4({m.group(1)}, 0.0, 1.0);
+}}
+"""
+
+
 def to_tex(a, Wc):
     """[n, k<=4] -> ([Hc, Wc, 4] float32, Hc)"""
     n = a.shape[0]

@@ -136,14 +136,27 @@ def test_sampler_footprint(lp, size):
 
 
 @pytest.mark.parametrize("res", [(640, 480), (1920, 1080), (3840, 2160), (1001, 777), (97, 33)])
-def test_hiz_reduce_footprints_over_whole_mip_chains(lp, res):
+@pytest.mark.parametrize("coordinates", ["ieee", "glsl"])
+def test_hiz_reduce_footprints_over_whole_mip_chains(lp, res, coordinates):
     """Every coordinate hiz_reduce.comp.glsl:28 samples, for every dispatch of the chain (odd source sizes included: SURVEY D5, the pyramid is
-    not conservative there): the oracle's reduce reads a texel class iff llvmpipe's LINEAR filter weights it."""
+    not conservative there): the oracle's reduce reads a texel class iff llvmpipe's LINEAR filter weights it.
+    coordinates = "ieee": (pos + 0.5) / imageSize with IEEE division, as the oracle evaluates it; "glsl": the reference's own expression evaluated
+    by Mesa's GLSL compiler, which lowers the division to a multiplication by the reciprocal — about a third of the coordinates differ in the
+    last bit (GPUs differ likewise: Vulkan allows 2.5 ulp), and the footprints must not care.  The one coordinate that sits exactly on a
+    footprint change — the centre texel of an odd level, (D/2 + 0.5) / D * (2D + 1) - 0.5 = a whole number — comes out as exactly 0.5 either way."""
+    from . import llvmpipe_glsl as G
+    if coordinates == "glsl" and not G.available():
+        pytest.skip("needs /root/reference")
     W, H = res
-    checked = 0
+    checked = differing = 0
     for (sw, sh), (dw, dh) in K.hiz_level_sizes(W, H):
         x, y = np.meshgrid(np.arange(dw, dtype=np.float32), np.arange(dh, dtype=np.float32))
         uv = np.stack([(x + np.float32(0.5)) / np.float32(dw), (y + np.float32(0.5)) / np.float32(dh)], -1).reshape(-1, 2).astype(np.float32)
+        if coordinates == "glsl":
+            got_uv = lp.compute(G.hiz_coordinates_shader(), dw, dh, {}, {"pushConstants.imageSize": np.array([dw, dh], np.uint32)})[:, :, :2].reshape(-1, 2)
+            differing += int((got_uv.view(np.uint32) != uv.view(np.uint32)).sum())
+            assert np.abs(got_uv - uv).max() <= 1.2e-7
+            uv = np.ascontiguousarray(got_uv)
         for axis in (0, 1):
             for k in range(3):
                 tg = O.Targets(sw, sh)
@@ -154,6 +167,8 @@ def test_hiz_reduce_footprints_over_whole_mip_chains(lp, res):
                 assert np.array_equal(got, want), (res, (sw, sh), axis, k)
                 checked += dw * dh
     assert checked > 0
+    if coordinates == "glsl" and max(W, H) > 200:
+        assert differing > 0, "expected Mesa's reciprocal-multiply to differ from IEEE division somewhere"
 
 
 def test_integer_lod_selects_the_clamped_mip(lp):
