@@ -42,6 +42,7 @@ def test_headless_example_rejects_unknown_arguments():
 
 
 @pytest.mark.gpu
+@pytest.mark.late   # ran green on the B200 before the decoder hook was added to the example; the present binary has not run on a device
 def test_headless_example_renders(tmp_path):
     _build()
     out = tmp_path / "frame.ppm"
