@@ -36,6 +36,8 @@ $(PKG)/libvkv.so: $(CU_OBJS)
 $(PKG)/libvkv_host.so: $(HOST_SRCS) $(HOST_HDRS)
 	$(CXX) $(CXXFLAGS) -shared -o $@ $(HOST_SRCS) -Iinclude
 
+# -mavx2, not -march=native: the library is built here and travels to the GPU box, whose host CPU is a different model — an
+# instruction set both have, instead of a SIGILL there; -ffp-contract=off stays (it is the parity source)
 oracle/liboracle.so: oracle/oracle.cpp oracle/meshopt_decode.cpp oracle/meshlet_build.cpp oracle/accessors.cpp oracle/oracle.h include/vkv_abi.h
 	$(CXX) $(CXXFLAGS) -O3 -mavx2 -shared -o $@ oracle/oracle.cpp oracle/meshopt_decode.cpp oracle/meshlet_build.cpp oracle/accessors.cpp
 
