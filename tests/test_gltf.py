@@ -354,3 +354,35 @@ def test_meshopt_compressed_asset_decoded_on_the_device(meshopt_ref):
         SC.set_meshopt_decoder(None)
         r.close()
     same_scene(got, Scene.from_glb(plain))
+
+
+def test_device_decoder_glue_with_a_stand_in_for_the_device(meshopt_ref):
+    """api.Renderer.meshopt_decoder()'s closure (view record, source slack, result slicing, return code) with Renderer.meshopt_decode replaced by
+    the reference's meshoptimizer: what the GPU test exercises with the real device decoder, minus the device"""
+    from tests import meshopt_lib as M
+    from vk_gltf_viewer_b200 import abi, api, scene as SC
+    comp, plain = _compressed_and_plain_assets(M)
+    kinds = {0: "vertex", 1: "index", 2: "sequence"}
+    seen = []
+
+    class Stand(api.Renderer):
+        def __init__(self):   # no context: only meshopt_decoder() / meshopt_decode() are used
+            pass
+
+        def meshopt_decode(self, src, views, dst_bytes):
+            assert views.dtype == abi.MESHOPT_VIEW_DTYPE and len(views) == 1 and dst_bytes % 16 == 0
+            v = views[0]
+            assert int(v["src_offset"]) == 0 and int(v["dst_offset"]) == 0 and src.size == int(v["src_size"]) + 32 and not src[int(v["src_size"]):].any()
+            rc, out = M.ref_decode(kinds[int(v["mode"])], int(v["count"]), int(v["stride"]), src[:int(v["src_size"])], fid=int(v["filter"]))
+            full = np.zeros(dst_bytes, np.uint8)
+            full[:out.size] = out
+            seen.append(int(v["mode"]))
+            return full, np.array([rc], np.int32)
+
+    SC.set_meshopt_decoder(Stand().meshopt_decoder())
+    try:
+        got = Scene.from_glb(comp)
+    finally:
+        SC.set_meshopt_decoder(None)
+    same_scene(got, Scene.from_glb(plain))
+    assert sorted(set(seen)) == [0, 1, 2] and len(seen) == 6        # three ATTRIBUTES, two TRIANGLES, one INDICES view, each decoded once
