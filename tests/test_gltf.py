@@ -386,3 +386,35 @@ def test_device_decoder_glue_with_a_stand_in_for_the_device(meshopt_ref):
         SC.set_meshopt_decoder(None)
     same_scene(got, Scene.from_glb(plain))
     assert sorted(set(seen)) == [0, 1, 2] and len(seen) == 6        # three ATTRIBUTES, two TRIANGLES, one INDICES view, each decoded once
+
+
+@pytest.mark.parametrize("field,value,needle", [
+    ("bufferViews.0.byteOffset", -1, "negative"), ("bufferViews.0.byteOffset", 2**63, "beyond"), ("bufferViews.0.byteLength", 1e300, "beyond"),
+    ("accessors.0.byteOffset", -8, "negative"), ("accessors.0.count", 2**62, "beyond"), ("bufferViews.0.byteStride", 4096, "byteStride"),
+    ("scene", -1, "scene index"), ("scenes.0.nodes.0", -3, "out of range"), ("scenes.0.nodes.0", 1e30, "out of range"),
+])
+def test_offsets_that_would_wrap_the_bounds_arithmetic_are_refused(field, value, needle):
+    """found by tools/fuzz_gltf.py under ASan: byteOffset -1 became 2^64 - 1, `offset + length` wrapped past the check and the first vertex was
+    read one byte before the buffer.  Sizes and offsets are now non-negative and below 2^40, and every bound is checked without an addition
+    that can wrap."""
+    import json, struct
+    w = GlbWriter()
+    pos, idx = S.grid_mesh(4, 4, lambda u, v: (u, v, 0 * u))
+    w.node(w.mesh([{"position": w.positions(pos), "indices": w.indices(idx.astype(np.uint16))}]))
+    glb = w.glb()
+    jlen = struct.unpack_from("<I", glb, 12)[0]
+    doc = json.loads(glb[20:20 + jlen])
+    ref = doc
+    keys = field.split(".")
+    for k in keys[:-1]:
+        ref = ref[int(k)] if k.isdigit() else ref[k]
+    last = keys[-1]
+    if last.isdigit():
+        ref[int(last)] = value
+    else:
+        ref[last] = value
+    js = json.dumps(doc, separators=(",", ":")).encode(); js += b" " * (-len(js) % 4)
+    rest = glb[20 + jlen:]
+    bad = struct.pack("<III", 0x46546C67, 2, 20 + len(js) + len(rest)) + struct.pack("<II", len(js), 0x4E4F534A) + js + rest
+    with pytest.raises(ValueError, match=needle):
+        Scene.from_glb(bad)

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Mutation fuzzer for the glTF reader (host/gltf.cpp: the one place on this path that parses untrusted bytes on the host).
 
-    python tools/fuzz_gltf.py [iterations] [seed] [compressed]
+    python tools/fuzz_gltf.py [iterations] [seed] [compressed | gltf]
 
 Builds a GLB with every feature the reader handles (float / quantised / strided / sparse accessors, u8 / u16 / u32 / generated indices,
 matrix and TRS nodes, several scenes' worth of hierarchy), then mutates JSON text and binary chunk (bit flips, number replacement, token
@@ -9,7 +9,7 @@ deletion / duplication, truncation, length-field edits) and feeds every mutant t
 accept it; it may not crash, hang or read out of bounds.  Run it against a sanitizer build for the last part:
 
     (in a scratch copy of the tree)
-    g++ -std=c++17 -fPIC -fsanitize=address,undefined -g -O1 -shared -o vk_gltf_viewer_b200/libvkv_host.so vk_gltf_viewer_b200/host/*.cpp -Iinclude
+    g++ -std=c++17 -fPIC -fsanitize=address,undefined,float-cast-overflow -g -O1 -shared -o vk_gltf_viewer_b200/libvkv_host.so vk_gltf_viewer_b200/host/*.cpp -Iinclude
     LD_PRELOAD="$(g++ -print-file-name=libasan.so) $(g++ -print-file-name=libubsan.so)" ASAN_OPTIONS=detect_leaks=0 python tools/fuzz_gltf.py 20000
 
 Every ACCEPTED mutant is then checked the way the device kernels trust it (the trust boundary of include/vkv.h): every MeshletDraw names an
@@ -32,7 +32,7 @@ from tests.gltf_writer import GlbWriter  # noqa: E402
 from tests import scenes as S  # noqa: E402
 
 
-def base_glb():
+def rebuild_writer():
     rng = np.random.default_rng(1)
     w = GlbWriter()
     m0 = w.material((0.8, 0.2, 0.1, 1.0), double_sided=False)
@@ -48,7 +48,11 @@ def base_glb():
     n1 = w.node(m[0], parent=root, rotation=(0, 0.6, 0, 0.8), scale=(2, 0.5, 1.5))
     w.node(m[1], parent=n1, translation=(0.5, 0, -1))
     w.node(m[0], scale=(1, 1, -1))
-    return w.glb()
+    return w
+
+
+def base_glb():
+    return rebuild_writer().glb()
 
 
 def split(glb):
@@ -151,7 +155,43 @@ def main():
     check(Scene.from_glb(glb))
     rng = np.random.default_rng(seed)
     accepted, reasons = 0, {}
+    as_file = len(sys.argv) > 3 and sys.argv[3] == "gltf"
+    if as_file:
+        # the .gltf route (vkvh_scene_load_file): a JSON document with a base64 data uri and an external .bin beside it, mutated as text
+        import tempfile
+        from tests.gltf_writer import GlbWriter as _W  # noqa: F401
+        tmp = tempfile.mkdtemp(prefix="vkv_fuzz_")
+        w = rebuild_writer()
+        doc_data, _ = w.gltf(None)                       # buffers[0] as a data uri
+        doc_file, bn = w.gltf("geometry.bin")            # buffers[0] as an external file
+        open(os.path.join(tmp, "geometry.bin"), "wb").write(bn)
+        bases = [doc_data, doc_file]
     for i in range(iters):
+        if as_file:
+            base = bytearray(bases[i % 2])
+            for _ in range(int(rng.integers(1, 4))):
+                k = int(rng.integers(0, 4))
+                if k == 0:
+                    ms = list(NUM.finditer(bytes(base)))
+                    m_ = ms[int(rng.integers(len(ms)))]
+                    base[m_.start():m_.end()] = INTERESTING[int(rng.integers(len(INTERESTING)))]
+                elif k == 1:
+                    base[int(rng.integers(len(base)))] = int(rng.integers(32, 127))
+                elif k == 2:
+                    a = int(rng.integers(len(base) - 1)); del base[a:min(len(base), a + int(rng.integers(1, 40)))]
+                else:
+                    a = int(rng.integers(len(base) - 1)); base[a:a] = base[a:min(len(base), a + int(rng.integers(1, 60)))]
+            path = os.path.join(tmp, "mutant.gltf")
+            open(path, "wb").write(bytes(base))
+            try:
+                scene = Scene.from_file(path)
+            except ValueError as e:
+                key = re.sub(r"\d+", "N", str(e))[:60]
+                reasons[key] = reasons.get(key, 0) + 1
+                continue
+            accepted += 1
+            check(scene)
+            continue
         m = mutate(rng, js, rest)
         try:
             scene = Scene.from_glb(m)

@@ -432,7 +432,10 @@ void vkvh_meshlet_bounds(const unsigned* meshlet_vertices, const unsigned char* 
 	const float e0 = fabsf(out->cone_axis_s8[0] / 127.f - out->cone_axis[0]);
 	const float e1 = fabsf(out->cone_axis_s8[1] / 127.f - out->cone_axis[1]);
 	const float e2 = fabsf(out->cone_axis_s8[2] / 127.f - out->cone_axis[2]);
-	const int cut = int(127 * (out->cone_cutoff + e0 + e1 + e2) + 1);
+	// (meshoptimizer converts this float unconditionally, clusterizer.cpp:858; positions with NaN / inf — a damaged asset — make it NaN, whose
+	// conversion is undefined: those meshlets get the "never reject" cutoff)
+	const float cutf = 127 * (out->cone_cutoff + e0 + e1 + e2) + 1;
+	const int cut = (cutf < 128.f) ? int(cutf) : 128;
 	out->cone_cutoff_s8 = (cut > 127) ? 127 : (signed char)cut;
 }
 

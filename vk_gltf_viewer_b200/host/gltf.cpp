@@ -52,7 +52,12 @@ struct Json {
 	}
 	bool has(const char* key) const { return get(key) != nullptr; }
 	double number(const char* key, double dflt) const { const Json* j = get(key); return (j && j->kind == Number) ? j->num : dflt; }
-	long long integer(const char* key, long long dflt) const { const Json* j = get(key); return (j && j->kind == Number) ? (long long)j->num : dflt; }
+	long long integer(const char* key, long long dflt) const {
+		const Json* j = get(key);
+		if (!j || j->kind != Number) return dflt;
+		if (!(j->num > -4.0e18)) return (long long)-4000000000000000000LL; // also NaN
+		return j->num < 4.0e18 ? (long long)j->num : 4000000000000000000LL;
+	}
 	bool boolean(const char* key, bool dflt) const { const Json* j = get(key); return (j && j->kind == Bool) ? j->b : dflt; }
 	size_t size() const { return kind == Array ? arr.size() : 0; }
 };
@@ -138,6 +143,17 @@ private:
 
 struct Fail { std::string msg; };
 [[noreturn]] void fail(const std::string& m) { throw Fail{m}; }
+
+// an array element used as an index (children, scene roots): anything that is not a small non-negative number is "out of range"
+size_t index_of(const Json& j) { return (j.kind == Json::Number && j.num >= 0.0 && j.num < 1.0e12) ? (size_t)j.num : (size_t)-1; }
+
+// a byte offset / length / element count from the document: never negative, and small enough (2^40) that the bounds arithmetic below
+// (offset + count * stride with stride <= 2^10) cannot wrap
+size_t usize(const Json& j, const char* key) {
+	const long long v = j.integer(key, 0);
+	if (v < 0 || v > (1LL << 40)) fail(std::string(key) + " is negative or beyond 2^40");
+	return (size_t)v;
+}
 
 std::vector<uint8_t> base64(const std::string& s, size_t from) {
 	std::vector<uint8_t> out;
@@ -232,6 +248,11 @@ struct Loader {
 	std::string baseDir;                    // folder of the asset file (assetPath.parent_path(), assets.cpp:548,558); empty = no file access
 	bool haveDir = false;
 
+	static size_t view_stride(const Json& bv) { // glTF 2.0: 4 .. 252; anything up to 2^10 is taken, more is refused (it would let offsets wrap)
+		const size_t st = usize(bv, "byteStride");
+		if (st > 1024) fail("bufferView.byteStride beyond 1024");
+		return st;
+	}
 	View bufferView(long long idx) {
 		const Json* bvs = doc.get("bufferViews");
 		if (!bvs || idx < 0 || (size_t)idx >= bvs->size()) fail("bufferView index out of range");
@@ -246,9 +267,9 @@ struct Loader {
 					     "vkv_meshopt_plan_create / vkv_meshopt_run takes the compressed views as they are)");
 				const long long cb = mc->integer("buffer", -1);
 				if (cb < 0 || (size_t)cb >= buffers.size() || !buffers[(size_t)cb].data) fail("EXT_meshopt_compression.buffer out of range or without data");
-				const size_t coff = (size_t)mc->integer("byteOffset", 0), clen = (size_t)mc->integer("byteLength", 0);
+				const size_t coff = usize(*mc, "byteOffset"), clen = usize(*mc, "byteLength");
 				if (coff > buffers[(size_t)cb].size || clen > buffers[(size_t)cb].size - coff) fail("EXT_meshopt_compression view exceeds its buffer");
-				const size_t stride = (size_t)mc->integer("byteStride", 0), count = (size_t)mc->integer("count", 0);
+				const size_t stride = usize(*mc, "byteStride"), count = usize(*mc, "count");
 				const Json* jm = mc->get("mode"); const Json* jf = mc->get("filter");
 				const std::string mode = jm && jm->kind == Json::String ? jm->str : "", filter = jf && jf->kind == Json::String ? jf->str : "NONE";
 				const int m = mode == "ATTRIBUTES" ? 0 : mode == "TRIANGLES" ? 1 : mode == "INDICES" ? 2 : -1;
@@ -268,16 +289,16 @@ struct Loader {
 				                                owned.back().data());
 				// (the reference ignores the decoders' return codes, assets.cpp:149-150; a stream that does not decode is refused here)
 				if (rc != 0) fail("bufferView " + std::to_string(idx) + ": EXT_meshopt_compression stream did not decode (code " + std::to_string(rc) + ")");
-				const View v{owned.back().data(), count * stride, (size_t)bv.integer("byteStride", 0)};
+				const View v{owned.back().data(), count * stride, view_stride(bv)};
 				decoded.emplace(idx, v);
 				return v;
 			}
 		const long long b = bv.integer("buffer", -1);
 		if (b < 0 || (size_t)b >= buffers.size()) fail("bufferView.buffer out of range");
 		if (!buffers[(size_t)b].data) fail("bufferView reads a fallback buffer (EXT_meshopt_compression placeholder without bytes)");
-		const size_t off = (size_t)bv.integer("byteOffset", 0), len = (size_t)bv.integer("byteLength", 0);
-		if (off + len > buffers[(size_t)b].size) fail("bufferView exceeds its buffer");
-		return View{buffers[(size_t)b].data + off, len, (size_t)bv.integer("byteStride", 0)};
+		const size_t off = usize(bv, "byteOffset"), len = usize(bv, "byteLength");
+		if (off > buffers[(size_t)b].size || len > buffers[(size_t)b].size - off) fail("bufferView exceeds its buffer");
+		return View{buffers[(size_t)b].data + off, len, view_stride(bv)};
 	}
 	Acc accessor(long long idx) {
 		const Json* as = doc.get("accessors");
@@ -287,8 +308,8 @@ struct Loader {
 		if (!a.has("bufferView") && !sparse) fail("accessor without bufferView");
 		Acc r;
 		r.json = &a;
-		r.offset = (size_t)a.integer("byteOffset", 0);
-		r.count = (size_t)a.integer("count", 0);
+		r.offset = usize(a, "byteOffset");
+		r.count = usize(a, "count");
 		r.ctype = (int)a.integer("componentType", 0);
 		r.normalized = a.boolean("normalized", false);
 		const Json* ty = a.get("type");
@@ -300,20 +321,20 @@ struct Loader {
 		if (a.has("bufferView")) {
 			r.view = bufferView(a.integer("bufferView", -1));
 			const size_t stride = r.view.stride ? r.view.stride : elem;
-			if (r.count && r.offset + (r.count - 1) * stride + elem > r.view.size) fail("accessor exceeds its bufferView");
+			if (r.count && (r.offset > r.view.size || (r.count - 1) * stride + elem > r.view.size - r.offset)) fail("accessor exceeds its bufferView");
 		} else r.view = View{nullptr, 0, 0};
 		if (sparse) {
 			// glTF 2.0 §3.6.2.3 as fastgltf's iterateAccessor reads it (tools.hpp: the sparse index / value pairs override the elements of
 			// the base view, or of zeros when the accessor has no bufferView): densified here into a tightly packed copy
-			const size_t n = (size_t)sparse->integer("count", 0);
+			const size_t n = usize(*sparse, "count");
 			const Json* si = sparse->get("indices"); const Json* sv = sparse->get("values");
 			if (!si || !sv) fail("sparse accessor without indices / values");
 			const int ict = (int)si->integer("componentType", 0);
 			const size_t is = ctype_size(ict);
 			if (ict != 5121 && ict != 5123 && ict != 5125) fail("sparse accessor: indices must be u8 / u16 / u32");
 			const View iv = bufferView(si->integer("bufferView", -1)), vv = bufferView(sv->integer("bufferView", -1));
-			const size_t io = (size_t)si->integer("byteOffset", 0), vo = (size_t)sv->integer("byteOffset", 0);
-			if (n > r.count || io + n * is > iv.size || vo + n * elem > vv.size) fail("sparse accessor exceeds its bufferViews");
+			const size_t io = usize(*si, "byteOffset"), vo = usize(*sv, "byteOffset");
+			if (n > r.count || io > iv.size || n * is > iv.size - io || vo > vv.size || n * elem > vv.size - vo) fail("sparse accessor exceeds its bufferViews");
 			owned.emplace_back(r.count * elem, (uint8_t)0);
 			std::vector<uint8_t>& dense = owned.back();
 			if (r.view.data) {
@@ -350,7 +371,7 @@ static vkvh_scene* load_document(vkvh::Loader& L) {
 			for (size_t i = 0; i < bufs->size(); ++i) {
 				const Json& b = bufs->arr[i];
 				const Json* uri = b.get("uri");
-				const size_t byteLength = (size_t)b.integer("byteLength", 0);
+				const size_t byteLength = usize(b, "byteLength");
 				const Json* bext = b.get("extensions");
 				const Json* bmc = bext ? bext->get("EXT_meshopt_compression") : nullptr;
 				if (!uri && bmc && bmc->boolean("fallback", false)) {
@@ -519,14 +540,15 @@ static vkvh_scene* load_document(vkvh::Loader& L) {
 			                                             mesh >= 0 ? (uint32_t)meshPrims[(size_t)mesh].size() : 0u, mesh >= 0 ? 1 : 0, t, r, sc);
 			if (self < 0) fail("invalid node");
 			if (const Json* ch = n.get("children"))
-				for (const Json& c : ch->arr) addNode((size_t)c.num, self, depth + 1);
+				for (const Json& c : ch->arr) addNode(index_of(c), self, depth + 1);
 		};
 		const Json* scenes = L.doc.get("scenes");
 		if (scenes && scenes->size()) {
-			const size_t si = (size_t)L.doc.integer("scene", 0);
-			if (si >= scenes->size()) fail("scene index out of range");
+			const long long sceneIndex = L.doc.integer("scene", 0);
+			if (sceneIndex < 0 || (size_t)sceneIndex >= scenes->size()) fail("scene index out of range");
+			const size_t si = (size_t)sceneIndex;
 			if (const Json* roots = scenes->arr[si].get("nodes"))
-				for (const Json& rn : roots->arr) addNode((size_t)rn.num, -1, 0);
+				for (const Json& rn : roots->arr) addNode(index_of(rn), -1, 0);
 		}
 		if (vkvh_scene_finalize(s) != 0) fail("the draw list exceeds 2^25 MeshletDraws (visbuffer.h.glsl:15-17)");
 		return s;
