@@ -418,3 +418,14 @@ def test_offsets_that_would_wrap_the_bounds_arithmetic_are_refused(field, value,
     bad = struct.pack("<III", 0x46546C67, 2, 20 + len(js) + len(rest)) + struct.pack("<II", len(js), 0x4E4F534A) + js + rest
     with pytest.raises(ValueError, match=needle):
         Scene.from_glb(bad)
+
+
+def test_a_node_with_two_parents_is_refused_instead_of_walked_exponentially():
+    import json, struct, time
+    nodes = [{"children": [i + 1, i + 1]} for i in range(60)] + [{}]
+    js = json.dumps({"asset": {"version": "2.0"}, "nodes": nodes, "scenes": [{"nodes": [0]}]}).encode()
+    js += b" " * (-len(js) % 4)
+    t = time.time()
+    with pytest.raises(ValueError, match="more than one parent"):
+        Scene.from_glb(struct.pack("<III", 0x46546C67, 2, 20 + len(js)) + struct.pack("<II", len(js), 0x4E4F534A) + js)
+    assert time.time() - t < 1.0

@@ -520,8 +520,11 @@ static vkvh_scene* load_document(vkvh::Loader& L) {
 		// nodes (world.cpp:187-228): TRS as given, matrices decomposed (Options::DecomposeNodeMatrices); scene roots in order
 		const Json* nodes = L.doc.get("nodes");
 		const size_t nNodes = nodes ? nodes->size() : 0;
+		std::vector<char> placed(nNodes, 0); // glTF 2.0 §3.5.2: the hierarchy is a strict tree — a node reached twice would make the walk exponential
 		std::function<void(size_t, int32_t, int)> addNode = [&](size_t ni, int32_t parent, int depth) {
 			if (ni >= nNodes || depth > 256) fail("node index out of range or node hierarchy too deep / cyclic");
+			if (placed[ni]) fail("node " + std::to_string(ni) + " has more than one parent (the node hierarchy must be a tree)");
+			placed[ni] = 1;
 			const Json& n = nodes->arr[ni];
 			float t[3] = {0, 0, 0}, r[4] = {0, 0, 0, 1}, sc[3] = {1, 1, 1};
 			if (const Json* m = n.get("matrix")) {
