@@ -335,6 +335,8 @@ struct Loader {
 			const View iv = bufferView(si->integer("bufferView", -1)), vv = bufferView(sv->integer("bufferView", -1));
 			const size_t io = usize(*si, "byteOffset"), vo = usize(*sv, "byteOffset");
 			if (n > r.count || io > iv.size || n * is > iv.size - io || vo > vv.size || n * elem > vv.size - vo) fail("sparse accessor exceeds its bufferViews");
+			// (an accessor WITH a bufferView is bounded by the bytes of the file; one made of zeros only is bounded here)
+			if (!r.view.data && r.count * elem > ((size_t)1 << 30)) fail("sparse accessor without a bufferView beyond 1 GiB");
 			owned.emplace_back(r.count * elem, (uint8_t)0);
 			std::vector<uint8_t>& dense = owned.back();
 			if (r.view.data) {
