@@ -299,3 +299,12 @@ def test_draw_limit_is_enforced():
     lib_counts = Scene.lattice(2, 1, 2, 8).counts()
     assert lib_counts.draws == lib_counts.meshlets_unique * 4 and lib_counts.transforms == 4
     assert abi.VISBUFFER_CLEAR == 0xFFFFFFFF
+
+
+def test_builtin_clusterizer_against_the_reference_on_random_meshes(meshopt_ref):
+    """tools/diff_meshlet_builder.py (random soups, shuffled grids, degenerate / duplicated triangles, coincident positions, tiny and huge
+    coordinates, random limits and cone weights): byte-identical partitions and bounds; a short run here, 1 650 cases in the tool's docstring"""
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "tools", "diff_meshlet_builder.py"), "7", "25"], capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0 and "mismatches 0" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
