@@ -93,3 +93,12 @@ def test_scalar_filter_definition_vs_the_sse_build():
         d = np.abs(sse.view(dt).astype(np.int64) - orc.view(dt).astype(np.int64))
         assert d.max() <= (0 if c["filter"] == 3 else 1), f"{c['name']}: SSE build differs by {d.max()}"
     assert seen >= 8
+
+
+def test_oracle_decoder_against_the_reference_on_mutated_streams(meshopt_ref):
+    """tools/diff_meshopt_decode.py: same return code, same bytes, on reference-encoded streams with random damage (short run; 20 000 mutants
+    in the tool's docstring)"""
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "tools", "diff_meshopt_decode.py"), "5", "1500"], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and "mismatches 0" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
