@@ -107,6 +107,30 @@ def test_coverage_on_arbitrary_float_triangles(lp, seed, W, H, ntri, scale, insi
     assert r["depth_q50"] < 1e-4 and r["depth_q99"] < 2e-3
 
 
+@pytest.mark.parametrize("seed,ntri,spread", [(4, 60, 2.0), (5, 200, 2.0), (6, 1000, 3.0), (7, 3000, 4.0)])
+def test_random_triangles_around_the_eye(lp, seed, ntri, spread):
+    """View-space triangles scattered around the camera: a fifth of them cross the near plane, a sixth lie behind the eye (w <= 0), many leave
+    through the sides.  The oracle clips only against near / far / a guard band (and only the triangles that need it), llvmpipe against all six
+    planes: what is left on the screen must be the same — coverage identical, the same id up to a few pixels where surfaces intersect."""
+    from vk_gltf_viewer_b200.scene import Camera
+    rng = np.random.default_rng(seed)
+    W, H = 256, 192
+    P = np.zeros((ntri * 3, 3), np.float32)
+    c = rng.uniform(-spread, spread, (ntri, 1, 3))
+    c[:, :, 2] = rng.uniform(-6, 2, (ntri, 1))
+    P[:] = (c + rng.uniform(-1.5, 1.5, (ntri, 3, 3))).reshape(-1, 3)
+    s = K.soup_scene(P)
+    pc = s.host_push_constants(Camera(W, H).look_at((0, 0, 0), (0, 0, -1)))
+    V, I = K.oracle_triangles(s, pc)
+    w = V[:, 3].reshape(-1, 3)
+    assert ((w.min(1) <= 0.1) & (w.max(1) > 0.1)).sum() > ntri // 10 and (w.max(1) <= 0).sum() > ntri // 12
+    tg = K.oracle_images(pc, W, H)
+    r = K.compare(tg, *lp.raster(W, H, V, I))
+    print(f"\n{ntri} triangles around the eye: {r}")
+    assert r["coverage_differs"] == 0 and r["covered"] > 0.4 * W * H
+    assert r["id_differs"] <= 2 + 2e-4 * r["covered"]
+
+
 @pytest.mark.parametrize("name", sorted(K.SCENE_CASES))
 def test_scenes_match_llvmpipe(lp, name):
     """Meshes through the whole oracle path (mesh shader arithmetic -> trivial reject -> clip -> snap -> edge functions -> depth test) against
