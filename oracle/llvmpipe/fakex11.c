@@ -1,7 +1,7 @@
 /* fakex11.c — a display-less stand-in for libX11.so.6 / libXext.so.6, just enough for Mesa's xlib GLX state tracker to create a
  * context whose rendering goes to framebuffer objects.
  *
- * TEST INFRASTRUCTURE ONLY (oracle/README: llvmpipe pin).  This image ships a complete Mesa software rasteriser — llvmpipe, the
+ * TEST INFRASTRUCTURE ONLY (oracle/README.md).  This image ships a complete Mesa software rasteriser — llvmpipe, the
  * rasteriser underneath lavapipe — inside Nsight Compute (host/…/Mesa/libGL.so.1, Mesa 18.1.9, its xlib build), but neither libX11
  * nor an X server.  That libGL imports 30 Xlib symbols; they are all here.  No pixel ever reaches X: the caller renders into FBOs
  * and reads them back with glReadPixels, so the drawing entry points (XPutImage, XFillRectangle, …) are no-ops.
