@@ -5,8 +5,10 @@
 // The reference writes a motion vector per FRAGMENT while rasterising (overdraw included, one more 4-byte attachment in the ROP path);
 // with a visibility buffer the same image is one gather per PIXEL after the depth test has settled: id -> MeshletDraw -> Meshlet ->
 // three vertices, two node products, the arithmetic of motion_core.h (shared with the host build the CPU suite checks against the oracle).
-// One thread per pixel; neighbouring pixels mostly share a triangle, so the gathers are L1 / L2 hits and the pass is bound by its own
-// 8 B read + 4 B written per pixel.  Optional: nothing on the cull -> raster -> pyramid path depends on it.
+// One thread per pixel; neighbouring pixels mostly share a triangle, so the gathers are L1 / L2 hits.  Per covered pixel: 8 B read, 4 B
+// written, ~400 fp32 operations and six IEEE divisions (224 of the operations are the two node products, recomputed per pixel here; the
+// per-node table the rasteriser uses would remove them) — issue-bound, not yet measured.  Optional: nothing on the cull -> raster ->
+// pyramid path depends on it.
 #include "kernels.cuh"
 #include "motion_core.h"
 
