@@ -131,6 +131,26 @@ def test_random_triangles_around_the_eye(lp, seed, ntri, spread):
     assert r["id_differs"] <= 2 + 2e-4 * r["covered"]
 
 
+@pytest.mark.parametrize("seed,ntri", [(8, 40), (9, 150)])
+def test_random_triangles_around_the_far_plane(lp, seed, ntri):
+    """large triangles scattered around z = far (reverse-Z: depth 0): more than half of them cross the far plane, a fifth lie beyond it"""
+    from vk_gltf_viewer_b200.scene import Camera
+    rng = np.random.default_rng(seed)
+    W, H = 256, 192
+    P = np.zeros((ntri * 3, 3), np.float32)
+    c = rng.uniform(-700, 700, (ntri, 1, 3))
+    c[:, :, 2] = rng.uniform(-1300, -700, (ntri, 1))
+    P[:] = (c + rng.uniform(-400, 400, (ntri, 3, 3))).reshape(-1, 3)
+    s = K.soup_scene(P)
+    pc = s.host_push_constants(Camera(W, H).look_at((0, 0, 0), (0, 0, -1)))
+    V, I = K.oracle_triangles(s, pc)
+    z = V[:, 2].reshape(-1, 3)
+    assert ((z.min(1) < 0) & (z.max(1) > 0)).sum() > ntri // 3 and (z.max(1) < 0).sum() > ntri // 10
+    tg = K.oracle_images(pc, W, H)
+    r = K.compare(tg, *lp.raster(W, H, V, I))
+    assert r["coverage_differs"] == 0 and r["covered"] > 0.2 * W * H and r["id_differs"] <= 2 + 2e-4 * r["covered"]
+
+
 @pytest.mark.parametrize("name", sorted(K.SCENE_CASES))
 def test_scenes_match_llvmpipe(lp, name):
     """Meshes through the whole oracle path (mesh shader arithmetic -> trivial reject -> clip -> snap -> edge functions -> depth test) against
